@@ -1,0 +1,132 @@
+"""The CPU oracle (oracle/mirror_nerf_oracle.py) against vectors produced by the unmodified reference
+(tests/golden/make_golden.py).  Float tolerance 1e-6 abs / 1e-5 rel (bit-identical in the container that
+generated them; a different host CPU may pick different BLAS kernels); indices must be exact."""
+import numpy as np
+import pytest
+import torch
+
+from mirror_nerf_b200.synthetic import make_state_dict
+from oracle import mirror_nerf_oracle as O
+
+
+def T(x):
+    return torch.from_numpy(np.asarray(x))
+
+
+def close(a, b, name, rtol=1e-5, atol=1e-6):
+    a = a.detach() if isinstance(a, torch.Tensor) else T(a)
+    b = T(b)
+    assert a.shape == b.shape, (name, a.shape, b.shape)
+    assert torch.allclose(a, b, rtol=rtol, atol=atol), (name, float((a - b).abs().max()))
+
+
+@pytest.fixture(scope="module")
+def params():
+    return {"coarse": make_state_dict(0), "fine": make_state_dict(1)}
+
+
+def test_embedding(golden):
+    g = golden("field")
+    assert torch.equal(O.embed(T(g["xyz"]), 10), T(g["pe_xyz"]))
+    assert torch.equal(O.embed(T(g["dir"]), 4), T(g["pe_dir"]))
+
+
+def test_field_forward(golden, params):
+    g = golden("field")
+    x = torch.cat([T(g["xyz"]), T(g["pe_dir"])], 1)
+    with torch.no_grad():
+        o = O.field_forward(params["fine"], x.clone(), compute_normal=False, sigma_only=False)
+    for k in ("sigma", "geo_feat", "pred_normal", "rgb", "is_mirror"):
+        close(o[k], g["full_" + k], k)
+    with torch.no_grad():
+        o = O.field_forward(params["fine"], T(g["xyz"]).clone(), compute_normal=False, sigma_only=True)
+    assert set(o) == {"sigma", "geo_feat", "pred_normal"}
+    close(o["sigma"], g["sigonly_sigma"], "sigonly_sigma")
+    close(o["pred_normal"], g["sigonly_pred_normal"], "sigonly_pred_normal")
+    o = O.field_forward(params["fine"], x.clone(), compute_normal=True, sigma_only=False)
+    for k in ("sigma", "normal", "pred_normal", "rgb", "is_mirror"):
+        close(o[k], g["grad_" + k], "grad_" + k)
+
+
+def test_explicit_normal_chain_matches_autograd(golden, params):
+    g = golden("field")
+    xyz = T(g["xyz"])
+    with torch.no_grad():
+        gx = O.analytic_normal_explicit(params["fine"], xyz)
+    n = O.l2_normalize(-gx)
+    ref = T(g["grad_normal"])
+    # autograd and the explicit chain sum in different orders: compare directions
+    cos = (n * ref).sum(-1)
+    assert float(cos.min()) > 1 - 1e-4
+
+
+def test_sample_pdf(golden):
+    g = golden("sample_pdf")
+    bins, w = T(g["bins"]), T(g["weights"])
+    s, inds, cdf = O.sample_pdf(bins, w, 128, det=True, return_inds=True)
+    assert torch.equal(inds, T(g["inds_det"]))
+    close(cdf, g["cdf"], "cdf", atol=0, rtol=0)
+    close(s, g["det"], "det")
+    s, inds, _ = O.sample_pdf(bins, w, 128, det=False, u=T(g["u"]), return_inds=True)
+    assert torch.equal(inds, T(g["inds_rnd"]))
+    close(s, g["rnd"], "rnd")
+    assert bool((s[:, :] >= bins[:, :1]).all()) and bool((s <= bins[:, -1:]).all())
+
+
+def test_render_eval(golden, params):
+    g = golden("render_eval")
+    with torch.no_grad():
+        r = O.render_rays(params, T(g["rays"]), 64, False, 0, 0, 128, 32768, False, test_time=True,
+                          compute_normal=False)
+    assert set(r) == set(g) - {"rays"}
+    for k in r:
+        close(r[k], g[k], k)
+
+
+VARIANTS = {
+    "white_back": dict(args=(64, False, 0, 0, 128, 32768, True), kw=dict(test_time=True), fine=True),
+    "use_disp": dict(args=(64, True, 0, 0, 128, 32768, False), kw=dict(test_time=True), fine=True),
+    "coarse_only": dict(args=(64, False, 0, 0, 0, 32768, False), kw=dict(test_time=True), fine=False),
+    "one_field": dict(args=(64, False, 0, 0, 128, 32768, False),
+                      kw=dict(test_time=True, only_one_field=True, current_epoch=3), fine=False),
+    "train_nonormal": dict(args=(64, False, 0, 0, 128, 32768, False), kw=dict(test_time=False), fine=True),
+    "s32_i16": dict(args=(32, False, 0, 0, 16, 1000, False), kw=dict(test_time=True), fine=True),
+}
+
+
+@pytest.mark.parametrize("tag", sorted(VARIANTS))
+def test_render_variants(golden, params, tag):
+    g = golden("render_variants")
+    v = VARIANTS[tag]
+    p = params if v["fine"] else {"coarse": params["coarse"]}
+    with torch.no_grad():
+        r = O.render_rays(p, T(g["rays"]), *v["args"], compute_normal=False, **v["kw"])
+    want = {k.split("/", 1)[1]: a for k, a in g.items() if k.startswith(tag + "/")}
+    assert set(r) == set(want)
+    for k in r:
+        close(r[k], want[k], f"{tag}/{k}")
+
+
+def test_render_train_with_grads(golden):
+    g = golden("render_train")
+    params = {"coarse": make_state_dict(0), "fine": make_state_dict(1)}
+    for p in params.values():
+        for t in p.values():
+            t.requires_grad_(True)
+    rng = {k.split("/", 1)[1]: T(a) for k, a in g.items() if k.startswith("rng/")}
+    r = O.render_rays(params, T(g["rays"]), 64, False, 1.0, 1.0, 128, 32768, False, test_time=False,
+                      compute_normal=True, rng=rng)
+    want = {k.split("/", 1)[1]: a for k, a in g.items() if k.startswith("out/")}
+    assert set(r) == set(want)
+    for k in r:
+        close(r[k], want[k], k, rtol=1e-4, atol=1e-5)
+    loss = sum((r[f"rgb_{t}"] ** 2).sum() + r[f"mirror_mask_{t}"].sum() + 0.1 * r[f"normal_dif_{t}"].sum()
+               + 0.01 * (r[f"depth_{t}"]).sum() for t in ("coarse", "fine"))
+    loss.backward()
+    close(loss, g["loss"], "loss", rtol=1e-5)
+    for tag in ("coarse", "fine"):
+        for k, t in params[tag].items():
+            gr = t.grad.flatten()[::13] if t.grad.numel() > 4096 else t.grad
+            want_g = T(g[f"grad/{tag}/{k}"])
+            scale = float(T(g[f"gradnorm/{tag}/{k}"])) / max(1.0, t.grad.numel() ** 0.5)
+            assert float((gr - want_g).abs().max()) <= 1e-4 * max(scale, 1e-6) + 1e-3 * float(want_g.abs().max()) + 1e-9, k
