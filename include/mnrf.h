@@ -1,0 +1,209 @@
+/* mnrf.h -- C ABI of libmnrf.so, the B200 (sm_100a) renderer for Mirror-NeRF's render_rays hot path.
+ *
+ * This is the drop-in boundary.  Every entry point takes plain pointers and sizes (no torch types).
+ * Unless a parameter is documented as HOST, every pointer is a DEVICE pointer to fp32 data on the
+ * current CUDA device and `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ * All functions return 0 on success, non-zero on error; mnrf_last_error() gives the message.
+ * There is no CPU fallback anywhere: without a CUDA device every compute call fails.
+ *
+ * Reference interfaces replaced (R/ = zju3dv/Mirror-NeRF @ fc0d7911):
+ *   mnrf_field_*            R/models/mirror_nerf.py:41-99   (MirrorNeRF.__init__ : parameter set/layout)
+ *   mnrf_field_eval_*       R/models/mirror_nerf.py:101-212 (MirrorNeRF.forward + Embedding :6-38)
+ *   mnrf_coarse_z           R/models/rendering.py:271-300   (stratified coarse depths)
+ *   mnrf_composite          R/models/rendering.py:175-264   (inference(): quadrature / compositing)
+ *   mnrf_sample_pdf         R/models/rendering.py:7-51,312-326 (inverse-CDF resampling + sort-merge)
+ *   mnrf_searchsorted_right R/models/rendering.py:33        (torch.searchsorted(cdf,u,right=True))
+ *   mnrf_render_level       R/models/rendering.py:54-369    (render_rays, one level)
+ *   mnrf_render_level_host  same, HOST buffers in/out (what eval.py:1122-1138,735-736 does around it)
+ *   mnrf_reflect_rays / mnrf_compact_rays / mnrf_blend_reflection
+ *                           R/eval.py:295-320,515-548,676-697 and R/train.py:153-296 (Whitted bounce)
+ */
+#ifndef MNRF_H_
+#define MNRF_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MNRF_ABI_VERSION 1
+
+/* ---- field (MirrorNeRF MLP) ------------------------------------------------------------------ */
+
+/* Parameter tensors in MirrorNeRF.state_dict() order, each fp32, [out,in] row-major as nn.Linear stores
+ * them (R/models/mirror_nerf.py:60-99; key names in SURVEY.md section 5).  Index -> key:
+ *   2*i, 2*i+1   xyz_encoding_{i+1}.0.weight / .bias        i = 0..7   (256x63, 256x256 x3, 256x319, 256x256 x3)
+ *   16,17        xyz_encoding_final.weight / .bias          (256x256)
+ *   18,19        dir_encoding.0.weight / .bias              (128x283)
+ *   20,21        sigma.weight / .bias                       (1x256)
+ *   22,23        rgb.0.weight / .bias                       (3x128)
+ *   24..27       normal_net.0.weight/.bias, normal_net.1.weight/.bias   (128x256, 3x128)  or all NULL
+ *   28..31       is_mirror_net.0.weight/.bias, is_mirror_net.2.weight/.bias (128x256, 1x128) or all NULL
+ * Only the reference architecture D=8, W=256, skips=[4], N_emb_xyz=10, N_emb_dir=4 is supported. */
+#define MNRF_NUM_PARAM_TENSORS 32
+
+typedef struct mnrf_field mnrf_field; /* opaque: device-resident packed weights */
+
+/* Pack the 32 tensors (HOST array of DEVICE pointers) into the kernel formats.  Asynchronous on stream. */
+int mnrf_field_create(mnrf_field** out, const float* const* tensors, void* stream);
+/* Re-pack after the parameters changed (optimizer step).  Same tensor set (heads may not appear/disappear). */
+int mnrf_field_update(mnrf_field* f, const float* const* tensors, void* stream);
+void mnrf_field_destroy(mnrf_field* f);
+int mnrf_field_has_normal(const mnrf_field* f);
+int mnrf_field_has_mirror(const mnrf_field* f);
+
+/* which kernel evaluates the MLP */
+#define MNRF_IMPL_TC3 3   /* tcgen05, fp16 hi/lo split operands, 3 MMAs per product (fp32-grade; parity mode) */
+#define MNRF_IMPL_TC1 1   /* tcgen05, single fp16 pass (speed mode; does not meet the 1e-3 parity bar)      */
+#define MNRF_IMPL_FP32 0  /* CUDA-core fp32 verification kernel (slow; also the only one with analytic normals) */
+
+/* raw per-point record written by the field kernels: 8 floats */
+#define MNRF_RAW_STRIDE 8 /* [sigma, r, g, b, is_mirror, pred_nx, pred_ny, pred_nz] */
+
+/* Evaluate the field at the samples of a ray batch: point (r,s) = o_r + d_r * z[r,s]  (rendering.py:302,326).
+ *   rays (n_rays,8) = [o,d,near,far];  z (n_rays,S).
+ *   sigma_only != 0: only `sigma_out` (n_rays*S) is written (coarse pass at test time, rendering.py:139-150).
+ *   otherwise `raw` (n_rays*S, 8) is written; absent heads give 0.
+ *   normal_out: optional (n_rays*S,3) analytic normal  normalize(-d sigma/d xyz) (mirror_nerf.py:136-146);
+ *               only MNRF_IMPL_FP32 supports it. */
+int mnrf_field_eval_rays(const mnrf_field* f, int impl, const float* rays, const float* z, int n_rays, int S,
+                         int sigma_only, float* raw, float* sigma_out, float* normal_out, void* stream);
+
+/* MirrorNeRF.forward on a flat batch (mirror_nerf.py:101-187): x (B, 3+27) = [xyz | embedded dir]
+ * (or (B,3) when sigma_only).  Outputs (any may be NULL): sigma (B), rgb (B,3), is_mirror (B),
+ * pred_normal (B,3, l2-normalised), normal (B,3, analytic; FP32 impl only), geo_feat (B,256). */
+int mnrf_field_eval_points(const mnrf_field* f, int impl, const float* x, int B, int sigma_only,
+                           float* sigma, float* rgb, float* is_mirror, float* pred_normal, float* normal,
+                           float* geo_feat, void* stream);
+
+/* Embedding.forward (mirror_nerf.py:21-38): out (n, 3+6*n_freqs) = [x, sin(2^k x), cos(2^k x) ...]. */
+int mnrf_embed(const float* x, int n, int n_freqs, float* out, void* stream);
+
+/* ---- sampler ----------------------------------------------------------------------------------- */
+
+/* z_steps: the S values of torch.linspace(0,1,S) (taken from the host library so they are bit-identical,
+ * SURVEY.md appendix A).  perturb_u: (n,S) uniform draws or NULL when perturb == 0.  z_out (n,S).
+ * Arithmetic is done with separately rounded fp32 mul/add so it is bit-exact against the CPU reference. */
+int mnrf_coarse_z(const float* rays, int n, const float* z_steps, int S, int use_disp, float perturb,
+                  const float* perturb_u, float* z_out, void* stream);
+
+/* inds[i,j] = #{k : cdf[i,k] <= u[i,j]}  (int64, like torch).  u_stride = 0 broadcasts one row of u. */
+int mnrf_searchsorted_right(const float* cdf, int n, int n_cdf, const float* u, int n_u, int u_stride,
+                            int64_t* inds, void* stream);
+
+/* sample_fine_points (rendering.py:312-326): bins = mid-points of z_coarse, pdf from weights[:,1:-1]+1e-5,
+ * inverse CDF at u, then sort(cat(z_coarse, samples)).  u: (n_imp) if u_stride==0 else (n,n_imp).
+ * z_fine (n, S+n_imp).  Optional: samples (n,n_imp), inds (n,n_imp) int64, cdf (n,S-1).  S <= 256, S+n_imp <= 512. */
+int mnrf_sample_pdf(const float* z_coarse, const float* weights, int n, int S, int n_imp, const float* u,
+                    int u_stride, float* z_fine, float* samples, int64_t* inds, float* cdf, void* stream);
+
+/* sample_pdf(bins, weights, N_importance) exactly as rendering.py:7-51 takes it: bins (n, n_w+1), weights (n, n_w).
+ * samples (n,n_imp); optional inds (n,n_imp) int64 and cdf (n,n_w+1). */
+int mnrf_sample_pdf_bins(const float* bins, const float* weights, int n, int n_w, int n_imp, const float* u,
+                         int u_stride, float* samples, int64_t* inds, float* cdf, void* stream);
+
+/* ---- compositor -------------------------------------------------------------------------------- */
+
+typedef struct mnrf_composite_out {
+  float* weights;        /* (n,S)    */
+  float* opacity;        /* (n)      */
+  float* rgb;            /* (n,3)    or NULL */
+  float* depth;          /* (n)      or NULL */
+  float* mirror_mask;    /* (n)      or NULL */
+  float* pred_normal;    /* (n,S,3)  or NULL : per-sample predicted normals (copied out of raw)      */
+  float* surface_normal; /* (n,3)    or NULL : sum_s w * pred_normal (NOT re-normalised)              */
+  float* surface_normal_grad; /* (n,3) or NULL : sum_s w * analytic normal                            */
+  float* normal_dif;     /* (n)      or NULL : sum_s w * |n - n_pred|^2                               */
+  float* x_surface;      /* (n,3)    or NULL : o + d * depth (rendering.py:363-367)                   */
+} mnrf_composite_out;
+
+/* sigma (n,S) with stride `sigma_stride` floats between consecutive samples (1 for a sigma array, 8 for raw);
+ * raw (n,S,8) or NULL when only weights are wanted; normal (n,S,3) analytic normals or NULL;
+ * noise (n,S) standard-normal draws or NULL (noise_std is then ignored).  */
+int mnrf_composite(const float* rays, const float* z, const float* sigma, int sigma_stride, const float* raw,
+                   const float* normal, const float* noise, float noise_std, int n, int S, int white_back,
+                   const mnrf_composite_out* out, void* stream);
+
+/* ---- one render level (render_rays) -------------------------------------------------------------- */
+
+typedef struct mnrf_level_cfg {
+  int n_samples;     /* N_samples                          */
+  int n_importance;  /* N_importance (0 = coarse only)     */
+  int use_disp;
+  float perturb;
+  float noise_std;
+  int white_back;
+  int test_time;     /* coarse pass sigma-only when a fine field exists (rendering.py:139,208)          */
+  int compute_normal;/* analytic normals (forces MNRF_IMPL_FP32)                                        */
+  int rerun_coarse_on_fine; /* only_one_field after only_one_field_fine_epoch (rendering.py:328-348)    */
+  int impl;          /* MNRF_IMPL_*                                                                     */
+} mnrf_level_cfg;
+
+typedef struct mnrf_level_rng { /* explicit draws (device); NULL -> deterministic (perturb=0 / noise 0) */
+  const float* perturb_u;    /* (n, n_samples)              */
+  const float* noise_coarse; /* (n, n_samples)              */
+  const float* u_pdf;        /* (n, n_importance)           */
+  const float* noise_fine;   /* (n, n_samples+n_importance) */
+} mnrf_level_rng;
+
+typedef struct mnrf_level_out {
+  float* z_coarse;             /* (n,Sc) required */
+  mnrf_composite_out coarse;   /* weights+opacity required */
+  float* normal_coarse;        /* (n,Sc,3) analytic normals or NULL */
+  float* z_fine;               /* (n,Sc+Ni) required when a second pass runs */
+  mnrf_composite_out fine;
+  float* normal_fine;          /* (n,Sc+Ni,3) or NULL */
+} mnrf_level_out;
+
+/* bytes of scratch mnrf_render_level needs for n rays */
+int64_t mnrf_level_workspace_bytes(int n, const mnrf_level_cfg* cfg);
+
+/* fine may be NULL (coarse only, or only_one_field).  z_steps (n_samples), u_det (n_importance) are the
+ * torch.linspace tables (device).  All launches go to `stream`; nothing synchronises. */
+int mnrf_render_level(const mnrf_field* coarse, const mnrf_field* fine, const float* rays, int n,
+                      const mnrf_level_cfg* cfg, const mnrf_level_rng* rng, const float* z_steps,
+                      const float* u_det, void* workspace, int64_t workspace_bytes, const mnrf_level_out* out,
+                      void* stream);
+
+/* Same level with HOST buffers: rays_host (n,8) in; compact per-ray results out (each may be NULL):
+ * rgb (n,3), depth (n), opacity (n), mirror_mask (n), surface_normal (n,3), x_surface (n,3) of the last pass.
+ * Copies H2D/D2H on `stream` and synchronises it before returning.  z_steps/u_det are HOST here. */
+int mnrf_render_level_host(const mnrf_field* coarse, const mnrf_field* fine, const float* rays_host, int n,
+                           const mnrf_level_cfg* cfg, const float* z_steps_host, const float* u_det_host,
+                           float* rgb, float* depth, float* opacity, float* mirror_mask, float* surface_normal,
+                           float* x_surface, void* stream);
+
+/* ---- Whitted bounce helpers (callers of render_rays: eval.py:295-697, train.py:153-296) ---------- */
+
+/* mask (n) is thresholded IN PLACE (>0.5 -> 1, <0.5 -> 0, exactly 0.5 kept; eval.py:305-306).
+ * secondary (n,8) = [x_surface, 2(n.w)n - w, near_secondary, far_parent] with n = l2norm(normal),
+ * w = l2norm(-d) (eval.py:515-540).  reflect_dir (n,3) optional.  any_mirror: device int, set to 1 if any mask==1. */
+int mnrf_reflect_rays(const float* rays, const float* x_surface, const float* normal, float* mask, int n,
+                      float near_secondary, float* secondary, float* reflect_dir, int* any_mirror, void* stream);
+
+/* Stable compaction (same order as boolean-mask indexing): out (count,row_floats) = in[mask != 0].
+ * index (n) int32 optional: destination row or -1.  count: device int.  */
+int mnrf_compact_rows(const float* in, const float* mask, int n, int row_floats, float* out, int* index,
+                      int* count, void* stream);
+
+/* rgb = m*reflect + (1-m)*base (eval.py:680-697).  child_rgb/child_depth are the bounce results, either
+ * dense (index == NULL, n rows) or compacted (index[i] = row in child or -1 -> reflect := base).
+ * Outputs: rgb_out (n,3), rgb_reflect (n,3) and depth_reflect (n) (zeros where not traced). */
+int mnrf_blend_reflection(const float* base_rgb, const float* mask, const float* child_rgb,
+                          const float* child_depth, const int* index, int n, float* rgb_out, float* rgb_reflect,
+                          float* depth_reflect, void* stream);
+
+/* ---- misc ----------------------------------------------------------------------------------------- */
+const char* mnrf_last_error(void);
+int mnrf_abi_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t mnrf_launch_count(void);
+/* algorithmic MACs per point (unpadded layer dims): full forward / sigma-only+pred-normal */
+int64_t mnrf_macs_full(void);
+int64_t mnrf_macs_sigma_only(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MNRF_H_ */

@@ -1,0 +1,114 @@
+"""ctypes binding of libmnrf.so (include/mnrf.h).  There is no fallback: if the library is missing, or a
+call fails, this raises -- the product never silently computes on the CPU or through plain PyTorch ops."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmnrf.so")
+
+IMPL_TC3, IMPL_TC1, IMPL_FP32 = 3, 1, 0
+IMPL_BY_NAME = {"tc3": IMPL_TC3, "tc1": IMPL_TC1, "fp32": IMPL_FP32}
+NUM_PARAM_TENSORS = 32
+RAW_STRIDE = 8
+
+c_float_p = C.c_void_p  # device or host pointers are passed as integers
+c_int = C.c_int
+
+
+class CompositeOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "weights", "opacity", "rgb", "depth", "mirror_mask", "pred_normal", "surface_normal",
+        "surface_normal_grad", "normal_dif", "x_surface")]
+
+
+class LevelCfg(C.Structure):
+    _fields_ = [("n_samples", c_int), ("n_importance", c_int), ("use_disp", c_int), ("perturb", C.c_float),
+                ("noise_std", C.c_float), ("white_back", c_int), ("test_time", c_int), ("compute_normal", c_int),
+                ("rerun_coarse_on_fine", c_int), ("impl", c_int)]
+
+
+class LevelRng(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("perturb_u", "noise_coarse", "u_pdf", "noise_fine")]
+
+
+class LevelOut(C.Structure):
+    _fields_ = [("z_coarse", C.c_void_p), ("coarse", CompositeOut), ("normal_coarse", C.c_void_p),
+                ("z_fine", C.c_void_p), ("fine", CompositeOut), ("normal_fine", C.c_void_p)]
+
+
+_SIGS = {
+    "mnrf_last_error": (C.c_char_p, []),
+    "mnrf_abi_version": (c_int, []),
+    "mnrf_launch_count": (C.c_int64, []),
+    "mnrf_macs_full": (C.c_int64, []),
+    "mnrf_macs_sigma_only": (C.c_int64, []),
+    "mnrf_field_create": (c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]),
+    "mnrf_field_update": (c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]),
+    "mnrf_field_destroy": (None, [C.c_void_p]),
+    "mnrf_field_has_normal": (c_int, [C.c_void_p]),
+    "mnrf_field_has_mirror": (c_int, [C.c_void_p]),
+    "mnrf_field_eval_rays": (c_int, [C.c_void_p, c_int, c_float_p, c_float_p, c_int, c_int, c_int, c_float_p,
+                                     c_float_p, c_float_p, C.c_void_p]),
+    "mnrf_field_eval_points": (c_int, [C.c_void_p, c_int, c_float_p, c_int, c_int, c_float_p, c_float_p, c_float_p,
+                                       c_float_p, c_float_p, c_float_p, C.c_void_p]),
+    "mnrf_embed": (c_int, [c_float_p, c_int, c_int, c_float_p, C.c_void_p]),
+    "mnrf_coarse_z": (c_int, [c_float_p, c_int, c_float_p, c_int, c_int, C.c_float, c_float_p, c_float_p, C.c_void_p]),
+    "mnrf_searchsorted_right": (c_int, [c_float_p, c_int, c_int, c_float_p, c_int, c_int, C.c_void_p, C.c_void_p]),
+    "mnrf_sample_pdf": (c_int, [c_float_p, c_float_p, c_int, c_int, c_int, c_float_p, c_int, c_float_p, c_float_p,
+                                C.c_void_p, c_float_p, C.c_void_p]),
+    "mnrf_sample_pdf_bins": (c_int, [c_float_p, c_float_p, c_int, c_int, c_int, c_float_p, c_int, c_float_p,
+                                     C.c_void_p, c_float_p, C.c_void_p]),
+    "mnrf_composite": (c_int, [c_float_p, c_float_p, c_float_p, c_int, c_float_p, c_float_p, c_float_p, C.c_float,
+                               c_int, c_int, c_int, C.POINTER(CompositeOut), C.c_void_p]),
+    "mnrf_level_workspace_bytes": (C.c_int64, [c_int, C.POINTER(LevelCfg)]),
+    "mnrf_render_level": (c_int, [C.c_void_p, C.c_void_p, c_float_p, c_int, C.POINTER(LevelCfg), C.POINTER(LevelRng),
+                                  c_float_p, c_float_p, C.c_void_p, C.c_int64, C.POINTER(LevelOut), C.c_void_p]),
+    "mnrf_render_level_host": (c_int, [C.c_void_p, C.c_void_p, c_float_p, c_int, C.POINTER(LevelCfg), c_float_p,
+                                       c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
+                                       C.c_void_p]),
+    "mnrf_reflect_rays": (c_int, [c_float_p, c_float_p, c_float_p, c_float_p, c_int, C.c_float, c_float_p, c_float_p,
+                                  C.c_void_p, C.c_void_p]),
+    "mnrf_compact_rows": (c_int, [c_float_p, c_float_p, c_int, c_int, c_float_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mnrf_blend_reflection": (c_int, [c_float_p, c_float_p, c_float_p, c_float_p, C.c_void_p, c_int, c_float_p,
+                                      c_float_p, c_float_p, C.c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(sorted(_SIGS))
+
+_lib = None
+
+
+class MnrfError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libmnrf.so (once).  Raises if it has not been built: run __graft_entry__.build() or
+    `make -C mirror_nerf_b200/csrc`."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MnrfError(f"{LIB_PATH} not found: build it with `make -C {os.path.join(_HERE, 'csrc')}` "
+                        "(there is no CPU / PyTorch fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)  # AttributeError if the ABI is incomplete
+        fn.restype = res
+        fn.argtypes = args
+    if lib.mnrf_abi_version() != 1:
+        raise MnrfError("libmnrf.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().mnrf_last_error().decode("utf-8", "replace")
+        raise MnrfError(f"{what} failed (rc={rc}): {msg}")
+
+
+def launch_count():
+    return int(load().mnrf_launch_count())

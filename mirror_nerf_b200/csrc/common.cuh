@@ -1,0 +1,191 @@
+// Shared declarations of libmnrf (internal).  See include/mnrf.h for the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mnrf.h"
+
+namespace mnrf {
+
+// ------------------------------------------------------------------------------------------------
+// architecture constants (R/models/mirror_nerf.py:41-99 defaults: D=8, W=256, skips=[4], 10/4 freqs)
+// ------------------------------------------------------------------------------------------------
+constexpr int W = 256;           // trunk width
+constexpr int WH = 128;          // head width (W/2)
+constexpr int NFREQ_XYZ = 10;
+constexpr int NFREQ_DIR = 4;
+constexpr int IN_XYZ = 3 + 6 * NFREQ_XYZ;  // 63
+constexpr int IN_DIR = 3 + 6 * NFREQ_DIR;  // 27
+constexpr int PE_PAD = 64;                 // 63 -> 64
+constexpr float FP32_EPS = 1.1920928955078125e-07f;
+
+// parameter tensor indices (mnrf.h)
+enum {
+  T_XYZ_W0 = 0,  // 2*i weight, 2*i+1 bias, i=0..7
+  T_FINAL_W = 16, T_FINAL_B = 17, T_DIR_W = 18, T_DIR_B = 19, T_SIGMA_W = 20, T_SIGMA_B = 21,
+  T_RGB_W = 22, T_RGB_B = 23, T_N0_W = 24, T_N0_B = 25, T_N1_W = 26, T_N1_B = 27,
+  T_M0_W = 28, T_M0_B = 29, T_M2_W = 30, T_M2_B = 31
+};
+
+// ------------------------------------------------------------------------------------------------
+// tensor-core GEMM steps of one 128-point tile (field_tc.cu) and their packed-weight blobs
+// ------------------------------------------------------------------------------------------------
+constexpr int TC_NUM_STEPS = 11;
+// step:            0    1    2    3    4    5    6    7    8(final) 9(mirror0) 10(dir)
+__host__ __device__ constexpr int tc_step_n(int s) { return s <= 8 ? 256 : 128; }
+__host__ __device__ constexpr int tc_step_k(int s) { return s == 0 ? 64 : (s == 4 ? 320 : 256); }
+__host__ __device__ constexpr int tc_step_chunks(int s) { return tc_step_k(s) / 32; }
+// bytes of one blob (hi or lo part of one K32 chunk): N rows x 32 halves
+__host__ __device__ constexpr int tc_blob_bytes(int s) { return tc_step_n(s) * 64; }
+__host__ __device__ constexpr int tc_step_bytes(int s) { return tc_step_chunks(s) * 2 * tc_blob_bytes(s); }
+__host__ __device__ constexpr int tc_step_offset(int s) {
+  int o = 0;
+  for (int i = 0; i < s; ++i) o += tc_step_bytes(i);
+  return o;
+}
+constexpr int TC_TOTAL_BYTES = tc_step_offset(TC_NUM_STEPS);
+
+// ------------------------------------------------------------------------------------------------
+// fp32 section layout (float offsets inside mnrf_field::f32)
+// ------------------------------------------------------------------------------------------------
+struct F32Layout {
+  // transposed, K padded to a multiple of 4 rows: Wt[k][n]
+  int wt_trunk[8];   // layers 1..8
+  int wt_final, wt_dir, wt_n0, wt_m0;
+  // original [out,in] copies (for the analytic-normal backward chain and the tiny heads)
+  int w_trunk[8];
+  int w_sigma, w_rgb, w_n1, w_m2;
+  // biases
+  int b_trunk[8];
+  int b_final, b_dir, b_sigma, b_rgb, b_n0, b_n1, b_m0, b_m2;
+  // tensor-core epilogue tables
+  int headw;      // float4[256]: {w_sigma[c], Wn_fold[0][c], Wn_fold[1][c], Wn_fold[2][c]}
+  int headb;      // float4: {b_sigma, bn_fold[0..2]}
+  int inv_scale;  // float[TC_NUM_STEPS]
+  int absmax;     // uint[TC_NUM_STEPS] scratch for the scale computation
+  int total;
+};
+
+__host__ __device__ inline int trunk_k(int l) { return l == 0 ? IN_XYZ : (l == 4 ? IN_XYZ + W : W); }
+__host__ __device__ inline int pad4(int k) { return (k + 3) & ~3; }
+
+inline F32Layout make_f32_layout() {
+  F32Layout L;
+  int o = 0;
+  auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };  // keep 16B alignment
+  for (int l = 0; l < 8; ++l) L.wt_trunk[l] = take(pad4(trunk_k(l)) * W);
+  L.wt_final = take(W * W);
+  L.wt_dir = take(pad4(W + IN_DIR) * WH);
+  L.wt_n0 = take(W * WH);
+  L.wt_m0 = take(W * WH);
+  for (int l = 0; l < 8; ++l) L.w_trunk[l] = take(W * trunk_k(l));
+  L.w_sigma = take(W);
+  L.w_rgb = take(3 * WH);
+  L.w_n1 = take(3 * WH);
+  L.w_m2 = take(WH);
+  for (int l = 0; l < 8; ++l) L.b_trunk[l] = take(W);
+  L.b_final = take(W);
+  L.b_dir = take(WH);
+  L.b_sigma = take(4);
+  L.b_rgb = take(4);
+  L.b_n0 = take(WH);
+  L.b_n1 = take(4);
+  L.b_m0 = take(WH);
+  L.b_m2 = take(4);
+  L.headw = take(4 * W);
+  L.headb = take(4);
+  L.inv_scale = take(16);
+  L.absmax = take(16);
+  L.total = o;
+  return L;
+}
+
+}  // namespace mnrf
+
+struct mnrf_field {
+  int has_normal;
+  int has_mirror;
+  float* f32;        // device, mnrf::F32Layout
+  uint8_t* tc;       // device, TC_TOTAL_BYTES of fp16 hi/lo blobs
+  mnrf::F32Layout L;
+};
+
+namespace mnrf {
+
+// error plumbing ---------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+#define MNRF_CUDA_OK(expr)                                                              \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      mnrf::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return 1;                                                                         \
+    }                                                                                   \
+  } while (0)
+#define MNRF_LAUNCH_OK()                                                                \
+  do {                                                                                  \
+    cudaError_t _e = cudaGetLastError();                                                \
+    if (_e != cudaSuccess) {                                                            \
+      mnrf::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return 1;                                                                         \
+    }                                                                                   \
+    mnrf::count_launch();                                                               \
+  } while (0)
+#define MNRF_REQUIRE(cond, ...)                                                         \
+  do {                                                                                  \
+    if (!(cond)) {                                                                      \
+      mnrf::set_error(__VA_ARGS__);                                                     \
+      return 2;                                                                         \
+    }                                                                                   \
+  } while (0)
+
+// internal launchers (each returns 0 / error) ----------------------------------------------------
+int pack_field(mnrf_field* f, const float* const* tensors, cudaStream_t st);
+
+// per-ray (or per-point) additive term of the dir layer: b_dir + W_dir[:,256:283] . embed(dir)
+// from_embedded == 0: src = rays (n,8), direction embedded in-kernel; else src = x (n,30), cols 3..29
+int launch_dirbias(const mnrf_field* f, const float* src, int n, int src_stride, int from_embedded, float* out,
+                   cudaStream_t st);
+
+struct FieldIO {
+  // geometry: point p -> ray p / S, sample p % S;  xyz = o + d*z  (flat mode: S = 1, xyz read from x)
+  const float* rays;    // (n_rays,8) or NULL in flat mode
+  const float* z;       // (n_rays,S)
+  const float* x;       // flat mode: (B, x_stride) rows, first 3 = xyz
+  int x_stride;
+  const float* dirbias; // (n_rays or B, 128) ; NULL when sigma_only
+  int n_points;
+  int S;
+  int sigma_only;
+  // outputs (NULL = skip)
+  float* raw;        // (n_points, 8)
+  float* sigma_out;  // (n_points)
+  float* normal_out; // (n_points, 3) analytic normal (fp32 kernel only)
+  float* geo_out;    // (n_points, 256)
+};
+
+int launch_coarse_z(const float* rays, int n, const float* z_steps, int S, int use_disp, float perturb,
+                    const float* u, float* z_out, cudaStream_t st);
+int launch_embed(const float* x, int n, int n_freqs, float* out, cudaStream_t st);
+int launch_searchsorted(const float* cdf, int n, int m, const float* u, int n_u, int u_stride, int64_t* inds,
+                        cudaStream_t st);
+int launch_sample_pdf(const float* z_coarse, const float* bins, const float* weights, int w_stride, int w_off, int n,
+                      int S, int n_imp, const float* u, int u_stride, float* z_fine, float* samples, int64_t* inds,
+                      float* cdf, cudaStream_t st);
+int launch_composite(const float* rays, const float* z, const float* sigma, int sigma_stride, const float* raw,
+                     const float* normal, const float* noise, float noise_std, int n, int S, int white_back,
+                     const mnrf_composite_out& out, cudaStream_t st);
+int launch_reflect(const float* rays, const float* x_surface, const float* normal, float* mask, int n, float near2,
+                   float* sec, float* refl, int* any_mirror, cudaStream_t st);
+int launch_compact(const float* in, const float* mask, int n, int row_floats, float* out, int* index, int* count,
+                   cudaStream_t st);
+int launch_blend(const float* base, const float* mask, const float* child_rgb, const float* child_depth,
+                 const int* index, int n, float* rgb_out, float* rgb_reflect, float* depth_reflect, cudaStream_t st);
+
+int launch_field_fp32(const mnrf_field* f, const FieldIO& io, cudaStream_t st);
+int launch_field_tc(const mnrf_field* f, const FieldIO& io, int precision /*1|3*/, cudaStream_t st);
+
+}  // namespace mnrf

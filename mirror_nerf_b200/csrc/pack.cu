@@ -1,0 +1,196 @@
+// Weight packing: MirrorNeRF.state_dict() tensors ([out,in] fp32, R/models/mirror_nerf.py:60-99)
+//   -> (a) fp32 section: transposed copies, biases, folded normal head, epilogue tables
+//   -> (b) tensor-core section: per GEMM step, per K32 chunk, an fp16 "hi" blob and an fp16 "lo" blob
+//          (W*2^s = hi + lo) in the tcgen05 K-major no-swizzle core-matrix layout, so that one
+//          cp.async.bulk drops a ready-to-use B operand stage into shared memory.
+// Everything runs on the device, asynchronously on the caller's stream (no host sync: the optimizer
+// can step and the next render can repack without draining the GPU).
+#include "common.cuh"
+
+namespace mnrf {
+
+// ---- small generic kernels ---------------------------------------------------------------------
+__global__ void k_copy(const float* __restrict__ src, float* __restrict__ dst, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
+// dst[k][n] = src[n][k]  (src is [N][K] row-major), rows k >= K (padding) are zero
+__global__ void k_transpose_pad(const float* __restrict__ src, float* __restrict__ dst, int N, int K, int Kpad) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Kpad * N) return;
+  int k = i / N, n = i % N;
+  dst[i] = (k < K) ? src[n * K + k] : 0.f;
+}
+
+__global__ void k_fill(float* dst, float v, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = v;
+}
+
+// normal_net has no activation between its two Linears (mirror_nerf.py:85-88), so
+//   n = W1 (W0 g + b0) + b1 = (W1 W0) g + (W1 b0 + b1):  fold to one 3x256 map (double accumulation).
+// headw[c] = {w_sigma[c], Wf[0][c], Wf[1][c], Wf[2][c]},  headb = {b_sigma, bf[0..2]}
+__global__ void k_fold_heads(const float* __restrict__ w_sigma, const float* __restrict__ b_sigma,
+                             const float* __restrict__ n0w, const float* __restrict__ n0b,
+                             const float* __restrict__ n1w, const float* __restrict__ n1b, float4* __restrict__ headw,
+                             float* __restrict__ headb) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < W) {
+    float4 o;
+    o.x = w_sigma[c];
+    float v[3] = {0.f, 0.f, 0.f};
+    if (n0w != nullptr) {
+      for (int i = 0; i < 3; ++i) {
+        double acc = 0.0;
+        for (int j = 0; j < WH; ++j) acc += (double)n1w[i * WH + j] * (double)n0w[j * W + c];
+        v[i] = (float)acc;
+      }
+    }
+    o.y = v[0]; o.z = v[1]; o.w = v[2];
+    headw[c] = o;
+  }
+  if (c < 4) {
+    float r;
+    if (c == 0) r = b_sigma[0];
+    else if (n0w == nullptr) r = 0.f;
+    else {
+      double acc = (double)n1b[c - 1];
+      for (int j = 0; j < WH; ++j) acc += (double)n1w[(c - 1) * WH + j] * (double)n0b[j];
+      r = (float)acc;
+    }
+    headb[c] = r;
+  }
+}
+
+// ---- tensor-core blobs -------------------------------------------------------------------------
+struct TcSrc {
+  const float* w[TC_NUM_STEPS];  // source matrices [N][ld]
+  int ld[TC_NUM_STEPS];          // row stride (in-features of the nn.Linear)
+};
+
+// column of the source matrix feeding padded K index k of step s, or -1 for zero padding
+__device__ __forceinline__ int tc_src_col(int s, int k) {
+  if (s == 0) return k < IN_XYZ ? k : -1;                       // 63 -> 64
+  if (s == 4) return k < IN_XYZ ? k : (k == IN_XYZ ? -1 : k - 1);  // [pe(63) pad | h(256)]
+  return k;                                                      // 256 (dir layer: feature part only)
+}
+
+__global__ void k_absmax(TcSrc src, unsigned int* __restrict__ absmax) {
+  int s = blockIdx.y;
+  if (src.w[s] == nullptr) return;
+  int N = tc_step_n(s), K = tc_step_k(s);
+  float m = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N * K; i += gridDim.x * blockDim.x) {
+    int n = i / K, k = i % K;
+    int c = tc_src_col(s, k);
+    if (c >= 0) m = fmaxf(m, fabsf(src.w[s][n * src.ld[s] + c]));
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(absmax + s, __float_as_uint(m));
+}
+
+// scale = 2^(9 - floor(log2(max)))  ->  max|W| * scale in [2^9, 2^10): fp16 "lo" parts of all but the
+// tiniest weights stay in the normal range, and hi never overflows.
+__global__ void k_scales(const unsigned int* __restrict__ absmax, float* __restrict__ inv_scale) {
+  int s = threadIdx.x;
+  if (s >= TC_NUM_STEPS) return;
+  float m = __uint_as_float(absmax[s]);
+  float inv = 1.f;
+  if (m > 0.f && isfinite(m)) {
+    int e = ilogbf(m);
+    inv = ldexpf(1.f, e - 9);
+  }
+  inv_scale[s] = inv;
+}
+
+__global__ void k_pack_tc(TcSrc src, const float* __restrict__ inv_scale, uint8_t* __restrict__ tc) {
+  int s = blockIdx.y;
+  int N = tc_step_n(s), K = tc_step_k(s);
+  uint8_t* base = tc + tc_step_offset(s);
+  int blob = tc_blob_bytes(s);
+  float scale = 1.f / inv_scale[s];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N * K; i += gridDim.x * blockDim.x) {
+    int n = i / K, k = i % K;
+    float v = 0.f;
+    if (src.w[s] != nullptr) {
+      int c = tc_src_col(s, k);
+      if (c >= 0) v = src.w[s][n * src.ld[s] + c] * scale;
+    }
+    __half hi = __float2half_rn(v);
+    __half lo = __float2half_rn(v - __half2float(hi));
+    int kc = k >> 5, kk = k & 31;
+    int off = (kk >> 3) * (N * 16) + (n >> 3) * 128 + (n & 7) * 16 + (kk & 7) * 2;
+    uint8_t* chunk = base + (size_t)kc * 2 * blob;
+    *reinterpret_cast<__half*>(chunk + off) = hi;
+    *reinterpret_cast<__half*>(chunk + blob + off) = lo;
+  }
+}
+
+static int copy_to(const float* src, float* dst, int n, cudaStream_t st) {
+  if (src == nullptr) {
+    k_fill<<<(n + 255) / 256, 256, 0, st>>>(dst, 0.f, n);
+  } else {
+    k_copy<<<(n + 255) / 256, 256, 0, st>>>(src, dst, n);
+  }
+  MNRF_LAUNCH_OK();
+  return 0;
+}
+
+static int transpose_to(const float* src, float* dst, int N, int K, cudaStream_t st) {
+  int Kp = pad4(K);
+  if (src == nullptr) {
+    k_fill<<<(Kp * N + 255) / 256, 256, 0, st>>>(dst, 0.f, Kp * N);
+  } else {
+    k_transpose_pad<<<(Kp * N + 255) / 256, 256, 0, st>>>(src, dst, N, K, Kp);
+  }
+  MNRF_LAUNCH_OK();
+  return 0;
+}
+
+int pack_field(mnrf_field* f, const float* const* t, cudaStream_t st) {
+  const F32Layout& L = f->L;
+  float* d = f->f32;
+  for (int l = 0; l < 8; ++l) {
+    if (transpose_to(t[2 * l], d + L.wt_trunk[l], W, trunk_k(l), st)) return 1;
+    if (copy_to(t[2 * l], d + L.w_trunk[l], W * trunk_k(l), st)) return 1;
+    if (copy_to(t[2 * l + 1], d + L.b_trunk[l], W, st)) return 1;
+  }
+  if (transpose_to(t[T_FINAL_W], d + L.wt_final, W, W, st)) return 1;
+  if (copy_to(t[T_FINAL_B], d + L.b_final, W, st)) return 1;
+  if (transpose_to(t[T_DIR_W], d + L.wt_dir, WH, W + IN_DIR, st)) return 1;
+  if (copy_to(t[T_DIR_B], d + L.b_dir, WH, st)) return 1;
+  if (copy_to(t[T_SIGMA_W], d + L.w_sigma, W, st)) return 1;
+  if (copy_to(t[T_SIGMA_B], d + L.b_sigma, 1, st)) return 1;
+  if (copy_to(t[T_RGB_W], d + L.w_rgb, 3 * WH, st)) return 1;
+  if (copy_to(t[T_RGB_B], d + L.b_rgb, 3, st)) return 1;
+  if (transpose_to(t[T_N0_W], d + L.wt_n0, WH, W, st)) return 1;
+  if (copy_to(t[T_N0_B], d + L.b_n0, WH, st)) return 1;
+  if (copy_to(t[T_N1_W], d + L.w_n1, 3 * WH, st)) return 1;
+  if (copy_to(t[T_N1_B], d + L.b_n1, 3, st)) return 1;
+  if (transpose_to(t[T_M0_W], d + L.wt_m0, WH, W, st)) return 1;
+  if (copy_to(t[T_M0_B], d + L.b_m0, WH, st)) return 1;
+  if (copy_to(t[T_M2_W], d + L.w_m2, WH, st)) return 1;
+  if (copy_to(t[T_M2_B], d + L.b_m2, 1, st)) return 1;
+
+  k_fold_heads<<<1, 256, 0, st>>>(t[T_SIGMA_W], t[T_SIGMA_B], t[T_N0_W], t[T_N0_B], t[T_N1_W], t[T_N1_B],
+                                  reinterpret_cast<float4*>(d + L.headw), d + L.headb);
+  MNRF_LAUNCH_OK();
+
+  TcSrc src;
+  for (int s = 0; s < 8; ++s) { src.w[s] = t[2 * s]; src.ld[s] = trunk_k(s); }
+  src.w[8] = t[T_FINAL_W]; src.ld[8] = W;
+  src.w[9] = t[T_M0_W];    src.ld[9] = W;
+  src.w[10] = t[T_DIR_W];  src.ld[10] = W + IN_DIR;
+  unsigned int* absmax = reinterpret_cast<unsigned int*>(d + L.absmax);
+  MNRF_CUDA_OK(cudaMemsetAsync(absmax, 0, 16 * sizeof(unsigned int), st));
+  k_absmax<<<dim3(32, TC_NUM_STEPS), 256, 0, st>>>(src, absmax);
+  MNRF_LAUNCH_OK();
+  k_scales<<<1, 32, 0, st>>>(absmax, d + L.inv_scale);
+  MNRF_LAUNCH_OK();
+  k_pack_tc<<<dim3(64, TC_NUM_STEPS), 256, 0, st>>>(src, d + L.inv_scale, f->tc);
+  MNRF_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace mnrf

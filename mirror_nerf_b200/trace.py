@@ -1,0 +1,107 @@
+"""Whitted-style recursion around render_rays -- SURVEY.md section 8f row 1 -- restating what the reference's callers do
+(R/eval.py:132-160,295-320,515-548,676-697; train semantics R/train.py:153-296) with the mask threshold, reflection,
+stable compaction and blend running as CUDA kernels of libmnrf.so instead of boolean-mask indexing.
+
+This is an ADDITIVE entry point: ``render_rays`` itself stays single-level and drop-in (the reference puts the bounce
+in its callers).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .mirror_nerf import _ptr, _stream_ptr
+from .rendering import render_rays
+
+__all__ = ["render_rays_recursive", "reflect_rays", "compact_rows", "blend_reflection"]
+
+RAY_FORWARD_OFFSET = 0.1  # near of a secondary ray (eval.py:529, train.py:232)
+
+
+def reflect_rays(rays, x_surface, normal, mask):
+    """Threshold `mask` IN PLACE (>0.5 -> 1, <0.5 -> 0) and build secondary rays.
+    Returns (secondary (n,8), reflect_direction (n,3), any_mirror: 0-d int32 device tensor)."""
+    lib = _lib.load()
+    n = rays.shape[0]
+    dev = rays.device
+    sec = torch.empty(n, 8, device=dev, dtype=torch.float32)
+    refl = torch.empty(n, 3, device=dev, dtype=torch.float32)
+    flag = torch.zeros((), device=dev, dtype=torch.int32)
+    for t in (rays, x_surface, normal, mask):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+    with torch.cuda.device(dev):
+        _lib.check(lib.mnrf_reflect_rays(_ptr(rays), _ptr(x_surface), _ptr(normal), _ptr(mask), n, RAY_FORWARD_OFFSET,
+                                         _ptr(sec), _ptr(refl), _ptr(flag), _stream_ptr()), "mnrf_reflect_rays")
+    return sec, refl, flag
+
+
+def compact_rows(rows, mask):
+    """rows[mask != 0] in the same (stable) order as boolean indexing.  Returns (compacted, index int32 (n,) with the
+    destination row or -1).  Reads the count back to size the result (one host sync, like `.any()` in the reference)."""
+    lib = _lib.load()
+    n, c = rows.shape
+    dev = rows.device
+    out = torch.empty(n, c, device=dev, dtype=torch.float32)
+    index = torch.empty(n, device=dev, dtype=torch.int32)
+    count = torch.zeros((), device=dev, dtype=torch.int32)
+    with torch.cuda.device(dev):
+        _lib.check(lib.mnrf_compact_rows(_ptr(rows), _ptr(mask), n, c, _ptr(out), _ptr(index), _ptr(count),
+                                         _stream_ptr()), "mnrf_compact_rows")
+    return out[: int(count.item())], index
+
+
+def blend_reflection(base_rgb, mask, child_rgb, child_depth, index=None):
+    """rgb = m * reflect + (1-m) * base with m = (mask != 0).  Returns (rgb, rgb_reflect, depth_reflect)."""
+    lib = _lib.load()
+    n = base_rgb.shape[0]
+    dev = base_rgb.device
+    rgb = torch.empty(n, 3, device=dev, dtype=torch.float32)
+    rgb_reflect = torch.empty(n, 3, device=dev, dtype=torch.float32)
+    depth_reflect = torch.empty(n, device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        _lib.check(lib.mnrf_blend_reflection(_ptr(base_rgb), _ptr(mask), _ptr(child_rgb.contiguous()),
+                                             _ptr(child_depth.contiguous()), _ptr(index), n, _ptr(rgb), _ptr(rgb_reflect),
+                                             _ptr(depth_reflect), _stream_ptr()), "mnrf_blend_reflection")
+    return rgb, rgb_reflect, depth_reflect
+
+
+def render_rays_recursive(models, embeddings, rays, N_samples=64, use_disp=False, perturb=0, noise_std=0,
+                          N_importance=0, chunk=1024 * 32, white_back=False, max_recursive_level=1,
+                          only_trace_rays_in_mirrors=None, test_time=True, _level=0, **kwargs):
+    """Eval-semantics recursion (R/eval.py:132-725): level 0 re-traces ALL rays of a batch that contains a mirror
+    pixel, deeper levels only the mirror rays; `only_trace_rays_in_mirrors=True` compacts at every level (train.py
+    semantics).  Returns the level-0 render_rays dict with rgb_{typ} blended plus rgb_{typ}_direct/_reflect,
+    depth_{typ}_reflect and reflect_direction."""
+    kwargs.setdefault("compute_normal", False)
+    res = render_rays(models, embeddings, rays, N_samples, use_disp, perturb, noise_std, N_importance, chunk,
+                      white_back, test_time=test_time, **kwargs)
+    typ = "fine" if (N_importance > 0 and not kwargs.get("only_one_field", False)) else "coarse"
+    if f"mirror_mask_{typ}" not in res:
+        return res
+    rays = rays.detach().contiguous()
+    normal = res.get(f"surface_normal_{typ}", res.get(f"surface_normal_grad_{typ}"))
+    mask = res[f"mirror_mask_{typ}"]
+    sec, refl, flag = reflect_rays(rays, res[f"x_surface_{typ}"], normal, mask)
+    base = res[f"rgb_{typ}"]
+    res[f"rgb_{typ}_reflect"] = torch.zeros_like(base)
+    res[f"depth_{typ}_reflect"] = torch.zeros_like(res[f"depth_{typ}"])
+    if _level >= max_recursive_level or int(flag.item()) == 0:  # the reference's mirror_mask.any() host sync
+        return res
+    res["reflect_direction"] = refl
+    only_mirror = (_level >= 1) if only_trace_rays_in_mirrors is None else bool(only_trace_rays_in_mirrors)
+    index = None
+    if only_mirror:
+        sec, index = compact_rows(sec, mask)
+    if sec.shape[0] == 0:
+        return res
+    sub = render_rays_recursive(models, embeddings, sec, N_samples, use_disp, perturb, noise_std, N_importance, chunk,
+                                white_back, max_recursive_level, only_trace_rays_in_mirrors, test_time,
+                                _level=_level + 1, **kwargs)
+    rgb, rgb_reflect, depth_reflect = blend_reflection(base, mask, sub[f"rgb_{typ}"], sub[f"depth_{typ}"], index)
+    res[f"rgb_{typ}_direct"] = base
+    res[f"rgb_{typ}"] = rgb
+    res[f"rgb_{typ}_reflect"] = rgb_reflect
+    res[f"depth_{typ}_reflect"] = depth_reflect
+    return res

@@ -1,0 +1,99 @@
+"""CPU-only checks (no compute calls): the C-ABI library loads and exports every symbol include/mnrf.h declares,
+the ctypes structs match the header, the host layer refuses non-CUDA inputs loudly, and the module mirrors the
+reference's state_dict layout."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "mnrf.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mnrf_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from mirror_nerf_b200 import _lib
+    lib = _lib.load()
+    names = header_functions()
+    assert len(names) >= 24
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/mnrf.h but not exported by libmnrf.so"
+    assert set(names) == set(_lib.EXPORTED_SYMBOLS), set(names) ^ set(_lib.EXPORTED_SYMBOLS)
+    assert lib.mnrf_abi_version() == 1
+    assert lib.mnrf_macs_full() == 659456 and lib.mnrf_macs_sigma_only() == 524416
+
+
+def test_struct_sizes_match_header():
+    from mirror_nerf_b200 import _lib
+    assert C.sizeof(_lib.CompositeOut) == 10 * 8
+    assert C.sizeof(_lib.LevelCfg) == 10 * 4
+    assert C.sizeof(_lib.LevelRng) == 4 * 8
+    assert C.sizeof(_lib.LevelOut) == 8 + 80 + 8 + 8 + 80 + 8
+    lib = _lib.load()
+    cfg = _lib.LevelCfg(n_samples=64, n_importance=128)
+    # dirbias n*128*4 + coarse n*64*32 + fine n*192*32 bytes
+    assert lib.mnrf_level_workspace_bytes(1000, C.byref(cfg)) == 1000 * (512 + 2048 + 6144)
+
+
+def test_compute_without_gpu_fails_loudly():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from mirror_nerf_b200 import _lib
+    lib = _lib.load()
+    h = C.c_void_p()
+    arr = (C.c_void_p * 32)(*[1] * 32)
+    assert lib.mnrf_field_create(C.byref(h), arr, None) != 0
+    assert b"cuda" in lib.mnrf_last_error().lower()
+
+
+def test_host_layer_rejects_cpu_tensors():
+    from mirror_nerf_b200.mirror_nerf import Embedding, MirrorNeRF
+    from mirror_nerf_b200.rendering import render_rays, sample_pdf
+    m = MirrorNeRF(predict_normal=True, predict_mirror_mask=True)
+    emb = {"xyz": Embedding(10), "dir": Embedding(4)}
+    with pytest.raises(RuntimeError, match="CUDA"):
+        render_rays({"coarse": m}, emb, torch.zeros(4, 8), 64, False, 0, 0, 0, 1024, False)
+    with pytest.raises(RuntimeError, match="rays must be"):
+        render_rays({"coarse": m}, emb, torch.zeros(4, 7), 64, False, 0, 0, 0, 1024, False)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        sample_pdf(torch.zeros(2, 63), torch.zeros(2, 62), 8, det=True)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(3, 30))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        emb["xyz"](torch.zeros(3, 3))
+
+
+def test_module_mirrors_reference_state_dict():
+    from mirror_nerf_b200.mirror_nerf import PARAM_KEYS, MirrorNeRF
+    from mirror_nerf_b200.synthetic import field_param_shapes, make_state_dict
+    m = MirrorNeRF(predict_normal=True, predict_mirror_mask=True)
+    sd = m.state_dict()
+    shapes = field_param_shapes()
+    assert list(sd) == list(shapes)  # same keys, same order as the reference module
+    assert set(sd) == set(PARAM_KEYS)
+    for k, s in shapes.items():
+        assert tuple(sd[k].shape) == tuple(s), k
+    m.load_state_dict(make_state_dict(3))
+    assert sum(p.numel() for p in m.parameters()) == 662152
+    m0 = MirrorNeRF()
+    assert sum(p.numel() for p in m0.parameters()) == 595844
+    with pytest.raises(NotImplementedError):
+        MirrorNeRF(D=4)
+
+
+def test_shard_plan():
+    from mirror_nerf_b200.parallel import shard_bounds
+    n = 640000
+    for world in (1, 2, 4, 8, 3):
+        b = [shard_bounds(n, r, world) for r in range(world)]
+        assert b[0][0] == 0 and b[-1][1] == n
+        assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+        sizes = [hi - lo for lo, hi in b]
+        assert max(sizes) - min(sizes) <= 128  # whole 128-ray tiles per rank
+    assert shard_bounds(5, 3, 8) == (5, 5)  # more ranks than tiles: empty shards are legal
