@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""bench.py -- rays/sec of the render_rays hot path on B200 (BASELINE.json metric).
+
+Workload (config[1] of BASELINE.json): synthetic 800x800 view (640,000 primary rays), 64 coarse + 128 importance
+samples (192 fine points), both heads, eval mode, 1 reflection bounce with the reference's eval semantics (level 0,
+then every ray of the batch is reflected and re-rendered once, then blended by the thresholded mirror mask:
+R/eval.py:132-160,545-548,676-697) -> 2 render levels per primary ray.  A "step" is one such image.  Multi-GPU: one
+process per GPU, each rank renders its own view (weak scaling), no data-path collective.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--field-impl tc3|tc1]
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the definition of every key.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H = W = 800
+N_SAMPLES, N_IMPORTANCE = 64, 128
+FLOP_PER_RAY_LEVEL = 320.36e6  # 64*S + 192*F MACs * 2 (unpadded reference layer sizes)
+LEVELS = 2                     # level 0 + 1 bounce (eval semantics re-traces all rays of the batch)
+METRIC = "rays/sec (64c+128f samples, 1 bounce)"
+WORKLOAD = "synthetic 800x800 mirror scene, 64+128 samples, 1 reflection bounce, eval semantics"
+
+
+def view_pose(i):
+    """Small orbit of camera poses (one per rank / step): rotate about y, camera 2.5 away looking at the origin."""
+    import math
+    import torch
+    a = 0.35 * i
+    c, s = math.cos(a), math.sin(a)
+    return torch.tensor([[c, 0.0, s, 2.5 * s], [0.0, 1.0, 0.0, 0.0], [-s, 0.0, c, 2.5 * c]])
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop_evt = index, [], set(), None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_reference_rate(n_rays, steps, warmup, threads):
+    """The reference algorithm (oracle restatement = the same ATen CPU kernels the reference runs) on the host cores:
+    `n_rays` rays of the same view per step, 64+128 samples, 1 bounce, eval semantics.  Returns (rays/s, rgb, rays)."""
+    import torch
+    from mirror_nerf_b200.synthetic import camera_rays, scene_state_dicts
+    from oracle import mirror_nerf_oracle as O
+    torch.set_num_threads(threads)
+    params = scene_state_dicts()
+    allrays = camera_rays(H, W, c2w=view_pose(0))
+    idx = torch.linspace(0, allrays.shape[0] - 1, n_rays).long()
+    rays = allrays[idx].contiguous()
+    fn = lambda r: O.render_rays(params, r, N_SAMPLES, False, 0, 0, N_IMPORTANCE, 32768, False, test_time=True,
+                                 compute_normal=False)
+    out = None
+    with torch.no_grad():
+        for _ in range(warmup):
+            O.trace_eval(fn, rays[: max(64, n_rays // 8)], 1)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out = O.trace_eval(fn, rays, 1)
+        dt = time.perf_counter() - t0
+    return n_rays * steps / dt, out["rgb_fine"], rays, dt / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n = args.ref_rays
+    rate, _, _, step_s = cpu_reference_rate(n, args.steps, min(args.warmup, 1), threads)
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "rays/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": f"{n} rays of the view per step"},
+            "cpu_baseline": {"value": rate, "unit": "rays/s", "cores": threads, "kind": "port",
+                             "sample": f"{n} rays x 2 levels per step, {args.steps} steps (oracle port of the "
+                                       "reference's torch CPU path; /root/reference cannot travel to the GPU box)"},
+            "e2e": {"value": rate, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mirror_nerf_b200 import _lib
+    from mirror_nerf_b200.mirror_nerf import Embedding, MirrorNeRF
+    from mirror_nerf_b200.synthetic import camera_rays, scene_state_dicts
+    from mirror_nerf_b200.trace import render_rays_recursive
+    import ctypes as C
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    models = {}
+    for k, sd in scene_state_dicts().items():
+        m = MirrorNeRF(predict_normal=True, predict_mirror_mask=True)
+        m.load_state_dict(sd)
+        models[k] = m.to(dev).eval()
+    emb = {"xyz": Embedding(10), "dir": Embedding(4)}
+    rays_host = camera_rays(H, W, c2w=view_pose(rank)).pin_memory()
+    rays_dev = rays_host.to(dev)
+    n = rays_dev.shape[0]
+    kw = dict(field_impl=args.field_impl)
+
+    def step(rays):
+        return render_rays_recursive(models, emb, rays, N_SAMPLES, False, 0, 0, N_IMPORTANCE, 32768, False,
+                                     max_recursive_level=1, **kw)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for a, b in ev:
+            flush.fill_(1)  # L2 flush between timed iterations (outside the timed events)
+            a.record()
+            fn()
+            b.record()
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            res = step(rays_dev)
+        torch.cuda.synchronize()
+        mirror_frac = float((res["mirror_mask_fine"] != 0).float().mean())
+
+        # ---- device-resident throughput (value) + live kernel timing (roofline) ----
+        sampler = ClockSampler(local)
+        sampler.start()
+        lib.mnrf_profile_enable(1)
+        l0 = _lib.launch_count()
+        ms_total = timed(lambda: step(rays_dev), args.steps)
+        launches = _lib.launch_count() - l0
+        lib.mnrf_profile_enable(0)
+        k_ms, k_fl, k_n = C.c_double(), C.c_double(), C.c_int64()
+        _lib.check(lib.mnrf_profile_collect(C.byref(k_ms), C.byref(k_fl), C.byref(k_n)))
+        clocks = sampler.stop()
+
+        # ---- end to end through the public API with host buffers (H2D of rays, D2H of the image) ----
+        out_host = torch.empty(n, 3, dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            r = rays_host.to(dev, non_blocking=True)
+            out = step(r)
+            out_host.copy_(out["rgb_fine"], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        e2e_steps = max(1, min(args.steps, 5))
+        e2e_step()
+        ms_e2e = timed(e2e_step, e2e_steps)
+
+    value = world * n * args.steps / (ms_total * 1e-3)
+    e2e_value = world * n * e2e_steps / (ms_e2e * 1e-3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("bf16_tflops_sustained")
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside the step)"
+    if peak is None:
+        peak, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)"
+    achieved = (k_fl.value / 1e12) / (k_ms.value * 1e-3) if k_ms.value > 0 else None
+    mma_per_mac = 3 if args.field_impl == "tc3" else 1
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f16x3-split operands, f32 accumulate (fp32-grade)" if args.field_impl == "tc3" else "f16, f32 accumulate",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": n, "levels_per_ray": LEVELS,
+                   "field_impl": args.field_impl, "mirror_ray_fraction": mirror_frac,
+                   "l2": "256 MB buffer written between timed steps (L2 flush); per-step scratch is > L2 anyway",
+                   "parallelism": f"ray-parallel x{world}, one view per rank, no collective"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": n * 12,
+                "steps": e2e_steps},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                     "frac": (achieved / peak if achieved else None), "traffic": None, "peak_source": peak_src,
+                     "kernel": "k_field_tc", "kernel_launches": int(k_n.value), "kernel_ms": k_ms.value,
+                     "kernel_share_of_step": k_ms.value / ms_total if ms_total else None,
+                     "flops_basis": "algorithmic 2*MAC of the reference layers (SURVEY.md 8d); the kernel issues "
+                                    f"{mma_per_mac} tensor-core MAC per algorithmic MAC",
+                     "tensor_pipe_flops_frac": (achieved * mma_per_mac / peak if achieved else None)},
+    }
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        rate, rgb_ref, rays_s, _ = cpu_reference_rate(args.ref_rays, 1, 1, threads)
+        with torch.no_grad():
+            got = step(rays_s.to(dev))["rgb_fine"].cpu()
+        mse = float(((got - rgb_ref) ** 2).mean())
+        import math
+        line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": threads, "kind": "port",
+                                "sample": f"{args.ref_rays} rays of the same view, 64+128 samples, 1 bounce, 1 step"}
+        line["psnr_vs_reference_db"] = (-10 * math.log10(mse) if mse > 0 else float("inf"))
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--field-impl", default="tc3", choices=["tc3", "tc1"])
+    ap.add_argument("--ref-rays", type=int, default=2048, help="rays per step of the CPU reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -199,6 +199,11 @@ const char* mnrf_last_error(void);
 int mnrf_abi_version(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t mnrf_launch_count(void);
+/* Time every launch of the tcgen05 field kernel with CUDA events recorded on its own launch stream.
+ * collect() waits for the recorded launches and returns their summed device time, summed ALGORITHMIC flops
+ * (2 * points * mnrf_macs_*()) and count, then clears the log. */
+int mnrf_profile_enable(int on);
+int mnrf_profile_collect(double* total_ms, double* total_flops, int64_t* launches);
 /* algorithmic MACs per point (unpadded layer dims): full forward / sigma-only+pred-normal */
 int64_t mnrf_macs_full(void);
 int64_t mnrf_macs_sigma_only(void);

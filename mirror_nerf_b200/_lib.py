@@ -42,6 +42,8 @@ _SIGS = {
     "mnrf_last_error": (C.c_char_p, []),
     "mnrf_abi_version": (c_int, []),
     "mnrf_launch_count": (C.c_int64, []),
+    "mnrf_profile_enable": (c_int, [c_int]),
+    "mnrf_profile_collect": (c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "mnrf_macs_full": (C.c_int64, []),
     "mnrf_macs_sigma_only": (C.c_int64, []),
     "mnrf_field_create": (c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]),

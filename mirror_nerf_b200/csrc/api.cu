@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 
@@ -19,6 +20,32 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- per-launch timing of the tcgen05 field kernel (roofline numbers of bench.py) ------------------
+struct ProfRec { cudaEvent_t e0, e1; double flops; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_prof_pool;
+static cudaEvent_t g_prof_pending = nullptr;
+
+static cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+void prof_begin(cudaStream_t st) {
+  if (!g_prof_on) return;
+  g_prof_pending = prof_event();
+  cudaEventRecord(g_prof_pending, st);
+}
+void prof_end(cudaStream_t st, double flops) {
+  if (!g_prof_on || g_prof_pending == nullptr) return;
+  ProfRec r{g_prof_pending, prof_event(), flops};
+  cudaEventRecord(r.e1, st);
+  g_prof.push_back(r);
+  g_prof_pending = nullptr;
+}
 
 namespace {
 
@@ -57,6 +84,27 @@ extern "C" {
 const char* mnrf_last_error(void) { return g_err; }
 int mnrf_abi_version(void) { return MNRF_ABI_VERSION; }
 int64_t mnrf_launch_count(void) { return (int64_t)g_launches.load(); }
+int mnrf_profile_enable(int on) {
+  g_prof_on = on != 0;
+  return 0;
+}
+int mnrf_profile_collect(double* total_ms, double* total_flops, int64_t* launches) {
+  double ms = 0.0, fl = 0.0;
+  for (ProfRec& r : g_prof) {
+    MNRF_CUDA_OK(cudaEventSynchronize(r.e1));
+    float t = 0.f;
+    MNRF_CUDA_OK(cudaEventElapsedTime(&t, r.e0, r.e1));
+    ms += t;
+    fl += r.flops;
+    g_prof_pool.push_back(r.e0);
+    g_prof_pool.push_back(r.e1);
+  }
+  if (total_ms) *total_ms = ms;
+  if (total_flops) *total_flops = fl;
+  if (launches) *launches = (int64_t)g_prof.size();
+  g_prof.clear();
+  return 0;
+}
 int64_t mnrf_macs_full(void) {
   // trunk 491,264 + colour 102,144 + normal 33,152 + mirror 32,896
   return 659456;

@@ -142,6 +142,10 @@ void count_launch(int n = 1);
     }                                                                                   \
   } while (0)
 
+// optional timing of the dominant kernel with CUDA events on its own launch stream (mnrf_profile_*)
+void prof_begin(cudaStream_t st);
+void prof_end(cudaStream_t st, double flops);
+
 // internal launchers (each returns 0 / error) ----------------------------------------------------
 int pack_field(mnrf_field* f, const float* const* tensors, cudaStream_t st);
 

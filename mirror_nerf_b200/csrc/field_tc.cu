@@ -535,7 +535,11 @@ int launch_field_tc(const mnrf_field* f, const FieldIO& io, int precision, cudaS
   P.io = io;
   P.n_tiles = (io.n_points + TILE_M - 1) / TILE_M;
   int grid = P.n_tiles < num_sms ? P.n_tiles : num_sms;
+  // algorithmic MACs of this launch (unpadded reference layer sizes)
+  const double macs = (double)io.n_points * (io.sigma_only ? (double)mnrf_macs_sigma_only() : (double)mnrf_macs_full());
+  prof_begin(st);
   k_field_tc<<<grid, NUM_THREADS, SM_TOTAL, st>>>(P);
+  prof_end(st, 2.0 * macs);
   MNRF_LAUNCH_OK();
   return 0;
 }

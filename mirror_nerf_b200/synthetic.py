@@ -44,7 +44,7 @@ def field_param_shapes(D=8, W=256, in_xyz=63, in_dir=27, skips=(4,), predict_nor
 
 
 def make_state_dict(seed=0, sigma_scale=40.0, sigma_bias=None, predict_normal=True,
-                    predict_mirror_mask=True, device="cpu"):
+                    predict_mirror_mask=True, device="cpu", mirror_scale=1.0):
     """nn.Linear-style U(-1/sqrt(fan_in), 1/sqrt(fan_in)) init from numpy PCG64(seed)."""
     g = np.random.Generator(np.random.PCG64(seed))
     sd = OrderedDict()
@@ -60,7 +60,22 @@ def make_state_dict(seed=0, sigma_scale=40.0, sigma_bias=None, predict_normal=Tr
     sd["sigma.weight"] = sd["sigma.weight"] * float(sigma_scale)
     if sigma_bias is not None:
         sd["sigma.bias"] = torch.full((1,), float(sigma_bias), dtype=torch.float32)
+    if predict_mirror_mask and mirror_scale != 1.0:
+        sd["is_mirror_net.2.weight"] = sd["is_mirror_net.2.weight"] * float(mirror_scale)
     return OrderedDict((k, v.to(device)) for k, v in sd.items())
+
+
+# The synthetic "scene" every fixture, test, smoke() and bench.py uses: coarse = seed 0, fine = seed 4 (about half of
+# random rays saturate, the rest stay translucent), sigma head x40 (sharp, adversarial density: SURVEY.md 7.3), mirror
+# head x100 so that the composited mirror probability straddles the 0.5 threshold (about half of the rays bounce).
+SCENE_SEEDS = {"coarse": 0, "fine": 4}
+SCENE_MIRROR_SCALE = 100.0
+
+
+def scene_state_dicts(predict_normal=True, predict_mirror_mask=True, device="cpu"):
+    return {k: make_state_dict(seed, 40.0, None, predict_normal, predict_mirror_mask, device,
+                               mirror_scale=SCENE_MIRROR_SCALE)
+            for k, seed in SCENE_SEEDS.items()}
 
 
 def random_rays(n, seed=1, near=0.05, far=8.0, device="cpu"):

@@ -33,17 +33,18 @@ def npify(d):
 
 
 def main():
-    from mirror_nerf_b200.synthetic import make_state_dict, random_rays
+    from mirror_nerf_b200.synthetic import random_rays, scene_state_dicts
     torch.set_num_threads(8)
     Embedding, MirrorNeRF, render_rays, sample_pdf = import_reference()
     emb = {"xyz": Embedding(10), "dir": Embedding(4)}
 
-    def model(seed, sigma_scale=40.0):
+    def model(sd):
         m = MirrorNeRF(predict_normal=True, predict_mirror_mask=True)
-        m.load_state_dict(make_state_dict(seed, sigma_scale))
+        m.load_state_dict(sd)
         return m.eval()
 
-    coarse, fine = model(0), model(1)
+    sds = scene_state_dicts()
+    coarse, fine = model(sds["coarse"]), model(sds["fine"])
     models = {"coarse": coarse, "fine": fine}
 
     # ---- 1. embedding + field forward on flat points ------------------------------------------
@@ -95,7 +96,7 @@ def main():
         "inds_rnd": torch.searchsorted(cdf, u, right=True)}))
 
     # ---- 3. render_rays, eval mode 64+128 (BASELINE config 2 per-level call) ---------------------
-    rays = random_rays(48, seed=1)
+    rays = random_rays(64, seed=1)
     with torch.no_grad():
         r = render_rays(models, emb, rays, 64, False, 0, 0, 128, 32768, False, test_time=True,
                         compute_normal=False)

@@ -33,8 +33,8 @@ def oracle():
 
 @pytest.fixture(scope="module")
 def params():
-    from mirror_nerf_b200.synthetic import make_state_dict
-    return {"coarse": make_state_dict(0), "fine": make_state_dict(1)}
+    from mirror_nerf_b200.synthetic import scene_state_dicts
+    return scene_state_dicts()
 
 
 def assert_close_dist(got, want, name, median=1e-4, frac=0.03, p99=None):
@@ -176,10 +176,9 @@ def test_field_tcgen05_kernel_golden(golden, mm, impl, med, p99):
 
 def test_field_heads_optional(oracle):
     """MirrorNeRF default (no normal / mirror heads): keys and values."""
-    from mirror_nerf_b200.synthetic import make_state_dict, random_rays
+    from mirror_nerf_b200.synthetic import random_rays, scene_state_dicts
     models, emb = make_models(predict_normal=False, predict_mirror_mask=False)
-    p = {"coarse": make_state_dict(0, predict_normal=False, predict_mirror_mask=False),
-         "fine": make_state_dict(1, predict_normal=False, predict_mirror_mask=False)}
+    p = scene_state_dicts(predict_normal=False, predict_mirror_mask=False)
     rays = random_rays(40, seed=8)
     from mirror_nerf_b200.rendering import render_rays
     with torch.no_grad():

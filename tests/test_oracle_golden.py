@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from mirror_nerf_b200.synthetic import make_state_dict
+from mirror_nerf_b200.synthetic import scene_state_dicts
 from oracle import mirror_nerf_oracle as O
 
 
@@ -22,7 +22,7 @@ def close(a, b, name, rtol=1e-5, atol=1e-6):
 
 @pytest.fixture(scope="module")
 def params():
-    return {"coarse": make_state_dict(0), "fine": make_state_dict(1)}
+    return scene_state_dicts()
 
 
 def test_embedding(golden):
@@ -109,7 +109,7 @@ def test_render_variants(golden, params, tag):
 
 def test_render_train_with_grads(golden):
     g = golden("render_train")
-    params = {"coarse": make_state_dict(0), "fine": make_state_dict(1)}
+    params = scene_state_dicts()
     for p in params.values():
         for t in p.values():
             t.requires_grad_(True)

@@ -2,21 +2,20 @@
 import numpy as np
 import torch
 
-from mirror_nerf_b200.synthetic import make_state_dict
+from mirror_nerf_b200.synthetic import scene_state_dicts
 
 
 def T(x, device="cpu"):
     return torch.from_numpy(np.asarray(x)).to(device)
 
 
-def make_models(device="cuda", seeds=(0, 1), sigma_scale=40.0, predict_normal=True, predict_mirror_mask=True):
+def make_models(device="cuda", predict_normal=True, predict_mirror_mask=True):
     """Two of OUR MirrorNeRF modules loaded with the synthetic state dicts the golden vectors were made with."""
     from mirror_nerf_b200.mirror_nerf import Embedding, MirrorNeRF
     models = {}
-    for name, seed in zip(("coarse", "fine"), seeds):
+    for name, sd in scene_state_dicts(predict_normal, predict_mirror_mask).items():
         m = MirrorNeRF(predict_normal=predict_normal, predict_mirror_mask=predict_mirror_mask)
-        m.load_state_dict(make_state_dict(seed, sigma_scale, predict_normal=predict_normal,
-                                          predict_mirror_mask=predict_mirror_mask))
+        m.load_state_dict(sd)
         models[name] = m.to(device).eval()
     emb = {"xyz": Embedding(10), "dir": Embedding(4)}
     return models, emb
