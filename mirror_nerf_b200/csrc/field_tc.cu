@@ -1,20 +1,24 @@
-// tcgen05 field kernel: MirrorNeRF.forward (R/models/mirror_nerf.py:101-212) fused per 128-point tile:
+// tcgen05 field kernel (v2): MirrorNeRF.forward (R/models/mirror_nerf.py:101-212) fused per 128-point tile:
 //   o + d*z  ->  positional encoding  ->  8x256 trunk (skip at layer 5)  ->  sigma / folded normal head
-//   ->  final 256x256  ->  mirror head  ->  dir layer (+ per-ray dir term)  ->  rgb      -> 8 floats/point.
+//   ->  mirror head  ->  final 256x256  ->  dir layer (+ per-ray dir term)  ->  rgb      -> 8 floats/point.
 //
 // One persistent CTA per SM, 12 warps:
-//   warp 0        weight producer: cp.async.bulk (TMA 1-D) of pre-packed B-operand blobs, 4-stage mbarrier ring
-//   warp 1        MMA issuer: one thread issues tcgen05.mma (M=128, N=256|128, K=16, fp16 -> fp32 in TMEM)
+//   warp 0        weight producer: cp.async.bulk (TMA 1-D) of pre-packed 8 KB B-operand blobs, 8-stage mbarrier ring
+//   warp 1        MMA issuer: one thread issues tcgen05.mma (M=128, N=128, K=16, fp16 -> fp32 in TMEM)
 //   warps 4..11   epilogue/PE: TMEM -> registers (tcgen05.ld) -> bias/ReLU -> fp16 hi/lo split -> next layer's
-//                 A operand written in place into shared memory in the UMMA K-major core-matrix layout;
-//                 per-64-column "chunk ready" mbarriers let the next layer's MMAs start while the rest of the
-//                 epilogue is still running (two 256-column TMEM accumulators alternate by layer).
+//                 A operand written in place into shared memory in the UMMA K-major core-matrix layout.
+//
+// Pipelining: every 256-wide layer is accumulated as two 128-column halves, half-major, each half with its own
+// "accumulator complete" mbarrier; the epilogue of half h produces two 64-column K chunks of the next layer, each with its
+// own "chunk ready" mbarrier, and the two 256-column TMEM accumulators alternate by layer.  So the epilogue of layer l
+// overlaps the second half of layer l's MMAs and the first K chunks of layer l+1's (simulated period max(T_mma, T_epi)
+// for T_epi <= 0.75 T_mma; v1, with one barrier per layer, measured T_epi + T_mma/2).
 //
 // Precision: operands are split x = hi + lo in fp16 (weights pre-scaled by 2^s per layer) and
 // each product is formed as hi*hi + lo*hi + hi*lo with fp32 accumulation ("3x" mode, fp32-grade);
-// precision == 1 drops the lo terms (speed mode).
+// PREC3 == false drops the lo terms (speed mode).
 //
-// Shared memory (1 CTA/SM): A hi/lo 2x64 KB | PE hi/lo 2x16 KB | 4 x 16 KB weight stages | 2 KB partial sums.
+// Shared memory (1 CTA/SM): A hi/lo 2x64 KB | PE hi/lo 2x16 KB | 8 x 8 KB weight stages | 2 KB partial sums.
 #include "common.cuh"
 
 namespace mnrf {
@@ -23,7 +27,7 @@ namespace {
 constexpr int TILE_M = 128;
 constexpr int NUM_THREADS = 384;
 constexpr int NUM_WSTAGES = 4;
-constexpr int WSTAGE_BYTES = 16384;
+constexpr uint32_t WSTAGE_BYTES = 2 * TC_BLOB_BYTES;  // 16 KB: tc3 = [hi,lo] of one K32 chunk; tc1 = hi of two K32 chunks
 
 constexpr uint32_t SM_A_HI = 0;
 constexpr uint32_t SM_A_LO = 65536;
@@ -35,15 +39,15 @@ constexpr uint32_t SM_BAR = SM_PART + 2048;                        // 231424
 constexpr uint32_t SM_TOTAL = SM_BAR + 256;                        // 231680 <= 232448
 
 // barrier slots (8 bytes each)
-constexpr int BAR_W_FULL = 0;    // [4]
-constexpr int BAR_W_EMPTY = 4;   // [4]
-constexpr int BAR_PE = 8;        // PE chunk written (8 warp arrivals)
-constexpr int BAR_A = 9;         // [4] A 64-column chunk written (4 warp arrivals)
-constexpr int BAR_ACC = 13;      // [2] GEMM step complete (tcgen05.commit)
-constexpr int BAR_TMEM_SLOT = 15;
+constexpr int BAR_W_FULL = 0;    // [4] (8 slots reserved)
+constexpr int BAR_W_EMPTY = 8;   // [4]
+constexpr int BAR_PE = 16;       // PE chunk written (8 warp arrivals)
+constexpr int BAR_A = 17;        // [4] A 64-column chunk written (4 warp arrivals)
+constexpr int BAR_ACC = 21;      // [4] accumulator half complete (tcgen05.commit): [buffer][half]
+constexpr int BAR_AFREE = 25;    // [4] A 64-column chunk no longer read by any issued MMA (tcgen05.commit)
+constexpr int BAR_TMEM_SLOT = 30;
 
-constexpr uint32_t IDESC_N256 = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);  // fp16 x fp16 -> fp32, K-major
-constexpr uint32_t IDESC_N128 = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t IDESC_N128 = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);  // f16 x f16 -> f32, K-major
 
 struct TcParams {
   const float* f32;        // fp32 section
@@ -51,8 +55,6 @@ struct TcParams {
   int b_trunk[8];
   int b_final, b_m0, w_m2, b_m2, w_rgb, b_rgb, headw, headb, inv_scale;
   int has_normal, has_mirror;
-  int precision;           // 1 | 3
-  int desc_swap;           // debug: swap LBO/SBO roles
   FieldIO io;
   int n_tiles;
 };
@@ -83,7 +85,7 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
 // bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU box
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try(bar, parity)) return;
-  long long t0 = clock64();
+  const long long t0 = clock64();
   while (!mbar_try(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {
       printf("mnrf field_tc: mbarrier timeout (block %d thread %d bar@%u parity %u)\n", blockIdx.x, threadIdx.x, bar,
@@ -112,7 +114,6 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -125,44 +126,73 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// wait for this thread's outstanding tcgen05.ld, then pin the destination registers behind the wait
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void pin32(uint32_t (&r)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(r[i]));
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
+}
+// one lane of a converged warp (the pattern ptxas turns into ELECT + predicated uniform-datapath instructions)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void epi_bar_sync(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
 
-// K-major, no-swizzle operand descriptor.  Core matrix = 8 rows x 16 bytes, stored as 128 contiguous bytes;
-// 8-row groups (M/N direction) are `mn_stride` bytes apart, K-adjacent core matrices `k_stride` bytes apart.
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t k_stride, uint32_t mn_stride, int swap) {
-  uint32_t lbo = swap ? mn_stride : k_stride;
-  uint32_t sbo = swap ? k_stride : mn_stride;
-  return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+// K-major, no-swizzle operand descriptor.  Core matrix = 8 rows x 16 bytes stored as 128 contiguous bytes;
+// LBO = byte distance between K-adjacent core matrices, SBO = byte distance between 8-row groups (M/N direction).
+// Both operand kinds here are 128 rows tall: LBO = 128*16 = 2048, SBO = 128; one K16 step = 4096 bytes.
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr) {
+  return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)(2048u >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
 }
 
-// x = hi + lo in fp16; two values packed per 32-bit word
-__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  __half2 h = __floats2half2_rn(a, b);
-  float2 hf = __half22float2(h);
-  __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
-  hi = *reinterpret_cast<uint32_t*>(&h);
-  lo = *reinterpret_cast<uint32_t*>(&l);
-}
-__device__ __forceinline__ float clampf16(float v) { return fminf(fmaxf(v, -60000.f), 60000.f); }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
+// ---- x = hi + lo in fp16, two values per 32-bit word (element 0 in the low half) -----------------------------------
+template <bool RELU, bool PREC3>
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  if (PREC3) {
+    // hi rounded toward zero so that the residual of a non-negative value is non-negative: both ReLUs ride on the cvt
+    if (RELU) asm("cvt.rz.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+    else      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+    const float2 hf = __half22float2(*reinterpret_cast<__half2*>(&hi));
+    if (RELU) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - hf.y), "f"(a - hf.x));
+    else      asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - hf.y), "f"(a - hf.x));
+  } else {
+    if (RELU) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+    else      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+    lo = 0;
+  }
+}
+
 // store 8 consecutive K values (one 16-byte core-matrix row) of an A-type operand, hi and lo parts
-__device__ __forceinline__ void store_a8(uint32_t hi_addr, uint32_t lo_addr, const float (&v)[8], bool with_lo) {
+template <bool RELU, bool PREC3>
+__device__ __forceinline__ void store_a8(uint32_t hi_addr, uint32_t lo_addr, const float (&v)[8]) {
   uint32_t h[4], l[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) split2(v[2 * i], v[2 * i + 1], h[i], l[i]);
+  for (int i = 0; i < 4; ++i) split2<RELU, PREC3>(v[2 * i], v[2 * i + 1], h[i], l[i]);
   st_shared_v4(hi_addr, h[0], h[1], h[2], h[3]);
-  if (with_lo) st_shared_v4(lo_addr, l[0], l[1], l[2], l[3]);
+  if (PREC3) st_shared_v4(lo_addr, l[0], l[1], l[2], l[3]);
+}
+
+// accurate sin/cos (arguments reach 2^9 * |x|): shared, not inlined 30 times
+__device__ __noinline__ float2 sincos_pe(float a) {
+  float s, c;
+  sincosf(a, &s, &c);
+  return make_float2(s, c);
 }
 
 // ---- positional encoding of one row, K range [32*HALF, 32*HALF+32) (mirror_nerf.py:33-38) ----------------
-template <int HALF>
-__device__ __forceinline__ void pe_fill(const float (&x)[3], uint32_t pe_hi, uint32_t pe_lo, uint32_t rowoff,
-                                        bool with_lo) {
+template <int HALF, bool PREC3>
+__device__ __forceinline__ void pe_fill(const float (&x)[3], uint32_t pe_hi, uint32_t pe_lo, uint32_t rowoff) {
   constexpr int K0 = 32 * HALF;
   float vals[32];
 #pragma unroll
@@ -177,10 +207,9 @@ __device__ __forceinline__ void pe_fill(const float (&x)[3], uint32_t pe_hi, uin
       const int ks = 3 + 6 * f + c, kc = ks + 3;
       const bool need_s = (ks >= K0 && ks < K0 + 32), need_c = (kc >= K0 && kc < K0 + 32);
       if (need_s || need_c) {
-        float s, co;
-        sincosf(ldexpf(x[c], f), &s, &co);  // accurate path; 2^f * x is exact
-        if (need_s) vals[ks - K0] = s;
-        if (need_c) vals[kc - K0] = co;
+        const float2 sc = sincos_pe(ldexpf(x[c], f));  // 2^f * x is exact
+        if (need_s) vals[ks - K0] = sc.x;
+        if (need_c) vals[kc - K0] = sc.y;
       }
     }
   }
@@ -189,15 +218,73 @@ __device__ __forceinline__ void pe_fill(const float (&x)[3], uint32_t pe_hi, uin
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = vals[8 * j + i];
-    uint32_t off = (uint32_t)(4 * HALF + j) * 2048u + rowoff;
-    store_a8(pe_hi + off, pe_lo + off, v, with_lo);
+    const uint32_t off = (uint32_t)(4 * HALF + j) * 2048u + rowoff;
+    store_a8<false, PREC3>(pe_hi + off, pe_lo + off, v);
   }
 }
 
+// ---- epilogue of 32 accumulator columns of one row ------------------------------------------------------------------
+template <bool RELU, bool DOTS, bool WRITE_A, bool PREC3>
+__device__ __forceinline__ void epi32(const uint32_t (&r)[32], const float4 (&b)[8], float inv, uint32_t s_hi,
+                                      uint32_t s_lo, const float4* __restrict__ hw, float (&d)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 b0 = b[2 * j], b1 = b[2 * j + 1];
+    float v[8];
+    v[0] = fmaf(__uint_as_float(r[8 * j + 0]), inv, b0.x);
+    v[1] = fmaf(__uint_as_float(r[8 * j + 1]), inv, b0.y);
+    v[2] = fmaf(__uint_as_float(r[8 * j + 2]), inv, b0.z);
+    v[3] = fmaf(__uint_as_float(r[8 * j + 3]), inv, b0.w);
+    v[4] = fmaf(__uint_as_float(r[8 * j + 4]), inv, b1.x);
+    v[5] = fmaf(__uint_as_float(r[8 * j + 5]), inv, b1.y);
+    v[6] = fmaf(__uint_as_float(r[8 * j + 6]), inv, b1.z);
+    v[7] = fmaf(__uint_as_float(r[8 * j + 7]), inv, b1.w);
+    if (DOTS) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v[i] = fmaxf(v[i], 0.f);
+        const float4 w = __ldg(hw + 8 * j + i);
+        d[0] = fmaf(v[i], w.x, d[0]); d[1] = fmaf(v[i], w.y, d[1]);
+        d[2] = fmaf(v[i], w.z, d[2]); d[3] = fmaf(v[i], w.w, d[3]);
+      }
+    }
+    if (WRITE_A) store_a8<RELU, PREC3>(s_hi + (uint32_t)j * 2048u, s_lo + (uint32_t)j * 2048u, v);
+  }
+}
+
+// 64 accumulator columns (this warp's share of a 128-column half): both TMEM loads in flight, bias prefetched
+template <bool RELU, bool DOTS, bool WRITE_A, bool PREC3>
+__device__ __forceinline__ void epi64(uint32_t tacc, const float* __restrict__ bias, float inv, uint32_t s_hi,
+                                      uint32_t s_lo, const float4* __restrict__ hw, float (&d)[4], uint32_t free_bar,
+                                      uint32_t free_parity) {
+  uint32_t ra[32], rb[32];
+  tmem_ld32(tacc, ra);
+  tmem_ld32(tacc + 32u, rb);
+  const float4* b4 = reinterpret_cast<const float4*>(bias);
+  float4 b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = __ldg(b4 + i);
+  tmem_wait_ld();
+  pin32(ra);
+  pin32(rb);
+  if (WRITE_A && free_bar != 0u) mbar_wait(free_bar, free_parity);  // in-place overwrite: wait for the chunk's last reader
+  epi32<RELU, DOTS, WRITE_A, PREC3>(ra, b, inv, s_hi, s_lo, hw, d);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = __ldg(b4 + 8 + i);
+  epi32<RELU, DOTS, WRITE_A, PREC3>(rb, b, inv, s_hi + 4u * 2048u, s_lo + 4u * 2048u, hw + 32, d);
+}
+
 // ---- step geometry --------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t acc_col(int s) { return s <= 7 ? (uint32_t)(s & 1) * 256u : (s == 8 ? 0u : (s == 9 ? 256u : 384u)); }
+// TMEM columns: trunk layers alternate [0,256) / [256,512); mirror head (step 9) -> [0,128); final (step 8) -> [128,384);
+// dir layer (step 10) -> [384,512).  Issue order: 0..7, 9, 8, 10.
+__device__ __forceinline__ uint32_t acc_col(int s, int h) {
+  return (s <= 7 ? (uint32_t)(s & 1) * 256u : (s == 9 ? 0u : (s == 8 ? 128u : 384u))) + (uint32_t)h * 128u;
+}
+__device__ __forceinline__ int acc_bar(int s, int h) { return s <= 7 ? 2 * (s & 1) + h : (s == 9 ? 0 : (s == 8 ? 1 + h : 3)); }
+__device__ __forceinline__ int step_at(int i) { return i < 8 ? i : (i == 8 ? 9 : (i == 9 ? 8 : 10)); }
 
 // ================================================================================================
+template <bool PREC3>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -206,16 +293,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
   const uint32_t bars = sbase + SM_BAR;
   auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SM_BAR + 8 * BAR_TMEM_SLOT);
-  const bool prec3 = P.precision == 3;
-  const int last_step = P.io.sigma_only ? 7 : 10;
+  const int n_issue = P.io.sigma_only ? 8 : 11;
 
   if (threadIdx.x == 0) {
     if (sbase & 127u) { printf("mnrf field_tc: unaligned dynamic smem base %u\n", sbase); __trap(); }
     for (int i = 0; i < NUM_WSTAGES; ++i) { mbar_init(bar(BAR_W_FULL + i), 1); mbar_init(bar(BAR_W_EMPTY + i), 1); }
     mbar_init(bar(BAR_PE), 8);
     for (int i = 0; i < 4; ++i) mbar_init(bar(BAR_A + i), 4);
-    mbar_init(bar(BAR_ACC + 0), 1);
-    mbar_init(bar(BAR_ACC + 1), 1);
+    for (int i = 0; i < 4; ++i) mbar_init(bar(BAR_ACC + i), 1);
+    for (int i = 0; i < 4; ++i) mbar_init(bar(BAR_AFREE + i), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -231,87 +317,92 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    // =========================== weight producer ===========================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-        for (int s = 0; s <= last_step; ++s) {
-          if (s == 9 && !P.has_mirror) continue;
-          const uint8_t* src = P.tc + tc_step_offset(s);
-          const uint32_t blob = (uint32_t)tc_blob_bytes(s);
-          const int nch = tc_step_chunks(s);
-          for (int kc = 0; kc < nch; ++kc) {
-            for (int part = 0; part < (prec3 ? 2 : 1); ++part) {
-              mbar_wait(bar(BAR_W_EMPTY + stage), phase ^ 1u);
-              mbar_expect_tx(bar(BAR_W_FULL + stage), blob);
-              bulk_g2s(sbase + SM_WST + stage * WSTAGE_BYTES, src + (size_t)(2 * kc + part) * blob, blob,
-                       bar(BAR_W_FULL + stage));
-              if (++stage == NUM_WSTAGES) { stage = 0; phase ^= 1u; }
+    // =========================== weight producer (whole warp in lock-step, one elected lane issues) ===========
+    uint32_t stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+      for (int i = 0; i < n_issue; ++i) {
+        const int s = step_at(i);
+        if (s == 9 && !P.has_mirror) continue;
+        const uint8_t* src = P.tc + tc_step_offset(s);
+        const int nst = tc_step_halves(s) * tc_step_chunks(s) / (PREC3 ? 1 : 2);  // stages of this step
+        for (int si = 0; si < nst; ++si) {
+          mbar_wait(bar(BAR_W_EMPTY + stage), phase ^ 1u);
+          if (elect_one()) {
+            const uint32_t dst = sbase + SM_WST + stage * WSTAGE_BYTES;
+            const uint32_t fb = bar(BAR_W_FULL + stage);
+            mbar_expect_tx(fb, WSTAGE_BYTES);
+            if (PREC3) {  // [hi, lo] blobs of one K32 chunk are contiguous
+              bulk_g2s(dst, src + (size_t)si * 2 * TC_BLOB_BYTES, 2 * TC_BLOB_BYTES, fb);
+            } else {      // hi blobs of two consecutive K32 chunks
+              bulk_g2s(dst, src + (size_t)(2 * si) * 2 * TC_BLOB_BYTES, TC_BLOB_BYTES, fb);
+              bulk_g2s(dst + TC_BLOB_BYTES, src + (size_t)(2 * si + 1) * 2 * TC_BLOB_BYTES, TC_BLOB_BYTES, fb);
             }
           }
+          __syncwarp();
+          if (++stage == NUM_WSTAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      uint32_t pe_phase = 0, a_phase[4] = {0, 0, 0, 0};
-      const int sw = P.desc_swap;
-      for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-        for (int s = 0; s <= last_step; ++s) {
-          if (s == 9 && !P.has_mirror) continue;
-          const int N = tc_step_n(s);
-          const uint32_t idesc = (N == 256) ? IDESC_N256 : IDESC_N128;
-          const uint32_t d_tmem = tmem + acc_col(s);
-          const int nch = tc_step_chunks(s);
-          const int n_pe = (s == 0 || s == 4) ? 2 : 0;  // leading K32 chunks that come from the PE buffer
+    // =========================== MMA issuer (whole warp in lock-step, one elected lane issues) ===========
+    uint32_t stage = 0, phase = 0;
+    uint32_t pe_phase = 0, a_phase = 0;  // a_phase: one parity bit per 64-column A chunk
+    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+      for (int i = 0; i < n_issue; ++i) {
+        const int s = step_at(i);
+        if (s == 9 && !P.has_mirror) continue;
+        const int nch = tc_step_chunks(s);
+        const int n_pe = (s == 0 || s == 4) ? 2 : 0;  // leading K32 chunks that come from the PE buffer
+        const bool a_reused = (s == 8 && P.has_mirror);  // h8 was already awaited by the mirror GEMM
+        // the epilogue of this step overwrites the A buffer in place while this step's second half is still
+        // reading it: release each 64-column chunk as soon as its last MMA has been issued
+        const bool a_release = (s >= 1 && s <= 8) && !(s == 7 && P.io.sigma_only);
+        for (int h = 0; h < tc_step_halves(s); ++h) {
+          const uint32_t d_tmem = tmem + acc_col(s, h);
           uint32_t accumulate = 0;
           for (int kc = 0; kc < nch; ++kc) {
             uint32_t a_hi, a_lo;
             if (kc < n_pe) {
-              if (s == 0 && kc == 0) { mbar_wait(bar(BAR_PE), pe_phase); pe_phase ^= 1u; tc_fence_after(); }
+              if (s == 0 && h == 0 && kc == 0) { mbar_wait(bar(BAR_PE), pe_phase); pe_phase ^= 1u; }
               a_hi = sbase + SM_PE_HI + (uint32_t)kc * 8192u;
               a_lo = sbase + SM_PE_LO + (uint32_t)kc * 8192u;
             } else {
               const int ka = kc - n_pe;  // K32 chunk inside the A buffer
-              if ((ka & 1) == 0 && s != 9) {  // first touch of a 64-column chunk of a new activation version
+              if (h == 0 && (ka & 1) == 0 && !a_reused) {  // first touch of a 64-column chunk of a new version
                 const int c = ka >> 1;
-                mbar_wait(bar(BAR_A + c), a_phase[c]); a_phase[c] ^= 1u; tc_fence_after();
+                mbar_wait(bar(BAR_A + c), (a_phase >> c) & 1u);
+                a_phase ^= 1u << c;
               }
               a_hi = sbase + SM_A_HI + (uint32_t)ka * 8192u;
               a_lo = sbase + SM_A_LO + (uint32_t)ka * 8192u;
             }
-            // ---- hi weights: A_hi*W_hi (+ A_lo*W_hi) ----
-            mbar_wait(bar(BAR_W_FULL + stage), phase);
+            const bool new_stage = PREC3 || (kc & 1) == 0;
+            const bool end_stage = PREC3 || (kc & 1) == 1;
+            if (new_stage) mbar_wait(bar(BAR_W_FULL + stage), phase);
             tc_fence_after();
-            {
-              const uint32_t b0 = sbase + SM_WST + stage * WSTAGE_BYTES;
+            const uint32_t b0 = sbase + SM_WST + stage * WSTAGE_BYTES + (PREC3 ? 0u : (uint32_t)(kc & 1) * TC_BLOB_BYTES);
+            if (elect_one()) {
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
-                const uint64_t bd = make_desc(b0 + (uint32_t)j * (uint32_t)N * 32u, (uint32_t)N * 16u, 128u, sw);
-                tc_mma(d_tmem, make_desc(a_hi + (uint32_t)j * 4096u, 2048u, 128u, sw), bd, idesc, accumulate);
+                const uint64_t bd = make_desc(b0 + (uint32_t)j * 4096u);
+                tc_mma(d_tmem, make_desc(a_hi + (uint32_t)j * 4096u), bd, IDESC_N128, accumulate);  // A_hi * W_hi
                 accumulate = 1;
-                if (prec3) tc_mma(d_tmem, make_desc(a_lo + (uint32_t)j * 4096u, 2048u, 128u, sw), bd, idesc, 1);
+                if (PREC3) tc_mma(d_tmem, make_desc(a_lo + (uint32_t)j * 4096u), bd, IDESC_N128, 1);  // A_lo * W_hi
               }
-            }
-            tc_commit(bar(BAR_W_EMPTY + stage));
-            if (++stage == NUM_WSTAGES) { stage = 0; phase ^= 1u; }
-            // ---- lo weights: A_hi*W_lo ----
-            if (prec3) {
-              mbar_wait(bar(BAR_W_FULL + stage), phase);
-              tc_fence_after();
-              const uint32_t b0 = sbase + SM_WST + stage * WSTAGE_BYTES;
+              if (PREC3) {
 #pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                const uint64_t bd = make_desc(b0 + (uint32_t)j * (uint32_t)N * 32u, (uint32_t)N * 16u, 128u, sw);
-                tc_mma(d_tmem, make_desc(a_hi + (uint32_t)j * 4096u, 2048u, 128u, sw), bd, idesc, 1);
+                for (int j = 0; j < 2; ++j)                                                            // A_hi * W_lo
+                  tc_mma(d_tmem, make_desc(a_hi + (uint32_t)j * 4096u), make_desc(b0 + TC_BLOB_BYTES + (uint32_t)j * 4096u),
+                         IDESC_N128, 1);
               }
-              tc_commit(bar(BAR_W_EMPTY + stage));
-              if (++stage == NUM_WSTAGES) { stage = 0; phase ^= 1u; }
+              if (end_stage) tc_commit(bar(BAR_W_EMPTY + stage));
+              if (a_release && h == 1 && kc >= n_pe && ((kc - n_pe) & 1) == 1) tc_commit(bar(BAR_AFREE + ((kc - n_pe) >> 1)));
+              if (kc == nch - 1) tc_commit(bar(BAR_ACC + acc_bar(s, h)));
             }
+            accumulate = 1;
+            __syncwarp();
+            if (end_stage && ++stage == NUM_WSTAGES) { stage = 0; phase ^= 1u; }
           }
-          tc_commit(bar(BAR_ACC + (s & 1)));
         }
       }
     }
@@ -319,157 +410,176 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
     // =========================== epilogue / PE warps ===========================
     const int ew = warp - 4;
     const int q = ew & 3;          // TMEM lane quarter == warp_id % 4
-    const int g = ew >> 2;         // column group
+    const int g = ew >> 2;         // 64-column group inside a 128-column half
     const int row = q * 32 + lane;
     const uint32_t rowoff = (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u;
     const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
     const float* F = P.f32;
     const float4* headw = reinterpret_cast<const float4*>(F + P.headw);
     float4* part = reinterpret_cast<float4*>(smem + SM_PART);
-    uint32_t acc_phase[2] = {0, 0};
-    auto wait_acc = [&](int s) { mbar_wait(bar(BAR_ACC + (s & 1)), acc_phase[s & 1]); acc_phase[s & 1] ^= 1u; tc_fence_after(); };
+    uint32_t acc_phase = 0;  // one parity bit per accumulator barrier
+    uint32_t free_phase = 0; // one parity bit per A-chunk release barrier
+    auto wait_acc = [&](int s, int h) {
+      const int b = acc_bar(s, h);
+      mbar_wait(bar(BAR_ACC + b), (acc_phase >> b) & 1u);
+      acc_phase ^= 1u << b;
+      tc_fence_after();
+    };
+    auto a_ready = [&](int c) {
+      tc_fence_before();
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(BAR_A + c));
+    };
+    // xyz + positional encoding of this thread's row of `tile` -> PE operand buffer
+    auto pe_tile = [&](int tile) {
+      const long long pr = (long long)tile * TILE_M + row;
+      const long long p = pr < P.io.n_points ? pr : (long long)P.io.n_points - 1;
+      float x[3];
+      if (P.io.rays != nullptr) {
+        const float* rr = P.io.rays + (p / P.io.S) * 8;
+        const float z = __ldg(P.io.z + p);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(__ldg(rr + c), __fmul_rn(__ldg(rr + 3 + c), z));
+      } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) x[c] = __ldg(P.io.x + p * P.io.x_stride + c);
+      }
+      if (g == 0) pe_fill<0, PREC3>(x, sbase + SM_PE_HI, sbase + SM_PE_LO, rowoff);
+      else        pe_fill<1, PREC3>(x, sbase + SM_PE_HI, sbase + SM_PE_LO, rowoff);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(BAR_PE));
+    };
 
+    if ((int)blockIdx.x < P.n_tiles) pe_tile(blockIdx.x);
     for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
       const long long p_raw = (long long)tile * TILE_M + row;
       const bool valid = p_raw < P.io.n_points;
       const long long p = valid ? p_raw : (long long)P.io.n_points - 1;
       const long long ray = (P.io.rays != nullptr) ? p / P.io.S : p;
-
-      // ---- xyz + positional encoding -> PE operand buffer ----
-      {
-        float x[3];
-        if (P.io.rays != nullptr) {
-          const float* rr = P.io.rays + ray * 8;
-          const float z = __ldg(P.io.z + p);
-#pragma unroll
-          for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(__ldg(rr + c), __fmul_rn(__ldg(rr + 3 + c), z));
-        } else {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) x[c] = __ldg(P.io.x + p * P.io.x_stride + c);
-        }
-        if (g == 0) pe_fill<0>(x, sbase + SM_PE_HI, sbase + SM_PE_LO, rowoff, prec3);
-        else        pe_fill<1>(x, sbase + SM_PE_HI, sbase + SM_PE_LO, rowoff, prec3);
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(BAR_PE));
-      }
-
       float o_sigma = 0.f, o_n[3] = {0.f, 0.f, 0.f}, o_mirror = 0.f, o_rgb[3] = {0.f, 0.f, 0.f};
+      float d[4] = {0.f, 0.f, 0.f, 0.f};
 
-      // ---- trunk layers 1..8 (steps 0..7) and the final linear (step 8) ----
-      for (int s = 0; s <= (P.io.sigma_only ? 7 : 8); ++s) {
-        wait_acc(s);
-        if (s == 8 && P.has_mirror) wait_acc(9);  // h8 (A buffer) is still being read by the mirror GEMM
-        const bool relu = s < 8;
-        const bool write_a = !(P.io.sigma_only && s == 7);
-        const bool dots = s == 7;
-        const float* bias = F + (s < 8 ? P.b_trunk[s] : P.b_final);
+      // ---- trunk layers 1..8 (steps 0..7) ----
+      for (int s = 0; s < 8; ++s) {
+        const float* bias = F + P.b_trunk[s] + g * 64;
         const float inv = __ldg(F + P.inv_scale + s);
-        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-        for (int ci = 0; ci < 2; ++ci) {
-          const int c = g + 2 * ci;  // 64-column chunk owned by this warp group
 #pragma unroll 1
-          for (int sub = 0; sub < 2; ++sub) {
-            const int col0 = c * 64 + sub * 32;
-            uint32_t r[32];
-            tmem_ld32(tlane + acc_col(s) + (uint32_t)col0, r);
-            tmem_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col0 + 8 * j));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + 8 * j + 4));
-              float v[8];
-              v[0] = fmaf(__uint_as_float(r[8 * j + 0]), inv, b0.x);
-              v[1] = fmaf(__uint_as_float(r[8 * j + 1]), inv, b0.y);
-              v[2] = fmaf(__uint_as_float(r[8 * j + 2]), inv, b0.z);
-              v[3] = fmaf(__uint_as_float(r[8 * j + 3]), inv, b0.w);
-              v[4] = fmaf(__uint_as_float(r[8 * j + 4]), inv, b1.x);
-              v[5] = fmaf(__uint_as_float(r[8 * j + 5]), inv, b1.y);
-              v[6] = fmaf(__uint_as_float(r[8 * j + 6]), inv, b1.z);
-              v[7] = fmaf(__uint_as_float(r[8 * j + 7]), inv, b1.w);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = relu ? fminf(fmaxf(v[i], 0.f), 60000.f) : clampf16(v[i]);
-              if (dots) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float4 hw = __ldg(headw + col0 + 8 * j + i);
-                  d0 = fmaf(v[i], hw.x, d0); d1 = fmaf(v[i], hw.y, d1);
-                  d2 = fmaf(v[i], hw.z, d2); d3 = fmaf(v[i], hw.w, d3);
-                }
-              }
-              if (write_a) {
-                const uint32_t off = (uint32_t)((col0 >> 3) + j) * 2048u + rowoff;
-                store_a8(sbase + SM_A_HI + off, sbase + SM_A_LO + off, v, prec3);
-              }
-            }
-          }
-          if (write_a) {
-            tc_fence_before();
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar(BAR_A + c));
+        for (int h = 0; h < 2; ++h) {
+          wait_acc(s, h);
+          const int c = 2 * h + g;  // 64-column chunk of the next layer's K produced by this warp
+          const uint32_t tacc = tlane + acc_col(s, h) + (uint32_t)g * 64u;
+          const uint32_t s_hi = sbase + SM_A_HI + (uint32_t)c * 16384u + rowoff;
+          const uint32_t s_lo = sbase + SM_A_LO + (uint32_t)c * 16384u + rowoff;
+          // steps >= 1 overwrite the activations their own second-half MMAs may still be reading
+          const uint32_t fb = s >= 1 ? bar(BAR_AFREE + c) : 0u;
+          const uint32_t fp = (free_phase >> c) & 1u;
+          if (s < 7) {
+            epi64<true, false, true, PREC3>(tacc, bias + h * 128, inv, s_hi, s_lo, nullptr, d, fb, fp);
+            if (s >= 1) free_phase ^= 1u << c;
+            a_ready(c);
+          } else if (!P.io.sigma_only) {
+            epi64<true, true, true, PREC3>(tacc, bias + h * 128, inv, s_hi, s_lo, headw + c * 64, d, fb, fp);
+            free_phase ^= 1u << c;
+            a_ready(c);
+          } else {
+            epi64<true, true, false, PREC3>(tacc, bias + h * 128, inv, s_hi, s_lo, headw + c * 64, d, 0u, 0u);
           }
         }
-        if (dots) {
-          // combine the two column groups' partial dot products (sigma + folded normal head)
-          if (g == 1) part[row] = make_float4(d0, d1, d2, d3);
-          epi_bar_sync(1);
-          if (g == 0) {
-            const float4 o = part[row];
-            const float4 hb = __ldg(reinterpret_cast<const float4*>(F + P.headb));
-            o_sigma = d0 + o.x + hb.x;
-            if (P.has_normal) {
-              float a = d1 + o.y + hb.y, b = d2 + o.z + hb.z, cc = d3 + o.w + hb.w;
-              float nn = sqrtf(fmaxf(a * a + b * b + cc * cc, FP32_EPS));  // utils/func.py:5-7
-              o_n[0] = a / nn; o_n[1] = b / nn; o_n[2] = cc / nn;
-            }
+        // the PE buffer is free once layer 5's MMAs are done: encode the next tile while the tensor pipe is busy
+        if (s == 5 && tile + (int)gridDim.x < P.n_tiles) pe_tile(tile + gridDim.x);
+      }
+      // combine the two column groups' partial dot products (sigma + folded normal head)
+      {
+        if (g == 1) part[row] = make_float4(d[0], d[1], d[2], d[3]);
+        epi_bar_sync(1);
+        if (g == 0) {
+          const float4 o = part[row];
+          const float4 hb = __ldg(reinterpret_cast<const float4*>(F + P.headb));
+          o_sigma = d[0] + o.x + hb.x;
+          if (P.has_normal) {
+            const float a = d[1] + o.y + hb.y, b = d[2] + o.z + hb.z, cc = d[3] + o.w + hb.w;
+            const float nn = sqrtf(fmaxf(a * a + b * b + cc * cc, FP32_EPS));  // utils/func.py:5-7
+            o_n[0] = a / nn; o_n[1] = b / nn; o_n[2] = cc / nn;
           }
-          epi_bar_sync(2);
         }
+        epi_bar_sync(2);
       }
 
       if (!P.io.sigma_only) {
         // ---- mirror head (step 9): LeakyReLU(0.01) -> Linear(128,1) -> sigmoid (mirror_nerf.py:94-99) ----
         if (P.has_mirror) {
+          wait_acc(9, 0);
           const float inv = __ldg(F + P.inv_scale + 9);
-          float d = 0.f;
-#pragma unroll 1
-          for (int sub = 0; sub < 2; ++sub) {
-            const int col0 = g * 64 + sub * 32;
-            uint32_t r[32];
-            tmem_ld32(tlane + acc_col(9) + (uint32_t)col0, r);
-            tmem_wait_ld();
+          float dm = 0.f;
+          uint32_t ra[32], rb[32];
+          tmem_ld32(tlane + acc_col(9, 0) + (uint32_t)g * 64u, ra);
+          tmem_ld32(tlane + acc_col(9, 0) + (uint32_t)g * 64u + 32u, rb);
+          tmem_wait_ld();
+          pin32(ra);
+          pin32(rb);
+          const float* bm = F + P.b_m0 + g * 64;
+          const float* wm = F + P.w_m2 + g * 64;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float v = fmaf(__uint_as_float(r[i]), inv, __ldg(F + P.b_m0 + col0 + i));
-              v = v > 0.f ? v : 0.01f * v;
-              d = fmaf(v, __ldg(F + P.w_m2 + col0 + i), d);
-            }
+          for (int i = 0; i < 32; ++i) {
+            float v = fmaf(__uint_as_float(ra[i]), inv, __ldg(bm + i));
+            v = v > 0.f ? v : 0.01f * v;
+            dm = fmaf(v, __ldg(wm + i), dm);
           }
-          if (g == 1) part[row].x = d;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float v = fmaf(__uint_as_float(rb[i]), inv, __ldg(bm + 32 + i));
+            v = v > 0.f ? v : 0.01f * v;
+            dm = fmaf(v, __ldg(wm + 32 + i), dm);
+          }
+          if (g == 1) part[row].x = dm;
           epi_bar_sync(1);
-          if (g == 0) o_mirror = sigmoidf_(d + part[row].x + __ldg(F + P.b_m2));
+          if (g == 0) o_mirror = sigmoidf_(dm + part[row].x + __ldg(F + P.b_m2));
           epi_bar_sync(2);
         }
+        // ---- final linear (step 8): f = W h8 + b, written over h8 chunk by chunk as its readers (steps 9, 8) finish ----
+        {
+          const float inv = __ldg(F + P.inv_scale + 8);
+          const float* bias = F + P.b_final + g * 64;
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            wait_acc(8, h);
+            const int c = 2 * h + g;
+            epi64<false, false, true, PREC3>(tlane + acc_col(8, h) + (uint32_t)g * 64u, bias + h * 128, inv,
+                                             sbase + SM_A_HI + (uint32_t)c * 16384u + rowoff,
+                                             sbase + SM_A_LO + (uint32_t)c * 16384u + rowoff, nullptr, d,
+                                             bar(BAR_AFREE + c), (free_phase >> c) & 1u);
+            free_phase ^= 1u << c;
+            a_ready(c);
+          }
+        }
         // ---- dir layer (step 10): relu(W_f f + [b + W_d embed(dir)]) -> rgb (mirror_nerf.py:199-204) ----
-        wait_acc(10);
+        wait_acc(10, 0);
         {
           const float inv = __ldg(F + P.inv_scale + 10);
-          const float* db = P.io.dirbias + ray * WH;
+          const float* db = P.io.dirbias + ray * WH + g * 64;
+          const float* wr = F + P.w_rgb + g * 64;
           float d0 = 0.f, d1 = 0.f, d2 = 0.f;
-#pragma unroll 1
-          for (int sub = 0; sub < 2; ++sub) {
-            const int col0 = g * 64 + sub * 32;
-            uint32_t r[32];
-            tmem_ld32(tlane + acc_col(10) + (uint32_t)col0, r);
-            tmem_wait_ld();
+          uint32_t ra[32], rb[32];
+          tmem_ld32(tlane + acc_col(10, 0) + (uint32_t)g * 64u, ra);
+          tmem_ld32(tlane + acc_col(10, 0) + (uint32_t)g * 64u + 32u, rb);
+          tmem_wait_ld();
+          pin32(ra);
+          pin32(rb);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float v = fmaxf(fmaf(__uint_as_float(r[i]), inv, __ldg(db + col0 + i)), 0.f);
-              d0 = fmaf(v, __ldg(F + P.w_rgb + col0 + i), d0);
-              d1 = fmaf(v, __ldg(F + P.w_rgb + WH + col0 + i), d1);
-              d2 = fmaf(v, __ldg(F + P.w_rgb + 2 * WH + col0 + i), d2);
-            }
+          for (int i = 0; i < 32; ++i) {
+            const float v = fmaxf(fmaf(__uint_as_float(ra[i]), inv, __ldg(db + i)), 0.f);
+            d0 = fmaf(v, __ldg(wr + i), d0);
+            d1 = fmaf(v, __ldg(wr + WH + i), d1);
+            d2 = fmaf(v, __ldg(wr + 2 * WH + i), d2);
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float v = fmaxf(fmaf(__uint_as_float(rb[i]), inv, __ldg(db + 32 + i)), 0.f);
+            d0 = fmaf(v, __ldg(wr + 32 + i), d0);
+            d1 = fmaf(v, __ldg(wr + WH + 32 + i), d1);
+            d2 = fmaf(v, __ldg(wr + 2 * WH + 32 + i), d2);
           }
           if (g == 1) part[row] = make_float4(d0, d1, d2, 0.f);
           epi_bar_sync(1);
@@ -519,7 +629,8 @@ int launch_field_tc(const mnrf_field* f, const FieldIO& io, int precision, cudaS
     int dev = 0;
     MNRF_CUDA_OK(cudaGetDevice(&dev));
     MNRF_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
+    MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
+    MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
   }
   TcParams P;
   const F32Layout& L = f->L;
@@ -529,16 +640,14 @@ int launch_field_tc(const mnrf_field* f, const FieldIO& io, int precision, cudaS
   P.b_final = L.b_final; P.b_m0 = L.b_m0; P.w_m2 = L.w_m2; P.b_m2 = L.b_m2;
   P.w_rgb = L.w_rgb; P.b_rgb = L.b_rgb; P.headw = L.headw; P.headb = L.headb; P.inv_scale = L.inv_scale;
   P.has_normal = f->has_normal; P.has_mirror = f->has_mirror;
-  P.precision = precision;
-  const char* sw = getenv("MNRF_TC_DESC_SWAP");
-  P.desc_swap = (sw != nullptr && sw[0] == '1') ? 1 : 0;
   P.io = io;
   P.n_tiles = (io.n_points + TILE_M - 1) / TILE_M;
-  int grid = P.n_tiles < num_sms ? P.n_tiles : num_sms;
+  const int grid = P.n_tiles < num_sms ? P.n_tiles : num_sms;
   // algorithmic MACs of this launch (unpadded reference layer sizes)
   const double macs = (double)io.n_points * (io.sigma_only ? (double)mnrf_macs_sigma_only() : (double)mnrf_macs_full());
   prof_begin(st);
-  k_field_tc<<<grid, NUM_THREADS, SM_TOTAL, st>>>(P);
+  if (precision == 3) k_field_tc<true><<<grid, NUM_THREADS, SM_TOTAL, st>>>(P);
+  else                k_field_tc<false><<<grid, NUM_THREADS, SM_TOTAL, st>>>(P);
   prof_end(st, 2.0 * macs);
   MNRF_LAUNCH_OK();
   return 0;

@@ -69,14 +69,18 @@ def blend_reflection(base_rgb, mask, child_rgb, child_depth, index=None):
 
 def render_rays_recursive(models, embeddings, rays, N_samples=64, use_disp=False, perturb=0, noise_std=0,
                           N_importance=0, chunk=1024 * 32, white_back=False, max_recursive_level=1,
-                          only_trace_rays_in_mirrors=None, test_time=True, _level=0, **kwargs):
+                          only_trace_rays_in_mirrors=None, test_time=True, _level=0, render_fn=None, **kwargs):
     """Eval-semantics recursion (R/eval.py:132-725): level 0 re-traces ALL rays of a batch that contains a mirror
     pixel, deeper levels only the mirror rays; `only_trace_rays_in_mirrors=True` compacts at every level (train.py
     semantics).  Returns the level-0 render_rays dict with rgb_{typ} blended plus rgb_{typ}_direct/_reflect,
-    depth_{typ}_reflect and reflect_direction."""
+    depth_{typ}_reflect and reflect_direction.  `render_fn(rays) -> dict` replaces render_rays (used by the tests to
+    check the recursion logic on a smooth stand-in field)."""
     kwargs.setdefault("compute_normal", False)
-    res = render_rays(models, embeddings, rays, N_samples, use_disp, perturb, noise_std, N_importance, chunk,
-                      white_back, test_time=test_time, **kwargs)
+    if render_fn is not None:
+        res = render_fn(rays)
+    else:
+        res = render_rays(models, embeddings, rays, N_samples, use_disp, perturb, noise_std, N_importance, chunk,
+                          white_back, test_time=test_time, **kwargs)
     typ = "fine" if (N_importance > 0 and not kwargs.get("only_one_field", False)) else "coarse"
     if f"mirror_mask_{typ}" not in res:
         return res
@@ -98,7 +102,7 @@ def render_rays_recursive(models, embeddings, rays, N_samples=64, use_disp=False
         return res
     sub = render_rays_recursive(models, embeddings, sec, N_samples, use_disp, perturb, noise_std, N_importance, chunk,
                                 white_back, max_recursive_level, only_trace_rays_in_mirrors, test_time,
-                                _level=_level + 1, **kwargs)
+                                _level=_level + 1, render_fn=render_fn, **kwargs)
     rgb, rgb_reflect, depth_reflect = blend_reflection(base, mask, sub[f"rgb_{typ}"], sub[f"depth_{typ}"], index)
     res[f"rgb_{typ}_direct"] = base
     res[f"rgb_{typ}"] = rgb

@@ -385,9 +385,69 @@ def test_recursive_render_vs_oracle(oracle, mm, params, levels):
         fn = lambda r: oracle.render_rays(params, r, 64, False, 0, 0, 128, 32768, False, test_time=True,
                                           compute_normal=False)
         want = oracle.trace_eval(fn, rays, levels)
+        # The synthetic field is chaotic (sigma head x40, 2^9 frequencies): the REFERENCE's own bounce output moves
+        # when its input rays move by one ulp.  That self-sensitivity is the noise floor our deviation is judged by.
+        rays_ulp = rays.clone()
+        rays_ulp[:, :6] = torch.nextafter(rays_ulp[:, :6], torch.full_like(rays_ulp[:, :6], 10.0))
+        want_ulp = oracle.trace_eval(fn, rays_ulp, levels)
     assert set(want) <= set(got), sorted(set(want) - set(got))
     flips = float((got["mirror_mask_fine"].cpu() != want["mirror_mask_fine"]).float().mean())
     assert flips <= 0.03
-    same = (got["mirror_mask_fine"].cpu() == want["mirror_mask_fine"])
+    # level-0 quantities are not amplified by the bounce: tight
+    assert_close_dist(got["rgb_fine_direct"].cpu(), want["rgb_fine_direct"], f"bounce{levels} direct")
+    assert_close_dist(got["depth_fine"].cpu(), want["depth_fine"], f"bounce{levels} depth")
+    same = (got["mirror_mask_fine"].cpu() == want["mirror_mask_fine"]) & \
+           (want_ulp["mirror_mask_fine"] == want["mirror_mask_fine"])
     for k in ("rgb_fine", "rgb_fine_reflect", "depth_fine_reflect"):
-        assert_close_dist(got[k].cpu()[same], want[k][same], f"bounce{levels} {k}", median=2e-4, frac=0.08)
+        ours = err_stats(got[k].cpu()[same], want[k][same])
+        floor = err_stats(want_ulp[k][same], want[k][same])
+        msg = fmt_stats(f"bounce{levels} {k} ours", ours) + " || " + fmt_stats("reference +1ulp", floor)
+        assert ours["median"] <= max(2e-4, 2.0 * floor["median"]), msg
+        assert ours["frac"] <= max(0.03, 1.5 * floor["frac"] + 0.03), msg
+
+
+@pytest.mark.parametrize("levels,only_mirror", [(1, None), (2, None), (2, True)])
+def test_recursion_logic_on_smooth_field(oracle, levels, only_mirror):
+    """The recursion driver itself (threshold, reflect, stable compaction, recursion depth, blend) against the oracle's
+    restatement of eval.py / train.py, with a smooth analytic stand-in for render_rays so nothing is chaotic."""
+    from mirror_nerf_b200.trace import render_rays_recursive
+
+    def fake(r):
+        o, d = r[:, :3], r[:, 3:6]
+        depth = 1.0 + 0.5 * torch.sin(o.sum(-1)) ** 2
+        return {"rgb_fine": 0.5 + 0.5 * torch.sin(o * 1.3 + d * 0.7),
+                "depth_fine": depth,
+                "mirror_mask_fine": 0.5 + 0.5 * torch.sin(3.0 * o[:, 0] + d[:, 1]),
+                "surface_normal_fine": torch.stack([torch.cos(o[:, 1]), torch.sin(o[:, 2]), 0.3 + d[:, 0] ** 2], -1),
+                "x_surface_fine": o + d * depth[:, None]}
+
+    gen = torch.Generator().manual_seed(31)
+    rays = torch.cat([torch.randn(3000, 6, generator=gen), torch.full((3000, 1), 0.05), torch.full((3000, 1), 8.0)], 1)
+    got = render_rays_recursive(None, None, rays.cuda(), 64, False, 0, 0, 128, 32768, False,
+                                max_recursive_level=levels, only_trace_rays_in_mirrors=only_mirror,
+                                render_fn=lambda r: {k: v.contiguous() for k, v in fake(r).items()})
+    if only_mirror is None:
+        want = oracle.trace_eval(fake, rays, levels)
+    else:  # train.py semantics: compact at every level
+        def trace_train(r, level=0):
+            res = fake(r)
+            m = res["mirror_mask_fine"]
+            m[m > 0.5] = 1
+            m[m < 0.5] = 0
+            mb = m.bool()
+            if bool(mb.any()) and level < levels:
+                sec, _ = oracle.reflect_rays(r, res["x_surface_fine"], res["surface_normal_fine"])
+                sub = trace_train(sec[mb], level + 1)
+                refl = res["rgb_fine"].clone()
+                refl[mb] = sub["rgb_fine"]
+                m3 = mb.float()[:, None]
+                res["rgb_fine"] = m3 * refl + (1 - m3) * res["rgb_fine"]
+            return res
+        want = trace_train(rays)
+    assert torch.equal(got["mirror_mask_fine"].cpu(), want["mirror_mask_fine"])
+    assert_close_dist(got["rgb_fine"].cpu(), want["rgb_fine"], "logic rgb", median=1e-6, frac=0.0, p99=1e-4)
+    if only_mirror is None:
+        assert_close_dist(got["rgb_fine_reflect"].cpu(), want["rgb_fine_reflect"], "logic reflect", median=1e-6,
+                          frac=0.0, p99=1e-4)
+        assert_close_dist(got["depth_fine_reflect"].cpu(), want["depth_fine_reflect"], "logic depth_reflect",
+                          median=1e-6, frac=0.0, p99=1e-4)
