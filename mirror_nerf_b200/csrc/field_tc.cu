@@ -154,6 +154,22 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr) {
   return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)(2048u >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
 }
 
+// All operands share the descriptor's high word (SBO = 128 B, descriptor version 1); the low word is
+// (address >> 4) | (LBO >> 4) << 16, so stepping through an operand is an integer add in 16-byte units
+// (K16 step = 256, K32 chunk = 512, K64 chunk = 1024).
+constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t addr) { return ((addr >> 4) & 0x3FFFu) | ((2048u >> 4) << 16); }
+__device__ __forceinline__ void tc_mma2(uint32_t d_tmem, uint32_t a_lo32, uint32_t b_lo32, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %4};\n\t"
+      "mov.b64 db, {%2, %4};\n\t"
+      "setp.ne.b32 p, %3, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo32), "r"(b_lo32), "r"(accumulate), "r"(DESC_HI), "r"(IDESC_N128)
+      : "memory");
+}
+
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
 // ---- x = hi + lo in fp16, two values per 32-bit word (element 0 in the low half) -----------------------------------
@@ -347,61 +363,81 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
     // =========================== MMA issuer (whole warp in lock-step, one elected lane issues) ===========
     uint32_t stage = 0, phase = 0;
     uint32_t pe_phase = 0, a_phase = 0;  // a_phase: one parity bit per 64-column A chunk
+    const uint32_t dl_a_hi = desc_lo(sbase + SM_A_HI), dl_a_lo = desc_lo(sbase + SM_A_LO);
+    const uint32_t dl_pe_hi = desc_lo(sbase + SM_PE_HI), dl_pe_lo = desc_lo(sbase + SM_PE_LO);
+    const uint32_t dl_w = desc_lo(sbase + SM_WST);
     for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
       for (int i = 0; i < n_issue; ++i) {
         const int s = step_at(i);
         if (s == 9 && !P.has_mirror) continue;
-        const int nch = tc_step_chunks(s);
-        const int n_pe = (s == 0 || s == 4) ? 2 : 0;  // leading K32 chunks that come from the PE buffer
-        const bool a_reused = (s == 8 && P.has_mirror);  // h8 was already awaited by the mirror GEMM
+        const int npairs = tc_step_chunks(s) >> 1;           // K64 chunks (= 64-column A chunks) of this step
+        const int pe_pairs = (s == 0 || s == 4) ? 1 : 0;     // the leading K64 chunk comes from the PE buffer
+        const bool a_reused = (s == 8 && P.has_mirror);      // h8 was already awaited by the mirror GEMM
         // the epilogue of this step overwrites the A buffer in place while this step's second half is still
         // reading it: release each 64-column chunk as soon as its last MMA has been issued
         const bool a_release = (s >= 1 && s <= 8) && !(s == 7 && P.io.sigma_only);
-        for (int h = 0; h < tc_step_halves(s); ++h) {
+        const int nhalves = tc_step_halves(s);
+        for (int h = 0; h < nhalves; ++h) {
           const uint32_t d_tmem = tmem + acc_col(s, h);
+          const uint32_t acc_done = bar(BAR_ACC + acc_bar(s, h));
+          const bool release = a_release && h == nhalves - 1;
           uint32_t accumulate = 0;
-          for (int kc = 0; kc < nch; ++kc) {
-            uint32_t a_hi, a_lo;
-            if (kc < n_pe) {
-              if (s == 0 && h == 0 && kc == 0) { mbar_wait(bar(BAR_PE), pe_phase); pe_phase ^= 1u; }
-              a_hi = sbase + SM_PE_HI + (uint32_t)kc * 8192u;
-              a_lo = sbase + SM_PE_LO + (uint32_t)kc * 8192u;
+          for (int kp = 0; kp < npairs; ++kp) {
+            // descriptor low words (16-byte units) of the A operand's hi / lo parts for this K64 chunk
+            uint32_t ah, al;
+            const int c = kp - pe_pairs;
+            if (c < 0) {
+              if (s == 0 && h == 0) { mbar_wait(bar(BAR_PE), pe_phase); pe_phase ^= 1u; }
+              ah = dl_pe_hi; al = dl_pe_lo;
             } else {
-              const int ka = kc - n_pe;  // K32 chunk inside the A buffer
-              if (h == 0 && (ka & 1) == 0 && !a_reused) {  // first touch of a 64-column chunk of a new version
-                const int c = ka >> 1;
+              if (h == 0 && !a_reused) {  // first touch of a 64-column chunk of a new activation version
                 mbar_wait(bar(BAR_A + c), (a_phase >> c) & 1u);
                 a_phase ^= 1u << c;
               }
-              a_hi = sbase + SM_A_HI + (uint32_t)ka * 8192u;
-              a_lo = sbase + SM_A_LO + (uint32_t)ka * 8192u;
+              ah = dl_a_hi + (uint32_t)c * 1024u; al = dl_a_lo + (uint32_t)c * 1024u;
             }
-            const bool new_stage = PREC3 || (kc & 1) == 0;
-            const bool end_stage = PREC3 || (kc & 1) == 1;
-            if (new_stage) mbar_wait(bar(BAR_W_FULL + stage), phase);
-            tc_fence_after();
-            const uint32_t b0 = sbase + SM_WST + stage * WSTAGE_BYTES + (PREC3 ? 0u : (uint32_t)(kc & 1) * TC_BLOB_BYTES);
-            if (elect_one()) {
+            const bool last = kp == npairs - 1;
+            if (PREC3) {
 #pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                const uint64_t bd = make_desc(b0 + (uint32_t)j * 4096u);
-                tc_mma(d_tmem, make_desc(a_hi + (uint32_t)j * 4096u), bd, IDESC_N128, accumulate);  // A_hi * W_hi
-                accumulate = 1;
-                if (PREC3) tc_mma(d_tmem, make_desc(a_lo + (uint32_t)j * 4096u), bd, IDESC_N128, 1);  // A_lo * W_hi
+              for (int q = 0; q < 2; ++q) {  // one 16 KB stage per K32 chunk: [W_hi | W_lo]
+                mbar_wait(bar(BAR_W_FULL + stage), phase);
+                tc_fence_after();
+                const uint32_t wb = dl_w + stage * 1024u;
+                const uint32_t a0 = ah + (uint32_t)q * 512u, l0 = al + (uint32_t)q * 512u;
+                if (elect_one()) {
+                  tc_mma2(d_tmem, a0, wb, accumulate);            // A_hi * W_hi  (k 0..15)
+                  tc_mma2(d_tmem, l0, wb, 1u);                    // A_lo * W_hi
+                  tc_mma2(d_tmem, a0 + 256u, wb + 256u, 1u);      // (k 16..31)
+                  tc_mma2(d_tmem, l0 + 256u, wb + 256u, 1u);
+                  tc_mma2(d_tmem, a0, wb + 512u, 1u);             // A_hi * W_lo
+                  tc_mma2(d_tmem, a0 + 256u, wb + 768u, 1u);
+                  tc_commit(bar(BAR_W_EMPTY + stage));
+                  if (q == 1) {
+                    if (release && c >= 0) tc_commit(bar(BAR_AFREE + c));
+                    if (last) tc_commit(acc_done);
+                  }
+                }
+                accumulate = 1u;
+                __syncwarp();
+                if (++stage == NUM_WSTAGES) { stage = 0; phase ^= 1u; }
               }
-              if (PREC3) {
-#pragma unroll
-                for (int j = 0; j < 2; ++j)                                                            // A_hi * W_lo
-                  tc_mma(d_tmem, make_desc(a_hi + (uint32_t)j * 4096u), make_desc(b0 + TC_BLOB_BYTES + (uint32_t)j * 4096u),
-                         IDESC_N128, 1);
+            } else {
+              mbar_wait(bar(BAR_W_FULL + stage), phase);  // one 16 KB stage per K64 chunk: W_hi of two K32 chunks
+              tc_fence_after();
+              const uint32_t wb = dl_w + stage * 1024u;
+              if (elect_one()) {
+                tc_mma2(d_tmem, ah, wb, accumulate);
+                tc_mma2(d_tmem, ah + 256u, wb + 256u, 1u);
+                tc_mma2(d_tmem, ah + 512u, wb + 512u, 1u);
+                tc_mma2(d_tmem, ah + 768u, wb + 768u, 1u);
+                tc_commit(bar(BAR_W_EMPTY + stage));
+                if (release && c >= 0) tc_commit(bar(BAR_AFREE + c));
+                if (last) tc_commit(acc_done);
               }
-              if (end_stage) tc_commit(bar(BAR_W_EMPTY + stage));
-              if (a_release && h == 1 && kc >= n_pe && ((kc - n_pe) & 1) == 1) tc_commit(bar(BAR_AFREE + ((kc - n_pe) >> 1)));
-              if (kc == nch - 1) tc_commit(bar(BAR_ACC + acc_bar(s, h)));
+              accumulate = 1u;
+              __syncwarp();
+              if (++stage == NUM_WSTAGES) { stage = 0; phase ^= 1u; }
             }
-            accumulate = 1;
-            __syncwarp();
-            if (end_stage && ++stage == NUM_WSTAGES) { stage = 0; phase ^= 1u; }
           }
         }
       }
