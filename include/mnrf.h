@@ -204,6 +204,9 @@ int64_t mnrf_launch_count(void);
  * (2 * points * mnrf_macs_*()) and count, then clears the log. */
 int mnrf_profile_enable(int on);
 int mnrf_profile_collect(double* total_ms, double* total_flops, int64_t* launches);
+/* Bring-up aid: CTA 0 of the tcgen05 field kernel logs (clock64, tag) pairs into buf = uint64[1 + 2*capacity]
+ * (buf[0] = event count; zero it first).  NULL disables. */
+int mnrf_debug_set_trace(void* buf, int64_t capacity_events);
 /* algorithmic MACs per point (unpadded layer dims): full forward / sigma-only+pred-normal */
 int64_t mnrf_macs_full(void);
 int64_t mnrf_macs_sigma_only(void);

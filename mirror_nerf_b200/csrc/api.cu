@@ -105,6 +105,10 @@ int mnrf_profile_collect(double* total_ms, double* total_flops, int64_t* launche
   g_prof.clear();
   return 0;
 }
+int mnrf_debug_set_trace(void* buf, int64_t capacity_events) {
+  set_tc_trace(reinterpret_cast<unsigned long long*>(buf), (unsigned int)capacity_events);
+  return 0;
+}
 int64_t mnrf_macs_full(void) {
   // trunk 491,264 + colour 102,144 + normal 33,152 + mirror 32,896
   return 659456;

@@ -192,6 +192,7 @@ int launch_blend(const float* base, const float* mask, const float* child_rgb, c
                  const int* index, int n, float* rgb_out, float* rgb_reflect, float* depth_reflect, cudaStream_t st);
 
 int launch_field_fp32(const mnrf_field* f, const FieldIO& io, cudaStream_t st);
+void set_tc_trace(unsigned long long* buf, unsigned int cap);
 int launch_field_tc(const mnrf_field* f, const FieldIO& io, int precision /*1|3*/, cudaStream_t st);
 
 }  // namespace mnrf

@@ -26,6 +26,10 @@ namespace {
 
 constexpr int TILE_M = 128;
 constexpr int NUM_THREADS = 384;
+// warp 0: weight producer; warp 1: MMA issuer; warps 4..11: epilogue/PE (TMEM lane quarter = warp % 4).
+// (Measured: putting the issuer at the highest warp id of its scheduler partition is 7-16 % slower.)
+constexpr int WARP_PRODUCER = 0;
+constexpr int WARP_MMA = 1;
 constexpr int NUM_WSTAGES = 4;
 constexpr uint32_t WSTAGE_BYTES = 2 * TC_BLOB_BYTES;  // 16 KB: tc3 = [hi,lo] of one K32 chunk; tc1 = hi of two K32 chunks
 
@@ -57,7 +61,29 @@ struct TcParams {
   int has_normal, has_mirror;
   FieldIO io;
   int n_tiles;
+  unsigned long long* trace;  // optional device-side event trace of CTA 0: [count, (clock, tag)...]
+  unsigned int trace_cap;
+  int debug;  // timing experiments (MNRF_TC_DEBUG): 1 = 16-byte weight copies, 2 = no MMA issue, 4 = no epilogue math
 };
+
+// device-side tracing (mnrf_debug_set_trace): one lane per warp of CTA 0 logs (clock64, who|event|a|b)
+__device__ __forceinline__ void trace_ev(const TcParams& P, int lane, int who, int ev, int a, int b) {
+#ifdef MNRF_TC_TRACE
+  if (P.trace != nullptr && blockIdx.x == 0 && lane == 0) {
+    const unsigned long long i = atomicAdd(P.trace, 1ull);
+    if (i < P.trace_cap) {
+      P.trace[1 + 2 * i] = (unsigned long long)clock64();
+      P.trace[2 + 2 * i] = ((unsigned long long)who << 24) | ((unsigned long long)ev << 16) | ((unsigned long long)a << 8) | (unsigned long long)b;
+    }
+  }
+#endif
+}
+// timing-experiment knobs (MNRF_TC_DEBUG) are compiled in only for bring-up builds (make EXTRA=-DMNRF_TC_TRACE)
+#ifdef MNRF_TC_TRACE
+#define MNRF_DBG(P, bit) ((P).debug & (bit))
+#else
+#define MNRF_DBG(P, bit) 0
+#endif
 
 // ---- PTX wrappers --------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -320,7 +346,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
     for (int i = 0; i < 4; ++i) mbar_init(bar(BAR_AFREE + i), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
+  if (warp == WARP_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32((const void*)tmem_slot)),
                  "r"(512)
@@ -332,7 +358,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == WARP_PRODUCER) {
     // =========================== weight producer (whole warp in lock-step, one elected lane issues) ===========
     uint32_t stage = 0, phase = 0;
     for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
@@ -346,10 +372,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
           if (elect_one()) {
             const uint32_t dst = sbase + SM_WST + stage * WSTAGE_BYTES;
             const uint32_t fb = bar(BAR_W_FULL + stage);
-            mbar_expect_tx(fb, WSTAGE_BYTES);
-            if (PREC3) {  // [hi, lo] blobs of one K32 chunk are contiguous
+            if (MNRF_DBG(P, 1)) {
+              mbar_expect_tx(fb, 16);
+              bulk_g2s(dst, src, 16, fb);
+            } else if (PREC3) {  // [hi, lo] blobs of one K32 chunk are contiguous
+              mbar_expect_tx(fb, WSTAGE_BYTES);
               bulk_g2s(dst, src + (size_t)si * 2 * TC_BLOB_BYTES, 2 * TC_BLOB_BYTES, fb);
             } else {      // hi blobs of two consecutive K32 chunks
+              mbar_expect_tx(fb, WSTAGE_BYTES);
               bulk_g2s(dst, src + (size_t)(2 * si) * 2 * TC_BLOB_BYTES, TC_BLOB_BYTES, fb);
               bulk_g2s(dst + TC_BLOB_BYTES, src + (size_t)(2 * si + 1) * 2 * TC_BLOB_BYTES, TC_BLOB_BYTES, fb);
             }
@@ -359,7 +389,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == WARP_MMA) {
     // =========================== MMA issuer (whole warp in lock-step, one elected lane issues) ===========
     uint32_t stage = 0, phase = 0;
     uint32_t pe_phase = 0, a_phase = 0;  // a_phase: one parity bit per 64-column A chunk
@@ -382,6 +412,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
           const uint32_t acc_done = bar(BAR_ACC + acc_bar(s, h));
           const bool release = a_release && h == nhalves - 1;
           uint32_t accumulate = 0;
+          trace_ev(P, lane, 1, 1, s, h);
           for (int kp = 0; kp < npairs; ++kp) {
             // descriptor low words (16-byte units) of the A operand's hi / lo parts for this K64 chunk
             uint32_t ah, al;
@@ -393,43 +424,57 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
               if (h == 0 && !a_reused) {  // first touch of a 64-column chunk of a new activation version
                 mbar_wait(bar(BAR_A + c), (a_phase >> c) & 1u);
                 a_phase ^= 1u << c;
+                trace_ev(P, lane, 1, 2, s, c);
               }
               ah = dl_a_hi + (uint32_t)c * 1024u; al = dl_a_lo + (uint32_t)c * 1024u;
             }
             const bool last = kp == npairs - 1;
+            if (last) trace_ev(P, lane, 1, 3, s, h);
             if (PREC3) {
-#pragma unroll
-              for (int q = 0; q < 2; ++q) {  // one 16 KB stage per K32 chunk: [W_hi | W_lo]
-                mbar_wait(bar(BAR_W_FULL + stage), phase);
-                tc_fence_after();
-                const uint32_t wb = dl_w + stage * 1024u;
-                const uint32_t a0 = ah + (uint32_t)q * 512u, l0 = al + (uint32_t)q * 512u;
-                if (elect_one()) {
-                  tc_mma2(d_tmem, a0, wb, accumulate);            // A_hi * W_hi  (k 0..15)
-                  tc_mma2(d_tmem, l0, wb, 1u);                    // A_lo * W_hi
-                  tc_mma2(d_tmem, a0 + 256u, wb + 256u, 1u);      // (k 16..31)
-                  tc_mma2(d_tmem, l0 + 256u, wb + 256u, 1u);
-                  tc_mma2(d_tmem, a0, wb + 512u, 1u);             // A_hi * W_lo
-                  tc_mma2(d_tmem, a0 + 256u, wb + 768u, 1u);
-                  tc_commit(bar(BAR_W_EMPTY + stage));
-                  if (q == 1) {
-                    if (release && c >= 0) tc_commit(bar(BAR_AFREE + c));
-                    if (last) tc_commit(acc_done);
-                  }
+              // two 16 KB stages ([W_hi | W_lo] of one K32 chunk each) per K64 chunk, issued from one elected block
+              const uint32_t st0 = stage, ph0 = phase;
+              if (++stage == NUM_WSTAGES) { stage = 0; phase ^= 1u; }
+              const uint32_t st1 = stage, ph1 = phase;
+              if (++stage == NUM_WSTAGES) { stage = 0; phase ^= 1u; }
+              mbar_wait(bar(BAR_W_FULL + st0), ph0);
+              mbar_wait(bar(BAR_W_FULL + st1), ph1);
+              tc_fence_after();
+              const uint32_t w0 = dl_w + st0 * 1024u, w1 = dl_w + st1 * 1024u;
+              if (elect_one()) {
+                if (!(MNRF_DBG(P, 2))) {
+                  tc_mma2(d_tmem, ah, w0, accumulate);                 // A_hi * W_hi  (k 0..15)
+                  tc_mma2(d_tmem, al, w0, 1u);                         // A_lo * W_hi
+                  tc_mma2(d_tmem, ah + 256u, w0 + 256u, 1u);           // (k 16..31)
+                  tc_mma2(d_tmem, al + 256u, w0 + 256u, 1u);
+                  tc_mma2(d_tmem, ah, w0 + 512u, 1u);                  // A_hi * W_lo
+                  tc_mma2(d_tmem, ah + 256u, w0 + 768u, 1u);
                 }
-                accumulate = 1u;
-                __syncwarp();
-                if (++stage == NUM_WSTAGES) { stage = 0; phase ^= 1u; }
+                tc_commit(bar(BAR_W_EMPTY + st0));
+                if (!(MNRF_DBG(P, 2))) {
+                  tc_mma2(d_tmem, ah + 512u, w1, 1u);                  // (k 32..47)
+                  tc_mma2(d_tmem, al + 512u, w1, 1u);
+                  tc_mma2(d_tmem, ah + 768u, w1 + 256u, 1u);           // (k 48..63)
+                  tc_mma2(d_tmem, al + 768u, w1 + 256u, 1u);
+                  tc_mma2(d_tmem, ah + 512u, w1 + 512u, 1u);
+                  tc_mma2(d_tmem, ah + 768u, w1 + 768u, 1u);
+                }
+                tc_commit(bar(BAR_W_EMPTY + st1));
+                if (release && c >= 0) tc_commit(bar(BAR_AFREE + c));
+                if (last) tc_commit(acc_done);
               }
+              accumulate = 1u;
+              __syncwarp();
             } else {
               mbar_wait(bar(BAR_W_FULL + stage), phase);  // one 16 KB stage per K64 chunk: W_hi of two K32 chunks
               tc_fence_after();
               const uint32_t wb = dl_w + stage * 1024u;
               if (elect_one()) {
+                if (!(MNRF_DBG(P, 2))) {
                 tc_mma2(d_tmem, ah, wb, accumulate);
                 tc_mma2(d_tmem, ah + 256u, wb + 256u, 1u);
                 tc_mma2(d_tmem, ah + 512u, wb + 512u, 1u);
                 tc_mma2(d_tmem, ah + 768u, wb + 768u, 1u);
+                }
                 tc_commit(bar(BAR_W_EMPTY + stage));
                 if (release && c >= 0) tc_commit(bar(BAR_AFREE + c));
                 if (last) tc_commit(acc_done);
@@ -460,15 +505,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
       mbar_wait(bar(BAR_ACC + b), (acc_phase >> b) & 1u);
       acc_phase ^= 1u << b;
       tc_fence_after();
+      if (q == 0) trace_ev(P, lane, 4 + g, 10, s, h);
     };
     auto a_ready = [&](int c) {
       tc_fence_before();
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(BAR_A + c));
+      if (q == 0) trace_ev(P, lane, 4 + g, 11, c, 0);
     };
     // xyz + positional encoding of this thread's row of `tile` -> PE operand buffer
     auto pe_tile = [&](int tile) {
+      if (q == 0) trace_ev(P, lane, 4 + g, 12, 0, 0);
       const long long pr = (long long)tile * TILE_M + row;
       const long long p = pr < P.io.n_points ? pr : (long long)P.io.n_points - 1;
       float x[3];
@@ -486,6 +534,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(BAR_PE));
+      if (q == 0) trace_ev(P, lane, 4 + g, 13, 0, 0);
     };
 
     if ((int)blockIdx.x < P.n_tiles) pe_tile(blockIdx.x);
@@ -511,7 +560,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
           // steps >= 1 overwrite the activations their own second-half MMAs may still be reading
           const uint32_t fb = s >= 1 ? bar(BAR_AFREE + c) : 0u;
           const uint32_t fp = (free_phase >> c) & 1u;
-          if (s < 7) {
+          if (MNRF_DBG(P, 4)) {
+            if (s >= 1 && !(s == 7 && P.io.sigma_only)) free_phase ^= 1u << c;
+            if (!(s == 7 && P.io.sigma_only)) a_ready(c);
+          } else if (s < 7) {
             epi64<true, false, true, PREC3>(tacc, bias + h * 128, inv, s_hi, s_lo, nullptr, d, fb, fp);
             if (s >= 1) free_phase ^= 1u << c;
             a_ready(c);
@@ -630,6 +682,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
       }
 
       // ---- write the point record ----
+      if (q == 0) trace_ev(P, lane, 4 + g, 14, 0, 0);
       tc_fence_before();
       if (g == 0 && valid) {
         if (P.io.sigma_out != nullptr) P.io.sigma_out[p_raw] = o_sigma;
@@ -646,13 +699,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 1) {
+  if (warp == WARP_MMA) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
   }
 }
 
 }  // namespace
+
+static unsigned long long* g_trace_buf = nullptr;
+static unsigned int g_trace_cap = 0;
+void set_tc_trace(unsigned long long* buf, unsigned int cap) { g_trace_buf = buf; g_trace_cap = cap; }
 
 int launch_field_tc(const mnrf_field* f, const FieldIO& io, int precision, cudaStream_t st) {
   if (io.n_points <= 0) return 0;
@@ -677,6 +734,10 @@ int launch_field_tc(const mnrf_field* f, const FieldIO& io, int precision, cudaS
   P.w_rgb = L.w_rgb; P.b_rgb = L.b_rgb; P.headw = L.headw; P.headb = L.headb; P.inv_scale = L.inv_scale;
   P.has_normal = f->has_normal; P.has_mirror = f->has_mirror;
   P.io = io;
+  P.trace = g_trace_buf;
+  P.trace_cap = g_trace_cap;
+  const char* dbg = getenv("MNRF_TC_DEBUG");
+  P.debug = dbg != nullptr ? atoi(dbg) : 0;
   P.n_tiles = (io.n_points + TILE_M - 1) / TILE_M;
   const int grid = P.n_tiles < num_sms ? P.n_tiles : num_sms;
   // algorithmic MACs of this launch (unpadded reference layer sizes)
