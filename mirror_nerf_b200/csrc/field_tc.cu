@@ -30,7 +30,7 @@ constexpr int NUM_THREADS = 384;
 // (Measured: putting the issuer at the highest warp id of its scheduler partition is 7-16 % slower.)
 constexpr int WARP_PRODUCER = 0;
 constexpr int WARP_MMA = 1;
-constexpr int NUM_WSTAGES = 4;
+constexpr int NUM_WSTAGES = 4;      // 3x mode; the 1x mode also uses the idle A_lo region: 8 stages
 constexpr uint32_t WSTAGE_BYTES = 2 * TC_BLOB_BYTES;  // 16 KB: tc3 = [hi,lo] of one K32 chunk; tc1 = hi of two K32 chunks
 
 constexpr uint32_t SM_A_HI = 0;
@@ -66,15 +66,16 @@ struct TcParams {
   int debug;  // timing experiments (MNRF_TC_DEBUG): 1 = 16-byte weight copies, 2 = no MMA issue, 4 = no epilogue math
 };
 
-// device-side tracing (mnrf_debug_set_trace): one lane per warp of CTA 0 logs (clock64, who|event|a|b)
-__device__ __forceinline__ void trace_ev(const TcParams& P, int lane, int who, int ev, int a, int b) {
+// device-side tracing (mnrf_debug_set_trace): lane 0 of a warp of CTA 0 logs (clock64, tag) with plain stores into its own
+// region of the buffer (no atomics, so the perturbation is one clock read + one store): region r = who, 8192 events each
+struct TraceCtx { unsigned int n; };
+__device__ __forceinline__ void trace_ev(const TcParams& P, TraceCtx& tc, int lane, int who, int ev, int a, int b) {
 #ifdef MNRF_TC_TRACE
-  if (P.trace != nullptr && blockIdx.x == 0 && lane == 0) {
-    const unsigned long long i = atomicAdd(P.trace, 1ull);
-    if (i < P.trace_cap) {
-      P.trace[1 + 2 * i] = (unsigned long long)clock64();
-      P.trace[2 + 2 * i] = ((unsigned long long)who << 24) | ((unsigned long long)ev << 16) | ((unsigned long long)a << 8) | (unsigned long long)b;
-    }
+  if (P.trace != nullptr && blockIdx.x == 0 && lane == 0 && tc.n < 8192u) {
+    unsigned long long* r = P.trace + 1 + (size_t)who * 2 * 8192 + 2 * tc.n;
+    r[0] = (unsigned long long)clock64();
+    r[1] = ((unsigned long long)who << 24) | ((unsigned long long)ev << 16) | ((unsigned long long)a << 8) | (unsigned long long)b;
+    ++tc.n;
   }
 #endif
 }
@@ -336,10 +337,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
   auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SM_BAR + 8 * BAR_TMEM_SLOT);
   const int n_issue = P.io.sigma_only ? 8 : 11;
+  constexpr uint32_t NST = PREC3 ? NUM_WSTAGES : 8;  // weight stages (the 1x mode leaves the A_lo region free)
+  auto stage_addr = [&](uint32_t st) { return sbase + (st < 4u ? SM_WST + st * WSTAGE_BYTES : SM_A_LO + (st - 4u) * WSTAGE_BYTES); };
 
   if (threadIdx.x == 0) {
     if (sbase & 127u) { printf("mnrf field_tc: unaligned dynamic smem base %u\n", sbase); __trap(); }
-    for (int i = 0; i < NUM_WSTAGES; ++i) { mbar_init(bar(BAR_W_FULL + i), 1); mbar_init(bar(BAR_W_EMPTY + i), 1); }
+    for (int i = 0; i < 8; ++i) { mbar_init(bar(BAR_W_FULL + i), 1); mbar_init(bar(BAR_W_EMPTY + i), 1); }
     mbar_init(bar(BAR_PE), 8);
     for (int i = 0; i < 4; ++i) mbar_init(bar(BAR_A + i), 4);
     for (int i = 0; i < 4; ++i) mbar_init(bar(BAR_ACC + i), 1);
@@ -370,32 +373,40 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
         for (int si = 0; si < nst; ++si) {
           mbar_wait(bar(BAR_W_EMPTY + stage), phase ^ 1u);
           if (elect_one()) {
-            const uint32_t dst = sbase + SM_WST + stage * WSTAGE_BYTES;
+            const uint32_t dst = stage_addr(stage);
             const uint32_t fb = bar(BAR_W_FULL + stage);
             if (MNRF_DBG(P, 1)) {
               mbar_expect_tx(fb, 16);
               bulk_g2s(dst, src, 16, fb);
             } else if (PREC3) {  // [hi, lo] blobs of one K32 chunk are contiguous
               mbar_expect_tx(fb, WSTAGE_BYTES);
-              bulk_g2s(dst, src + (size_t)si * 2 * TC_BLOB_BYTES, 2 * TC_BLOB_BYTES, fb);
+              const uint8_t* g = src + (size_t)si * 2 * TC_BLOB_BYTES;
+#pragma unroll
+              for (int piece = 0; piece < 4; ++piece)  // four 4 KB copies in flight per stage
+                bulk_g2s(dst + piece * 4096u, g + piece * 4096, 4096u, fb);
             } else {      // hi blobs of two consecutive K32 chunks
               mbar_expect_tx(fb, WSTAGE_BYTES);
-              bulk_g2s(dst, src + (size_t)(2 * si) * 2 * TC_BLOB_BYTES, TC_BLOB_BYTES, fb);
-              bulk_g2s(dst + TC_BLOB_BYTES, src + (size_t)(2 * si + 1) * 2 * TC_BLOB_BYTES, TC_BLOB_BYTES, fb);
+#pragma unroll
+              for (int piece = 0; piece < 2; ++piece) {
+                bulk_g2s(dst + piece * 4096u, src + (size_t)(2 * si) * 2 * TC_BLOB_BYTES + piece * 4096, 4096u, fb);
+                bulk_g2s(dst + TC_BLOB_BYTES + piece * 4096u, src + (size_t)(2 * si + 1) * 2 * TC_BLOB_BYTES + piece * 4096, 4096u, fb);
+              }
             }
           }
           __syncwarp();
-          if (++stage == NUM_WSTAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == NST) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == WARP_MMA) {
-    // =========================== MMA issuer (whole warp in lock-step, one elected lane issues) ===========
+    // =========================== MMA issuer: ONE elected thread runs the whole role ===========
+    // (waits included: the tensor pipe queue hides them; per-block elect/reconverge cost ~25 cycles per MMA otherwise)
+    if (elect_one()) {
     uint32_t stage = 0, phase = 0;
     uint32_t pe_phase = 0, a_phase = 0;  // a_phase: one parity bit per 64-column A chunk
+    TraceCtx trc{0};
     const uint32_t dl_a_hi = desc_lo(sbase + SM_A_HI), dl_a_lo = desc_lo(sbase + SM_A_LO);
     const uint32_t dl_pe_hi = desc_lo(sbase + SM_PE_HI), dl_pe_lo = desc_lo(sbase + SM_PE_LO);
-    const uint32_t dl_w = desc_lo(sbase + SM_WST);
     for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
       for (int i = 0; i < n_issue; ++i) {
         const int s = step_at(i);
@@ -412,7 +423,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
           const uint32_t acc_done = bar(BAR_ACC + acc_bar(s, h));
           const bool release = a_release && h == nhalves - 1;
           uint32_t accumulate = 0;
-          trace_ev(P, lane, 1, 1, s, h);
+          trace_ev(P, trc, 0, 1, 1, s, h);
           for (int kp = 0; kp < npairs; ++kp) {
             // descriptor low words (16-byte units) of the A operand's hi / lo parts for this K64 chunk
             uint32_t ah, al;
@@ -424,23 +435,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
               if (h == 0 && !a_reused) {  // first touch of a 64-column chunk of a new activation version
                 mbar_wait(bar(BAR_A + c), (a_phase >> c) & 1u);
                 a_phase ^= 1u << c;
-                trace_ev(P, lane, 1, 2, s, c);
+                trace_ev(P, trc, 0, 1, 2, s, c);
               }
               ah = dl_a_hi + (uint32_t)c * 1024u; al = dl_a_lo + (uint32_t)c * 1024u;
             }
             const bool last = kp == npairs - 1;
-            if (last) trace_ev(P, lane, 1, 3, s, h);
+            if (last) trace_ev(P, trc, 0, 1, 3, s, h);
             if (PREC3) {
               // two 16 KB stages ([W_hi | W_lo] of one K32 chunk each) per K64 chunk, issued from one elected block
               const uint32_t st0 = stage, ph0 = phase;
-              if (++stage == NUM_WSTAGES) { stage = 0; phase ^= 1u; }
+              if (++stage == NST) { stage = 0; phase ^= 1u; }
               const uint32_t st1 = stage, ph1 = phase;
-              if (++stage == NUM_WSTAGES) { stage = 0; phase ^= 1u; }
+              if (++stage == NST) { stage = 0; phase ^= 1u; }
               mbar_wait(bar(BAR_W_FULL + st0), ph0);
               mbar_wait(bar(BAR_W_FULL + st1), ph1);
               tc_fence_after();
-              const uint32_t w0 = dl_w + st0 * 1024u, w1 = dl_w + st1 * 1024u;
-              if (elect_one()) {
+              const uint32_t w0 = desc_lo(stage_addr(st0)), w1 = desc_lo(stage_addr(st1));
+              {
                 if (!(MNRF_DBG(P, 2))) {
                   tc_mma2(d_tmem, ah, w0, accumulate);                 // A_hi * W_hi  (k 0..15)
                   tc_mma2(d_tmem, al, w0, 1u);                         // A_lo * W_hi
@@ -463,12 +474,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
                 if (last) tc_commit(acc_done);
               }
               accumulate = 1u;
-              __syncwarp();
             } else {
               mbar_wait(bar(BAR_W_FULL + stage), phase);  // one 16 KB stage per K64 chunk: W_hi of two K32 chunks
               tc_fence_after();
-              const uint32_t wb = dl_w + stage * 1024u;
-              if (elect_one()) {
+              const uint32_t wb = desc_lo(stage_addr(stage));
+              {
                 if (!(MNRF_DBG(P, 2))) {
                 tc_mma2(d_tmem, ah, wb, accumulate);
                 tc_mma2(d_tmem, ah + 256u, wb + 256u, 1u);
@@ -480,12 +490,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
                 if (last) tc_commit(acc_done);
               }
               accumulate = 1u;
-              __syncwarp();
-              if (++stage == NUM_WSTAGES) { stage = 0; phase ^= 1u; }
+              if (++stage == NST) { stage = 0; phase ^= 1u; }
             }
           }
         }
       }
+    }
     }
   } else if (warp >= 4) {
     // =========================== epilogue / PE warps ===========================
@@ -499,24 +509,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
     const float4* headw = reinterpret_cast<const float4*>(F + P.headw);
     float4* part = reinterpret_cast<float4*>(smem + SM_PART);
     uint32_t acc_phase = 0;  // one parity bit per accumulator barrier
+    TraceCtx trc{0};
     uint32_t free_phase = 0; // one parity bit per A-chunk release barrier
     auto wait_acc = [&](int s, int h) {
       const int b = acc_bar(s, h);
       mbar_wait(bar(BAR_ACC + b), (acc_phase >> b) & 1u);
       acc_phase ^= 1u << b;
       tc_fence_after();
-      if (q == 0) trace_ev(P, lane, 4 + g, 10, s, h);
+      if (q == 0) trace_ev(P, trc, lane, 4 + g, 10, s, h);
     };
     auto a_ready = [&](int c) {
       tc_fence_before();
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(BAR_A + c));
-      if (q == 0) trace_ev(P, lane, 4 + g, 11, c, 0);
+      if (q == 0) trace_ev(P, trc, lane, 4 + g, 11, c, 0);
     };
     // xyz + positional encoding of this thread's row of `tile` -> PE operand buffer
     auto pe_tile = [&](int tile) {
-      if (q == 0) trace_ev(P, lane, 4 + g, 12, 0, 0);
+      if (q == 0) trace_ev(P, trc, lane, 4 + g, 12, 0, 0);
       const long long pr = (long long)tile * TILE_M + row;
       const long long p = pr < P.io.n_points ? pr : (long long)P.io.n_points - 1;
       float x[3];
@@ -534,7 +545,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(BAR_PE));
-      if (q == 0) trace_ev(P, lane, 4 + g, 13, 0, 0);
+      if (q == 0) trace_ev(P, trc, lane, 4 + g, 13, 0, 0);
     };
 
     if ((int)blockIdx.x < P.n_tiles) pe_tile(blockIdx.x);
@@ -682,7 +693,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
       }
 
       // ---- write the point record ----
-      if (q == 0) trace_ev(P, lane, 4 + g, 14, 0, 0);
+      if (q == 0) trace_ev(P, trc, lane, 4 + g, 14, 0, 0);
       tc_fence_before();
       if (g == 0 && valid) {
         if (P.io.sigma_out != nullptr) P.io.sigma_out[p_raw] = o_sigma;

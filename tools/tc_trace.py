@@ -19,26 +19,35 @@ rays = camera_rays(800, 800)[::19][:32768].contiguous().cuda()
 cap = 200000
 kw = dict(test_time=True, compute_normal=False, field_impl=impl)
 with torch.no_grad():
-    render_rays(models, emb, rays, 64, False, 0, 0, 128, 32768, False, **kw)
+    # a single full-model launch: coarse-only render with train-style (non sigma-only) coarse pass, 192 samples
+    one = {"coarse": models["fine"]}
+    kw["test_time"] = False
+    render_rays(one, emb, rays, 192, False, 0, 0, 0, 32768, False, **kw)
     buf = torch.zeros(1 + 2 * cap, dtype=torch.int64, device="cuda")
     lib.mnrf_debug_set_trace(buf.data_ptr(), cap)
-    render_rays(models, emb, rays, 64, False, 0, 0, 128, 32768, False, **kw)
+    render_rays(one, emb, rays, 192, False, 0, 0, 0, 32768, False, **kw)
     torch.cuda.synchronize()
     lib.mnrf_debug_set_trace(None, 0)
 b = buf.cpu().numpy()
-n = int(b[0])
-print("events", n)
-ev = sorted((int(b[1 + 2 * i]), int(b[2 + 2 * i])) for i in range(min(n, cap)))
+ev = []
+for who in range(12):
+    base = 1 + who * 2 * 8192
+    for i in range(8192):
+        t, tag = int(b[base + 2 * i]), int(b[base + 2 * i + 1])
+        if t == 0:
+            break
+        ev.append((t, tag))
+ev.sort()
+print("events", len(ev))
 # the trace holds the coarse launch then the fine launch: split at the largest time gap, keep the fine one
-gaps = [(ev[i + 1][0] - ev[i][0], i) for i in range(len(ev) - 1)]
-fine = ev[max(gaps)[1] + 1:]
+fine = ev
 names = {1: "mma_begin", 2: "mma_A_ready", 3: "mma_last_chunk", 10: "epi_acc_ready", 11: "epi_chunk_written",
          12: "pe_begin", 13: "pe_end", 14: "tile_epilogue_done"}
 starts = [i for i, (t, tag) in enumerate(fine)
           if (tag >> 24) == 1 and ((tag >> 16) & 255) == 1 and ((tag >> 8) & 255) == 0 and (tag & 255) == 0]
 print("tiles traced", len(starts))
 print("tile period (cycles):", [fine[starts[j + 1]][0] - fine[starts[j]][0] for j in range(2, min(14, len(starts) - 1))])
-k = min(5, len(starts) - 2)
+k = min(20, len(starts) - 2)
 lo, hi = starts[k], starts[k + 1]
 t0 = fine[lo][0]
 for t, tag in fine[lo:hi + 8]:
