@@ -37,11 +37,10 @@ constexpr int TC_NUM_STEPS = 11;
 __host__ __device__ constexpr int tc_step_n(int s) { return s <= 8 ? 256 : 128; }
 __host__ __device__ constexpr int tc_step_k(int s) { return s == 0 ? 64 : (s == 4 ? 320 : 256); }
 __host__ __device__ constexpr int tc_step_chunks(int s) { return tc_step_k(s) / 32; }
-// One blob = hi or lo part of one K32 chunk of one 128-row N-half: 128 rows x 32 halves = 8 KB.
-// Order inside a step: [half h][chunk kc][hi, lo].
-constexpr int TC_BLOB_BYTES = 128 * 64;
-__host__ __device__ constexpr int tc_step_halves(int s) { return tc_step_n(s) / 128; }
-__host__ __device__ constexpr int tc_step_bytes(int s) { return tc_step_halves(s) * tc_step_chunks(s) * 2 * TC_BLOB_BYTES; }
+// One blob = hi or lo part of one K32 chunk of a step's weight matrix: N rows x 32 halves (16 KB for N=256, 8 KB for
+// N=128), stored as the shared-memory image of a tcgen05 K-major no-swizzle B operand.  Order inside a step: [chunk kc][hi, lo].
+__host__ __device__ constexpr int tc_blob_bytes(int s) { return tc_step_n(s) * 64; }
+__host__ __device__ constexpr int tc_step_bytes(int s) { return tc_step_chunks(s) * 2 * tc_blob_bytes(s); }
 __host__ __device__ constexpr int tc_step_offset(int s) {
   int o = 0;
   for (int i = 0; i < s; ++i) o += tc_step_bytes(i);

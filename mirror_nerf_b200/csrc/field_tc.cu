@@ -1,24 +1,27 @@
-// tcgen05 field kernel (v2): MirrorNeRF.forward (R/models/mirror_nerf.py:101-212) fused per 128-point tile:
+// tcgen05 field kernel (v3): MirrorNeRF.forward (R/models/mirror_nerf.py:101-212) fused per 128-point tile:
 //   o + d*z  ->  positional encoding  ->  8x256 trunk (skip at layer 5)  ->  sigma / folded normal head
 //   ->  mirror head  ->  final 256x256  ->  dir layer (+ per-ray dir term)  ->  rgb      -> 8 floats/point.
 //
 // One persistent CTA per SM, 12 warps:
-//   warp 0        weight producer: cp.async.bulk (TMA 1-D) of pre-packed 8 KB B-operand blobs, 8-stage mbarrier ring
-//   warp 1        MMA issuer: one thread issues tcgen05.mma (M=128, N=128, K=16, fp16 -> fp32 in TMEM)
+//   warp 0        weight producer: cp.async.bulk (TMA 1-D) of pre-packed B-operand blobs, 16 KB mbarrier-ring stages
+//   warp 1        MMA issuer: ONE elected thread runs the whole role and issues tcgen05.mma
+//                 (M=128, N=256 | 128, K=16, fp16 operands in shared memory, fp32 accumulators in TMEM)
 //   warps 4..11   epilogue/PE: TMEM -> registers (tcgen05.ld) -> bias/ReLU -> fp16 hi/lo split -> next layer's
 //                 A operand written in place into shared memory in the UMMA K-major core-matrix layout.
 //
-// Pipelining: every 256-wide layer is accumulated as two 128-column halves, half-major, each half with its own
-// "accumulator complete" mbarrier; the epilogue of half h produces two 64-column K chunks of the next layer, each with its
-// own "chunk ready" mbarrier, and the two 256-column TMEM accumulators alternate by layer.  So the epilogue of layer l
-// overlaps the second half of layer l's MMAs and the first K chunks of layer l+1's (simulated period max(T_mma, T_epi)
-// for T_epi <= 0.75 T_mma; v1, with one barrier per layer, measured T_epi + T_mma/2).
+// Pipelining.  Measured on B200 (tools/mma_bench*.cu, profiles/): the tensor pipe needs 128 cycles per M128xN256xK16 and 64
+// per N128; a single issuing thread with an mbarrier wait + commit per weight stage sustains one MMA per ~90-110 cycles.
+// So the 256-wide layers are issued as N=256 instructions (issue cost hidden behind 128 cycles of work), one accumulator
+// barrier per layer, two 256-column TMEM accumulators alternating by layer.  The epilogue of layer l starts when its
+// accumulator is complete (every reader of the in-place activations is done by then), walks the four 64-column K chunks in
+// order with all 8 warps on each chunk (32 columns per warp) and signals a per-chunk mbarrier, so layer l+1's MMAs start
+// after a quarter of the epilogue and then run back to back:  period = T_mma + T_epi/4 + handshake.
 //
 // Precision: operands are split x = hi + lo in fp16 (weights pre-scaled by 2^s per layer) and
 // each product is formed as hi*hi + lo*hi + hi*lo with fp32 accumulation ("3x" mode, fp32-grade);
 // PREC3 == false drops the lo terms (speed mode).
 //
-// Shared memory (1 CTA/SM): A hi/lo 2x64 KB | PE hi/lo 2x16 KB | 8 x 8 KB weight stages | 2 KB partial sums.
+// Shared memory (1 CTA/SM): A hi/lo 2x64 KB | PE hi/lo 2x16 KB | 4 x 16 KB weight stages | 2 KB partial sums.
 #include "common.cuh"
 
 namespace mnrf {
@@ -27,31 +30,29 @@ namespace {
 constexpr int TILE_M = 128;
 constexpr int NUM_THREADS = 384;
 // warp 0: weight producer; warp 1: MMA issuer; warps 4..11: epilogue/PE (TMEM lane quarter = warp % 4).
-// (Measured: putting the issuer at the highest warp id of its scheduler partition is 7-16 % slower.)
 constexpr int WARP_PRODUCER = 0;
 constexpr int WARP_MMA = 1;
-constexpr int NUM_WSTAGES = 4;      // 3x mode; the 1x mode also uses the idle A_lo region: 8 stages
-constexpr uint32_t WSTAGE_BYTES = 2 * TC_BLOB_BYTES;  // 16 KB: tc3 = [hi,lo] of one K32 chunk; tc1 = hi of two K32 chunks
+constexpr uint32_t WSTAGE_BYTES = 16384;
 
 constexpr uint32_t SM_A_HI = 0;
 constexpr uint32_t SM_A_LO = 65536;
 constexpr uint32_t SM_PE_HI = 131072;
 constexpr uint32_t SM_PE_LO = 147456;
 constexpr uint32_t SM_WST = 163840;
-constexpr uint32_t SM_PART = SM_WST + NUM_WSTAGES * WSTAGE_BYTES;  // 229376: float4[128]
-constexpr uint32_t SM_BAR = SM_PART + 2048;                        // 231424
-constexpr uint32_t SM_TOTAL = SM_BAR + 256;                        // 231680 <= 232448
+constexpr uint32_t SM_PART = SM_WST + 4 * WSTAGE_BYTES;  // 229376: float4[128]
+constexpr uint32_t SM_BAR = SM_PART + 2048;              // 231424
+constexpr uint32_t SM_TOTAL = SM_BAR + 256;              // 231680 <= 232448
 
 // barrier slots (8 bytes each)
-constexpr int BAR_W_FULL = 0;    // [4] (8 slots reserved)
-constexpr int BAR_W_EMPTY = 8;   // [4]
+constexpr int BAR_W_FULL = 0;    // [8]
+constexpr int BAR_W_EMPTY = 8;   // [8]
 constexpr int BAR_PE = 16;       // PE chunk written (8 warp arrivals)
-constexpr int BAR_A = 17;        // [4] A 64-column chunk written (4 warp arrivals)
-constexpr int BAR_ACC = 21;      // [4] accumulator half complete (tcgen05.commit): [buffer][half]
-constexpr int BAR_AFREE = 25;    // [4] A 64-column chunk no longer read by any issued MMA (tcgen05.commit)
+constexpr int BAR_A = 17;        // [4] A 64-column chunk written (8 warp arrivals)
+constexpr int BAR_ACC = 21;      // [4] accumulator of a GEMM step complete (tcgen05.commit)
 constexpr int BAR_TMEM_SLOT = 30;
 
-constexpr uint32_t IDESC_N128 = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);  // f16 x f16 -> f32, K-major
+constexpr uint32_t IDESC_N256 = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);  // f16 x f16 -> f32, K-major
+constexpr uint32_t IDESC_N128 = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
 struct TcParams {
   const float* f32;        // fp32 section
@@ -61,9 +62,9 @@ struct TcParams {
   int has_normal, has_mirror;
   FieldIO io;
   int n_tiles;
-  unsigned long long* trace;  // optional device-side event trace of CTA 0: [count, (clock, tag)...]
+  unsigned long long* trace;  // optional device-side event trace of CTA 0 (bring-up builds)
   unsigned int trace_cap;
-  int debug;  // timing experiments (MNRF_TC_DEBUG): 1 = 16-byte weight copies, 2 = no MMA issue, 4 = no epilogue math
+  int debug;
 };
 
 // device-side tracing (mnrf_debug_set_trace): lane 0 of a warp of CTA 0 logs (clock64, tag) with plain stores into its own
@@ -79,12 +80,6 @@ __device__ __forceinline__ void trace_ev(const TcParams& P, TraceCtx& tc, int la
   }
 #endif
 }
-// timing-experiment knobs (MNRF_TC_DEBUG) are compiled in only for bring-up builds (make EXTRA=-DMNRF_TC_TRACE)
-#ifdef MNRF_TC_TRACE
-#define MNRF_DBG(P, bit) ((P).debug & (bit))
-#else
-#define MNRF_DBG(P, bit) 0
-#endif
 
 // ---- PTX wrappers --------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -132,15 +127,6 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                       uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -174,26 +160,21 @@ __device__ __forceinline__ bool elect_one() {
 }
 __device__ __forceinline__ void epi_bar_sync(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
 
-// K-major, no-swizzle operand descriptor.  Core matrix = 8 rows x 16 bytes stored as 128 contiguous bytes;
-// LBO = byte distance between K-adjacent core matrices, SBO = byte distance between 8-row groups (M/N direction).
-// Both operand kinds here are 128 rows tall: LBO = 128*16 = 2048, SBO = 128; one K16 step = 4096 bytes.
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr) {
-  return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)(2048u >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
-}
-
-// All operands share the descriptor's high word (SBO = 128 B, descriptor version 1); the low word is
-// (address >> 4) | (LBO >> 4) << 16, so stepping through an operand is an integer add in 16-byte units
-// (K16 step = 256, K32 chunk = 512, K64 chunk = 1024).
+// K-major, no-swizzle operand descriptors.  Core matrix = 8 rows x 16 bytes stored as 128 contiguous bytes; SBO (distance
+// between 8-row groups) = 128 B for every operand, so all descriptors share the high word; LBO (distance between K-adjacent
+// core matrices) = rows*16: 2048 for the 128-row A operands and N=128 weights, 4096 for N=256 weights.  The low word is
+// (address >> 4) | (LBO >> 4) << 16, so stepping through an operand is an integer add in 16-byte units.
 constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
-__device__ __forceinline__ uint32_t desc_lo(uint32_t addr) { return ((addr >> 4) & 0x3FFFu) | ((2048u >> 4) << 16); }
-__device__ __forceinline__ void tc_mma2(uint32_t d_tmem, uint32_t a_lo32, uint32_t b_lo32, uint32_t accumulate) {
+__device__ __forceinline__ uint32_t desc_lo(uint32_t addr, uint32_t lbo) { return ((addr >> 4) & 0x3FFFu) | ((lbo >> 4) << 16); }
+template <int N>
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint32_t a_lo32, uint32_t b_lo32, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
       "mov.b64 da, {%1, %4};\n\t"
       "mov.b64 db, {%2, %4};\n\t"
       "setp.ne.b32 p, %3, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_lo32), "r"(b_lo32), "r"(accumulate), "r"(DESC_HI), "r"(IDESC_N128)
+      ::"r"(d_tmem), "r"(a_lo32), "r"(b_lo32), "r"(accumulate), "r"(DESC_HI), "r"(N == 256 ? IDESC_N256 : IDESC_N128)
       : "memory");
 }
 
@@ -295,35 +276,17 @@ __device__ __forceinline__ void epi32(const uint32_t (&r)[32], const float4 (&b)
   }
 }
 
-// 64 accumulator columns (this warp's share of a 128-column half): both TMEM loads in flight, bias prefetched
-template <bool RELU, bool DOTS, bool WRITE_A, bool PREC3>
-__device__ __forceinline__ void epi64(uint32_t tacc, const float* __restrict__ bias, float inv, uint32_t s_hi,
-                                      uint32_t s_lo, const float4* __restrict__ hw, float (&d)[4], uint32_t free_bar,
-                                      uint32_t free_parity) {
-  uint32_t ra[32], rb[32];
-  tmem_ld32(tacc, ra);
-  tmem_ld32(tacc + 32u, rb);
-  const float4* b4 = reinterpret_cast<const float4*>(bias);
-  float4 b[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) b[i] = __ldg(b4 + i);
-  tmem_wait_ld();
-  pin32(ra);
-  pin32(rb);
-  if (WRITE_A && free_bar != 0u) mbar_wait(free_bar, free_parity);  // in-place overwrite: wait for the chunk's last reader
-  epi32<RELU, DOTS, WRITE_A, PREC3>(ra, b, inv, s_hi, s_lo, hw, d);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) b[i] = __ldg(b4 + 8 + i);
-  epi32<RELU, DOTS, WRITE_A, PREC3>(rb, b, inv, s_hi + 4u * 2048u, s_lo + 4u * 2048u, hw + 32, d);
-}
+// epilogue flavours of a 256-wide layer
+struct TagTrunk { static constexpr bool relu = true, dots = false, write_a = true; };   // layers 1..7
+struct TagLast  { static constexpr bool relu = true, dots = true, write_a = true; };    // layer 8 (+ sigma / normal dots)
+struct TagSigma { static constexpr bool relu = true, dots = true, write_a = false; };   // layer 8 of a sigma-only launch
+struct TagFinal { static constexpr bool relu = false, dots = false, write_a = true; };  // xyz_encoding_final (no activation)
 
 // ---- step geometry --------------------------------------------------------------------------------
 // TMEM columns: trunk layers alternate [0,256) / [256,512); mirror head (step 9) -> [0,128); final (step 8) -> [128,384);
 // dir layer (step 10) -> [384,512).  Issue order: 0..7, 9, 8, 10.
-__device__ __forceinline__ uint32_t acc_col(int s, int h) {
-  return (s <= 7 ? (uint32_t)(s & 1) * 256u : (s == 9 ? 0u : (s == 8 ? 128u : 384u))) + (uint32_t)h * 128u;
-}
-__device__ __forceinline__ int acc_bar(int s, int h) { return s <= 7 ? 2 * (s & 1) + h : (s == 9 ? 0 : (s == 8 ? 1 + h : 3)); }
+__device__ __forceinline__ uint32_t acc_col(int s) { return s <= 7 ? (uint32_t)(s & 1) * 256u : (s == 9 ? 0u : (s == 8 ? 128u : 384u)); }
+__device__ __forceinline__ int acc_bar(int s) { return s <= 7 ? (s & 1) : (s == 8 ? 3 : 2); }  // steps 9 and 10 share slot 2
 __device__ __forceinline__ int step_at(int i) { return i < 8 ? i : (i == 8 ? 9 : (i == 9 ? 8 : 10)); }
 
 // ================================================================================================
@@ -337,16 +300,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
   auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SM_BAR + 8 * BAR_TMEM_SLOT);
   const int n_issue = P.io.sigma_only ? 8 : 11;
-  constexpr uint32_t NST = PREC3 ? NUM_WSTAGES : 8;  // weight stages (the 1x mode leaves the A_lo region free)
+  constexpr uint32_t NST = PREC3 ? 4u : 8u;  // weight stages (the 1x mode also uses the idle A_lo region)
   auto stage_addr = [&](uint32_t st) { return sbase + (st < 4u ? SM_WST + st * WSTAGE_BYTES : SM_A_LO + (st - 4u) * WSTAGE_BYTES); };
 
   if (threadIdx.x == 0) {
     if (sbase & 127u) { printf("mnrf field_tc: unaligned dynamic smem base %u\n", sbase); __trap(); }
     for (int i = 0; i < 8; ++i) { mbar_init(bar(BAR_W_FULL + i), 1); mbar_init(bar(BAR_W_EMPTY + i), 1); }
     mbar_init(bar(BAR_PE), 8);
-    for (int i = 0; i < 4; ++i) mbar_init(bar(BAR_A + i), 4);
+    for (int i = 0; i < 4; ++i) mbar_init(bar(BAR_A + i), 8);
     for (int i = 0; i < 4; ++i) mbar_init(bar(BAR_ACC + i), 1);
-    for (int i = 0; i < 4; ++i) mbar_init(bar(BAR_AFREE + i), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == WARP_MMA) {
@@ -362,146 +324,127 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
   const uint32_t tmem = *tmem_slot;
 
   if (warp == WARP_PRODUCER) {
-    // =========================== weight producer (whole warp in lock-step, one elected lane issues) ===========
-    uint32_t stage = 0, phase = 0;
-    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-      for (int i = 0; i < n_issue; ++i) {
-        const int s = step_at(i);
-        if (s == 9 && !P.has_mirror) continue;
-        const uint8_t* src = P.tc + tc_step_offset(s);
-        const int nst = tc_step_halves(s) * tc_step_chunks(s) / (PREC3 ? 1 : 2);  // stages of this step
-        for (int si = 0; si < nst; ++si) {
-          mbar_wait(bar(BAR_W_EMPTY + stage), phase ^ 1u);
-          if (elect_one()) {
+    // =========================== weight producer (one elected thread) ===========================
+    // Stage contents.  3x mode: N=256 steps -> one blob (hi or lo of a K32 chunk, 16 KB); N=128 steps -> [hi|lo] of a K32
+    // chunk (2 x 8 KB, contiguous).  1x mode: N=256 -> hi blob of a K32 chunk; N=128 -> hi blobs of two K32 chunks.
+    if (elect_one()) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+        for (int i = 0; i < n_issue; ++i) {
+          const int s = step_at(i);
+          if (s == 9 && !P.has_mirror) continue;
+          const uint8_t* src = P.tc + tc_step_offset(s);
+          const bool wide = tc_step_n(s) == 256;
+          const int nch = tc_step_chunks(s);
+          const int nst = PREC3 ? (wide ? 2 * nch : nch) : (wide ? nch : nch / 2);
+          for (int si = 0; si < nst; ++si) {
+            mbar_wait(bar(BAR_W_EMPTY + stage), phase ^ 1u);
             const uint32_t dst = stage_addr(stage);
             const uint32_t fb = bar(BAR_W_FULL + stage);
-            if (MNRF_DBG(P, 1)) {
-              mbar_expect_tx(fb, 16);
-              bulk_g2s(dst, src, 16, fb);
-            } else if (PREC3) {  // [hi, lo] blobs of one K32 chunk are contiguous
-              mbar_expect_tx(fb, WSTAGE_BYTES);
-              const uint8_t* g = src + (size_t)si * 2 * TC_BLOB_BYTES;
+            mbar_expect_tx(fb, WSTAGE_BYTES);
+            if (PREC3 || wide) {
+              // 16 contiguous KB: blob si (3x wide), blobs 2si,2si+1 (3x narrow), blob 2si = hi of chunk si (1x wide)
+              const uint8_t* g = src + (size_t)(PREC3 ? si : 2 * si) * WSTAGE_BYTES;
 #pragma unroll
-              for (int piece = 0; piece < 4; ++piece)  // four 4 KB copies in flight per stage
-                bulk_g2s(dst + piece * 4096u, g + piece * 4096, 4096u, fb);
-            } else {      // hi blobs of two consecutive K32 chunks
-              mbar_expect_tx(fb, WSTAGE_BYTES);
-#pragma unroll
-              for (int piece = 0; piece < 2; ++piece) {
-                bulk_g2s(dst + piece * 4096u, src + (size_t)(2 * si) * 2 * TC_BLOB_BYTES + piece * 4096, 4096u, fb);
-                bulk_g2s(dst + TC_BLOB_BYTES + piece * 4096u, src + (size_t)(2 * si + 1) * 2 * TC_BLOB_BYTES + piece * 4096, 4096u, fb);
-              }
+              for (int piece = 0; piece < 4; ++piece) bulk_g2s(dst + piece * 4096u, g + piece * 4096, 4096u, fb);
+            } else {
+              // 1x narrow: hi blobs (8 KB) of chunks 2si and 2si+1; a chunk's [hi|lo] pair is 16 KB
+              bulk_g2s(dst, src + (size_t)(2 * si) * 16384, 8192u, fb);
+              bulk_g2s(dst + 8192u, src + (size_t)(2 * si + 1) * 16384, 8192u, fb);
             }
+            if (++stage == NST) { stage = 0; phase ^= 1u; }
           }
-          __syncwarp();
-          if (++stage == NST) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == WARP_MMA) {
-    // =========================== MMA issuer: ONE elected thread runs the whole role ===========
-    // (waits included: the tensor pipe queue hides them; per-block elect/reconverge cost ~25 cycles per MMA otherwise)
+    // =========================== MMA issuer: ONE elected thread runs the whole role ===========================
     if (elect_one()) {
-    uint32_t stage = 0, phase = 0;
-    uint32_t pe_phase = 0, a_phase = 0;  // a_phase: one parity bit per 64-column A chunk
-    TraceCtx trc{0};
-    const uint32_t dl_a_hi = desc_lo(sbase + SM_A_HI), dl_a_lo = desc_lo(sbase + SM_A_LO);
-    const uint32_t dl_pe_hi = desc_lo(sbase + SM_PE_HI), dl_pe_lo = desc_lo(sbase + SM_PE_LO);
-    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-      for (int i = 0; i < n_issue; ++i) {
-        const int s = step_at(i);
-        if (s == 9 && !P.has_mirror) continue;
-        const int npairs = tc_step_chunks(s) >> 1;           // K64 chunks (= 64-column A chunks) of this step
-        const int pe_pairs = (s == 0 || s == 4) ? 1 : 0;     // the leading K64 chunk comes from the PE buffer
-        const bool a_reused = (s == 8 && P.has_mirror);      // h8 was already awaited by the mirror GEMM
-        // the epilogue of this step overwrites the A buffer in place while this step's second half is still
-        // reading it: release each 64-column chunk as soon as its last MMA has been issued
-        const bool a_release = (s >= 1 && s <= 8) && !(s == 7 && P.io.sigma_only);
-        const int nhalves = tc_step_halves(s);
-        for (int h = 0; h < nhalves; ++h) {
-          const uint32_t d_tmem = tmem + acc_col(s, h);
-          const uint32_t acc_done = bar(BAR_ACC + acc_bar(s, h));
-          const bool release = a_release && h == nhalves - 1;
+      uint32_t stage = 0, phase = 0;
+      uint32_t pe_phase = 0, a_phase = 0;  // a_phase: one parity bit per 64-column A chunk
+      TraceCtx trc{0};
+      const uint32_t dl_a_hi = desc_lo(sbase + SM_A_HI, 2048), dl_a_lo = desc_lo(sbase + SM_A_LO, 2048);
+      const uint32_t dl_pe_hi = desc_lo(sbase + SM_PE_HI, 2048), dl_pe_lo = desc_lo(sbase + SM_PE_LO, 2048);
+      auto next_stage = [&]() { if (++stage == NST) { stage = 0; phase ^= 1u; } };
+      for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+        for (int i = 0; i < n_issue; ++i) {
+          const int s = step_at(i);
+          if (s == 9 && !P.has_mirror) continue;
+          const bool wide = tc_step_n(s) == 256;
+          const int nch = tc_step_chunks(s);
+          const int n_pe = (s == 0 || s == 4) ? 2 : 0;       // leading K32 chunks that come from the PE buffer
+          const bool a_reused = (s == 8 && P.has_mirror);    // h8 was already awaited by the mirror GEMM
+          const uint32_t d_tmem = tmem + acc_col(s);
           uint32_t accumulate = 0;
-          trace_ev(P, trc, 0, 1, 1, s, h);
-          for (int kp = 0; kp < npairs; ++kp) {
-            // descriptor low words (16-byte units) of the A operand's hi / lo parts for this K64 chunk
-            uint32_t ah, al;
-            const int c = kp - pe_pairs;
-            if (c < 0) {
-              if (s == 0 && h == 0) { mbar_wait(bar(BAR_PE), pe_phase); pe_phase ^= 1u; }
-              ah = dl_pe_hi; al = dl_pe_lo;
+          trace_ev(P, trc, 0, 1, 1, s, 0);
+          for (int kc = 0; kc < nch; ++kc) {
+            uint32_t ah, al;  // descriptor low words of this K32 chunk of the A operand (hi / lo parts)
+            if (kc < n_pe) {
+              if (s == 0 && kc == 0) { mbar_wait(bar(BAR_PE), pe_phase); pe_phase ^= 1u; }
+              ah = dl_pe_hi + (uint32_t)kc * 512u; al = dl_pe_lo + (uint32_t)kc * 512u;
             } else {
-              if (h == 0 && !a_reused) {  // first touch of a 64-column chunk of a new activation version
+              const int ka = kc - n_pe;
+              if ((ka & 1) == 0 && !a_reused) {  // first touch of a 64-column chunk of a new activation version
+                const int c = ka >> 1;
                 mbar_wait(bar(BAR_A + c), (a_phase >> c) & 1u);
                 a_phase ^= 1u << c;
                 trace_ev(P, trc, 0, 1, 2, s, c);
               }
-              ah = dl_a_hi + (uint32_t)c * 1024u; al = dl_a_lo + (uint32_t)c * 1024u;
+              ah = dl_a_hi + (uint32_t)ka * 512u; al = dl_a_lo + (uint32_t)ka * 512u;
             }
-            const bool last = kp == npairs - 1;
-            if (last) trace_ev(P, trc, 0, 1, 3, s, h);
-            if (PREC3) {
-              // two 16 KB stages ([W_hi | W_lo] of one K32 chunk each) per K64 chunk, issued from one elected block
-              const uint32_t st0 = stage, ph0 = phase;
-              if (++stage == NST) { stage = 0; phase ^= 1u; }
-              const uint32_t st1 = stage, ph1 = phase;
-              if (++stage == NST) { stage = 0; phase ^= 1u; }
-              mbar_wait(bar(BAR_W_FULL + st0), ph0);
-              mbar_wait(bar(BAR_W_FULL + st1), ph1);
+            if (wide) {
+              // ---- N = 256: K16 step of the B operand = 8192 B = 512 units ----
+              mbar_wait(bar(BAR_W_FULL + stage), phase);
               tc_fence_after();
-              const uint32_t w0 = desc_lo(stage_addr(st0)), w1 = desc_lo(stage_addr(st1));
-              {
-                if (!(MNRF_DBG(P, 2))) {
-                  tc_mma2(d_tmem, ah, w0, accumulate);                 // A_hi * W_hi  (k 0..15)
-                  tc_mma2(d_tmem, al, w0, 1u);                         // A_lo * W_hi
-                  tc_mma2(d_tmem, ah + 256u, w0 + 256u, 1u);           // (k 16..31)
-                  tc_mma2(d_tmem, al + 256u, w0 + 256u, 1u);
-                  tc_mma2(d_tmem, ah, w0 + 512u, 1u);                  // A_hi * W_lo
-                  tc_mma2(d_tmem, ah + 256u, w0 + 768u, 1u);
-                }
-                tc_commit(bar(BAR_W_EMPTY + st0));
-                if (!(MNRF_DBG(P, 2))) {
-                  tc_mma2(d_tmem, ah + 512u, w1, 1u);                  // (k 32..47)
-                  tc_mma2(d_tmem, al + 512u, w1, 1u);
-                  tc_mma2(d_tmem, ah + 768u, w1 + 256u, 1u);           // (k 48..63)
-                  tc_mma2(d_tmem, al + 768u, w1 + 256u, 1u);
-                  tc_mma2(d_tmem, ah + 512u, w1 + 512u, 1u);
-                  tc_mma2(d_tmem, ah + 768u, w1 + 768u, 1u);
-                }
-                tc_commit(bar(BAR_W_EMPTY + st1));
-                if (release && c >= 0) tc_commit(bar(BAR_AFREE + c));
-                if (last) tc_commit(acc_done);
-              }
-              accumulate = 1u;
-            } else {
-              mbar_wait(bar(BAR_W_FULL + stage), phase);  // one 16 KB stage per K64 chunk: W_hi of two K32 chunks
-              tc_fence_after();
-              const uint32_t wb = desc_lo(stage_addr(stage));
-              {
-                if (!(MNRF_DBG(P, 2))) {
-                tc_mma2(d_tmem, ah, wb, accumulate);
-                tc_mma2(d_tmem, ah + 256u, wb + 256u, 1u);
-                tc_mma2(d_tmem, ah + 512u, wb + 512u, 1u);
-                tc_mma2(d_tmem, ah + 768u, wb + 768u, 1u);
-                }
+              uint32_t wb = desc_lo(stage_addr(stage), 4096);
+              tc_mma<256>(d_tmem, ah, wb, accumulate);                        // A_hi * W_hi  (k 0..15)
+              if (PREC3) tc_mma<256>(d_tmem, al, wb, 1u);                     // A_lo * W_hi
+              tc_mma<256>(d_tmem, ah + 256u, wb + 512u, 1u);                  // (k 16..31)
+              if (PREC3) tc_mma<256>(d_tmem, al + 256u, wb + 512u, 1u);
+              tc_commit(bar(BAR_W_EMPTY + stage));
+              next_stage();
+              if (PREC3) {
+                mbar_wait(bar(BAR_W_FULL + stage), phase);
+                tc_fence_after();
+                wb = desc_lo(stage_addr(stage), 4096);
+                tc_mma<256>(d_tmem, ah, wb, 1u);                              // A_hi * W_lo
+                tc_mma<256>(d_tmem, ah + 256u, wb + 512u, 1u);
                 tc_commit(bar(BAR_W_EMPTY + stage));
-                if (release && c >= 0) tc_commit(bar(BAR_AFREE + c));
-                if (last) tc_commit(acc_done);
+                next_stage();
               }
-              accumulate = 1u;
-              if (++stage == NST) { stage = 0; phase ^= 1u; }
+            } else if (PREC3) {
+              // ---- N = 128, 3x: stage = [W_hi | W_lo] of this K32 chunk; K16 step = 4096 B = 256 units ----
+              mbar_wait(bar(BAR_W_FULL + stage), phase);
+              tc_fence_after();
+              const uint32_t wb = desc_lo(stage_addr(stage), 2048);
+              tc_mma<128>(d_tmem, ah, wb, accumulate);
+              tc_mma<128>(d_tmem, al, wb, 1u);
+              tc_mma<128>(d_tmem, ah + 256u, wb + 256u, 1u);
+              tc_mma<128>(d_tmem, al + 256u, wb + 256u, 1u);
+              tc_mma<128>(d_tmem, ah, wb + 512u, 1u);
+              tc_mma<128>(d_tmem, ah + 256u, wb + 768u, 1u);
+              tc_commit(bar(BAR_W_EMPTY + stage));
+              next_stage();
+            } else {
+              // ---- N = 128, 1x: stage = W_hi of two K32 chunks ----
+              if ((kc & 1) == 0) { mbar_wait(bar(BAR_W_FULL + stage), phase); tc_fence_after(); }
+              const uint32_t wb = desc_lo(stage_addr(stage), 2048) + (uint32_t)(kc & 1) * 512u;
+              tc_mma<128>(d_tmem, ah, wb, accumulate);
+              tc_mma<128>(d_tmem, ah + 256u, wb + 256u, 1u);
+              if (kc & 1) { tc_commit(bar(BAR_W_EMPTY + stage)); next_stage(); }
             }
+            accumulate = 1u;
           }
+          tc_commit(bar(BAR_ACC + acc_bar(s)));
+          trace_ev(P, trc, 0, 1, 3, s, 0);
         }
       }
-    }
     }
   } else if (warp >= 4) {
     // =========================== epilogue / PE warps ===========================
     const int ew = warp - 4;
     const int q = ew & 3;          // TMEM lane quarter == warp_id % 4
-    const int g = ew >> 2;         // 64-column group inside a 128-column half
+    const int g = ew >> 2;         // 32-column half of every 64-column chunk (64-column half of the 128-wide heads)
     const int row = q * 32 + lane;
     const uint32_t rowoff = (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u;
     const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
@@ -510,13 +453,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
     float4* part = reinterpret_cast<float4*>(smem + SM_PART);
     uint32_t acc_phase = 0;  // one parity bit per accumulator barrier
     TraceCtx trc{0};
-    uint32_t free_phase = 0; // one parity bit per A-chunk release barrier
-    auto wait_acc = [&](int s, int h) {
-      const int b = acc_bar(s, h);
+    auto wait_acc = [&](int s) {
+      const int b = acc_bar(s);
       mbar_wait(bar(BAR_ACC + b), (acc_phase >> b) & 1u);
       acc_phase ^= 1u << b;
       tc_fence_after();
-      if (q == 0) trace_ev(P, trc, lane, 4 + g, 10, s, h);
+      if (q == 0) trace_ev(P, trc, lane, 4 + g, 10, s, 0);
     };
     auto a_ready = [&](int c) {
       tc_fence_before();
@@ -547,6 +489,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
       if (lane == 0) mbar_arrive(bar(BAR_PE));
       if (q == 0) trace_ev(P, trc, lane, 4 + g, 13, 0, 0);
     };
+    // One 256-wide layer: this warp owns columns [64c + 32g, 64c + 32g + 32) of every chunk c, chunks in K order, the next
+    // chunk's TMEM load in flight while the current one is converted.
+    auto layer_epilogue = [&](auto tag, int s, const float* bias256, float (&d)[4]) {
+      constexpr bool RELU = decltype(tag)::relu, DOTS = decltype(tag)::dots, WRITE_A = decltype(tag)::write_a;
+      const float inv = __ldg(F + P.inv_scale + s);
+      const uint32_t tacc = tlane + acc_col(s) + (uint32_t)g * 32u;
+      const float4* b4 = reinterpret_cast<const float4*>(bias256 + g * 32);
+      uint32_t ra[32], rb[32];
+      float4 b[8];
+      tmem_ld32(tacc, ra);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) b[i] = __ldg(b4 + c * 16 + i);
+        tmem_wait_ld();  // the load of chunk c (issued one iteration ago) has landed
+        if (c < 3) {     // next chunk's load flies while this chunk is converted
+          if (c & 1) tmem_ld32(tacc + (uint32_t)(c + 1) * 64u, ra); else tmem_ld32(tacc + (uint32_t)(c + 1) * 64u, rb);
+        }
+        const uint32_t off = (uint32_t)(c * 8 + g * 4) * 2048u + rowoff;
+        if (c & 1) { pin32(rb); epi32<RELU, DOTS, WRITE_A, PREC3>(rb, b, inv, sbase + SM_A_HI + off, sbase + SM_A_LO + off, headw + c * 64 + g * 32, d); }
+        else       { pin32(ra); epi32<RELU, DOTS, WRITE_A, PREC3>(ra, b, inv, sbase + SM_A_HI + off, sbase + SM_A_LO + off, headw + c * 64 + g * 32, d); }
+        if (WRITE_A) a_ready(c);
+      }
+    };
 
     if ((int)blockIdx.x < P.n_tiles) pe_tile(blockIdx.x);
     for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
@@ -558,34 +524,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
       float d[4] = {0.f, 0.f, 0.f, 0.f};
 
       // ---- trunk layers 1..8 (steps 0..7) ----
-      for (int s = 0; s < 8; ++s) {
-        const float* bias = F + P.b_trunk[s] + g * 64;
-        const float inv = __ldg(F + P.inv_scale + s);
 #pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-          wait_acc(s, h);
-          const int c = 2 * h + g;  // 64-column chunk of the next layer's K produced by this warp
-          const uint32_t tacc = tlane + acc_col(s, h) + (uint32_t)g * 64u;
-          const uint32_t s_hi = sbase + SM_A_HI + (uint32_t)c * 16384u + rowoff;
-          const uint32_t s_lo = sbase + SM_A_LO + (uint32_t)c * 16384u + rowoff;
-          // steps >= 1 overwrite the activations their own second-half MMAs may still be reading
-          const uint32_t fb = s >= 1 ? bar(BAR_AFREE + c) : 0u;
-          const uint32_t fp = (free_phase >> c) & 1u;
-          if (MNRF_DBG(P, 4)) {
-            if (s >= 1 && !(s == 7 && P.io.sigma_only)) free_phase ^= 1u << c;
-            if (!(s == 7 && P.io.sigma_only)) a_ready(c);
-          } else if (s < 7) {
-            epi64<true, false, true, PREC3>(tacc, bias + h * 128, inv, s_hi, s_lo, nullptr, d, fb, fp);
-            if (s >= 1) free_phase ^= 1u << c;
-            a_ready(c);
-          } else if (!P.io.sigma_only) {
-            epi64<true, true, true, PREC3>(tacc, bias + h * 128, inv, s_hi, s_lo, headw + c * 64, d, fb, fp);
-            free_phase ^= 1u << c;
-            a_ready(c);
-          } else {
-            epi64<true, true, false, PREC3>(tacc, bias + h * 128, inv, s_hi, s_lo, headw + c * 64, d, 0u, 0u);
-          }
-        }
+      for (int s = 0; s < 8; ++s) {
+        wait_acc(s);
+        const float* bias = F + P.b_trunk[s];
+        if (s < 7) layer_epilogue(TagTrunk{}, s, bias, d);
+        else if (!P.io.sigma_only) layer_epilogue(TagLast{}, s, bias, d);
+        else layer_epilogue(TagSigma{}, s, bias, d);
         // the PE buffer is free once layer 5's MMAs are done: encode the next tile while the tensor pipe is busy
         if (s == 5 && tile + (int)gridDim.x < P.n_tiles) pe_tile(tile + gridDim.x);
       }
@@ -609,76 +554,78 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
       if (!P.io.sigma_only) {
         // ---- mirror head (step 9): LeakyReLU(0.01) -> Linear(128,1) -> sigmoid (mirror_nerf.py:94-99) ----
         if (P.has_mirror) {
-          wait_acc(9, 0);
+          wait_acc(9);
           const float inv = __ldg(F + P.inv_scale + 9);
           float dm = 0.f;
           uint32_t ra[32], rb[32];
-          tmem_ld32(tlane + acc_col(9, 0) + (uint32_t)g * 64u, ra);
-          tmem_ld32(tlane + acc_col(9, 0) + (uint32_t)g * 64u + 32u, rb);
+          tmem_ld32(tlane + acc_col(9) + (uint32_t)g * 64u, ra);
+          tmem_ld32(tlane + acc_col(9) + (uint32_t)g * 64u + 32u, rb);
+          const float4* bm = reinterpret_cast<const float4*>(F + P.b_m0 + g * 64);
+          const float4* wm = reinterpret_cast<const float4*>(F + P.w_m2 + g * 64);
           tmem_wait_ld();
           pin32(ra);
           pin32(rb);
-          const float* bm = F + P.b_m0 + g * 64;
-          const float* wm = F + P.w_m2 + g * 64;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float v = fmaf(__uint_as_float(ra[i]), inv, __ldg(bm + i));
-            v = v > 0.f ? v : 0.01f * v;
-            dm = fmaf(v, __ldg(wm + i), dm);
+          for (int i = 0; i < 8; ++i) {
+            const float4 bb = __ldg(bm + i), ww = __ldg(wm + i);
+            float v0 = fmaf(__uint_as_float(ra[4 * i + 0]), inv, bb.x), v1 = fmaf(__uint_as_float(ra[4 * i + 1]), inv, bb.y);
+            float v2 = fmaf(__uint_as_float(ra[4 * i + 2]), inv, bb.z), v3 = fmaf(__uint_as_float(ra[4 * i + 3]), inv, bb.w);
+            v0 = v0 > 0.f ? v0 : 0.01f * v0; v1 = v1 > 0.f ? v1 : 0.01f * v1;
+            v2 = v2 > 0.f ? v2 : 0.01f * v2; v3 = v3 > 0.f ? v3 : 0.01f * v3;
+            dm = fmaf(v0, ww.x, dm); dm = fmaf(v1, ww.y, dm); dm = fmaf(v2, ww.z, dm); dm = fmaf(v3, ww.w, dm);
           }
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float v = fmaf(__uint_as_float(rb[i]), inv, __ldg(bm + 32 + i));
-            v = v > 0.f ? v : 0.01f * v;
-            dm = fmaf(v, __ldg(wm + 32 + i), dm);
+          for (int i = 0; i < 8; ++i) {
+            const float4 bb = __ldg(bm + 8 + i), ww = __ldg(wm + 8 + i);
+            float v0 = fmaf(__uint_as_float(rb[4 * i + 0]), inv, bb.x), v1 = fmaf(__uint_as_float(rb[4 * i + 1]), inv, bb.y);
+            float v2 = fmaf(__uint_as_float(rb[4 * i + 2]), inv, bb.z), v3 = fmaf(__uint_as_float(rb[4 * i + 3]), inv, bb.w);
+            v0 = v0 > 0.f ? v0 : 0.01f * v0; v1 = v1 > 0.f ? v1 : 0.01f * v1;
+            v2 = v2 > 0.f ? v2 : 0.01f * v2; v3 = v3 > 0.f ? v3 : 0.01f * v3;
+            dm = fmaf(v0, ww.x, dm); dm = fmaf(v1, ww.y, dm); dm = fmaf(v2, ww.z, dm); dm = fmaf(v3, ww.w, dm);
           }
           if (g == 1) part[row].x = dm;
           epi_bar_sync(1);
           if (g == 0) o_mirror = sigmoidf_(dm + part[row].x + __ldg(F + P.b_m2));
           epi_bar_sync(2);
         }
-        // ---- final linear (step 8): f = W h8 + b, written over h8 chunk by chunk as its readers (steps 9, 8) finish ----
-        {
-          const float inv = __ldg(F + P.inv_scale + 8);
-          const float* bias = F + P.b_final + g * 64;
-#pragma unroll 1
-          for (int h = 0; h < 2; ++h) {
-            wait_acc(8, h);
-            const int c = 2 * h + g;
-            epi64<false, false, true, PREC3>(tlane + acc_col(8, h) + (uint32_t)g * 64u, bias + h * 128, inv,
-                                             sbase + SM_A_HI + (uint32_t)c * 16384u + rowoff,
-                                             sbase + SM_A_LO + (uint32_t)c * 16384u + rowoff, nullptr, d,
-                                             bar(BAR_AFREE + c), (free_phase >> c) & 1u);
-            free_phase ^= 1u << c;
-            a_ready(c);
-          }
-        }
+        // ---- final linear (step 8): f = W h8 + b, written over h8 (its readers, steps 9 and 8, are complete) ----
+        wait_acc(8);
+        layer_epilogue(TagFinal{}, 8, F + P.b_final, d);
         // ---- dir layer (step 10): relu(W_f f + [b + W_d embed(dir)]) -> rgb (mirror_nerf.py:199-204) ----
-        wait_acc(10, 0);
+        wait_acc(10);
         {
           const float inv = __ldg(F + P.inv_scale + 10);
-          const float* db = P.io.dirbias + ray * WH + g * 64;
-          const float* wr = F + P.w_rgb + g * 64;
+          const float4* db = reinterpret_cast<const float4*>(P.io.dirbias + ray * WH + g * 64);
+          const float4* wr = reinterpret_cast<const float4*>(F + P.w_rgb + g * 64);
           float d0 = 0.f, d1 = 0.f, d2 = 0.f;
           uint32_t ra[32], rb[32];
-          tmem_ld32(tlane + acc_col(10, 0) + (uint32_t)g * 64u, ra);
-          tmem_ld32(tlane + acc_col(10, 0) + (uint32_t)g * 64u + 32u, rb);
+          tmem_ld32(tlane + acc_col(10) + (uint32_t)g * 64u, ra);
+          tmem_ld32(tlane + acc_col(10) + (uint32_t)g * 64u + 32u, rb);
           tmem_wait_ld();
           pin32(ra);
           pin32(rb);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float v = fmaxf(fmaf(__uint_as_float(ra[i]), inv, __ldg(db + i)), 0.f);
-            d0 = fmaf(v, __ldg(wr + i), d0);
-            d1 = fmaf(v, __ldg(wr + WH + i), d1);
-            d2 = fmaf(v, __ldg(wr + 2 * WH + i), d2);
+          for (int i = 0; i < 8; ++i) {
+            const float4 bb = __ldg(db + i), w0 = __ldg(wr + i), w1 = __ldg(wr + WH / 4 + i), w2 = __ldg(wr + 2 * (WH / 4) + i);
+            const float v0 = fmaxf(fmaf(__uint_as_float(ra[4 * i + 0]), inv, bb.x), 0.f);
+            const float v1 = fmaxf(fmaf(__uint_as_float(ra[4 * i + 1]), inv, bb.y), 0.f);
+            const float v2 = fmaxf(fmaf(__uint_as_float(ra[4 * i + 2]), inv, bb.z), 0.f);
+            const float v3 = fmaxf(fmaf(__uint_as_float(ra[4 * i + 3]), inv, bb.w), 0.f);
+            d0 = fmaf(v0, w0.x, d0); d0 = fmaf(v1, w0.y, d0); d0 = fmaf(v2, w0.z, d0); d0 = fmaf(v3, w0.w, d0);
+            d1 = fmaf(v0, w1.x, d1); d1 = fmaf(v1, w1.y, d1); d1 = fmaf(v2, w1.z, d1); d1 = fmaf(v3, w1.w, d1);
+            d2 = fmaf(v0, w2.x, d2); d2 = fmaf(v1, w2.y, d2); d2 = fmaf(v2, w2.z, d2); d2 = fmaf(v3, w2.w, d2);
           }
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float v = fmaxf(fmaf(__uint_as_float(rb[i]), inv, __ldg(db + 32 + i)), 0.f);
-            d0 = fmaf(v, __ldg(wr + 32 + i), d0);
-            d1 = fmaf(v, __ldg(wr + WH + 32 + i), d1);
-            d2 = fmaf(v, __ldg(wr + 2 * WH + 32 + i), d2);
+          for (int i = 0; i < 8; ++i) {
+            const float4 bb = __ldg(db + 8 + i), w0 = __ldg(wr + 8 + i), w1 = __ldg(wr + WH / 4 + 8 + i),
+                         w2 = __ldg(wr + 2 * (WH / 4) + 8 + i);
+            const float v0 = fmaxf(fmaf(__uint_as_float(rb[4 * i + 0]), inv, bb.x), 0.f);
+            const float v1 = fmaxf(fmaf(__uint_as_float(rb[4 * i + 1]), inv, bb.y), 0.f);
+            const float v2 = fmaxf(fmaf(__uint_as_float(rb[4 * i + 2]), inv, bb.z), 0.f);
+            const float v3 = fmaxf(fmaf(__uint_as_float(rb[4 * i + 3]), inv, bb.w), 0.f);
+            d0 = fmaf(v0, w0.x, d0); d0 = fmaf(v1, w0.y, d0); d0 = fmaf(v2, w0.z, d0); d0 = fmaf(v3, w0.w, d0);
+            d1 = fmaf(v0, w1.x, d1); d1 = fmaf(v1, w1.y, d1); d1 = fmaf(v2, w1.z, d1); d1 = fmaf(v3, w1.w, d1);
+            d2 = fmaf(v0, w2.x, d2); d2 = fmaf(v1, w2.y, d2); d2 = fmaf(v2, w2.z, d2); d2 = fmaf(v3, w2.w, d2);
           }
           if (g == 1) part[row] = make_float4(d0, d1, d2, 0.f);
           epi_bar_sync(1);
@@ -747,8 +694,7 @@ int launch_field_tc(const mnrf_field* f, const FieldIO& io, int precision, cudaS
   P.io = io;
   P.trace = g_trace_buf;
   P.trace_cap = g_trace_cap;
-  const char* dbg = getenv("MNRF_TC_DEBUG");
-  P.debug = dbg != nullptr ? atoi(dbg) : 0;
+  P.debug = 0;
   P.n_tiles = (io.n_points + TILE_M - 1) / TILE_M;
   const int grid = P.n_tiles < num_sms ? P.n_tiles : num_sms;
   // algorithmic MACs of this launch (unpadded reference layer sizes)

@@ -108,8 +108,7 @@ __global__ void k_pack_tc(TcSrc src, const float* __restrict__ inv_scale, uint8_
   int s = blockIdx.y;
   int N = tc_step_n(s), K = tc_step_k(s);
   uint8_t* base = tc + tc_step_offset(s);
-  const int blob = TC_BLOB_BYTES;
-  const int nch = tc_step_chunks(s);
+  const int blob = tc_blob_bytes(s);
   float scale = 1.f / inv_scale[s];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N * K; i += gridDim.x * blockDim.x) {
     int n = i / K, k = i % K;
@@ -121,10 +120,9 @@ __global__ void k_pack_tc(TcSrc src, const float* __restrict__ inv_scale, uint8_
     __half hi = __float2half_rn(v);
     __half lo = __float2half_rn(v - __half2float(hi));
     int kc = k >> 5, kk = k & 31;
-    int h = n >> 7, nl = n & 127;  // 128-row N-half and row inside it
-    // K-major no-swizzle core matrices: 8 rows x 16 B contiguous; 8-row groups 128 B apart; K-groups 128*16 B apart
-    int off = (kk >> 3) * (128 * 16) + (nl >> 3) * 128 + (nl & 7) * 16 + (kk & 7) * 2;
-    uint8_t* chunk = base + (size_t)(h * nch + kc) * 2 * blob;
+    // K-major no-swizzle core matrices: 8 rows x 16 B contiguous; 8-row groups 128 B apart; K-groups N*16 B apart
+    int off = (kk >> 3) * (N * 16) + (n >> 3) * 128 + (n & 7) * 16 + (kk & 7) * 2;
+    uint8_t* chunk = base + (size_t)kc * 2 * blob;
     *reinterpret_cast<__half*>(chunk + off) = hi;
     *reinterpret_cast<__half*>(chunk + blob + off) = lo;
   }
