@@ -47,8 +47,8 @@ constexpr uint32_t SM_TOTAL = SM_BAR + 256;              // 231680 <= 232448
 constexpr int BAR_W_FULL = 0;    // [8]
 constexpr int BAR_W_EMPTY = 8;   // [8]
 constexpr int BAR_PE = 16;       // PE chunk written (8 warp arrivals)
-constexpr int BAR_A = 17;        // [4] A 64-column chunk written (8 warp arrivals)
-constexpr int BAR_ACC = 21;      // [4] accumulator of a GEMM step complete (tcgen05.commit)
+constexpr int BAR_A = 17;        // [5] A columns written (8 warp arrivals): [0] cols 0-31, [1..3] 64-col chunks 1..3, [4] cols 32-63
+constexpr int BAR_ACC = 22;      // [4] accumulator of a GEMM step complete (tcgen05.commit)
 constexpr int BAR_TMEM_SLOT = 30;
 
 constexpr uint32_t IDESC_N256 = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);  // f16 x f16 -> f32, K-major
@@ -139,12 +139,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 // wait for this thread's outstanding tcgen05.ld, then pin the destination registers behind the wait
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void pin32(uint32_t (&r)[32]) {
+template <int NR>
+__device__ __forceinline__ void pin(uint32_t (&r)[NR]) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(r[i]));
+  for (int i = 0; i < NR; ++i) asm volatile("" : "+r"(r[i]));
 }
+__device__ __forceinline__ void pin32(uint32_t (&r)[32]) { pin<32>(r); }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
 }
@@ -248,11 +259,11 @@ __device__ __forceinline__ void pe_fill(const float (&x)[3], uint32_t pe_hi, uin
 }
 
 // ---- epilogue of 32 accumulator columns of one row ------------------------------------------------------------------
-template <bool RELU, bool DOTS, bool WRITE_A, bool PREC3>
-__device__ __forceinline__ void epi32(const uint32_t (&r)[32], const float4 (&b)[8], float inv, uint32_t s_hi,
-                                      uint32_t s_lo, const float4* __restrict__ hw, float (&d)[4]) {
+template <int NC, bool RELU, bool DOTS, bool WRITE_A, bool PREC3>
+__device__ __forceinline__ void epi_cols(const uint32_t (&r)[NC], const float4 (&b)[NC / 4], float inv, uint32_t s_hi,
+                                         uint32_t s_lo, const float4* __restrict__ hw, float (&d)[4]) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < NC / 8; ++j) {
     const float4 b0 = b[2 * j], b1 = b[2 * j + 1];
     float v[8];
     v[0] = fmaf(__uint_as_float(r[8 * j + 0]), inv, b0.x);
@@ -307,7 +318,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
     if (sbase & 127u) { printf("mnrf field_tc: unaligned dynamic smem base %u\n", sbase); __trap(); }
     for (int i = 0; i < 8; ++i) { mbar_init(bar(BAR_W_FULL + i), 1); mbar_init(bar(BAR_W_EMPTY + i), 1); }
     mbar_init(bar(BAR_PE), 8);
-    for (int i = 0; i < 4; ++i) mbar_init(bar(BAR_A + i), 8);
+    for (int i = 0; i < 5; ++i) mbar_init(bar(BAR_A + i), 8);
     for (int i = 0; i < 4; ++i) mbar_init(bar(BAR_ACC + i), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -384,8 +395,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
               ah = dl_pe_hi + (uint32_t)kc * 512u; al = dl_pe_lo + (uint32_t)kc * 512u;
             } else {
               const int ka = kc - n_pe;
-              if ((ka & 1) == 0 && !a_reused) {  // first touch of a 64-column chunk of a new activation version
-                const int c = ka >> 1;
+              // first touch of freshly written activation columns: chunk 0 is signalled in two 32-column halves
+              if (((ka & 1) == 0 || ka == 1) && !a_reused) {
+                const int c = ka == 1 ? 4 : (ka >> 1);
                 mbar_wait(bar(BAR_A + c), (a_phase >> c) & 1u);
                 a_phase ^= 1u << c;
                 trace_ev(P, trc, 0, 1, 2, s, c);
@@ -493,23 +505,45 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
     // chunk's TMEM load in flight while the current one is converted.
     auto layer_epilogue = [&](auto tag, int s, const float* bias256, float (&d)[4]) {
       constexpr bool RELU = decltype(tag)::relu, DOTS = decltype(tag)::dots, WRITE_A = decltype(tag)::write_a;
+      const float4* b4 = reinterpret_cast<const float4*>(bias256);
+      // everything that does not depend on the accumulator is fetched before waiting for it
       const float inv = __ldg(F + P.inv_scale + s);
-      const uint32_t tacc = tlane + acc_col(s) + (uint32_t)g * 32u;
-      const float4* b4 = reinterpret_cast<const float4*>(bias256 + g * 32);
-      uint32_t ra[32], rb[32];
-      float4 b[8];
-      tmem_ld32(tacc, ra);
+      float4 b0a[4], b0b[4], b[8];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int i = 0; i < 4; ++i) { b0a[i] = __ldg(b4 + 4 * g + i); b0b[i] = __ldg(b4 + 8 + 4 * g + i); }
+      wait_acc(s);
+      const uint32_t tcol = tlane + acc_col(s);
+      // chunk 0 goes out as two 32-column K chunks (16 columns per warp each) so that the next layer's MMAs can start
+      // after a quarter of a chunk; chunks 1..3: 32 columns per warp, next chunk's TMEM load in flight during conversion
+      uint32_t r0a[16], r0b[16], ra[32], rb[32];
+      tmem_ld16(tcol + (uint32_t)g * 16u, r0a);
+      tmem_ld16(tcol + 32u + (uint32_t)g * 16u, r0b);
+      tmem_wait_ld();
+      tmem_ld32(tcol + 64u + (uint32_t)g * 32u, rb);  // chunk 1
+      pin<16>(r0a);
+      pin<16>(r0b);
+      {
+        const uint32_t off = (uint32_t)(g * 2) * 2048u + rowoff;
+        epi_cols<16, RELU, DOTS, WRITE_A, PREC3>(r0a, b0a, inv, sbase + SM_A_HI + off, sbase + SM_A_LO + off, headw + g * 16, d);
+        if (WRITE_A) a_ready(0);
+      }
+      {
+        const uint32_t off = (uint32_t)(4 + g * 2) * 2048u + rowoff;
+        epi_cols<16, RELU, DOTS, WRITE_A, PREC3>(r0b, b0b, inv, sbase + SM_A_HI + off, sbase + SM_A_LO + off, headw + 32 + g * 16, d);
+        if (WRITE_A) a_ready(4);
+      }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) b[i] = __ldg(b4 + c * 16 + i);
+      for (int c = 1; c < 4; ++c) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) b[i] = __ldg(b4 + c * 16 + g * 8 + i);
         tmem_wait_ld();  // the load of chunk c (issued one iteration ago) has landed
         if (c < 3) {     // next chunk's load flies while this chunk is converted
-          if (c & 1) tmem_ld32(tacc + (uint32_t)(c + 1) * 64u, ra); else tmem_ld32(tacc + (uint32_t)(c + 1) * 64u, rb);
+          if (c & 1) tmem_ld32(tcol + (uint32_t)(c + 1) * 64u + (uint32_t)g * 32u, ra);
+          else       tmem_ld32(tcol + (uint32_t)(c + 1) * 64u + (uint32_t)g * 32u, rb);
         }
         const uint32_t off = (uint32_t)(c * 8 + g * 4) * 2048u + rowoff;
-        if (c & 1) { pin32(rb); epi32<RELU, DOTS, WRITE_A, PREC3>(rb, b, inv, sbase + SM_A_HI + off, sbase + SM_A_LO + off, headw + c * 64 + g * 32, d); }
-        else       { pin32(ra); epi32<RELU, DOTS, WRITE_A, PREC3>(ra, b, inv, sbase + SM_A_HI + off, sbase + SM_A_LO + off, headw + c * 64 + g * 32, d); }
+        if (c & 1) { pin32(rb); epi_cols<32, RELU, DOTS, WRITE_A, PREC3>(rb, b, inv, sbase + SM_A_HI + off, sbase + SM_A_LO + off, headw + c * 64 + g * 32, d); }
+        else       { pin32(ra); epi_cols<32, RELU, DOTS, WRITE_A, PREC3>(ra, b, inv, sbase + SM_A_HI + off, sbase + SM_A_LO + off, headw + c * 64 + g * 32, d); }
         if (WRITE_A) a_ready(c);
       }
     };
@@ -526,7 +560,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
       // ---- trunk layers 1..8 (steps 0..7) ----
 #pragma unroll 1
       for (int s = 0; s < 8; ++s) {
-        wait_acc(s);
         const float* bias = F + P.b_trunk[s];
         if (s < 7) layer_epilogue(TagTrunk{}, s, bias, d);
         else if (!P.io.sigma_only) layer_epilogue(TagLast{}, s, bias, d);
@@ -589,7 +622,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
           epi_bar_sync(2);
         }
         // ---- final linear (step 8): f = W h8 + b, written over h8 (its readers, steps 9 and 8, are complete) ----
-        wait_acc(8);
         layer_epilogue(TagFinal{}, 8, F + P.b_final, d);
         // ---- dir layer (step 10): relu(W_f f + [b + W_d embed(dir)]) -> rgb (mirror_nerf.py:199-204) ----
         wait_acc(10);
