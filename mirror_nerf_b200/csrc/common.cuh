@@ -51,7 +51,22 @@ constexpr int TC_TOTAL_BYTES = tc_step_offset(TC_NUM_STEPS);
 // ------------------------------------------------------------------------------------------------
 // fp32 section layout (float offsets inside mnrf_field::f32)
 // ------------------------------------------------------------------------------------------------
+// Contiguous "epilogue table" inside the fp32 section (float offsets relative to F32Layout::epi_tab): everything the
+// tensor-core kernel's epilogues read that is uniform across a warp.  It is copied to __constant__ memory before a launch,
+// so those reads become constant-cache (LDC) accesses instead of global loads.
+constexpr int ET_BIAS = 0;                      // [9][256]: trunk layers 1..8, xyz_encoding_final
+constexpr int ET_HEADW = ET_BIAS + 9 * 256;     // float4[256]: {w_sigma[c], Wn_fold[0..2][c]}
+constexpr int ET_B_M0 = ET_HEADW + 4 * 256;     // [128]
+constexpr int ET_W_M2 = ET_B_M0 + 128;          // [128]
+constexpr int ET_W_RGB = ET_W_M2 + 128;         // [3][128]
+constexpr int ET_HEADB = ET_W_RGB + 3 * 128;    // {b_sigma, bn_fold[0..2]}
+constexpr int ET_INV_SCALE = ET_HEADB + 4;      // [12] (11 used)
+constexpr int ET_B_M2 = ET_INV_SCALE + 12;      // [4] (1 used)
+constexpr int ET_B_RGB = ET_B_M2 + 4;           // [4] (3 used)
+constexpr int ET_TOTAL = ET_B_RGB + 4;          // 3992 floats = 15,968 bytes
+
 struct F32Layout {
+  int epi_tab;
   // transposed, K padded to a multiple of 4 rows: Wt[k][n]
   int wt_trunk[8];   // layers 1..8
   int wt_final, wt_dir, wt_n0, wt_m0;
@@ -83,21 +98,22 @@ inline F32Layout make_f32_layout() {
   L.wt_m0 = take(W * WH);
   for (int l = 0; l < 8; ++l) L.w_trunk[l] = take(W * trunk_k(l));
   L.w_sigma = take(W);
-  L.w_rgb = take(3 * WH);
   L.w_n1 = take(3 * WH);
-  L.w_m2 = take(WH);
-  for (int l = 0; l < 8; ++l) L.b_trunk[l] = take(W);
-  L.b_final = take(W);
   L.b_dir = take(WH);
   L.b_sigma = take(4);
-  L.b_rgb = take(4);
   L.b_n0 = take(WH);
   L.b_n1 = take(4);
-  L.b_m0 = take(WH);
-  L.b_m2 = take(4);
-  L.headw = take(4 * W);
-  L.headb = take(4);
-  L.inv_scale = take(16);
+  L.epi_tab = take(ET_TOTAL);
+  for (int l = 0; l < 8; ++l) L.b_trunk[l] = L.epi_tab + ET_BIAS + 256 * l;
+  L.b_final = L.epi_tab + ET_BIAS + 256 * 8;
+  L.headw = L.epi_tab + ET_HEADW;
+  L.b_m0 = L.epi_tab + ET_B_M0;
+  L.w_m2 = L.epi_tab + ET_W_M2;
+  L.w_rgb = L.epi_tab + ET_W_RGB;
+  L.headb = L.epi_tab + ET_HEADB;
+  L.inv_scale = L.epi_tab + ET_INV_SCALE;
+  L.b_m2 = L.epi_tab + ET_B_M2;
+  L.b_rgb = L.epi_tab + ET_B_RGB;
   L.absmax = take(16);
   L.total = o;
   return L;

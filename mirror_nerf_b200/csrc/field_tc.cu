@@ -67,6 +67,10 @@ struct TcParams {
   int debug;
 };
 
+// Epilogue table (biases, head weights, scales: common.cuh ET_*): copied device-to-device into constant memory in front of
+// every launch (stream ordered), so the warp-uniform epilogue reads are constant-cache accesses instead of global loads.
+__constant__ float c_epi[ET_TOTAL];
+
 // device-side tracing (mnrf_debug_set_trace): lane 0 of a warp of CTA 0 logs (clock64, tag) with plain stores into its own
 // region of the buffer (no atomics, so the perturbation is one clock read + one store): region r = who, 8192 events each
 struct TraceCtx { unsigned int n; };
@@ -278,7 +282,7 @@ __device__ __forceinline__ void epi_cols(const uint32_t (&r)[NC], const float4 (
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         v[i] = fmaxf(v[i], 0.f);
-        const float4 w = __ldg(hw + 8 * j + i);
+        const float4 w = hw[8 * j + i];
         d[0] = fmaf(v[i], w.x, d[0]); d[1] = fmaf(v[i], w.y, d[1]);
         d[2] = fmaf(v[i], w.z, d[2]); d[3] = fmaf(v[i], w.w, d[3]);
       }
@@ -461,7 +465,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
     const uint32_t rowoff = (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u;
     const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
     const float* F = P.f32;
-    const float4* headw = reinterpret_cast<const float4*>(F + P.headw);
+    const float4* headw = reinterpret_cast<const float4*>(c_epi + ET_HEADW);
     float4* part = reinterpret_cast<float4*>(smem + SM_PART);
     uint32_t acc_phase = 0;  // one parity bit per accumulator barrier
     TraceCtx trc{0};
@@ -507,10 +511,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
       constexpr bool RELU = decltype(tag)::relu, DOTS = decltype(tag)::dots, WRITE_A = decltype(tag)::write_a;
       const float4* b4 = reinterpret_cast<const float4*>(bias256);
       // everything that does not depend on the accumulator is fetched before waiting for it
-      const float inv = __ldg(F + P.inv_scale + s);
+      const float inv = c_epi[ET_INV_SCALE + s];
       float4 b0a[4], b0b[4], b[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { b0a[i] = __ldg(b4 + 4 * g + i); b0b[i] = __ldg(b4 + 8 + 4 * g + i); }
+      for (int i = 0; i < 4; ++i) { b0a[i] = b4[4 * g + i]; b0b[i] = b4[8 + 4 * g + i]; }
       wait_acc(s);
       const uint32_t tcol = tlane + acc_col(s);
       // chunk 0 goes out as two 32-column K chunks (16 columns per warp each) so that the next layer's MMAs can start
@@ -535,7 +539,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
 #pragma unroll
       for (int c = 1; c < 4; ++c) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) b[i] = __ldg(b4 + c * 16 + g * 8 + i);
+        for (int i = 0; i < 8; ++i) b[i] = b4[c * 16 + g * 8 + i];
         tmem_wait_ld();  // the load of chunk c (issued one iteration ago) has landed
         if (c < 3) {     // next chunk's load flies while this chunk is converted
           if (c & 1) tmem_ld32(tcol + (uint32_t)(c + 1) * 64u + (uint32_t)g * 32u, ra);
@@ -560,7 +564,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
       // ---- trunk layers 1..8 (steps 0..7) ----
 #pragma unroll 1
       for (int s = 0; s < 8; ++s) {
-        const float* bias = F + P.b_trunk[s];
+        const float* bias = c_epi + ET_BIAS + 256 * s;
         if (s < 7) layer_epilogue(TagTrunk{}, s, bias, d);
         else if (!P.io.sigma_only) layer_epilogue(TagLast{}, s, bias, d);
         else layer_epilogue(TagSigma{}, s, bias, d);
@@ -573,7 +577,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
         epi_bar_sync(1);
         if (g == 0) {
           const float4 o = part[row];
-          const float4 hb = __ldg(reinterpret_cast<const float4*>(F + P.headb));
+          const float4 hb = *reinterpret_cast<const float4*>(c_epi + ET_HEADB);
           o_sigma = d[0] + o.x + hb.x;
           if (P.has_normal) {
             const float a = d[1] + o.y + hb.y, b = d[2] + o.z + hb.z, cc = d[3] + o.w + hb.w;
@@ -588,19 +592,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
         // ---- mirror head (step 9): LeakyReLU(0.01) -> Linear(128,1) -> sigmoid (mirror_nerf.py:94-99) ----
         if (P.has_mirror) {
           wait_acc(9);
-          const float inv = __ldg(F + P.inv_scale + 9);
+          const float inv = c_epi[ET_INV_SCALE + 9];
           float dm = 0.f;
           uint32_t ra[32], rb[32];
           tmem_ld32(tlane + acc_col(9) + (uint32_t)g * 64u, ra);
           tmem_ld32(tlane + acc_col(9) + (uint32_t)g * 64u + 32u, rb);
-          const float4* bm = reinterpret_cast<const float4*>(F + P.b_m0 + g * 64);
-          const float4* wm = reinterpret_cast<const float4*>(F + P.w_m2 + g * 64);
+          const float4* bm = reinterpret_cast<const float4*>(c_epi + ET_B_M0 + g * 64);
+          const float4* wm = reinterpret_cast<const float4*>(c_epi + ET_W_M2 + g * 64);
           tmem_wait_ld();
           pin32(ra);
           pin32(rb);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 bb = __ldg(bm + i), ww = __ldg(wm + i);
+            const float4 bb = bm[i], ww = wm[i];
             float v0 = fmaf(__uint_as_float(ra[4 * i + 0]), inv, bb.x), v1 = fmaf(__uint_as_float(ra[4 * i + 1]), inv, bb.y);
             float v2 = fmaf(__uint_as_float(ra[4 * i + 2]), inv, bb.z), v3 = fmaf(__uint_as_float(ra[4 * i + 3]), inv, bb.w);
             v0 = v0 > 0.f ? v0 : 0.01f * v0; v1 = v1 > 0.f ? v1 : 0.01f * v1;
@@ -609,7 +613,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 bb = __ldg(bm + 8 + i), ww = __ldg(wm + 8 + i);
+            const float4 bb = bm[8 + i], ww = wm[8 + i];
             float v0 = fmaf(__uint_as_float(rb[4 * i + 0]), inv, bb.x), v1 = fmaf(__uint_as_float(rb[4 * i + 1]), inv, bb.y);
             float v2 = fmaf(__uint_as_float(rb[4 * i + 2]), inv, bb.z), v3 = fmaf(__uint_as_float(rb[4 * i + 3]), inv, bb.w);
             v0 = v0 > 0.f ? v0 : 0.01f * v0; v1 = v1 > 0.f ? v1 : 0.01f * v1;
@@ -618,17 +622,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
           }
           if (g == 1) part[row].x = dm;
           epi_bar_sync(1);
-          if (g == 0) o_mirror = sigmoidf_(dm + part[row].x + __ldg(F + P.b_m2));
+          if (g == 0) o_mirror = sigmoidf_(dm + part[row].x + c_epi[ET_B_M2]);
           epi_bar_sync(2);
         }
         // ---- final linear (step 8): f = W h8 + b, written over h8 (its readers, steps 9 and 8, are complete) ----
-        layer_epilogue(TagFinal{}, 8, F + P.b_final, d);
+        layer_epilogue(TagFinal{}, 8, c_epi + ET_BIAS + 256 * 8, d);
         // ---- dir layer (step 10): relu(W_f f + [b + W_d embed(dir)]) -> rgb (mirror_nerf.py:199-204) ----
         wait_acc(10);
         {
-          const float inv = __ldg(F + P.inv_scale + 10);
+          const float inv = c_epi[ET_INV_SCALE + 10];
           const float4* db = reinterpret_cast<const float4*>(P.io.dirbias + ray * WH + g * 64);
-          const float4* wr = reinterpret_cast<const float4*>(F + P.w_rgb + g * 64);
+          const float4* wr = reinterpret_cast<const float4*>(c_epi + ET_W_RGB + g * 64);
           float d0 = 0.f, d1 = 0.f, d2 = 0.f;
           uint32_t ra[32], rb[32];
           tmem_ld32(tlane + acc_col(10) + (uint32_t)g * 64u, ra);
@@ -638,7 +642,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
           pin32(rb);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 bb = __ldg(db + i), w0 = __ldg(wr + i), w1 = __ldg(wr + WH / 4 + i), w2 = __ldg(wr + 2 * (WH / 4) + i);
+            const float4 bb = __ldg(db + i), w0 = wr[i], w1 = wr[WH / 4 + i], w2 = wr[2 * (WH / 4) + i];
             const float v0 = fmaxf(fmaf(__uint_as_float(ra[4 * i + 0]), inv, bb.x), 0.f);
             const float v1 = fmaxf(fmaf(__uint_as_float(ra[4 * i + 1]), inv, bb.y), 0.f);
             const float v2 = fmaxf(fmaf(__uint_as_float(ra[4 * i + 2]), inv, bb.z), 0.f);
@@ -649,8 +653,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 bb = __ldg(db + 8 + i), w0 = __ldg(wr + 8 + i), w1 = __ldg(wr + WH / 4 + 8 + i),
-                         w2 = __ldg(wr + 2 * (WH / 4) + 8 + i);
+            const float4 bb = __ldg(db + 8 + i), w0 = wr[8 + i], w1 = wr[WH / 4 + 8 + i], w2 = wr[2 * (WH / 4) + 8 + i];
             const float v0 = fmaxf(fmaf(__uint_as_float(rb[4 * i + 0]), inv, bb.x), 0.f);
             const float v1 = fmaxf(fmaf(__uint_as_float(rb[4 * i + 1]), inv, bb.y), 0.f);
             const float v2 = fmaxf(fmaf(__uint_as_float(rb[4 * i + 2]), inv, bb.z), 0.f);
@@ -663,9 +666,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
           epi_bar_sync(1);
           if (g == 0) {
             const float4 o = part[row];
-            o_rgb[0] = sigmoidf_(d0 + o.x + __ldg(F + P.b_rgb + 0));
-            o_rgb[1] = sigmoidf_(d1 + o.y + __ldg(F + P.b_rgb + 1));
-            o_rgb[2] = sigmoidf_(d2 + o.z + __ldg(F + P.b_rgb + 2));
+            o_rgb[0] = sigmoidf_(d0 + o.x + c_epi[ET_B_RGB + 0]);
+            o_rgb[1] = sigmoidf_(d1 + o.y + c_epi[ET_B_RGB + 1]);
+            o_rgb[2] = sigmoidf_(d2 + o.z + c_epi[ET_B_RGB + 2]);
           }
           epi_bar_sync(2);
         }
@@ -731,6 +734,7 @@ int launch_field_tc(const mnrf_field* f, const FieldIO& io, int precision, cudaS
   const int grid = P.n_tiles < num_sms ? P.n_tiles : num_sms;
   // algorithmic MACs of this launch (unpadded reference layer sizes)
   const double macs = (double)io.n_points * (io.sigma_only ? (double)mnrf_macs_sigma_only() : (double)mnrf_macs_full());
+  MNRF_CUDA_OK(cudaMemcpyToSymbolAsync(c_epi, f->f32 + L.epi_tab, sizeof(float) * ET_TOTAL, 0, cudaMemcpyDeviceToDevice, st));
   prof_begin(st);
   if (precision == 3) k_field_tc<true><<<grid, NUM_THREADS, SM_TOTAL, st>>>(P);
   else                k_field_tc<false><<<grid, NUM_THREADS, SM_TOTAL, st>>>(P);
