@@ -80,6 +80,11 @@ int mnrf_field_eval_points(const mnrf_field* f, int impl, const float* x, int B,
 /* Embedding.forward (mirror_nerf.py:21-38): out (n, 3+6*n_freqs) = [x, sin(2^k x), cos(2^k x) ...]. */
 int mnrf_embed(const float* x, int n, int n_freqs, float* out, void* stream);
 
+/* Rays of one pinhole view, generated on the device (R/datasets/ray_utils.py:6-53, R/datasets/blender.py:158-168):
+ * c2w_host = 12 HOST floats (3x4 row-major camera-to-world); rays (H*W, 8) = [o, normalised d, near, far]. */
+int mnrf_generate_rays(int H, int W, float focal, const float* c2w_host, float near, float far, float* rays,
+                       void* stream);
+
 /* ---- sampler ----------------------------------------------------------------------------------- */
 
 /* z_steps: the S values of torch.linspace(0,1,S) (taken from the host library so they are bit-identical,
@@ -186,6 +191,11 @@ int mnrf_reflect_rays(const float* rays, const float* x_surface, const float* no
  * index (n) int32 optional: destination row or -1.  count: device int.  */
 int mnrf_compact_rows(const float* in, const float* mask, int n, int row_floats, float* out, int* index,
                       int* count, void* stream);
+
+/* dense[i] = alpha*dense[i] + beta*compact[index[i]] for rows with index[i] >= 0 (index NULL: identity; compact NULL: scale
+ * only).  Accumulates the extra jittered reflections of the roughness cone (eval.py:623-674) into the first one. */
+int mnrf_axpy_rows(float* dense, const float* compact, const int* index, int n, int c, float alpha, float beta,
+                   void* stream);
 
 /* rgb = m*reflect + (1-m)*base (eval.py:680-697).  child_rgb/child_depth are the bounce results, either
  * dense (index == NULL, n rows) or compacted (index[i] = row in child or -1 -> reflect := base).

@@ -56,6 +56,8 @@ _SIGS = {
                                      c_float_p, c_float_p, C.c_void_p]),
     "mnrf_field_eval_points": (c_int, [C.c_void_p, c_int, c_float_p, c_int, c_int, c_float_p, c_float_p, c_float_p,
                                        c_float_p, c_float_p, c_float_p, C.c_void_p]),
+    "mnrf_generate_rays": (c_int, [c_int, c_int, C.c_float, C.POINTER(C.c_float), C.c_float, C.c_float, c_float_p,
+                                   C.c_void_p]),
     "mnrf_embed": (c_int, [c_float_p, c_int, c_int, c_float_p, C.c_void_p]),
     "mnrf_coarse_z": (c_int, [c_float_p, c_int, c_float_p, c_int, c_int, C.c_float, c_float_p, c_float_p, C.c_void_p]),
     "mnrf_searchsorted_right": (c_int, [c_float_p, c_int, c_int, c_float_p, c_int, c_int, C.c_void_p, C.c_void_p]),
@@ -74,6 +76,7 @@ _SIGS = {
     "mnrf_reflect_rays": (c_int, [c_float_p, c_float_p, c_float_p, c_float_p, c_int, C.c_float, c_float_p, c_float_p,
                                   C.c_void_p, C.c_void_p]),
     "mnrf_compact_rows": (c_int, [c_float_p, c_float_p, c_int, c_int, c_float_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mnrf_axpy_rows": (c_int, [c_float_p, c_float_p, C.c_void_p, c_int, c_int, C.c_float, C.c_float, C.c_void_p]),
     "mnrf_blend_reflection": (c_int, [c_float_p, c_float_p, c_float_p, c_float_p, C.c_void_p, c_int, c_float_p,
                                       c_float_p, c_float_p, C.c_void_p]),
 }

@@ -219,6 +219,12 @@ int mnrf_field_eval_points(const mnrf_field* f, int impl, const float* x, int B,
   return rc;
 }
 
+int mnrf_generate_rays(int H, int W, float focal, const float* c2w_host, float near, float far, float* rays,
+                       void* stream) {
+  MNRF_REQUIRE(c2w_host && rays && focal > 0.f, "generate_rays: bad argument");
+  return launch_generate_rays(H, W, focal, c2w_host, near, far, rays, S_(stream));
+}
+
 int mnrf_embed(const float* x, int n, int n_freqs, float* out, void* stream) {
   MNRF_REQUIRE(x && out && n_freqs >= 0 && n_freqs <= 32, "embed: bad argument");
   return launch_embed(x, n, n_freqs, out, S_(stream));
@@ -407,6 +413,12 @@ int mnrf_compact_rows(const float* in, const float* mask, int n, int row_floats,
                       void* stream) {
   MNRF_REQUIRE(mask && count && (out == nullptr || in != nullptr), "compact_rows: null argument");
   return launch_compact(in, mask, n, row_floats, out, index, count, S_(stream));
+}
+
+int mnrf_axpy_rows(float* dense, const float* compact, const int* index, int n, int c, float alpha, float beta,
+                   void* stream) {
+  MNRF_REQUIRE(dense != nullptr && c >= 1, "axpy_rows: bad argument");
+  return launch_axpy_rows(dense, compact, index, n, c, alpha, beta, S_(stream));
 }
 
 int mnrf_blend_reflection(const float* base_rgb, const float* mask, const float* child_rgb, const float* child_depth,

@@ -190,6 +190,8 @@ struct FieldIO {
 
 int launch_coarse_z(const float* rays, int n, const float* z_steps, int S, int use_disp, float perturb,
                     const float* u, float* z_out, cudaStream_t st);
+int launch_generate_rays(int H, int W, float focal, const float* c2w_host, float near, float far, float* rays,
+                         cudaStream_t st);
 int launch_embed(const float* x, int n, int n_freqs, float* out, cudaStream_t st);
 int launch_searchsorted(const float* cdf, int n, int m, const float* u, int n_u, int u_stride, int64_t* inds,
                         cudaStream_t st);
@@ -203,6 +205,8 @@ int launch_reflect(const float* rays, const float* x_surface, const float* norma
                    float* sec, float* refl, int* any_mirror, cudaStream_t st);
 int launch_compact(const float* in, const float* mask, int n, int row_floats, float* out, int* index, int* count,
                    cudaStream_t st);
+int launch_axpy_rows(float* dense, const float* compact, const int* index, int n, int c, float alpha, float beta,
+                     cudaStream_t st);
 int launch_blend(const float* base, const float* mask, const float* child_rgb, const float* child_depth,
                  const int* index, int n, float* rgb_out, float* rgb_reflect, float* depth_reflect, cudaStream_t st);
 

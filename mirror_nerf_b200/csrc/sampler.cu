@@ -49,6 +49,27 @@ __global__ void k_embed(const float* __restrict__ x, int n, int n_freqs, float* 
   out[i] = v;
 }
 
+// pinhole camera rays (R/datasets/ray_utils.py:6-53 + R/datasets/blender.py:158-168): pixel (i = column, j = row),
+// direction [(i - W/2)/f, -(j - H/2)/f, -1] (no +0.5), rotated by c2w[:, :3], normalised; origin c2w[:, 3]
+struct Pose { float m[12]; };
+__global__ void k_generate_rays(int H, int W, float focal, Pose c2w, float near, float far, float* __restrict__ rays) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= H * W) return;
+  const int j = idx / W, i = idx % W;
+  const float dx = __fdiv_rn(__fsub_rn((float)i, W * 0.5f), focal);
+  const float dy = -__fdiv_rn(__fsub_rn((float)j, H * 0.5f), focal);
+  const float dz = -1.f;
+  float r[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    r[k] = __fadd_rn(__fadd_rn(__fmul_rn(dx, c2w.m[4 * k + 0]), __fmul_rn(dy, c2w.m[4 * k + 1])), __fmul_rn(dz, c2w.m[4 * k + 2]));
+  const float n = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(r[0], r[0]), __fmul_rn(r[1], r[1])), __fmul_rn(r[2], r[2])));
+  float* o = rays + (size_t)idx * 8;
+  o[0] = c2w.m[3]; o[1] = c2w.m[7]; o[2] = c2w.m[11];
+  o[3] = __fdiv_rn(r[0], n); o[4] = __fdiv_rn(r[1], n); o[5] = __fdiv_rn(r[2], n);
+  o[6] = near; o[7] = far;
+}
+
 // count of cdf entries <= u  (torch.searchsorted(..., right=True)) on a sorted row of length m
 __device__ __forceinline__ int upper_bound(const float* cdf, int m, float u) {
   int lo = 0, hi = m;
@@ -189,6 +210,16 @@ int launch_coarse_z(const float* rays, int n, const float* z_steps, int S, int u
   MNRF_REQUIRE(!(perturb > 0.f) || u != nullptr, "coarse_z: perturb > 0 needs perturb_u");
   long long total = (long long)n * S;
   k_coarse_z<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(rays, n, z_steps, S, use_disp, perturb, u, z_out);
+  MNRF_LAUNCH_OK();
+  return 0;
+}
+
+int launch_generate_rays(int H, int W, float focal, const float* c2w_host, float near, float far, float* rays,
+                         cudaStream_t st) {
+  if (H <= 0 || W <= 0) return 0;
+  Pose p;
+  for (int i = 0; i < 12; ++i) p.m[i] = c2w_host[i];
+  k_generate_rays<<<(H * W + 255) / 256, 256, 0, st>>>(H, W, focal, p, near, far, rays);
   MNRF_LAUNCH_OK();
   return 0;
 }

@@ -130,7 +130,29 @@ __global__ void k_blend(const float* __restrict__ base, const float* __restrict_
   }
 }
 
+// dense[i] = alpha * dense[i] + beta * compact[index[i]]  for rows with index[i] >= 0 (compact may be NULL: beta term dropped)
+__global__ void k_axpy_rows(float* __restrict__ dense, const float* __restrict__ compact, const int* __restrict__ index, int n,
+                            int c, float alpha, float beta) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int src = index != nullptr ? index[i] : i;
+  if (src < 0) return;
+  for (int k = 0; k < c; ++k) {
+    float v = alpha * dense[(size_t)i * c + k];
+    if (compact != nullptr) v += beta * compact[(size_t)src * c + k];
+    dense[(size_t)i * c + k] = v;
+  }
+}
+
 }  // namespace
+
+int launch_axpy_rows(float* dense, const float* compact, const int* index, int n, int c, float alpha, float beta,
+                     cudaStream_t st) {
+  if (n <= 0) return 0;
+  k_axpy_rows<<<(n + 255) / 256, 256, 0, st>>>(dense, compact, index, n, c, alpha, beta);
+  MNRF_LAUNCH_OK();
+  return 0;
+}
 
 int launch_reflect(const float* rays, const float* x_surface, const float* normal, float* mask, int n, float near2,
                    float* sec, float* refl, int* any_mirror, cudaStream_t st) {

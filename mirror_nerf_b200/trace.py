@@ -15,7 +15,7 @@ from . import _lib
 from .mirror_nerf import _ptr, _stream_ptr
 from .rendering import render_rays
 
-__all__ = ["render_rays_recursive", "reflect_rays", "compact_rows", "blend_reflection"]
+__all__ = ["render_rays_recursive", "reflect_rays", "compact_rows", "blend_reflection", "axpy_rows"]
 
 RAY_FORWARD_OFFSET = 0.1  # near of a secondary ray (eval.py:529, train.py:232)
 
@@ -67,14 +67,31 @@ def blend_reflection(base_rgb, mask, child_rgb, child_depth, index=None):
     return rgb, rgb_reflect, depth_reflect
 
 
+def axpy_rows(dense, compact, index, alpha, beta):
+    """dense[i] = alpha*dense[i] + beta*compact[index[i]] for rows with index[i] >= 0, in place."""
+    lib = _lib.load()
+    n, c = dense.shape
+    with torch.cuda.device(dense.device):
+        _lib.check(lib.mnrf_axpy_rows(_ptr(dense), _ptr(None if compact is None else compact.contiguous()), _ptr(index),
+                                      n, c, float(alpha), float(beta), _stream_ptr()), "mnrf_axpy_rows")
+    return dense
+
+
 def render_rays_recursive(models, embeddings, rays, N_samples=64, use_disp=False, perturb=0, noise_std=0,
                           N_importance=0, chunk=1024 * 32, white_back=False, max_recursive_level=1,
-                          only_trace_rays_in_mirrors=None, test_time=True, _level=0, render_fn=None, **kwargs):
+                          only_trace_rays_in_mirrors=None, test_time=True, _level=0, render_fn=None,
+                          normal_noise_std=0.0, trace_ray_times=0, normal_noises=None, **kwargs):
     """Eval-semantics recursion (R/eval.py:132-725): level 0 re-traces ALL rays of a batch that contains a mirror
     pixel, deeper levels only the mirror rays; `only_trace_rays_in_mirrors=True` compacts at every level (train.py
     semantics).  Returns the level-0 render_rays dict with rgb_{typ} blended plus rgb_{typ}_direct/_reflect,
     depth_{typ}_reflect and reflect_direction.  `render_fn(rays) -> dict` replaces render_rays (used by the tests to
-    check the recursion logic on a smooth stand-in field)."""
+    check the recursion logic on a smooth stand-in field).
+
+    Roughness cone (R/eval.py:506-511,623-674, --app_control_mirror_roughness): with
+    `normal_noise_std` > 0 the surface normal is jittered by N(0, std^2) before reflecting, and `trace_ray_times` extra
+    jittered reflections of the MIRROR rays are rendered and averaged with the first one (the reference adds an
+    (N_mirror,3) tensor to an (N_rays,3) one at level 0 -- a latent shape bug; the evident intent, mirror rays only, is
+    what is implemented).  `normal_noises`: optional list of trace_ray_times+1 explicit (n,3) noise tensors (tests)."""
     kwargs.setdefault("compute_normal", False)
     if render_fn is not None:
         res = render_fn(rays)
@@ -87,7 +104,15 @@ def render_rays_recursive(models, embeddings, rays, N_samples=64, use_disp=False
     rays = rays.detach().contiguous()
     normal = res.get(f"surface_normal_{typ}", res.get(f"surface_normal_grad_{typ}"))
     mask = res[f"mirror_mask_{typ}"]
-    sec, refl, flag = reflect_rays(rays, res[f"x_surface_{typ}"], normal, mask)
+    rough = normal_noise_std > 0
+
+    def jitter(t):
+        if not rough:
+            return normal
+        nz = normal_noises[t].to(normal) if normal_noises is not None else torch.randn_like(normal) * normal_noise_std
+        return (normal + nz).contiguous()
+
+    sec, refl, flag = reflect_rays(rays, res[f"x_surface_{typ}"], jitter(0), mask)
     base = res[f"rgb_{typ}"]
     res[f"rgb_{typ}_reflect"] = torch.zeros_like(base)
     res[f"depth_{typ}_reflect"] = torch.zeros_like(res[f"depth_{typ}"])
@@ -102,7 +127,31 @@ def render_rays_recursive(models, embeddings, rays, N_samples=64, use_disp=False
         return res
     sub = render_rays_recursive(models, embeddings, sec, N_samples, use_disp, perturb, noise_std, N_importance, chunk,
                                 white_back, max_recursive_level, only_trace_rays_in_mirrors, test_time,
-                                _level=_level + 1, render_fn=render_fn, **kwargs)
+                                _level=_level + 1, render_fn=render_fn, normal_noise_std=normal_noise_std,
+                                trace_ray_times=trace_ray_times, **kwargs)
+    if rough and trace_ray_times > 0:
+        # extra jittered reflections of the mirror rays only, averaged into the first one
+        acc = sub[f"rgb_{typ}"].clone()
+        for t in range(1, trace_ray_times + 1):
+            sec_t, _, _ = reflect_rays(rays, res[f"x_surface_{typ}"], jitter(t), mask)
+            sec_m, index_m = compact_rows(sec_t, mask)
+            if sec_m.shape[0] == 0:
+                break
+            sub_t = render_rays_recursive(models, embeddings, sec_m, N_samples, use_disp, perturb, noise_std,
+                                          N_importance, chunk, white_back, max_recursive_level,
+                                          only_trace_rays_in_mirrors, test_time, _level=_level + 1, render_fn=render_fn,
+                                          normal_noise_std=normal_noise_std, trace_ray_times=trace_ray_times, **kwargs)
+            if only_mirror:   # acc is compacted too, same order
+                axpy_rows(acc, sub_t[f"rgb_{typ}"], None, 1.0, 1.0)
+            else:             # acc is dense: add at the mirror rows
+                axpy_rows(acc, sub_t[f"rgb_{typ}"], index_m, 1.0, 1.0)
+        if only_mirror:
+            axpy_rows(acc, None, None, 1.0 / (trace_ray_times + 1), 0.0)
+        else:
+            _, index_m = compact_rows(sec, mask)
+            axpy_rows(acc, None, index_m, 1.0 / (trace_ray_times + 1), 0.0)
+        sub = dict(sub)
+        sub[f"rgb_{typ}"] = acc
     rgb, rgb_reflect, depth_reflect = blend_reflection(base, mask, sub[f"rgb_{typ}"], sub[f"depth_{typ}"], index)
     res[f"rgb_{typ}_direct"] = base
     res[f"rgb_{typ}"] = rgb

@@ -368,9 +368,13 @@ def reflect_rays(rays, x_surface, normal, near=0.1):
     return torch.cat([x_surface, r, torch.ones_like(rays[:, 7:8]) * near, rays[:, 7:8]], -1), r
 
 
-def trace_eval(render_fn, rays, max_recursive_level, level=0, typ="fine"):
-    """Eval-semantics recursion (R/eval.py:132-160, 295-320, 515-548, 676-697): level 0 re-traces ALL
-    rays, deeper levels only mirror rays; blend rgb = m*reflect + (1-m)*base with the hard mask."""
+def trace_eval(render_fn, rays, max_recursive_level, level=0, typ="fine", normal_noises=None, trace_ray_times=0):
+    """Eval-semantics recursion (R/eval.py:132-160, 295-320, 515-548, 676-697): level 0 re-traces ALL rays, deeper
+    levels only mirror rays; blend rgb = m*reflect + (1-m)*base with the hard mask.
+
+    Roughness cone (R/eval.py:506-511, 623-674): `normal_noises` = list of trace_ray_times+1 noise tensors (n,3) added to
+    the surface normal before reflecting; the extra jittered reflections are traced for the mirror rays only and averaged
+    with the first (the reference's evident intent; as written it adds an (N_mirror,3) to an (N_rays,3) tensor)."""
     res = render_fn(rays)
     mask = res[f"mirror_mask_{typ}"]
     mask[mask > 0.5] = 1
@@ -379,20 +383,35 @@ def trace_eval(render_fn, rays, max_recursive_level, level=0, typ="fine"):
     res[f"rgb_{typ}_reflect"] = torch.zeros_like(res[f"rgb_{typ}"])
     res[f"depth_{typ}_reflect"] = torch.zeros_like(res[f"depth_{typ}"])
     if bool(mb.any()) and level < max_recursive_level:
-        sec, r = reflect_rays(rays, res[f"x_surface_{typ}"], res[f"surface_normal_{typ}"])
+        n0 = res[f"surface_normal_{typ}"]
+        jit = (lambda t: n0 + normal_noises[t]) if normal_noises is not None else (lambda t: n0)
+        sec, r = reflect_rays(rays, res[f"x_surface_{typ}"], jit(0))
         res["reflect_direction"] = r
         only_mirror = not (level < 1)
         sub = trace_eval(render_fn, sec[mb] if only_mirror else sec, max_recursive_level, level + 1, typ)
+        child = sub[f"rgb_{typ}"].clone()
+        if normal_noises is not None and trace_ray_times > 0:
+            for t in range(1, trace_ray_times + 1):
+                sec_t, _ = reflect_rays(rays, res[f"x_surface_{typ}"], jit(t))
+                sub_t = trace_eval(render_fn, sec_t[mb], max_recursive_level, level + 1, typ)
+                if only_mirror:
+                    child = child + sub_t[f"rgb_{typ}"]
+                else:
+                    child[mb] = child[mb] + sub_t[f"rgb_{typ}"]
+            if only_mirror:
+                child = child / (trace_ray_times + 1)
+            else:
+                child[mb] = child[mb] / (trace_ray_times + 1)
         base = res[f"rgb_{typ}"]
         res[f"rgb_{typ}_direct"] = base
         if only_mirror:
             refl = base.clone()
-            refl[mb] = sub[f"rgb_{typ}"]
-            res[f"rgb_{typ}_reflect"][mb] = sub[f"rgb_{typ}"]
+            refl[mb] = child
+            res[f"rgb_{typ}_reflect"][mb] = child
             res[f"depth_{typ}_reflect"][mb] = sub[f"depth_{typ}"]
         else:
-            refl = sub[f"rgb_{typ}"]
-            res[f"rgb_{typ}_reflect"] = sub[f"rgb_{typ}"]
+            refl = child
+            res[f"rgb_{typ}_reflect"] = child
             res[f"depth_{typ}_reflect"] = sub[f"depth_{typ}"]
         m3 = mb.float().unsqueeze(-1).repeat(1, 3)
         res[f"rgb_{typ}"] = m3 * refl + (1 - m3) * base

@@ -451,3 +451,44 @@ def test_recursion_logic_on_smooth_field(oracle, levels, only_mirror):
                           frac=0.0, p99=1e-4)
         assert_close_dist(got["depth_fine_reflect"].cpu(), want["depth_fine_reflect"], "logic depth_reflect",
                           median=1e-6, frac=0.0, p99=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------- section 8f rows 3-4
+def test_roughness_cone_logic_on_smooth_field(oracle):
+    """--app_control_mirror_roughness: jittered normals, T extra reflections of the mirror rays averaged (eval.py:623-674)."""
+    from mirror_nerf_b200.trace import render_rays_recursive
+
+    def fake(r):
+        o, d = r[:, :3], r[:, 3:6]
+        depth = 1.0 + 0.5 * torch.sin(o.sum(-1)) ** 2
+        return {"rgb_fine": 0.5 + 0.5 * torch.sin(o * 1.3 + d * 0.7), "depth_fine": depth,
+                "mirror_mask_fine": 0.5 + 0.5 * torch.sin(3.0 * o[:, 0] + d[:, 1]),
+                "surface_normal_fine": torch.stack([torch.cos(o[:, 1]), torch.sin(o[:, 2]), 0.3 + d[:, 0] ** 2], -1),
+                "x_surface_fine": o + d * depth[:, None]}
+
+    gen = torch.Generator().manual_seed(41)
+    n, T_extra = 2000, 3
+    rays = torch.cat([torch.randn(n, 6, generator=gen), torch.full((n, 1), 0.05), torch.full((n, 1), 8.0)], 1)
+    noises = [0.05 * torch.randn(n, 3, generator=gen) for _ in range(T_extra + 1)]
+    got = render_rays_recursive(None, None, rays.cuda(), 64, False, 0, 0, 128, 32768, False, max_recursive_level=1,
+                                render_fn=lambda r: {k: v.contiguous() for k, v in fake(r).items()},
+                                normal_noise_std=0.05, trace_ray_times=T_extra, normal_noises=[z.cuda() for z in noises])
+    want = oracle.trace_eval(fake, rays, 1, normal_noises=noises, trace_ray_times=T_extra)
+    assert torch.equal(got["mirror_mask_fine"].cpu(), want["mirror_mask_fine"])
+    assert_close_dist(got["rgb_fine"].cpu(), want["rgb_fine"], "roughness rgb", median=1e-6, frac=0.0, p99=1e-4)
+
+
+def test_generate_rays_matches_reference_camera():
+    """Device ray generation vs the CPU restatement of ray_utils.get_ray_directions/get_rays (blender.py:158-168)."""
+    import math
+    from mirror_nerf_b200.ray_utils import focal_from_fov, generate_rays
+    from mirror_nerf_b200.synthetic import camera_rays
+    a = 0.4
+    c2w = torch.tensor([[math.cos(a), 0.0, math.sin(a), 1.0], [0.0, 1.0, 0.0, -0.5], [-math.sin(a), 0.0, math.cos(a), 2.5]])
+    for H, W in ((400, 400), (300, 400), (7, 5)):
+        fov = 0.6911112070083618
+        want = camera_rays(H, W, fov, c2w, near=0.05, far=8.0)
+        got = generate_rays(H, W, focal_from_fov(W, fov), c2w, 0.05, 8.0).cpu()
+        assert got.shape == want.shape
+        assert torch.equal(got[:, [0, 1, 2, 6, 7]], want[:, [0, 1, 2, 6, 7]])
+        assert float((got[:, 3:6] - want[:, 3:6]).abs().max()) <= 2e-7  # matmul summation order / FMA contraction

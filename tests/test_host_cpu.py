@@ -97,3 +97,25 @@ def test_shard_plan():
         sizes = [hi - lo for lo, hi in b]
         assert max(sizes) - min(sizes) <= 128  # whole 128-ray tiles per rank
     assert shard_bounds(5, 3, 8) == (5, 5)  # more ranks than tiles: empty shards are legal
+
+
+def test_checkpoint_import_pl_prefixes(tmp_path):
+    """R/utils/__init__.py:109-136: a Lightning checkpoint keeps both fields under nerf_coarse./nerf_fine. prefixes."""
+    from mirror_nerf_b200.checkpoint import extract_model_state_dict, load_ckpt
+    from mirror_nerf_b200.mirror_nerf import MirrorNeRF
+    from mirror_nerf_b200.synthetic import make_state_dict
+    sd_c, sd_f = make_state_dict(7), make_state_dict(8)
+    pl = {"epoch": 3, "state_dict": {**{f"nerf_coarse.{k}": v for k, v in sd_c.items()},
+                                     **{f"nerf_fine.{k}": v for k, v in sd_f.items()},
+                                     "nerf_fine.normal_net_bg.0.weight": torch.zeros(1)}}
+    path = tmp_path / "epoch=3.ckpt"
+    torch.save(pl, path)
+    got = extract_model_state_dict(str(path), "nerf_fine", prefixes_to_ignore=["normal_net_bg"])
+    assert set(got) == set(sd_f)
+    m = MirrorNeRF(predict_normal=True, predict_mirror_mask=True)
+    load_ckpt(m, str(path), "nerf_coarse")
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, sd_c[k]), k
+    load_ckpt(m, "", "nerf_coarse")  # empty path: silently ignored like the reference
+    with pytest.raises(AssertionError):
+        load_ckpt(m, str(path), "nerf_missing")
