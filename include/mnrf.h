@@ -56,7 +56,7 @@ int mnrf_field_has_mirror(const mnrf_field* f);
 /* which kernel evaluates the MLP */
 #define MNRF_IMPL_TC3 3   /* tcgen05, fp16 hi/lo split operands, 3 MMAs per product (fp32-grade; parity mode) */
 #define MNRF_IMPL_TC1 1   /* tcgen05, single fp16 pass (speed mode; does not meet the 1e-3 parity bar)      */
-#define MNRF_IMPL_FP32 0  /* CUDA-core fp32 verification kernel (slow; also the only one with analytic normals) */
+#define MNRF_IMPL_FP32 0  /* CUDA-core fp32 verification kernel (slow; the only one that exports geo_feat) */
 
 /* raw per-point record written by the field kernels: 8 floats */
 #define MNRF_RAW_STRIDE 8 /* [sigma, r, g, b, is_mirror, pred_nx, pred_ny, pred_nz] */
@@ -65,8 +65,8 @@ int mnrf_field_has_mirror(const mnrf_field* f);
  *   rays (n_rays,8) = [o,d,near,far];  z (n_rays,S).
  *   sigma_only != 0: only `sigma_out` (n_rays*S) is written (coarse pass at test time, rendering.py:139-150).
  *   otherwise `raw` (n_rays*S, 8) is written; absent heads give 0.
- *   normal_out: optional (n_rays*S,3) analytic normal  normalize(-d sigma/d xyz) (mirror_nerf.py:136-146);
- *               only MNRF_IMPL_FP32 supports it. */
+ *   normal_out: optional (n_rays*S,3) analytic normal  normalize(-d sigma/d xyz) (mirror_nerf.py:136-146): the tensor-core
+ *               kernels run the reverse chain through the trunk as 9 more GEMM steps with transposed weights. */
 int mnrf_field_eval_rays(const mnrf_field* f, int impl, const float* rays, const float* z, int n_rays, int S,
                          int sigma_only, float* raw, float* sigma_out, float* normal_out, void* stream);
 
@@ -140,7 +140,7 @@ typedef struct mnrf_level_cfg {
   float noise_std;
   int white_back;
   int test_time;     /* coarse pass sigma-only when a fine field exists (rendering.py:139,208)          */
-  int compute_normal;/* analytic normals (forces MNRF_IMPL_FP32)                                        */
+  int compute_normal;/* analytic normals normalize(-d sigma/d xyz) for every pass that is not sigma-only         */
   int rerun_coarse_on_fine; /* only_one_field after only_one_field_fine_epoch (rendering.py:328-348)    */
   int impl;          /* MNRF_IMPL_*                                                                     */
 } mnrf_level_cfg;

@@ -173,7 +173,7 @@ int mnrf_field_eval_rays(const mnrf_field* f, int impl, const float* rays, const
   io.rays = rays; io.z = z; io.x = nullptr; io.x_stride = 0; io.dirbias = dirbias;
   io.n_points = n_rays * S; io.S = S; io.sigma_only = sigma_only;
   io.raw = sigma_only ? nullptr : raw; io.sigma_out = sigma_out; io.normal_out = normal_out; io.geo_out = nullptr;
-  int rc = run_field(f, normal_out ? (int)MNRF_IMPL_FP32 : impl, io, st);
+  int rc = run_field(f, impl, io, st);
   if (dirbias) MNRF_CUDA_OK(cudaFreeAsync(dirbias, st));
   return rc;
 }
@@ -184,7 +184,7 @@ int mnrf_field_eval_points(const mnrf_field* f, int impl, const float* x, int B,
   MNRF_REQUIRE(f && x, "field_eval_points: null argument");
   if (check_impl(impl)) return 2;
   if (B <= 0) return 0;
-  if (normal != nullptr || geo_feat != nullptr) impl = MNRF_IMPL_FP32;
+  if (geo_feat != nullptr) impl = MNRF_IMPL_FP32;  // only the fp32 kernel exports the 256-wide feature
   cudaStream_t st = S_(stream);
   const int stride = sigma_only ? 3 : 3 + IN_DIR;
   float* dirbias = nullptr;
@@ -292,7 +292,7 @@ int mnrf_render_level(const mnrf_field* coarse, const mnrf_field* fine, const fl
   float* dirbias = reinterpret_cast<float*>(ws); ws += align256(sizeof(float) * (size_t)n * WH);
   float* buf_c = reinterpret_cast<float*>(ws);   ws += align256(sizeof(float) * (size_t)n * Sc * 8);
   float* buf_f = reinterpret_cast<float*>(ws);
-  const int impl = cfg->compute_normal ? (int)MNRF_IMPL_FP32 : cfg->impl;
+  const int impl = cfg->impl;
 
   // ---- coarse pass (rendering.py:271-305) ----
   if (launch_coarse_z(rays, n, z_steps, Sc, cfg->use_disp, cfg->perturb, rng->perturb_u, out->z_coarse, st)) return 1;

@@ -32,10 +32,16 @@ enum {
 // ------------------------------------------------------------------------------------------------
 // tensor-core GEMM steps of one 128-point tile (field_tc.cu) and their packed-weight blobs
 // ------------------------------------------------------------------------------------------------
-constexpr int TC_NUM_STEPS = 11;
+// Steps 11..19 are the TRANSPOSED trunk weights of the analytic-normal chain d sigma / d xyz (mirror_nerf.py:136-146):
+//   11: W8^T  12: W7^T  13: W6^T  14: W5^T (h part, 256 inputs)  15: W5^T (PE part, 63->64 inputs)
+//   16: W4^T  17: W3^T  18: W2^T  19: W1^T (63->64 inputs)          B operand [n = input feature][k = output feature]
+constexpr int TC_FWD_STEPS = 11;
+constexpr int TC_NUM_STEPS = 20;
 // step:            0    1    2    3    4    5    6    7    8(final) 9(mirror0) 10(dir)
-__host__ __device__ constexpr int tc_step_n(int s) { return s <= 8 ? 256 : 128; }
+__host__ __device__ constexpr int tc_step_n(int s) { return s <= 8 ? 256 : (s <= 10 ? 128 : ((s == 15 || s == 19) ? 64 : 256)); }
 __host__ __device__ constexpr int tc_step_k(int s) { return s == 0 ? 64 : (s == 4 ? 320 : 256); }
+// forward trunk layer (0-based) whose weight matrix a transposed step uses
+__host__ __device__ constexpr int tc_step_layer(int s) { return s <= 13 ? 18 - s : (s <= 15 ? 4 : 19 - s); }
 __host__ __device__ constexpr int tc_step_chunks(int s) { return tc_step_k(s) / 32; }
 // One blob = hi or lo part of one K32 chunk of a step's weight matrix: N rows x 32 halves (16 KB for N=256, 8 KB for
 // N=128), stored as the shared-memory image of a tcgen05 K-major no-swizzle B operand.  Order inside a step: [chunk kc][hi, lo].
@@ -60,8 +66,8 @@ constexpr int ET_B_M0 = ET_HEADW + 4 * 256;     // [128]
 constexpr int ET_W_M2 = ET_B_M0 + 128;          // [128]
 constexpr int ET_W_RGB = ET_W_M2 + 128;         // [3][128]
 constexpr int ET_HEADB = ET_W_RGB + 3 * 128;    // {b_sigma, bn_fold[0..2]}
-constexpr int ET_INV_SCALE = ET_HEADB + 4;      // [12] (11 used)
-constexpr int ET_B_M2 = ET_INV_SCALE + 12;      // [4] (1 used)
+constexpr int ET_INV_SCALE = ET_HEADB + 4;      // [20] one per GEMM step
+constexpr int ET_B_M2 = ET_INV_SCALE + 20;      // [4] (1 used)
 constexpr int ET_B_RGB = ET_B_M2 + 4;           // [4] (3 used)
 constexpr int ET_TOTAL = ET_B_RGB + 4;          // 3992 floats = 15,968 bytes
 
@@ -114,7 +120,7 @@ inline F32Layout make_f32_layout() {
   L.inv_scale = L.epi_tab + ET_INV_SCALE;
   L.b_m2 = L.epi_tab + ET_B_M2;
   L.b_rgb = L.epi_tab + ET_B_RGB;
-  L.absmax = take(16);
+  L.absmax = take(32);
   L.total = o;
   return L;
 }

@@ -53,6 +53,7 @@ constexpr int BAR_TMEM_SLOT = 30;
 
 constexpr uint32_t IDESC_N256 = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);  // f16 x f16 -> f32, K-major
 constexpr uint32_t IDESC_N128 = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t IDESC_N64 = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
 struct TcParams {
   const float* f32;        // fp32 section
@@ -189,7 +190,7 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint32_t a_lo32, uint32_
       "mov.b64 db, {%2, %4};\n\t"
       "setp.ne.b32 p, %3, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_lo32), "r"(b_lo32), "r"(accumulate), "r"(DESC_HI), "r"(N == 256 ? IDESC_N256 : IDESC_N128)
+      ::"r"(d_tmem), "r"(a_lo32), "r"(b_lo32), "r"(accumulate), "r"(DESC_HI), "r"(N == 256 ? IDESC_N256 : (N == 128 ? IDESC_N128 : IDESC_N64))
       : "memory");
 }
 
@@ -262,22 +263,34 @@ __device__ __forceinline__ void pe_fill(const float (&x)[3], uint32_t pe_hi, uin
   }
 }
 
-// ---- epilogue of 32 accumulator columns of one row ------------------------------------------------------------------
-template <int NC, bool RELU, bool DOTS, bool WRITE_A, bool PREC3>
+// ---- epilogue of NC accumulator columns of one row ------------------------------------------------------------------
+// MASK: 0 = none; 1 = record (bit i of `mbits` from `bit0` up := value > 0, the ReLU derivative needed by the analytic-normal
+// chain); 2 = apply (value := bit ? value : 0, no bias: a step of the chain g_{l-1} = (g_l W_l) * relu'(h_{l-1})).
+template <int NC, bool RELU, bool DOTS, bool WRITE_A, bool PREC3, int MASK>
 __device__ __forceinline__ void epi_cols(const uint32_t (&r)[NC], const float4 (&b)[NC / 4], float inv, uint32_t s_hi,
-                                         uint32_t s_lo, const float4* __restrict__ hw, float (&d)[4]) {
+                                         uint32_t s_lo, const float4* __restrict__ hw, float (&d)[4], uint32_t& mbits,
+                                         int bit0) {
 #pragma unroll
   for (int j = 0; j < NC / 8; ++j) {
-    const float4 b0 = b[2 * j], b1 = b[2 * j + 1];
     float v[8];
-    v[0] = fmaf(__uint_as_float(r[8 * j + 0]), inv, b0.x);
-    v[1] = fmaf(__uint_as_float(r[8 * j + 1]), inv, b0.y);
-    v[2] = fmaf(__uint_as_float(r[8 * j + 2]), inv, b0.z);
-    v[3] = fmaf(__uint_as_float(r[8 * j + 3]), inv, b0.w);
-    v[4] = fmaf(__uint_as_float(r[8 * j + 4]), inv, b1.x);
-    v[5] = fmaf(__uint_as_float(r[8 * j + 5]), inv, b1.y);
-    v[6] = fmaf(__uint_as_float(r[8 * j + 6]), inv, b1.z);
-    v[7] = fmaf(__uint_as_float(r[8 * j + 7]), inv, b1.w);
+    if (MASK == 2) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = ((mbits >> (bit0 + 8 * j + i)) & 1u) ? __uint_as_float(r[8 * j + i]) * inv : 0.f;
+    } else {
+      const float4 b0 = b[2 * j], b1 = b[2 * j + 1];
+      v[0] = fmaf(__uint_as_float(r[8 * j + 0]), inv, b0.x);
+      v[1] = fmaf(__uint_as_float(r[8 * j + 1]), inv, b0.y);
+      v[2] = fmaf(__uint_as_float(r[8 * j + 2]), inv, b0.z);
+      v[3] = fmaf(__uint_as_float(r[8 * j + 3]), inv, b0.w);
+      v[4] = fmaf(__uint_as_float(r[8 * j + 4]), inv, b1.x);
+      v[5] = fmaf(__uint_as_float(r[8 * j + 5]), inv, b1.y);
+      v[6] = fmaf(__uint_as_float(r[8 * j + 6]), inv, b1.z);
+      v[7] = fmaf(__uint_as_float(r[8 * j + 7]), inv, b1.w);
+    }
+    if (MASK == 1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mbits |= (v[i] > 0.f ? 1u : 0u) << (bit0 + 8 * j + i);
+    }
     if (DOTS) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -292,20 +305,39 @@ __device__ __forceinline__ void epi_cols(const uint32_t (&r)[NC], const float4 (
 }
 
 // epilogue flavours of a 256-wide layer
-struct TagTrunk { static constexpr bool relu = true, dots = false, write_a = true; };   // layers 1..7
-struct TagLast  { static constexpr bool relu = true, dots = true, write_a = true; };    // layer 8 (+ sigma / normal dots)
-struct TagSigma { static constexpr bool relu = true, dots = true, write_a = false; };   // layer 8 of a sigma-only launch
-struct TagFinal { static constexpr bool relu = false, dots = false, write_a = true; };  // xyz_encoding_final (no activation)
+struct TagTrunk { static constexpr bool relu = true, dots = false, write_a = true; static constexpr int mask = 0; };   // layers 1..7
+struct TagLast  { static constexpr bool relu = true, dots = true, write_a = true; static constexpr int mask = 0; };    // layer 8 (+ sigma / normal dots)
+struct TagSigma { static constexpr bool relu = true, dots = true, write_a = false; static constexpr int mask = 0; };   // layer 8 of a sigma-only launch
+struct TagFinal { static constexpr bool relu = false, dots = false, write_a = true; static constexpr int mask = 0; };  // xyz_encoding_final (no activation)
+struct TagTrunkM { static constexpr bool relu = true, dots = false, write_a = true; static constexpr int mask = 1; };  // ... recording relu' bits
+struct TagLastM  { static constexpr bool relu = true, dots = true, write_a = true; static constexpr int mask = 1; };
+struct TagSigmaM { static constexpr bool relu = true, dots = true, write_a = false; static constexpr int mask = 1; };
+struct TagChain  { static constexpr bool relu = false, dots = false, write_a = true; static constexpr int mask = 2; }; // analytic-normal chain step
 
 // ---- step geometry --------------------------------------------------------------------------------
 // TMEM columns: trunk layers alternate [0,256) / [256,512); mirror head (step 9) -> [0,128); final (step 8) -> [128,384);
 // dir layer (step 10) -> [384,512).  Issue order: 0..7, 9, 8, 10.
-__device__ __forceinline__ uint32_t acc_col(int s) { return s <= 7 ? (uint32_t)(s & 1) * 256u : (s == 9 ? 0u : (s == 8 ? 128u : 384u)); }
-__device__ __forceinline__ int acc_bar(int s) { return s <= 7 ? (s & 1) : (s == 8 ? 3 : 2); }  // steps 9 and 10 share slot 2
-__device__ __forceinline__ int step_at(int i) { return i < 8 ? i : (i == 8 ? 9 : (i == 9 ? 8 : 10)); }
+// Analytic-normal chain (steps 11..19, issued in numeric order after step 10): the seven 256-wide steps alternate
+// [0,256) / [256,512) again; the two 64-wide PE-gradient steps use 64 columns of the buffer that is idle at that point.
+__device__ __forceinline__ int chain_w(int s) { return s <= 14 ? s - 11 : s - 12; }  // index among the wide chain steps (s != 15, 19)
+__device__ __forceinline__ uint32_t acc_col(int s) {
+  if (s <= 7) return (uint32_t)(s & 1) * 256u;
+  if (s <= 10) return s == 9 ? 0u : (s == 8 ? 128u : 384u);
+  if (s == 15) return 0u;     // W5^T PE part: after step 14 (which owns [256,512))
+  if (s == 19) return 256u;   // W1^T: after step 18 (which owns [0,256))
+  return (uint32_t)(chain_w(s) & 1) * 256u;
+}
+__device__ __forceinline__ int acc_bar(int s) {  // steps 9 and 10 share slot 2; chain: wide -> 0/1, 15 -> 2, 19 -> 3
+  if (s <= 7) return s & 1;
+  if (s <= 10) return s == 8 ? 3 : 2;
+  if (s == 15) return 2;
+  if (s == 19) return 3;
+  return chain_w(s) & 1;
+}
+__device__ __forceinline__ int step_at(int i) { return i < 8 ? i : (i == 8 ? 9 : (i == 9 ? 8 : i)); }
 
 // ================================================================================================
-template <bool PREC3>
+template <bool PREC3, bool NORMALS>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -314,7 +346,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
   const uint32_t bars = sbase + SM_BAR;
   auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SM_BAR + 8 * BAR_TMEM_SLOT);
-  const int n_issue = P.io.sigma_only ? 8 : 11;
+  const int n_issue = P.io.sigma_only ? 8 : (NORMALS ? 20 : 11);
   constexpr uint32_t NST = PREC3 ? 4u : 8u;  // weight stages (the 1x mode also uses the idle A_lo region)
   auto stage_addr = [&](uint32_t st) { return sbase + (st < 4u ? SM_WST + st * WSTAGE_BYTES : SM_A_LO + (st - 4u) * WSTAGE_BYTES); };
 
@@ -349,15 +381,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
           const int s = step_at(i);
           if (s == 9 && !P.has_mirror) continue;
           const uint8_t* src = P.tc + tc_step_offset(s);
-          const bool wide = tc_step_n(s) == 256;
+          const int sn = tc_step_n(s);
+          const bool wide = sn == 256;
           const int nch = tc_step_chunks(s);
-          const int nst = PREC3 ? (wide ? 2 * nch : nch) : (wide ? nch : nch / 2);
+          // N = 64 steps (4 KB blobs): 3x -> [hi|lo] of two K32 chunks per stage (contiguous); 1x -> hi of four chunks
+          const int nst = sn == 64 ? (PREC3 ? nch / 2 : nch / 4) : (PREC3 ? (wide ? 2 * nch : nch) : (wide ? nch : nch / 2));
           for (int si = 0; si < nst; ++si) {
             mbar_wait(bar(BAR_W_EMPTY + stage), phase ^ 1u);
             const uint32_t dst = stage_addr(stage);
             const uint32_t fb = bar(BAR_W_FULL + stage);
             mbar_expect_tx(fb, WSTAGE_BYTES);
-            if (PREC3 || wide) {
+            if (sn == 64 && !PREC3) {
+#pragma unroll
+              for (int piece = 0; piece < 4; ++piece) bulk_g2s(dst + piece * 4096u, src + (size_t)(4 * si + piece) * 8192, 4096u, fb);
+            } else if (PREC3 || wide) {
               // 16 contiguous KB: blob si (3x wide), blobs 2si,2si+1 (3x narrow), blob 2si = hi of chunk si (1x wide)
               const uint8_t* g = src + (size_t)(PREC3 ? si : 2 * si) * WSTAGE_BYTES;
 #pragma unroll
@@ -388,7 +425,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
           const bool wide = tc_step_n(s) == 256;
           const int nch = tc_step_chunks(s);
           const int n_pe = (s == 0 || s == 4) ? 2 : 0;       // leading K32 chunks that come from the PE buffer
-          const bool a_reused = (s == 8 && P.has_mirror);    // h8 was already awaited by the mirror GEMM
+          const bool a_reused = (s == 8 && P.has_mirror) || s == 15;  // operand already awaited by the previous GEMM
           const uint32_t d_tmem = tmem + acc_col(s);
           uint32_t accumulate = 0;
           trace_ev(P, trc, 0, 1, 1, s, 0);
@@ -427,6 +464,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
                 tc_mma<256>(d_tmem, ah + 256u, wb + 512u, 1u);
                 tc_commit(bar(BAR_W_EMPTY + stage));
                 next_stage();
+              }
+            } else if (tc_step_n(s) == 64) {
+              // ---- N = 64 (PE-gradient steps of the normal chain): K16 step of B = 2048 B = 128 units, LBO = 1024 ----
+              if (PREC3) {  // stage = [hi|lo] of chunks 2j, 2j+1 (4 x 4 KB)
+                if ((kc & 1) == 0) { mbar_wait(bar(BAR_W_FULL + stage), phase); tc_fence_after(); }
+                const uint32_t wb = desc_lo(stage_addr(stage), 1024) + (uint32_t)(kc & 1) * 512u;
+                tc_mma<64>(d_tmem, ah, wb, accumulate);
+                tc_mma<64>(d_tmem, al, wb, 1u);
+                tc_mma<64>(d_tmem, ah + 256u, wb + 128u, 1u);
+                tc_mma<64>(d_tmem, al + 256u, wb + 128u, 1u);
+                tc_mma<64>(d_tmem, ah, wb + 256u, 1u);
+                tc_mma<64>(d_tmem, ah + 256u, wb + 384u, 1u);
+                if (kc & 1) { tc_commit(bar(BAR_W_EMPTY + stage)); next_stage(); }
+              } else {      // stage = hi of chunks 4j..4j+3
+                if ((kc & 3) == 0) { mbar_wait(bar(BAR_W_FULL + stage), phase); tc_fence_after(); }
+                const uint32_t wb = desc_lo(stage_addr(stage), 1024) + (uint32_t)(kc & 3) * 256u;
+                tc_mma<64>(d_tmem, ah, wb, accumulate);
+                tc_mma<64>(d_tmem, ah + 256u, wb + 128u, 1u);
+                if ((kc & 3) == 3) { tc_commit(bar(BAR_W_EMPTY + stage)); next_stage(); }
               }
             } else if (PREC3) {
               // ---- N = 128, 3x: stage = [W_hi | W_lo] of this K32 chunk; K16 step = 4096 B = 256 units ----
@@ -507,8 +563,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
     };
     // One 256-wide layer: this warp owns columns [64c + 32g, 64c + 32g + 32) of every chunk c, chunks in K order, the next
     // chunk's TMEM load in flight while the current one is converted.
-    auto layer_epilogue = [&](auto tag, int s, const float* bias256, float (&d)[4]) {
+    // mk: this thread's four 32-bit relu' words of the layer (chunk c -> mk[c]; chunk 0's two 16-column pieces share mk[0])
+    auto layer_epilogue = [&](auto tag, int s, const float* bias256, float (&d)[4], uint32_t (&mk)[4]) {
       constexpr bool RELU = decltype(tag)::relu, DOTS = decltype(tag)::dots, WRITE_A = decltype(tag)::write_a;
+      constexpr int MASK = decltype(tag)::mask;
+      if (MASK == 1) { mk[0] = 0u; mk[1] = 0u; mk[2] = 0u; mk[3] = 0u; }
       const float4* b4 = reinterpret_cast<const float4*>(bias256);
       // everything that does not depend on the accumulator is fetched before waiting for it
       const float inv = c_epi[ET_INV_SCALE + s];
@@ -528,12 +587,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
       pin<16>(r0b);
       {
         const uint32_t off = (uint32_t)(g * 2) * 2048u + rowoff;
-        epi_cols<16, RELU, DOTS, WRITE_A, PREC3>(r0a, b0a, inv, sbase + SM_A_HI + off, sbase + SM_A_LO + off, headw + g * 16, d);
+        epi_cols<16, RELU, DOTS, WRITE_A, PREC3, MASK>(r0a, b0a, inv, sbase + SM_A_HI + off, sbase + SM_A_LO + off, headw + g * 16, d, mk[0], 0);
         if (WRITE_A) a_ready(0);
       }
       {
         const uint32_t off = (uint32_t)(4 + g * 2) * 2048u + rowoff;
-        epi_cols<16, RELU, DOTS, WRITE_A, PREC3>(r0b, b0b, inv, sbase + SM_A_HI + off, sbase + SM_A_LO + off, headw + 32 + g * 16, d);
+        epi_cols<16, RELU, DOTS, WRITE_A, PREC3, MASK>(r0b, b0b, inv, sbase + SM_A_HI + off, sbase + SM_A_LO + off, headw + 32 + g * 16, d, mk[0], 16);
         if (WRITE_A) a_ready(4);
       }
 #pragma unroll
@@ -546,8 +605,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
           else       tmem_ld32(tcol + (uint32_t)(c + 1) * 64u + (uint32_t)g * 32u, rb);
         }
         const uint32_t off = (uint32_t)(c * 8 + g * 4) * 2048u + rowoff;
-        if (c & 1) { pin32(rb); epi_cols<32, RELU, DOTS, WRITE_A, PREC3>(rb, b, inv, sbase + SM_A_HI + off, sbase + SM_A_LO + off, headw + c * 64 + g * 32, d); }
-        else       { pin32(ra); epi_cols<32, RELU, DOTS, WRITE_A, PREC3>(ra, b, inv, sbase + SM_A_HI + off, sbase + SM_A_LO + off, headw + c * 64 + g * 32, d); }
+        if (c & 1) { pin32(rb); epi_cols<32, RELU, DOTS, WRITE_A, PREC3, MASK>(rb, b, inv, sbase + SM_A_HI + off, sbase + SM_A_LO + off, headw + c * 64 + g * 32, d, mk[c], 0); }
+        else       { pin32(ra); epi_cols<32, RELU, DOTS, WRITE_A, PREC3, MASK>(ra, b, inv, sbase + SM_A_HI + off, sbase + SM_A_LO + off, headw + c * 64 + g * 32, d, mk[c], 0); }
         if (WRITE_A) a_ready(c);
       }
     };
@@ -560,14 +619,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
       const long long ray = (P.io.rays != nullptr) ? p / P.io.S : p;
       float o_sigma = 0.f, o_n[3] = {0.f, 0.f, 0.f}, o_mirror = 0.f, o_rgb[3] = {0.f, 0.f, 0.f};
       float d[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t masks[NORMALS ? 8 : 1][4];  // relu' bits of this thread's (row, columns) for every trunk layer
+      float o_an[3] = {0.f, 0.f, 0.f};     // analytic normal
 
       // ---- trunk layers 1..8 (steps 0..7) ----
 #pragma unroll 1
       for (int s = 0; s < 8; ++s) {
         const float* bias = c_epi + ET_BIAS + 256 * s;
-        if (s < 7) layer_epilogue(TagTrunk{}, s, bias, d);
-        else if (!P.io.sigma_only) layer_epilogue(TagLast{}, s, bias, d);
-        else layer_epilogue(TagSigma{}, s, bias, d);
+        if (NORMALS) {
+          if (s < 7) layer_epilogue(TagTrunkM{}, s, bias, d, masks[s]);
+          else if (!P.io.sigma_only) layer_epilogue(TagLastM{}, s, bias, d, masks[s]);
+          else layer_epilogue(TagSigmaM{}, s, bias, d, masks[s]);
+        } else {
+          if (s < 7) layer_epilogue(TagTrunk{}, s, bias, d, masks[0]);
+          else if (!P.io.sigma_only) layer_epilogue(TagLast{}, s, bias, d, masks[0]);
+          else layer_epilogue(TagSigma{}, s, bias, d, masks[0]);
+        }
         // the PE buffer is free once layer 5's MMAs are done: encode the next tile while the tensor pipe is busy
         if (s == 5 && tile + (int)gridDim.x < P.n_tiles) pe_tile(tile + gridDim.x);
       }
@@ -626,7 +693,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
           epi_bar_sync(2);
         }
         // ---- final linear (step 8): f = W h8 + b, written over h8 (its readers, steps 9 and 8, are complete) ----
-        layer_epilogue(TagFinal{}, 8, c_epi + ET_BIAS + 256 * 8, d);
+        layer_epilogue(TagFinal{}, 8, c_epi + ET_BIAS + 256 * 8, d, masks[0]);
         // ---- dir layer (step 10): relu(W_f f + [b + W_d embed(dir)]) -> rgb (mirror_nerf.py:199-204) ----
         wait_acc(10);
         {
@@ -674,6 +741,96 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
         }
       }
 
+      // ---- analytic normal: n = normalize(-d sigma / d xyz) as a reverse chain on the tensor cores (mirror_nerf.py:136-146) ----
+      if (NORMALS && !P.io.sigma_only) {
+        // g7 = w_sigma * relu'(h8), written straight into the A buffer (its last reader, the dir GEMM, is complete)
+        {
+          const float4* hw = headw;
+#pragma unroll
+          for (int piece = 0; piece < 5; ++piece) {  // same column ownership as layer_epilogue: chunk 0 as two 16-col pieces
+            const int c = piece < 2 ? 0 : piece - 1;
+            const int ncol = piece < 2 ? 16 : 32;
+            const int col0 = piece == 0 ? g * 16 : (piece == 1 ? 32 + g * 16 : c * 64 + g * 32);
+            const int bit0 = piece == 1 ? 16 : 0;
+#pragma unroll
+            for (int j = 0; j < ncol / 8; ++j) {
+              float v[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = ((masks[7][c] >> (bit0 + 8 * j + i)) & 1u) ? hw[col0 + 8 * j + i].x : 0.f;
+              const uint32_t off = (uint32_t)(col0 / 8 + j) * 2048u + rowoff;
+              store_a8<false, PREC3>(sbase + SM_A_HI + off, sbase + SM_A_LO + off, v);
+            }
+            a_ready(piece == 0 ? 0 : (piece == 1 ? 4 : c));
+          }
+        }
+        float gpe[32];  // this thread's 32 of the 64 PE-gradient entries: columns [32g, 32g+32)
+        // wide chain steps: 11 (W8^T) .. 18 (W2^T), masks of the layer whose output the gradient now refers to
+#pragma unroll 1
+        for (int s = 11; s <= 18; ++s) {
+          if (s == 15) continue;
+          if (s == 14) {
+            // the PE part of layer 5 (step 15) lands in 64 columns that the NEXT wide step overwrites: read it first
+            wait_acc(15);
+            uint32_t r[32];
+            tmem_ld32(tlane + acc_col(15) + (uint32_t)g * 32u, r);
+            tmem_wait_ld();
+            pin32(r);
+            const float inv15 = c_epi[ET_INV_SCALE + 15];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) gpe[i] = __uint_as_float(r[i]) * inv15;
+          }
+          const int layer = tc_step_layer(s);  // 0-based trunk layer of this transposed weight; gradient is w.r.t. its input
+          layer_epilogue(TagChain{}, s, c_epi, d, masks[layer - 1]);
+        }
+        // last step 19 (W1^T): PE gradient of layer 1; total PE gradient -> xyz gradient through the PE Jacobian
+        wait_acc(19);
+        {
+          uint32_t r[32];
+          tmem_ld32(tlane + acc_col(19) + (uint32_t)g * 32u, r);
+          tmem_wait_ld();
+          pin32(r);
+          const float inv19 = c_epi[ET_INV_SCALE + 19];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) gpe[i] = fmaf(__uint_as_float(r[i]), inv19, gpe[i]);
+          float x[3];
+          if (P.io.rays != nullptr) {
+            const float* rr = P.io.rays + ray * 8;
+            const float z = __ldg(P.io.z + p);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(__ldg(rr + c), __fmul_rn(__ldg(rr + 3 + c), z));
+          } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) x[c] = __ldg(P.io.x + p * P.io.x_stride + c);
+          }
+          float dx[3] = {0.f, 0.f, 0.f};
+          const int K0 = 32 * g;
+          if (g == 0) { dx[0] = gpe[0]; dx[1] = gpe[1]; dx[2] = gpe[2]; }
+#pragma unroll
+          for (int f = 0; f < NFREQ_XYZ; ++f) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const int ks = 3 + 6 * f + c, kc = ks + 3;  // PE columns of sin(2^f x_c) and cos(2^f x_c)
+              const bool need_s = (ks >= K0 && ks < K0 + 32), need_c = (kc >= K0 && kc < K0 + 32);
+              if (need_s || need_c) {
+                const float fr = (float)(1 << f);
+                const float2 sc = sincos_pe(fr * x[c]);
+                if (need_s) dx[c] = fmaf(fr * gpe[(ks - K0) & 31], sc.y, dx[c]);    // d sin = +f cos
+                if (need_c) dx[c] = fmaf(-fr * gpe[(kc - K0) & 31], sc.x, dx[c]);   // d cos = -f sin
+              }
+            }
+          }
+          if (g == 1) part[row] = make_float4(dx[0], dx[1], dx[2], 0.f);
+          epi_bar_sync(1);
+          if (g == 0) {
+            const float4 o = part[row];
+            const float a = -(dx[0] + o.x), b = -(dx[1] + o.y), cc = -(dx[2] + o.z);
+            const float nn = sqrtf(fmaxf(a * a + b * b + cc * cc, FP32_EPS));  // utils/func.py:5-7
+            o_an[0] = a / nn; o_an[1] = b / nn; o_an[2] = cc / nn;
+          }
+          epi_bar_sync(2);
+        }
+      }
+
       // ---- write the point record ----
       if (q == 0) trace_ev(P, trc, lane, 4 + g, 14, 0, 0);
       tc_fence_before();
@@ -683,6 +840,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
           float4* o = reinterpret_cast<float4*>(P.io.raw + p_raw * 8);
           o[0] = make_float4(o_sigma, o_rgb[0], o_rgb[1], o_rgb[2]);
           o[1] = make_float4(o_mirror, o_n[0], o_n[1], o_n[2]);
+        }
+        if (NORMALS && P.io.normal_out != nullptr) {
+          float* no = P.io.normal_out + p_raw * 3;
+          no[0] = o_an[0]; no[1] = o_an[1]; no[2] = o_an[2];
         }
       }
     }
@@ -707,7 +868,7 @@ void set_tc_trace(unsigned long long* buf, unsigned int cap) { g_trace_buf = buf
 int launch_field_tc(const mnrf_field* f, const FieldIO& io, int precision, cudaStream_t st) {
   if (io.n_points <= 0) return 0;
   MNRF_REQUIRE(precision == 1 || precision == 3, "field_tc: precision must be 1 or 3");
-  MNRF_REQUIRE(io.normal_out == nullptr, "field_tc: analytic normals need MNRF_IMPL_FP32");
+  MNRF_REQUIRE(io.normal_out == nullptr || !io.sigma_only, "field_tc: analytic normals need the full (non sigma-only) pass");
   MNRF_REQUIRE(io.geo_out == nullptr, "field_tc: geo_feat output needs MNRF_IMPL_FP32");
   MNRF_REQUIRE(io.sigma_only || io.dirbias != nullptr, "field_tc: dirbias missing");
   static int num_sms = 0;
@@ -715,8 +876,10 @@ int launch_field_tc(const mnrf_field* f, const FieldIO& io, int precision, cudaS
     int dev = 0;
     MNRF_CUDA_OK(cudaGetDevice(&dev));
     MNRF_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
-    MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
+    MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
+    MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
+    MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_tc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
+    MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
   }
   TcParams P;
   const F32Layout& L = f->L;
@@ -736,8 +899,14 @@ int launch_field_tc(const mnrf_field* f, const FieldIO& io, int precision, cudaS
   const double macs = (double)io.n_points * (io.sigma_only ? (double)mnrf_macs_sigma_only() : (double)mnrf_macs_full());
   MNRF_CUDA_OK(cudaMemcpyToSymbolAsync(c_epi, f->f32 + L.epi_tab, sizeof(float) * ET_TOTAL, 0, cudaMemcpyDeviceToDevice, st));
   prof_begin(st);
-  if (precision == 3) k_field_tc<true><<<grid, NUM_THREADS, SM_TOTAL, st>>>(P);
-  else                k_field_tc<false><<<grid, NUM_THREADS, SM_TOTAL, st>>>(P);
+  const bool normals = io.normal_out != nullptr;
+  if (precision == 3) {
+    if (normals) k_field_tc<true, true><<<grid, NUM_THREADS, SM_TOTAL, st>>>(P);
+    else         k_field_tc<true, false><<<grid, NUM_THREADS, SM_TOTAL, st>>>(P);
+  } else {
+    if (normals) k_field_tc<false, true><<<grid, NUM_THREADS, SM_TOTAL, st>>>(P);
+    else         k_field_tc<false, false><<<grid, NUM_THREADS, SM_TOTAL, st>>>(P);
+  }
   prof_end(st, 2.0 * macs);
   MNRF_LAUNCH_OK();
   return 0;

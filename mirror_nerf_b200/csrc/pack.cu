@@ -65,15 +65,34 @@ __global__ void k_fold_heads(const float* __restrict__ w_sigma, const float* __r
 
 // ---- tensor-core blobs -------------------------------------------------------------------------
 struct TcSrc {
-  const float* w[TC_NUM_STEPS];  // source matrices [N][ld]
+  const float* w[TC_NUM_STEPS];  // source matrices [out][ld] as nn.Linear stores them
   int ld[TC_NUM_STEPS];          // row stride (in-features of the nn.Linear)
 };
+
+// value of element (n, k) of step s's B operand, or 0 for padding.  Forward steps: B[n][k] = W[n][col(k)].
+// Transposed steps (analytic-normal chain): B[n][k] = W[k][col(n)], n = input feature, k = output feature.
+__device__ __forceinline__ float tc_src_value(const TcSrc& src, int s, int n, int k);
 
 // column of the source matrix feeding padded K index k of step s, or -1 for zero padding
 __device__ __forceinline__ int tc_src_col(int s, int k) {
   if (s == 0) return k < IN_XYZ ? k : -1;                       // 63 -> 64
   if (s == 4) return k < IN_XYZ ? k : (k == IN_XYZ ? -1 : k - 1);  // [pe(63) pad | h(256)]
   return k;                                                      // 256 (dir layer: feature part only)
+}
+
+__device__ __forceinline__ float tc_src_value(const TcSrc& src, int s, int n, int k) {
+  const float* w = src.w[s];
+  if (w == nullptr) return 0.f;
+  if (s < TC_FWD_STEPS) {
+    const int c = tc_src_col(s, k);
+    return c >= 0 ? w[n * src.ld[s] + c] : 0.f;
+  }
+  int c;  // input-feature column of the layer's weight matrix
+  if (s == 15) c = n < IN_XYZ ? n : -1;          // PE part of layer 5 (63 -> 64)
+  else if (s == 14) c = IN_XYZ + n;              // h part of layer 5
+  else if (s == 19) c = n < IN_XYZ ? n : -1;     // layer 1 (63 -> 64)
+  else c = n;
+  return c >= 0 ? w[k * src.ld[s] + c] : 0.f;
 }
 
 __global__ void k_absmax(TcSrc src, unsigned int* __restrict__ absmax) {
@@ -83,8 +102,7 @@ __global__ void k_absmax(TcSrc src, unsigned int* __restrict__ absmax) {
   float m = 0.f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N * K; i += gridDim.x * blockDim.x) {
     int n = i / K, k = i % K;
-    int c = tc_src_col(s, k);
-    if (c >= 0) m = fmaxf(m, fabsf(src.w[s][n * src.ld[s] + c]));
+    m = fmaxf(m, fabsf(tc_src_value(src, s, n, k)));
   }
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) atomicMax(absmax + s, __float_as_uint(m));
@@ -112,11 +130,7 @@ __global__ void k_pack_tc(TcSrc src, const float* __restrict__ inv_scale, uint8_
   float scale = 1.f / inv_scale[s];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N * K; i += gridDim.x * blockDim.x) {
     int n = i / K, k = i % K;
-    float v = 0.f;
-    if (src.w[s] != nullptr) {
-      int c = tc_src_col(s, k);
-      if (c >= 0) v = src.w[s][n * src.ld[s] + c] * scale;
-    }
+    const float v = tc_src_value(src, s, n, k) * scale;
     __half hi = __float2half_rn(v);
     __half lo = __float2half_rn(v - __half2float(hi));
     int kc = k >> 5, kk = k & 31;
@@ -183,8 +197,9 @@ int pack_field(mnrf_field* f, const float* const* t, cudaStream_t st) {
   src.w[8] = t[T_FINAL_W]; src.ld[8] = W;
   src.w[9] = t[T_M0_W];    src.ld[9] = W;
   src.w[10] = t[T_DIR_W];  src.ld[10] = W + IN_DIR;
+  for (int s = TC_FWD_STEPS; s < TC_NUM_STEPS; ++s) { const int l = tc_step_layer(s); src.w[s] = t[2 * l]; src.ld[s] = trunk_k(l); }
   unsigned int* absmax = reinterpret_cast<unsigned int*>(d + L.absmax);
-  MNRF_CUDA_OK(cudaMemsetAsync(absmax, 0, 16 * sizeof(unsigned int), st));
+  MNRF_CUDA_OK(cudaMemsetAsync(absmax, 0, 32 * sizeof(unsigned int), st));
   k_absmax<<<dim3(32, TC_NUM_STEPS), 256, 0, st>>>(src, absmax);
   MNRF_LAUNCH_OK();
   k_scales<<<1, 32, 0, st>>>(absmax, d + L.inv_scale);
