@@ -32,7 +32,8 @@ def npify(d):
     return {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in d.items()}
 
 
-def main():
+def generate():
+    """Run the reference on the seeded inputs; returns {fixture name: {key: ndarray}} (nothing is written)."""
     from mirror_nerf_b200.synthetic import random_rays, scene_state_dicts
     torch.set_num_threads(8)
     Embedding, MirrorNeRF, render_rays, sample_pdf = import_reference()
@@ -67,7 +68,7 @@ def main():
     o = fine(x_full.clone(), compute_normal=True, sigma_only=False, embedding_xyz=emb["xyz"])
     for k in ("sigma", "normal", "pred_normal", "rgb", "is_mirror"):
         out["grad_" + k] = o[k]
-    np.savez_compressed(os.path.join(HERE, "field.npz"), **npify(out))
+    files = {"field": npify(out)}
 
     # ---- 2. sample_pdf ---------------------------------------------------------------------------
     g = np.random.Generator(np.random.PCG64(11))
@@ -90,17 +91,17 @@ def main():
     pdf = ww / ww.sum(-1, keepdim=True)
     cdf = torch.cat([torch.zeros(n, 1), torch.cumsum(pdf, -1)], -1)
     u_det = torch.linspace(0, 1, 128).expand(n, 128).contiguous()
-    np.savez_compressed(os.path.join(HERE, "sample_pdf.npz"), **npify({
+    files["sample_pdf"] = npify({
         "bins": bins, "weights": w, "det": det, "rnd": rnd, "u": u, "cdf": cdf,
         "inds_det": torch.searchsorted(cdf, u_det, right=True),
-        "inds_rnd": torch.searchsorted(cdf, u, right=True)}))
+        "inds_rnd": torch.searchsorted(cdf, u, right=True)})
 
     # ---- 3. render_rays, eval mode 64+128 (BASELINE config 2 per-level call) ---------------------
     rays = random_rays(64, seed=1)
     with torch.no_grad():
         r = render_rays(models, emb, rays, 64, False, 0, 0, 128, 32768, False, test_time=True,
                         compute_normal=False)
-    np.savez_compressed(os.path.join(HERE, "render_eval.npz"), rays=rays.numpy(), **npify(r))
+    files["render_eval"] = dict(rays=rays.numpy(), **npify(r))
 
     # ---- 4. variants -------------------------------------------------------------------------------
     rays_s = random_rays(12, seed=2)
@@ -124,7 +125,7 @@ def main():
                                           test_time=False, compute_normal=False))
         put("s32_i16", render_rays(models, emb, rays_s, 32, False, 0, 0, 16, 1000, False, test_time=True,
                                    compute_normal=False))
-    np.savez_compressed(os.path.join(HERE, "render_variants.npz"), **npify(var))
+    files["render_variants"] = npify(var)
 
     # ---- 5. train mode: grad normals, perturb + noise with a replayable RNG stream, and gradients --
     rays_t = random_rays(8, seed=3)
@@ -149,7 +150,13 @@ def main():
             # big matrices: every 13th element + the L2 norm (keeps the fixture small)
             tr[f"grad/{tag}/{k}"] = p.grad.flatten()[::13] if p.grad.numel() > 4096 else p.grad
             tr[f"gradnorm/{tag}/{k}"] = p.grad.norm()
-    np.savez_compressed(os.path.join(HERE, "render_train.npz"), **npify(tr))
+    files["render_train"] = npify(tr)
+    return files
+
+
+def main():
+    for name, d in generate().items():
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

@@ -1,23 +1,36 @@
-"""The CPU oracle (oracle/mirror_nerf_oracle.py) against vectors produced by the unmodified reference
-(tests/golden/make_golden.py).  Float tolerance 1e-6 abs / 1e-5 rel (bit-identical in the container that
-generated them; a different host CPU may pick different BLAS kernels); indices must be exact."""
+"""The CPU oracle (oracle/mirror_nerf_oracle.py) against the unmodified reference, twice (fixture `golden`):
+
+* "live": the reference is imported from /root/reference and run in this process -> the oracle must be BIT-IDENTICAL
+  (same ATen kernels, same host).  Skipped where the reference tree does not exist (the GPU box).
+* "file": the committed vectors of tests/golden/*.npz.  They were produced on another host CPU; the reference itself
+  moves by ~5e-7 per point between hosts (different BLAS kernels) and the sharp synthetic field amplifies that along a
+  ray (observed reference-vs-reference: up to 1.7e-3 on single `weights_fine` entries).  Per-point field outputs:
+  1e-5 rel / 2e-6 abs.  Rendered outputs: median relative error <= 1e-5 and at most 5 % of a tensor's entries off
+  by more than 1e-3 (relative to max(|want|, rms)).  Indices / CDF of sample_pdf on given weights are exact."""
 import numpy as np
 import pytest
 import torch
 
 from mirror_nerf_b200.synthetic import scene_state_dicts
 from oracle import mirror_nerf_oracle as O
+from util import err_stats
 
 
 def T(x):
     return torch.from_numpy(np.asarray(x))
 
 
-def close(a, b, name, rtol=1e-5, atol=1e-6):
+def close(a, b, name, rtol=1e-5, atol=2e-6, exact=False, rendered=False, med=1e-5, frac=0.05):
     a = a.detach() if isinstance(a, torch.Tensor) else T(a)
     b = T(b)
     assert a.shape == b.shape, (name, a.shape, b.shape)
-    assert torch.allclose(a, b, rtol=rtol, atol=atol), (name, float((a - b).abs().max()))
+    if exact:
+        assert torch.equal(a, b), (name, float((a - b).abs().max()))
+    elif rendered:
+        s = err_stats(a, b)
+        assert s["median"] <= med and s["frac"] <= frac, (name, s)
+    else:
+        assert torch.allclose(a, b, rtol=rtol, atol=atol), (name, float((a - b).abs().max()))
 
 
 @pytest.fixture(scope="module")
@@ -37,15 +50,17 @@ def test_field_forward(golden, params):
     with torch.no_grad():
         o = O.field_forward(params["fine"], x.clone(), compute_normal=False, sigma_only=False)
     for k in ("sigma", "geo_feat", "pred_normal", "rgb", "is_mirror"):
-        close(o[k], g["full_" + k], k)
+        close(o[k], g["full_" + k], k, exact=golden.exact)
     with torch.no_grad():
         o = O.field_forward(params["fine"], T(g["xyz"]).clone(), compute_normal=False, sigma_only=True)
     assert set(o) == {"sigma", "geo_feat", "pred_normal"}
-    close(o["sigma"], g["sigonly_sigma"], "sigonly_sigma")
-    close(o["pred_normal"], g["sigonly_pred_normal"], "sigonly_pred_normal")
+    close(o["sigma"], g["sigonly_sigma"], "sigonly_sigma", exact=golden.exact)
+    close(o["pred_normal"], g["sigonly_pred_normal"], "sigonly_pred_normal", exact=golden.exact)
     o = O.field_forward(params["fine"], x.clone(), compute_normal=True, sigma_only=False)
     for k in ("sigma", "normal", "pred_normal", "rgb", "is_mirror"):
-        close(o[k], g["grad_" + k], "grad_" + k)
+        # the autograd normal is a normalised gradient of a sharp field: BLAS kernel choice on another host CPU moves it
+        # by a few 1e-6 (observed 2.2e-6), so it gets a looser absolute tolerance than the forward outputs
+        close(o[k], g["grad_" + k], "grad_" + k, atol=2e-5 if k == "normal" else 2e-6, exact=golden.exact)
 
 
 def test_explicit_normal_chain_matches_autograd(golden, params):
@@ -66,10 +81,10 @@ def test_sample_pdf(golden):
     s, inds, cdf = O.sample_pdf(bins, w, 128, det=True, return_inds=True)
     assert torch.equal(inds, T(g["inds_det"]))
     close(cdf, g["cdf"], "cdf", atol=0, rtol=0)
-    close(s, g["det"], "det")
+    close(s, g["det"], "det", exact=golden.exact)
     s, inds, _ = O.sample_pdf(bins, w, 128, det=False, u=T(g["u"]), return_inds=True)
     assert torch.equal(inds, T(g["inds_rnd"]))
-    close(s, g["rnd"], "rnd")
+    close(s, g["rnd"], "rnd", exact=golden.exact)
     assert bool((s[:, :] >= bins[:, :1]).all()) and bool((s <= bins[:, -1:]).all())
 
 
@@ -80,7 +95,7 @@ def test_render_eval(golden, params):
                           compute_normal=False)
     assert set(r) == set(g) - {"rays"}
     for k in r:
-        close(r[k], g[k], k)
+        close(r[k], g[k], k, exact=golden.exact, rendered=True)
 
 
 VARIANTS = {
@@ -104,7 +119,7 @@ def test_render_variants(golden, params, tag):
     want = {k.split("/", 1)[1]: a for k, a in g.items() if k.startswith(tag + "/")}
     assert set(r) == set(want)
     for k in r:
-        close(r[k], want[k], f"{tag}/{k}")
+        close(r[k], want[k], f"{tag}/{k}", exact=golden.exact, rendered=True)
 
 
 def test_render_train_with_grads(golden):
@@ -119,14 +134,24 @@ def test_render_train_with_grads(golden):
     want = {k.split("/", 1)[1]: a for k, a in g.items() if k.startswith("out/")}
     assert set(r) == set(want)
     for k in r:
-        close(r[k], want[k], k, rtol=1e-4, atol=1e-5)
+        # 8 rays, perturbed samples, normals = normalised autograd gradients of the sharp field: the host-to-host
+        # movement of the reference itself reaches 2e-3 on a few of the 24 composited-normal entries
+        close(r[k], want[k], k, exact=golden.exact, rendered=True, med=1e-4, frac=0.25)
     loss = sum((r[f"rgb_{t}"] ** 2).sum() + r[f"mirror_mask_{t}"].sum() + 0.1 * r[f"normal_dif_{t}"].sum()
                + 0.01 * (r[f"depth_{t}"]).sum() for t in ("coarse", "fine"))
     loss.backward()
-    close(loss, g["loss"], "loss", rtol=1e-5)
+    close(loss, g["loss"], "loss", rtol=1e-4, exact=golden.exact)
     for tag in ("coarse", "fine"):
         for k, t in params[tag].items():
             gr = t.grad.flatten()[::13] if t.grad.numel() > 4096 else t.grad
             want_g = T(g[f"grad/{tag}/{k}"])
-            scale = float(T(g[f"gradnorm/{tag}/{k}"])) / max(1.0, t.grad.numel() ** 0.5)
-            assert float((gr - want_g).abs().max()) <= 1e-4 * max(scale, 1e-6) + 1e-3 * float(want_g.abs().max()) + 1e-9, k
+            if golden.exact:
+                assert torch.equal(gr.detach(), want_g), k
+                assert torch.equal(t.grad.norm(), T(g[f"gradnorm/{tag}/{k}"])), k
+                continue
+            # host-tolerant: direction of the (subsampled) gradient and its norm
+            a, b = gr.detach().double().flatten(), want_g.double().flatten()
+            cos = float((a * b).sum() / (a.norm() * b.norm()).clamp_min(1e-300))
+            assert cos > 0.999, (k, cos)
+            gn, wn = float(t.grad.norm()), float(T(g[f"gradnorm/{tag}/{k}"]))
+            assert abs(gn - wn) <= 2e-2 * wn + 1e-9, (k, gn, wn)
