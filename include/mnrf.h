@@ -179,6 +179,61 @@ int mnrf_render_level_host(const mnrf_field* coarse, const mnrf_field* fine, con
                            float* rgb, float* depth, float* opacity, float* mirror_mask, float* surface_normal,
                            float* x_surface, void* stream);
 
+/* ---- training: one pass with saved activations and its backward -------------------
+ * Replaces what torch.autograd records for R/models/rendering.py:87-266 (inference(): model call + quadrature) when
+ * train.py:129-145 calls render_rays with gradients enabled: forward of one pass (field at the samples of a ray batch
+ * -> compositor) that keeps every activation the backward needs in a caller-provided workspace, and the backward
+ * that turns the gradients of the pass outputs into gradients of the 32 parameter tensors -- including the second-order
+ * path through the analytic normal  n = normalize(-d sigma/d xyz)  (mirror_nerf.py:136-146, create_graph=True in
+ * utils/func.py:10-25).  All GEMMs are fp32 CUDA-core kernels (train.cu).  Gradients w.r.t. rays / z are not produced
+ * (z_fine is detached by the reference, rendering.py:335,353). */
+typedef struct mnrf_train_cfg {
+  int S;              /* samples per ray of this pass */
+  int compute_normal; /* analytic normals (and their double backward) */
+  int white_back;
+  float noise_std;    /* multiplies `noise` (ignored when noise == NULL) */
+  int detach_density_for_mask_loss;   /* mirror_nerf.py:169-170, rendering.py:222-226 */
+  int detach_density_for_normal_loss; /* mirror_nerf.py:158, rendering.py:245-247 */
+} mnrf_train_cfg;
+
+/* gradients of the pass outputs (device, any may be NULL = zero) */
+typedef struct mnrf_train_grads {
+  const float* rgb;                 /* (n,3) */
+  const float* depth;               /* (n)   */
+  const float* opacity;             /* (n)   */
+  const float* mirror_mask;         /* (n)   */
+  const float* surface_normal;      /* (n,3) */
+  const float* surface_normal_grad; /* (n,3) */
+  const float* normal_dif;          /* (n)   */
+  const float* x_surface;           /* (n,3) */
+  const float* weights;             /* (n,S) */
+  const float* pred_normal;         /* (n,S,3) */
+  const float* normal;              /* (n,S,3) */
+} mnrf_train_grads;
+
+int64_t mnrf_train_fwd_workspace_bytes(int n, int S, int compute_normal);
+int64_t mnrf_train_bwd_workspace_bytes(int n, int S, int compute_normal);
+
+/* Forward: rays (n,8), z (n,S), noise (n,S) or NULL.  Writes the compositor outputs (`out`, same meaning as
+ * mnrf_composite) and, when cfg->compute_normal, the per-sample analytic normals normal_out (n,S,3).
+ * ws: mnrf_train_fwd_workspace_bytes(n,S,compute_normal) bytes, must stay untouched until the backward has run. */
+int mnrf_train_pass_fwd(const mnrf_field* f, const float* rays, const float* z, const float* noise, int n,
+                        const mnrf_train_cfg* cfg, void* ws, int64_t ws_bytes, const mnrf_composite_out* out,
+                        float* normal_out, void* stream);
+
+/* Backward.  grad_tensors: HOST array of 32 DEVICE pointers in mnrf_field_create order, each the size of its
+ * parameter ([out,in] layout), ACCUMULATED into (zero them first for plain gradients); entries of absent heads NULL.
+ * ray_detach_mirror: optional (n) floats, != 0 marks rays whose density is detached from the mirror-mask loss
+ * (detach_density_outside_mirror_for_mask_loss, mirror_nerf.py:171-183 / rendering.py:227-238: rays outside the
+ * ground-truth mirror).  Accumulation uses atomics: results are not bit-reproducible run to run. */
+int mnrf_train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, const float* noise, int n,
+                        const mnrf_train_cfg* cfg, const void* ws_fwd, int64_t ws_fwd_bytes, void* ws_bwd,
+                        int64_t ws_bwd_bytes, const mnrf_train_grads* grads, const float* ray_detach_mirror,
+                        float* const* grad_tensors, void* stream);
+
+/* out[i] += alpha * in[i] (fp32, n elements): gradient-buffer plumbing for the data-parallel all-reduce */
+int mnrf_axpy(float* out, const float* in, int64_t n, float alpha, void* stream);
+
 /* ---- Whitted bounce helpers (callers of render_rays: eval.py:295-697, train.py:153-296) ---------- */
 
 /* mask (n) is thresholded IN PLACE (>0.5 -> 1, <0.5 -> 0, exactly 0.5 kept; eval.py:305-306).

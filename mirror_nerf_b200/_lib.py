@@ -38,6 +38,19 @@ class LevelOut(C.Structure):
                 ("z_fine", C.c_void_p), ("fine", CompositeOut), ("normal_fine", C.c_void_p)]
 
 
+class TrainCfg(C.Structure):
+    _fields_ = [("S", c_int), ("compute_normal", c_int), ("white_back", c_int), ("noise_std", C.c_float),
+                ("detach_density_for_mask_loss", c_int), ("detach_density_for_normal_loss", c_int)]
+
+
+TRAIN_GRAD_FIELDS = ("rgb", "depth", "opacity", "mirror_mask", "surface_normal", "surface_normal_grad", "normal_dif",
+                     "x_surface", "weights", "pred_normal", "normal")
+
+
+class TrainGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in TRAIN_GRAD_FIELDS]
+
+
 _SIGS = {
     "mnrf_last_error": (C.c_char_p, []),
     "mnrf_abi_version": (c_int, []),
@@ -73,6 +86,14 @@ _SIGS = {
     "mnrf_render_level_host": (c_int, [C.c_void_p, C.c_void_p, c_float_p, c_int, C.POINTER(LevelCfg), c_float_p,
                                        c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
                                        C.c_void_p]),
+    "mnrf_train_fwd_workspace_bytes": (C.c_int64, [c_int, c_int, c_int]),
+    "mnrf_train_bwd_workspace_bytes": (C.c_int64, [c_int, c_int, c_int]),
+    "mnrf_train_pass_fwd": (c_int, [C.c_void_p, c_float_p, c_float_p, c_float_p, c_int, C.POINTER(TrainCfg), C.c_void_p,
+                                    C.c_int64, C.POINTER(CompositeOut), c_float_p, C.c_void_p]),
+    "mnrf_train_pass_bwd": (c_int, [C.c_void_p, c_float_p, c_float_p, c_float_p, c_int, C.POINTER(TrainCfg), C.c_void_p,
+                                    C.c_int64, C.c_void_p, C.c_int64, C.POINTER(TrainGrads), c_float_p,
+                                    C.POINTER(C.c_void_p), C.c_void_p]),
+    "mnrf_axpy": (c_int, [c_float_p, c_float_p, C.c_int64, C.c_float, C.c_void_p]),
     "mnrf_reflect_rays": (c_int, [c_float_p, c_float_p, c_float_p, c_float_p, c_int, C.c_float, c_float_p, c_float_p,
                                   C.c_void_p, C.c_void_p]),
     "mnrf_compact_rows": (c_int, [c_float_p, c_float_p, c_int, c_int, c_float_p, C.c_void_p, C.c_void_p, C.c_void_p]),

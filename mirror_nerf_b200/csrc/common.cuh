@@ -87,6 +87,14 @@ struct F32Layout {
   int headb;      // float4: {b_sigma, bn_fold[0..2]}
   int inv_scale;  // float[TC_NUM_STEPS]
   int absmax;     // uint[TC_NUM_STEPS] scratch for the scale computation
+  // training path (train.cu): [out][in] copies with 16-byte aligned rows, the B operands of the dgrad / normal-chain GEMMs
+  int tw_l1;      // [256][64]   W1, column 63 zero
+  int tw_l5a;     // [256][64]   W5[:, :63] (PE part), column 63 zero
+  int tw_l5b;     // [256][256]  W5[:, 63:] (h part)
+  int tw_final;   // [256][256]
+  int tw_dira;    // [128][256]  W_dir[:, :256] (feature part)
+  int tw_n0;      // [128][256]
+  int tw_m0;      // [128][256]
   int total;
 };
 
@@ -121,6 +129,13 @@ inline F32Layout make_f32_layout() {
   L.b_m2 = L.epi_tab + ET_B_M2;
   L.b_rgb = L.epi_tab + ET_B_RGB;
   L.absmax = take(32);
+  L.tw_l1 = take(W * PE_PAD);
+  L.tw_l5a = take(W * PE_PAD);
+  L.tw_l5b = take(W * W);
+  L.tw_final = take(W * W);
+  L.tw_dira = take(WH * W);
+  L.tw_n0 = take(WH * W);
+  L.tw_m0 = take(WH * W);
   L.total = o;
   return L;
 }
@@ -217,6 +232,16 @@ int launch_blend(const float* base, const float* mask, const float* child_rgb, c
                  const int* index, int n, float* rgb_out, float* rgb_reflect, float* depth_reflect, cudaStream_t st);
 
 int launch_field_fp32(const mnrf_field* f, const FieldIO& io, cudaStream_t st);
+
+// training path (train.cu): one field + compositor pass with saved activations, and its backward
+int64_t train_fwd_workspace_bytes(int n, int S, int compute_normal);
+int64_t train_bwd_workspace_bytes(int n, int S, int compute_normal);
+int train_pass_fwd(const mnrf_field* f, const float* rays, const float* z, const float* noise, int n,
+                   const mnrf_train_cfg& cfg, void* ws, const mnrf_composite_out& out, float* normal_out,
+                   cudaStream_t st);
+int train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, const float* noise, int n,
+                   const mnrf_train_cfg& cfg, const void* ws_fwd, void* ws_bwd, const mnrf_train_grads& g,
+                   const float* ray_detach_mirror, float* const* grad_tensors, cudaStream_t st);
 void set_tc_trace(unsigned long long* buf, unsigned int cap);
 int launch_field_tc(const mnrf_field* f, const FieldIO& io, int precision /*1|3*/, cudaStream_t st);
 

@@ -23,6 +23,15 @@ __global__ void k_transpose_pad(const float* __restrict__ src, float* __restrict
   dst[i] = (k < K) ? src[n * K + k] : 0.f;
 }
 
+// dst[r][c] = c < cols ? src[r*ld + c0 + c] : 0   (dst is [rows][cols_pad]): aligned-row copies for the training GEMMs
+__global__ void k_copy_block_pad(const float* __restrict__ src, float* __restrict__ dst, int rows, int ld, int c0, int cols,
+                                 int cols_pad) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols_pad) return;
+  int r = i / cols_pad, c = i % cols_pad;
+  dst[i] = (c < cols) ? src[(size_t)r * ld + c0 + c] : 0.f;
+}
+
 __global__ void k_fill(float* dst, float v, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = v;
@@ -152,6 +161,17 @@ static int copy_to(const float* src, float* dst, int n, cudaStream_t st) {
   return 0;
 }
 
+static int block_to(const float* src, float* dst, int rows, int ld, int c0, int cols, int cols_pad, cudaStream_t st) {
+  const int n = rows * cols_pad;
+  if (src == nullptr) {
+    k_fill<<<(n + 255) / 256, 256, 0, st>>>(dst, 0.f, n);
+  } else {
+    k_copy_block_pad<<<(n + 255) / 256, 256, 0, st>>>(src, dst, rows, ld, c0, cols, cols_pad);
+  }
+  MNRF_LAUNCH_OK();
+  return 0;
+}
+
 static int transpose_to(const float* src, float* dst, int N, int K, cudaStream_t st) {
   int Kp = pad4(K);
   if (src == nullptr) {
@@ -187,6 +207,15 @@ int pack_field(mnrf_field* f, const float* const* t, cudaStream_t st) {
   if (copy_to(t[T_M0_B], d + L.b_m0, WH, st)) return 1;
   if (copy_to(t[T_M2_W], d + L.w_m2, WH, st)) return 1;
   if (copy_to(t[T_M2_B], d + L.b_m2, 1, st)) return 1;
+
+  // aligned [out][in] copies for the training path (train.cu)
+  if (block_to(t[0], d + L.tw_l1, W, IN_XYZ, 0, IN_XYZ, PE_PAD, st)) return 1;
+  if (block_to(t[8], d + L.tw_l5a, W, IN_XYZ + W, 0, IN_XYZ, PE_PAD, st)) return 1;
+  if (block_to(t[8], d + L.tw_l5b, W, IN_XYZ + W, IN_XYZ, W, W, st)) return 1;
+  if (block_to(t[T_FINAL_W], d + L.tw_final, W, W, 0, W, W, st)) return 1;
+  if (block_to(t[T_DIR_W], d + L.tw_dira, WH, W + IN_DIR, 0, W, W, st)) return 1;
+  if (block_to(t[T_N0_W], d + L.tw_n0, WH, W, 0, W, W, st)) return 1;
+  if (block_to(t[T_M0_W], d + L.tw_m0, WH, W, 0, W, W, st)) return 1;
 
   k_fold_heads<<<1, 256, 0, st>>>(t[T_SIGMA_W], t[T_SIGMA_B], t[T_N0_W], t[T_N0_B], t[T_N1_W], t[T_N1_B],
                                   reinterpret_cast<float4*>(d + L.headw), d + L.headb);

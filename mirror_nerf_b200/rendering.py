@@ -7,7 +7,9 @@ Differences from the reference that a caller can observe:
   * inputs must be CUDA float32 tensors -- there is no CPU path (RuntimeError otherwise);
   * ``chunk`` does not change results (the reference's don't depend on it either); it is ignored, the ray batch
     is processed in sub-batches sized to bound scratch memory;
-  * gradients are not produced yet: calling with autograd enabled on parameters that require grad raises;
+  * with autograd enabled and parameters that require grad, the level runs through the training path
+    (``autograd.py`` / ``csrc/train.cu``: fp32 layer-by-layer kernels with a hand-written backward); gradients reach the
+    parameters of both models, not the rays;
   * a batch of exactly one ray works (the reference's ``.squeeze()`` at rendering.py:365 breaks it);
   * ``view_dir`` (never passed by any reference caller) is not supported.
 """
@@ -19,7 +21,7 @@ import os
 import torch
 
 from . import _lib
-from .mirror_nerf import _no_autograd, _ptr, _stream_ptr, packed_field
+from .mirror_nerf import _ptr, _stream_ptr, packed_field
 
 __all__ = ["render_rays", "sample_pdf"]
 
@@ -78,12 +80,87 @@ def sample_pdf(bins, weights, N_importance, det=False, eps=1e-5, return_inds=Fal
     return samples
 
 
+def _render_level_train(lib, models, rays, Sc, Ni, second_pass, rerun, sig_only, use_disp, perturb, noise_std, white_back,
+                        compute_normal, kwargs, perturb_u, noise_c, u_pdf, noise_f):
+    """render_rays with gradients (rendering.py:268-369 under autograd): per group of rays, coarse depths -> differentiable
+    coarse pass -> inverse-CDF resampling on the DETACHED coarse weights (rendering.py:335,353) -> differentiable second
+    pass.  Each pass is one autograd node (autograd._PassFn)."""
+    from . import autograd as AG
+    dev = rays.device
+    n = rays.shape[0]
+    Sf = Sc + Ni
+    detach_mask = bool(kwargs.get("detach_density_for_mask_loss", False))
+    detach_normal = bool(kwargs.get("detach_density_for_normal_loss", False))
+    ray_detach_all = None
+    mm = kwargs.get("mirror_mask")
+    if kwargs.get("detach_density_outside_mirror_for_mask_loss", False) and mm is not None and not detach_mask:
+        mm = mm.to(dev).reshape(-1)
+        if not bool((mm < 0).any()):  # rendering.py:227-231 (host sync, as in the reference)
+            if mm.shape[0] != n:
+                raise RuntimeError(f"mirror_mask has {mm.shape[0]} entries for {n} rays")
+            ray_detach_all = (~mm.bool()).float().contiguous()
+    z_steps = _linspace(Sc, dev)
+    u_det = _linspace(Ni, dev) if Ni > 0 else None
+    second_module = models["coarse"] if rerun else models.get("fine")
+    parts_c, parts_f = [], []
+    cut = lambda t, lo, hi: None if t is None else t[lo:hi].contiguous()
+    for lo in range(0, max(n, 1), AG.MAX_TRAIN_RAYS):
+        hi = min(n, lo + AG.MAX_TRAIN_RAYS)
+        m = hi - lo
+        r = rays[lo:hi].contiguous()
+        rd = cut(ray_detach_all, lo, hi)
+        z_c = torch.empty(m, Sc, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            _lib.check(lib.mnrf_coarse_z(_ptr(r), m, _ptr(z_steps), Sc, int(bool(use_disp)), float(perturb),
+                                         _ptr(cut(perturb_u, lo, hi)), _ptr(z_c), _stream_ptr()), "mnrf_coarse_z")
+        common = dict(compute_normal=compute_normal, white_back=bool(white_back), noise_std=float(noise_std),
+                      detach_mask=detach_mask, detach_normal=detach_normal)
+        oc = AG.run_pass(models["coarse"], r, z_c, cut(noise_c, lo, hi), rd, **common)
+        oc["z_vals"] = z_c
+        if sig_only:  # rendering.py:208-209: the coarse pass only publishes weights / opacity / z_vals at test time
+            oc = {k: oc[k] for k in ("weights", "opacity", "z_vals")}
+        parts_c.append(oc)
+        if second_pass:
+            z_f = torch.empty(m, Sf, device=dev, dtype=torch.float32)
+            u = cut(u_pdf, lo, hi) if u_pdf is not None else u_det
+            with torch.cuda.device(dev):
+                _lib.check(lib.mnrf_sample_pdf(_ptr(z_c), _ptr(oc["weights"].detach()), m, Sc, Ni, _ptr(u),
+                                               Ni if u_pdf is not None else 0, _ptr(z_f), None, None, None,
+                                               _stream_ptr()), "mnrf_sample_pdf")
+            of = AG.run_pass(second_module, r, z_f, cut(noise_f, lo, hi), rd, **common)
+            of["z_vals"] = z_f
+            parts_f.append(of)
+
+    def merge(parts):
+        return {k: (parts[0][k] if len(parts) == 1 else torch.cat([p[k] for p in parts], 0)) for k in parts[0]}
+
+    order = ("weights", "opacity", "z_vals", "rgb", "depth", "mirror_mask", "normal", "surface_normal_grad",
+             "pred_normal", "surface_normal", "normal_dif")
+    res = {}
+    tc = merge(parts_c)
+    for k in order:
+        if k in tc:
+            res[f"{k}_coarse"] = tc[k]
+    if second_pass:
+        tf = merge(parts_f)
+        typ = "coarse" if rerun else "fine"
+        for k in order:
+            if k in tf:
+                res[f"{k}_{typ}"] = tf[k]
+        if "x_surface" in tc and not rerun:
+            res["x_surface_coarse"] = tc["x_surface"]
+        res[f"x_surface_{typ}"] = tf["x_surface"]
+    elif "x_surface" in tc:
+        res["x_surface_coarse"] = tc["x_surface"]
+    return res
+
+
 def render_rays(models, embeddings, rays, N_samples=64, use_disp=False, perturb=0, noise_std=1, N_importance=0,
                 chunk=1024 * 32, white_back=False, test_time=False, **kwargs):
     """One render level.  See the module docstring; kwargs consumed: compute_normal (default True, like the
     reference), only_one_field, current_epoch, only_one_field_fine_epoch, field_impl ("tc3" | "tc1" | "fp32"),
     rng (dict of explicit draws: perturb_u, noise_coarse, u_pdf, noise_fine -- for tests).  mirror_mask and the three
-    detach_* flags only affect gradients and are accepted and ignored in this forward-only build."""
+    detach_* flags only shape gradients: they are honoured by the training path and have no effect on forward values."""
     lib = _lib.load()
     rays = _check_rays(rays)
     dev = rays.device
@@ -108,7 +185,7 @@ def render_rays(models, embeddings, rays, N_samples=64, use_disp=False, perturb=
     params = list(models["coarse"].parameters()) if hasattr(models["coarse"], "parameters") else []
     if has_fine_model and hasattr(models["fine"], "parameters"):
         params += list(models["fine"].parameters())
-    _no_autograd("render_rays", params)
+    needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
 
     coarse = packed_field(models["coarse"])
     fine = packed_field(models["fine"]) if (has_fine_model and not only_one_field) else None
@@ -136,6 +213,10 @@ def render_rays(models, embeddings, rays, N_samples=64, use_disp=False, perturb=
     noise_c = draw("noise_coarse", (n, Sc), torch.randn) if noise_std != 0 else None
     u_pdf = draw("u_pdf", (n, Ni), torch.rand) if (second_pass and perturb != 0) else None
     noise_f = draw("noise_fine", (n, Sf), torch.randn) if (second_pass and noise_std != 0) else None
+
+    if needs_grad:
+        return _render_level_train(lib, models, rays, Sc, Ni, second_pass, rerun, sig_only, use_disp, perturb, noise_std,
+                                   white_back, compute_normal, kwargs, perturb_u, noise_c, u_pdf, noise_f)
 
     new = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
     res = {}
