@@ -126,6 +126,104 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+TRAIN_RAYS = 4096             # BASELINE config 5: 4096-ray batches (per process, PL semantics: R/train.py:368-375)
+TRAIN_FLOP_PER_RAY = 1.77e9   # 256 points x ~6.9 MFLOP (forward + analytic-normal chain + backward + double backward)
+
+
+def train_loss(r, target, mask_gt):
+    """Stand-in for R/losses.py:201-259 (colour MSE on both passes, mirror-mask BCE, normal consistency 1e-4,
+    normal regularisation 1e-4): tiny per-ray torch ops, every differentiable output of the level is used."""
+    import torch
+    loss = 0.0
+    for t in ("coarse", "fine"):
+        loss = loss + ((r[f"rgb_{t}"] - target) ** 2).mean()
+        m = r[f"mirror_mask_{t}"].clamp(1e-7, 1 - 1e-7)
+        loss = loss + 0.1 * torch.nn.functional.binary_cross_entropy(m, mask_gt)
+        loss = loss + 1e-4 * r[f"normal_dif_{t}"].mean()
+        loss = loss + 1e-4 * (torch.relu(r[f"pred_normal_{t}"] * r["_rays_d"].unsqueeze(1)).sum(-1) * r[f"weights_{t}"]).mean()
+    return loss
+
+
+def train_bench(dev, world, rank, steps, warmup):
+    """BASELINE config 5 on this rank: 4096-ray batch, train semantics (perturb=1, noise_std=1, analytic normals), forward +
+    backward through csrc/train.cu, ONE flat NCCL all-reduce of the 5.3 MB gradient buffer, one Adam kernel.  Returns a dict."""
+    import torch
+    import torch.distributed as dist
+    from mirror_nerf_b200 import _lib
+    from mirror_nerf_b200.mirror_nerf import Embedding, MirrorNeRF
+    from mirror_nerf_b200.parallel import FlatDataParallel
+    from mirror_nerf_b200.rendering import render_rays
+    from mirror_nerf_b200.synthetic import camera_rays, scene_state_dicts
+    models = {}
+    for k, sd in scene_state_dicts().items():
+        m = MirrorNeRF(predict_normal=True, predict_mirror_mask=True)
+        m.load_state_dict(sd)
+        models[k] = m.to(dev).train()
+    emb = {"xyz": Embedding(10), "dir": Embedding(4)}
+    ddp = FlatDataParallel(models, lr=5e-4)
+    g = torch.Generator().manual_seed(1234 + rank)
+    allrays = camera_rays(H, W, c2w=view_pose(rank))
+    rays = allrays[torch.randperm(allrays.shape[0], generator=g)[:TRAIN_RAYS]].contiguous().to(dev)
+    target = torch.rand(TRAIN_RAYS, 3, generator=g).to(dev)
+    mask_gt = (torch.rand(TRAIN_RAYS, generator=g) > 0.7).float().to(dev)
+    losses = []
+
+    def one():
+        ddp.zero_grad()
+        r = render_rays(models, emb, rays, N_SAMPLES, False, 1.0, 1.0, N_IMPORTANCE, 32768, False, test_time=False,
+                        compute_normal=True)
+        r["_rays_d"] = rays[:, 3:6]
+        loss = train_loss(r, target, mask_gt)
+        loss.backward()
+        ddp.step()
+        losses.append(loss.detach())
+
+    for _ in range(warmup):
+        one()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    rate = world * TRAIN_RAYS * steps / (ms * 1e-3)
+    return {"metric": "rays/sec (train step: forward + backward + gradient all-reduce + Adam; 4096-ray batch per GPU, "
+                      "64+128 samples, analytic normals, fp32)",
+            "value": rate, "unit": "rays/s", "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
+            "dtype": "f32 (CUDA-core GEMMs)", "launches_per_step": (_lib.launch_count() - l0) / steps,
+            "algorithmic_tflops": rate / world * TRAIN_FLOP_PER_RAY / 1e12,
+            "allreduce_bytes_per_step": ddp.flat_grads.numel() * 4 if world > 1 else 0,
+            "loss_first": float(losses[0]), "loss_last": float(losses[-1])}
+
+
+def cpu_train_rate(n_rays, threads):
+    """The reference's training step (oracle port: torch CPU autograd, same loss) on the host cores."""
+    import torch
+    from mirror_nerf_b200.synthetic import camera_rays, scene_state_dicts
+    from oracle import mirror_nerf_oracle as O
+    torch.set_num_threads(threads)
+    params = {t: {k: v.clone().requires_grad_(True) for k, v in sd.items()} for t, sd in scene_state_dicts().items()}
+    g = torch.Generator().manual_seed(1234)
+    allrays = camera_rays(H, W, c2w=view_pose(0))
+    rays = allrays[torch.randperm(allrays.shape[0], generator=g)[:n_rays]].contiguous()
+    target = torch.rand(n_rays, 3, generator=g)
+    mask_gt = (torch.rand(n_rays, generator=g) > 0.7).float()
+    t0 = time.perf_counter()
+    r = O.render_rays(params, rays, N_SAMPLES, False, 1.0, 1.0, N_IMPORTANCE, 32768, False, test_time=False,
+                      compute_normal=True)
+    r["_rays_d"] = rays[:, 3:6]
+    train_loss(r, target, mask_gt).backward()
+    return n_rays / (time.perf_counter() - t0)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -253,6 +351,9 @@ def run_ours(args):
                      "tensor_pipe_flops_frac": (achieved * mma_per_mac / peak if achieved else None)},
     }
 
+    if not args.no_train:
+        line["train_step"] = train_bench(dev, world, rank, max(2, min(args.steps, 5)), 3)
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         rate, rgb_ref, rays_s, _ = cpu_reference_rate(args.ref_rays, 1, 1, threads)
@@ -263,6 +364,10 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": threads, "kind": "port",
                                 "sample": f"{args.ref_rays} rays of the same view, 64+128 samples, 1 bounce, 1 step"}
         line["psnr_vs_reference_db"] = (-10 * math.log10(mse) if mse > 0 else float("inf"))
+        if "train_step" in line:
+            line["train_step"]["cpu_baseline"] = {
+                "value": cpu_train_rate(128, threads), "unit": "rays/s", "cores": threads, "kind": "port",
+                "sample": "one 128-ray train step (forward + backward) of the oracle port on the host cores"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -279,6 +384,7 @@ def main():
     ap.add_argument("--field-impl", default="tc3", choices=["tc3", "tc1"])
     ap.add_argument("--ref-rays", type=int, default=2048, help="rays per step of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary train-step measurement (config 5)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

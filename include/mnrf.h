@@ -231,6 +231,12 @@ int mnrf_train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, 
                         int64_t ws_bwd_bytes, const mnrf_train_grads* grads, const float* ray_detach_mirror,
                         float* const* grad_tensors, void* stream);
 
+/* One torch.optim.Adam step (the reference's optimizer: R/utils/__init__.py:47-58, lr 5e-4, eps 1e-8, L2 weight decay) on flat
+ * fp32 buffers of n elements: g = grads*grad_scale + weight_decay*p; m,v updated in place; p -= lr/(1-b1^t) * m/(sqrt(v)/
+ * sqrt(1-b2^t) + eps).  `step` is t (1-based).  grad_scale = 1/world_size turns an all-reduce SUM into DDP's average. */
+int mnrf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
+
 /* out[i] += alpha * in[i] (fp32, n elements): gradient-buffer plumbing for the data-parallel all-reduce */
 int mnrf_axpy(float* out, const float* in, int64_t n, float alpha, void* stream);
 

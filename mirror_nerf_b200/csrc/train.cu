@@ -12,6 +12,8 @@
 // Its backward (the reference gets it from create_graph=True, utils/func.py:10-25) is linear in the weights because
 // relu'' = 0: with t0 = J_pe dL/dg_x,  t_k = (t_{k-1} W_k^T) * relu'(z_k)  [a second "tangent" forward pass],
 //   dW_k += q_k^T t_{k-1},   d w_sigma += sum_p t8.
+#include <cmath>
+
 #include "common.cuh"
 
 namespace mnrf {
@@ -729,6 +731,24 @@ __global__ void k_axpy(float* __restrict__ out, const float* __restrict__ in, lo
   if (i < n) out[i] = fmaf(alpha, in[i], out[i]);
 }
 
+// torch.optim.Adam (the reference's optimizer, R/utils/__init__.py:47-58: lr, eps=1e-8, weight_decay as L2) on flat buffers;
+// `grad_scale` folds the 1/world_size of the data-parallel gradient average into the same pass.
+__global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                       long long n, float lr, float beta1, float beta2, float eps, float weight_decay, float bc1, float bc2_sqrt,
+                       float grad_scale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float gi = g[i] * grad_scale;
+  const float pi = p[i];
+  if (weight_decay != 0.f) gi = fmaf(weight_decay, pi, gi);
+  const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+  const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] = pi - (lr / bc1) * (mi / denom);
+}
+
 // ---- host-side helpers -----------------------------------------------------------------------------------------------
 inline size_t al(size_t b) { return (b + 255) & ~(size_t)255; }
 
@@ -1096,6 +1116,18 @@ int mnrf_train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, 
   if (n == 0) return 0;
   return train_pass_bwd(f, rays, z, noise, n, *cfg, ws_fwd, ws_bwd, *grads, ray_detach_mirror, grad_tensors,
                         reinterpret_cast<cudaStream_t>(stream));
+}
+
+int mnrf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream) {
+  MNRF_REQUIRE(params && grads && exp_avg && exp_avg_sq && n >= 0 && step >= 1, "adam_step: bad argument");
+  if (n == 0) return 0;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  k_adam<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      params, grads, exp_avg, exp_avg_sq, (long long)n, lr, beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2),
+      grad_scale);
+  MNRF_LAUNCH_OK();
+  return 0;
 }
 
 int mnrf_axpy(float* out, const float* in, int64_t n, float alpha, void* stream) {

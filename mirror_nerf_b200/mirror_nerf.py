@@ -107,10 +107,18 @@ def packed_field(source) -> PackedField:
     return pf
 
 
+def invalidate_packed(module):
+    """Force a re-pack at the next use (parameters were changed by a raw kernel that does not bump ``_version``)."""
+    cached = module.__dict__.get("_mnrf_packed")
+    if cached is not None:
+        module.__dict__["_mnrf_packed"] = (cached[0], None, cached[2])
+
+
 def _no_autograd(what, tensors):
     if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
         raise NotImplementedError(
-            f"{what}: the backward pass (SURVEY.md section 8 row a12) is not built yet; call under torch.no_grad()")
+            f"{what}: gradients are produced by render_rays (mirror_nerf_b200/autograd.py), not by this flat-batch "
+            "forward; call it under torch.no_grad()")
 
 
 class Embedding(nn.Module):
