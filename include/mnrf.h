@@ -185,8 +185,9 @@ int mnrf_render_level_host(const mnrf_field* coarse, const mnrf_field* fine, con
  * -> compositor) that keeps every activation the backward needs in a caller-provided workspace, and the backward
  * that turns the gradients of the pass outputs into gradients of the 32 parameter tensors -- including the second-order
  * path through the analytic normal  n = normalize(-d sigma/d xyz)  (mirror_nerf.py:136-146, create_graph=True in
- * utils/func.py:10-25).  All GEMMs are fp32 CUDA-core kernels (train.cu).  Gradients w.r.t. rays / z are not produced
- * (z_fine is detached by the reference, rendering.py:335,353). */
+ * utils/func.py:10-25).  All GEMMs are fp32 CUDA-core kernels (train.cu).  Optionally also the gradient w.r.t. the rays'
+ * origin and direction (train.py:194-243 builds secondary rays from x_surface / normals without detaching).  z carries no
+ * gradient (z_fine is detached by the reference, rendering.py:335,353; near/far are constants). */
 typedef struct mnrf_train_cfg {
   int S;              /* samples per ray of this pass */
   int compute_normal; /* analytic normals (and their double backward) */
@@ -225,11 +226,13 @@ int mnrf_train_pass_fwd(const mnrf_field* f, const float* rays, const float* z, 
  * parameter ([out,in] layout), ACCUMULATED into (zero them first for plain gradients); entries of absent heads NULL.
  * ray_detach_mirror: optional (n) floats, != 0 marks rays whose density is detached from the mirror-mask loss
  * (detach_density_outside_mirror_for_mask_loss, mirror_nerf.py:171-183 / rendering.py:227-238: rays outside the
- * ground-truth mirror).  Accumulation uses atomics: results are not bit-reproducible run to run. */
+ * ground-truth mirror).  grad_rays: optional (n,8) OVERWRITTEN with dL/d[o, d, near, far] (near/far columns zero); it needs
+ * `depth` (n), the forward's depth output, when grads->x_surface is set.
+ * Accumulation uses atomics: results are not bit-reproducible run to run. */
 int mnrf_train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, const float* noise, int n,
                         const mnrf_train_cfg* cfg, const void* ws_fwd, int64_t ws_fwd_bytes, void* ws_bwd,
                         int64_t ws_bwd_bytes, const mnrf_train_grads* grads, const float* ray_detach_mirror,
-                        float* const* grad_tensors, void* stream);
+                        float* const* grad_tensors, const float* depth, float* grad_rays, void* stream);
 
 /* One torch.optim.Adam step (the reference's optimizer: R/utils/__init__.py:47-58, lr 5e-4, eps 1e-8, L2 weight decay) on flat
  * fp32 buffers of n elements: g = grads*grad_scale + weight_decay*p; m,v updated in place; p -= lr/(1-b1^t) * m/(sqrt(v)/

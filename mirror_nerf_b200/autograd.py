@@ -6,8 +6,9 @@ One ``torch.autograd.Function`` per pass (field at the samples of a ray batch ->
 backward, including the double backward through the analytic normals).  torch is only the plumbing: it owns the memory,
 routes the output gradients into the Function and the parameter gradients into ``.grad``.
 
-Not differentiable here (the reference differentiates them only through the Whitted recursion of its callers): the rays
-themselves.  ``z_vals_*`` carry no gradient in the reference either (rendering.py:335,353 detach the fine depths).
+Rays that require grad (secondary rays built from x_surface / surface normals, train.py:194-243) receive dL/d[o, d] as
+well.  ``z_vals_*`` carry no gradient, as in the reference (rendering.py:335,353 detach the fine depths; the coarse depths
+depend on near / far only).
 """
 from __future__ import annotations
 
@@ -70,7 +71,8 @@ class _PassFn(torch.autograd.Function):
             _lib.check(lib.mnrf_train_pass_fwd(pf.handle, _ptr(rays), _ptr(z), _ptr(noise), n, C.byref(cfg), _ptr(ws),
                                                need, C.byref(out), p("normal"), _stream_ptr()), "mnrf_train_pass_fwd")
         ctx.meta, ctx.cfg, ctx.ws, ctx.ws_bytes = meta, cfg, ws, need
-        ctx.rays, ctx.z, ctx.noise, ctx.ray_detach = rays, z, noise, ray_detach
+        ctx.rays, ctx.z, ctx.noise, ctx.ray_detach = rays.detach(), z, noise, ray_detach
+        ctx.depth = t["depth"].clone()  # private copy: callers may modify outputs in place
         ctx.param_shapes = [tuple(q.shape) for q in params]
         ctx.out_keys = [k for k in _OUT_ORDER if k in t]
         return tuple(t[k] for k in ctx.out_keys)
@@ -90,13 +92,15 @@ class _PassFn(torch.autograd.Function):
         # gradient tensors in the reference's parameter order / layout; absent heads stay NULL
         gts = {k: torch.zeros(shp, device=dev, dtype=torch.float32) for k, shp in zip(meta["keys"], ctx.param_shapes)}
         arr = (C.c_void_p * _lib.NUM_PARAM_TENSORS)(*[None if k not in gts else gts[k].data_ptr() for k in PARAM_KEYS])
+        grad_rays = torch.empty(n, 8, device=dev, dtype=torch.float32) if ctx.needs_input_grad[1] else None
         with torch.cuda.device(dev):
             need = int(lib.mnrf_train_bwd_workspace_bytes(n, S, cfg.compute_normal))
             wsb = torch.empty(max(need, 1), device=dev, dtype=torch.uint8)
             _lib.check(lib.mnrf_train_pass_bwd(pf.handle, _ptr(ctx.rays), _ptr(ctx.z), _ptr(ctx.noise), n, C.byref(cfg),
                                                _ptr(ctx.ws), ctx.ws_bytes, _ptr(wsb), need, C.byref(grads),
-                                               _ptr(ctx.ray_detach), arr, _stream_ptr()), "mnrf_train_pass_bwd")
-        return (None, None, None, None, None) + tuple(gts[k] for k in meta["keys"])
+                                               _ptr(ctx.ray_detach), arr, _ptr(ctx.depth), _ptr(grad_rays),
+                                               _stream_ptr()), "mnrf_train_pass_bwd")
+        return (None, grad_rays, None, None, None) + tuple(gts[k] for k in meta["keys"])
 
 
 def run_pass(module, rays, z, noise, ray_detach, *, compute_normal, white_back, noise_std, detach_mask, detach_normal):

@@ -241,7 +241,8 @@ int train_pass_fwd(const mnrf_field* f, const float* rays, const float* z, const
                    cudaStream_t st);
 int train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, const float* noise, int n,
                    const mnrf_train_cfg& cfg, const void* ws_fwd, void* ws_bwd, const mnrf_train_grads& g,
-                   const float* ray_detach_mirror, float* const* grad_tensors, cudaStream_t st);
+                   const float* ray_detach_mirror, float* const* grad_tensors, const float* depth, float* grad_rays,
+                   cudaStream_t st);
 void set_tc_trace(unsigned long long* buf, unsigned int cap);
 int launch_field_tc(const mnrf_field* f, const FieldIO& io, int precision /*1|3*/, cudaStream_t st);
 

@@ -710,6 +710,77 @@ __global__ void k_train_tangent_start(const float* __restrict__ DR, const float*
   for (int i = 0; i < 16; ++i) o[i] = make_float4(t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3]);
 }
 
+// Gradient w.r.t. the rays (origin, direction): the reference gets it from autograd when train.py:194-243 builds secondary
+// rays from x_surface / surface normals without detaching.  Per ray r (one block):
+//   d xyz_p = J_pe(x_p)^T dPE_p  [+ second-order term through the analytic normal: d g_x / d x = d J_pe^T / dx * g_pe]
+//   d o = sum_p d xyz_p + g_xs,   d d = sum_p z_p d xyz_p + depth * g_xs + J_dirpe(d)^T W_dir[:,256:]^T sum_s dD1pre
+__global__ void __launch_bounds__(64)
+k_train_ray_grad(const float* __restrict__ rays, const float* __restrict__ z, const float* __restrict__ PE,
+                 const float* __restrict__ dPE, const float* __restrict__ GPE, const float* __restrict__ GX,
+                 const float* __restrict__ DR, const float* __restrict__ rsum, const float* __restrict__ dirpe,
+                 const float* __restrict__ wt_dir, const float* __restrict__ g_xs, const float* __restrict__ depth, int S,
+                 int second_order, float* __restrict__ grad_rays) {
+  __shared__ float red[6][64];
+  __shared__ float ddir[IN_DIR];
+  const int r = blockIdx.x, t = threadIdx.x;
+  float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int s = t; s < S; s += 64) {
+    const size_t p = (size_t)r * S + s;
+    const float* e = PE + p * 64;
+    const float* dp = dPE + p * 64;
+    float dx[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float v = dp[c];
+      for (int f = 0; f < NFREQ_XYZ; ++f)
+        v += ldexpf(1.f, f) * (dp[3 + 6 * f + c] * e[6 + 6 * f + c] - dp[6 + 6 * f + c] * e[3 + 6 * f + c]);
+      dx[c] = v;
+    }
+    if (second_order) {
+      const float4 gx4 = *reinterpret_cast<const float4*>(GX + p * 4);
+      const float v[3] = {-gx4.x, -gx4.y, -gx4.z};
+      const float dy[3] = {DR[p * DR_STRIDE + 8], DR[p * DR_STRIDE + 9], DR[p * DR_STRIDE + 10]};
+      float dv[3];
+      normalize_bwd(v, dy, dv);
+      const float* gp = GPE + p * 64;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float h = 0.f;  // d g_x[c] / d x[c]
+        for (int f = 0; f < NFREQ_XYZ; ++f)
+          h -= ldexpf(1.f, 2 * f) * (gp[3 + 6 * f + c] * e[3 + 6 * f + c] + gp[6 + 6 * f + c] * e[6 + 6 * f + c]);
+        dx[c] += -dv[c] * h;  // dL/dg_x = -dv
+      }
+    }
+    const float zz = z[p];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { acc[c] += dx[c]; acc[3 + c] = fmaf(zz, dx[c], acc[3 + c]); }
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) red[i][t] = acc[i];
+  // d L / d embed(dir)[j] = sum_i W_dir[i][256 + j] * rsum[r][i]
+  if (t < IN_DIR) {
+    float v = 0.f;
+    for (int i = 0; i < WH; ++i) v = fmaf(wt_dir[(size_t)(W + t) * WH + i], rsum[(size_t)r * WH + i], v);
+    ddir[t] = v;
+  }
+  __syncthreads();
+  if (t < 6) {
+    float v = 0.f;
+    for (int i = 0; i < 64; ++i) v += red[t][i];
+    const int c = t % 3;
+    if (g_xs != nullptr) v += (t < 3 ? 1.f : depth[r]) * g_xs[(size_t)r * 3 + c];
+    if (t >= 3) {
+      const float* de = dirpe + (size_t)r * 64;
+      float w = ddir[c];
+      for (int f = 0; f < NFREQ_DIR; ++f)
+        w += ldexpf(1.f, f) * (ddir[3 + 6 * f + c] * de[6 + 6 * f + c] - ddir[6 + 6 * f + c] * de[3 + 6 * f + c]);
+      v += w;
+    }
+    grad_rays[(size_t)r * 8 + t] = v;
+  }
+  if (t >= 6 && t < 8) grad_rays[(size_t)r * 8 + t] = 0.f;
+}
+
 // R[r][c] = sum_s X[r*S + s][c]   (c < 128): per-ray sum of the dir layer's pre-activation gradient
 __global__ void __launch_bounds__(WH) k_train_sum_samples(const float* __restrict__ X, int S, float* __restrict__ R) {
   const int r = blockIdx.x, c = threadIdx.x;
@@ -777,7 +848,7 @@ FwdWs fwd_layout(int n, int S, int compute_normal) {
   return L;
 }
 struct BwdWs {
-  size_t dr, dd1, dn1, dm1, df, dz[2], t0, t[2], rsum, dirpe, total;
+  size_t dr, dd1, dn1, dm1, df, dz[2], t0, t[2], rsum, dirpe, dpe, total;
 };
 BwdWs bwd_layout(int n, int S, int compute_normal) {
   const size_t P = (size_t)n * S;
@@ -796,6 +867,7 @@ BwdWs bwd_layout(int n, int S, int compute_normal) {
   L.t[1] = compute_normal ? take(P * W) : 0;
   L.rsum = take((size_t)n * WH);
   L.dirpe = take((size_t)n * 64);
+  L.dpe = take(P * 64);
   L.total = o;
   return L;
 }
@@ -934,7 +1006,8 @@ int train_pass_fwd(const mnrf_field* f, const float* rays, const float* z, const
 
 int train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, const float* noise, int n,
                    const mnrf_train_cfg& cfg, const void* ws_fwd, void* ws_bwd, const mnrf_train_grads& g,
-                   const float* ray_detach_mirror, float* const* gt, cudaStream_t st) {
+                   const float* ray_detach_mirror, float* const* gt, const float* depth, float* grad_rays,
+                   cudaStream_t st) {
   const int S = cfg.S;
   const int P = n * S;
   const FwdWs L = fwd_layout(n, S, cfg.compute_normal);
@@ -1027,6 +1100,11 @@ int train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, const
     } else {
       if (gemm_tn(dZ, W, W, H[l - 1], W, W, gt[2 * l], W, 0, W, P, st)) return 1;
     }
+    if (grad_rays != nullptr && (l == 4 || l == 0)) {  // dL/dPE = dZ_5 W_5[:, :63] + dZ_1 W_1
+      GemmEpi e;
+      e.accumulate = l == 0;
+      if (gemm_nn(dZ, W, F + (l == 4 ? FL.tw_l5a : FL.tw_l1), 64, b + B.dpe, 64, P, 64, W, e, st)) return 1;
+    }
     if (l > 0) {  // dZ_{l-1} = (dZ_l W_l) * relu'(h_{l-1})
       GemmEpi e;
       e.act = 2; e.mask = H[l - 1]; e.ld_mask = W;
@@ -1076,6 +1154,14 @@ int train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, const
     // q8 = w_sigma * relu'(h8):  d w_sigma += sum_p t8
     if (colsum(Tprev, W, P, W, gt[T_SIGMA_W], st)) return 1;
   }
+  // 8. gradient w.r.t. the rays
+  if (grad_rays != nullptr) {
+    MNRF_REQUIRE(g.x_surface == nullptr || depth != nullptr, "train_pass_bwd: ray gradients need the depth output");
+    k_train_ray_grad<<<n, 64, 0, st>>>(rays, z, PE, b + B.dpe, cfg.compute_normal ? w + L.gpe : nullptr,
+                                       cfg.compute_normal ? w + L.gx : nullptr, b + B.dr, b + B.rsum, b + B.dirpe,
+                                       F + FL.wt_dir, g.x_surface, depth, S, normal_grads ? 1 : 0, grad_rays);
+    MNRF_LAUNCH_OK();
+  }
   return 0;
 }
 
@@ -1107,15 +1193,15 @@ int mnrf_train_pass_fwd(const mnrf_field* f, const float* rays, const float* z, 
 int mnrf_train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, const float* noise, int n,
                         const mnrf_train_cfg* cfg, const void* ws_fwd, int64_t ws_fwd_bytes, void* ws_bwd,
                         int64_t ws_bwd_bytes, const mnrf_train_grads* grads, const float* ray_detach_mirror,
-                        float* const* grad_tensors, void* stream) {
+                        float* const* grad_tensors, const float* depth, float* grad_rays, void* stream) {
   MNRF_REQUIRE(f && rays && z && cfg && ws_fwd && ws_bwd && grads && grad_tensors, "train_pass_bwd: null argument");
   MNRF_REQUIRE(n >= 0 && cfg->S >= 1 && (long long)n * cfg->S < (1ll << 31) / 256, "train_pass_bwd: bad sizes");
   MNRF_REQUIRE(ws_fwd_bytes >= train_fwd_workspace_bytes(n, cfg->S, cfg->compute_normal) &&
                    ws_bwd_bytes >= train_bwd_workspace_bytes(n, cfg->S, cfg->compute_normal),
                "train_pass_bwd: workspace too small");
   if (n == 0) return 0;
-  return train_pass_bwd(f, rays, z, noise, n, *cfg, ws_fwd, ws_bwd, *grads, ray_detach_mirror, grad_tensors,
-                        reinterpret_cast<cudaStream_t>(stream));
+  return train_pass_bwd(f, rays, z, noise, n, *cfg, ws_fwd, ws_bwd, *grads, ray_detach_mirror, grad_tensors, depth,
+                        grad_rays, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int mnrf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,

@@ -9,7 +9,7 @@ Differences from the reference that a caller can observe:
     is processed in sub-batches sized to bound scratch memory;
   * with autograd enabled and parameters that require grad, the level runs through the training path
     (``autograd.py`` / ``csrc/train.cu``: fp32 layer-by-layer kernels with a hand-written backward); gradients reach the
-    parameters of both models, not the rays;
+    parameters of both models and, when the rays require grad, the rays' origins and directions;
   * a batch of exactly one ray works (the reference's ``.squeeze()`` at rendering.py:365 breaks it);
   * ``view_dir`` (never passed by any reference caller) is not supported.
 """
@@ -162,6 +162,7 @@ def render_rays(models, embeddings, rays, N_samples=64, use_disp=False, perturb=
     rng (dict of explicit draws: perturb_u, noise_coarse, u_pdf, noise_fine -- for tests).  mirror_mask and the three
     detach_* flags only shape gradients: they are honoured by the training path and have no effect on forward values."""
     lib = _lib.load()
+    rays_in = rays
     rays = _check_rays(rays)
     dev = rays.device
     n = rays.shape[0]
@@ -185,7 +186,7 @@ def render_rays(models, embeddings, rays, N_samples=64, use_disp=False, perturb=
     params = list(models["coarse"].parameters()) if hasattr(models["coarse"], "parameters") else []
     if has_fine_model and hasattr(models["fine"], "parameters"):
         params += list(models["fine"].parameters())
-    needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    needs_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in params) or rays_in.requires_grad)
 
     coarse = packed_field(models["coarse"])
     fine = packed_field(models["fine"]) if (has_fine_model and not only_one_field) else None
@@ -215,7 +216,7 @@ def render_rays(models, embeddings, rays, N_samples=64, use_disp=False, perturb=
     noise_f = draw("noise_fine", (n, Sf), torch.randn) if (second_pass and noise_std != 0) else None
 
     if needs_grad:
-        return _render_level_train(lib, models, rays, Sc, Ni, second_pass, rerun, sig_only, use_disp, perturb, noise_std,
+        return _render_level_train(lib, models, rays_in.contiguous(), Sc, Ni, second_pass, rerun, sig_only, use_disp, perturb, noise_std,
                                    white_back, compute_normal, kwargs, perturb_u, noise_c, u_pdf, noise_f)
 
     new = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)

@@ -260,3 +260,40 @@ def test_training_loop_reduces_loss_and_repacks_weights():
     with torch.no_grad():
         after = render_rays(models, emb, rays, 64, False, 0, 0, 128, 32768, False, test_time=True, compute_normal=False)["rgb_fine"]
     assert float((after - before).abs().max()) > 1e-3
+
+
+@pytest.mark.parametrize("compute_normal", [True, False])
+def test_train_ray_gradients(compute_normal):
+    """Rays that require grad (secondary rays of the training recursion, train.py:194-243) receive dL/d[o, d]: through the
+    sample positions (PE Jacobian, incl. the second-order term of the analytic normals), the embedded direction and
+    x_surface.  near / far get zero."""
+    from mirror_nerf_b200.rendering import render_rays
+    from mirror_nerf_b200.synthetic import random_rays
+    from oracle import mirror_nerf_oracle as O
+    sds = _smooth_sds()
+    n = 16
+    rays = random_rays(n, seed=6)
+    rng = _rng(n)
+    args = (64, False, 1.0, 1.0, 128, 32768, False)
+    kw = dict(test_time=False, compute_normal=compute_normal)
+    params = {t: {k: v.clone().requires_grad_(True) for k, v in sd.items()} for t, sd in sds.items()}
+    rc = rays.clone().requires_grad_(True)
+    _loss(O.render_rays(params, rc, *args, rng=rng, **kw), rays[:, 3:6], 3).backward()
+    models, emb = _models(sds)
+    rg = rays.cuda().requires_grad_(True)
+    _loss(render_rays(models, emb, rg, *args, rng=rng, **kw), rays[:, 3:6].cuda(), 3).backward()
+    a, b = rg.grad.double().cpu(), rc.grad.double()
+    assert float(a[:, 6:].abs().max()) == 0.0
+    for name, sl in (("origin", slice(0, 3)), ("direction", slice(3, 6))):
+        x, y = a[:, sl].flatten(), b[:, sl].flatten()
+        cos = float((x * y).sum() / (x.norm() * y.norm()))
+        print(f"ray gradient ({name}, compute_normal={compute_normal}): cos {cos:.6f}, norm ratio {float(x.norm() / y.norm()):.5f}")
+        assert cos > 0.999 and abs(float(x.norm() / y.norm()) - 1) < 1e-2, (name, cos)
+    _grad_compare(models, params, cos_min=0.999, norm_tol=5e-3)
+    # frozen parameters, rays only
+    for m in models.values():
+        for p in m.parameters():
+            p.requires_grad_(False)
+    rg2 = rays.cuda().requires_grad_(True)
+    _loss(render_rays(models, emb, rg2, *args, rng=rng, **kw), rays[:, 3:6].cuda(), 3).backward()
+    assert torch.allclose(rg2.grad, rg.grad, rtol=1e-3, atol=1e-5 * float(rg.grad.abs().max()))
