@@ -297,3 +297,58 @@ def test_train_ray_gradients(compute_normal):
     rg2 = rays.cuda().requires_grad_(True)
     _loss(render_rays(models, emb, rg2, *args, rng=rng, **kw), rays[:, 3:6].cuda(), 3).backward()
     assert torch.allclose(rg2.grad, rg.grad, rtol=1e-3, atol=1e-5 * float(rg.grad.abs().max()))
+
+
+def _train_recursion(render_fn, rays, level=0, max_level=1):
+    """The reference's training recursion around render_rays (R/train.py:129-296, only_trace_rays_in_mirrors=True,
+    predicted mask, nothing detached) in plain torch ops -- device agnostic, used for the oracle and for our render_rays."""
+    r = render_fn(rays)
+    mask = r["mirror_mask_fine"].detach().clone()
+    mask[mask > 0.5] = 1
+    mask[mask < 0.5] = 0
+    if level >= max_level or not bool(mask.bool().any()):
+        return r
+    n = r["surface_normal_fine"]
+    n = n / torch.sqrt(torch.clamp((n ** 2).sum(-1, keepdim=True), min=torch.finfo(torch.float32).eps))
+    d = -rays[:, 3:6]
+    w = d / torch.sqrt(torch.clamp((d ** 2).sum(-1, keepdim=True), min=torch.finfo(torch.float32).eps))
+    cos = (w * n).sum(-1, keepdim=True)
+    refl = 2 * cos * n - w
+    sec = torch.cat([r["x_surface_fine"], refl, torch.full_like(rays[:, 6:7], 0.1), rays[:, 7:8]], -1)
+    sec = sec[mask.bool()]
+    child = _train_recursion(render_fn, sec, level + 1, max_level)
+    for typ in ("coarse", "fine"):
+        base = r[f"rgb_{typ}"]
+        part = base.clone().detach()
+        part[mask.bool()] = child[f"rgb_{typ}"]
+        m3 = mask.float().unsqueeze(-1)
+        r[f"rgb_{typ}_direct"] = base
+        r[f"rgb_{typ}"] = m3 * part + (1 - m3) * base
+    return r
+
+
+def test_training_recursion_gradients_through_secondary_rays():
+    """One bounce with train semantics: gradients reach the parameters through the child level's outputs AND through the
+    secondary rays' geometry (x_surface, surface normal) -- the reference's callers need nothing but render_rays."""
+    from mirror_nerf_b200.rendering import render_rays
+    from mirror_nerf_b200.synthetic import make_state_dict, random_rays
+    from oracle import mirror_nerf_oracle as O
+    # smooth density, sharp mirror head so that a good part of the rays bounces
+    sds = {"coarse": make_state_dict(21, 5.0, None, True, True, mirror_scale=100.0),
+           "fine": make_state_dict(22, 5.0, None, True, True, mirror_scale=100.0)}
+    n = 32
+    rays = random_rays(n, seed=13)
+    args = (64, False, 0.0, 0.0, 128, 32768, False)
+    kw = dict(test_time=False, compute_normal=False)
+    g = torch.Generator().manual_seed(4)
+    target = torch.rand(n, 3, generator=g)
+    params = {t: {k: v.clone().requires_grad_(True) for k, v in sd.items()} for t, sd in sds.items()}
+    want = _train_recursion(lambda r: O.render_rays(params, r, *args, **kw), rays)
+    assert "rgb_fine_direct" in want, "test scene must bounce"
+    (((want["rgb_fine"] - target) ** 2).mean() + ((want["rgb_coarse"] - target) ** 2).mean()).backward()
+    models, emb = _models(sds)
+    got = _train_recursion(lambda r: render_rays(models, emb, r, *args, **kw), rays.cuda())
+    (((got["rgb_fine"] - target.cuda()) ** 2).mean() + ((got["rgb_coarse"] - target.cuda()) ** 2).mean()).backward()
+    s = err_stats(got["rgb_fine"].detach().cpu(), want["rgb_fine"].detach())
+    assert s["median"] <= 1e-4 and s["frac"] <= 0.1, fmt_stats("rgb_fine (1 bounce)", s)
+    _grad_compare(models, params, cos_min=None, norm_tol=None, whole_cos_min=0.995)
