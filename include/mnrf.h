@@ -185,7 +185,7 @@ int mnrf_render_level_host(const mnrf_field* coarse, const mnrf_field* fine, con
  * -> compositor) that keeps every activation the backward needs in a caller-provided workspace, and the backward
  * that turns the gradients of the pass outputs into gradients of the 32 parameter tensors -- including the second-order
  * path through the analytic normal  n = normalize(-d sigma/d xyz)  (mirror_nerf.py:136-146, create_graph=True in
- * utils/func.py:10-25).  All GEMMs are fp32 CUDA-core kernels (train.cu).  Optionally also the gradient w.r.t. the rays'
+ * utils/func.py:10-25).  The GEMMs run on the tensor cores (tcgen05 kind::tf32, 3x split = fp32-grade; train_tc.cu).  Optionally also the gradient w.r.t. the rays'
  * origin and direction (train.py:194-243 builds secondary rays from x_surface / normals without detaching).  z carries no
  * gradient (z_fine is detached by the reference, rendering.py:335,353; near/far are constants). */
 typedef struct mnrf_train_cfg {
@@ -233,6 +233,10 @@ int mnrf_train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, 
                         const mnrf_train_cfg* cfg, const void* ws_fwd, int64_t ws_fwd_bytes, void* ws_bwd,
                         int64_t ws_bwd_bytes, const mnrf_train_grads* grads, const float* ray_detach_mirror,
                         float* const* grad_tensors, const float* depth, float* grad_rays, void* stream);
+
+/* GEMM engine of the training path: 1 (default) = tcgen05 tf32 3x-split kernels (train_tc.cu), 0 = fp32 CUDA-core kernels
+ * (verification twin).  The environment variable MNRF_TRAIN_GEMM=simt selects 0 at first use. */
+int mnrf_train_set_gemm(int tensor_cores);
 
 /* One torch.optim.Adam step (the reference's optimizer: R/utils/__init__.py:47-58, lr 5e-4, eps 1e-8, L2 weight decay) on flat
  * fp32 buffers of n elements: g = grads*grad_scale + weight_decay*p; m,v updated in place; p -= lr/(1-b1^t) * m/(sqrt(v)/

@@ -93,6 +93,7 @@ _SIGS = {
     "mnrf_train_pass_bwd": (c_int, [C.c_void_p, c_float_p, c_float_p, c_float_p, c_int, C.POINTER(TrainCfg), C.c_void_p,
                                     C.c_int64, C.c_void_p, C.c_int64, C.POINTER(TrainGrads), c_float_p,
                                     C.POINTER(C.c_void_p), c_float_p, c_float_p, C.c_void_p]),
+    "mnrf_train_set_gemm": (c_int, [c_int]),
     "mnrf_adam_step": (c_int, [c_float_p, c_float_p, c_float_p, c_float_p, C.c_int64, C.c_float, C.c_float, C.c_float,
                                C.c_float, C.c_float, c_int, C.c_float, C.c_void_p]),
     "mnrf_axpy": (c_int, [c_float_p, c_float_p, C.c_int64, C.c_float, C.c_void_p]),

@@ -127,10 +127,12 @@ int mnrf_field_create(mnrf_field** out, const float* const* tensors, void* strea
   f->L = make_f32_layout();
   f->f32 = nullptr;
   f->tc = nullptr;
+  f->t32 = nullptr;
   if (cudaMalloc(&f->f32, sizeof(float) * f->L.total) != cudaSuccess ||
-      cudaMalloc(&f->tc, TC_TOTAL_BYTES) != cudaSuccess) {
+      cudaMalloc(&f->tc, TC_TOTAL_BYTES) != cudaSuccess || cudaMalloc(&f->t32, T32_TOTAL_BYTES) != cudaSuccess) {
     set_error("field_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (f->f32) cudaFree(f->f32);
+    if (f->tc) cudaFree(f->tc);
     delete f;
     return 1;
   }
@@ -150,6 +152,7 @@ void mnrf_field_destroy(mnrf_field* f) {
   if (f == nullptr) return;
   if (f->f32) cudaFree(f->f32);
   if (f->tc) cudaFree(f->tc);
+  if (f->t32) cudaFree(f->t32);
   delete f;
 }
 int mnrf_field_has_normal(const mnrf_field* f) { return f ? f->has_normal : 0; }

@@ -54,6 +54,21 @@ __host__ __device__ constexpr int tc_step_offset(int s) {
 }
 constexpr int TC_TOTAL_BYTES = tc_step_offset(TC_NUM_STEPS);
 
+// tf32 hi/lo blobs of the training GEMMs (train_tc.cu): steps 0..19 as above plus
+//   20: normal_net.0 (N128,K256)   21: dir layer^T, feature part (N256,K128)   22: final^T (N256,K256)
+//   23: normal_net.0^T (N256,K128) 24: is_mirror_net.0^T (N256,K128)
+// One blob = hi or lo part of one K16 chunk: N rows x 16 floats (N*64 bytes) as the shared-memory image of a tcgen05 K-major
+// no-swizzle B operand (core matrix = 8 rows x 4 tf32).  Order inside a step: [chunk kc][hi, lo].
+constexpr int T32_NUM_STEPS = 25;
+__host__ __device__ constexpr int t32_step_n(int s) { return s < TC_NUM_STEPS ? tc_step_n(s) : (s == 20 ? 128 : 256); }
+__host__ __device__ constexpr int t32_step_k(int s) { return s < TC_NUM_STEPS ? tc_step_k(s) : ((s == 20 || s == 22) ? 256 : 128); }
+__host__ __device__ constexpr long long t32_step_offset(int s) {
+  long long o = 0;
+  for (int i = 0; i < s; ++i) o += (long long)t32_step_n(i) * t32_step_k(i) * 8;
+  return o;
+}
+constexpr long long T32_TOTAL_BYTES = t32_step_offset(T32_NUM_STEPS);
+
 // ------------------------------------------------------------------------------------------------
 // fp32 section layout (float offsets inside mnrf_field::f32)
 // ------------------------------------------------------------------------------------------------
@@ -147,6 +162,7 @@ struct mnrf_field {
   int has_mirror;
   float* f32;        // device, mnrf::F32Layout
   uint8_t* tc;       // device, TC_TOTAL_BYTES of fp16 hi/lo blobs
+  uint8_t* t32;      // device, T32_TOTAL_BYTES of tf32 hi/lo blobs (training GEMMs)
   mnrf::F32Layout L;
 };
 
@@ -232,6 +248,26 @@ int launch_blend(const float* base, const float* mask, const float* child_rgb, c
                  const int* index, int n, float* rgb_out, float* rgb_reflect, float* depth_reflect, cudaStream_t st);
 
 int launch_field_fp32(const mnrf_field* f, const FieldIO& io, cudaStream_t st);
+
+// epilogue of the training GEMMs:  v = acc [+ C] [+ bias[col]] [+ rowbias[row / rb_div][col]] [+ rvec[row] * cvec[col]];  act(v)
+struct GemmEpi {
+  const float* bias = nullptr;
+  const float* rowbias = nullptr;
+  int rb_div = 1, ld_rb = 0;
+  const float* rvec = nullptr;
+  int ld_rvec = 0;
+  const float* cvec = nullptr;
+  const float* mask = nullptr;  // act == 2: keep v where mask[row][col] > 0 (relu' of a saved activation), else 0
+  int ld_mask = 0;
+  int act = 0;                  // 0 none | 1 relu | 2 mask | 3 leaky relu (0.01)
+  int accumulate = 0;
+};
+// C[M,N] = epi([A0 | A1] * B_step^T) on the tensor cores (3x tf32 split); A0 supplies the first K0 reduction columns
+int gemm_nn_tc(const mnrf_field* f, int step, const float* A0, int lda0, int K0, const float* A1, int lda1, float* C,
+               int ldc, int M, const GemmEpi& e, cudaStream_t st);
+// Wg[NA rows][col0 + (0..valid)] += A[P,NA]^T B[P,NB] on the tensor cores (3x tf32 split), NA in {128,256}, NB in {64,128,256}
+int gemm_tn_tc(const float* A, int lda, int NA, const float* B, int ldb, int NB, float* Wg, int ldw, int col0, int valid,
+               int P, cudaStream_t st);
 
 // training path (train.cu): one field + compositor pass with saved activations, and its backward
 int64_t train_fwd_workspace_bytes(int n, int S, int compute_normal);

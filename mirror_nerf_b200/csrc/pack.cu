@@ -151,6 +151,40 @@ __global__ void k_pack_tc(TcSrc src, const float* __restrict__ inv_scale, uint8_
   }
 }
 
+// ---- tf32 blobs of the training GEMMs (common.cuh T32_*) ------------------------------------------------------------
+struct T32Src {
+  TcSrc base;
+  const float *w_n0, *w_dir, *w_final, *w_m0;
+};
+__device__ __forceinline__ float t32_value(const T32Src& src, int s, int n, int k) {
+  if (s < TC_NUM_STEPS) return tc_src_value(src.base, s, n, k);
+  if (s == 20) return src.w_n0 != nullptr ? src.w_n0[n * W + k] : 0.f;             // normal_net.0:      B[n][k] = W[n][k]
+  if (s == 21) return src.w_dir[k * (W + IN_DIR) + n];                              // dir layer^T:       B[n=f][k=j] = W[j][f]
+  if (s == 22) return src.w_final[k * W + n];                                       // final^T
+  if (s == 23) return src.w_n0 != nullptr ? src.w_n0[k * W + n] : 0.f;              // normal_net.0^T
+  return src.w_m0 != nullptr ? src.w_m0[k * W + n] : 0.f;                           // is_mirror_net.0^T
+}
+__global__ void k_pack_t32(T32Src src, uint8_t* __restrict__ t32) {
+  const int s = blockIdx.y;
+  const int N = t32_step_n(s), K = t32_step_k(s);
+  uint8_t* base = t32 + t32_step_offset(s);
+  const int blob = N * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N * K; i += gridDim.x * blockDim.x) {
+    const int n = i / K, k = i % K;
+    const float v = t32_value(src, s, n, k);
+    uint32_t hi, lo;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
+    const float r = v - __uint_as_float(hi);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+    const int kc = k >> 4, kk = k & 15;
+    // K-major no-swizzle core matrices of 8 rows x 4 tf32: 8-row groups 128 B apart, K-groups N*16 B apart
+    const int off = (kk >> 2) * (N * 16) + (n >> 3) * 128 + (n & 7) * 16 + (kk & 3) * 4;
+    uint8_t* chunk = base + (size_t)kc * 2 * blob;
+    *reinterpret_cast<uint32_t*>(chunk + off) = hi;
+    *reinterpret_cast<uint32_t*>(chunk + blob + off) = lo;
+  }
+}
+
 static int copy_to(const float* src, float* dst, int n, cudaStream_t st) {
   if (src == nullptr) {
     k_fill<<<(n + 255) / 256, 256, 0, st>>>(dst, 0.f, n);
@@ -234,6 +268,11 @@ int pack_field(mnrf_field* f, const float* const* t, cudaStream_t st) {
   k_scales<<<1, 32, 0, st>>>(absmax, d + L.inv_scale);
   MNRF_LAUNCH_OK();
   k_pack_tc<<<dim3(64, TC_NUM_STEPS), 256, 0, st>>>(src, d + L.inv_scale, f->tc);
+  MNRF_LAUNCH_OK();
+  T32Src s32;
+  s32.base = src;
+  s32.w_n0 = t[T_N0_W]; s32.w_dir = t[T_DIR_W]; s32.w_final = t[T_FINAL_W]; s32.w_m0 = t[T_M0_W];
+  k_pack_t32<<<dim3(64, T32_NUM_STEPS), 256, 0, st>>>(s32, f->t32);
   MNRF_LAUNCH_OK();
   return 0;
 }

@@ -13,6 +13,8 @@
 // relu'' = 0: with t0 = J_pe dL/dg_x,  t_k = (t_{k-1} W_k^T) * relu'(z_k)  [a second "tangent" forward pass],
 //   dW_k += q_k^T t_{k-1},   d w_sigma += sum_p t8.
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -21,20 +23,6 @@ namespace {
 
 constexpr int GB_M = 128;  // rows of C per CTA
 constexpr int GB_K = 16;   // reduction slab
-
-// epilogue of k_gemm_nn:  v = acc [+ C] [+ bias[col]] [+ rowbias[row / rb_div][col]] [+ rvec[row] * cvec[col]];  act(v)
-struct GemmEpi {
-  const float* bias = nullptr;
-  const float* rowbias = nullptr;
-  int rb_div = 1, ld_rb = 0;
-  const float* rvec = nullptr;
-  int ld_rvec = 0;
-  const float* cvec = nullptr;
-  const float* mask = nullptr;  // act == 2: keep v where mask[row][col] > 0 (relu' of a saved activation), else 0
-  int ld_mask = 0;
-  int act = 0;                  // 0 none | 1 relu | 2 mask | 3 leaky relu (0.01)
-  int accumulate = 0;
-};
 
 __device__ __forceinline__ float apply_act(float v, int act, float m) {
   if (act == 1) return fmaxf(v, 0.f);
@@ -912,6 +900,60 @@ int colsum(const float* X, int ld, int P, int N, float* out, cudaStream_t st) {
   return 0;
 }
 
+// ---- GEMM engine: tcgen05 (train_tc.cu) by default; MNRF_TRAIN_GEMM=simt or mnrf_train_set_gemm(0) selects the fp32 CUDA-core
+// kernels above (verification twin).
+int g_engine = -1;
+bool use_tc() {
+  if (g_engine < 0) {
+    const char* e = getenv("MNRF_TRAIN_GEMM");
+    g_engine = (e != nullptr && strcmp(e, "simt") == 0) ? 0 : 1;
+  }
+  return g_engine != 0;
+}
+
+inline int chain_step(int l) { return l >= 5 ? 18 - l : (l == 4 ? 14 : 19 - l); }  // W_l^T (h part for l == 4); PE part of l == 4: 15
+
+// C[P, N(step)] = epi([A0 | A1] * B_step^T): B_step is the weight matrix of GEMM step `step` (common.cuh T32 numbering)
+int gemm_w(const mnrf_field* f, int step, const float* A0, int lda0, int K0, const float* A1, int lda1, float* C, int ldc,
+           int P, const GemmEpi& e, cudaStream_t st) {
+  if (use_tc()) return gemm_nn_tc(f, step, A0, lda0, K0, A1, lda1, C, ldc, P, e, st);
+  const float* F = f->f32;
+  const F32Layout& L = f->L;
+  const int N = t32_step_n(step), K = t32_step_k(step);
+  const float* B0 = nullptr;
+  const float* B1 = nullptr;  // second K segment (only the skip layer has one)
+  int ldb = W;
+  if (step < 8) {
+    B0 = F + L.wt_trunk[step];
+    if (step == 4) B1 = F + L.wt_trunk[4] + (size_t)IN_XYZ * W;
+  } else if (step == 8) B0 = F + L.wt_final;
+  else if (step == 9) { B0 = F + L.wt_m0; ldb = WH; }
+  else if (step == 10) { B0 = F + L.wt_dir; ldb = WH; }
+  else if (step == 20) { B0 = F + L.wt_n0; ldb = WH; }
+  else if (step == 14) B0 = F + L.tw_l5b;
+  else if (step == 15) { B0 = F + L.tw_l5a; ldb = 64; }
+  else if (step == 19) { B0 = F + L.tw_l1; ldb = 64; }
+  else if (step < TC_NUM_STEPS) B0 = F + L.w_trunk[tc_step_layer(step)];
+  else if (step == 21) B0 = F + L.tw_dira;
+  else if (step == 22) B0 = F + L.tw_final;
+  else if (step == 23) B0 = F + L.tw_n0;
+  else B0 = F + L.tw_m0;
+  if (K0 == K) return gemm_nn(A0, lda0, B0, ldb, C, ldc, P, N, K, e, st);
+  MNRF_REQUIRE(B1 != nullptr && A1 != nullptr, "train gemm_w: step %d has no second K segment", step);
+  GemmEpi e0;
+  e0.accumulate = e.accumulate;
+  if (gemm_nn(A0, lda0, B0, ldb, C, ldc, P, N, K0, e0, st)) return 1;
+  GemmEpi e1 = e;
+  e1.accumulate = 1;
+  return gemm_nn(A1, lda1, B1, ldb, C, ldc, P, N, K - K0, e1, st);
+}
+
+int gemm_g(const float* A, int lda, int NA, const float* B, int ldb, int NB, float* Wg, int ldw, int col0, int valid, int P,
+           cudaStream_t st) {
+  if (use_tc()) return gemm_tn_tc(A, lda, NA, B, ldb, NB, Wg, ldw, col0, valid, P, st);
+  return gemm_tn(A, lda, NA, B, ldb, NB, Wg, ldw, col0, valid, P, st);
+}
+
 }  // namespace
 
 int64_t train_fwd_workspace_bytes(int n, int S, int compute_normal) {
@@ -935,42 +977,38 @@ int train_pass_fwd(const mnrf_field* f, const float* rays, const float* z, const
 
   k_train_pe<<<(P + 127) / 128, 128, 0, st>>>(rays, z, P, S, PE);
   MNRF_LAUNCH_OK();
-  // trunk (mirror_nerf.py:189-197): Wt[k][n] transposed copies are the B operands
+  // trunk (mirror_nerf.py:189-197); the skip layer reads [pe | h4] as two K segments (PE column 63 is zero)
   for (int l = 0; l < 8; ++l) {
     GemmEpi e;
     e.bias = F + FL.b_trunk[l];
     e.act = 1;
     if (l == 0) {
-      if (gemm_nn(PE, 64, F + FL.wt_trunk[0], W, H[0], W, P, W, 64, e, st)) return 1;
+      if (gemm_w(f, 0, PE, 64, 64, nullptr, 0, H[0], W, P, e, st)) return 1;
     } else if (l == 4) {
-      // skip connection: z5 = [pe | h4] W5^T  = pe * Wt5[0:63] + h4 * Wt5[63:319]   (PE column 63 is zero)
-      GemmEpi e0;
-      if (gemm_nn(PE, 64, F + FL.wt_trunk[4], W, H[4], W, P, W, 64, e0, st)) return 1;
-      e.accumulate = 1;
-      if (gemm_nn(H[3], W, F + FL.wt_trunk[4] + (size_t)IN_XYZ * W, W, H[4], W, P, W, W, e, st)) return 1;
+      if (gemm_w(f, 4, PE, 64, 64, H[3], W, H[4], W, P, e, st)) return 1;
     } else {
-      if (gemm_nn(H[l - 1], W, F + FL.wt_trunk[l], W, H[l], W, P, W, W, e, st)) return 1;
+      if (gemm_w(f, l, H[l - 1], W, W, nullptr, 0, H[l], W, P, e, st)) return 1;
     }
   }
   // colour branch (mirror_nerf.py:199-204)
   {
     GemmEpi e;
     e.bias = F + FL.b_final;
-    if (gemm_nn(H[7], W, F + FL.wt_final, W, w + L.f, W, P, W, W, e, st)) return 1;
+    if (gemm_w(f, 8, H[7], W, W, nullptr, 0, w + L.f, W, P, e, st)) return 1;
     if (launch_dirbias(f, rays, n, 8, 0, w + L.dirbias, st)) return 1;  // b_dir + W_dir[:,256:] embed(d) per ray
     GemmEpi e2;
     e2.rowbias = w + L.dirbias; e2.rb_div = S; e2.ld_rb = WH; e2.act = 1;
-    if (gemm_nn(w + L.f, W, F + FL.wt_dir, WH, w + L.d1, WH, P, WH, W, e2, st)) return 1;
+    if (gemm_w(f, 10, w + L.f, W, W, nullptr, 0, w + L.d1, WH, P, e2, st)) return 1;
   }
   if (f->has_normal) {  // normal_net.0 (no activation, mirror_nerf.py:85-88)
     GemmEpi e;
     e.bias = F + FL.b_n0;
-    if (gemm_nn(H[7], W, F + FL.wt_n0, WH, w + L.n1, WH, P, WH, W, e, st)) return 1;
+    if (gemm_w(f, 20, H[7], W, W, nullptr, 0, w + L.n1, WH, P, e, st)) return 1;
   }
   if (f->has_mirror) {  // is_mirror_net.0 + LeakyReLU (mirror_nerf.py:94-96)
     GemmEpi e;
     e.bias = F + FL.b_m0; e.act = 3;
-    if (gemm_nn(H[7], W, F + FL.wt_m0, WH, w + L.m1, WH, P, WH, W, e, st)) return 1;
+    if (gemm_w(f, 9, H[7], W, W, nullptr, 0, w + L.m1, WH, P, e, st)) return 1;
   }
   HeadW hw{F + FL.w_sigma, F + FL.b_sigma, F + FL.w_rgb, F + FL.b_rgb, F + FL.w_n1, F + FL.b_n1, F + FL.w_m2, F + FL.b_m2};
   k_train_heads_fwd<<<148 * 4, 256, 0, st>>>(H[7], w + L.d1, f->has_normal ? w + L.n1 : nullptr,
@@ -987,14 +1025,13 @@ int train_pass_fwd(const mnrf_field* f, const float* rays, const float* z, const
     for (int l = 7; l >= 1; --l) {  // q_{l-1} = (q_l W_l) * relu'(h_{l-1});  W_l = layer l+1 in 1-based naming
       GemmEpi e;
       e.act = 2; e.mask = H[l - 1]; e.ld_mask = W;
-      const float* Bw = (l == 4) ? F + FL.tw_l5b : F + FL.w_trunk[l];
-      if (gemm_nn(Q[l], W, Bw, W, Q[l - 1], W, P, W, W, e, st)) return 1;
+      if (gemm_w(f, chain_step(l), Q[l], W, W, nullptr, 0, Q[l - 1], W, P, e, st)) return 1;
     }
     GemmEpi e0;
-    if (gemm_nn(Q[0], W, F + FL.tw_l1, 64, w + L.gpe, 64, P, 64, W, e0, st)) return 1;
+    if (gemm_w(f, 19, Q[0], W, W, nullptr, 0, w + L.gpe, 64, P, e0, st)) return 1;
     GemmEpi e1;
     e1.accumulate = 1;
-    if (gemm_nn(Q[4], W, F + FL.tw_l5a, 64, w + L.gpe, 64, P, 64, W, e1, st)) return 1;
+    if (gemm_w(f, 15, Q[4], W, W, nullptr, 0, w + L.gpe, 64, P, e1, st)) return 1;
     k_train_normal<<<(P + 127) / 128, 128, 0, st>>>(w + L.gpe, PE, P, w + L.gx, w + L.nrm);
     MNRF_LAUNCH_OK();
     normal = w + L.nrm;
@@ -1041,26 +1078,26 @@ int train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, const
 
   // 3. colour branch: dir layer and final linear
   if (colsum(b + B.dd1, WH, P, WH, gt[T_DIR_B], st)) return 1;
-  if (gemm_tn(b + B.dd1, WH, WH, w + L.f, W, W, gt[T_DIR_W], W + IN_DIR, 0, W, P, st)) return 1;
+  if (gemm_g(b + B.dd1, WH, WH, w + L.f, W, W, gt[T_DIR_W], W + IN_DIR, 0, W, P, st)) return 1;
   k_train_sum_samples<<<n, WH, 0, st>>>(b + B.dd1, S, b + B.rsum);
   MNRF_LAUNCH_OK();
   k_train_dir_pe<<<(n + 127) / 128, 128, 0, st>>>(rays, n, b + B.dirpe);
   MNRF_LAUNCH_OK();
-  if (gemm_tn(b + B.rsum, WH, WH, b + B.dirpe, 64, 64, gt[T_DIR_W], W + IN_DIR, W, IN_DIR, n, st)) return 1;
+  if (gemm_g(b + B.rsum, WH, WH, b + B.dirpe, 64, 64, gt[T_DIR_W], W + IN_DIR, W, IN_DIR, n, st)) return 1;
   {
     GemmEpi e;  // dF = dD1pre * W_dir[:, :256]
-    if (gemm_nn(b + B.dd1, WH, F + FL.tw_dira, W, b + B.df, W, P, W, WH, e, st)) return 1;
+    if (gemm_w(f, 21, b + B.dd1, WH, WH, nullptr, 0, b + B.df, W, P, e, st)) return 1;
   }
   if (colsum(b + B.df, W, P, W, gt[T_FINAL_B], st)) return 1;
-  if (gemm_tn(b + B.df, W, W, H[7], W, W, gt[T_FINAL_W], W, 0, W, P, st)) return 1;
+  if (gemm_g(b + B.df, W, W, H[7], W, W, gt[T_FINAL_W], W, 0, W, P, st)) return 1;
   // 4. normal / mirror head first layers
   if (hn) {
     if (colsum(b + B.dn1, WH, P, WH, gt[T_N0_B], st)) return 1;
-    if (gemm_tn(b + B.dn1, WH, WH, H[7], W, W, gt[T_N0_W], W, 0, W, P, st)) return 1;
+    if (gemm_g(b + B.dn1, WH, WH, H[7], W, W, gt[T_N0_W], W, 0, W, P, st)) return 1;
   }
   if (hm) {
     if (colsum(b + B.dm1, WH, P, WH, gt[T_M0_B], st)) return 1;
-    if (gemm_tn(b + B.dm1, WH, WH, H[7], W, W, gt[T_M0_W], W, 0, W, P, st)) return 1;
+    if (gemm_g(b + B.dm1, WH, WH, H[7], W, W, gt[T_M0_W], W, 0, W, P, st)) return 1;
   }
   // 5. dH8 = dF W_final + [dN1 W_n0] + [dM1 W_m0] + d sigma (x) w_sigma, then * relu'(h8) -> dZ8
   const bool use_n = hn && !cfg.detach_density_for_normal_loss;
@@ -1084,32 +1121,31 @@ int train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, const
       e.accumulate = t > 0;
       return e;
     };
-    if (gemm_nn(b + B.df, W, F + FL.tw_final, W, dZ, W, P, W, W, epi_for(term++), st)) return 1;
-    if (use_n) { if (gemm_nn(b + B.dn1, WH, F + FL.tw_n0, W, dZ, W, P, W, WH, epi_for(term++), st)) return 1; }
-    if (use_m) { if (gemm_nn(b + B.dm1, WH, F + FL.tw_m0, W, dZ, W, P, W, WH, epi_for(term++), st)) return 1; }
+    if (gemm_w(f, 22, b + B.df, W, W, nullptr, 0, dZ, W, P, epi_for(term++), st)) return 1;
+    if (use_n) { if (gemm_w(f, 23, b + B.dn1, WH, WH, nullptr, 0, dZ, W, P, epi_for(term++), st)) return 1; }
+    if (use_m) { if (gemm_w(f, 24, b + B.dm1, WH, WH, nullptr, 0, dZ, W, P, epi_for(term++), st)) return 1; }
   }
   // 6. trunk backward
   for (int l = 7; l >= 0; --l) {
     // bias and weight gradients of layer l (0-based) from dZ = dL/dz_l
     if (colsum(dZ, W, P, W, gt[2 * l + 1], st)) return 1;
     if (l == 0) {
-      if (gemm_tn(dZ, W, W, PE, 64, 64, gt[0], IN_XYZ, 0, IN_XYZ, P, st)) return 1;
+      if (gemm_g(dZ, W, W, PE, 64, 64, gt[0], IN_XYZ, 0, IN_XYZ, P, st)) return 1;
     } else if (l == 4) {
-      if (gemm_tn(dZ, W, W, PE, 64, 64, gt[8], IN_XYZ + W, 0, IN_XYZ, P, st)) return 1;
-      if (gemm_tn(dZ, W, W, H[3], W, W, gt[8], IN_XYZ + W, IN_XYZ, W, P, st)) return 1;
+      if (gemm_g(dZ, W, W, PE, 64, 64, gt[8], IN_XYZ + W, 0, IN_XYZ, P, st)) return 1;
+      if (gemm_g(dZ, W, W, H[3], W, W, gt[8], IN_XYZ + W, IN_XYZ, W, P, st)) return 1;
     } else {
-      if (gemm_tn(dZ, W, W, H[l - 1], W, W, gt[2 * l], W, 0, W, P, st)) return 1;
+      if (gemm_g(dZ, W, W, H[l - 1], W, W, gt[2 * l], W, 0, W, P, st)) return 1;
     }
     if (grad_rays != nullptr && (l == 4 || l == 0)) {  // dL/dPE = dZ_5 W_5[:, :63] + dZ_1 W_1
       GemmEpi e;
       e.accumulate = l == 0;
-      if (gemm_nn(dZ, W, F + (l == 4 ? FL.tw_l5a : FL.tw_l1), 64, b + B.dpe, 64, P, 64, W, e, st)) return 1;
+      if (gemm_w(f, l == 4 ? 15 : 19, dZ, W, W, nullptr, 0, b + B.dpe, 64, P, e, st)) return 1;
     }
     if (l > 0) {  // dZ_{l-1} = (dZ_l W_l) * relu'(h_{l-1})
       GemmEpi e;
       e.act = 2; e.mask = H[l - 1]; e.ld_mask = W;
-      const float* Bw = (l == 4) ? F + FL.tw_l5b : F + FL.w_trunk[l];
-      if (gemm_nn(dZ, W, Bw, W, dZn, W, P, W, W, e, st)) return 1;
+      if (gemm_w(f, chain_step(l), dZ, W, W, nullptr, 0, dZn, W, P, e, st)) return 1;
       float* t = dZ; dZ = dZn; dZn = t;
     }
   }
@@ -1128,25 +1164,22 @@ int train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, const
     for (int l = 0; l < 8; ++l) {
       // dW_l += q_l^T t_{l-1}
       if (l == 0) {
-        if (gemm_tn(Q[0], W, W, T0, 64, 64, gt[0], IN_XYZ, 0, IN_XYZ, P, st)) return 1;
+        if (gemm_g(Q[0], W, W, T0, 64, 64, gt[0], IN_XYZ, 0, IN_XYZ, P, st)) return 1;
       } else if (l == 4) {
-        if (gemm_tn(Q[4], W, W, T0, 64, 64, gt[8], IN_XYZ + W, 0, IN_XYZ, P, st)) return 1;
-        if (gemm_tn(Q[4], W, W, Tprev, W, W, gt[8], IN_XYZ + W, IN_XYZ, W, P, st)) return 1;
+        if (gemm_g(Q[4], W, W, T0, 64, 64, gt[8], IN_XYZ + W, 0, IN_XYZ, P, st)) return 1;
+        if (gemm_g(Q[4], W, W, Tprev, W, W, gt[8], IN_XYZ + W, IN_XYZ, W, P, st)) return 1;
       } else {
-        if (gemm_tn(Q[l], W, W, Tprev, W, W, gt[2 * l], W, 0, W, P, st)) return 1;
+        if (gemm_g(Q[l], W, W, Tprev, W, W, gt[2 * l], W, 0, W, P, st)) return 1;
       }
       // t_l = (t_{l-1} W_l^T) * relu'(h_l)
       GemmEpi e;
       e.act = 2; e.mask = H[l]; e.ld_mask = W;
       if (l == 0) {
-        if (gemm_nn(T0, 64, F + FL.wt_trunk[0], W, Tc, W, P, W, 64, e, st)) return 1;
+        if (gemm_w(f, 0, T0, 64, 64, nullptr, 0, Tc, W, P, e, st)) return 1;
       } else if (l == 4) {
-        GemmEpi e0;
-        if (gemm_nn(T0, 64, F + FL.wt_trunk[4], W, Tc, W, P, W, 64, e0, st)) return 1;
-        e.accumulate = 1;
-        if (gemm_nn(Tprev, W, F + FL.wt_trunk[4] + (size_t)IN_XYZ * W, W, Tc, W, P, W, W, e, st)) return 1;
+        if (gemm_w(f, 4, T0, 64, 64, Tprev, W, Tc, W, P, e, st)) return 1;
       } else {
-        if (gemm_nn(Tprev, W, F + FL.wt_trunk[l], W, Tc, W, P, W, W, e, st)) return 1;
+        if (gemm_w(f, l, Tprev, W, W, nullptr, 0, Tc, W, P, e, st)) return 1;
       }
       Tprev = Tc;
       float* t = Tc; Tc = Tn; Tn = t;
@@ -1202,6 +1235,11 @@ int mnrf_train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, 
   if (n == 0) return 0;
   return train_pass_bwd(f, rays, z, noise, n, *cfg, ws_fwd, ws_bwd, *grads, ray_detach_mirror, grad_tensors, depth,
                         grad_rays, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int mnrf_train_set_gemm(int tensor_cores) {
+  g_engine = tensor_cores ? 1 : 0;
+  return 0;
 }
 
 int mnrf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,

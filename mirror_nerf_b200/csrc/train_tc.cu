@@ -1,0 +1,518 @@
+// Tensor-core GEMMs of the training path (train.cu): tcgen05.mma kind::tf32 with 3x split operands (x = hi + lo, both tf32;
+// hi*hi + lo*hi + hi*lo accumulated in fp32 TMEM) -- fp32-grade products without any scaling, because tf32 keeps the fp32
+// exponent range (gradients span many decades; the fp16 split of field_tc.cu would need per-row scales).
+//
+// k_gemm_tc_nn   C[M,N] = epi([A0 | A1][M,K] * W^T)      activations x packed weight blobs (pack.cu k_pack_t32)
+//   persistent CTA per SM, 128-row tiles, 18 warps:
+//     warp 0       B producer: cp.async.bulk of the pre-packed tf32 hi|lo blob of a K16 chunk into the stage
+//     warp 1       MMA issuer (one elected thread): 6 MMAs (2 K8 steps x 3 passes) per stage, accumulators double-buffered in TMEM
+//     warps 2..9   A loaders: global fp32 -> registers (4 chunks in flight per thread) -> tf32 hi/lo -> UMMA K-major core matrices
+//     warps 10..17 epilogue: tcgen05.ld -> bias / per-ray term / rank-1 term / ReLU / ReLU-mask / accumulate -> global fp32
+// k_gemm_tc_tn   dW[NA,NB] += A[P,NA]^T B[P,NB]          weight gradients: the reduction runs over the points
+//     both operands are transposed on the fly by the loaders (a core-matrix row = one feature x 4 consecutive points), the
+//     whole dW tile (<= 256 x 256) lives in TMEM for the CTA's slab of points and is flushed once with red.global.add.
+//
+// Per-unit cost: a 128 x 256 x 256 layer tile = 32 K8 steps x 3 passes x 128 cycles = 12.3k tensor cycles against
+// 128 KB read + 128 KB written (+128 KB mask) of HBM traffic: the unfused layer GEMMs sit at the HBM/tensor balance point.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace mnrf {
+namespace {
+
+using namespace tcx;
+
+// ------------------------------------------------------------------------------------------------ NN
+constexpr int NN_STAGES = 4;
+// A operand: K-adjacent core matrices are LBO = 2048 + 32 bytes apart (not 2048): with the loaders' mapping (4 lanes = the four
+// 16-byte K quads of a row, 8 rows per instruction -> 64-byte runs of global memory) the padding makes the st.shared.v4
+// phases bank-conflict free.
+constexpr uint32_t NN_A_LBO = 2080;
+constexpr uint32_t NN_A_PART = 4 * NN_A_LBO;   // 8320: 128 rows x 16 tf32 (padded)
+constexpr uint32_t NN_B_PART = 16384;          // up to 256 rows x 16 tf32
+constexpr uint32_t NN_STAGE = 2 * NN_A_PART + 2 * NN_B_PART;  // 49408
+constexpr uint32_t NN_SM_EPI = NN_STAGES * NN_STAGE;          // 197632: 8 epilogue warps x 4 KB transposition tiles
+constexpr uint32_t NN_SM_BAR = NN_SM_EPI + 8 * 4096;          // 230400
+constexpr uint32_t NN_SM_TOTAL = NN_SM_BAR + 256;
+constexpr int NN_THREADS = 576;
+constexpr int NN_LOADER_WARP0 = 2, NN_EPI_WARP0 = 10;
+// barrier slots
+constexpr int NB_A_FULL = 0, NB_B_FULL = 4, NB_EMPTY = 8, NB_ACC_FULL = 12, NB_ACC_EMPTY = 14, NB_TMEM_SLOT = 16;
+
+struct NNParams {
+  const float* A0; int lda0; int K0;
+  const float* A1; int lda1;
+  const uint8_t* blob;   // this step's blobs: [kc][hi | lo], N*64 bytes each
+  float* C; int ldc;
+  int M, N, K, n_tiles;
+  GemmEpi e;
+};
+
+__device__ __forceinline__ float act_apply(float v, int act, float m) {
+  if (act == 1) return fmaxf(v, 0.f);
+  if (act == 2) return m > 0.f ? v : 0.f;
+  if (act == 3) return v > 0.f ? v : 0.01f * v;
+  return v;
+}
+
+// epilogue of 4 consecutive columns [col, col+4) of row `grow` (a warp covers 4 rows x 128 contiguous bytes per call)
+__device__ __forceinline__ void nn_epi4(float4 acc, const NNParams& P, long long grow, int col) {
+  const GemmEpi& e = P.e;
+  float* cp = P.C + (size_t)grow * P.ldc + col;
+  float v[4] = {acc.x, acc.y, acc.z, acc.w};
+  if (e.accumulate) {
+    const float4 c = *reinterpret_cast<const float4*>(cp);
+    v[0] += c.x; v[1] += c.y; v[2] += c.z; v[3] += c.w;
+  }
+  if (e.bias != nullptr) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+    v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+  }
+  if (e.rowbias != nullptr) {
+    const float4 b = *reinterpret_cast<const float4*>(e.rowbias + (size_t)(grow / e.rb_div) * e.ld_rb + col);
+    v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+  }
+  if (e.rvec != nullptr) {
+    const float rv = e.rvec[(size_t)grow * e.ld_rvec];
+    const float4 c = __ldg(reinterpret_cast<const float4*>(e.cvec + col));
+    v[0] = fmaf(rv, c.x, v[0]); v[1] = fmaf(rv, c.y, v[1]); v[2] = fmaf(rv, c.z, v[2]); v[3] = fmaf(rv, c.w, v[3]);
+  }
+  float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (e.act == 2) m = *reinterpret_cast<const float4*>(e.mask + (size_t)grow * e.ld_mask + col);
+  float4 o;
+  o.x = act_apply(v[0], e.act, m.x); o.y = act_apply(v[1], e.act, m.y);
+  o.z = act_apply(v[2], e.act, m.z); o.w = act_apply(v[3], e.act, m.w);
+  *reinterpret_cast<float4*>(cp) = o;
+}
+
+__global__ void __launch_bounds__(NN_THREADS, 1) k_gemm_tc_nn(const NNParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bars = sbase + NN_SM_BAR;
+  auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + NN_SM_BAR + 8 * NB_TMEM_SLOT);
+  const int nkc = P.K >> 4;
+  const uint32_t N = (uint32_t)P.N;
+
+  if (threadIdx.x == 0) {
+    if (sbase & 127u) { printf("mnrf train_tc: unaligned dynamic smem base %u\n", sbase); __trap(); }
+    for (int i = 0; i < NN_STAGES; ++i) { mbar_init(bar(NB_A_FULL + i), 8); mbar_init(bar(NB_B_FULL + i), 1); mbar_init(bar(NB_EMPTY + i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(NB_ACC_FULL + i), 1); mbar_init(bar(NB_ACC_EMPTY + i), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int my_tiles = ((int)blockIdx.x < P.n_tiles) ? (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  if (warp == 0) {
+    // ------------------------------ B producer ------------------------------
+    if (elect_one()) {
+      uint32_t stage = 0, phase = 0;
+      const uint32_t bytes = 2u * N * 64u;
+      for (int t = 0; t < my_tiles; ++t) {
+        for (int kc = 0; kc < nkc; ++kc) {
+          mbar_wait(bar(NB_EMPTY + stage), phase ^ 1u);
+          const uint32_t dst = sbase + stage * NN_STAGE + 2 * NN_A_PART;
+          const uint32_t fb = bar(NB_B_FULL + stage);
+          mbar_expect_tx(fb, bytes);
+          const uint8_t* src = P.blob + (size_t)kc * bytes;
+          for (uint32_t o = 0; o < bytes; o += 8192u) bulk_g2s(dst + o, src + o, 8192u, fb);
+          if (++stage == NN_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (elect_one()) {
+      uint32_t stage = 0, phase = 0;
+      const uint32_t idesc = idesc_tf32(N);
+      const uint32_t bstep = 2u * N;  // one K8 step of B = 2 core columns = 2 * N*16 bytes, in 16-byte units
+      for (int t = 0; t < my_tiles; ++t) {
+        const int buf = t & 1;
+        if (t >= 2) mbar_wait(bar(NB_ACC_EMPTY + buf), (uint32_t)(((t >> 1) - 1) & 1));
+        tc_fence_after();
+        const uint32_t d_tmem = tmem + (uint32_t)buf * 256u;
+        uint32_t accumulate = 0;
+        for (int kc = 0; kc < nkc; ++kc) {
+          mbar_wait(bar(NB_A_FULL + stage), phase);
+          mbar_wait(bar(NB_B_FULL + stage), phase);
+          tc_fence_after();
+          const uint32_t sa = sbase + stage * NN_STAGE;
+          const uint32_t a_hi = desc_lo(sa, NN_A_LBO), a_lo = desc_lo(sa + NN_A_PART, NN_A_LBO);
+          const uint32_t b_hi = desc_lo(sa + 2 * NN_A_PART, N * 16u), b_lo = desc_lo(sa + 2 * NN_A_PART + N * 64u, N * 16u);
+          constexpr uint32_t astep = 2u * NN_A_LBO / 16u;  // one K8 step of A = 2 core columns
+#pragma unroll
+          for (uint32_t j = 0; j < 2; ++j) {
+            mma_tf32(d_tmem, a_hi + j * astep, b_hi + j * bstep, idesc, accumulate);
+            mma_tf32(d_tmem, a_lo + j * astep, b_hi + j * bstep, idesc, 1u);
+            mma_tf32(d_tmem, a_hi + j * astep, b_lo + j * bstep, idesc, 1u);
+            accumulate = 1u;
+          }
+          tc_commit(bar(NB_EMPTY + stage));
+          if (++stage == NN_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(bar(NB_ACC_FULL + buf));
+      }
+    }
+  } else if (warp >= NN_LOADER_WARP0 && warp < NN_EPI_WARP0) {
+    // ------------------------------ A loaders ------------------------------
+    // thread -> K quad (lt & 3) of rows (lt >> 2) and (lt >> 2) + 64: a warp instruction reads 8 rows x 64 contiguous bytes
+    const int lt = threadIdx.x - NN_LOADER_WARP0 * 32;
+    const int quad = lt & 3, row0 = lt >> 2;
+    const int total = my_tiles * nkc;
+    float4 rb[4][2];
+    auto issue = [&](int i, float4 (&dst)[2]) {
+      const int t = i / nkc, kc = i - t * nkc;
+      const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
+      const int k = kc * 16;
+      const bool first = k < P.K0;
+      const float* base = first ? P.A0 + k : P.A1 + (k - P.K0);
+      const size_t ld = first ? (size_t)P.lda0 : (size_t)P.lda1;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        long long grow = tile * 128 + row0 + 64 * h;
+        if (grow >= P.M) grow = P.M - 1;
+        dst[h] = *reinterpret_cast<const float4*>(base + (size_t)grow * ld + quad * 4);
+      }
+    };
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < total) issue(j, rb[j]);
+    uint32_t stage = 0, phase = 0;
+    uint32_t so[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int row = row0 + 64 * h;
+      so[h] = (uint32_t)quad * NN_A_LBO + (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u;
+    }
+    for (int i0 = 0; i0 < total; i0 += 4) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j;
+        if (i < total) {
+          mbar_wait(bar(NB_EMPTY + stage), phase ^ 1u);
+          const uint32_t sa = sbase + stage * NN_STAGE;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const float4 v = rb[j][h];
+            uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+            split_tf32(v.x, h0, l0); split_tf32(v.y, h1, l1); split_tf32(v.z, h2, l2); split_tf32(v.w, h3, l3);
+            st_shared_v4(sa + so[h], h0, h1, h2, h3);
+            st_shared_v4(sa + so[h] + NN_A_PART, l0, l1, l2, l3);
+          }
+          if (i + 4 < total) issue(i + 4, rb[j]);
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(NB_A_FULL + stage));
+          if (++stage == NN_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= NN_EPI_WARP0) {
+    // ------------------------------ epilogue ------------------------------
+    // TMEM -> registers (thread = row) -> per-warp 32x32 transposition tile in shared memory (16-byte XOR swizzle) -> each
+    // global access of the warp then covers 4 rows x 128 contiguous bytes (C, mask, accumulate and per-ray operands alike)
+    const int q = warp & 3;                       // TMEM lane quarter = warp_id % 4
+    const int ew = warp - NN_EPI_WARP0;
+    const int g = ew >> 2;                        // column half
+    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+    const uint32_t tb = sbase + NN_SM_EPI + (uint32_t)ew * 4096u;
+    const int ncol = P.N >> 1;
+    const int nch = ncol >> 5;                    // 32-column chunks of this warp: 4 | 2 | 1
+    const int rsub = lane >> 3, c4 = lane & 7;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int buf = t & 1;
+      const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
+      const long long row_base = tile * 128 + q * 32;
+      mbar_wait(bar(NB_ACC_FULL + buf), (uint32_t)((t >> 1) & 1));
+      tc_fence_after();
+      const uint32_t tcol = tlane + (uint32_t)buf * 256u + (uint32_t)(g * ncol);
+      uint32_t ra[32], rb2[32];
+      tmem_ld32(tcol, ra);
+      for (int c = 0; c < nch; ++c) {
+        tmem_wait_ld();
+        const bool more = c + 1 < nch;
+        if (more) {
+          if (c & 1) tmem_ld32(tcol + (uint32_t)(c + 1) * 32u, ra);
+          else       tmem_ld32(tcol + (uint32_t)(c + 1) * 32u, rb2);
+        } else {
+          // every column of this warp has left TMEM: hand the accumulator buffer back before the global traffic
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(NB_ACC_EMPTY + buf));
+        }
+        const uint32_t wrow = tb + (uint32_t)lane * 128u;
+        if (c & 1) {
+          pin32(rb2);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) st_shared_v4(wrow + (uint32_t)((j ^ (lane & 7)) * 16), rb2[4 * j], rb2[4 * j + 1], rb2[4 * j + 2], rb2[4 * j + 3]);
+        } else {
+          pin32(ra);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) st_shared_v4(wrow + (uint32_t)((j ^ (lane & 7)) * 16), ra[4 * j], ra[4 * j + 1], ra[4 * j + 2], ra[4 * j + 3]);
+        }
+        __syncwarp();
+        const int col = g * ncol + c * 32 + c4 * 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = 4 * i + rsub;
+          const float4 v = ld_shared_v4(tb + (uint32_t)r * 128u + (uint32_t)((c4 ^ (r & 7)) * 16));
+          const long long grow = row_base + r;
+          if (grow < P.M) nn_epi4(v, P, grow, col);
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ TN (weight gradients)
+constexpr int TN_STAGES = 3;
+// Operand rows are features, K = points.  8-row groups are SBO = 144 bytes apart (not 128): the loaders read float4 along the
+// features (coalesced) and each thread then owns 4 core-matrix rows 64 bytes apart; the 16-byte pad per group makes those
+// st.shared.v4 phases bank-conflict free.  K-adjacent core matrices: LBO = (features / 8) * 144.
+constexpr uint32_t TN_SBO = 144;
+constexpr uint32_t TN_PART = 4 * 32 * TN_SBO;       // 18432: up to 256 features x 16 points, one tf32 part
+constexpr uint32_t TN_STAGE = 4 * TN_PART;          // A_hi | A_lo | B_hi | B_lo = 73728
+constexpr uint32_t TN_SM_BAR = TN_STAGES * TN_STAGE;  // 221184
+constexpr uint32_t TN_SM_TOTAL = TN_SM_BAR + 256;
+constexpr int TN_THREADS = 576;                     // warp 1: MMA; warps 2..9 loaders; warps 10..17 epilogue
+constexpr int TB_FULL = 0, TB_EMPTY = 4, TB_ACC = 8, TB_TMEM_SLOT = 10;
+
+struct TNParams {
+  const float* A; int lda; int NA;
+  const float* B; int ldb; int NB;
+  float* Wg; int ldw; int col0; int valid;
+  int P; int rows_per_cta;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tc_tn(const TNParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bars = sbase + TN_SM_BAR;
+  auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + TN_SM_BAR + 8 * TB_TMEM_SLOT);
+  const int NA = P.NA, NB = P.NB;
+  const int p_begin = blockIdx.x * P.rows_per_cta;
+  const int p_end = min(P.P, p_begin + P.rows_per_cta);
+  const int nchunks = p_end > p_begin ? (p_end - p_begin + 15) >> 4 : 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TN_STAGES; ++i) { mbar_init(bar(TB_FULL + i), 8); mbar_init(bar(TB_EMPTY + i), 1); }
+    mbar_init(bar(TB_ACC), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 1) {
+    if (elect_one() && nchunks > 0) {
+      uint32_t stage = 0, phase = 0;
+      const uint32_t idesc = idesc_tf32((uint32_t)NB);
+      const uint32_t lbo_a = (uint32_t)(NA >> 3) * TN_SBO, lbo_b = (uint32_t)(NB >> 3) * TN_SBO;
+      const uint32_t astep = 2u * lbo_a / 16u, bstep = 2u * lbo_b / 16u;  // one K8 step = 2 core columns (16-byte units)
+      const uint32_t dhi = desc_hi(TN_SBO);
+      const int MT = NA >> 7;
+      for (int c = 0; c < nchunks; ++c) {
+        mbar_wait(bar(TB_FULL + stage), phase);
+        tc_fence_after();
+        const uint32_t sa = sbase + stage * TN_STAGE;
+        const uint32_t a_hi = desc_lo(sa, lbo_a), a_lo = desc_lo(sa + TN_PART, lbo_a);
+        const uint32_t b_hi = desc_lo(sa + 2 * TN_PART, lbo_b), b_lo = desc_lo(sa + 3 * TN_PART, lbo_b);
+        for (int mt = 0; mt < MT; ++mt) {
+          const uint32_t d_tmem = tmem + (uint32_t)(mt * NB);
+          const uint32_t mo = (uint32_t)mt * (16u * TN_SBO / 16u);  // 128 rows = 16 row groups
+#pragma unroll
+          for (uint32_t j = 0; j < 2; ++j) {
+            mma_tf32(d_tmem, a_hi + mo + j * astep, b_hi + j * bstep, idesc, (c > 0 || j > 0) ? 1u : 0u, dhi, dhi);
+            mma_tf32(d_tmem, a_lo + mo + j * astep, b_hi + j * bstep, idesc, 1u, dhi, dhi);
+            mma_tf32(d_tmem, a_hi + mo + j * astep, b_lo + j * bstep, idesc, 1u, dhi, dhi);
+          }
+        }
+        tc_commit(bar(TB_EMPTY + stage));
+        if (++stage == TN_STAGES) { stage = 0; phase ^= 1u; }
+      }
+      tc_commit(bar(TB_ACC));
+    }
+  } else if (warp >= 2 && warp < 10) {
+    // loaders: thread -> (feature quad fq, point group j): 4 float4 loads along the features (coalesced), a 4x4 register
+    // transpose, 4 core-matrix rows (one feature x 4 points each) per operand.  Two chunks in flight per thread.
+    const int lt = threadIdx.x - 64;
+    const int sha = 31 - __clz(NA >> 2), shb = 31 - __clz(NB >> 2);  // log2(feature quads)
+    const bool on_a = lt < NA, on_b = lt < NB;
+    const int fqa = lt & ((NA >> 2) - 1), ja = lt >> sha;
+    const int fqb = lt & ((NB >> 2) - 1), jb = lt >> shb;
+    const float* pa = P.A + (size_t)(p_begin + 4 * ja) * P.lda + 4 * fqa;
+    const float* pb = P.B + (size_t)(p_begin + 4 * jb) * P.ldb + 4 * fqb;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 va[2][4], vb[2][4];
+    auto issue = [&](int c, float4 (&xa)[4], float4 (&xb)[4]) {
+      const int p0 = p_begin + c * 16;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        xa[i] = (on_a && p0 + 4 * ja + i < p_end) ? *reinterpret_cast<const float4*>(pa + ((size_t)c * 16 + i) * P.lda) : zero4;
+        xb[i] = (on_b && p0 + 4 * jb + i < p_end) ? *reinterpret_cast<const float4*>(pb + ((size_t)c * 16 + i) * P.ldb) : zero4;
+      }
+    };
+    auto put = [&](uint32_t base, const float4 (&x)[4], int fq, int j, int NX) {
+      const uint32_t lbo = (uint32_t)(NX >> 3) * TN_SBO;
+      const float r[4][4] = {{x[0].x, x[1].x, x[2].x, x[3].x}, {x[0].y, x[1].y, x[2].y, x[3].y},
+                             {x[0].z, x[1].z, x[2].z, x[3].z}, {x[0].w, x[1].w, x[2].w, x[3].w}};
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const int f = 4 * fq + cc;
+        uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+        split_tf32(r[cc][0], h0, l0); split_tf32(r[cc][1], h1, l1); split_tf32(r[cc][2], h2, l2); split_tf32(r[cc][3], h3, l3);
+        const uint32_t a = base + (uint32_t)j * lbo + (uint32_t)(f >> 3) * TN_SBO + (uint32_t)(f & 7) * 16u;
+        st_shared_v4(a, h0, h1, h2, h3);
+        st_shared_v4(a + TN_PART, l0, l1, l2, l3);
+      }
+    };
+    if (nchunks > 0) issue(0, va[0], vb[0]);
+    if (nchunks > 1) issue(1, va[1], vb[1]);
+    uint32_t stage = 0, phase = 0;
+    for (int c0 = 0; c0 < nchunks; c0 += 2) {
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2) {
+        const int c = c0 + s2;
+        if (c < nchunks) {
+          mbar_wait(bar(TB_EMPTY + stage), phase ^ 1u);
+          const uint32_t sa = sbase + stage * TN_STAGE;
+          if (on_a) put(sa, va[s2], fqa, ja, NA);
+          if (on_b) put(sa + 2 * TN_PART, vb[s2], fqb, jb, NB);
+          if (c + 2 < nchunks) issue(c + 2, va[s2], vb[s2]);
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(TB_FULL + stage));
+          if (++stage == TN_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= 10 && nchunks > 0) {
+    // epilogue: flush the dW tile with reductions into global memory
+    const int q = warp & 3, g = (warp - 10) >> 2;
+    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+    mbar_wait(bar(TB_ACC), 0u);
+    tc_fence_after();
+    const int ncol = NB >> 1, nch = ncol >> 5;
+    const bool vec = ((P.ldw & 3) == 0) && ((P.col0 & 3) == 0) && P.valid == NB;
+    for (int mt = 0; mt < (NA >> 7); ++mt) {
+      const int r = mt * 128 + q * 32 + lane;
+      float* wrow = P.Wg + (size_t)r * P.ldw + P.col0;
+      for (int c = 0; c < nch; ++c) {
+        uint32_t v[32];
+        const int cb = g * ncol + c * 32;
+        tmem_ld32(tlane + (uint32_t)(mt * NB + cb), v);
+        tmem_wait_ld();
+        pin32(v);
+        if (vec) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            red_add_v4(wrow + cb + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                       __uint_as_float(v[4 * j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (cb + j < P.valid) atomicAdd(wrow + cb + j, __uint_as_float(v[j]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 0;
+  }
+  return n;
+}
+
+}  // namespace
+
+int gemm_nn_tc(const mnrf_field* f, int step, const float* A0, int lda0, int K0, const float* A1, int lda1, float* C,
+               int ldc, int M, const GemmEpi& e, cudaStream_t st) {
+  if (M <= 0) return 0;
+  MNRF_REQUIRE(step >= 0 && step < T32_NUM_STEPS, "gemm_nn_tc: bad step %d", step);
+  const int N = t32_step_n(step), K = t32_step_k(step);
+  MNRF_REQUIRE(K0 % 16 == 0 && K0 <= K && (K0 == K || A1 != nullptr), "gemm_nn_tc: bad K split %d of %d", K0, K);
+  MNRF_REQUIRE(lda0 % 4 == 0 && (A1 == nullptr || lda1 % 4 == 0) && ldc % 4 == 0, "gemm_nn_tc: leading dimensions must be multiples of 4");
+  static bool attr = false;
+  if (!attr) {
+    MNRF_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SM_TOTAL));
+    attr = true;
+  }
+  const int sms = num_sms();
+  MNRF_REQUIRE(sms > 0, "gemm_nn_tc: no CUDA device");
+  NNParams P;
+  P.A0 = A0; P.lda0 = lda0; P.K0 = K0; P.A1 = A1; P.lda1 = lda1;
+  P.blob = f->t32 + t32_step_offset(step);
+  P.C = C; P.ldc = ldc; P.M = M; P.N = N; P.K = K;
+  P.n_tiles = (M + 127) / 128;
+  P.e = e;
+  const int grid = P.n_tiles < sms ? P.n_tiles : sms;
+  k_gemm_tc_nn<<<grid, NN_THREADS, NN_SM_TOTAL, st>>>(P);
+  MNRF_LAUNCH_OK();
+  return 0;
+}
+
+int gemm_tn_tc(const float* A, int lda, int NA, const float* B, int ldb, int NB, float* Wg, int ldw, int col0, int valid,
+               int Pn, cudaStream_t st) {
+  if (Wg == nullptr || Pn <= 0) return 0;
+  MNRF_REQUIRE((NA == 128 || NA == 256) && (NB == 64 || NB == 128 || NB == 256), "gemm_tn_tc: bad shape %d x %d", NA, NB);
+  static bool attr = false;
+  if (!attr) {
+    MNRF_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_tn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TN_SM_TOTAL));
+    attr = true;
+  }
+  const int sms = num_sms();
+  MNRF_REQUIRE(sms > 0, "gemm_tn_tc: no CUDA device");
+  TNParams P;
+  P.A = A; P.lda = lda; P.NA = NA; P.B = B; P.ldb = ldb; P.NB = NB;
+  P.Wg = Wg; P.ldw = ldw; P.col0 = col0; P.valid = valid; P.P = Pn;
+  int rows = (Pn + sms - 1) / sms;
+  rows = ((rows + 15) / 16) * 16;
+  if (rows < 256) rows = 256;  // small problems: fewer CTAs, fewer atomics
+  P.rows_per_cta = rows;
+  const int grid = (Pn + rows - 1) / rows;
+  k_gemm_tc_tn<<<grid, TN_THREADS, TN_SM_TOTAL, st>>>(P);
+  MNRF_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace mnrf
