@@ -238,6 +238,10 @@ int mnrf_train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, 
  * (verification twin).  The environment variable MNRF_TRAIN_GEMM=simt selects 0 at first use. */
 int mnrf_train_set_gemm(int tensor_cores);
 
+/* Bring-up aid: milliseconds per launch of one training GEMM on synthetic operands (kind 0 = layer GEMM `step` over P rows,
+ * kind 1 = 256x256 weight-gradient GEMM over P rows; engine as above; dbg = train_tc.cu debug bits, 0 for a real run). */
+int mnrf_debug_gemm_bench(const mnrf_field* f, int kind, int step, int P, int engine, int dbg, int iters, float* ms_out);
+
 /* One torch.optim.Adam step (the reference's optimizer: R/utils/__init__.py:47-58, lr 5e-4, eps 1e-8, L2 weight decay) on flat
  * fp32 buffers of n elements: g = grads*grad_scale + weight_decay*p; m,v updated in place; p -= lr/(1-b1^t) * m/(sqrt(v)/
  * sqrt(1-b2^t) + eps).  `step` is t (1-based).  grad_scale = 1/world_size turns an all-reduce SUM into DDP's average. */

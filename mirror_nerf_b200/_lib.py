@@ -94,6 +94,7 @@ _SIGS = {
                                     C.c_int64, C.c_void_p, C.c_int64, C.POINTER(TrainGrads), c_float_p,
                                     C.POINTER(C.c_void_p), c_float_p, c_float_p, C.c_void_p]),
     "mnrf_train_set_gemm": (c_int, [c_int]),
+    "mnrf_debug_gemm_bench": (c_int, [C.c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, C.POINTER(C.c_float)]),
     "mnrf_adam_step": (c_int, [c_float_p, c_float_p, c_float_p, c_float_p, C.c_int64, C.c_float, C.c_float, C.c_float,
                                C.c_float, C.c_float, c_int, C.c_float, C.c_void_p]),
     "mnrf_axpy": (c_int, [c_float_p, c_float_p, C.c_int64, C.c_float, C.c_void_p]),

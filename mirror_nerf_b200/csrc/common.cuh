@@ -269,6 +269,8 @@ int gemm_nn_tc(const mnrf_field* f, int step, const float* A0, int lda0, int K0,
 int gemm_tn_tc(const float* A, int lda, int NA, const float* B, int ldb, int NB, float* Wg, int ldw, int col0, int valid,
                int P, cudaStream_t st);
 
+void set_train_tc_debug(int flags);
+
 // training path (train.cu): one field + compositor pass with saved activations, and its backward
 int64_t train_fwd_workspace_bytes(int n, int S, int compute_normal);
 int64_t train_bwd_workspace_bytes(int n, int S, int compute_normal);

@@ -1237,6 +1237,47 @@ int mnrf_train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, 
                         grad_rays, reinterpret_cast<cudaStream_t>(stream));
 }
 
+// Bring-up aid: time `iters` launches of one training GEMM on synthetic operands.  kind 0: NN step `step` on P rows; kind 1:
+// TN 256x256 over P rows.  engine 1 = tcgen05, 0 = CUDA cores.  dbg: train_tc.cu debug bits.  Returns milliseconds per launch.
+int mnrf_debug_gemm_bench(const mnrf_field* f, int kind, int step, int P, int engine, int dbg, int iters, float* ms_out) {
+  MNRF_REQUIRE(f && ms_out && P > 0 && iters > 0, "gemm_bench: bad argument");
+  float *A = nullptr, *C = nullptr, *Wg = nullptr;
+  MNRF_CUDA_OK(cudaMalloc(&A, sizeof(float) * (size_t)P * W));
+  MNRF_CUDA_OK(cudaMalloc(&C, sizeof(float) * (size_t)P * W));
+  MNRF_CUDA_OK(cudaMalloc(&Wg, sizeof(float) * W * W));
+  MNRF_CUDA_OK(cudaMemset(A, 0, sizeof(float) * (size_t)P * W));
+  MNRF_CUDA_OK(cudaMemset(C, 0, sizeof(float) * (size_t)P * W));
+  MNRF_CUDA_OK(cudaMemset(Wg, 0, sizeof(float) * W * W));
+  const int saved = g_engine;
+  g_engine = engine;
+  set_train_tc_debug(dbg);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  int rc = 0;
+  for (int it = -1; it < iters && rc == 0; ++it) {
+    if (it == 0) cudaEventRecord(e0, 0);
+    if (kind == 0) {
+      GemmEpi e;
+      e.act = 1;
+      const int K = t32_step_k(step);
+      rc = gemm_w(f, step, A, W, K > W ? 64 : K, K > W ? A : nullptr, W, C, W, P, e, 0);
+    } else {
+      rc = gemm_g(A, W, W, C, W, W, Wg, W, 0, W, P, 0);
+    }
+  }
+  cudaEventRecord(e1, 0);
+  cudaError_t err = cudaEventSynchronize(e1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  *ms_out = ms / iters;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  set_train_tc_debug(0);
+  g_engine = saved;
+  cudaFree(A); cudaFree(C); cudaFree(Wg);
+  if (err != cudaSuccess) { set_error("gemm_bench: %s", cudaGetErrorString(err)); return 1; }
+  return rc;
+}
+
 int mnrf_train_set_gemm(int tensor_cores) {
   g_engine = tensor_cores ? 1 : 0;
   return 0;

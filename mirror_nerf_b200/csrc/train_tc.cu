@@ -46,6 +46,7 @@ struct NNParams {
   float* C; int ldc;
   int M, N, K, n_tiles;
   GemmEpi e;
+  int dbg;  // bring-up: 1 = no global loads of A, 2 = no conversion/stores of A, 4 = no MMAs, 8 = no epilogue global traffic, 16 = no B copies
 };
 
 __device__ __forceinline__ float act_apply(float v, int act, float m) {
@@ -55,34 +56,45 @@ __device__ __forceinline__ float act_apply(float v, int act, float m) {
   return v;
 }
 
-// epilogue of 4 consecutive columns [col, col+4) of row `grow` (a warp covers 4 rows x 128 contiguous bytes per call)
-__device__ __forceinline__ void nn_epi4(float4 acc, const NNParams& P, long long grow, int col) {
+// Epilogue of a 32 x 32 block held in the warp's transposition tile: lane -> (row 4*i + rsub, columns col..col+3), i = 0..7.
+// All global operands (C for accumulate, ReLU mask, per-ray term, rank-1 row factor) are fetched for four rows at a time BEFORE
+// the dependent arithmetic and stores, so that their latencies overlap instead of serialising the 8 iterations.
+__device__ __forceinline__ void nn_epi_block(const NNParams& P, uint32_t tb, long long row_base, int rsub, int c4, int col) {
   const GemmEpi& e = P.e;
-  float* cp = P.C + (size_t)grow * P.ldc + col;
-  float v[4] = {acc.x, acc.y, acc.z, acc.w};
-  if (e.accumulate) {
-    const float4 c = *reinterpret_cast<const float4*>(cp);
-    v[0] += c.x; v[1] += c.y; v[2] += c.z; v[3] += c.w;
+  float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), cv = bias;
+  if (e.bias != nullptr) bias = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+  if (e.rvec != nullptr) cv = __ldg(reinterpret_cast<const float4*>(e.cvec + col));
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    float4 cin[4], mk[4], rbv[4];
+    float rv[4];
+    bool ok[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = 4 * (4 * half + k) + rsub;
+      const long long grow = row_base + r;
+      ok[k] = grow < P.M;
+      cin[k] = make_float4(0.f, 0.f, 0.f, 0.f); mk[k] = cin[k]; rbv[k] = cin[k]; rv[k] = 0.f;
+      if (ok[k]) {
+        if (e.accumulate) cin[k] = *reinterpret_cast<const float4*>(P.C + (size_t)grow * P.ldc + col);
+        if (e.act == 2) mk[k] = *reinterpret_cast<const float4*>(e.mask + (size_t)grow * e.ld_mask + col);
+        if (e.rowbias != nullptr) rbv[k] = *reinterpret_cast<const float4*>(e.rowbias + (size_t)(grow / e.rb_div) * e.ld_rb + col);
+        if (e.rvec != nullptr) rv[k] = e.rvec[(size_t)grow * e.ld_rvec];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = 4 * (4 * half + k) + rsub;
+      const float4 a = ld_shared_v4(tb + (uint32_t)r * 128u + (uint32_t)((c4 ^ (r & 7)) * 16));
+      float v[4] = {a.x + cin[k].x + bias.x + rbv[k].x, a.y + cin[k].y + bias.y + rbv[k].y, a.z + cin[k].z + bias.z + rbv[k].z,
+                    a.w + cin[k].w + bias.w + rbv[k].w};
+      v[0] = fmaf(rv[k], cv.x, v[0]); v[1] = fmaf(rv[k], cv.y, v[1]); v[2] = fmaf(rv[k], cv.z, v[2]); v[3] = fmaf(rv[k], cv.w, v[3]);
+      float4 o;
+      o.x = act_apply(v[0], e.act, mk[k].x); o.y = act_apply(v[1], e.act, mk[k].y);
+      o.z = act_apply(v[2], e.act, mk[k].z); o.w = act_apply(v[3], e.act, mk[k].w);
+      if (ok[k]) *reinterpret_cast<float4*>(P.C + (size_t)(row_base + r) * P.ldc + col) = o;
+    }
   }
-  if (e.bias != nullptr) {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col));
-    v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
-  }
-  if (e.rowbias != nullptr) {
-    const float4 b = *reinterpret_cast<const float4*>(e.rowbias + (size_t)(grow / e.rb_div) * e.ld_rb + col);
-    v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
-  }
-  if (e.rvec != nullptr) {
-    const float rv = e.rvec[(size_t)grow * e.ld_rvec];
-    const float4 c = __ldg(reinterpret_cast<const float4*>(e.cvec + col));
-    v[0] = fmaf(rv, c.x, v[0]); v[1] = fmaf(rv, c.y, v[1]); v[2] = fmaf(rv, c.z, v[2]); v[3] = fmaf(rv, c.w, v[3]);
-  }
-  float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (e.act == 2) m = *reinterpret_cast<const float4*>(e.mask + (size_t)grow * e.ld_mask + col);
-  float4 o;
-  o.x = act_apply(v[0], e.act, m.x); o.y = act_apply(v[1], e.act, m.y);
-  o.z = act_apply(v[2], e.act, m.z); o.w = act_apply(v[3], e.act, m.w);
-  *reinterpret_cast<float4*>(cp) = o;
 }
 
 __global__ void __launch_bounds__(NN_THREADS, 1) k_gemm_tc_nn(const NNParams P) {
@@ -121,9 +133,13 @@ __global__ void __launch_bounds__(NN_THREADS, 1) k_gemm_tc_nn(const NNParams P) 
           mbar_wait(bar(NB_EMPTY + stage), phase ^ 1u);
           const uint32_t dst = sbase + stage * NN_STAGE + 2 * NN_A_PART;
           const uint32_t fb = bar(NB_B_FULL + stage);
-          mbar_expect_tx(fb, bytes);
           const uint8_t* src = P.blob + (size_t)kc * bytes;
-          for (uint32_t o = 0; o < bytes; o += 8192u) bulk_g2s(dst + o, src + o, 8192u, fb);
+          if (P.dbg & 16) {
+            mbar_expect_tx(fb, 0);
+          } else {
+            mbar_expect_tx(fb, bytes);
+            for (uint32_t o = 0; o < bytes; o += 8192u) bulk_g2s(dst + o, src + o, 8192u, fb);
+          }
           if (++stage == NN_STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -148,12 +164,14 @@ __global__ void __launch_bounds__(NN_THREADS, 1) k_gemm_tc_nn(const NNParams P) 
           const uint32_t a_hi = desc_lo(sa, NN_A_LBO), a_lo = desc_lo(sa + NN_A_PART, NN_A_LBO);
           const uint32_t b_hi = desc_lo(sa + 2 * NN_A_PART, N * 16u), b_lo = desc_lo(sa + 2 * NN_A_PART + N * 64u, N * 16u);
           constexpr uint32_t astep = 2u * NN_A_LBO / 16u;  // one K8 step of A = 2 core columns
+          if (!(P.dbg & 4)) {
 #pragma unroll
-          for (uint32_t j = 0; j < 2; ++j) {
-            mma_tf32(d_tmem, a_hi + j * astep, b_hi + j * bstep, idesc, accumulate);
-            mma_tf32(d_tmem, a_lo + j * astep, b_hi + j * bstep, idesc, 1u);
-            mma_tf32(d_tmem, a_hi + j * astep, b_lo + j * bstep, idesc, 1u);
-            accumulate = 1u;
+            for (uint32_t j = 0; j < 2; ++j) {
+              mma_tf32(d_tmem, a_hi + j * astep, b_hi + j * bstep, idesc, accumulate);
+              mma_tf32(d_tmem, a_lo + j * astep, b_hi + j * bstep, idesc, 1u);
+              mma_tf32(d_tmem, a_hi + j * astep, b_lo + j * bstep, idesc, 1u);
+              accumulate = 1u;
+            }
           }
           tc_commit(bar(NB_EMPTY + stage));
           if (++stage == NN_STAGES) { stage = 0; phase ^= 1u; }
@@ -167,7 +185,8 @@ __global__ void __launch_bounds__(NN_THREADS, 1) k_gemm_tc_nn(const NNParams P) 
     const int lt = threadIdx.x - NN_LOADER_WARP0 * 32;
     const int quad = lt & 3, row0 = lt >> 2;
     const int total = my_tiles * nkc;
-    float4 rb[4][2];
+    constexpr int NPF = 8;  // chunks in flight per thread (8 x 2 float4 = 64 registers)
+    float4 rb[NPF][2];
     auto issue = [&](int i, float4 (&dst)[2]) {
       const int t = i / nkc, kc = i - t * nkc;
       const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
@@ -179,11 +198,11 @@ __global__ void __launch_bounds__(NN_THREADS, 1) k_gemm_tc_nn(const NNParams P) 
       for (int h = 0; h < 2; ++h) {
         long long grow = tile * 128 + row0 + 64 * h;
         if (grow >= P.M) grow = P.M - 1;
-        dst[h] = *reinterpret_cast<const float4*>(base + (size_t)grow * ld + quad * 4);
+        dst[h] = (P.dbg & 1) ? make_float4(1.f, 2.f, 3.f, 4.f) : *reinterpret_cast<const float4*>(base + (size_t)grow * ld + quad * 4);
       }
     };
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < NPF; ++j)
       if (j < total) issue(j, rb[j]);
     uint32_t stage = 0, phase = 0;
     uint32_t so[2];
@@ -192,9 +211,9 @@ __global__ void __launch_bounds__(NN_THREADS, 1) k_gemm_tc_nn(const NNParams P) 
       const int row = row0 + 64 * h;
       so[h] = (uint32_t)quad * NN_A_LBO + (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u;
     }
-    for (int i0 = 0; i0 < total; i0 += 4) {
+    for (int i0 = 0; i0 < total; i0 += NPF) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < NPF; ++j) {
         const int i = i0 + j;
         if (i < total) {
           mbar_wait(bar(NB_EMPTY + stage), phase ^ 1u);
@@ -202,12 +221,13 @@ __global__ void __launch_bounds__(NN_THREADS, 1) k_gemm_tc_nn(const NNParams P) 
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const float4 v = rb[j][h];
+            if (P.dbg & 2) continue;
             uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
             split_tf32(v.x, h0, l0); split_tf32(v.y, h1, l1); split_tf32(v.z, h2, l2); split_tf32(v.w, h3, l3);
             st_shared_v4(sa + so[h], h0, h1, h2, h3);
             st_shared_v4(sa + so[h] + NN_A_PART, l0, l1, l2, l3);
           }
-          if (i + 4 < total) issue(i + 4, rb[j]);
+          if (i + NPF < total) issue(i + NPF, rb[j]);
           fence_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar(NB_A_FULL + stage));
@@ -234,39 +254,23 @@ __global__ void __launch_bounds__(NN_THREADS, 1) k_gemm_tc_nn(const NNParams P) 
       mbar_wait(bar(NB_ACC_FULL + buf), (uint32_t)((t >> 1) & 1));
       tc_fence_after();
       const uint32_t tcol = tlane + (uint32_t)buf * 256u + (uint32_t)(g * ncol);
-      uint32_t ra[32], rb2[32];
-      tmem_ld32(tcol, ra);
       for (int c = 0; c < nch; ++c) {
+        uint32_t ra[32];
+        tmem_ld32(tcol + (uint32_t)c * 32u, ra);
         tmem_wait_ld();
-        const bool more = c + 1 < nch;
-        if (more) {
-          if (c & 1) tmem_ld32(tcol + (uint32_t)(c + 1) * 32u, ra);
-          else       tmem_ld32(tcol + (uint32_t)(c + 1) * 32u, rb2);
-        } else {
+        if (c + 1 == nch) {
           // every column of this warp has left TMEM: hand the accumulator buffer back before the global traffic
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar(NB_ACC_EMPTY + buf));
         }
+        pin32(ra);
         const uint32_t wrow = tb + (uint32_t)lane * 128u;
-        if (c & 1) {
-          pin32(rb2);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) st_shared_v4(wrow + (uint32_t)((j ^ (lane & 7)) * 16), rb2[4 * j], rb2[4 * j + 1], rb2[4 * j + 2], rb2[4 * j + 3]);
-        } else {
-          pin32(ra);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) st_shared_v4(wrow + (uint32_t)((j ^ (lane & 7)) * 16), ra[4 * j], ra[4 * j + 1], ra[4 * j + 2], ra[4 * j + 3]);
-        }
+        for (int j = 0; j < 8; ++j) st_shared_v4(wrow + (uint32_t)((j ^ (lane & 7)) * 16), ra[4 * j], ra[4 * j + 1], ra[4 * j + 2], ra[4 * j + 3]);
         __syncwarp();
         const int col = g * ncol + c * 32 + c4 * 4;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = 4 * i + rsub;
-          const float4 v = ld_shared_v4(tb + (uint32_t)r * 128u + (uint32_t)((c4 ^ (r & 7)) * 16));
-          const long long grow = row_base + r;
-          if (grow < P.M) nn_epi4(v, P, grow, col);
-        }
+        if (!(P.dbg & 8)) nn_epi_block(P, tb, row_base, rsub, c4, col);
         __syncwarp();
       }
     }
@@ -282,23 +286,27 @@ __global__ void __launch_bounds__(NN_THREADS, 1) k_gemm_tc_nn(const NNParams P) 
 }
 
 // ------------------------------------------------------------------------------------------------ TN (weight gradients)
-constexpr int TN_STAGES = 3;
+constexpr int TN_STAGES = 2;   // UMMA operand stages (hi/lo of both operands, 72 KB each)
+constexpr int TN_RAW = 2;      // raw fp32 chunks in flight behind them (TMA bulk copies, 32 KB each)
 // Operand rows are features, K = points.  8-row groups are SBO = 144 bytes apart (not 128): the loaders read float4 along the
 // features (coalesced) and each thread then owns 4 core-matrix rows 64 bytes apart; the 16-byte pad per group makes those
 // st.shared.v4 phases bank-conflict free.  K-adjacent core matrices: LBO = (features / 8) * 144.
 constexpr uint32_t TN_SBO = 144;
 constexpr uint32_t TN_PART = 4 * 32 * TN_SBO;       // 18432: up to 256 features x 16 points, one tf32 part
 constexpr uint32_t TN_STAGE = 4 * TN_PART;          // A_hi | A_lo | B_hi | B_lo = 73728
-constexpr uint32_t TN_SM_BAR = TN_STAGES * TN_STAGE;  // 221184
+constexpr uint32_t TN_SM_RAW = TN_STAGES * TN_STAGE;  // 147456: raw ring, per slot [A 16 KB | B 16 KB]
+constexpr uint32_t TN_RAW_SLOT = 32768;
+constexpr uint32_t TN_SM_BAR = TN_SM_RAW + TN_RAW * TN_RAW_SLOT;  // 212992
 constexpr uint32_t TN_SM_TOTAL = TN_SM_BAR + 256;
-constexpr int TN_THREADS = 576;                     // warp 1: MMA; warps 2..9 loaders; warps 10..17 epilogue
-constexpr int TB_FULL = 0, TB_EMPTY = 4, TB_ACC = 8, TB_TMEM_SLOT = 10;
+constexpr int TN_THREADS = 576;                     // warp 1: MMA; warps 2..17: loaders (2..9 operand A, 10..17 operand B), then epilogue
+constexpr int TB_FULL = 0, TB_EMPTY = 4, TB_ACC = 8, TB_TMEM_SLOT = 10, TB_RAW_FULL = 12, TB_RAW_EMPTY = 16;
 
 struct TNParams {
   const float* A; int lda; int NA;
   const float* B; int ldb; int NB;
   float* Wg; int ldw; int col0; int valid;
   int P; int rows_per_cta;
+  int dbg;  // bring-up: 1 = no global loads, 2 = no conversion/stores, 4 = no MMAs, 8 = no flush
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -318,7 +326,8 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tc_tn(const TNParams P) 
   const int nchunks = p_end > p_begin ? (p_end - p_begin + 15) >> 4 : 0;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < TN_STAGES; ++i) { mbar_init(bar(TB_FULL + i), 8); mbar_init(bar(TB_EMPTY + i), 1); }
+    for (int i = 0; i < TN_STAGES; ++i) { mbar_init(bar(TB_FULL + i), 16); mbar_init(bar(TB_EMPTY + i), 1); }
+    for (int i = 0; i < TN_RAW; ++i) { mbar_init(bar(TB_RAW_FULL + i), 1); mbar_init(bar(TB_RAW_EMPTY + i), 16); }
     mbar_init(bar(TB_ACC), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -331,7 +340,30 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tc_tn(const TNParams P) 
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 1) {
+  if (warp == 0) {
+    // raw producer: the 16 points of a chunk are contiguous in both operands (lda == NA, ldb == NB): two bulk copies per chunk
+    if (elect_one()) {
+      uint32_t slot = 0, phase = 0;
+      for (int c = 0; c < nchunks; ++c) {
+        mbar_wait(bar(TB_RAW_EMPTY + slot), phase ^ 1u);
+        const int p0 = p_begin + c * 16;
+        const uint32_t rows = (uint32_t)min(16, p_end - p0);
+        const uint32_t ba = rows * (uint32_t)NA * 4u, bb = rows * (uint32_t)NB * 4u;
+        const uint32_t fb = bar(TB_RAW_FULL + slot);
+        const uint32_t dst = sbase + TN_SM_RAW + slot * TN_RAW_SLOT;
+        mbar_expect_tx(fb, ba + bb);
+        if (!(P.dbg & 1)) {
+          const uint8_t* ga = reinterpret_cast<const uint8_t*>(P.A + (size_t)p0 * NA);
+          const uint8_t* gb = reinterpret_cast<const uint8_t*>(P.B + (size_t)p0 * NB);
+          for (uint32_t o = 0; o < ba; o += 8192u) bulk_g2s(dst + o, ga + o, min(8192u, ba - o), fb);
+          for (uint32_t o = 0; o < bb; o += 8192u) bulk_g2s(dst + 16384u + o, gb + o, min(8192u, bb - o), fb);
+        } else {
+          asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(fb), "r"(ba + bb) : "memory");
+        }
+        if (++slot == TN_RAW) { slot = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
     if (elect_one() && nchunks > 0) {
       uint32_t stage = 0, phase = 0;
       const uint32_t idesc = idesc_tf32((uint32_t)NB);
@@ -345,7 +377,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tc_tn(const TNParams P) 
         const uint32_t sa = sbase + stage * TN_STAGE;
         const uint32_t a_hi = desc_lo(sa, lbo_a), a_lo = desc_lo(sa + TN_PART, lbo_a);
         const uint32_t b_hi = desc_lo(sa + 2 * TN_PART, lbo_b), b_lo = desc_lo(sa + 3 * TN_PART, lbo_b);
-        for (int mt = 0; mt < MT; ++mt) {
+        for (int mt = 0; mt < MT && !(P.dbg & 4); ++mt) {
           const uint32_t d_tmem = tmem + (uint32_t)(mt * NB);
           const uint32_t mo = (uint32_t)mt * (16u * TN_SBO / 16u);  // 128 rows = 16 row groups
 #pragma unroll
@@ -360,28 +392,21 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tc_tn(const TNParams P) 
       }
       tc_commit(bar(TB_ACC));
     }
-  } else if (warp >= 2 && warp < 10) {
-    // loaders: thread -> (feature quad fq, point group j): 4 float4 loads along the features (coalesced), a 4x4 register
-    // transpose, 4 core-matrix rows (one feature x 4 points each) per operand.  Two chunks in flight per thread.
-    const int lt = threadIdx.x - 64;
-    const int sha = 31 - __clz(NA >> 2), shb = 31 - __clz(NB >> 2);  // log2(feature quads)
-    const bool on_a = lt < NA, on_b = lt < NB;
-    const int fqa = lt & ((NA >> 2) - 1), ja = lt >> sha;
-    const int fqb = lt & ((NB >> 2) - 1), jb = lt >> shb;
-    const float* pa = P.A + (size_t)(p_begin + 4 * ja) * P.lda + 4 * fqa;
-    const float* pb = P.B + (size_t)(p_begin + 4 * jb) * P.ldb + 4 * fqb;
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 va[2][4], vb[2][4];
-    auto issue = [&](int c, float4 (&xa)[4], float4 (&xb)[4]) {
-      const int p0 = p_begin + c * 16;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        xa[i] = (on_a && p0 + 4 * ja + i < p_end) ? *reinterpret_cast<const float4*>(pa + ((size_t)c * 16 + i) * P.lda) : zero4;
-        xb[i] = (on_b && p0 + 4 * jb + i < p_end) ? *reinterpret_cast<const float4*>(pb + ((size_t)c * 16 + i) * P.ldb) : zero4;
-      }
-    };
-    auto put = [&](uint32_t base, const float4 (&x)[4], int fq, int j, int NX) {
-      const uint32_t lbo = (uint32_t)(NX >> 3) * TN_SBO;
+  } else if (warp >= 2) {
+    // loaders: warps 2..9 stage operand A, warps 10..17 operand B.  thread -> (feature quad fq, point group j): 4 float4 loads along
+    // the features (coalesced), a 4x4 register transpose, 4 core-matrix rows (one feature x 4 points each).  Four chunks in flight.
+    const int lt = (threadIdx.x - 64) & 255;
+    const bool is_b = warp >= 10;
+    const int NX = is_b ? NB : NA;
+    const float* X = is_b ? P.B : P.A;
+    const size_t ldx = is_b ? (size_t)P.ldb : (size_t)P.lda;
+    const int sh = 31 - __clz(NX >> 2);  // log2(feature quads)
+    const bool on = lt < NX;
+    const int fq = lt & ((NX >> 2) - 1), j = lt >> sh;
+    const uint32_t lbo = (uint32_t)(NX >> 3) * TN_SBO;
+    const uint32_t part0 = is_b ? 2 * TN_PART : 0u;
+    const uint32_t raw_off = (is_b ? 16384u : 0u) + (uint32_t)(4 * j * NX + 4 * fq) * 4u;  // (point 4j, feature 4fq) of the raw slot
+    auto put = [&](uint32_t base, const float4 (&x)[4]) {
       const float r[4][4] = {{x[0].x, x[1].x, x[2].x, x[3].x}, {x[0].y, x[1].y, x[2].y, x[3].y},
                              {x[0].z, x[1].z, x[2].z, x[3].z}, {x[0].w, x[1].w, x[2].w, x[3].w}};
 #pragma unroll
@@ -394,52 +419,52 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tc_tn(const TNParams P) 
         st_shared_v4(a + TN_PART, l0, l1, l2, l3);
       }
     };
-    if (nchunks > 0) issue(0, va[0], vb[0]);
-    if (nchunks > 1) issue(1, va[1], vb[1]);
-    uint32_t stage = 0, phase = 0;
-    for (int c0 = 0; c0 < nchunks; c0 += 2) {
+    uint32_t stage = 0, phase = 0, slot = 0, rphase = 0;
+    (void)X; (void)ldx;
+    for (int c = 0; c < nchunks; ++c) {
+      const int p0 = p_begin + c * 16 + 4 * j;
+      mbar_wait(bar(TB_RAW_FULL + slot), rphase);
+      float4 x[4];
 #pragma unroll
-      for (int s2 = 0; s2 < 2; ++s2) {
-        const int c = c0 + s2;
-        if (c < nchunks) {
-          mbar_wait(bar(TB_EMPTY + stage), phase ^ 1u);
-          const uint32_t sa = sbase + stage * TN_STAGE;
-          if (on_a) put(sa, va[s2], fqa, ja, NA);
-          if (on_b) put(sa + 2 * TN_PART, vb[s2], fqb, jb, NB);
-          if (c + 2 < nchunks) issue(c + 2, va[s2], vb[s2]);
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar(TB_FULL + stage));
-          if (++stage == TN_STAGES) { stage = 0; phase ^= 1u; }
-        }
-      }
+      for (int i = 0; i < 4; ++i)
+        x[i] = (on && p0 + i < p_end && !(P.dbg & 1)) ? ld_shared_v4(sbase + TN_SM_RAW + slot * TN_RAW_SLOT + raw_off + (uint32_t)(i * NX) * 4u)
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+      mbar_wait(bar(TB_EMPTY + stage), phase ^ 1u);
+      if (on && !(P.dbg & 2)) put(sbase + stage * TN_STAGE + part0, x);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(bar(TB_FULL + stage)); mbar_arrive(bar(TB_RAW_EMPTY + slot)); }
+      if (++stage == TN_STAGES) { stage = 0; phase ^= 1u; }
+      if (++slot == TN_RAW) { slot = 0; rphase ^= 1u; }
     }
-  } else if (warp >= 10 && nchunks > 0) {
-    // epilogue: flush the dW tile with reductions into global memory
-    const int q = warp & 3, g = (warp - 10) >> 2;
-    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
-    mbar_wait(bar(TB_ACC), 0u);
-    tc_fence_after();
-    const int ncol = NB >> 1, nch = ncol >> 5;
-    const bool vec = ((P.ldw & 3) == 0) && ((P.col0 & 3) == 0) && P.valid == NB;
-    for (int mt = 0; mt < (NA >> 7); ++mt) {
-      const int r = mt * 128 + q * 32 + lane;
-      float* wrow = P.Wg + (size_t)r * P.ldw + P.col0;
-      for (int c = 0; c < nch; ++c) {
+    // epilogue (same 16 warps): flush the dW tile with reductions into global memory.  The MT x NB accumulator columns are split
+    // into four column groups (one per set of 4 warps with distinct TMEM lane quarters).
+    if (nchunks > 0 && !(P.dbg & 8)) {
+      const int q = warp & 3, g4 = (warp - 2) >> 2;
+      const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+      mbar_wait(bar(TB_ACC), 0u);
+      tc_fence_after();
+      const int tot = (NA >> 7) * NB;                  // TMEM columns in use (64 .. 512)
+      const int ng = tot >= 128 ? 4 : tot >> 5;        // column groups that get work
+      const int per = tot / ng;                        // columns per group (multiple of 32)
+      const bool vec = ((P.ldw & 3) == 0) && ((P.col0 & 3) == 0) && P.valid == NB;
+      for (int tc0 = g4 * per; g4 < ng && tc0 < (g4 + 1) * per; tc0 += 32) {
+        const int mt = tc0 / NB, cb = tc0 - mt * NB;
+        const int r = mt * 128 + q * 32 + lane;
+        float* wrow = P.Wg + (size_t)r * P.ldw + P.col0;
         uint32_t v[32];
-        const int cb = g * ncol + c * 32;
-        tmem_ld32(tlane + (uint32_t)(mt * NB + cb), v);
+        tmem_ld32(tlane + (uint32_t)tc0, v);
         tmem_wait_ld();
         pin32(v);
         if (vec) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            red_add_v4(wrow + cb + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                       __uint_as_float(v[4 * j + 3]));
+          for (int jj = 0; jj < 8; ++jj)
+            red_add_v4(wrow + cb + 4 * jj, __uint_as_float(v[4 * jj]), __uint_as_float(v[4 * jj + 1]), __uint_as_float(v[4 * jj + 2]),
+                       __uint_as_float(v[4 * jj + 3]));
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (cb + j < P.valid) atomicAdd(wrow + cb + j, __uint_as_float(v[j]));
+          for (int jj = 0; jj < 32; ++jj)
+            if (cb + jj < P.valid) atomicAdd(wrow + cb + jj, __uint_as_float(v[jj]));
         }
       }
     }
@@ -454,6 +479,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tc_tn(const TNParams P) 
   }
 }
 
+int g_dbg = 0;
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -485,6 +511,7 @@ int gemm_nn_tc(const mnrf_field* f, int step, const float* A0, int lda0, int K0,
   P.C = C; P.ldc = ldc; P.M = M; P.N = N; P.K = K;
   P.n_tiles = (M + 127) / 128;
   P.e = e;
+  P.dbg = g_dbg;
   const int grid = P.n_tiles < sms ? P.n_tiles : sms;
   k_gemm_tc_nn<<<grid, NN_THREADS, NN_SM_TOTAL, st>>>(P);
   MNRF_LAUNCH_OK();
@@ -495,6 +522,7 @@ int gemm_tn_tc(const float* A, int lda, int NA, const float* B, int ldb, int NB,
                int Pn, cudaStream_t st) {
   if (Wg == nullptr || Pn <= 0) return 0;
   MNRF_REQUIRE((NA == 128 || NA == 256) && (NB == 64 || NB == 128 || NB == 256), "gemm_tn_tc: bad shape %d x %d", NA, NB);
+  MNRF_REQUIRE(lda == NA && ldb == NB, "gemm_tn_tc: operands must be contiguous (lda == NA, ldb == NB): their chunks are bulk-copied");
   static bool attr = false;
   if (!attr) {
     MNRF_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_tn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TN_SM_TOTAL));
@@ -509,10 +537,13 @@ int gemm_tn_tc(const float* A, int lda, int NA, const float* B, int ldb, int NB,
   rows = ((rows + 15) / 16) * 16;
   if (rows < 256) rows = 256;  // small problems: fewer CTAs, fewer atomics
   P.rows_per_cta = rows;
+  P.dbg = g_dbg;
   const int grid = (Pn + rows - 1) / rows;
   k_gemm_tc_tn<<<grid, TN_THREADS, TN_SM_TOTAL, st>>>(P);
   MNRF_LAUNCH_OK();
   return 0;
 }
+
+void set_train_tc_debug(int flags) { g_dbg = flags; }
 
 }  // namespace mnrf
