@@ -146,7 +146,7 @@ def train_loss(r, target, mask_gt):
 
 def train_bench(dev, world, rank, steps, warmup):
     """BASELINE config 5 on this rank: 4096-ray batch, train semantics (perturb=1, noise_std=1, analytic normals), forward +
-    backward through csrc/train.cu, ONE flat NCCL all-reduce of the 5.3 MB gradient buffer, one Adam kernel.  Returns a dict."""
+    backward through csrc/train.cu + train_tc.cu, ONE flat NCCL all-reduce of the 5.3 MB gradient buffer, one Adam kernel.  Returns a dict."""
     import torch
     import torch.distributed as dist
     from mirror_nerf_b200 import _lib
@@ -198,7 +198,7 @@ def train_bench(dev, world, rank, steps, warmup):
     return {"metric": "rays/sec (train step: forward + backward + gradient all-reduce + Adam; 4096-ray batch per GPU, "
                       "64+128 samples, analytic normals, fp32)",
             "value": rate, "unit": "rays/s", "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
-            "dtype": "f32 (CUDA-core GEMMs)", "launches_per_step": (_lib.launch_count() - l0) / steps,
+            "dtype": "tf32x3-split operands, f32 accumulate (tcgen05 kind::tf32; fp32-grade)", "launches_per_step": (_lib.launch_count() - l0) / steps,
             "algorithmic_tflops": rate / world * TRAIN_FLOP_PER_RAY / 1e12,
             "allreduce_bytes_per_step": ddp.flat_grads.numel() * 4 if world > 1 else 0,
             "loss_first": float(losses[0]), "loss_last": float(losses[-1])}
