@@ -53,6 +53,19 @@ void mnrf_field_destroy(mnrf_field* f);
 int mnrf_field_has_normal(const mnrf_field* f);
 int mnrf_field_has_mirror(const mnrf_field* f);
 
+/* Hash-grid field (BASELINE config 3; R/models/mirror_nerf_tcnn.py:13-259 with the arguments of R/train.py:73-100): 16-level
+ * multiresolution hash encoding + small bias-free MLPs.  tensors = HOST array of 12 DEVICE pointers:
+ *   0 encoder.params (table_floats) | 1,2 sigma_net.{0,1}.weight (64x32, 16x64) | 3,4,5 color_net.{0,1,2}.weight (64x31, 64x64,
+ *   3x64) | 6,7 normal_net.{0,1}.weight (64x15, 3x64) or NULL | 8..11 is_mirror_net.0.{weight,bias} (32x15, 32),
+ *   is_mirror_net.2.{weight,bias} (1x32, 1) or NULL.
+ * The level table (HOST arrays of 16: grid scale, resolution, first table entry, entries) is computed by the caller so that it
+ * is defined in one place (mirror_nerf_b200/mirror_nerf_tcnn.py::level_table, following tinycudann's grid.h).
+ * The returned object is used wherever a mnrf_field is accepted (mnrf_field_eval_*, mnrf_render_level*); analytic normals
+ * (compute_normal) and gradients are not built for it.  Destroy with mnrf_field_destroy. */
+int mnrf_hash_field_create(mnrf_field** out, const float* const* tensors, int64_t table_floats, float bound,
+                           const float* level_scale, const int* level_res, const uint32_t* level_offset,
+                           const uint32_t* level_size, void* stream);
+
 /* which kernel evaluates the MLP */
 #define MNRF_IMPL_TC3 3   /* tcgen05, fp16 hi/lo split operands, 3 MMAs per product (fp32-grade; parity mode) */
 #define MNRF_IMPL_TC1 1   /* tcgen05, single fp16 pass (speed mode; does not meet the 1e-3 parity bar)      */

@@ -61,6 +61,9 @@ _SIGS = {
     "mnrf_macs_full": (C.c_int64, []),
     "mnrf_macs_sigma_only": (C.c_int64, []),
     "mnrf_field_create": (c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]),
+    "mnrf_hash_field_create": (c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int64, C.c_float,
+                                       C.POINTER(C.c_float), C.POINTER(c_int), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                       C.c_void_p]),
     "mnrf_field_update": (c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]),
     "mnrf_field_destroy": (None, [C.c_void_p]),
     "mnrf_field_has_normal": (c_int, [C.c_void_p]),

@@ -1,5 +1,6 @@
 // C ABI of libmnrf.so (include/mnrf.h): argument checking, scratch management and the per-level launch
 // sequence of render_rays (R/models/rendering.py:54-369).  No torch types, no CPU compute path.
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdlib>
@@ -70,6 +71,7 @@ int check_impl(int impl) {
 }
 
 int run_field(const mnrf_field* f, int impl, const FieldIO& io, cudaStream_t st) {
+  if (f->kind == 1) return launch_field_hash(f, io, st);
   if (impl == MNRF_IMPL_FP32) return launch_field_fp32(f, io, st);
   return launch_field_tc(f, io, impl == MNRF_IMPL_TC3 ? 3 : 1, st);
 }
@@ -122,6 +124,9 @@ int mnrf_field_create(mnrf_field** out, const float* const* tensors, void* strea
   for (int i = 24; i < 28; ++i) MNRF_REQUIRE((tensors[i] != nullptr) == hn, "field_create: normal_net tensors must be all set or all NULL");
   for (int i = 28; i < 32; ++i) MNRF_REQUIRE((tensors[i] != nullptr) == hm, "field_create: is_mirror_net tensors must be all set or all NULL");
   mnrf_field* f = new mnrf_field();
+  f->kind = 0;
+  f->hash_table = nullptr;
+  f->hash_w = nullptr;
   f->has_normal = hn;
   f->has_mirror = hm;
   f->L = make_f32_layout();
@@ -141,8 +146,46 @@ int mnrf_field_create(mnrf_field** out, const float* const* tensors, void* strea
   return 0;
 }
 
+int mnrf_hash_field_create(mnrf_field** out, const float* const* tensors, int64_t table_floats, float bound,
+                           const float* level_scale, const int* level_res, const uint32_t* level_offset,
+                           const uint32_t* level_size, void* stream) {
+  MNRF_REQUIRE(out && tensors && level_scale && level_res && level_offset && level_size, "hash_field_create: null argument");
+  for (int i = 0; i < 6; ++i) MNRF_REQUIRE(tensors[i] != nullptr, "hash_field_create: tensor %d is required", i);
+  const bool hn = tensors[6] != nullptr, hm = tensors[8] != nullptr;
+  MNRF_REQUIRE((tensors[7] != nullptr) == hn, "hash_field_create: normal_net tensors must be all set or all NULL");
+  for (int i = 9; i < 12; ++i) MNRF_REQUIRE((tensors[i] != nullptr) == hm, "hash_field_create: is_mirror_net tensors must be all set or all NULL");
+  MNRF_REQUIRE(bound > 0.f && table_floats > 0, "hash_field_create: bad bound / table size");
+  long long need = 0;
+  for (int l = 0; l < HG_LEVELS; ++l) {
+    MNRF_REQUIRE(level_size[l] > 0 && level_res[l] > 0, "hash_field_create: bad level table");
+    need = std::max(need, ((long long)level_offset[l] + level_size[l]) * 2);
+  }
+  MNRF_REQUIRE(need == table_floats, "hash_field_create: encoder.params has %lld floats, the level table needs %lld",
+               (long long)table_floats, need);
+  mnrf_field* f = new mnrf_field();
+  f->kind = 1;
+  f->has_normal = hn;
+  f->has_mirror = hm;
+  f->f32 = nullptr; f->tc = nullptr; f->t32 = nullptr;
+  f->hash_table = nullptr; f->hash_w = nullptr;
+  f->hg.bound = bound;
+  for (int l = 0; l < HG_LEVELS; ++l) {
+    f->hg.scale[l] = level_scale[l]; f->hg.res[l] = level_res[l]; f->hg.offset[l] = level_offset[l]; f->hg.size[l] = level_size[l];
+  }
+  if (cudaMalloc(&f->hash_table, sizeof(float) * (size_t)table_floats) != cudaSuccess ||
+      cudaMalloc(&f->hash_w, sizeof(float) * HW_TOTAL) != cudaSuccess) {
+    set_error("hash_field_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+    mnrf_field_destroy(f);
+    return 1;
+  }
+  if (pack_hash_field(f, tensors, table_floats, S_(stream))) { mnrf_field_destroy(f); return 1; }
+  *out = f;
+  return 0;
+}
+
 int mnrf_field_update(mnrf_field* f, const float* const* tensors, void* stream) {
   MNRF_REQUIRE(f != nullptr && tensors != nullptr, "field_update: null argument");
+  MNRF_REQUIRE(f->kind == 0, "field_update: hash-grid fields are re-created, not updated");
   MNRF_REQUIRE((tensors[T_N0_W] != nullptr) == (f->has_normal != 0) && (tensors[T_M0_W] != nullptr) == (f->has_mirror != 0),
                "field_update: head set changed");
   return pack_field(f, tensors, S_(stream));
@@ -153,6 +196,8 @@ void mnrf_field_destroy(mnrf_field* f) {
   if (f->f32) cudaFree(f->f32);
   if (f->tc) cudaFree(f->tc);
   if (f->t32) cudaFree(f->t32);
+  if (f->hash_table) cudaFree(f->hash_table);
+  if (f->hash_w) cudaFree(f->hash_w);
   delete f;
 }
 int mnrf_field_has_normal(const mnrf_field* f) { return f ? f->has_normal : 0; }
@@ -168,7 +213,7 @@ int mnrf_field_eval_rays(const mnrf_field* f, int impl, const float* rays, const
   if (n_rays == 0) return 0;
   cudaStream_t st = S_(stream);
   float* dirbias = nullptr;
-  if (!sigma_only) {
+  if (!sigma_only && f->kind == 0) {
     MNRF_CUDA_OK(cudaMallocAsync(&dirbias, sizeof(float) * (size_t)n_rays * WH, st));
     if (launch_dirbias(f, rays, n_rays, 8, 0, dirbias, st)) return 1;
   }
@@ -189,6 +234,21 @@ int mnrf_field_eval_points(const mnrf_field* f, int impl, const float* x, int B,
   if (B <= 0) return 0;
   if (geo_feat != nullptr) impl = MNRF_IMPL_FP32;  // only the fp32 kernel exports the 256-wide feature
   cudaStream_t st = S_(stream);
+  if (f->kind == 1) {
+    // hash-grid field: x (B, 3+3) = [xyz | d] (identity embeddings, R/train.py:69-70) or (B,3) when sigma_only
+    MNRF_REQUIRE(normal == nullptr && geo_feat == nullptr, "field_eval_points: hash-grid field has no analytic-normal / geo_feat export");
+    float* rawh = nullptr;
+    MNRF_CUDA_OK(cudaMallocAsync(&rawh, sizeof(float) * (size_t)B * 8, st));
+    FieldIO ioh{};
+    ioh.x = x; ioh.x_stride = sigma_only ? 3 : 6; ioh.n_points = B; ioh.S = 1; ioh.sigma_only = sigma_only; ioh.raw = rawh;
+    int rch = launch_field_hash(f, ioh, st);
+    if (rch == 0) {
+      k_unpack_raw<<<(B + 255) / 256, 256, 0, st>>>(rawh, B, sigma, sigma_only ? nullptr : rgb, sigma_only ? nullptr : is_mirror, pred_normal);
+      MNRF_LAUNCH_OK();
+    }
+    MNRF_CUDA_OK(cudaFreeAsync(rawh, st));
+    return rch;
+  }
   const int stride = sigma_only ? 3 : 3 + IN_DIR;
   float* dirbias = nullptr;
   float* raw = nullptr;
@@ -305,7 +365,7 @@ int mnrf_render_level(const mnrf_field* coarse, const mnrf_field* fine, const fl
   if (sig_only) {
     io.sigma_out = buf_c;
   } else {
-    if (launch_dirbias(coarse, rays, n, 8, 0, dirbias, st)) return 1;
+    if (coarse->kind == 0 && launch_dirbias(coarse, rays, n, 8, 0, dirbias, st)) return 1;
     io.dirbias = dirbias;
     io.raw = buf_c;
     if (cfg->compute_normal) {
@@ -328,7 +388,7 @@ int mnrf_render_level(const mnrf_field* coarse, const mnrf_field* fine, const fl
     if (launch_sample_pdf(out->z_coarse, nullptr, out->coarse.weights, Sc, 1, n, Sc, Ni, u,
                           rng->u_pdf != nullptr ? Ni : 0, out->z_fine, nullptr, nullptr, nullptr, st))
       return 1;
-    if (launch_dirbias(second, rays, n, 8, 0, dirbias, st)) return 1;
+    if (second->kind == 0 && launch_dirbias(second, rays, n, 8, 0, dirbias, st)) return 1;
     FieldIO io2{};
     io2.rays = rays; io2.z = out->z_fine; io2.n_points = n * Sf; io2.S = Sf; io2.sigma_only = 0;
     io2.dirbias = dirbias; io2.raw = buf_f;

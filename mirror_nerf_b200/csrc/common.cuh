@@ -157,7 +157,26 @@ inline F32Layout make_f32_layout() {
 
 }  // namespace mnrf
 
+namespace mnrf {
+// hash-grid field (field_hash.cu; R/models/mirror_nerf_tcnn.py): level table + packed small MLPs
+constexpr int HG_LEVELS = 16;
+struct HashGridMeta {
+  float bound;
+  float scale[HG_LEVELS];
+  int res[HG_LEVELS];
+  unsigned int offset[HG_LEVELS];  // in table entries (2 floats each)
+  unsigned int size[HG_LEVELS];
+};
+// float offsets inside the packed weight block (rows padded to multiples of 4 inputs; see field_hash.cu)
+constexpr int HW_S0 = 0, HW_S1 = 2048, HW_C0 = 3072, HW_C1 = 5120, HW_C2 = 9216, HW_N0 = 9472, HW_N1 = 10496, HW_M0 = 10752,
+              HW_M0B = 11264, HW_M2 = 11296, HW_M2B = 11328, HW_TOTAL = 11332;
+}  // namespace mnrf
+
 struct mnrf_field {
+  int kind;          // 0 = MirrorNeRF MLP field, 1 = hash-grid field
+  float* hash_table; // kind 1: device copy of encoder.params
+  float* hash_w;     // kind 1: HW_TOTAL packed floats
+  mnrf::HashGridMeta hg;
   int has_normal;
   int has_mirror;
   float* f32;        // device, mnrf::F32Layout
@@ -248,6 +267,8 @@ int launch_blend(const float* base, const float* mask, const float* child_rgb, c
                  const int* index, int n, float* rgb_out, float* rgb_reflect, float* depth_reflect, cudaStream_t st);
 
 int launch_field_fp32(const mnrf_field* f, const FieldIO& io, cudaStream_t st);
+int launch_field_hash(const mnrf_field* f, const FieldIO& io, cudaStream_t st);
+int pack_hash_field(mnrf_field* f, const float* const* tensors, long long table_floats, cudaStream_t st);
 
 // epilogue of the training GEMMs:  v = acc [+ C] [+ bias[col]] [+ rowbias[row / rb_div][col]] [+ rvec[row] * cvec[col]];  act(v)
 struct GemmEpi {

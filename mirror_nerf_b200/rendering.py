@@ -166,11 +166,17 @@ def render_rays(models, embeddings, rays, N_samples=64, use_disp=False, perturb=
     rays = _check_rays(rays)
     dev = rays.device
     n = rays.shape[0]
-    for name, want in (("xyz", 10), ("dir", 4)):
+    if "coarse" not in models:
+        raise KeyError("models must contain 'coarse'")
+    from .mirror_nerf_tcnn import is_hash_field, packed_hash_field
+    hashed = is_hash_field(models["coarse"])  # nerf_tcnn model family (BASELINE config 3): identity embeddings, [xyz | d] input
+    for name, want in (("xyz", 0 if hashed else 10), ("dir", 0 if hashed else 4)):
         emb = embeddings.get(name) if isinstance(embeddings, dict) else None
         nf = getattr(emb, "N_freqs", want)
         if nf != want:
-            raise NotImplementedError(f"embedding_{name}.N_freqs={nf}: only the reference's 10/4 frequencies are built")
+            raise NotImplementedError(f"embedding_{name}.N_freqs={nf}: the {'hash-grid' if hashed else 'MLP'} field takes "
+                                      f"N_freqs={want} (R/train.py:45-47,69-70)")
+    pack = packed_hash_field if hashed else packed_field
     if "view_dir" in kwargs:
         raise NotImplementedError("view_dir is not supported (no reference caller passes it)")
     if "coarse" not in models:
@@ -188,8 +194,11 @@ def render_rays(models, embeddings, rays, N_samples=64, use_disp=False, perturb=
         params += list(models["fine"].parameters())
     needs_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in params) or rays_in.requires_grad)
 
-    coarse = packed_field(models["coarse"])
-    fine = packed_field(models["fine"]) if (has_fine_model and not only_one_field) else None
+    if hashed and (needs_grad or compute_normal):
+        raise NotImplementedError("hash-grid field: inference with predicted normals only (compute_normal=False, "
+                                  "torch.no_grad()); analytic normals and gradients are not built for it")
+    coarse = pack(models["coarse"])
+    fine = pack(models["fine"]) if (has_fine_model and not only_one_field) else None
     # NB rendering.py:139 tests '"fine" in models' for the sigma-only shortcut
     sig_only = bool(test_time) and has_fine_model
     fine_for_lib = fine if fine is not None else (coarse if sig_only else None)

@@ -318,8 +318,12 @@ def render_rays(params, rays, N_samples=64, use_disp=False, perturb=0, noise_std
             pts = flat[i:i + chunk]
             mmc = None if mm_flat is None else mm_flat[i:i + chunk]
             xin = pts if sig_only else torch.cat([pts, dir_flat[i:i + chunk]], 1)
-            o = field_forward(p, xin, n_freqs_xyz=n_freqs_xyz, in_dir=in_dir, compute_normal=compute_normal,
-                              sigma_only=sig_only, mirror_mask=mmc, **flags)
+            if "encoder.params" in p:  # nerf_tcnn model family (oracle/hashgrid_oracle.py; identity embeddings)
+                from . import hashgrid_oracle as HG
+                o = HG.field_forward(p, xin, bound=kw.get("bound", 1.0), sigma_only=sig_only)
+            else:
+                o = field_forward(p, xin, n_freqs_xyz=n_freqs_xyz, in_dir=in_dir, compute_normal=compute_normal,
+                                  sigma_only=sig_only, mirror_mask=mmc, **flags)
             for k in acc:
                 if k in o:
                     acc[k].append(o[k])

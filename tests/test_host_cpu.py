@@ -119,3 +119,44 @@ def test_checkpoint_import_pl_prefixes(tmp_path):
     load_ckpt(m, "", "nerf_coarse")  # empty path: silently ignored like the reference
     with pytest.raises(AssertionError):
         load_ckpt(m, str(path), "nerf_missing")
+
+
+def test_hashgrid_module_mirrors_reference_state_dict_and_level_table():
+    """nerf_tcnn model family: state_dict keys/shapes of R/models/mirror_nerf_tcnn.py, tinycudann's parameter count for the
+    configuration (16 levels x 2 features, 2^19, base 16, finest 2048 -> 12,196,240), and the host level table == the oracle's."""
+    from mirror_nerf_b200.mirror_nerf_tcnn import MirrorNeRFTcnn, level_table, n_encoder_params
+    from oracle import hashgrid_oracle as H
+    assert n_encoder_params(1.0) == 12196240 == H.n_encoder_params(1.0)
+    for bound in (1.0, 2.0, 0.5):
+        assert level_table(bound) == H.level_table(bound)
+    m = MirrorNeRFTcnn(bound=1, predict_normal=True, predict_mirror_mask=True)
+    sd = m.state_dict()
+    shapes = H.param_shapes()
+    assert list(sd) == list(shapes)
+    for k, s in shapes.items():
+        assert tuple(sd[k].shape) == tuple(s), k
+    with pytest.raises(NotImplementedError):
+        MirrorNeRFTcnn(hidden_dim=128)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(2, 6), compute_normal=False)
+
+
+def test_hashgrid_oracle_properties():
+    """The restated encoder: C0-continuous across cell boundaries, level-major layout, dense levels index the table directly."""
+    from oracle import hashgrid_oracle as H
+    lv, total = H.level_table(1.0)
+    g = torch.Generator().manual_seed(0)
+    table = torch.randn(total * 2, generator=g)
+    x = torch.rand(64, 3, generator=g)
+    e0 = H.hashgrid_encode(table, x)
+    assert e0.shape == (64, 32)
+    e1 = H.hashgrid_encode(table, x + 1e-6)
+    assert float((e0 - e1).abs().max()) < 5e-2  # no jumps: |d enc| <= scale_max * |dx| * |table| ~ 2048 * 1e-6 * 4
+    # level 0 is dense (16^3 = 4096 entries): a point at the centre-offset grid node reads exactly one entry
+    scale, res, off, size = lv[0]
+    node = torch.tensor([[3, 5, 7]], dtype=torch.float32)
+    xn = (node - 0.5) / scale
+    e = H.hashgrid_encode(table, xn)
+    idx = 3 + 5 * res + 7 * res * res
+    assert torch.allclose(e[0, :2], table.view(-1, 2)[off + idx], atol=1e-5)
+    assert H.sh4(torch.tensor([[0.0, 0.0, 1.0]])).shape == (1, 16)
