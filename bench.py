@@ -204,6 +204,48 @@ def train_bench(dev, world, rank, steps, warmup):
             "loss_first": float(losses[0]), "loss_last": float(losses[-1])}
 
 
+def hash_level_bench(dev, steps):
+    """BASELINE config 3 shape: one eval render level (64+128 samples) of an 800x800 view with the hash-grid field
+    (nerf_tcnn family; synthetic table and weights).  Returns a dict (rays/s per level)."""
+    import numpy as np
+    import torch
+    from mirror_nerf_b200.mirror_nerf import Embedding
+    from mirror_nerf_b200.mirror_nerf_tcnn import MirrorNeRFTcnn
+    from mirror_nerf_b200.rendering import render_rays
+    from mirror_nerf_b200.synthetic import camera_rays
+    models = {}
+    for k, seed in (("coarse", 7), ("fine", 8)):
+        m = MirrorNeRFTcnn(bound=1, predict_normal=True, predict_mirror_mask=True)
+        g = np.random.Generator(np.random.PCG64(seed))
+        with torch.no_grad():
+            for name, p in m.named_parameters():
+                lim = 1.0 if name == "encoder.params" else 1.0 / (p.shape[-1] ** 0.5)
+                p.copy_(torch.from_numpy(g.uniform(-lim, lim, size=tuple(p.shape)).astype(np.float32)))
+            m.sigma_net[1].weight[0] *= 20.0
+        models[k] = m.to(dev).eval()
+    emb = {"xyz": Embedding(0), "dir": Embedding(0)}
+    c2w = torch.tensor([[1.0, 0, 0, 0], [0, 1.0, 0, 0], [0, 0, 1.0, 0.9]])
+    rays = camera_rays(H, W, c2w=c2w, near=0.05, far=2.0).to(dev)
+    fn = lambda: render_rays(models, emb, rays, N_SAMPLES, False, 0, 0, N_IMPORTANCE, 32768, False, test_time=True,
+                             compute_normal=False)
+    with torch.no_grad():
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    n = rays.shape[0]
+    return {"metric": "rays/sec per render level (hash-grid field, 64c+128f samples, eval, predicted normals)",
+            "value": n / ms * 1e3, "unit": "rays/s", "ms_per_level": ms, "dtype": "f32 (CUDA cores; gather-bound)",
+            "points_per_s": n * 256 / ms * 1e3, "table_read_GBps_algorithmic": n * 256 * 1024 / ms / 1e6,
+            "note": "parity unpinned: tinycudann is an un-vendored dependency of the reference (DESIGN.md 3.5)"}
+
+
 def cpu_train_rate(n_rays, threads):
     """The reference's training step (oracle port: torch CPU autograd, same loss) on the host cores."""
     import torch
@@ -353,6 +395,8 @@ def run_ours(args):
 
     if not args.no_train:
         line["train_step"] = train_bench(dev, world, rank, max(2, min(args.steps, 5)), 3)
+        if rank == 0:
+            line["hash_grid_level"] = hash_level_bench(dev, 3)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1

@@ -59,44 +59,58 @@ __device__ __forceinline__ float act_apply(float v, int act, float m) {
 // Epilogue of a 32 x 32 block held in the warp's transposition tile: lane -> (row 4*i + rsub, columns col..col+3), i = 0..7.
 // All global operands (C for accumulate, ReLU mask, per-ray term, rank-1 row factor) are fetched for four rows at a time BEFORE
 // the dependent arithmetic and stores, so that their latencies overlap instead of serialising the 8 iterations.
+// MODE: 0 = generic (every feature decided at run time), 1 = bias + ReLU (forward trunk), 2 = ReLU-mask only (normal chain,
+// dgrad, tangent pass) -- the two hot flavours are compiled without the unused operand streams.
+template <int MODE>
 __device__ __forceinline__ void nn_epi_block(const NNParams& P, uint32_t tb, long long row_base, int rsub, int c4, int col) {
   const GemmEpi& e = P.e;
+  const bool use_acc = MODE == 0 && e.accumulate, use_bias = MODE == 1 || (MODE == 0 && e.bias != nullptr);
+  const bool use_rb = MODE == 0 && e.rowbias != nullptr, use_rv = MODE == 0 && e.rvec != nullptr;
+  const int act = MODE == 1 ? 1 : (MODE == 2 ? 2 : e.act);
   float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), cv = bias;
-  if (e.bias != nullptr) bias = __ldg(reinterpret_cast<const float4*>(e.bias + col));
-  if (e.rvec != nullptr) cv = __ldg(reinterpret_cast<const float4*>(e.cvec + col));
+  if (use_bias) bias = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+  if (use_rv) cv = __ldg(reinterpret_cast<const float4*>(e.cvec + col));
+  // rows handled by this lane: row_base + rsub + 4*i; element offsets advance by 4 rows per i
+  const long long r0 = row_base + rsub;
+  float* cp = P.C + (size_t)r0 * P.ldc + col;
+  const float* mp = act == 2 ? e.mask + (size_t)r0 * e.ld_mask + col : nullptr;
+  const size_t cstep = (size_t)4 * P.ldc, mstep = (size_t)4 * e.ld_mask;
+  const int rows_left = (int)min((long long)32, P.M - row_base) - rsub;  // rows r0 + 4*i with 4*i < rows_left exist
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     float4 cin[4], mk[4], rbv[4];
     float rv[4];
-    bool ok[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int r = 4 * (4 * half + k) + rsub;
-      const long long grow = row_base + r;
-      ok[k] = grow < P.M;
+      const int i = 4 * half + k;
+      const bool ok = 4 * i < rows_left;
       cin[k] = make_float4(0.f, 0.f, 0.f, 0.f); mk[k] = cin[k]; rbv[k] = cin[k]; rv[k] = 0.f;
-      if (ok[k]) {
-        if (e.accumulate) cin[k] = *reinterpret_cast<const float4*>(P.C + (size_t)grow * P.ldc + col);
-        if (e.act == 2) mk[k] = *reinterpret_cast<const float4*>(e.mask + (size_t)grow * e.ld_mask + col);
-        if (e.rowbias != nullptr) rbv[k] = *reinterpret_cast<const float4*>(e.rowbias + (size_t)(grow / e.rb_div) * e.ld_rb + col);
-        if (e.rvec != nullptr) rv[k] = e.rvec[(size_t)grow * e.ld_rvec];
+      if (ok) {
+        if (use_acc) cin[k] = *reinterpret_cast<const float4*>(cp + i * cstep);
+        if (act == 2) mk[k] = *reinterpret_cast<const float4*>(mp + i * mstep);
+        if (use_rb) rbv[k] = *reinterpret_cast<const float4*>(e.rowbias + (size_t)((r0 + 4 * i) / e.rb_div) * e.ld_rb + col);
+        if (use_rv) rv[k] = e.rvec[(size_t)(r0 + 4 * i) * e.ld_rvec];
       }
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int r = 4 * (4 * half + k) + rsub;
+      const int i = 4 * half + k;
+      const int r = 4 * i + rsub;
       const float4 a = ld_shared_v4(tb + (uint32_t)r * 128u + (uint32_t)((c4 ^ (r & 7)) * 16));
-      float v[4] = {a.x + cin[k].x + bias.x + rbv[k].x, a.y + cin[k].y + bias.y + rbv[k].y, a.z + cin[k].z + bias.z + rbv[k].z,
-                    a.w + cin[k].w + bias.w + rbv[k].w};
-      v[0] = fmaf(rv[k], cv.x, v[0]); v[1] = fmaf(rv[k], cv.y, v[1]); v[2] = fmaf(rv[k], cv.z, v[2]); v[3] = fmaf(rv[k], cv.w, v[3]);
+      float v[4] = {a.x, a.y, a.z, a.w};
+      if (use_acc) { v[0] += cin[k].x; v[1] += cin[k].y; v[2] += cin[k].z; v[3] += cin[k].w; }
+      if (use_bias) { v[0] += bias.x; v[1] += bias.y; v[2] += bias.z; v[3] += bias.w; }
+      if (use_rb) { v[0] += rbv[k].x; v[1] += rbv[k].y; v[2] += rbv[k].z; v[3] += rbv[k].w; }
+      if (use_rv) { v[0] = fmaf(rv[k], cv.x, v[0]); v[1] = fmaf(rv[k], cv.y, v[1]); v[2] = fmaf(rv[k], cv.z, v[2]); v[3] = fmaf(rv[k], cv.w, v[3]); }
       float4 o;
-      o.x = act_apply(v[0], e.act, mk[k].x); o.y = act_apply(v[1], e.act, mk[k].y);
-      o.z = act_apply(v[2], e.act, mk[k].z); o.w = act_apply(v[3], e.act, mk[k].w);
-      if (ok[k]) *reinterpret_cast<float4*>(P.C + (size_t)(row_base + r) * P.ldc + col) = o;
+      o.x = act_apply(v[0], act, mk[k].x); o.y = act_apply(v[1], act, mk[k].y);
+      o.z = act_apply(v[2], act, mk[k].z); o.w = act_apply(v[3], act, mk[k].w);
+      if (4 * i < rows_left) *reinterpret_cast<float4*>(cp + i * cstep) = o;
     }
   }
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(NN_THREADS, 1) k_gemm_tc_nn(const NNParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -185,25 +199,34 @@ __global__ void __launch_bounds__(NN_THREADS, 1) k_gemm_tc_nn(const NNParams P) 
     const int lt = threadIdx.x - NN_LOADER_WARP0 * 32;
     const int quad = lt & 3, row0 = lt >> 2;
     const int total = my_tiles * nkc;
-    constexpr int NPF = 8;  // chunks in flight per thread (8 x 2 float4 = 64 registers)
+    constexpr int NPF = 6;  // chunks in flight per thread (6 x 2 float4 = 48 registers)
     float4 rb[NPF][2];
-    auto issue = [&](int i, float4 (&dst)[2]) {
-      const int t = i / nkc, kc = i - t * nkc;
-      const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
-      const int k = kc * 16;
-      const bool first = k < P.K0;
-      const float* base = first ? P.A0 + k : P.A1 + (k - P.K0);
-      const size_t ld = first ? (size_t)P.lda0 : (size_t)P.lda1;
+    // prefetch cursor: walks (tile, K chunk) in issue order; the two row pointers are recomputed once per tile
+    int pf_kc = 0;
+    long long pf_tile = blockIdx.x;
+    const float* pf_a0[2];
+    const float* pf_a1[2];
+    auto set_rows = [&]() {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        long long grow = tile * 128 + row0 + 64 * h;
+        long long grow = pf_tile * 128 + row0 + 64 * h;
         if (grow >= P.M) grow = P.M - 1;
-        dst[h] = (P.dbg & 1) ? make_float4(1.f, 2.f, 3.f, 4.f) : *reinterpret_cast<const float4*>(base + (size_t)grow * ld + quad * 4);
+        pf_a0[h] = P.A0 + (size_t)grow * P.lda0 + quad * 4;
+        pf_a1[h] = P.A1 != nullptr ? P.A1 + (size_t)grow * P.lda1 + quad * 4 - P.K0 : nullptr;
       }
+    };
+    set_rows();
+    auto issue = [&](float4 (&dst)[2]) {
+      const int k = pf_kc * 16;
+      const bool first = k < P.K0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        dst[h] = (P.dbg & 1) ? make_float4(1.f, 2.f, 3.f, 4.f) : *reinterpret_cast<const float4*>((first ? pf_a0[h] : pf_a1[h]) + k);
+      if (++pf_kc == nkc) { pf_kc = 0; pf_tile += gridDim.x; set_rows(); }
     };
 #pragma unroll
     for (int j = 0; j < NPF; ++j)
-      if (j < total) issue(j, rb[j]);
+      if (j < total) issue(rb[j]);
     uint32_t stage = 0, phase = 0;
     uint32_t so[2];
 #pragma unroll
@@ -227,7 +250,7 @@ __global__ void __launch_bounds__(NN_THREADS, 1) k_gemm_tc_nn(const NNParams P) 
             st_shared_v4(sa + so[h], h0, h1, h2, h3);
             st_shared_v4(sa + so[h] + NN_A_PART, l0, l1, l2, l3);
           }
-          if (i + NPF < total) issue(i + NPF, rb[j]);
+          if (i + NPF < total) issue(rb[j]);
           fence_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar(NB_A_FULL + stage));
@@ -270,7 +293,7 @@ __global__ void __launch_bounds__(NN_THREADS, 1) k_gemm_tc_nn(const NNParams P) 
         for (int j = 0; j < 8; ++j) st_shared_v4(wrow + (uint32_t)((j ^ (lane & 7)) * 16), ra[4 * j], ra[4 * j + 1], ra[4 * j + 2], ra[4 * j + 3]);
         __syncwarp();
         const int col = g * ncol + c * 32 + c4 * 4;
-        if (!(P.dbg & 8)) nn_epi_block(P, tb, row_base, rsub, c4, col);
+        if (!(P.dbg & 8)) nn_epi_block<MODE>(P, tb, row_base, rsub, c4, col);
         __syncwarp();
       }
     }
@@ -500,7 +523,9 @@ int gemm_nn_tc(const mnrf_field* f, int step, const float* A0, int lda0, int K0,
   MNRF_REQUIRE(lda0 % 4 == 0 && (A1 == nullptr || lda1 % 4 == 0) && ldc % 4 == 0, "gemm_nn_tc: leading dimensions must be multiples of 4");
   static bool attr = false;
   if (!attr) {
-    MNRF_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SM_TOTAL));
+    MNRF_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nn<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SM_TOTAL));
+    MNRF_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nn<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SM_TOTAL));
+    MNRF_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nn<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SM_TOTAL));
     attr = true;
   }
   const int sms = num_sms();
@@ -513,7 +538,10 @@ int gemm_nn_tc(const mnrf_field* f, int step, const float* A0, int lda0, int K0,
   P.e = e;
   P.dbg = g_dbg;
   const int grid = P.n_tiles < sms ? P.n_tiles : sms;
-  k_gemm_tc_nn<<<grid, NN_THREADS, NN_SM_TOTAL, st>>>(P);
+  const bool plain = !e.accumulate && e.rowbias == nullptr && e.rvec == nullptr;
+  if (plain && e.act == 1 && e.bias != nullptr) k_gemm_tc_nn<1><<<grid, NN_THREADS, NN_SM_TOTAL, st>>>(P);
+  else if (plain && e.act == 2 && e.bias == nullptr) k_gemm_tc_nn<2><<<grid, NN_THREADS, NN_SM_TOTAL, st>>>(P);
+  else k_gemm_tc_nn<0><<<grid, NN_THREADS, NN_SM_TOTAL, st>>>(P);
   MNRF_LAUNCH_OK();
   return 0;
 }
