@@ -14,6 +14,8 @@
 //
 // Per-unit cost: a 128 x 256 x 256 layer tile = 32 K8 steps x 3 passes x 128 cycles = 12.3k tensor cycles against
 // 128 KB read + 128 KB written (+128 KB mask) of HBM traffic: the unfused layer GEMMs sit at the HBM/tensor balance point.
+#include <cuda.h>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -23,7 +25,8 @@ namespace {
 using namespace tcx;
 
 // ------------------------------------------------------------------------------------------------ NN
-constexpr int NN_STAGES = 4;
+constexpr int NN_STAGES = 3;   // UMMA operand stages (A hi/lo + B hi/lo of one K16 chunk)
+constexpr int NN_RAW = 6;      // raw fp32 A chunks (128 rows x 16 columns, 8 KB) in flight behind them: TMA tensor-map loads
 // A operand: K-adjacent core matrices are LBO = 2048 + 32 bytes apart (not 2048): with the loaders' mapping (4 lanes = the four
 // 16-byte K quads of a row, 8 rows per instruction -> 64-byte runs of global memory) the padding makes the st.shared.v4
 // phases bank-conflict free.
@@ -31,13 +34,16 @@ constexpr uint32_t NN_A_LBO = 2080;
 constexpr uint32_t NN_A_PART = 4 * NN_A_LBO;   // 8320: 128 rows x 16 tf32 (padded)
 constexpr uint32_t NN_B_PART = 16384;          // up to 256 rows x 16 tf32
 constexpr uint32_t NN_STAGE = 2 * NN_A_PART + 2 * NN_B_PART;  // 49408
-constexpr uint32_t NN_SM_EPI = NN_STAGES * NN_STAGE;          // 197632: 8 epilogue warps x 4 KB transposition tiles
-constexpr uint32_t NN_SM_BAR = NN_SM_EPI + 8 * 4096;          // 230400
+constexpr uint32_t NN_SM_RAW = NN_STAGES * NN_STAGE;          // 148224: raw ring
+constexpr uint32_t NN_RAW_SLOT = 8192;
+constexpr uint32_t NN_SM_EPI = NN_SM_RAW + NN_RAW * NN_RAW_SLOT;  // 197376: 8 epilogue warps x 4 KB transposition tiles
+constexpr uint32_t NN_SM_BAR = NN_SM_EPI + 8 * 4096;          // 230144
 constexpr uint32_t NN_SM_TOTAL = NN_SM_BAR + 256;
-constexpr int NN_THREADS = 576;
-constexpr int NN_LOADER_WARP0 = 2, NN_EPI_WARP0 = 10;
+constexpr int NN_THREADS = 640;  // warp 0 B producer | 1 MMA | 2 A producer (TMA) | 3 idle | 4..11 converters | 12..19 epilogue
+constexpr int NN_LOADER_WARP0 = 4, NN_EPI_WARP0 = 12;
 // barrier slots
-constexpr int NB_A_FULL = 0, NB_B_FULL = 4, NB_EMPTY = 8, NB_ACC_FULL = 12, NB_ACC_EMPTY = 14, NB_TMEM_SLOT = 16;
+constexpr int NB_A_FULL = 0, NB_B_FULL = 4, NB_EMPTY = 8, NB_ACC_FULL = 12, NB_ACC_EMPTY = 14, NB_TMEM_SLOT = 16, NB_RAW_FULL = 18,
+              NB_RAW_EMPTY = 24;
 
 struct NNParams {
   const float* A0; int lda0; int K0;
@@ -111,7 +117,8 @@ __device__ __forceinline__ void nn_epi_block(const NNParams& P, uint32_t tb, lon
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(NN_THREADS, 1) k_gemm_tc_nn(const NNParams P) {
+__global__ void __launch_bounds__(NN_THREADS, 1)
+k_gemm_tc_nn(const NNParams P, const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -125,6 +132,7 @@ __global__ void __launch_bounds__(NN_THREADS, 1) k_gemm_tc_nn(const NNParams P) 
     if (sbase & 127u) { printf("mnrf train_tc: unaligned dynamic smem base %u\n", sbase); __trap(); }
     for (int i = 0; i < NN_STAGES; ++i) { mbar_init(bar(NB_A_FULL + i), 8); mbar_init(bar(NB_B_FULL + i), 1); mbar_init(bar(NB_EMPTY + i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar(NB_ACC_FULL + i), 1); mbar_init(bar(NB_ACC_EMPTY + i), 8); }
+    for (int i = 0; i < NN_RAW; ++i) { mbar_init(bar(NB_RAW_FULL + i), 1); mbar_init(bar(NB_RAW_EMPTY + i), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -193,70 +201,62 @@ __global__ void __launch_bounds__(NN_THREADS, 1) k_gemm_tc_nn(const NNParams P) 
         tc_commit(bar(NB_ACC_FULL + buf));
       }
     }
+  } else if (warp == 2) {
+    // ------------------------------ A producer: one tensor-map load (128 rows x 16 fp32 columns) per K chunk ------------------------------
+    if (elect_one()) {
+      uint32_t slot = 0, phase = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        const int row = (int)(((long long)blockIdx.x + (long long)t * gridDim.x) * 128);
+        for (int kc = 0; kc < nkc; ++kc) {
+          mbar_wait(bar(NB_RAW_EMPTY + slot), phase ^ 1u);
+          const uint32_t fb = bar(NB_RAW_FULL + slot);
+          const int k = kc * 16;
+          mbar_expect_tx(fb, NN_RAW_SLOT);
+          if (P.dbg & 1) {
+            asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(fb), "r"(NN_RAW_SLOT) : "memory");
+          } else if (k < P.K0) {
+            tma_load_2d(sbase + NN_SM_RAW + slot * NN_RAW_SLOT, &tmA0, k, row, fb);   // rows past M are zero-filled by the TMA unit
+          } else {
+            tma_load_2d(sbase + NN_SM_RAW + slot * NN_RAW_SLOT, &tmA1, k - P.K0, row, fb);
+          }
+          if (++slot == NN_RAW) { slot = 0; phase ^= 1u; }
+        }
+      }
+    }
   } else if (warp >= NN_LOADER_WARP0 && warp < NN_EPI_WARP0) {
-    // ------------------------------ A loaders ------------------------------
-    // thread -> K quad (lt & 3) of rows (lt >> 2) and (lt >> 2) + 64: a warp instruction reads 8 rows x 64 contiguous bytes
+    // ------------------------------ A converters: raw fp32 chunk -> tf32 hi/lo UMMA core matrices ------------------------------
+    // thread -> K quad (lt & 3) of rows (lt >> 2) and (lt >> 2) + 64 (raw chunk: [128 rows][16 floats], 64 bytes per row)
     const int lt = threadIdx.x - NN_LOADER_WARP0 * 32;
     const int quad = lt & 3, row0 = lt >> 2;
     const int total = my_tiles * nkc;
-    constexpr int NPF = 6;  // chunks in flight per thread (6 x 2 float4 = 48 registers)
-    float4 rb[NPF][2];
-    // prefetch cursor: walks (tile, K chunk) in issue order; the two row pointers are recomputed once per tile
-    int pf_kc = 0;
-    long long pf_tile = blockIdx.x;
-    const float* pf_a0[2];
-    const float* pf_a1[2];
-    auto set_rows = [&]() {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        long long grow = pf_tile * 128 + row0 + 64 * h;
-        if (grow >= P.M) grow = P.M - 1;
-        pf_a0[h] = P.A0 + (size_t)grow * P.lda0 + quad * 4;
-        pf_a1[h] = P.A1 != nullptr ? P.A1 + (size_t)grow * P.lda1 + quad * 4 - P.K0 : nullptr;
-      }
-    };
-    set_rows();
-    auto issue = [&](float4 (&dst)[2]) {
-      const int k = pf_kc * 16;
-      const bool first = k < P.K0;
-#pragma unroll
-      for (int h = 0; h < 2; ++h)
-        dst[h] = (P.dbg & 1) ? make_float4(1.f, 2.f, 3.f, 4.f) : *reinterpret_cast<const float4*>((first ? pf_a0[h] : pf_a1[h]) + k);
-      if (++pf_kc == nkc) { pf_kc = 0; pf_tile += gridDim.x; set_rows(); }
-    };
-#pragma unroll
-    for (int j = 0; j < NPF; ++j)
-      if (j < total) issue(rb[j]);
-    uint32_t stage = 0, phase = 0;
-    uint32_t so[2];
+    uint32_t stage = 0, phase = 0, slot = 0, rphase = 0;
+    uint32_t so[2], ro[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int row = row0 + 64 * h;
       so[h] = (uint32_t)quad * NN_A_LBO + (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u;
+      ro[h] = (uint32_t)row * 64u + (uint32_t)quad * 16u;
     }
-    for (int i0 = 0; i0 < total; i0 += NPF) {
-#pragma unroll
-      for (int j = 0; j < NPF; ++j) {
-        const int i = i0 + j;
-        if (i < total) {
-          mbar_wait(bar(NB_EMPTY + stage), phase ^ 1u);
-          const uint32_t sa = sbase + stage * NN_STAGE;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const float4 v = rb[j][h];
-            if (P.dbg & 2) continue;
-            uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
-            split_tf32(v.x, h0, l0); split_tf32(v.y, h1, l1); split_tf32(v.z, h2, l2); split_tf32(v.w, h3, l3);
-            st_shared_v4(sa + so[h], h0, h1, h2, h3);
-            st_shared_v4(sa + so[h] + NN_A_PART, l0, l1, l2, l3);
-          }
-          if (i + NPF < total) issue(rb[j]);
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar(NB_A_FULL + stage));
-          if (++stage == NN_STAGES) { stage = 0; phase ^= 1u; }
-        }
+    for (int i = 0; i < total; ++i) {
+      mbar_wait(bar(NB_RAW_FULL + slot), rphase);
+      const uint32_t rs = sbase + NN_SM_RAW + slot * NN_RAW_SLOT;
+      const float4 v0 = ld_shared_v4(rs + ro[0]), v1 = ld_shared_v4(rs + ro[1]);
+      mbar_wait(bar(NB_EMPTY + stage), phase ^ 1u);
+      const uint32_t sa = sbase + stage * NN_STAGE;
+      if (!(P.dbg & 2)) {
+        uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+        split_tf32(v0.x, h0, l0); split_tf32(v0.y, h1, l1); split_tf32(v0.z, h2, l2); split_tf32(v0.w, h3, l3);
+        st_shared_v4(sa + so[0], h0, h1, h2, h3);
+        st_shared_v4(sa + so[0] + NN_A_PART, l0, l1, l2, l3);
+        split_tf32(v1.x, h0, l0); split_tf32(v1.y, h1, l1); split_tf32(v1.z, h2, l2); split_tf32(v1.w, h3, l3);
+        st_shared_v4(sa + so[1], h0, h1, h2, h3);
+        st_shared_v4(sa + so[1] + NN_A_PART, l0, l1, l2, l3);
       }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(bar(NB_A_FULL + stage)); mbar_arrive(bar(NB_RAW_EMPTY + slot)); }
+      if (++stage == NN_STAGES) { stage = 0; phase ^= 1u; }
+      if (++slot == NN_RAW) { slot = 0; rphase ^= 1u; }
     }
   } else if (warp >= NN_EPI_WARP0) {
     // ------------------------------ epilogue ------------------------------
@@ -503,6 +503,35 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tc_tn(const TNParams P) 
 }
 
 int g_dbg = 0;
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// fp32 matrix [rows, cols] with row stride ld (floats) -> boxes of 128 rows x 16 columns, no swizzle, zero fill outside
+int make_a_map(CUtensorMap* m, const float* A, int rows, int cols, int ld) {
+  EncodeTiledFn enc = encode_tiled();
+  MNRF_REQUIRE(enc != nullptr, "gemm_nn_tc: cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
+  const cuuint32_t box[2] = {16, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(A), gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MNRF_REQUIRE(r == CUDA_SUCCESS, "gemm_nn_tc: cuTensorMapEncodeTiled failed (%d) for a %d x %d matrix, ld %d", (int)r, rows, cols, ld);
+  return 0;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -538,10 +567,14 @@ int gemm_nn_tc(const mnrf_field* f, int step, const float* A0, int lda0, int K0,
   P.e = e;
   P.dbg = g_dbg;
   const int grid = P.n_tiles < sms ? P.n_tiles : sms;
+  CUtensorMap m0, m1;
+  MNRF_REQUIRE(((uintptr_t)A0 & 15) == 0 && (A1 == nullptr || ((uintptr_t)A1 & 15) == 0), "gemm_nn_tc: A must be 16-byte aligned");
+  if (make_a_map(&m0, A0, M, K0, lda0)) return 2;
+  if (K0 < K) { if (make_a_map(&m1, A1, M, K - K0, lda1)) return 2; } else m1 = m0;
   const bool plain = !e.accumulate && e.rowbias == nullptr && e.rvec == nullptr;
-  if (plain && e.act == 1 && e.bias != nullptr) k_gemm_tc_nn<1><<<grid, NN_THREADS, NN_SM_TOTAL, st>>>(P);
-  else if (plain && e.act == 2 && e.bias == nullptr) k_gemm_tc_nn<2><<<grid, NN_THREADS, NN_SM_TOTAL, st>>>(P);
-  else k_gemm_tc_nn<0><<<grid, NN_THREADS, NN_SM_TOTAL, st>>>(P);
+  if (plain && e.act == 1 && e.bias != nullptr) k_gemm_tc_nn<1><<<grid, NN_THREADS, NN_SM_TOTAL, st>>>(P, m0, m1);
+  else if (plain && e.act == 2 && e.bias == nullptr) k_gemm_tc_nn<2><<<grid, NN_THREADS, NN_SM_TOTAL, st>>>(P, m0, m1);
+  else k_gemm_tc_nn<0><<<grid, NN_THREADS, NN_SM_TOTAL, st>>>(P, m0, m1);
   MNRF_LAUNCH_OK();
   return 0;
 }
