@@ -26,9 +26,13 @@ torch.cuda.synchronize()
 l0 = _lib.launch_count()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 K = 3
+t0 = time.perf_counter()
 e0.record()
 for i in range(K): step()
-e1.record(); torch.cuda.synchronize()
+e1.record()
+t_host = (time.perf_counter() - t0) / K * 1e3
+torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / K
 flops = n * 256 * 6.9e6
+print(f"host enqueue time per step: {t_host:.1f} ms")
 print(f"train step {n} rays: {ms:.1f} ms  {n / ms * 1e3:.0f} rays/s  ~{flops / ms / 1e9:.1f} TFLOP/s  launches/step {(_lib.launch_count() - l0) / K:.0f}  peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB")
