@@ -287,8 +287,9 @@ struct GemmEpi {
 int gemm_nn_tc(const mnrf_field* f, int step, const float* A0, int lda0, int K0, const float* A1, int lda1, float* C,
                int ldc, int M, const GemmEpi& e, cudaStream_t st);
 // Wg[NA rows][col0 + (0..valid)] += A[P,NA]^T B[P,NB] on the tensor cores (3x tf32 split), NA in {128,256}, NB in {64,128,256}
+// colsum_out (optional): colsum_out[f] += sum_p A[p][f], the bias gradient, fused into the same pass over A
 int gemm_tn_tc(const float* A, int lda, int NA, const float* B, int ldb, int NB, float* Wg, int ldw, int col0, int valid,
-               int P, cudaStream_t st);
+               int P, float* colsum_out, cudaStream_t st);
 
 void set_train_tc_debug(int flags);
 

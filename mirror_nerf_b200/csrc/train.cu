@@ -948,9 +948,11 @@ int gemm_w(const mnrf_field* f, int step, const float* A0, int lda0, int K0, con
   return gemm_nn(A1, lda1, B1, ldb, C, ldc, P, N, K - K0, e1, st);
 }
 
+// weight gradient Wg += A^T B; bias_g (optional) += column sums of A (fused into the tensor-core kernel's pass over A)
 int gemm_g(const float* A, int lda, int NA, const float* B, int ldb, int NB, float* Wg, int ldw, int col0, int valid, int P,
-           cudaStream_t st) {
-  if (use_tc()) return gemm_tn_tc(A, lda, NA, B, ldb, NB, Wg, ldw, col0, valid, P, st);
+           cudaStream_t st, float* bias_g = nullptr) {
+  if (use_tc()) return gemm_tn_tc(A, lda, NA, B, ldb, NB, Wg, ldw, col0, valid, P, bias_g, st);
+  if (bias_g != nullptr && colsum(A, lda, P, NA, bias_g, st)) return 1;
   return gemm_tn(A, lda, NA, B, ldb, NB, Wg, ldw, col0, valid, P, st);
 }
 
@@ -1077,8 +1079,7 @@ int train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, const
   MNRF_LAUNCH_OK();
 
   // 3. colour branch: dir layer and final linear
-  if (colsum(b + B.dd1, WH, P, WH, gt[T_DIR_B], st)) return 1;
-  if (gemm_g(b + B.dd1, WH, WH, w + L.f, W, W, gt[T_DIR_W], W + IN_DIR, 0, W, P, st)) return 1;
+  if (gemm_g(b + B.dd1, WH, WH, w + L.f, W, W, gt[T_DIR_W], W + IN_DIR, 0, W, P, st, gt[T_DIR_B])) return 1;
   k_train_sum_samples<<<n, WH, 0, st>>>(b + B.dd1, S, b + B.rsum);
   MNRF_LAUNCH_OK();
   k_train_dir_pe<<<(n + 127) / 128, 128, 0, st>>>(rays, n, b + B.dirpe);
@@ -1088,16 +1089,13 @@ int train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, const
     GemmEpi e;  // dF = dD1pre * W_dir[:, :256]
     if (gemm_w(f, 21, b + B.dd1, WH, WH, nullptr, 0, b + B.df, W, P, e, st)) return 1;
   }
-  if (colsum(b + B.df, W, P, W, gt[T_FINAL_B], st)) return 1;
-  if (gemm_g(b + B.df, W, W, H[7], W, W, gt[T_FINAL_W], W, 0, W, P, st)) return 1;
+  if (gemm_g(b + B.df, W, W, H[7], W, W, gt[T_FINAL_W], W, 0, W, P, st, gt[T_FINAL_B])) return 1;
   // 4. normal / mirror head first layers
   if (hn) {
-    if (colsum(b + B.dn1, WH, P, WH, gt[T_N0_B], st)) return 1;
-    if (gemm_g(b + B.dn1, WH, WH, H[7], W, W, gt[T_N0_W], W, 0, W, P, st)) return 1;
+    if (gemm_g(b + B.dn1, WH, WH, H[7], W, W, gt[T_N0_W], W, 0, W, P, st, gt[T_N0_B])) return 1;
   }
   if (hm) {
-    if (colsum(b + B.dm1, WH, P, WH, gt[T_M0_B], st)) return 1;
-    if (gemm_g(b + B.dm1, WH, WH, H[7], W, W, gt[T_M0_W], W, 0, W, P, st)) return 1;
+    if (gemm_g(b + B.dm1, WH, WH, H[7], W, W, gt[T_M0_W], W, 0, W, P, st, gt[T_M0_B])) return 1;
   }
   // 5. dH8 = dF W_final + [dN1 W_n0] + [dM1 W_m0] + d sigma (x) w_sigma, then * relu'(h8) -> dZ8
   const bool use_n = hn && !cfg.detach_density_for_normal_loss;
@@ -1128,14 +1126,13 @@ int train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, const
   // 6. trunk backward
   for (int l = 7; l >= 0; --l) {
     // bias and weight gradients of layer l (0-based) from dZ = dL/dz_l
-    if (colsum(dZ, W, P, W, gt[2 * l + 1], st)) return 1;
     if (l == 0) {
-      if (gemm_g(dZ, W, W, PE, 64, 64, gt[0], IN_XYZ, 0, IN_XYZ, P, st)) return 1;
+      if (gemm_g(dZ, W, W, PE, 64, 64, gt[0], IN_XYZ, 0, IN_XYZ, P, st, gt[1])) return 1;
     } else if (l == 4) {
-      if (gemm_g(dZ, W, W, PE, 64, 64, gt[8], IN_XYZ + W, 0, IN_XYZ, P, st)) return 1;
+      if (gemm_g(dZ, W, W, PE, 64, 64, gt[8], IN_XYZ + W, 0, IN_XYZ, P, st, gt[9])) return 1;
       if (gemm_g(dZ, W, W, H[3], W, W, gt[8], IN_XYZ + W, IN_XYZ, W, P, st)) return 1;
     } else {
-      if (gemm_g(dZ, W, W, H[l - 1], W, W, gt[2 * l], W, 0, W, P, st)) return 1;
+      if (gemm_g(dZ, W, W, H[l - 1], W, W, gt[2 * l], W, 0, W, P, st, gt[2 * l + 1])) return 1;
     }
     if (grad_rays != nullptr && (l == 4 || l == 0)) {  // dL/dPE = dZ_5 W_5[:, :63] + dZ_1 W_1
       GemmEpi e;

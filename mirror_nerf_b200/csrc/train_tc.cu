@@ -329,6 +329,7 @@ struct TNParams {
   const float* B; int ldb; int NB;
   float* Wg; int ldw; int col0; int valid;
   int P; int rows_per_cta;
+  float* colsum;  // optional: colsum[f] += sum_p A[p][f] (bias gradient, fused into the operand-A converters)
   int dbg;  // bring-up: 1 = no global loads, 2 = no conversion/stores, 4 = no MMAs, 8 = no flush
 };
 
@@ -444,6 +445,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tc_tn(const TNParams P) 
     };
     uint32_t stage = 0, phase = 0, slot = 0, rphase = 0;
     (void)X; (void)ldx;
+    float cs[4] = {0.f, 0.f, 0.f, 0.f};  // column sums of operand A over this thread's points
     for (int c = 0; c < nchunks; ++c) {
       const int p0 = p_begin + c * 16 + 4 * j;
       mbar_wait(bar(TB_RAW_FULL + slot), rphase);
@@ -452,6 +454,10 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tc_tn(const TNParams P) 
       for (int i = 0; i < 4; ++i)
         x[i] = (on && p0 + i < p_end && !(P.dbg & 1)) ? ld_shared_v4(sbase + TN_SM_RAW + slot * TN_RAW_SLOT + raw_off + (uint32_t)(i * NX) * 4u)
                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!is_b && P.colsum != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { cs[0] += x[i].x; cs[1] += x[i].y; cs[2] += x[i].z; cs[3] += x[i].w; }
+      }
       mbar_wait(bar(TB_EMPTY + stage), phase ^ 1u);
       if (on && !(P.dbg & 2)) put(sbase + stage * TN_STAGE + part0, x);
       fence_async_smem();
@@ -459,6 +465,10 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tc_tn(const TNParams P) 
       if (lane == 0) { mbar_arrive(bar(TB_FULL + stage)); mbar_arrive(bar(TB_RAW_EMPTY + slot)); }
       if (++stage == TN_STAGES) { stage = 0; phase ^= 1u; }
       if (++slot == TN_RAW) { slot = 0; rphase ^= 1u; }
+    }
+    if (!is_b && on && P.colsum != nullptr) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) atomicAdd(P.colsum + 4 * fq + c, cs[c]);
     }
     // epilogue (same 16 warps): flush the dW tile with reductions into global memory.  The MT x NB accumulator columns are split
     // into four column groups (one per set of 4 warps with distinct TMEM lane quarters).
@@ -580,7 +590,7 @@ int gemm_nn_tc(const mnrf_field* f, int step, const float* A0, int lda0, int K0,
 }
 
 int gemm_tn_tc(const float* A, int lda, int NA, const float* B, int ldb, int NB, float* Wg, int ldw, int col0, int valid,
-               int Pn, cudaStream_t st) {
+               int Pn, float* colsum_out, cudaStream_t st) {
   if (Wg == nullptr || Pn <= 0) return 0;
   MNRF_REQUIRE((NA == 128 || NA == 256) && (NB == 64 || NB == 128 || NB == 256), "gemm_tn_tc: bad shape %d x %d", NA, NB);
   MNRF_REQUIRE(lda == NA && ldb == NB, "gemm_tn_tc: operands must be contiguous (lda == NA, ldb == NB): their chunks are bulk-copied");
@@ -598,6 +608,7 @@ int gemm_tn_tc(const float* A, int lda, int NA, const float* B, int ldb, int NB,
   rows = ((rows + 15) / 16) * 16;
   if (rows < 256) rows = 256;  // small problems: fewer CTAs, fewer atomics
   P.rows_per_cta = rows;
+  P.colsum = colsum_out;
   P.dbg = g_dbg;
   const int grid = (Pn + rows - 1) / rows;
   k_gemm_tc_tn<<<grid, TN_THREADS, TN_SM_TOTAL, st>>>(P);
