@@ -368,6 +368,13 @@ def run_ours(args):
     if peak is None:
         peak, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)"
     achieved = (k_fl.value / 1e12) / (k_ms.value * 1e-3) if k_ms.value > 0 else None
+    # DRAM bytes per launch of the dominant kernel: from the committed ncu capture of this same command (not measurable live)
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_v3_field_tc_traffic.json")))
+        traffic, traffic_src = tj["dram_bytes_per_launch_avg"], tj["source"]
+    except Exception:
+        pass
     mma_per_mac = 3 if args.field_impl == "tc3" else 1
 
     line = {
@@ -385,7 +392,8 @@ def run_ours(args):
                 "steps": e2e_steps},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": (achieved / peak if achieved else None), "traffic": None, "peak_source": peak_src,
+                     "frac": (achieved / peak if achieved else None), "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write)",
+                     "traffic_source": traffic_src, "peak_source": peak_src,
                      "kernel": "k_field_tc", "kernel_launches": int(k_n.value), "kernel_ms": k_ms.value,
                      "kernel_share_of_step": k_ms.value / ms_total if ms_total else None,
                      "flops_basis": "algorithmic 2*MAC of the reference layers (SURVEY.md 8d); the kernel issues "
