@@ -255,7 +255,7 @@ def test_training_loop_reduces_loss_and_repacks_weights():
         loss = ((r["rgb_fine"] - target) ** 2).mean() + ((r["rgb_coarse"] - target) ** 2).mean() + 1e-4 * r["normal_dif_fine"].mean()
         loss.backward()
         ddp.step()
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
     assert losses[-1] < 0.9 * losses[0], losses
     with torch.no_grad():
         after = render_rays(models, emb, rays, 64, False, 0, 0, 128, 32768, False, test_time=True, compute_normal=False)["rgb_fine"]
@@ -352,3 +352,49 @@ def test_training_recursion_gradients_through_secondary_rays():
     s = err_stats(got["rgb_fine"].detach().cpu(), want["rgb_fine"].detach())
     assert s["median"] <= 1e-4 and s["frac"] <= 0.1, fmt_stats("rgb_fine (1 bounce)", s)
     _grad_compare(models, params, cos_min=None, norm_tol=None, whole_cos_min=0.995)
+
+
+def test_train_full_size_engines_agree_and_gradients_are_linear():
+    """BASELINE config-5 size (4096 rays x (64+128) samples, analytic normals), size-independent properties:
+    (i) the tcgen05 tf32x3 GEMM engine and the fp32 CUDA-core twin produce the same gradients (cosine >= 0.9999 per large tensor);
+    (ii) backward is linear in the cotangent: doubling the loss doubles every gradient (relative 1e-3; atomics reorder sums)."""
+    import ctypes as C
+    from mirror_nerf_b200 import _lib
+    from mirror_nerf_b200.rendering import render_rays
+    from mirror_nerf_b200.synthetic import random_rays
+    lib = _lib.load()
+    sds = _smooth_sds()
+    n = 4096
+    rays = random_rays(n, seed=31).cuda()
+    g = torch.Generator().manual_seed(2)
+    rng = {k: v.cuda() for k, v in _rng(n).items()}
+    target = torch.rand(n, 3, generator=g).cuda()
+    args = (64, False, 1.0, 1.0, 128, 32768, False)
+
+    def grads(engine, scale):
+        _lib.check(lib.mnrf_train_set_gemm(engine))
+        models, emb = _models(sds)
+        r = render_rays(models, emb, rays, *args, rng=rng, test_time=False, compute_normal=True)
+        loss = sum(((r[f"rgb_{t}"] - target) ** 2).mean() + 1e-2 * r[f"normal_dif_{t}"].mean() + r[f"mirror_mask_{t}"].mean()
+                   + 1e-2 * (r[f"normal_{t}"] * r[f"weights_{t}"].unsqueeze(-1)).sum(1).pow(2).mean() for t in ("coarse", "fine"))
+        (scale * loss).backward()
+        return {f"{t}.{k}": p.grad.double() for t, m in models.items() for k, p in m.named_parameters()}, float(loss.detach())
+
+    try:
+        g_tc, l_tc = grads(1, 1.0)
+        g_tc2, _ = grads(1, 2.0)
+        g_simt, l_simt = grads(0, 1.0)
+    finally:
+        lib.mnrf_train_set_gemm(1)
+    assert abs(l_tc - l_simt) <= 1e-4 * abs(l_simt), (l_tc, l_simt)
+    worst = 1.0
+    for k in g_tc:
+        a, b, a2 = g_tc[k].flatten(), g_simt[k].flatten(), g_tc2[k].flatten()
+        if float(b.norm()) < 1e-12:
+            continue
+        cos = float((a * b).sum() / (a.norm() * b.norm()))
+        worst = min(worst, cos)
+        if a.numel() >= 256:
+            assert cos >= 0.9999, (k, cos)
+        assert float((a2 - 2 * a).norm()) <= 1e-3 * float((2 * a).norm()) + 1e-12, k
+    print(f"full-size engine agreement: worst per-tensor cosine {worst:.6f}")
