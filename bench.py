@@ -283,7 +283,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: stdout carries exactly one JSON line
+        # stdout carries exactly one JSON line: NCCL's banner / debug lines (printed to stdout at NCCL_DEBUG >= VERSION) go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
