@@ -123,7 +123,7 @@ def run_reference(args):
                              "sample": f"{n} rays x 2 levels per step, {args.steps} steps (oracle port of the "
                                        "reference's torch CPU path; /root/reference cannot travel to the GPU box)"},
             "e2e": {"value": rate, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 TRAIN_RAYS = 4096             # BASELINE config 5: 4096-ray batches (per process, PL semantics: R/train.py:368-375)
@@ -283,8 +283,6 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries exactly one JSON line: NCCL's banner / debug lines (printed to stdout at NCCL_DEBUG >= VERSION) go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
@@ -422,13 +420,34 @@ def run_ours(args):
                 "value": cpu_train_rate(128, threads), "unit": "rays/s", "cores": threads, "kind": "port",
                 "sample": "one 128-ray train step (forward + backward) of the oracle port on the host cores"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line, but libraries write there too (NCCL prints its version banner to stdout with
+    printf whenever NCCL_DEBUG >= VERSION is set in the environment): keep a private duplicate of fd 1 for the JSON line and point
+    fd 1 at stderr for everything else in this process."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -125,7 +125,7 @@ def test_train_gradients_adversarial_scene():
 
 
 @pytest.mark.parametrize("variant", ["no_normal_grad", "white_back_disp", "coarse_only", "one_field", "no_heads",
-                                     "detach_mask", "detach_normal", "detach_outside_mirror"])
+                                     "detach_mask", "detach_normal", "detach_outside_mirror", "odd_sizes"])
 def test_train_gradient_variants(variant):
     sds = _smooth_sds()
     args = (64, False, 1.0, 1.0, 128, 32768, False)
@@ -147,6 +147,9 @@ def test_train_gradient_variants(variant):
         kw["detach_density_for_mask_loss"] = True
     elif variant == "detach_normal":
         kw["detach_density_for_normal_loss"] = True
+    elif variant == "odd_sizes":  # 7 rays x (40 + 25) samples: point counts that are not multiples of 16 / 128
+        args = (40, False, 1.0, 1.0, 25, 32768, False)
+        n = 7
     elif variant == "detach_outside_mirror":
         g = torch.Generator().manual_seed(9)
         kw.update(detach_density_outside_mirror_for_mask_loss=True,
@@ -155,7 +158,7 @@ def test_train_gradient_variants(variant):
     from mirror_nerf_b200.synthetic import random_rays
     from oracle import mirror_nerf_oracle as O
     rays = random_rays(n, seed=4)
-    rng = _rng(n, 64, args[4] if args[4] else 1)
+    rng = _rng(n, args[0], args[4] if args[4] else 1)
     params = {t: {k: v.clone().requires_grad_(True) for k, v in sd.items()} for t, sd in sds.items()}
     want = O.render_rays(params, rays, *args, rng=rng, **kw)
     _loss(want, rays[:, 3:6], 1).backward()
