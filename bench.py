@@ -400,6 +400,20 @@ def run_ours(args):
                      "tensor_pipe_flops_frac": (achieved * mma_per_mac / peak if achieved else None)},
     }
 
+    if args.config4:
+        # BASELINE config 4: 2 reflection bounces + roughness cone (8 jittered reflected rays = trace_ray_times 7), ray-parallel
+        def step4():
+            return render_rays_recursive(models, emb, rays_dev, N_SAMPLES, False, 0, 0, N_IMPORTANCE, 32768, False,
+                                         max_recursive_level=2, normal_noise_std=0.05, trace_ray_times=7, **kw)
+        with torch.no_grad():
+            l0 = _lib.launch_count()
+            step4()
+            per_step = _lib.launch_count() - l0
+            ms4 = timed(step4, 2)
+        line["config4"] = {"metric": "rays/sec (64c+128f samples, 2 bounces + roughness cone of 8 jittered reflections)",
+                           "value": world * n * 2 / (ms4 * 1e-3), "unit": "rays/s", "ms_per_step": ms4 / 2,
+                           "gpu_launches_per_step": per_step, "normal_noise_std": 0.05, "trace_ray_times": 7}
+
     if not args.no_train:
         line["train_step"] = train_bench(dev, world, rank, max(2, min(args.steps, 5)), 3)
         if rank == 0:
@@ -456,6 +470,7 @@ def main():
     ap.add_argument("--field-impl", default="tc3", choices=["tc3", "tc1"])
     ap.add_argument("--ref-rays", type=int, default=2048, help="rays per step of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config4", action="store_true", help="also time BASELINE config 4 (2 bounces + roughness cone)")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary train-step measurement (config 5)")
     args = ap.parse_args()
     if args.impl == "reference":
