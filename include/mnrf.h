@@ -247,9 +247,11 @@ int mnrf_train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, 
                         int64_t ws_bwd_bytes, const mnrf_train_grads* grads, const float* ray_detach_mirror,
                         float* const* grad_tensors, const float* depth, float* grad_rays, void* stream);
 
-/* GEMM engine of the training path: 1 (default) = tcgen05 tf32 3x-split kernels (train_tc.cu), 0 = fp32 CUDA-core kernels
- * (verification twin).  The environment variable MNRF_TRAIN_GEMM=simt selects 0 at first use. */
-int mnrf_train_set_gemm(int tensor_cores);
+/* GEMM engine of the training path: 1 (default, parity mode) = tcgen05 tf32 3x-split kernels (train_tc.cu, fp32-grade products);
+ * 0 = fp32 CUDA-core kernels (verification twin); 2 = tcgen05 single tf32 pass (speed mode: 10-bit mantissa operands, what
+ * torch.backends.cuda.matmul.allow_tf32 = True would do -- NOT the reference's fp32 arithmetic).  The environment variable
+ * MNRF_TRAIN_GEMM = simt | tf32 selects 0 | 2 at first use. */
+int mnrf_train_set_gemm(int engine);
 
 /* Bring-up aid: milliseconds per launch of one training GEMM on synthetic operands (kind 0 = layer GEMM `step` over P rows,
  * kind 1 = 256x256 weight-gradient GEMM over P rows; engine as above; dbg = train_tc.cu debug bits, 0 for a real run). */

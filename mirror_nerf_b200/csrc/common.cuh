@@ -292,6 +292,7 @@ int gemm_tn_tc(const float* A, int lda, int NA, const float* B, int ldb, int NB,
                int P, float* colsum_out, cudaStream_t st);
 
 void set_train_tc_debug(int flags);
+void set_train_tc_one_pass(int on);
 
 // training path (train.cu): one field + compositor pass with saved activations, and its backward
 int64_t train_fwd_workspace_bytes(int n, int S, int compute_normal);

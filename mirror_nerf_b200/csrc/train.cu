@@ -906,7 +906,8 @@ int g_engine = -1;
 bool use_tc() {
   if (g_engine < 0) {
     const char* e = getenv("MNRF_TRAIN_GEMM");
-    g_engine = (e != nullptr && strcmp(e, "simt") == 0) ? 0 : 1;
+    g_engine = (e != nullptr && strcmp(e, "simt") == 0) ? 0 : ((e != nullptr && strcmp(e, "tf32") == 0) ? 2 : 1);
+    set_train_tc_one_pass(g_engine == 2);
   }
   return g_engine != 0;
 }
@@ -1247,6 +1248,7 @@ int mnrf_debug_gemm_bench(const mnrf_field* f, int kind, int step, int P, int en
   MNRF_CUDA_OK(cudaMemset(Wg, 0, sizeof(float) * W * W));
   const int saved = g_engine;
   g_engine = engine;
+  set_train_tc_one_pass(engine == 2);
   set_train_tc_debug(dbg);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -1270,13 +1272,16 @@ int mnrf_debug_gemm_bench(const mnrf_field* f, int kind, int step, int P, int en
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   set_train_tc_debug(0);
   g_engine = saved;
+  set_train_tc_one_pass(saved == 2);
   cudaFree(A); cudaFree(C); cudaFree(Wg);
   if (err != cudaSuccess) { set_error("gemm_bench: %s", cudaGetErrorString(err)); return 1; }
   return rc;
 }
 
-int mnrf_train_set_gemm(int tensor_cores) {
-  g_engine = tensor_cores ? 1 : 0;
+int mnrf_train_set_gemm(int engine) {
+  MNRF_REQUIRE(engine >= 0 && engine <= 2, "train_set_gemm: engine must be 0 (CUDA cores), 1 (tf32 x3) or 2 (tf32 x1)");
+  g_engine = engine;
+  set_train_tc_one_pass(engine == 2);
   return 0;
 }
 

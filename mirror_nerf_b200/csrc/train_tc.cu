@@ -52,6 +52,7 @@ struct NNParams {
   float* C; int ldc;
   int M, N, K, n_tiles;
   GemmEpi e;
+  int one_pass;  // speed mode: single tf32 pass (hi parts only; 10-bit mantissa operands) instead of the 3-pass split
   int dbg;  // bring-up: 1 = no global loads of A, 2 = no conversion/stores of A, 4 = no MMAs, 8 = no epilogue global traffic, 16 = no B copies
 };
 
@@ -149,18 +150,19 @@ k_gemm_tc_nn(const NNParams P, const __grid_constant__ CUtensorMap tmA0, const _
     // ------------------------------ B producer ------------------------------
     if (elect_one()) {
       uint32_t stage = 0, phase = 0;
-      const uint32_t bytes = 2u * N * 64u;
+      const uint32_t chunk_bytes = 2u * N * 64u;
+      const uint32_t bytes = P.one_pass ? N * 64u : chunk_bytes;
       for (int t = 0; t < my_tiles; ++t) {
         for (int kc = 0; kc < nkc; ++kc) {
           mbar_wait(bar(NB_EMPTY + stage), phase ^ 1u);
           const uint32_t dst = sbase + stage * NN_STAGE + 2 * NN_A_PART;
           const uint32_t fb = bar(NB_B_FULL + stage);
-          const uint8_t* src = P.blob + (size_t)kc * bytes;
+          const uint8_t* src = P.blob + (size_t)kc * chunk_bytes;
           if (P.dbg & 16) {
             mbar_expect_tx(fb, 0);
           } else {
             mbar_expect_tx(fb, bytes);
-            for (uint32_t o = 0; o < bytes; o += 8192u) bulk_g2s(dst + o, src + o, 8192u, fb);
+            for (uint32_t o = 0; o < bytes; o += 8192u) bulk_g2s(dst + o, src + o, min(8192u, bytes - o), fb);
           }
           if (++stage == NN_STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -190,8 +192,10 @@ k_gemm_tc_nn(const NNParams P, const __grid_constant__ CUtensorMap tmA0, const _
 #pragma unroll
             for (uint32_t j = 0; j < 2; ++j) {
               mma_tf32(d_tmem, a_hi + j * astep, b_hi + j * bstep, idesc, accumulate);
-              mma_tf32(d_tmem, a_lo + j * astep, b_hi + j * bstep, idesc, 1u);
-              mma_tf32(d_tmem, a_hi + j * astep, b_lo + j * bstep, idesc, 1u);
+              if (!P.one_pass) {
+                mma_tf32(d_tmem, a_lo + j * astep, b_hi + j * bstep, idesc, 1u);
+                mma_tf32(d_tmem, a_hi + j * astep, b_lo + j * bstep, idesc, 1u);
+              }
               accumulate = 1u;
             }
           }
@@ -247,10 +251,10 @@ k_gemm_tc_nn(const NNParams P, const __grid_constant__ CUtensorMap tmA0, const _
         uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
         split_tf32(v0.x, h0, l0); split_tf32(v0.y, h1, l1); split_tf32(v0.z, h2, l2); split_tf32(v0.w, h3, l3);
         st_shared_v4(sa + so[0], h0, h1, h2, h3);
-        st_shared_v4(sa + so[0] + NN_A_PART, l0, l1, l2, l3);
+        if (!P.one_pass) st_shared_v4(sa + so[0] + NN_A_PART, l0, l1, l2, l3);
         split_tf32(v1.x, h0, l0); split_tf32(v1.y, h1, l1); split_tf32(v1.z, h2, l2); split_tf32(v1.w, h3, l3);
         st_shared_v4(sa + so[1], h0, h1, h2, h3);
-        st_shared_v4(sa + so[1] + NN_A_PART, l0, l1, l2, l3);
+        if (!P.one_pass) st_shared_v4(sa + so[1] + NN_A_PART, l0, l1, l2, l3);
       }
       fence_async_smem();
       __syncwarp();
@@ -329,6 +333,7 @@ struct TNParams {
   const float* B; int ldb; int NB;
   float* Wg; int ldw; int col0; int valid;
   int P; int rows_per_cta;
+  int one_pass;
   float* colsum;  // optional: colsum[f] += sum_p A[p][f] (bias gradient, fused into the operand-A converters)
   int dbg;  // bring-up: 1 = no global loads, 2 = no conversion/stores, 4 = no MMAs, 8 = no flush
 };
@@ -407,8 +412,10 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tc_tn(const TNParams P) 
 #pragma unroll
           for (uint32_t j = 0; j < 2; ++j) {
             mma_tf32(d_tmem, a_hi + mo + j * astep, b_hi + j * bstep, idesc, (c > 0 || j > 0) ? 1u : 0u, dhi, dhi);
-            mma_tf32(d_tmem, a_lo + mo + j * astep, b_hi + j * bstep, idesc, 1u, dhi, dhi);
-            mma_tf32(d_tmem, a_hi + mo + j * astep, b_lo + j * bstep, idesc, 1u, dhi, dhi);
+            if (!P.one_pass) {
+              mma_tf32(d_tmem, a_lo + mo + j * astep, b_hi + j * bstep, idesc, 1u, dhi, dhi);
+              mma_tf32(d_tmem, a_hi + mo + j * astep, b_lo + j * bstep, idesc, 1u, dhi, dhi);
+            }
           }
         }
         tc_commit(bar(TB_EMPTY + stage));
@@ -440,7 +447,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tc_tn(const TNParams P) 
         split_tf32(r[cc][0], h0, l0); split_tf32(r[cc][1], h1, l1); split_tf32(r[cc][2], h2, l2); split_tf32(r[cc][3], h3, l3);
         const uint32_t a = base + (uint32_t)j * lbo + (uint32_t)(f >> 3) * TN_SBO + (uint32_t)(f & 7) * 16u;
         st_shared_v4(a, h0, h1, h2, h3);
-        st_shared_v4(a + TN_PART, l0, l1, l2, l3);
+        if (!P.one_pass) st_shared_v4(a + TN_PART, l0, l1, l2, l3);
       }
     };
     uint32_t stage = 0, phase = 0, slot = 0, rphase = 0;
@@ -513,6 +520,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tc_tn(const TNParams P) 
 }
 
 int g_dbg = 0;
+int g_one_pass = 0;
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -575,6 +583,7 @@ int gemm_nn_tc(const mnrf_field* f, int step, const float* A0, int lda0, int K0,
   P.C = C; P.ldc = ldc; P.M = M; P.N = N; P.K = K;
   P.n_tiles = (M + 127) / 128;
   P.e = e;
+  P.one_pass = g_one_pass;
   P.dbg = g_dbg;
   const int grid = P.n_tiles < sms ? P.n_tiles : sms;
   CUtensorMap m0, m1;
@@ -609,6 +618,7 @@ int gemm_tn_tc(const float* A, int lda, int NA, const float* B, int ldb, int NB,
   if (rows < 256) rows = 256;  // small problems: fewer CTAs, fewer atomics
   P.rows_per_cta = rows;
   P.colsum = colsum_out;
+  P.one_pass = g_one_pass;
   P.dbg = g_dbg;
   const int grid = (Pn + rows - 1) / rows;
   k_gemm_tc_tn<<<grid, TN_THREADS, TN_SM_TOTAL, st>>>(P);
@@ -617,5 +627,6 @@ int gemm_tn_tc(const float* A, int lda, int NA, const float* B, int ldb, int NB,
 }
 
 void set_train_tc_debug(int flags) { g_dbg = flags; }
+void set_train_tc_one_pass(int on) { g_one_pass = on ? 1 : 0; }
 
 }  // namespace mnrf

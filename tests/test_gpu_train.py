@@ -401,3 +401,30 @@ def test_train_full_size_engines_agree_and_gradients_are_linear():
             assert cos >= 0.9999, (k, cos)
         assert float((a2 - 2 * a).norm()) <= 1e-3 * float((2 * a).norm()) + 1e-12, k
     print(f"full-size engine agreement: worst per-tensor cosine {worst:.6f}")
+
+
+def test_train_single_pass_tf32_speed_mode():
+    """Engine 2 (one tf32 pass, opt-in speed mode; 39.0 vs 45.4 ms per 4096-ray step): gradients stay in the neighbourhood of the
+    fp32-grade default (whole-vector cosine >= 0.99; measured 0.9958 on 64 rays) but are measurably different -- this is why
+    the 3-pass split is the default and the only parity mode."""
+    from mirror_nerf_b200 import _lib
+    from mirror_nerf_b200.rendering import render_rays
+    from mirror_nerf_b200.synthetic import random_rays
+    lib = _lib.load()
+    sds = _smooth_sds()
+    rays = random_rays(64, seed=17).cuda()
+    rng = _rng(64)
+    args = (64, False, 1.0, 1.0, 128, 32768, False)
+    out = []
+    try:
+        for engine in (1, 2):
+            _lib.check(lib.mnrf_train_set_gemm(engine))
+            models, emb = _models(sds)
+            r = render_rays(models, emb, rays, *args, rng=rng, test_time=False, compute_normal=True)
+            _loss(r, rays[:, 3:6], 4).backward()
+            out.append(torch.cat([p.grad.flatten() for m in models.values() for p in m.parameters()]).double())
+    finally:
+        lib.mnrf_train_set_gemm(1)
+    cos = float((out[0] * out[1]).sum() / (out[0].norm() * out[1].norm()))
+    print(f"tf32x1 vs tf32x3 gradient cosine {cos:.6f}")
+    assert 0.99 <= cos < 1.0 - 1e-9  # close, but measurably not the same arithmetic

@@ -21,4 +21,5 @@ for kind, step, name in ((0, 1, "NN 256x256"), (0, 9, "NN N128 K256"), (0, 19, "
         if kind == 1 and dbg >= 16: continue
         t = run(kind, step, 1, dbg)
         print(f" | dbg{dbg}: {t:6.3f}", end="", flush=True)
+    print(f" | tf32x1: {run(kind, step, 2, 0):6.3f}", end="")
     print(f"   (ideal tensor {flop * 3 / 1.13e15 * 1e3 * (128 if step == 9 else 64 if step == 19 else 256) / 256:.3f} ms)")
