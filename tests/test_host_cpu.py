@@ -160,3 +160,29 @@ def test_hashgrid_oracle_properties():
     idx = 3 + 5 * res + 7 * res * res
     assert torch.allclose(e[0, :2], table.view(-1, 2)[off + idx], atol=1e-5)
     assert H.sh4(torch.tensor([[0.0, 0.0, 1.0]])).shape == (1, 16)
+
+
+def test_dropin_install_patches_reference_module():
+    """after install(), `from models.rendering import render_rays` (R/eval.py:10, R/train.py:14) binds
+    ours; the signature keeps the reference's positional parameters (R/models/rendering.py:54-67)."""
+    import inspect
+    import sys
+    ref_root = os.environ.get("MNRF_REFERENCE", "/root/reference")
+    if not os.path.isdir(os.path.join(ref_root, "models")):
+        pytest.skip("reference tree not present on this machine")
+    from mirror_nerf_b200 import dropin, rendering
+    mod = dropin.install(ref_root)
+    try:
+        ns = {}
+        exec("from models.rendering import render_rays, sample_pdf", ns)
+        assert ns["render_rays"] is rendering.render_rays and ns["sample_pdf"] is rendering.sample_pdf
+        ours = list(inspect.signature(rendering.render_rays).parameters)
+        theirs = list(inspect.signature(mod._reference_render_rays).parameters)
+        assert ours[:len(theirs) - 1] == theirs[:-1] and ours[-1] == theirs[-1] == "kwargs", (ours, theirs)
+        for name in theirs[:-1]:
+            a = inspect.signature(rendering.render_rays).parameters[name].default
+            b = inspect.signature(mod._reference_render_rays).parameters[name].default
+            assert a == b, (name, a, b)
+    finally:
+        dropin.uninstall()
+    assert sys.modules["models.rendering"].render_rays is mod._reference_render_rays
