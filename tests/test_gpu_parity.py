@@ -524,3 +524,27 @@ def test_generate_rays_matches_reference_camera():
         assert got.shape == want.shape
         assert torch.equal(got[:, [0, 1, 2, 6, 7]], want[:, [0, 1, 2, 6, 7]])
         assert float((got[:, 3:6] - want[:, 3:6]).abs().max()) <= 2e-7  # matmul summation order / FMA contraction
+
+
+def test_sharded_render_equals_unsharded_bitwise(mm):
+    """rays are independent units, so a ray's result must not depend on which rank's shard it lands in --
+    rendering the tile-aligned shards of mirror_nerf_b200.parallel.shard_bounds one after the other (what N ranks do) gives
+    bit-identical outputs to rendering the whole batch."""
+    from mirror_nerf_b200.parallel import shard_bounds
+    from mirror_nerf_b200.rendering import render_rays
+    from mirror_nerf_b200.synthetic import random_rays
+    models, emb = mm
+    n = 1000
+    rays = random_rays(n, seed=21).cuda()
+    args = (64, False, 0, 0, 128, 32768, False)
+    with torch.no_grad():
+        whole = render_rays(models, emb, rays, *args, test_time=True, compute_normal=False)
+        for world in (2, 3, 8):
+            parts = []
+            for rank in range(world):
+                lo, hi = shard_bounds(n, rank, world)
+                if hi > lo:
+                    parts.append(render_rays(models, emb, rays[lo:hi].contiguous(), *args, test_time=True, compute_normal=False))
+            for k in ("rgb_fine", "depth_fine", "mirror_mask_fine", "weights_fine", "z_vals_fine", "surface_normal_fine"):
+                got = torch.cat([p[k] for p in parts], 0)
+                assert torch.equal(got, whole[k]), (world, k, float((got - whole[k]).abs().max()))
