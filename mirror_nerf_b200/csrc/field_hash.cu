@@ -5,28 +5,84 @@
 //   sigma_net 32->64->16 (sigma raw = out[0], geo_feat = out[1:16]) -> colour net [SH4(d) | geo] 31->64->64->3 sigmoid,
 //   normal net 15->64->3 l2-normalised, mirror net 15->32->1 (LeakyReLU, biases, sigmoid)    -> 8 floats / point.
 // This path is gather-bound (128 table reads of 8 bytes per point against a 46.5 MB fp32 table that lives mostly in the 126 MB
-// L2) with ~11 k MAC per point, so it runs on the CUDA cores: weights (45 KB) are staged in shared memory and read as
-// warp-uniform float4 broadcasts; every layer after the first of each net is consumed output-by-output, so only one 64-wide
-// activation vector is live in registers.  fp32 throughout (tinycudann evaluates in fp16).
+// L2) with ~11 k MAC per point, so it runs on the CUDA cores.  Gather phase: one thread per point.  MLP phase: each warp treats
+// its 32 points as a small GEMM batch -- activations live in a per-warp shared-memory buffer (feature-major [k][32 points]),
+// weights (45 KB, transposed to [k][out]) in shared memory, and every lane accumulates a register tile of 4 points x 16 (8, 4)
+// outputs, i.e. 64 FMAs per 5 shared-memory loads instead of 4 per load with one point per thread (the first version of this
+// kernel was shared-memory-bandwidth bound: ncu L1/TEX 77 %).  The tiny last layers (64->3, 64->3, 32->1) are fused into
+// the tile epilogue of the layer before them (partial dots + two shuffles).  fp32 throughout (tinycudann evaluates in fp16).
 #include "common.cuh"
 
 namespace mnrf {
 namespace {
 
-constexpr int HB = 128;  // threads per block
+constexpr int HB = 128;        // threads per block = 4 warps x 32 points
+constexpr int HX = 64 * 32;    // floats of one per-warp activation buffer: [64 features][32 points]
+constexpr int H_SMEM_FLOATS = HW_TOTAL + 4 * 2 * HX;
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
-// dot of a shared-memory weight row (K floats, K % 4 == 0) with a register vector
-template <int K>
-__device__ __forceinline__ float dotw(const float* __restrict__ w, const float (&v)[K]) {
-  float acc = 0.f;
+// acc[p][j] += sum_k X[k][4*pg + p] * Wt[k][o0 + j]      X: [K][32] floats (feature-major), Wt: [K][N] floats
+template <int NO>
+__device__ __forceinline__ void tile_gemm(const float* __restrict__ X, const float* __restrict__ Wt, int N, int K, int pg, int o0,
+                                          float (&acc)[4][NO]) {
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    const float4 x = *reinterpret_cast<const float4*>(X + k * 32 + 4 * pg);
 #pragma unroll
-  for (int k = 0; k < K; k += 4) {
-    const float4 q = *reinterpret_cast<const float4*>(w + k);
-    acc = fmaf(q.x, v[k], acc); acc = fmaf(q.y, v[k + 1], acc); acc = fmaf(q.z, v[k + 2], acc); acc = fmaf(q.w, v[k + 3], acc);
+    for (int j = 0; j < NO; j += 4) {
+      const float4 w = *reinterpret_cast<const float4*>(Wt + k * N + o0 + j);
+      acc[0][j] = fmaf(x.x, w.x, acc[0][j]); acc[0][j + 1] = fmaf(x.x, w.y, acc[0][j + 1]); acc[0][j + 2] = fmaf(x.x, w.z, acc[0][j + 2]); acc[0][j + 3] = fmaf(x.x, w.w, acc[0][j + 3]);
+      acc[1][j] = fmaf(x.y, w.x, acc[1][j]); acc[1][j + 1] = fmaf(x.y, w.y, acc[1][j + 1]); acc[1][j + 2] = fmaf(x.y, w.z, acc[1][j + 2]); acc[1][j + 3] = fmaf(x.y, w.w, acc[1][j + 3]);
+      acc[2][j] = fmaf(x.z, w.x, acc[2][j]); acc[2][j + 1] = fmaf(x.z, w.y, acc[2][j + 1]); acc[2][j + 2] = fmaf(x.z, w.z, acc[2][j + 2]); acc[2][j + 3] = fmaf(x.z, w.w, acc[2][j + 3]);
+      acc[3][j] = fmaf(x.w, w.x, acc[3][j]); acc[3][j + 1] = fmaf(x.w, w.y, acc[3][j + 1]); acc[3][j + 2] = fmaf(x.w, w.z, acc[3][j + 2]); acc[3][j + 3] = fmaf(x.w, w.w, acc[3][j + 3]);
+    }
   }
-  return acc;
+}
+template <int NO>
+__device__ __forceinline__ void tile_zero(float (&acc)[4][NO]) {
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int j = 0; j < NO; ++j) acc[p][j] = 0.f;
+}
+// Y[o0 + j][4*pg .. 4*pg+3] = acc[.][j]
+template <int NO>
+__device__ __forceinline__ void tile_store(float* __restrict__ Y, int pg, int o0, const float (&acc)[4][NO]) {
+#pragma unroll
+  for (int j = 0; j < NO; ++j)
+    *reinterpret_cast<float4*>(Y + (o0 + j) * 32 + 4 * pg) = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
+}
+// fused last layer: out[c][point] = sum_o Wf[c][o] * hidden[o][point] for c < NC; partial dots over this lane's NO outputs, summed
+// over the 4 lanes that share the point group (lane ^ 8, lane ^ 16), delivered to the owning threads through Y[c][point]
+template <int NO, int NC>
+__device__ __forceinline__ void tile_final(const float (&hid)[4][NO], const float* __restrict__ Wf, int ldw, int pg, int og, int o0,
+                                           float* __restrict__ Y) {
+  float part[4][NC];
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int c = 0; c < NC; ++c) part[p][c] = 0.f;
+#pragma unroll
+  for (int j = 0; j < NO; ++j)
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const float w = Wf[c * ldw + o0 + j];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) part[p][c] = fmaf(hid[p][j], w, part[p][c]);
+    }
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      part[p][c] += __shfl_xor_sync(0xffffffffu, part[p][c], 8);
+      part[p][c] += __shfl_xor_sync(0xffffffffu, part[p][c], 16);
+    }
+  if (og == 0) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+      *reinterpret_cast<float4*>(Y + c * 32 + 4 * pg) = make_float4(part[0][c], part[1][c], part[2][c], part[3][c]);
+  }
 }
 
 __global__ void __launch_bounds__(HB) k_field_hash(const float* __restrict__ table, const float* __restrict__ wpack, HashGridMeta M,
@@ -35,8 +91,13 @@ __global__ void __launch_bounds__(HB) k_field_hash(const float* __restrict__ tab
   for (int i = threadIdx.x; i < HW_TOTAL / 4; i += HB)
     reinterpret_cast<float4*>(sw)[i] = reinterpret_cast<const float4*>(wpack)[i];
   __syncthreads();
-  const long long p = (long long)blockIdx.x * HB + threadIdx.x;
-  if (p >= io.n_points) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pg = lane & 7, og = lane >> 3;
+  float* X0 = sw + HW_TOTAL + warp * 2 * HX;
+  float* X1 = X0 + HX;
+  const long long p_raw = (long long)blockIdx.x * HB + threadIdx.x;
+  const bool valid = p_raw < io.n_points;
+  const long long p = valid ? p_raw : (long long)io.n_points - 1;  // tail threads shadow the last point (warp-collective MLP)
   float x[3], d[3] = {0.f, 0.f, 0.f};
   if (io.rays != nullptr) {
     const float* rr = io.rays + (p / io.S) * 8;
@@ -53,8 +114,7 @@ __global__ void __launch_bounds__(HB) k_field_hash(const float* __restrict__ tab
 #pragma unroll
   for (int c = 0; c < 3; ++c) u[c] = __fdiv_rn(__fadd_rn(x[c], M.bound), __fmul_rn(2.f, M.bound));
 
-  // ---- multiresolution hash encoding ----
-  float enc[32];
+  // ---- multiresolution hash encoding (thread = point) -> X0[2l + f][lane] ----
   const float2* tab = reinterpret_cast<const float2*>(table);
 #pragma unroll 1
   for (int l = 0; l < HG_LEVELS; ++l) {
@@ -85,86 +145,134 @@ __global__ void __launch_bounds__(HB) k_field_hash(const float* __restrict__ tab
       for (; dim < 3 && stride <= size; ++dim) { index += c3[dim] * stride; stride *= res; }
       if (size < stride) index = (c3[0] * 1u) ^ (c3[1] * 2654435761u) ^ (c3[2] * 805459861u);
       index %= size;
-      const float2 f = __ldg(tab + M.offset[l] + index);
+      const float2 f = __ldg(tab + M.offset[l] + index);  // through L1: __ldcg (L2 only) measured 15 % slower, coarse levels hit in L1
       a0 = __fadd_rn(a0, __fmul_rn(w, f.x));
       a1 = __fadd_rn(a1, __fmul_rn(w, f.y));
     }
-    enc[2 * l] = a0;
-    enc[2 * l + 1] = a1;
+    X0[(2 * l) * 32 + lane] = a0;
+    X0[(2 * l + 1) * 32 + lane] = a1;
   }
+  __syncwarp();
 
-  // ---- sigma_net: 32 -> 64 (ReLU) -> 16 ----
-  float h[64];
+  // ---- sigma_net: 32 -> 64 (ReLU) -> 16; [sigma, geo_feat(15)] ends up in X0 rows 0..15 ----
+  {
+    float acc[4][16];
+    tile_zero<16>(acc);
+    tile_gemm<16>(X0, sw + HW_S0, 64, 32, pg, 16 * og, acc);
 #pragma unroll
-  for (int o = 0; o < 64; ++o) h[o] = fmaxf(dotw<32>(sw + HW_S0 + o * 32, enc), 0.f);
-  float geo[16];  // [sigma, geo_feat(15)]
+    for (int pp = 0; pp < 4; ++pp)
 #pragma unroll
-  for (int o = 0; o < 16; ++o) geo[o] = dotw<64>(sw + HW_S1 + o * 64, h);
-  const float sigma = geo[0];
+      for (int j = 0; j < 16; ++j) acc[pp][j] = fmaxf(acc[pp][j], 0.f);
+    tile_store<16>(X1, pg, 16 * og, acc);
+  }
+  __syncwarp();
+  {
+    float acc[4][4];
+    tile_zero<4>(acc);
+    tile_gemm<4>(X1, sw + HW_S1, 16, 64, pg, 4 * og, acc);
+    __syncwarp();  // every lane is done reading X0 (the encoding) before it is overwritten
+    tile_store<4>(X0, pg, 4 * og, acc);
+  }
+  __syncwarp();
+  const float sigma = X0[lane];
   if (io.sigma_only) {
-    if (io.sigma_out != nullptr) io.sigma_out[p] = sigma;
-    if (io.raw == nullptr) return;
+    if (io.sigma_out != nullptr && valid) io.sigma_out[p_raw] = sigma;
+    if (io.raw == nullptr) return;  // warp-uniform
   }
-  float g16[16];  // geo_feat padded to 16
-#pragma unroll
-  for (int i = 0; i < 15; ++i) g16[i] = geo[1 + i];
-  g16[15] = 0.f;
-
+  const float* GEO = X0 + 32;  // rows 1..15 = geo_feat
   float o_n[3] = {0.f, 0.f, 0.f}, o_rgb[3] = {0.f, 0.f, 0.f}, o_m = 0.f;
+
   if (has_normal) {  // 15 -> 64 (ReLU) -> 3, l2-normalised
-    float n2[3] = {0.f, 0.f, 0.f};
-#pragma unroll 8
-    for (int o = 0; o < 64; ++o) {
-      const float v = fmaxf(dotw<16>(sw + HW_N0 + o * 16, g16), 0.f);
-      n2[0] = fmaf(sw[HW_N1 + o], v, n2[0]); n2[1] = fmaf(sw[HW_N1 + 64 + o], v, n2[1]); n2[2] = fmaf(sw[HW_N1 + 128 + o], v, n2[2]);
-    }
-    const float len = sqrtf(fmaxf(n2[0] * n2[0] + n2[1] * n2[1] + n2[2] * n2[2], FP32_EPS));
-    o_n[0] = n2[0] / len; o_n[1] = n2[1] / len; o_n[2] = n2[2] / len;
+    float acc[4][16];
+    tile_zero<16>(acc);
+    tile_gemm<16>(GEO, sw + HW_N0, 64, 15, pg, 16 * og, acc);
+#pragma unroll
+    for (int pp = 0; pp < 4; ++pp)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[pp][j] = fmaxf(acc[pp][j], 0.f);
+    tile_final<16, 3>(acc, sw + HW_N1, 64, pg, og, 16 * og, X1);
+    __syncwarp();
+    const float n0 = X1[lane], n1 = X1[32 + lane], n2 = X1[64 + lane];
+    const float len = sqrtf(fmaxf(n0 * n0 + n1 * n1 + n2 * n2, FP32_EPS));
+    o_n[0] = n0 / len; o_n[1] = n1 / len; o_n[2] = n2 / len;
+    __syncwarp();
   }
   if (!io.sigma_only) {
-    // colour net: [SH4(d) (16) | geo_feat (15) | 0] -> 64 (ReLU) -> 64 (ReLU) -> 3 sigmoid
-    float in[32];
+    if (has_mirror) {  // 15 -> 32 (+bias, LeakyReLU 0.01) -> 1 (+bias) sigmoid
+      float acc[4][8];
+      tile_zero<8>(acc);
+      tile_gemm<8>(GEO, sw + HW_M0, 32, 15, pg, 8 * og, acc);
+#pragma unroll
+      for (int pp = 0; pp < 4; ++pp)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float v = acc[pp][j] + sw[HW_M0B + 8 * og + j];
+          acc[pp][j] = v > 0.f ? v : 0.01f * v;
+        }
+      tile_final<8, 1>(acc, sw + HW_M2, 32, pg, og, 8 * og, X1);
+      __syncwarp();
+      o_m = sigmoidf_(X1[lane] + sw[HW_M2B]);
+      __syncwarp();
+    }
+    // colour net input [SH4(d) (16) | geo_feat (15) | 0] -> X1 rows 0..31
     {
       const float X = d[0], Y = d[1], Z = d[2];
       const float xy = X * Y, xz = X * Z, yz = Y * Z, x2 = X * X, y2 = Y * Y, z2 = Z * Z;
-      in[0] = 0.28209479177387814f;
-      in[1] = -0.48860251190291987f * Y; in[2] = 0.48860251190291987f * Z; in[3] = -0.48860251190291987f * X;
-      in[4] = 1.0925484305920792f * xy; in[5] = -1.0925484305920792f * yz;
-      in[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
-      in[7] = -1.0925484305920792f * xz; in[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
-      in[9] = 0.59004358992664352f * Y * (-3.0f * x2 + y2); in[10] = 2.8906114426405538f * xy * Z;
-      in[11] = 0.45704579946446572f * Y * (1.0f - 5.0f * z2); in[12] = 0.3731763325901154f * Z * (5.0f * z2 - 3.0f);
-      in[13] = 0.45704579946446572f * X * (1.0f - 5.0f * z2); in[14] = 1.4453057213202769f * Z * (x2 - y2);
-      in[15] = 0.59004358992664352f * X * (-x2 + 3.0f * y2);
-    }
+      float sh[16];
+      sh[0] = 0.28209479177387814f;
+      sh[1] = -0.48860251190291987f * Y; sh[2] = 0.48860251190291987f * Z; sh[3] = -0.48860251190291987f * X;
+      sh[4] = 1.0925484305920792f * xy; sh[5] = -1.0925484305920792f * yz;
+      sh[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
+      sh[7] = -1.0925484305920792f * xz; sh[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+      sh[9] = 0.59004358992664352f * Y * (-3.0f * x2 + y2); sh[10] = 2.8906114426405538f * xy * Z;
+      sh[11] = 0.45704579946446572f * Y * (1.0f - 5.0f * z2); sh[12] = 0.3731763325901154f * Z * (5.0f * z2 - 3.0f);
+      sh[13] = 0.45704579946446572f * X * (1.0f - 5.0f * z2); sh[14] = 1.4453057213202769f * Z * (x2 - y2);
+      sh[15] = 0.59004358992664352f * X * (-x2 + 3.0f * y2);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) in[16 + i] = g16[i];
+      for (int i = 0; i < 16; ++i) X1[i * 32 + lane] = sh[i];
 #pragma unroll
-    for (int o = 0; o < 64; ++o) h[o] = fmaxf(dotw<32>(sw + HW_C0 + o * 32, in), 0.f);
-    float c[3] = {0.f, 0.f, 0.f};
-#pragma unroll 4
-    for (int o = 0; o < 64; ++o) {
-      const float v = fmaxf(dotw<64>(sw + HW_C1 + o * 64, h), 0.f);
-      c[0] = fmaf(sw[HW_C2 + o], v, c[0]); c[1] = fmaf(sw[HW_C2 + 64 + o], v, c[1]); c[2] = fmaf(sw[HW_C2 + 128 + o], v, c[2]);
+      for (int i = 0; i < 15; ++i) X1[(16 + i) * 32 + lane] = GEO[i * 32 + lane];
+      X1[31 * 32 + lane] = 0.f;
     }
-    o_rgb[0] = sigmoidf_(c[0]); o_rgb[1] = sigmoidf_(c[1]); o_rgb[2] = sigmoidf_(c[2]);
-    if (has_mirror) {  // 15 -> 32 (+bias, LeakyReLU 0.01) -> 1 (+bias) sigmoid
-      float acc = sw[HW_M2B];
-#pragma unroll 8
-      for (int o = 0; o < 32; ++o) {
-        float v = dotw<16>(sw + HW_M0 + o * 16, g16) + sw[HW_M0B + o];
-        v = v > 0.f ? v : 0.01f * v;
-        acc = fmaf(sw[HW_M2 + o], v, acc);
-      }
-      o_m = sigmoidf_(acc);
+    __syncwarp();
+    {
+      float acc[4][16];
+      tile_zero<16>(acc);
+      tile_gemm<16>(X1, sw + HW_C0, 64, 32, pg, 16 * og, acc);
+#pragma unroll
+      for (int pp = 0; pp < 4; ++pp)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[pp][j] = fmaxf(acc[pp][j], 0.f);
+      tile_store<16>(X0, pg, 16 * og, acc);  // geo_feat is no longer needed
     }
+    __syncwarp();
+    {
+      float acc[4][16];
+      tile_zero<16>(acc);
+      tile_gemm<16>(X0, sw + HW_C1, 64, 64, pg, 16 * og, acc);
+#pragma unroll
+      for (int pp = 0; pp < 4; ++pp)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[pp][j] = fmaxf(acc[pp][j], 0.f);
+      tile_final<16, 3>(acc, sw + HW_C2, 64, pg, og, 16 * og, X1);
+    }
+    __syncwarp();
+    o_rgb[0] = sigmoidf_(X1[lane]); o_rgb[1] = sigmoidf_(X1[32 + lane]); o_rgb[2] = sigmoidf_(X1[64 + lane]);
   }
-  if (io.raw != nullptr) {
-    float4* o = reinterpret_cast<float4*>(io.raw + p * 8);
+  if (io.raw != nullptr && valid) {
+    float4* o = reinterpret_cast<float4*>(io.raw + p_raw * 8);
     o[0] = make_float4(sigma, o_rgb[0], o_rgb[1], o_rgb[2]);
     o[1] = make_float4(o_m, o_n[0], o_n[1], o_n[2]);
   }
-  if (io.sigma_out != nullptr && !io.sigma_only) io.sigma_out[p] = sigma;
+  if (io.sigma_out != nullptr && !io.sigma_only && valid) io.sigma_out[p_raw] = sigma;
+}
+
+// hidden-layer weights are stored transposed: dst[k][o] (N wide) = k < K && o < N ? src[o][k] : 0
+__global__ void k_hash_pack_t(const float* __restrict__ src, float* __restrict__ dst, int N, int K, int Kpad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Kpad * N) return;
+  const int k = i / N, o = i % N;
+  dst[i] = (src != nullptr && k < K) ? src[(size_t)o * K + k] : 0.f;
 }
 
 // dst[r][c] (cols_pad wide) = c < cols ? src[r][c0 + c] : 0
@@ -190,14 +298,19 @@ int pack_rows(const float* src, float* dst, int rows, int cols, int cols_pad, in
 int pack_hash_field(mnrf_field* f, const float* const* t, long long table_floats, cudaStream_t st) {
   MNRF_CUDA_OK(cudaMemcpyAsync(f->hash_table, t[0], sizeof(float) * (size_t)table_floats, cudaMemcpyDeviceToDevice, st));
   float* w = f->hash_w;
-  if (pack_rows(t[1], w + HW_S0, 64, 32, 32, 64, st)) return 1;
-  if (pack_rows(t[2], w + HW_S1, 16, 64, 64, 16, st)) return 1;
-  if (pack_rows(t[3], w + HW_C0, 64, 31, 32, 64, st)) return 1;
-  if (pack_rows(t[4], w + HW_C1, 64, 64, 64, 64, st)) return 1;
+  auto pack_t = [&](const float* src, float* dst, int N, int K, int Kpad) {  // dst[k][o] = src[o][k]
+    k_hash_pack_t<<<(Kpad * N + 255) / 256, 256, 0, st>>>(src, dst, N, K, Kpad);
+    MNRF_LAUNCH_OK();
+    return 0;
+  };
+  if (pack_t(t[1], w + HW_S0, 64, 32, 32)) return 1;
+  if (pack_t(t[2], w + HW_S1, 16, 64, 64)) return 1;
+  if (pack_t(t[3], w + HW_C0, 64, 31, 32)) return 1;
+  if (pack_t(t[4], w + HW_C1, 64, 64, 64)) return 1;
   if (pack_rows(t[5], w + HW_C2, 3, 64, 64, 4, st)) return 1;
-  if (pack_rows(t[6], w + HW_N0, 64, 15, 16, 64, st)) return 1;
+  if (pack_t(t[6], w + HW_N0, 64, 15, 16)) return 1;
   if (pack_rows(t[7], w + HW_N1, 3, 64, 64, 4, st)) return 1;
-  if (pack_rows(t[8], w + HW_M0, 32, 15, 16, 32, st)) return 1;
+  if (pack_t(t[8], w + HW_M0, 32, 15, 16)) return 1;
   if (pack_rows(t[9], w + HW_M0B, 1, 32, 32, 1, st)) return 1;
   if (pack_rows(t[10], w + HW_M2, 1, 32, 32, 1, st)) return 1;
   if (pack_rows(t[11], w + HW_M2B, 1, 1, 4, 1, st)) return 1;
@@ -210,11 +323,11 @@ int launch_field_hash(const mnrf_field* f, const FieldIO& io, cudaStream_t st) {
   MNRF_REQUIRE(io.geo_out == nullptr, "hash-grid field: geo_feat export is not built");
   static bool attr = false;
   if (!attr) {
-    MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_hash, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(HW_TOTAL * sizeof(float))));
+    MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_hash, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(H_SMEM_FLOATS * sizeof(float))));
     attr = true;
   }
   const long long blocks = ((long long)io.n_points + HB - 1) / HB;
-  k_field_hash<<<(unsigned)blocks, HB, HW_TOTAL * sizeof(float), st>>>(f->hash_table, f->hash_w, f->hg, io, f->has_normal, f->has_mirror);
+  k_field_hash<<<(unsigned)blocks, HB, H_SMEM_FLOATS * sizeof(float), st>>>(f->hash_table, f->hash_w, f->hg, io, f->has_normal, f->has_mirror);
   MNRF_LAUNCH_OK();
   return 0;
 }
