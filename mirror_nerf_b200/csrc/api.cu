@@ -236,11 +236,13 @@ int mnrf_field_eval_points(const mnrf_field* f, int impl, const float* x, int B,
   cudaStream_t st = S_(stream);
   if (f->kind == 1) {
     // hash-grid field: x (B, 3+3) = [xyz | d] (identity embeddings, R/train.py:69-70) or (B,3) when sigma_only
-    MNRF_REQUIRE(normal == nullptr && geo_feat == nullptr, "field_eval_points: hash-grid field has no analytic-normal / geo_feat export");
+    MNRF_REQUIRE(geo_feat == nullptr, "field_eval_points: the hash-grid field has no geo_feat export");
+    MNRF_REQUIRE(normal == nullptr || !sigma_only, "field_eval_points: hash-grid analytic normals need the full pass");
     float* rawh = nullptr;
     MNRF_CUDA_OK(cudaMallocAsync(&rawh, sizeof(float) * (size_t)B * 8, st));
     FieldIO ioh{};
     ioh.x = x; ioh.x_stride = sigma_only ? 3 : 6; ioh.n_points = B; ioh.S = 1; ioh.sigma_only = sigma_only; ioh.raw = rawh;
+    ioh.normal_out = normal;
     int rch = launch_field_hash(f, ioh, st);
     if (rch == 0) {
       k_unpack_raw<<<(B + 255) / 256, 256, 0, st>>>(rawh, B, sigma, sigma_only ? nullptr : rgb, sigma_only ? nullptr : is_mirror, pred_normal);

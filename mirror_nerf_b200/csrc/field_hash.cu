@@ -85,6 +85,10 @@ __device__ __forceinline__ void tile_final(const float (&hid)[4][NO], const floa
   }
 }
 
+// NORMALS: also the analytic normal normalize(-d sigma / d xyz) (mirror_nerf_tcnn.py:170-178: autograd through the encoder in the
+// reference): d sigma/d enc = W0^T (W1[0,:] * relu'(h)), then a second pass over the 8 corners of every level with the derivative
+// of the trilinear weights (d frac / d u = scale_l, d u / d x = 1 / (2 bound); floor() has no gradient).
+template <bool NORMALS>
 __global__ void __launch_bounds__(HB) k_field_hash(const float* __restrict__ table, const float* __restrict__ wpack, HashGridMeta M,
                                                    FieldIO io, int has_normal, int has_mirror) {
   extern __shared__ __align__(16) float sw[];
@@ -174,6 +178,70 @@ __global__ void __launch_bounds__(HB) k_field_hash(const float* __restrict__ tab
     tile_store<4>(X0, pg, 4 * og, acc);
   }
   __syncwarp();
+  float o_an[3] = {0.f, 0.f, 0.f};
+  if (NORMALS && !io.sigma_only) {
+    // g_h = W1[0,:] * relu'(h) (thread = point), g_enc[k] = sum_o W0[o][k] g_h[o] -> X1 rows 0..31 (the hidden layer is consumed)
+    float gh[64];
+#pragma unroll
+    for (int o = 0; o < 64; ++o) gh[o] = X1[o * 32 + lane] > 0.f ? sw[HW_S1 + o * 16] : 0.f;
+    __syncwarp();
+#pragma unroll 1
+    for (int k = 0; k < 32; ++k) {
+      float acc = 0.f;
+#pragma unroll
+      for (int o = 0; o < 64; o += 4) {
+        const float4 w = *reinterpret_cast<const float4*>(sw + HW_S0 + k * 64 + o);
+        acc = fmaf(w.x, gh[o], acc); acc = fmaf(w.y, gh[o + 1], acc); acc = fmaf(w.z, gh[o + 2], acc); acc = fmaf(w.w, gh[o + 3], acc);
+      }
+      X1[k * 32 + lane] = acc;
+    }
+    __syncwarp();
+    float gu[3] = {0.f, 0.f, 0.f};  // d sigma / d u
+#pragma unroll 1
+    for (int l = 0; l < HG_LEVELS; ++l) {
+      const float scale = M.scale[l];
+      const unsigned int res = (unsigned int)M.res[l], size = M.size[l];
+      unsigned int g[3];
+      float fr[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float pos = __fadd_rn(__fmul_rn(u[c], scale), 0.5f);
+        const float fl = floorf(pos);
+        g[c] = (unsigned int)(int)fl;
+        fr[c] = __fsub_rn(pos, fl);
+      }
+      const float ge0 = X1[(2 * l) * 32 + lane], ge1 = X1[(2 * l + 1) * 32 + lane];
+      float dl[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int corner = 0; corner < 8; ++corner) {
+        unsigned int c3[3];
+        float wd[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int bit = (corner >> c) & 1;
+          wd[c] = bit ? fr[c] : 1.f - fr[c];
+          c3[c] = g[c] + bit;
+        }
+        unsigned int stride = 1, index = 0;
+        int dim = 0;
+        for (; dim < 3 && stride <= size; ++dim) { index += c3[dim] * stride; stride *= res; }
+        if (size < stride) index = (c3[0] * 1u) ^ (c3[1] * 2654435761u) ^ (c3[2] * 805459861u);
+        index %= size;
+        const float2 f = __ldg(tab + M.offset[l] + index);
+        const float v = ge0 * f.x + ge1 * f.y;
+        dl[0] += ((corner & 1) ? v : -v) * wd[1] * wd[2];
+        dl[1] += ((corner & 2) ? v : -v) * wd[0] * wd[2];
+        dl[2] += ((corner & 4) ? v : -v) * wd[0] * wd[1];
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gu[c] = fmaf(scale, dl[c], gu[c]);
+    }
+    const float inv2b = 1.f / (2.f * M.bound);
+    const float a = -gu[0] * inv2b, b = -gu[1] * inv2b, cc = -gu[2] * inv2b;
+    const float len = sqrtf(fmaxf(a * a + b * b + cc * cc, FP32_EPS));  // utils/func.py:5-7
+    o_an[0] = a / len; o_an[1] = b / len; o_an[2] = cc / len;
+    __syncwarp();
+  }
   const float sigma = X0[lane];
   if (io.sigma_only) {
     if (io.sigma_out != nullptr && valid) io.sigma_out[p_raw] = sigma;
@@ -265,6 +333,9 @@ __global__ void __launch_bounds__(HB) k_field_hash(const float* __restrict__ tab
     o[1] = make_float4(o_m, o_n[0], o_n[1], o_n[2]);
   }
   if (io.sigma_out != nullptr && !io.sigma_only && valid) io.sigma_out[p_raw] = sigma;
+  if (NORMALS && io.normal_out != nullptr && valid) {
+    io.normal_out[p_raw * 3 + 0] = o_an[0]; io.normal_out[p_raw * 3 + 1] = o_an[1]; io.normal_out[p_raw * 3 + 2] = o_an[2];
+  }
 }
 
 // hidden-layer weights are stored transposed: dst[k][o] (N wide) = k < K && o < N ? src[o][k] : 0
@@ -319,15 +390,19 @@ int pack_hash_field(mnrf_field* f, const float* const* t, long long table_floats
 
 int launch_field_hash(const mnrf_field* f, const FieldIO& io, cudaStream_t st) {
   if (io.n_points <= 0) return 0;
-  MNRF_REQUIRE(io.normal_out == nullptr, "hash-grid field: analytic normals (compute_normal=True) are not built; use the predicted normals");
+  MNRF_REQUIRE(io.normal_out == nullptr || !io.sigma_only, "hash-grid field: analytic normals need the full (non sigma-only) pass");
   MNRF_REQUIRE(io.geo_out == nullptr, "hash-grid field: geo_feat export is not built");
   static bool attr = false;
   if (!attr) {
-    MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_hash, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(H_SMEM_FLOATS * sizeof(float))));
+    MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_hash<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(H_SMEM_FLOATS * sizeof(float))));
+    MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_hash<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(H_SMEM_FLOATS * sizeof(float))));
     attr = true;
   }
   const long long blocks = ((long long)io.n_points + HB - 1) / HB;
-  k_field_hash<<<(unsigned)blocks, HB, H_SMEM_FLOATS * sizeof(float), st>>>(f->hash_table, f->hash_w, f->hg, io, f->has_normal, f->has_mirror);
+  if (io.normal_out != nullptr)
+    k_field_hash<true><<<(unsigned)blocks, HB, H_SMEM_FLOATS * sizeof(float), st>>>(f->hash_table, f->hash_w, f->hg, io, f->has_normal, f->has_mirror);
+  else
+    k_field_hash<false><<<(unsigned)blocks, HB, H_SMEM_FLOATS * sizeof(float), st>>>(f->hash_table, f->hash_w, f->hg, io, f->has_normal, f->has_mirror);
   MNRF_LAUNCH_OK();
   return 0;
 }

@@ -4,8 +4,8 @@ the reference's constructor arguments and ``state_dict`` keys (``encoder.params`
 whose forward runs ``csrc/field_hash.cu``.  ``render_rays`` accepts these modules in ``models`` together with the identity
 embeddings ``Embedding(0)`` the reference uses for this model (R/train.py:69-70).
 
-The encoder follows tinycudann's HashGrid algorithm (parity unpinned, see oracle/hashgrid_oracle.py).  Inference only:
-``compute_normal=True`` (analytic normals through the hash grid) and gradients are not built for this field.
+The encoder follows tinycudann's HashGrid algorithm (parity unpinned, see oracle/hashgrid_oracle.py).  Inference only
+(predicted and analytic normals); gradients are not built for this field.
 """
 from __future__ import annotations
 
@@ -161,11 +161,11 @@ class MirrorNeRFTcnn(nn.Module):
                 detach_density_outside_mirror_for_mask_loss=False, detach_density_for_mask_loss=False,
                 detach_density_for_normal_loss=False):
         """x: (B, 3+3) = [xyz | d], or (B,3) when sigma_only.  Returns sigma (B,) [the reference's shape, mirror_nerf_tcnn.py:
-        234], pred_normal? (B,3), rgb? (B,3), is_mirror? (B,1).  geo_feat is not exported."""
+        234], normal? (B,3, analytic), pred_normal? (B,3), rgb? (B,3), is_mirror? (B,1).  geo_feat is not exported."""
         if not x.is_cuda:
             raise RuntimeError("MirrorNeRFTcnn.forward: input must be a CUDA tensor (no CPU path)")
-        if compute_normal:
-            raise NotImplementedError("analytic normals through the hash grid are not built; pass compute_normal=False")
+        if compute_normal and sigma_only:
+            raise NotImplementedError("MirrorNeRFTcnn: analytic normals need the full pass (sigma_only=False)")
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
             raise NotImplementedError("MirrorNeRFTcnn: gradients are not built for the hash-grid field; use torch.no_grad()")
         width = 3 if sigma_only else 6
@@ -176,15 +176,18 @@ class MirrorNeRFTcnn(nn.Module):
         pf = packed_hash_field(self)
         new = lambda *s: torch.empty(*s, device=x.device, dtype=torch.float32)
         sigma = new(B)
+        normal = new(B, 3) if compute_normal else None
         pred = new(B, 3) if pf.has_normal else None
         rgb = None if sigma_only else new(B, 3)
         mirror = None if (sigma_only or not pf.has_mirror) else new(B, 1)
         with torch.cuda.device(x.device):
             lib = _lib.load()
             _lib.check(lib.mnrf_field_eval_points(pf.handle, _lib.IMPL_FP32, _ptr(x), B, int(sigma_only), _ptr(sigma),
-                                                  _ptr(rgb), _ptr(mirror), _ptr(pred), None, None, _stream_ptr()),
+                                                  _ptr(rgb), _ptr(mirror), _ptr(pred), _ptr(normal), None, _stream_ptr()),
                        "mnrf_field_eval_points")
         out = {"sigma": sigma}
+        if normal is not None:
+            out["normal"] = normal
         if pred is not None:
             out["pred_normal"] = pred
         if not sigma_only:

@@ -126,13 +126,25 @@ def param_shapes(bound=1.0, predict_normal=True, predict_mirror_mask=True):
     return s
 
 
-def field_forward(p, x, bound=1.0, sigma_only=False):
-    """MirrorNeRFTcnn.forward with compute_normal=False (mirror_nerf_tcnn.py:151-259).  x: (B,6) = [xyz | d] or (B,3)."""
+def field_forward(p, x, bound=1.0, sigma_only=False, compute_normal=False):
+    """MirrorNeRFTcnn.forward (mirror_nerf_tcnn.py:151-259).  x: (B,6) = [xyz | d] or (B,3).  compute_normal: the analytic
+    normal normalize(-d sigma/d xyz) by autograd through the restated encoder (mirror_nerf_tcnn.py:170-178)."""
     xyz = x[:, :3]
-    h = hashgrid_encode(p["encoder.params"], (xyz + bound) / (2 * bound), bound)
-    h = F.relu(F.linear(h, p["sigma_net.0.weight"]))
-    h = F.linear(h, p["sigma_net.1.weight"])
-    out = {"sigma": h[:, 0:1], "geo_feat": h[:, 1:]}  # sigma raw (mirror_nerf_tcnn.py:233-234), shaped (B,1) like the MLP field
+    out = {}
+    if compute_normal:
+        with torch.enable_grad():
+            xyz = xyz.detach().clone().requires_grad_(True)
+            h = hashgrid_encode(p["encoder.params"], (xyz + bound) / (2 * bound), bound)
+            h = F.linear(F.relu(F.linear(h, p["sigma_net.0.weight"])), p["sigma_net.1.weight"])
+            sig = h[:, 0:1]
+            g = torch.autograd.grad(sig, xyz, torch.ones_like(sig), retain_graph=True)[0]
+        out["normal"] = l2_normalize(-g.detach())
+        if not any(t.requires_grad for t in p.values()):
+            h = h.detach()
+    else:
+        h = hashgrid_encode(p["encoder.params"], (xyz + bound) / (2 * bound), bound)
+        h = F.linear(F.relu(F.linear(h, p["sigma_net.0.weight"])), p["sigma_net.1.weight"])
+    out.update({"sigma": h[:, 0:1], "geo_feat": h[:, 1:]})  # sigma raw (mirror_nerf_tcnn.py:233-234), shaped (B,1) like the MLP field
     geo = out["geo_feat"]
     if "normal_net.0.weight" in p:
         nh = F.linear(F.relu(F.linear(geo, p["normal_net.0.weight"])), p["normal_net.1.weight"])

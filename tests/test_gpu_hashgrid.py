@@ -51,6 +51,12 @@ def test_hash_field_points_vs_oracle(bound):
         so = m(xyz.cuda(), compute_normal=False, sigma_only=True)
     assert set(so) == {"sigma", "pred_normal"}
     _close(so["sigma"], want["sigma"].flatten(), "sigma (sigma_only)")
+    # analytic normals: kernel's explicit derivative of the trilinear weights vs autograd through the restated encoder
+    want_n = H.field_forward(sd, x, bound=bound, compute_normal=True)["normal"]
+    with torch.no_grad():
+        got_n = m(x.cuda(), compute_normal=True)["normal"]
+    cos = (got_n.cpu() * want_n).sum(-1)
+    assert float(cos.median()) > 1 - 1e-6 and float((cos < 1 - 1e-3).float().mean()) <= 0.01, (float(cos.min()), float(cos.median()))
 
 
 def test_hash_field_without_heads_and_errors():
@@ -63,8 +69,9 @@ def test_hash_field_without_heads_and_errors():
         got = m(x.cuda(), compute_normal=False)
     assert set(got) == {"sigma", "rgb"}
     _close(got["rgb"], want["rgb"], "rgb")
-    with pytest.raises(NotImplementedError):
-        m(x.cuda())  # compute_normal defaults to True like the reference: analytic normals are not built for the hash grid
+    with torch.no_grad():
+        gn = m(x.cuda())  # compute_normal defaults to True like the reference
+    assert set(gn) == {"sigma", "rgb", "normal"}
     with pytest.raises(RuntimeError, match="CUDA"):
         m(x, compute_normal=False)
 
@@ -91,8 +98,16 @@ def test_render_rays_hash_field_vs_oracle():
         assert tuple(got[k].shape) == tuple(want[k].shape), k
         s = err_stats(got[k].cpu(), want[k])
         assert s["median"] <= 1e-4 and s["frac"] <= 0.05, fmt_stats(k, s)
-    with pytest.raises(NotImplementedError):
-        render_rays(models, emb, rays.cuda(), 64, False, 0, 0, 128, 32768, False, test_time=True)  # compute_normal=True
+    # compute_normal=True (the signature's default): analytic normals through the hash grid
+    want_n = O.render_rays(sds, rays, 64, False, 0, 0, 128, 32768, False, test_time=True, compute_normal=True,
+                           n_freqs_xyz=0, n_freqs_dir=0)
+    with torch.no_grad():
+        got_n = render_rays(models, emb, rays.cuda(), 64, False, 0, 0, 128, 32768, False, test_time=True)
+    assert set(got_n) == set(want_n), sorted(set(got_n) ^ set(want_n))
+    for k in ("normal_fine", "surface_normal_grad_fine", "normal_dif_fine", "rgb_fine"):
+        s = err_stats(got_n[k].cpu(), want_n[k])
+        # analytic normals jump at cell faces of the fine levels and at ReLU kinks: same allowance as the MLP-field tests
+        assert s["median"] <= 1e-4 and s["frac"] <= (0.13 if "normal" in k else 0.05), fmt_stats(k, s)
     with pytest.raises(NotImplementedError):
         render_rays(models, {"xyz": Embedding(10), "dir": Embedding(4)}, rays.cuda(), 64, False, 0, 0, 128, 32768, False,
                     test_time=True, compute_normal=False)
