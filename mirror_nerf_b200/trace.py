@@ -93,6 +93,13 @@ def render_rays_recursive(models, embeddings, rays, N_samples=64, use_disp=False
     (N_mirror,3) tensor to an (N_rays,3) one at level 0 -- a latent shape bug; the evident intent, mirror rays only, is
     what is implemented).  `normal_noises`: optional list of trace_ray_times+1 explicit (n,3) noise tensors (tests)."""
     kwargs.setdefault("compute_normal", False)
+    if render_fn is None and torch.is_grad_enabled() and any(
+            p.requires_grad for m in models.values() if hasattr(m, "parameters") for p in m.parameters()):
+        # the reflect / compact / blend kernels of this driver are not differentiable: refuse instead of silently cutting the graph
+        raise NotImplementedError(
+            "render_rays_recursive is the inference (eval-semantics) driver; for training call render_rays per level and build "
+            "the secondary rays / blend with torch ops as R/train.py:194-296 does (render_rays is differentiable w.r.t. "
+            "parameters and rays), or wrap this call in torch.no_grad()")
     if render_fn is not None:
         res = render_fn(rays)
     else:

@@ -428,3 +428,15 @@ def test_train_single_pass_tf32_speed_mode():
     cos = float((out[0] * out[1]).sum() / (out[0].norm() * out[1].norm()))
     print(f"tf32x1 vs tf32x3 gradient cosine {cos:.6f}")
     assert 0.99 <= cos < 1.0 - 1e-9  # close, but measurably not the same arithmetic
+
+
+def test_recursive_eval_driver_refuses_to_run_under_autograd():
+    from mirror_nerf_b200.synthetic import random_rays
+    from mirror_nerf_b200.trace import render_rays_recursive
+    models, emb = _models(_smooth_sds())
+    rays = random_rays(8, seed=1).cuda()
+    with pytest.raises(NotImplementedError, match="inference"):
+        render_rays_recursive(models, emb, rays, 64, False, 0, 0, 128, 32768, False, max_recursive_level=1)
+    with torch.no_grad():
+        r = render_rays_recursive(models, emb, rays, 64, False, 0, 0, 128, 32768, False, max_recursive_level=1)
+    assert "rgb_fine" in r
