@@ -429,6 +429,39 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": threads, "kind": "port",
                                 "sample": f"{args.ref_rays} rays of the same view, 64+128 samples, 1 bounce, 1 step"}
         line["psnr_vs_reference_db"] = (-10 * math.log10(mse) if mse > 0 else float("inf"))
+        # PSNR on a scene-like field: the analytic room scene (room_scene.py), field = tests/golden/room_field.npz (this repo's
+        # training path, tools/train_room.py); ours (1 bounce, eval semantics) and the oracle against the analytic ground truth
+        try:
+            import numpy as np
+            from mirror_nerf_b200.room_scene import room_pose, trace_room
+            from oracle import mirror_nerf_oracle as O
+            z = np.load(os.path.join(ROOT, "tests", "golden", "room_field.npz"))
+            sds = {"coarse": {}, "fine": {}}
+            for k in z.files:
+                tag, name = k.split("/", 1)
+                sds[tag][name] = torch.from_numpy(z[k].astype(np.float32))
+            rmodels = {}
+            for k, sd in sds.items():
+                m = MirrorNeRF(predict_normal=True, predict_mirror_mask=True)
+                m.load_state_dict(sd)
+                rmodels[k] = m.to(dev).eval()
+            allr = camera_rays(400, 400, c2w=room_pose(2), near=0.05, far=12.0)
+            rr = allr[torch.linspace(0, allr.shape[0] - 1, args.ref_rays).long()].contiguous()
+            gt, gt_mask, _ = trace_room(rr)
+            fn = lambda r: O.render_rays(sds, r, N_SAMPLES, False, 0, 0, N_IMPORTANCE, 32768, False, test_time=True,
+                                         compute_normal=False)
+            with torch.no_grad():
+                ref_rgb = O.trace_eval(fn, rr, 1)["rgb_fine"]
+                our_rgb = render_rays_recursive(rmodels, emb, rr.to(dev), N_SAMPLES, False, 0, 0, N_IMPORTANCE, 32768, False,
+                                                max_recursive_level=1, **kw)["rgb_fine"].cpu()
+            ps = lambda x: -10 * math.log10(float(((x - gt) ** 2).mean()))
+            line["psnr"] = {"ours_db": ps(our_rgb), "reference_db": ps(ref_rgb), "delta_db": ps(our_rgb) - ps(ref_rgb),
+                            "ours_vs_reference_db": -10 * math.log10(max(float(((our_rgb - ref_rgb) ** 2).mean()), 1e-20)),
+                            "rays": args.ref_rays, "mirror_ray_fraction": float(gt_mask.mean()),
+                            "scene": "analytic box room with a planar mirror (mirror_nerf_b200/room_scene.py); field fitted by "
+                                     "tools/train_room.py (3000 steps of this repo's training path), ground truth ray-traced"}
+        except Exception as e:  # the fixture is optional
+            line["psnr"] = {"unavailable": repr(e)}
         if "train_step" in line:
             line["train_step"]["cpu_baseline"] = {
                 "value": cpu_train_rate(128, threads), "unit": "rays/s", "cores": threads, "kind": "port",

@@ -548,3 +548,39 @@ def test_sharded_render_equals_unsharded_bitwise(mm):
             for k in ("rgb_fine", "depth_fine", "mirror_mask_fine", "weights_fine", "z_vals_fine", "surface_normal_fine"):
                 got = torch.cat([p[k] for p in parts], 0)
                 assert torch.equal(got, whole[k]), (world, k, float((got - whole[k]).abs().max()))
+
+
+def test_room_scene_parity_and_psnr(oracle):
+    """The north-star bar on a SCENE-LIKE field (tests/golden/room_field.npz: our training path fitted to the analytic room of
+    mirror_nerf_b200/room_scene.py): one bounce with eval semantics, ours (tc3) vs the oracle on the same rays --
+    rgb / depth within 1e-3 (relative to max(|want|, rms)) on >= 99 % of the rays, and PSNR against the analytic ground truth
+    within 0.05 dB of the reference's."""
+    import math
+    from mirror_nerf_b200.mirror_nerf import Embedding, MirrorNeRF
+    from mirror_nerf_b200.room_scene import room_pose, trace_room
+    from mirror_nerf_b200.synthetic import camera_rays
+    from mirror_nerf_b200.trace import render_rays_recursive
+    from util import room_state_dicts
+    sds = room_state_dicts()
+    models = {}
+    for k, sd in sds.items():
+        m = MirrorNeRF(predict_normal=True, predict_mirror_mask=True)
+        m.load_state_dict(sd)
+        models[k] = m.cuda().eval()
+    emb = {"xyz": Embedding(10), "dir": Embedding(4)}
+    allrays = camera_rays(200, 200, c2w=room_pose(1), near=0.05, far=12.0)
+    rays = allrays[torch.linspace(0, allrays.shape[0] - 1, 1536).long()].contiguous()
+    gt, gt_mask, _ = trace_room(rays)
+    fn = lambda r: oracle.render_rays(sds, r, 64, False, 0, 0, 128, 32768, False, test_time=True, compute_normal=False)
+    with torch.no_grad():
+        want = oracle.trace_eval(fn, rays, 1)
+        got = render_rays_recursive(models, emb, rays.cuda(), 64, False, 0, 0, 128, 32768, False, max_recursive_level=1)
+    for k in ("rgb_fine", "depth_fine", "opacity_fine"):
+        s = err_stats(got[k].cpu(), want[k])
+        assert s["median"] <= 1e-5 and s["frac"] <= 0.01, fmt_stats(k, s)
+    assert float((got["mirror_mask_fine"].cpu() != want["mirror_mask_fine"]).float().mean()) <= 0.002  # thresholded masks
+    psnr = lambda x: -10 * math.log10(float(((x - gt) ** 2).mean()))
+    p_ours, p_ref = psnr(got["rgb_fine"].cpu()), psnr(want["rgb_fine"])
+    print(f"room scene: PSNR ours {p_ours:.4f} dB, reference {p_ref:.4f} dB, mirror fraction {float(gt_mask.mean()):.3f}")
+    assert p_ref > 18.0, "fixture should be a fitted scene"
+    assert abs(p_ours - p_ref) <= 0.05

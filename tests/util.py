@@ -38,3 +38,16 @@ def err_stats(got, want, floor=None):
 
 def fmt_stats(name, s):
     return f"{name:28s} median {s['median']:.2e}  p99 {s['p99']:.2e}  max {s['max']:.2e}  frac>1e-3 {s['frac']:.4f}"
+
+
+def room_state_dicts():
+    """The scene-like field: this repo's training path fitted to the analytic room scene (tools/train_room.py, 3000 steps;
+    stored as fp16, used as fp32).  {"coarse": state_dict, "fine": state_dict}."""
+    import os
+    from collections import OrderedDict
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "room_field.npz"))
+    out = {"coarse": OrderedDict(), "fine": OrderedDict()}
+    for k in z.files:
+        tag, name = k.split("/", 1)
+        out[tag][name] = torch.from_numpy(z[k].astype(np.float32))
+    return out
