@@ -584,3 +584,10 @@ def test_room_scene_parity_and_psnr(oracle):
     print(f"room scene: PSNR ours {p_ours:.4f} dB, reference {p_ref:.4f} dB, mirror fraction {float(gt_mask.mean()):.3f}")
     assert p_ref > 18.0, "fixture should be a fitted scene"
     assert abs(p_ours - p_ref) <= 0.05
+    # the single-pass speed mode on the same scene (informational + the PSNR bar only: its per-ray errors are ~1e-3)
+    with torch.no_grad():
+        fast = render_rays_recursive(models, emb, rays.cuda(), 64, False, 0, 0, 128, 32768, False, max_recursive_level=1,
+                                     field_impl="tc1")
+    s1 = err_stats(fast["rgb_fine"].cpu(), want["rgb_fine"])
+    print(f"room scene, tc1: PSNR {psnr(fast['rgb_fine'].cpu()):.4f} dB; " + fmt_stats("rgb_fine", s1))
+    assert abs(psnr(fast["rgb_fine"].cpu()) - p_ref) <= 0.05
