@@ -280,6 +280,11 @@ struct GemmEpi {
   const float* cvec = nullptr;
   const float* mask = nullptr;  // act == 2: keep v where mask[row][col] > 0 (relu' of a saved activation), else 0
   int ld_mask = 0;
+  // the same mask as one bit per element, 8 words per row of 256 columns (bit c&31 of word c>>5): the tensor-core kernels read
+  // this (32 B per point, prefetched for a whole tile while the MMAs run) instead of the 1 KB activation row, and write it
+  // (bits_out) from the bias+ReLU epilogue of the forward trunk
+  const uint32_t* mask_bits = nullptr;
+  uint32_t* bits_out = nullptr;
   int act = 0;                  // 0 none | 1 relu | 2 mask | 3 leaky relu (0.01)
   int accumulate = 0;
 };

@@ -808,11 +808,21 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
   p[i] = pi - (lr / bc1) * (mi / denom);
 }
 
+// relu' bits of a [P,256] activation matrix: word w of row p holds columns 32w..32w+31 (CUDA-core engine; the tensor-core
+// forward epilogue writes the same words itself)
+__global__ void k_train_make_bits(const float* __restrict__ H, size_t n_words, uint32_t* __restrict__ bits) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one warp per word: lane = column inside the word
+  const size_t word = i >> 5;
+  if (word >= n_words) return;
+  const uint32_t b = __ballot_sync(0xffffffffu, H[word * 32 + (i & 31)] > 0.f);
+  if ((i & 31) == 0) bits[word] = b;
+}
+
 // ---- host-side helpers -----------------------------------------------------------------------------------------------
 inline size_t al(size_t b) { return (b + 255) & ~(size_t)255; }
 
 struct FwdWs {  // float offsets into the forward workspace
-  size_t pe, h[8], f, d1, n1, m1, raw, n2, dirbias, q[8], gpe, gx, nrm, total;
+  size_t pe, h[8], hb[8], f, d1, n1, m1, raw, n2, dirbias, q[8], gpe, gx, nrm, total;
 };
 FwdWs fwd_layout(int n, int S, int compute_normal) {
   const size_t P = (size_t)n * S;
@@ -821,6 +831,7 @@ FwdWs fwd_layout(int n, int S, int compute_normal) {
   auto take = [&](size_t floats) { size_t r = o; o += al(floats * sizeof(float)) / sizeof(float); return r; };
   L.pe = take(P * 64);
   for (int l = 0; l < 8; ++l) L.h[l] = take(P * W);
+  for (int l = 0; l < 8; ++l) L.hb[l] = take(P * 8);  // relu' bit masks (uint32 words)
   L.f = take(P * W);
   L.d1 = take(P * WH);
   L.n1 = take(P * WH);
@@ -981,16 +992,24 @@ int train_pass_fwd(const mnrf_field* f, const float* rays, const float* z, const
   k_train_pe<<<(P + 127) / 128, 128, 0, st>>>(rays, z, P, S, PE);
   MNRF_LAUNCH_OK();
   // trunk (mirror_nerf.py:189-197); the skip layer reads [pe | h4] as two K segments (PE column 63 is zero)
+  uint32_t* HB[8];
+  for (int l = 0; l < 8; ++l) HB[l] = reinterpret_cast<uint32_t*>(w + L.hb[l]);
   for (int l = 0; l < 8; ++l) {
     GemmEpi e;
     e.bias = F + FL.b_trunk[l];
     e.act = 1;
+    e.bits_out = HB[l];
     if (l == 0) {
       if (gemm_w(f, 0, PE, 64, 64, nullptr, 0, H[0], W, P, e, st)) return 1;
     } else if (l == 4) {
       if (gemm_w(f, 4, PE, 64, 64, H[3], W, H[4], W, P, e, st)) return 1;
     } else {
       if (gemm_w(f, l, H[l - 1], W, W, nullptr, 0, H[l], W, P, e, st)) return 1;
+    }
+    if (!use_tc()) {  // the CUDA-core GEMM has no bit-mask epilogue
+      const size_t nw = (size_t)P * 8;
+      k_train_make_bits<<<(unsigned)((nw * 32 + 255) / 256), 256, 0, st>>>(H[l], nw, HB[l]);
+      MNRF_LAUNCH_OK();
     }
   }
   // colour branch (mirror_nerf.py:199-204)
@@ -1027,7 +1046,7 @@ int train_pass_fwd(const mnrf_field* f, const float* rays, const float* z, const
     MNRF_LAUNCH_OK();
     for (int l = 7; l >= 1; --l) {  // q_{l-1} = (q_l W_l) * relu'(h_{l-1});  W_l = layer l+1 in 1-based naming
       GemmEpi e;
-      e.act = 2; e.mask = H[l - 1]; e.ld_mask = W;
+      e.act = 2; e.mask = H[l - 1]; e.ld_mask = W; e.mask_bits = HB[l - 1];
       if (gemm_w(f, chain_step(l), Q[l], W, W, nullptr, 0, Q[l - 1], W, P, e, st)) return 1;
     }
     GemmEpi e0;
@@ -1059,6 +1078,8 @@ int train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, const
   const float* PE = w + L.pe;
   const float* H[8];
   for (int l = 0; l < 8; ++l) H[l] = w + L.h[l];
+  const uint32_t* HB[8];
+  for (int l = 0; l < 8; ++l) HB[l] = reinterpret_cast<const uint32_t*>(w + L.hb[l]);
   const float* normal = cfg.compute_normal ? w + L.nrm : nullptr;
   const bool hn = f->has_normal != 0, hm = f->has_mirror != 0;
   for (int i = 0; i < 24; ++i) MNRF_REQUIRE(gt[i] != nullptr, "train_pass_bwd: gradient tensor %d missing", i);
@@ -1111,7 +1132,7 @@ int train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, const
   {
     GemmEpi last;  // the last GEMM of the sum carries the rank-1 sigma term and the relu' mask
     last.rvec = b + B.dr; last.ld_rvec = DR_STRIDE; last.cvec = F + FL.w_sigma;
-    last.act = 2; last.mask = H[7]; last.ld_mask = W;
+    last.act = 2; last.mask = H[7]; last.ld_mask = W; last.mask_bits = HB[7];
     GemmEpi plain;
     const int n_terms = 1 + (use_n ? 1 : 0) + (use_m ? 1 : 0);
     int term = 0;
@@ -1142,7 +1163,7 @@ int train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, const
     }
     if (l > 0) {  // dZ_{l-1} = (dZ_l W_l) * relu'(h_{l-1})
       GemmEpi e;
-      e.act = 2; e.mask = H[l - 1]; e.ld_mask = W;
+      e.act = 2; e.mask = H[l - 1]; e.ld_mask = W; e.mask_bits = HB[l - 1];
       if (gemm_w(f, chain_step(l), dZ, W, W, nullptr, 0, dZn, W, P, e, st)) return 1;
       float* t = dZ; dZ = dZn; dZn = t;
     }
@@ -1171,7 +1192,7 @@ int train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, const
       }
       // t_l = (t_{l-1} W_l^T) * relu'(h_l)
       GemmEpi e;
-      e.act = 2; e.mask = H[l]; e.ld_mask = W;
+      e.act = 2; e.mask = H[l]; e.ld_mask = W; e.mask_bits = HB[l];
       if (l == 0) {
         if (gemm_w(f, 0, T0, 64, 64, nullptr, 0, Tc, W, P, e, st)) return 1;
       } else if (l == 4) {

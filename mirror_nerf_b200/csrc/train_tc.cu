@@ -15,6 +15,7 @@
 // Per-unit cost: a 128 x 256 x 256 layer tile = 32 K8 steps x 3 passes x 128 cycles = 12.3k tensor cycles against
 // 128 KB read + 128 KB written (+128 KB mask) of HBM traffic: the unfused layer GEMMs sit at the HBM/tensor balance point.
 #include <cuda.h>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -69,7 +70,8 @@ __device__ __forceinline__ float act_apply(float v, int act, float m) {
 // MODE: 0 = generic (every feature decided at run time), 1 = bias + ReLU (forward trunk), 2 = ReLU-mask only (normal chain,
 // dgrad, tangent pass) -- the two hot flavours are compiled without the unused operand streams.
 template <int MODE>
-__device__ __forceinline__ void nn_epi_block(const NNParams& P, uint32_t tb, long long row_base, int rsub, int c4, int col) {
+__device__ __forceinline__ void nn_epi_block(const NNParams& P, uint32_t tb, long long row_base, int rsub, int c4, int col,
+                                             const uint32_t (&mbits)[8], bool have_bits) {
   const GemmEpi& e = P.e;
   const bool use_acc = MODE == 0 && e.accumulate, use_bias = MODE == 1 || (MODE == 0 && e.bias != nullptr);
   const bool use_rb = MODE == 0 && e.rowbias != nullptr, use_rv = MODE == 0 && e.rvec != nullptr;
@@ -80,7 +82,9 @@ __device__ __forceinline__ void nn_epi_block(const NNParams& P, uint32_t tb, lon
   // rows handled by this lane: row_base + rsub + 4*i; element offsets advance by 4 rows per i
   const long long r0 = row_base + rsub;
   float* cp = P.C + (size_t)r0 * P.ldc + col;
-  const float* mp = act == 2 ? e.mask + (size_t)r0 * e.ld_mask + col : nullptr;
+  const bool bitmask = act == 2 && have_bits;
+  const float* mp = (act == 2 && !bitmask) ? e.mask + (size_t)r0 * e.ld_mask + col : nullptr;
+  const int bsh = col & 31;
   const size_t cstep = (size_t)4 * P.ldc, mstep = (size_t)4 * e.ld_mask;
   const int rows_left = (int)min((long long)32, P.M - row_base) - rsub;  // rows r0 + 4*i with 4*i < rows_left exist
 #pragma unroll
@@ -94,7 +98,12 @@ __device__ __forceinline__ void nn_epi_block(const NNParams& P, uint32_t tb, lon
       cin[k] = make_float4(0.f, 0.f, 0.f, 0.f); mk[k] = cin[k]; rbv[k] = cin[k]; rv[k] = 0.f;
       if (ok) {
         if (use_acc) cin[k] = *reinterpret_cast<const float4*>(cp + i * cstep);
-        if (act == 2) mk[k] = *reinterpret_cast<const float4*>(mp + i * mstep);
+        if (bitmask) {
+          const uint32_t wb = mbits[i] >> bsh;
+          mk[k] = make_float4((wb & 1u) ? 1.f : 0.f, (wb & 2u) ? 1.f : 0.f, (wb & 4u) ? 1.f : 0.f, (wb & 8u) ? 1.f : 0.f);
+        } else if (act == 2) {
+          mk[k] = *reinterpret_cast<const float4*>(mp + i * mstep);
+        }
         if (use_rb) rbv[k] = *reinterpret_cast<const float4*>(e.rowbias + (size_t)((r0 + 4 * i) / e.rb_div) * e.ld_rb + col);
         if (use_rv) rv[k] = e.rvec[(size_t)(r0 + 4 * i) * e.ld_rvec];
       }
@@ -113,6 +122,14 @@ __device__ __forceinline__ void nn_epi_block(const NNParams& P, uint32_t tb, lon
       o.x = act_apply(v[0], act, mk[k].x); o.y = act_apply(v[1], act, mk[k].y);
       o.z = act_apply(v[2], act, mk[k].z); o.w = act_apply(v[3], act, mk[k].w);
       if (4 * i < rows_left) *reinterpret_cast<float4*>(cp + i * cstep) = o;
+      if (MODE == 1 && e.bits_out != nullptr) {
+        // relu' bits of this row's 32-column chunk: 4 bits per lane, OR-combined over the 8 lanes that share the row
+        uint32_t nib = ((o.x > 0.f ? 1u : 0u) | (o.y > 0.f ? 2u : 0u) | (o.z > 0.f ? 4u : 0u) | (o.w > 0.f ? 8u : 0u)) << (4 * c4);
+        nib |= __shfl_xor_sync(0xffffffffu, nib, 1);
+        nib |= __shfl_xor_sync(0xffffffffu, nib, 2);
+        nib |= __shfl_xor_sync(0xffffffffu, nib, 4);
+        if (c4 == 0 && 4 * i < rows_left) e.bits_out[(size_t)(r0 + 4 * i) * 8 + (col >> 5)] = nib;
+      }
     }
   }
 }
@@ -278,6 +295,18 @@ k_gemm_tc_nn(const NNParams P, const __grid_constant__ CUtensorMap tmA0, const _
       const int buf = t & 1;
       const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
       const long long row_base = tile * 128 + q * 32;
+      // relu' bit masks of this lane's 8 rows x this warp's 32-column chunks: fetched while the MMAs of the tile still run
+      uint32_t mw[4][8];
+      const bool have_bits = (MODE == 2 || MODE == 0) && P.e.act == 2 && P.e.mask_bits != nullptr;
+      if (have_bits) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const long long grow = row_base + rsub + 4 * i;
+            mw[c][i] = (c < nch && grow < P.M) ? __ldg(P.e.mask_bits + (size_t)grow * 8 + ((g * ncol + c * 32) >> 5)) : 0u;
+          }
+      }
       mbar_wait(bar(NB_ACC_FULL + buf), (uint32_t)((t >> 1) & 1));
       tc_fence_after();
       const uint32_t tcol = tlane + (uint32_t)buf * 256u + (uint32_t)(g * ncol);
@@ -297,7 +326,13 @@ k_gemm_tc_nn(const NNParams P, const __grid_constant__ CUtensorMap tmA0, const _
         for (int j = 0; j < 8; ++j) st_shared_v4(wrow + (uint32_t)((j ^ (lane & 7)) * 16), ra[4 * j], ra[4 * j + 1], ra[4 * j + 2], ra[4 * j + 3]);
         __syncwarp();
         const int col = g * ncol + c * 32 + c4 * 4;
-        if (!(P.dbg & 8)) nn_epi_block<MODE>(P, tb, row_base, rsub, c4, col);
+        if (!(P.dbg & 8)) {
+          // the chunk index selects the prefetched words at compile time (register array)
+          if (c == 0) nn_epi_block<MODE>(P, tb, row_base, rsub, c4, col, mw[0], have_bits);
+          else if (c == 1) nn_epi_block<MODE>(P, tb, row_base, rsub, c4, col, mw[1], have_bits);
+          else if (c == 2) nn_epi_block<MODE>(P, tb, row_base, rsub, c4, col, mw[2], have_bits);
+          else nn_epi_block<MODE>(P, tb, row_base, rsub, c4, col, mw[3], have_bits);
+        }
         __syncwarp();
       }
     }
@@ -583,6 +618,7 @@ int gemm_nn_tc(const mnrf_field* f, int step, const float* A0, int lda0, int K0,
   P.C = C; P.ldc = ldc; P.M = M; P.N = N; P.K = K;
   P.n_tiles = (M + 127) / 128;
   P.e = e;
+  if (getenv("MNRF_NO_BITS") != nullptr) P.e.mask_bits = nullptr;  // A/B switch: read the fp32 activation as the mask
   P.one_pass = g_one_pass;
   P.dbg = g_dbg;
   const int grid = P.n_tiles < sms ? P.n_tiles : sms;
