@@ -68,14 +68,15 @@ __device__ __forceinline__ float act_apply(float v, int act, float m) {
 // All global operands (C for accumulate, ReLU mask, per-ray term, rank-1 row factor) are fetched for four rows at a time BEFORE
 // the dependent arithmetic and stores, so that their latencies overlap instead of serialising the 8 iterations.
 // MODE: 0 = generic (every feature decided at run time), 1 = bias + ReLU (forward trunk), 2 = ReLU-mask only (normal chain,
-// dgrad, tangent pass) -- the two hot flavours are compiled without the unused operand streams.
+// dgrad, tangent pass), 3 = plain linear with optional bias (final, normal_net.0, dF, PE gradients) -- the hot flavours are
+// compiled without the unused operand streams.
 template <int MODE>
 __device__ __forceinline__ void nn_epi_block(const NNParams& P, uint32_t tb, long long row_base, int rsub, int c4, int col,
                                              const uint32_t (&mbits)[8], bool have_bits) {
   const GemmEpi& e = P.e;
-  const bool use_acc = MODE == 0 && e.accumulate, use_bias = MODE == 1 || (MODE == 0 && e.bias != nullptr);
+  const bool use_acc = MODE == 0 && e.accumulate, use_bias = MODE == 1 || ((MODE == 0 || MODE == 3) && e.bias != nullptr);
   const bool use_rb = MODE == 0 && e.rowbias != nullptr, use_rv = MODE == 0 && e.rvec != nullptr;
-  const int act = MODE == 1 ? 1 : (MODE == 2 ? 2 : e.act);
+  const int act = MODE == 1 ? 1 : (MODE == 2 ? 2 : (MODE == 3 ? 0 : e.act));
   float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), cv = bias;
   if (use_bias) bias = __ldg(reinterpret_cast<const float4*>(e.bias + col));
   if (use_rv) cv = __ldg(reinterpret_cast<const float4*>(e.cvec + col));
@@ -608,6 +609,7 @@ int gemm_nn_tc(const mnrf_field* f, int step, const float* A0, int lda0, int K0,
     MNRF_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nn<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SM_TOTAL));
     MNRF_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nn<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SM_TOTAL));
     MNRF_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nn<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SM_TOTAL));
+    MNRF_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nn<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SM_TOTAL));
     attr = true;
   }
   const int sms = num_sms();
@@ -629,6 +631,7 @@ int gemm_nn_tc(const mnrf_field* f, int step, const float* A0, int lda0, int K0,
   const bool plain = !e.accumulate && e.rowbias == nullptr && e.rvec == nullptr;
   if (plain && e.act == 1 && e.bias != nullptr) k_gemm_tc_nn<1><<<grid, NN_THREADS, NN_SM_TOTAL, st>>>(P, m0, m1);
   else if (plain && e.act == 2 && e.bias == nullptr) k_gemm_tc_nn<2><<<grid, NN_THREADS, NN_SM_TOTAL, st>>>(P, m0, m1);
+  else if (plain && e.act == 0) k_gemm_tc_nn<3><<<grid, NN_THREADS, NN_SM_TOTAL, st>>>(P, m0, m1);
   else k_gemm_tc_nn<0><<<grid, NN_THREADS, NN_SM_TOTAL, st>>>(P, m0, m1);
   MNRF_LAUNCH_OK();
   return 0;
