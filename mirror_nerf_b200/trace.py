@@ -7,8 +7,6 @@ in its callers).
 """
 from __future__ import annotations
 
-import ctypes as C
-
 import torch
 
 from . import _lib

@@ -3,7 +3,6 @@ The oracle restates tinycudann's published HashGrid algorithm (PARITY UNPINNED: 
 unpinned third-party CUDA extension -- see the oracle's header); what these tests pin is kernel == restatement.
 Tolerances: table indices are integer work (any mismatch shows up as O(1) feature errors); per-point outputs median <= 1e-5,
 p99 <= 1e-3 relative (fp32 on both sides, different summation order); rendered outputs like the MLP-field eval tests."""
-import numpy as np
 import pytest
 import torch
 

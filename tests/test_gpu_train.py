@@ -5,11 +5,10 @@ Tolerances.  Forward outputs: same distribution criteria as the eval-mode parity
 cosine similarity with the oracle gradient and relative norm error; on the smooth test field (sigma head x5) cos >= 0.9998
 and |norm ratio - 1| <= 3e-3 (24 rays; 0.997 / 1.5e-2 for the 12-ray variants); on the adversarial scene field (sigma head x40, where the reference's own outputs move by
 > 1e-3 under one-ulp input changes) cos >= 0.98 on the whole flattened gradient."""
-import numpy as np
 import pytest
 import torch
 
-from util import T, err_stats, fmt_stats
+from util import err_stats, fmt_stats
 
 pytestmark = pytest.mark.gpu
 
@@ -361,7 +360,6 @@ def test_train_full_size_engines_agree_and_gradients_are_linear():
     """BASELINE config-5 size (4096 rays x (64+128) samples, analytic normals), size-independent properties:
     (i) the tcgen05 tf32x3 GEMM engine and the fp32 CUDA-core twin produce the same gradients (cosine >= 0.9999 per large tensor);
     (ii) backward is linear in the cotangent: doubling the loss doubles every gradient (relative 1e-3; atomics reorder sums)."""
-    import ctypes as C
     from mirror_nerf_b200 import _lib
     from mirror_nerf_b200.rendering import render_rays
     from mirror_nerf_b200.synthetic import random_rays
