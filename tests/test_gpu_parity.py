@@ -11,7 +11,6 @@ Tolerances (north-star: ray/sample indices bit-exact; rgb/depth within 1e-3 rela
     discontinuous in sign(sigma_last) and re-ordering fp32 sums already moves 0.05-0.15 % of rays by > 1e-3):
     median <= 1e-4 and at most 3 % of entries off by more than 1e-3 (relative to max(|ref|, rms)).
 """
-import numpy as np
 import pytest
 import torch
 
