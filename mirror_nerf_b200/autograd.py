@@ -78,6 +78,7 @@ class _PassFn(torch.autograd.Function):
         return tuple(t[k] for k in ctx.out_keys)
 
     @staticmethod
+    @torch.autograd.function.once_differentiable  # the hand-written backward is not itself differentiable: fail loudly on create_graph
     def backward(ctx, *gouts):
         lib = _lib.load()
         meta, cfg = ctx.meta, ctx.cfg
