@@ -144,7 +144,7 @@ def train_loss(r, target, mask_gt):
     return loss
 
 
-def train_bench(dev, world, rank, steps, warmup):
+def train_bench(dev, world, rank, steps, warmup, peer_fused=False):
     """BASELINE config 5 on this rank: 4096-ray batch, train semantics (perturb=1, noise_std=1, analytic normals), forward +
     backward through csrc/train.cu + train_tc.cu, ONE flat NCCL all-reduce of the 5.3 MB gradient buffer, one Adam kernel.  Returns a dict."""
     import torch
@@ -160,7 +160,7 @@ def train_bench(dev, world, rank, steps, warmup):
         m.load_state_dict(sd)
         models[k] = m.to(dev).train()
     emb = {"xyz": Embedding(10), "dir": Embedding(4)}
-    ddp = FlatDataParallel(models, lr=5e-4)
+    ddp = FlatDataParallel(models, lr=5e-4, peer_fused=peer_fused and world > 1)
     g = torch.Generator().manual_seed(1234 + rank)
     allrays = camera_rays(H, W, c2w=view_pose(rank))
     rays = allrays[torch.randperm(allrays.shape[0], generator=g)[:TRAIN_RAYS]].contiguous().to(dev)
@@ -201,6 +201,8 @@ def train_bench(dev, world, rank, steps, warmup):
             "dtype": "tf32x3-split operands, f32 accumulate (tcgen05 kind::tf32; fp32-grade)", "launches_per_step": (_lib.launch_count() - l0) / steps,
             "algorithmic_tflops": rate / world * TRAIN_FLOP_PER_RAY / 1e12,
             "allreduce_bytes_per_step": ddp.flat_grads.numel() * 4 if world > 1 else 0,
+            "exchange": ("none" if world == 1 else ("fused peer-memory reduce-scatter + Adam + all-gather kernel (NVLink P2P)"
+                                                    if ddp.peer is not None else "ncclAllReduce (flat buffer) + Adam kernel")),
             "loss_first": float(losses[0]), "loss_last": float(losses[-1])}
 
 
@@ -415,7 +417,7 @@ def run_ours(args):
                            "gpu_launches_per_step": per_step, "normal_noise_std": 0.05, "trace_ray_times": 7}
 
     if not args.no_train:
-        line["train_step"] = train_bench(dev, world, rank, max(2, min(args.steps, 5)), 3)
+        line["train_step"] = train_bench(dev, world, rank, max(2, min(args.steps, 5)), 3, args.peer_fused)
         if rank == 0:
             line["hash_grid_level"] = hash_level_bench(dev, 3)
 
@@ -504,6 +506,8 @@ def main():
     ap.add_argument("--ref-rays", type=int, default=2048, help="rays per step of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--config4", action="store_true", help="also time BASELINE config 4 (2 bounces + roughness cone)")
+    ap.add_argument("--peer-fused", action="store_true",
+                    help="train step: one peer-memory kernel (reduce-scatter + Adam + all-gather) instead of ncclAllReduce + Adam")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary train-step measurement (config 5)")
     args = ap.parse_args()
     if args.impl == "reference":

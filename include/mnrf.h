@@ -263,6 +263,18 @@ int mnrf_debug_gemm_bench(const mnrf_field* f, int kind, int step, int P, int en
 int mnrf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                    float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
 
+/* The same data-parallel step as all-reduce + mnrf_adam_step, as ONE kernel over NVLink / NVSwitch peer memory: grad_ptrs /
+ * param_ptrs = HOST arrays of `world` (<= 8) device pointers to every rank's flat gradient / parameter buffer, peer-mapped
+ * into this process (e.g. torch.distributed._symmetric_memory buffer_ptrs).  Rank r owns the shard mnrf_peer_shard() returns:
+ * it sums that shard of all ranks' gradients (P2P loads), divides by world, applies Adam with its OWN moment shards
+ * (exp_avg_shard / exp_avg_sq_shard: hi-lo elements) and stores the new parameters into every rank's buffer (P2P stores).
+ * n must be a multiple of 4.  The caller orders ranks with a device-side barrier before (all gradients written) and after
+ * (all parameter shards visible).  Replaces PL DDP's all-reduce + torch.optim.Adam (R/train.py:582, R/utils/__init__.py:47-58). */
+int mnrf_peer_shard(int64_t n, int world, int rank, int64_t* lo, int64_t* hi);
+int mnrf_peer_allreduce_adam(const uint64_t* grad_ptrs, const uint64_t* param_ptrs, int world, int rank, float* exp_avg_shard,
+                             float* exp_avg_sq_shard, int64_t n, float lr, float beta1, float beta2, float eps,
+                             float weight_decay, int step, void* stream);
+
 /* out[i] += alpha * in[i] (fp32, n elements): gradient-buffer plumbing for the data-parallel all-reduce */
 int mnrf_axpy(float* out, const float* in, int64_t n, float alpha, void* stream);
 

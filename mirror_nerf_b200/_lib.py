@@ -100,6 +100,9 @@ _SIGS = {
     "mnrf_debug_gemm_bench": (c_int, [C.c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, C.POINTER(C.c_float)]),
     "mnrf_adam_step": (c_int, [c_float_p, c_float_p, c_float_p, c_float_p, C.c_int64, C.c_float, C.c_float, C.c_float,
                                C.c_float, C.c_float, c_int, C.c_float, C.c_void_p]),
+    "mnrf_peer_shard": (c_int, [C.c_int64, c_int, c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "mnrf_peer_allreduce_adam": (c_int, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), c_int, c_int, c_float_p, c_float_p,
+                                         C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, c_int, C.c_void_p]),
     "mnrf_axpy": (c_int, [c_float_p, c_float_p, C.c_int64, C.c_float, C.c_void_p]),
     "mnrf_reflect_rays": (c_int, [c_float_p, c_float_p, c_float_p, c_float_p, c_int, C.c_float, c_float_p, c_float_p,
                                   C.c_void_p, C.c_void_p]),

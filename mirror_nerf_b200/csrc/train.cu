@@ -12,6 +12,7 @@
 // Its backward (the reference gets it from create_graph=True, utils/func.py:10-25) is linear in the weights because
 // relu'' = 0: with t0 = J_pe dL/dg_x,  t_k = (t_{k-1} W_k^T) * relu'(z_k)  [a second "tangent" forward pass],
 //   dW_k += q_k^T t_{k-1},   d w_sigma += sum_p t8.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -818,6 +819,42 @@ __global__ void k_train_make_bits(const float* __restrict__ H, size_t n_words, u
   if ((i & 31) == 0) bits[word] = b;
 }
 
+// Data-parallel optimizer step over NVLink peer memory: reduce-scatter + Adam + all-gather in ONE kernel.  Every rank owns a
+// contiguous shard of the flat parameter vector: it sums that shard of the gradient over all ranks' (peer-mapped) gradient
+// buffers with 16-byte P2P loads, applies torch.optim.Adam to it (moment estimates exist only for the owned shard), and stores
+// the new parameters into every rank's parameter buffer with P2P stores.  Cross-rank ordering (gradients complete before /
+// parameters visible after) is the caller's device-side barrier on the symmetric-memory signal pads.
+struct PeerPtrs { float* p[8]; };
+__global__ void k_peer_allreduce_adam(PeerPtrs grads, PeerPtrs params, int world, long long lo, long long hi, float* __restrict__ m,
+                                      float* __restrict__ v, float lr, float beta1, float beta2, float eps, float weight_decay,
+                                      float bc1, float bc2_sqrt, float grad_scale, int rank) {
+  const long long i = lo + 4 * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
+  if (i >= hi) return;
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = 0; r < world; ++r) {
+    const float4 x = *reinterpret_cast<const float4*>(grads.p[r] + i);
+    g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
+  }
+  const float4 p4 = *reinterpret_cast<const float4*>(params.p[rank] + i);
+  float gv[4] = {g.x * grad_scale, g.y * grad_scale, g.z * grad_scale, g.w * grad_scale};
+  float pv[4] = {p4.x, p4.y, p4.z, p4.w};
+  const long long j = i - lo;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (i + k < hi) {
+      float gi = gv[k];
+      if (weight_decay != 0.f) gi = fmaf(weight_decay, pv[k], gi);
+      const float mi = beta1 * m[j + k] + (1.f - beta1) * gi;
+      const float vi = beta2 * v[j + k] + (1.f - beta2) * gi * gi;
+      m[j + k] = mi;
+      v[j + k] = vi;
+      pv[k] = pv[k] - (lr / bc1) * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+    }
+  }
+  const float4 out = make_float4(pv[0], pv[1], pv[2], pv[3]);
+  for (int r = 0; r < world; ++r) *reinterpret_cast<float4*>(params.p[r] + i) = out;
+}
+
 // ---- host-side helpers -----------------------------------------------------------------------------------------------
 inline size_t al(size_t b) { return (b + 255) & ~(size_t)255; }
 
@@ -1314,6 +1351,40 @@ int mnrf_adam_step(float* params, const float* grads, float* exp_avg, float* exp
   k_adam<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       params, grads, exp_avg, exp_avg_sq, (long long)n, lr, beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2),
       grad_scale);
+  MNRF_LAUNCH_OK();
+  return 0;
+}
+
+int mnrf_peer_shard(int64_t n, int world, int rank, int64_t* lo, int64_t* hi) {
+  MNRF_REQUIRE(n >= 0 && world >= 1 && rank >= 0 && rank < world && lo && hi, "peer_shard: bad argument");
+  int64_t chunk = (n + world - 1) / world;
+  chunk = (chunk + 3) / 4 * 4;  // 16-byte granules
+  *lo = std::min<int64_t>(n, chunk * rank);
+  *hi = std::min<int64_t>(n, chunk * (rank + 1));
+  return 0;
+}
+
+int mnrf_peer_allreduce_adam(const uint64_t* grad_ptrs, const uint64_t* param_ptrs, int world, int rank, float* exp_avg_shard,
+                             float* exp_avg_sq_shard, int64_t n, float lr, float beta1, float beta2, float eps,
+                             float weight_decay, int step, void* stream) {
+  MNRF_REQUIRE(grad_ptrs && param_ptrs && exp_avg_shard && exp_avg_sq_shard && step >= 1, "peer_allreduce_adam: bad argument");
+  MNRF_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "peer_allreduce_adam: 1 <= world <= 8");
+  MNRF_REQUIRE(n % 4 == 0, "peer_allreduce_adam: the flat buffers must be padded to a multiple of 4 elements");
+  int64_t lo, hi;
+  if (mnrf_peer_shard(n, world, rank, &lo, &hi)) return 2;
+  if (hi <= lo) return 0;
+  PeerPtrs g{}, p{};
+  for (int r = 0; r < world; ++r) {
+    MNRF_REQUIRE(grad_ptrs[r] != 0 && param_ptrs[r] != 0 && grad_ptrs[r] % 16 == 0 && param_ptrs[r] % 16 == 0,
+                 "peer_allreduce_adam: peer buffer %d missing or not 16-byte aligned", r);
+    g.p[r] = reinterpret_cast<float*>(grad_ptrs[r]);
+    p.p[r] = reinterpret_cast<float*>(param_ptrs[r]);
+  }
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  const long long quads = (hi - lo + 3) / 4;
+  k_peer_allreduce_adam<<<(unsigned)((quads + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      g, p, world, lo, hi, exp_avg_shard, exp_avg_sq_shard, lr, beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2),
+      1.f / (float)world, rank);
   MNRF_LAUNCH_OK();
   return 0;
 }

@@ -68,7 +68,11 @@ class FlatDataParallel:
     group (NCCL on GPUs; gloo in the CPU tests, where only the exchange is exercised -- the Adam kernel needs a GPU).
     """
 
-    def __init__(self, models, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, group=None):
+    def __init__(self, models, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, group=None, peer_fused=False):
+        """peer_fused=True (NCCL world > 1 on one NVLink/NVSwitch node): the flat buffers live in symmetric memory
+        (torch.distributed._symmetric_memory) and step() runs ONE kernel, mnrf_peer_allreduce_adam -- reduce-scatter of the
+        gradients with P2P loads, Adam on the owned shard (sharded moment estimates), all-gather of the new parameters with P2P
+        stores -- between two device-side barriers, instead of ncclAllReduce + mnrf_adam_step."""
         mods = list(models.values()) if isinstance(models, dict) else list(models)
         self.modules = mods
         self.params = [p for m in mods for p in m.parameters()]  # R/utils/__init__.py:33-45 order
@@ -78,8 +82,25 @@ class FlatDataParallel:
         if dt != torch.float32 or any(p.dtype != dt or p.device != dev for p in self.params):
             raise RuntimeError("FlatDataParallel: all parameters must be float32 on one device")
         n = sum(p.numel() for p in self.params)
-        self.flat_params = torch.empty(n, device=dev, dtype=dt)
-        self.flat_grads = torch.zeros(n, device=dev, dtype=dt)
+        self.n = n
+        self.peer = None
+        if peer_fused:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+            if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1 and dev.type == "cuda"):
+                raise RuntimeError("peer_fused=True needs an initialised NCCL process group with world_size > 1 on CUDA")
+            pg = group if group is not None else dist.group.WORLD
+            n_pad = (n + 3) // 4 * 4
+            self.flat_params = symm_mem.empty(n_pad, dtype=dt, device=dev)
+            self.flat_grads = symm_mem.empty(n_pad, dtype=dt, device=dev)
+            self.flat_params.zero_()
+            self.flat_grads.zero_()
+            hp = symm_mem.rendezvous(self.flat_params, pg.group_name)
+            hg = symm_mem.rendezvous(self.flat_grads, pg.group_name)
+            self.peer = dict(hp=hp, hg=hg, world=hp.world_size, rank=hp.rank, n_pad=n_pad)
+        else:
+            self.flat_params = torch.empty(n, device=dev, dtype=dt)
+            self.flat_grads = torch.zeros(n, device=dev, dtype=dt)
         o = 0
         with torch.no_grad():
             for p in self.params:
@@ -88,8 +109,17 @@ class FlatDataParallel:
                 p.data = self.flat_params[o:o + k].view(p.shape)
                 p.grad = self.flat_grads[o:o + k].view(p.shape)
                 o += k
-        self.exp_avg = torch.zeros_like(self.flat_params)
-        self.exp_avg_sq = torch.zeros_like(self.flat_params)
+        if self.peer is not None:
+            import ctypes as C
+            from . import _lib
+            lo, hi = C.c_int64(), C.c_int64()
+            _lib.check(_lib.load().mnrf_peer_shard(self.peer["n_pad"], self.peer["world"], self.peer["rank"], C.byref(lo), C.byref(hi)))
+            self.peer["shard"] = (lo.value, hi.value)
+            self.exp_avg = torch.zeros(max(hi.value - lo.value, 1), device=dev, dtype=dt)     # moments of the owned shard only
+            self.exp_avg_sq = torch.zeros_like(self.exp_avg)
+        else:
+            self.exp_avg = torch.zeros_like(self.flat_params)
+            self.exp_avg_sq = torch.zeros_like(self.flat_params)
         self.lr, self.betas, self.eps, self.weight_decay = float(lr), tuple(betas), float(eps), float(weight_decay)
         self.group = group
         self.step_count = 0
@@ -122,6 +152,8 @@ class FlatDataParallel:
         from .mirror_nerf import invalidate_packed
         if not self.flat_params.is_cuda:
             raise RuntimeError("FlatDataParallel.step: the optimizer kernel runs on CUDA only (no CPU path)")
+        if self.peer is not None:
+            return self._step_peer()
         self.all_reduce_grads()
         self.step_count += 1
         lib = _lib.load()
@@ -131,5 +163,26 @@ class FlatDataParallel:
                 C.c_void_p(self.exp_avg.data_ptr()), C.c_void_p(self.exp_avg_sq.data_ptr()), self.flat_params.numel(),
                 self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, self.step_count, 1.0 / self.world,
                 C.c_void_p(torch.cuda.current_stream().cuda_stream)), "mnrf_adam_step")
+        for m in self.modules:
+            invalidate_packed(m)
+
+    def _step_peer(self):
+        """reduce-scatter + Adam + all-gather as one kernel over peer memory, fenced by two device-side barriers."""
+        import ctypes as C
+        from . import _lib
+        from .mirror_nerf import invalidate_packed
+        pr = self.peer
+        self.step_count += 1
+        lib = _lib.load()
+        W = pr["world"]
+        gp = (C.c_uint64 * W)(*[int(x) for x in pr["hg"].buffer_ptrs])
+        pp = (C.c_uint64 * W)(*[int(x) for x in pr["hp"].buffer_ptrs])
+        with torch.cuda.device(self.flat_params.device):
+            pr["hg"].barrier(channel=0)   # every rank's backward has written its gradients
+            _lib.check(lib.mnrf_peer_allreduce_adam(
+                gp, pp, W, pr["rank"], C.c_void_p(self.exp_avg.data_ptr()), C.c_void_p(self.exp_avg_sq.data_ptr()), pr["n_pad"],
+                self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, self.step_count,
+                C.c_void_p(torch.cuda.current_stream().cuda_stream)), "mnrf_peer_allreduce_adam")
+            pr["hp"].barrier(channel=1)   # every owner's parameter shard has landed in this rank's buffer
         for m in self.modules:
             invalidate_packed(m)
