@@ -461,7 +461,7 @@ def run_ours(args):
                             "ours_vs_reference_db": -10 * math.log10(max(float(((our_rgb - ref_rgb) ** 2).mean()), 1e-20)),
                             "rays": args.ref_rays, "mirror_ray_fraction": float(gt_mask.mean()),
                             "scene": "analytic box room with a planar mirror (mirror_nerf_b200/room_scene.py); field fitted by "
-                                     "tools/train_room.py (3000 steps of this repo's training path), ground truth ray-traced"}
+                                     "tools/train_room.py (6000 steps of this repo's training path), ground truth ray-traced"}
         except Exception as e:  # the fixture is optional
             line["psnr"] = {"unavailable": repr(e)}
         if "train_step" in line:

@@ -41,7 +41,7 @@ def fmt_stats(name, s):
 
 
 def room_state_dicts():
-    """The scene-like field: this repo's training path fitted to the analytic room scene (tools/train_room.py, 3000 steps;
+    """The scene-like field: this repo's training path fitted to the analytic room scene (tools/train_room.py, 6000 steps, 33.7 dB;
     stored as fp16, used as fp32).  {"coarse": state_dict, "fine": state_dict}."""
     import os
     from collections import OrderedDict

@@ -2,7 +2,7 @@
 (render_rays under autograd, one-bounce recursion as R/train.py:194-296 does it with torch ops, FlatDataParallel Adam) and save
 the resulting *scene-like* field as tests/golden/room_field.npz (fp16 storage; loaded back as fp32).
 
-    python tools/train_room.py [--steps 3000] [--rays 4096] [--out tests/golden/room_field.npz]
+    python tools/train_room.py [--steps 6000] [--rays 4096] [--out tests/golden/room_field.npz]
 
 Prints the PSNR against the analytic ground truth on a held-out view as training proceeds."""
 import argparse, math, os, sys, time
@@ -18,7 +18,7 @@ from mirror_nerf_b200.synthetic import camera_rays
 from mirror_nerf_b200.trace import render_rays_recursive
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--steps", type=int, default=3000)
+ap.add_argument("--steps", type=int, default=6000)
 ap.add_argument("--rays", type=int, default=4096)
 ap.add_argument("--lr", type=float, default=5e-4)
 ap.add_argument("--out", default=os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "room_field.npz"))
