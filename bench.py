@@ -268,6 +268,44 @@ def cpu_train_rate(n_rays, threads):
     return n_rays / (time.perf_counter() - t0)
 
 
+def torch_cuda_baseline(dev):
+    """Informational: the reference's PyTorch arithmetic (oracle restatement, fp32, TF32 off) on the same B200 --
+    what the reference itself would do on this GPU.  Eval: 16,384 rays of the bench view, 1 bounce; train: one 1024-ray step."""
+    import torch
+    from mirror_nerf_b200.synthetic import camera_rays, scene_state_dicts
+    from oracle import mirror_nerf_oracle as O
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    params = scene_state_dicts(device=dev)
+    allrays = camera_rays(H, W, c2w=view_pose(0))
+    rays = allrays[torch.linspace(0, allrays.shape[0] - 1, 16384).long()].contiguous().to(dev)
+    fn = lambda r: O.render_rays(params, r, N_SAMPLES, False, 0, 0, N_IMPORTANCE, 32768, False, test_time=True,
+                                 compute_normal=False)
+    with torch.no_grad():
+        O.trace_eval(fn, rays[:2048], 1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        O.trace_eval(fn, rays, 1)
+        torch.cuda.synchronize()
+        eval_rate = rays.shape[0] / (time.perf_counter() - t0)
+    tp = {t: {k: v.clone().requires_grad_(True) for k, v in sd.items()} for t, sd in params.items()}
+    g = torch.Generator().manual_seed(1234)
+    n = 1024
+    tr = allrays[torch.randperm(allrays.shape[0], generator=g)[:n]].contiguous().to(dev)
+    target, mask_gt = torch.rand(n, 3, generator=g).to(dev), (torch.rand(n, generator=g) > 0.7).float().to(dev)
+    rates = []
+    for _ in range(2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = O.render_rays(tp, tr, N_SAMPLES, False, 1.0, 1.0, N_IMPORTANCE, 32768, False, test_time=False, compute_normal=True)
+        r["_rays_d"] = tr[:, 3:6]
+        train_loss(r, target, mask_gt).backward()
+        torch.cuda.synchronize()
+        rates.append(n / (time.perf_counter() - t0))
+    return {"eval_rays_per_s": eval_rate, "train_rays_per_s": rates[-1], "dtype": "f32 (torch CUDA, allow_tf32=False)",
+            "note": "oracle restatement of the reference's torch ops on this GPU; informational, not the reference arm"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -464,6 +502,10 @@ def run_ours(args):
                                      "tools/train_room.py (6000 steps of this repo's training path), ground truth ray-traced"}
         except Exception as e:  # the fixture is optional
             line["psnr"] = {"unavailable": repr(e)}
+        try:
+            line["torch_cuda_baseline"] = torch_cuda_baseline(dev)
+        except Exception as e:
+            line["torch_cuda_baseline"] = {"unavailable": repr(e)[:200]}
         if "train_step" in line:
             line["train_step"]["cpu_baseline"] = {
                 "value": cpu_train_rate(128, threads), "unit": "rays/s", "cores": threads, "kind": "port",
