@@ -17,6 +17,10 @@
  *   mnrf_render_level_host  same, HOST buffers in/out (what eval.py:1122-1138,735-736 does around it)
  *   mnrf_reflect_rays / mnrf_compact_rays / mnrf_blend_reflection
  *                           R/eval.py:295-320,515-548,676-697 and R/train.py:153-296 (Whitted bounce)
+ *   mnrf_train_pass_fwd/bwd implicit torch.autograd of R/models/rendering.py:87-266 + mirror_nerf.py:101-212 (training)
+ *   mnrf_adam_step / mnrf_peer_allreduce_adam
+ *                           R/utils/__init__.py:47-58 (torch.optim.Adam) + PL DDP gradient all-reduce (R/train.py:582)
+ *   mnrf_hash_field_create  R/models/mirror_nerf_tcnn.py:13-259 (MirrorNeRFTcnn: hash-grid field, inference)
  */
 #ifndef MNRF_H_
 #define MNRF_H_
@@ -60,8 +64,8 @@ int mnrf_field_has_mirror(const mnrf_field* f);
  *   is_mirror_net.2.{weight,bias} (1x32, 1) or NULL.
  * The level table (HOST arrays of 16: grid scale, resolution, first table entry, entries) is computed by the caller so that it
  * is defined in one place (mirror_nerf_b200/mirror_nerf_tcnn.py::level_table, following tinycudann's grid.h).
- * The returned object is used wherever a mnrf_field is accepted (mnrf_field_eval_*, mnrf_render_level*); analytic normals
- * (compute_normal) and gradients are not built for it.  Destroy with mnrf_field_destroy. */
+ * The returned object is used wherever a mnrf_field is accepted (mnrf_field_eval_*, mnrf_render_level*), including analytic
+ * normals (compute_normal); gradients (mnrf_train_*) are not built for it.  Destroy with mnrf_field_destroy. */
 int mnrf_hash_field_create(mnrf_field** out, const float* const* tensors, int64_t table_floats, float bound,
                            const float* level_scale, const int* level_res, const uint32_t* level_offset,
                            const uint32_t* level_size, void* stream);
