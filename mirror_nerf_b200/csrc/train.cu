@@ -1273,6 +1273,7 @@ int mnrf_train_pass_fwd(const mnrf_field* f, const float* rays, const float* z, 
                         const mnrf_train_cfg* cfg, void* ws, int64_t ws_bytes, const mnrf_composite_out* out,
                         float* normal_out, void* stream) {
   MNRF_REQUIRE(f && rays && z && cfg && ws && out, "train_pass_fwd: null argument");
+  MNRF_REQUIRE(f->kind == 0, "train_pass_fwd: gradients are built for the MirrorNeRF MLP field only (not the hash-grid field)");
   MNRF_REQUIRE(n >= 0 && cfg->S >= 1 && (long long)n * cfg->S < (1ll << 31) / 256, "train_pass_fwd: bad sizes");
   MNRF_REQUIRE(ws_bytes >= train_fwd_workspace_bytes(n, cfg->S, cfg->compute_normal), "train_pass_fwd: workspace too small");
   if (n == 0) return 0;
@@ -1284,6 +1285,7 @@ int mnrf_train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, 
                         int64_t ws_bwd_bytes, const mnrf_train_grads* grads, const float* ray_detach_mirror,
                         float* const* grad_tensors, const float* depth, float* grad_rays, void* stream) {
   MNRF_REQUIRE(f && rays && z && cfg && ws_fwd && ws_bwd && grads && grad_tensors, "train_pass_bwd: null argument");
+  MNRF_REQUIRE(f->kind == 0, "train_pass_bwd: gradients are built for the MirrorNeRF MLP field only (not the hash-grid field)");
   MNRF_REQUIRE(n >= 0 && cfg->S >= 1 && (long long)n * cfg->S < (1ll << 31) / 256, "train_pass_bwd: bad sizes");
   MNRF_REQUIRE(ws_fwd_bytes >= train_fwd_workspace_bytes(n, cfg->S, cfg->compute_normal) &&
                    ws_bwd_bytes >= train_bwd_workspace_bytes(n, cfg->S, cfg->compute_normal),
@@ -1296,7 +1298,7 @@ int mnrf_train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, 
 // Bring-up aid: time `iters` launches of one training GEMM on synthetic operands.  kind 0: NN step `step` on P rows; kind 1:
 // TN 256x256 over P rows.  engine 1 = tcgen05, 0 = CUDA cores.  dbg: train_tc.cu debug bits.  Returns milliseconds per launch.
 int mnrf_debug_gemm_bench(const mnrf_field* f, int kind, int step, int P, int engine, int dbg, int iters, float* ms_out) {
-  MNRF_REQUIRE(f && ms_out && P > 0 && iters > 0, "gemm_bench: bad argument");
+  MNRF_REQUIRE(f && ms_out && P > 0 && iters > 0 && f->kind == 0, "gemm_bench: bad argument");
   float *A = nullptr, *C = nullptr, *Wg = nullptr;
   MNRF_CUDA_OK(cudaMalloc(&A, sizeof(float) * (size_t)P * W));
   MNRF_CUDA_OK(cudaMalloc(&C, sizeof(float) * (size_t)P * W));
