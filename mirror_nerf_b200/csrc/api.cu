@@ -127,6 +127,7 @@ int mnrf_field_create(mnrf_field** out, const float* const* tensors, void* strea
   f->kind = 0;
   f->hash_table = nullptr;
   f->hash_w = nullptr;
+  f->hash_wref = nullptr;
   f->has_normal = hn;
   f->has_mirror = hm;
   f->L = make_f32_layout();
@@ -167,13 +168,14 @@ int mnrf_hash_field_create(mnrf_field** out, const float* const* tensors, int64_
   f->has_normal = hn;
   f->has_mirror = hm;
   f->f32 = nullptr; f->tc = nullptr; f->t32 = nullptr;
-  f->hash_table = nullptr; f->hash_w = nullptr;
+  f->hash_table = nullptr; f->hash_w = nullptr; f->hash_wref = nullptr;
   f->hg.bound = bound;
   for (int l = 0; l < HG_LEVELS; ++l) {
     f->hg.scale[l] = level_scale[l]; f->hg.res[l] = level_res[l]; f->hg.offset[l] = level_offset[l]; f->hg.size[l] = level_size[l];
   }
   if (cudaMalloc(&f->hash_table, sizeof(float) * (size_t)table_floats) != cudaSuccess ||
-      cudaMalloc(&f->hash_w, sizeof(float) * HW_TOTAL) != cudaSuccess) {
+      cudaMalloc(&f->hash_w, sizeof(float) * HW_TOTAL) != cudaSuccess ||
+      cudaMalloc(&f->hash_wref, sizeof(float) * HASH_WREF_FLOATS) != cudaSuccess) {
     set_error("hash_field_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
     mnrf_field_destroy(f);
     return 1;
@@ -198,6 +200,7 @@ void mnrf_field_destroy(mnrf_field* f) {
   if (f->t32) cudaFree(f->t32);
   if (f->hash_table) cudaFree(f->hash_table);
   if (f->hash_w) cudaFree(f->hash_w);
+  if (f->hash_wref) cudaFree(f->hash_wref);
   delete f;
 }
 int mnrf_field_has_normal(const mnrf_field* f) { return f ? f->has_normal : 0; }

@@ -170,12 +170,14 @@ struct HashGridMeta {
 // float offsets inside the packed weight block (rows padded to multiples of 4 inputs; see field_hash.cu)
 constexpr int HW_S0 = 0, HW_S1 = 2048, HW_C0 = 3072, HW_C1 = 5120, HW_C2 = 9216, HW_N0 = 9472, HW_N1 = 10496, HW_M0 = 10752,
               HW_M0B = 11264, HW_M2 = 11296, HW_M2B = 11328, HW_TOTAL = 11332;
+constexpr int HASH_WREF_FLOATS = 11044;  // the same weights in their reference layouts (hash_train_math.cuh: HT_NW_PAD)
 }  // namespace mnrf
 
 struct mnrf_field {
   int kind;          // 0 = MirrorNeRF MLP field, 1 = hash-grid field
   float* hash_table; // kind 1: device copy of encoder.params
   float* hash_w;     // kind 1: HW_TOTAL packed floats
+  float* hash_wref;  // kind 1: the small MLP weights in their reference layouts (hash_train_math.cuh offsets), for the backward
   mnrf::HashGridMeta hg;
   int has_normal;
   int has_mirror;
@@ -269,6 +271,17 @@ int launch_blend(const float* base, const float* mask, const float* child_rgb, c
 int launch_field_fp32(const mnrf_field* f, const FieldIO& io, cudaStream_t st);
 int launch_field_hash(const mnrf_field* f, const FieldIO& io, cudaStream_t st);
 int pack_hash_field(mnrf_field* f, const float* const* tensors, long long table_floats, cudaStream_t st);
+// training pass of the hash-grid field (train_hash.cu) and the compositor backward it shares with the MLP field (train.cu)
+int64_t hash_train_fwd_workspace_bytes(int n, int S, int compute_normal);
+int64_t hash_train_bwd_workspace_bytes(int n, int S, int compute_normal);
+int hash_train_pass_fwd(const mnrf_field* f, const float* rays, const float* z, const float* noise, int n,
+                        const mnrf_train_cfg& cfg, void* ws, const mnrf_composite_out& out, float* normal_out, cudaStream_t st);
+int hash_train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, const float* noise, int n,
+                        const mnrf_train_cfg& cfg, const void* ws_fwd, void* ws_bwd, const mnrf_train_grads& g,
+                        const float* ray_detach_mirror, float* const* gt, const float* depth, float* grad_rays, cudaStream_t st);
+int launch_composite_bwd(const float* rays, const float* z, const float* raw, const float* normal, const float* noise,
+                         const mnrf_train_cfg& cfg, int n, const float* ray_detach_mirror, const mnrf_train_grads& g, float* DR,
+                         cudaStream_t st);
 
 // epilogue of the training GEMMs:  v = acc [+ C] [+ bias[col]] [+ rowbias[row / rb_div][col]] [+ rvec[row] * cvec[col]];  act(v)
 struct GemmEpi {

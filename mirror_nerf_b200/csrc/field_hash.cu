@@ -12,10 +12,12 @@
 // kernel was shared-memory-bandwidth bound: ncu L1/TEX 77 %).  The tiny last layers (64->3, 64->3, 32->1) are fused into
 // the tile epilogue of the layer before them (partial dots + two shuffles).  fp32 throughout (tinycudann evaluates in fp16).
 #include "common.cuh"
+#include "hash_train_math.cuh"
 
 namespace mnrf {
 namespace {
 
+static_assert(HASH_WREF_FLOATS == ht::HT_NW_PAD, "reference-layout weight block size");
 constexpr int HB = 128;        // threads per block = 4 warps x 32 points
 constexpr int HX = 64 * 32;    // floats of one per-warp activation buffer: [64 features][32 points]
 constexpr int H_SMEM_FLOATS = HW_TOTAL + 4 * 2 * HX;
@@ -385,6 +387,12 @@ int pack_hash_field(mnrf_field* f, const float* const* t, long long table_floats
   if (pack_rows(t[9], w + HW_M0B, 1, 32, 32, 1, st)) return 1;
   if (pack_rows(t[10], w + HW_M2, 1, 32, 32, 1, st)) return 1;
   if (pack_rows(t[11], w + HW_M2B, 1, 1, 4, 1, st)) return 1;
+  // reference-layout copy for the backward (train_hash.cu); absent heads stay zero
+  MNRF_CUDA_OK(cudaMemsetAsync(f->hash_wref, 0, sizeof(float) * HASH_WREF_FLOATS, st));
+  for (int i = 1; i < 12; ++i)
+    if (t[i] != nullptr)
+      MNRF_CUDA_OK(cudaMemcpyAsync(f->hash_wref + ht::small_offset(i), t[i], sizeof(float) * ht::small_count(i),
+                                   cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 

@@ -1007,6 +1007,19 @@ int gemm_g(const float* A, int lda, int NA, const float* B, int ldb, int NB, flo
 
 }  // namespace
 
+// compositor backward alone (also the first step of the hash-grid field's backward, train_hash.cu): DR (n*S, 12)
+int launch_composite_bwd(const float* rays, const float* z, const float* raw, const float* normal, const float* noise,
+                         const mnrf_train_cfg& cfg, int n, const float* ray_detach_mirror, const mnrf_train_grads& g, float* DR,
+                         cudaStream_t st) {
+  static_assert(DR_STRIDE == 12, "train_hash.cu reads 12-float gradient records");
+  MNRF_REQUIRE(cfg.S <= CB_MAXS, "train_pass_bwd: S <= %d", CB_MAXS);
+  k_train_composite_bwd<<<(n + CB_WARPS - 1) / CB_WARPS, CB_WARPS * 32, 0, st>>>(
+      rays, z, raw, normal, noise, cfg.noise_std, n, cfg.S, cfg.white_back, cfg.detach_density_for_mask_loss,
+      cfg.detach_density_for_normal_loss, ray_detach_mirror, g, DR);
+  MNRF_LAUNCH_OK();
+  return 0;
+}
+
 int64_t train_fwd_workspace_bytes(int n, int S, int compute_normal) {
   return (int64_t)(fwd_layout(n, S, compute_normal).total * sizeof(float));
 }
@@ -1124,11 +1137,7 @@ int train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, const
   if (hm) for (int i = 28; i < 32; ++i) MNRF_REQUIRE(gt[i] != nullptr, "train_pass_bwd: gradient tensor %d missing", i);
 
   // 1. compositor backward -> per-point record
-  MNRF_REQUIRE(S <= CB_MAXS, "train_pass_bwd: S <= %d", CB_MAXS);
-  k_train_composite_bwd<<<(n + CB_WARPS - 1) / CB_WARPS, CB_WARPS * 32, 0, st>>>(
-      rays, z, w + L.raw, normal, noise, cfg.noise_std, n, S, cfg.white_back, cfg.detach_density_for_mask_loss,
-      cfg.detach_density_for_normal_loss, ray_detach_mirror, g, b + B.dr);
-  MNRF_LAUNCH_OK();
+  if (launch_composite_bwd(rays, z, w + L.raw, normal, noise, cfg, n, ray_detach_mirror, g, b + B.dr, st)) return 1;
 
   // 2. heads backward (small weights' gradients; gradients of the 128-wide hidden rows)
   HeadW hw{F + FL.w_sigma, F + FL.b_sigma, F + FL.w_rgb, F + FL.b_rgb, F + FL.w_n1, F + FL.b_n1, F + FL.w_m2, F + FL.b_m2};
@@ -1269,14 +1278,24 @@ int64_t mnrf_train_bwd_workspace_bytes(int n, int S, int compute_normal) {
   return train_bwd_workspace_bytes(n, S, compute_normal);
 }
 
+int64_t mnrf_field_train_fwd_workspace_bytes(const mnrf_field* f, int n, int S, int compute_normal) {
+  if (f == nullptr || n < 0 || S < 1) return -1;
+  return f->kind == 1 ? hash_train_fwd_workspace_bytes(n, S, compute_normal) : train_fwd_workspace_bytes(n, S, compute_normal);
+}
+int64_t mnrf_field_train_bwd_workspace_bytes(const mnrf_field* f, int n, int S, int compute_normal) {
+  if (f == nullptr || n < 0 || S < 1) return -1;
+  return f->kind == 1 ? hash_train_bwd_workspace_bytes(n, S, compute_normal) : train_bwd_workspace_bytes(n, S, compute_normal);
+}
+
 int mnrf_train_pass_fwd(const mnrf_field* f, const float* rays, const float* z, const float* noise, int n,
                         const mnrf_train_cfg* cfg, void* ws, int64_t ws_bytes, const mnrf_composite_out* out,
                         float* normal_out, void* stream) {
   MNRF_REQUIRE(f && rays && z && cfg && ws && out, "train_pass_fwd: null argument");
-  MNRF_REQUIRE(f->kind == 0, "train_pass_fwd: gradients are built for the MirrorNeRF MLP field only (not the hash-grid field)");
   MNRF_REQUIRE(n >= 0 && cfg->S >= 1 && (long long)n * cfg->S < (1ll << 31) / 256, "train_pass_fwd: bad sizes");
-  MNRF_REQUIRE(ws_bytes >= train_fwd_workspace_bytes(n, cfg->S, cfg->compute_normal), "train_pass_fwd: workspace too small");
+  MNRF_REQUIRE(ws_bytes >= mnrf_field_train_fwd_workspace_bytes(f, n, cfg->S, cfg->compute_normal), "train_pass_fwd: workspace too small");
   if (n == 0) return 0;
+  if (f->kind == 1)
+    return hash_train_pass_fwd(f, rays, z, noise, n, *cfg, ws, *out, normal_out, reinterpret_cast<cudaStream_t>(stream));
   return train_pass_fwd(f, rays, z, noise, n, *cfg, ws, *out, normal_out, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -1285,12 +1304,14 @@ int mnrf_train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, 
                         int64_t ws_bwd_bytes, const mnrf_train_grads* grads, const float* ray_detach_mirror,
                         float* const* grad_tensors, const float* depth, float* grad_rays, void* stream) {
   MNRF_REQUIRE(f && rays && z && cfg && ws_fwd && ws_bwd && grads && grad_tensors, "train_pass_bwd: null argument");
-  MNRF_REQUIRE(f->kind == 0, "train_pass_bwd: gradients are built for the MirrorNeRF MLP field only (not the hash-grid field)");
   MNRF_REQUIRE(n >= 0 && cfg->S >= 1 && (long long)n * cfg->S < (1ll << 31) / 256, "train_pass_bwd: bad sizes");
-  MNRF_REQUIRE(ws_fwd_bytes >= train_fwd_workspace_bytes(n, cfg->S, cfg->compute_normal) &&
-                   ws_bwd_bytes >= train_bwd_workspace_bytes(n, cfg->S, cfg->compute_normal),
+  MNRF_REQUIRE(ws_fwd_bytes >= mnrf_field_train_fwd_workspace_bytes(f, n, cfg->S, cfg->compute_normal) &&
+                   ws_bwd_bytes >= mnrf_field_train_bwd_workspace_bytes(f, n, cfg->S, cfg->compute_normal),
                "train_pass_bwd: workspace too small");
   if (n == 0) return 0;
+  if (f->kind == 1)
+    return hash_train_pass_bwd(f, rays, z, noise, n, *cfg, ws_fwd, ws_bwd, *grads, ray_detach_mirror, grad_tensors, depth,
+                               grad_rays, reinterpret_cast<cudaStream_t>(stream));
   return train_pass_bwd(f, rays, z, noise, n, *cfg, ws_fwd, ws_bwd, *grads, ray_detach_mirror, grad_tensors, depth,
                         grad_rays, reinterpret_cast<cudaStream_t>(stream));
 }

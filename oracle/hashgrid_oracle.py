@@ -126,20 +126,28 @@ def param_shapes(bound=1.0, predict_normal=True, predict_mirror_mask=True):
     return s
 
 
-def field_forward(p, x, bound=1.0, sigma_only=False, compute_normal=False):
+def field_forward(p, x, bound=1.0, sigma_only=False, compute_normal=False, mirror_mask=None,
+                  detach_density_outside_mirror_for_mask_loss=False, detach_density_for_mask_loss=False,
+                  detach_density_for_normal_loss=False):
     """MirrorNeRFTcnn.forward (mirror_nerf_tcnn.py:151-259).  x: (B,6) = [xyz | d] or (B,3).  compute_normal: the analytic
-    normal normalize(-d sigma/d xyz) by autograd through the restated encoder (mirror_nerf_tcnn.py:170-178)."""
+    normal normalize(-d sigma/d xyz) by autograd through the restated encoder (mirror_nerf_tcnn.py:170-178); when gradients are
+    being recorded (a parameter or x requires grad) the graph of that derivative is kept (create_graph=True, R/utils/func.py:
+    10-25), so losses on the normal reach the table and sigma_net by double backward, as in the reference."""
     xyz = x[:, :3]
     out = {}
+    train = torch.is_grad_enabled() and (x.requires_grad or any(t.requires_grad for t in p.values()))
     if compute_normal:
         with torch.enable_grad():
-            xyz = xyz.detach().clone().requires_grad_(True)
+            if not (train and xyz.requires_grad):
+                xyz = xyz.detach().clone().requires_grad_(True)
             h = hashgrid_encode(p["encoder.params"], (xyz + bound) / (2 * bound), bound)
             h = F.linear(F.relu(F.linear(h, p["sigma_net.0.weight"])), p["sigma_net.1.weight"])
             sig = h[:, 0:1]
-            g = torch.autograd.grad(sig, xyz, torch.ones_like(sig), retain_graph=True)[0]
-        out["normal"] = l2_normalize(-g.detach())
-        if not any(t.requires_grad for t in p.values()):
+            g = torch.autograd.grad(sig, xyz, torch.ones_like(sig), retain_graph=True, create_graph=train)[0]
+        if train:
+            out["normal"] = l2_normalize(-g)
+        else:
+            out["normal"] = l2_normalize(-g.detach())
             h = h.detach()
     else:
         h = hashgrid_encode(p["encoder.params"], (xyz + bound) / (2 * bound), bound)
@@ -147,7 +155,8 @@ def field_forward(p, x, bound=1.0, sigma_only=False, compute_normal=False):
     out.update({"sigma": h[:, 0:1], "geo_feat": h[:, 1:]})  # sigma raw (mirror_nerf_tcnn.py:233-234), shaped (B,1) like the MLP field
     geo = out["geo_feat"]
     if "normal_net.0.weight" in p:
-        nh = F.linear(F.relu(F.linear(geo, p["normal_net.0.weight"])), p["normal_net.1.weight"])
+        gn = geo.detach() if detach_density_for_normal_loss else geo  # mirror_nerf_tcnn.py:186-191
+        nh = F.linear(F.relu(F.linear(gn, p["normal_net.0.weight"])), p["normal_net.1.weight"])
         out["pred_normal"] = l2_normalize(nh)
     if not sigma_only:
         c = torch.cat([sh4(x[:, 3:6]), geo], -1)
@@ -155,7 +164,14 @@ def field_forward(p, x, bound=1.0, sigma_only=False, compute_normal=False):
         c = F.relu(F.linear(c, p["color_net.1.weight"]))
         out["rgb"] = torch.sigmoid(F.linear(c, p["color_net.2.weight"]))
         if "is_mirror_net.0.weight" in p:
-            m = F.leaky_relu(F.linear(geo, p["is_mirror_net.0.weight"], p["is_mirror_net.0.bias"]), 0.01)
+            gm = geo
+            if detach_density_for_mask_loss:  # mirror_nerf_tcnn.py:199-216
+                gm = geo.detach()
+            elif (detach_density_outside_mirror_for_mask_loss and mirror_mask is not None
+                  and not bool((mirror_mask < 0).any())):
+                keep = mirror_mask.clone().bool().unsqueeze(-1)
+                gm = torch.where(keep, geo, geo.detach())
+            m = F.leaky_relu(F.linear(gm, p["is_mirror_net.0.weight"], p["is_mirror_net.0.bias"]), 0.01)
             out["is_mirror"] = torch.sigmoid(F.linear(m, p["is_mirror_net.2.weight"], p["is_mirror_net.2.bias"]))
     return out
 

@@ -321,7 +321,7 @@ def render_rays(params, rays, N_samples=64, use_disp=False, perturb=0, noise_std
             if "encoder.params" in p:  # nerf_tcnn model family (oracle/hashgrid_oracle.py; identity embeddings)
                 from . import hashgrid_oracle as HG
                 o = HG.field_forward(p, xin, bound=kw.get("bound", 1.0), sigma_only=sig_only,
-                                     compute_normal=compute_normal and not sig_only)
+                                     compute_normal=compute_normal and not sig_only, mirror_mask=mmc, **flags)
             else:
                 o = field_forward(p, xin, n_freqs_xyz=n_freqs_xyz, in_dir=in_dir, compute_normal=compute_normal,
                                   sigma_only=sig_only, mirror_mask=mmc, **flags)
