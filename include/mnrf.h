@@ -20,7 +20,8 @@
  *   mnrf_train_pass_fwd/bwd implicit torch.autograd of R/models/rendering.py:87-266 + mirror_nerf.py:101-212 (training)
  *   mnrf_adam_step / mnrf_peer_allreduce_adam
  *                           R/utils/__init__.py:47-58 (torch.optim.Adam) + PL DDP gradient all-reduce (R/train.py:582)
- *   mnrf_hash_field_create  R/models/mirror_nerf_tcnn.py:13-259 (MirrorNeRFTcnn: hash-grid field, inference)
+ *   mnrf_hash_field_create  R/models/mirror_nerf_tcnn.py:13-259 (MirrorNeRFTcnn: hash-grid field; its gradients come from
+ *                           mnrf_train_pass_fwd/bwd with a hash-grid handle: tinycudann's grid backward + torch.autograd)
  */
 #ifndef MNRF_H_
 #define MNRF_H_
@@ -51,7 +52,8 @@ typedef struct mnrf_field mnrf_field; /* opaque: device-resident packed weights 
 
 /* Pack the 32 tensors (HOST array of DEVICE pointers) into the kernel formats.  Asynchronous on stream. */
 int mnrf_field_create(mnrf_field** out, const float* const* tensors, void* stream);
-/* Re-pack after the parameters changed (optimizer step).  Same tensor set (heads may not appear/disappear). */
+/* Re-pack after the parameters changed (optimizer step).  Same tensor set (heads may not appear/disappear).  For a hash-grid
+ * field `tensors` are the 12 pointers of mnrf_hash_field_create (same table size). */
 int mnrf_field_update(mnrf_field* f, const float* const* tensors, void* stream);
 void mnrf_field_destroy(mnrf_field* f);
 int mnrf_field_has_normal(const mnrf_field* f);
@@ -65,7 +67,7 @@ int mnrf_field_has_mirror(const mnrf_field* f);
  * The level table (HOST arrays of 16: grid scale, resolution, first table entry, entries) is computed by the caller so that it
  * is defined in one place (mirror_nerf_b200/mirror_nerf_tcnn.py::level_table, following tinycudann's grid.h).
  * The returned object is used wherever a mnrf_field is accepted (mnrf_field_eval_*, mnrf_render_level*), including analytic
- * normals (compute_normal); gradients (mnrf_train_*) are not built for it.  Destroy with mnrf_field_destroy. */
+ * normals (compute_normal) and the training pass (mnrf_train_pass_fwd/bwd).  Destroy with mnrf_field_destroy. */
 int mnrf_hash_field_create(mnrf_field** out, const float* const* tensors, int64_t table_floats, float bound,
                            const float* level_scale, const int* level_res, const uint32_t* level_offset,
                            const uint32_t* level_size, void* stream);
@@ -229,8 +231,11 @@ typedef struct mnrf_train_grads {
   const float* normal;              /* (n,S,3) */
 } mnrf_train_grads;
 
-int64_t mnrf_train_fwd_workspace_bytes(int n, int S, int compute_normal);
-int64_t mnrf_train_bwd_workspace_bytes(int n, int S, int compute_normal);
+int64_t mnrf_train_fwd_workspace_bytes(int n, int S, int compute_normal); /* MLP field */
+int64_t mnrf_train_bwd_workspace_bytes(int n, int S, int compute_normal); /* MLP field */
+/* the same for any field handle (the hash-grid field recomputes its forward in the backward and needs 44 / 80 bytes per point) */
+int64_t mnrf_field_train_fwd_workspace_bytes(const mnrf_field* f, int n, int S, int compute_normal);
+int64_t mnrf_field_train_bwd_workspace_bytes(const mnrf_field* f, int n, int S, int compute_normal);
 
 /* Forward: rays (n,8), z (n,S), noise (n,S) or NULL.  Writes the compositor outputs (`out`, same meaning as
  * mnrf_composite) and, when cfg->compute_normal, the per-sample analytic normals normal_out (n,S,3).
@@ -241,6 +246,9 @@ int mnrf_train_pass_fwd(const mnrf_field* f, const float* rays, const float* z, 
 
 /* Backward.  grad_tensors: HOST array of 32 DEVICE pointers in mnrf_field_create order, each the size of its
  * parameter ([out,in] layout), ACCUMULATED into (zero them first for plain gradients); entries of absent heads NULL.
+ * For a hash-grid field: 12 pointers in mnrf_hash_field_create order (entry 0 = gradient of encoder.params, table_floats
+ * elements, scatter-added with atomics as tinycudann's grid backward does; R/models/mirror_nerf_tcnn.py:151-259 under
+ * torch.autograd, incl. the double backward through the analytic normal of :170-178).
  * ray_detach_mirror: optional (n) floats, != 0 marks rays whose density is detached from the mirror-mask loss
  * (detach_density_outside_mirror_for_mask_loss, mirror_nerf.py:171-183 / rendering.py:227-238: rays outside the
  * ground-truth mirror).  grad_rays: optional (n,8) OVERWRITTEN with dL/d[o, d, near, far] (near/far columns zero); it needs

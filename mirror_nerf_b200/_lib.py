@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmnrf.so")
 IMPL_TC3, IMPL_TC1, IMPL_FP32 = 3, 1, 0
 IMPL_BY_NAME = {"tc3": IMPL_TC3, "tc1": IMPL_TC1, "fp32": IMPL_FP32}
 NUM_PARAM_TENSORS = 32
+NUM_HASH_PARAM_TENSORS = 12
 RAW_STRIDE = 8
 
 c_float_p = C.c_void_p  # device or host pointers are passed as integers
@@ -91,6 +92,8 @@ _SIGS = {
                                        C.c_void_p]),
     "mnrf_train_fwd_workspace_bytes": (C.c_int64, [c_int, c_int, c_int]),
     "mnrf_train_bwd_workspace_bytes": (C.c_int64, [c_int, c_int, c_int]),
+    "mnrf_field_train_fwd_workspace_bytes": (C.c_int64, [C.c_void_p, c_int, c_int, c_int]),
+    "mnrf_field_train_bwd_workspace_bytes": (C.c_int64, [C.c_void_p, c_int, c_int, c_int]),
     "mnrf_train_pass_fwd": (c_int, [C.c_void_p, c_float_p, c_float_p, c_float_p, c_int, C.POINTER(TrainCfg), C.c_void_p,
                                     C.c_int64, C.POINTER(CompositeOut), c_float_p, C.c_void_p]),
     "mnrf_train_pass_bwd": (c_int, [C.c_void_p, c_float_p, c_float_p, c_float_p, c_int, C.POINTER(TrainCfg), C.c_void_p,

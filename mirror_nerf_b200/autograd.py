@@ -6,6 +6,10 @@ One ``torch.autograd.Function`` per pass (field at the samples of a ray batch ->
 backward, including the double backward through the analytic normals).  torch is only the plumbing: it owns the memory,
 routes the output gradients into the Function and the parameter gradients into ``.grad``.
 
+The same Function serves both field kinds: the MirrorNeRF MLP (32 parameter tensors, csrc/train.cu + train_tc.cu) and the
+hash-grid field MirrorNeRFTcnn (12 parameter tensors incl. the hash table, csrc/train_hash.cu); the library dispatches on the
+field handle.
+
 Rays that require grad (secondary rays built from x_surface / surface normals, train.py:194-243) receive dL/d[o, d] as
 well.  ``z_vals_*`` carry no gradient, as in the reference (rendering.py:335,353 detach the fine depths; the coarse depths
 depend on near / far only).
@@ -27,10 +31,10 @@ _OUT_ORDER = ("weights", "opacity", "rgb", "depth", "mirror_mask", "normal", "su
               "surface_normal", "normal_dif", "x_surface")
 
 
-def _present_params(module):
-    """(keys, tensors): the module's parameters in PARAM_KEYS order (absent heads skipped)."""
+def _present_params(module, all_keys=PARAM_KEYS):
+    """(keys, tensors): the module's parameters in ABI order (absent heads skipped)."""
     named = dict(module.named_parameters())
-    keys = [k for k in PARAM_KEYS if k in named]
+    keys = [k for k in all_keys if k in named]
     return keys, [named[k] for k in keys]
 
 
@@ -61,7 +65,7 @@ class _PassFn(torch.autograd.Function):
                             detach_density_for_mask_loss=int(meta["detach_mask"]),
                             detach_density_for_normal_loss=int(meta["detach_normal"]))
         with torch.cuda.device(dev):
-            need = int(lib.mnrf_train_fwd_workspace_bytes(n, S, cn))
+            need = int(lib.mnrf_field_train_fwd_workspace_bytes(pf.handle, n, S, cn))
             ws = torch.empty(max(need, 1), device=dev, dtype=torch.uint8)
             p = lambda k: _ptr(t.get(k))
             out = _lib.CompositeOut(weights=p("weights"), opacity=p("opacity"), rgb=p("rgb"), depth=p("depth"),
@@ -92,10 +96,11 @@ class _PassFn(torch.autograd.Function):
         grads = _lib.TrainGrads(**{k: _ptr(g.get(k)) for k in _lib.TRAIN_GRAD_FIELDS})
         # gradient tensors in the reference's parameter order / layout; absent heads stay NULL
         gts = {k: torch.zeros(shp, device=dev, dtype=torch.float32) for k, shp in zip(meta["keys"], ctx.param_shapes)}
-        arr = (C.c_void_p * _lib.NUM_PARAM_TENSORS)(*[None if k not in gts else gts[k].data_ptr() for k in PARAM_KEYS])
+        all_keys = meta["all_keys"]  # the ABI's tensor order for this field kind (32 MLP tensors / 12 hash-grid tensors)
+        arr = (C.c_void_p * len(all_keys))(*[None if k not in gts else gts[k].data_ptr() for k in all_keys])
         grad_rays = torch.empty(n, 8, device=dev, dtype=torch.float32) if ctx.needs_input_grad[1] else None
         with torch.cuda.device(dev):
-            need = int(lib.mnrf_train_bwd_workspace_bytes(n, S, cfg.compute_normal))
+            need = int(lib.mnrf_field_train_bwd_workspace_bytes(pf.handle, n, S, cfg.compute_normal))
             wsb = torch.empty(max(need, 1), device=dev, dtype=torch.uint8)
             _lib.check(lib.mnrf_train_pass_bwd(pf.handle, _ptr(ctx.rays), _ptr(ctx.z), _ptr(ctx.noise), n, C.byref(cfg),
                                                _ptr(ctx.ws), ctx.ws_bytes, _ptr(wsb), need, C.byref(grads),
@@ -106,9 +111,12 @@ class _PassFn(torch.autograd.Function):
 
 def run_pass(module, rays, z, noise, ray_detach, *, compute_normal, white_back, noise_std, detach_mask, detach_normal):
     """One differentiable pass.  Returns {name: tensor} (without the _coarse/_fine suffix)."""
-    pf = packed_field(module)
-    keys, params = _present_params(module)
-    meta = dict(field=pf, keys=keys, compute_normal=compute_normal, white_back=white_back, noise_std=noise_std,
+    from .mirror_nerf_tcnn import HASH_PARAM_KEYS, is_hash_field, packed_hash_field
+    hashed = is_hash_field(module)
+    pf = packed_hash_field(module) if hashed else packed_field(module)
+    all_keys = HASH_PARAM_KEYS if hashed else PARAM_KEYS
+    keys, params = _present_params(module, all_keys)
+    meta = dict(field=pf, keys=keys, all_keys=all_keys, compute_normal=compute_normal, white_back=white_back, noise_std=noise_std,
                 detach_mask=detach_mask, detach_normal=detach_normal)
     outs = _PassFn.apply(meta, rays, z, noise, ray_detach, *params)
     names = [k for k in _OUT_ORDER if (k not in ("mirror_mask",) or pf.has_mirror)

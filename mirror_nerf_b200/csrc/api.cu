@@ -187,7 +187,16 @@ int mnrf_hash_field_create(mnrf_field** out, const float* const* tensors, int64_
 
 int mnrf_field_update(mnrf_field* f, const float* const* tensors, void* stream) {
   MNRF_REQUIRE(f != nullptr && tensors != nullptr, "field_update: null argument");
-  MNRF_REQUIRE(f->kind == 0, "field_update: hash-grid fields are re-created, not updated");
+  if (f->kind == 1) {  // hash-grid field: tensors = the 12 pointers of mnrf_hash_field_create; same table size and head set
+    for (int i = 0; i < 6; ++i) MNRF_REQUIRE(tensors[i] != nullptr, "field_update: hash-grid tensor %d is required", i);
+    MNRF_REQUIRE((tensors[6] != nullptr) == (f->has_normal != 0) && (tensors[7] != nullptr) == (f->has_normal != 0) &&
+                     (tensors[8] != nullptr) == (f->has_mirror != 0),
+                 "field_update: head set changed");
+    for (int i = 9; i < 12; ++i) MNRF_REQUIRE((tensors[i] != nullptr) == (f->has_mirror != 0), "field_update: head set changed");
+    long long table_floats = 0;
+    for (int l = 0; l < HG_LEVELS; ++l) table_floats = std::max(table_floats, ((long long)f->hg.offset[l] + f->hg.size[l]) * 2);
+    return pack_hash_field(f, tensors, table_floats, S_(stream));
+  }
   MNRF_REQUIRE((tensors[T_N0_W] != nullptr) == (f->has_normal != 0) && (tensors[T_M0_W] != nullptr) == (f->has_mirror != 0),
                "field_update: head set changed");
   return pack_field(f, tensors, S_(stream));

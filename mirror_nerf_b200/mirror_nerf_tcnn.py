@@ -4,8 +4,9 @@ the reference's constructor arguments and ``state_dict`` keys (``encoder.params`
 whose forward runs ``csrc/field_hash.cu``.  ``render_rays`` accepts these modules in ``models`` together with the identity
 embeddings ``Embedding(0)`` the reference uses for this model (R/train.py:69-70).
 
-The encoder follows tinycudann's HashGrid algorithm (parity unpinned, see oracle/hashgrid_oracle.py).  Inference only
-(predicted and analytic normals); gradients are not built for this field.
+The encoder follows tinycudann's HashGrid algorithm (parity unpinned, see oracle/hashgrid_oracle.py).  Gradients (hash table,
+small MLPs, rays, double backward through the analytic normal) flow through ``render_rays`` (autograd.py -> csrc/train_hash.cu);
+calling ``forward`` directly is inference only.
 """
 from __future__ import annotations
 
@@ -75,6 +76,11 @@ class PackedHashField:
         self.has_mirror = bool(self._lib.mnrf_field_has_mirror(self.handle))
         self.kind = "hash"
 
+    def update(self, tensors):
+        """Re-pack in place after an optimizer step (same table size and head set)."""
+        arr = (C.c_void_p * 12)(*[None if t is None else t.data_ptr() for t in tensors])
+        _lib.check(self._lib.mnrf_field_update(self.handle, arr, _stream_ptr()), "mnrf_field_update")
+
     def __del__(self):
         try:
             if getattr(self, "handle", None) and self.handle.value:
@@ -119,8 +125,15 @@ def packed_hash_field(module) -> PackedHashField:
                            f"bound={bound} (16 levels x 2 features, 2^19 hash map, base resolution 16)")
     key = tuple((None if t is None else (t.data_ptr(), t._version)) for t in tensors) + (bound,)
     cached = module.__dict__.get("_mnrf_packed")
-    if cached is not None and cached[1] == key and cached[2] == tensors[0].device:
-        return cached[0]
+    if cached is not None and cached[2] == tensors[0].device:
+        if cached[1] == key:
+            return cached[0]
+        if cached[1] is not None and cached[1][-1] == bound and \
+                tuple(e is None for e in cached[1][:-1]) == tuple(t is None for t in tensors):
+            with torch.cuda.device(tensors[0].device):
+                cached[0].update(tensors)  # parameters changed (optimizer step): re-pack in place
+            module.__dict__["_mnrf_packed"] = (cached[0], key, tensors[0].device)
+            return cached[0]
     with torch.cuda.device(tensors[0].device):
         pf = PackedHashField(tensors, bound)
     module.__dict__["_mnrf_packed"] = (pf, key, tensors[0].device)
@@ -167,7 +180,8 @@ class MirrorNeRFTcnn(nn.Module):
         if compute_normal and sigma_only:
             raise NotImplementedError("MirrorNeRFTcnn: analytic normals need the full pass (sigma_only=False)")
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError("MirrorNeRFTcnn: gradients are not built for the hash-grid field; use torch.no_grad()")
+            raise NotImplementedError("MirrorNeRFTcnn.forward is inference only (call it under torch.no_grad()); gradients of "
+                                      "the hash-grid field flow through render_rays")
         width = 3 if sigma_only else 6
         if x.dim() != 2 or x.shape[1] != width:
             raise RuntimeError(f"MirrorNeRFTcnn.forward: expected x of shape (B,{width}), got {tuple(x.shape)}")

@@ -194,8 +194,6 @@ def render_rays(models, embeddings, rays, N_samples=64, use_disp=False, perturb=
         params += list(models["fine"].parameters())
     needs_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in params) or rays_in.requires_grad)
 
-    if hashed and needs_grad:
-        raise NotImplementedError("hash-grid field: inference only (call under torch.no_grad()); gradients are not built for it")
     coarse = pack(models["coarse"])
     fine = pack(models["fine"]) if (has_fine_model and not only_one_field) else None
     # NB rendering.py:139 tests '"fine" in models' for the sigma-only shortcut
