@@ -206,6 +206,80 @@ def train_bench(dev, world, rank, steps, warmup, peer_fused=False):
             "loss_first": float(losses[0]), "loss_last": float(losses[-1])}
 
 
+def hash_models(dev, sigma_scale=20.0):
+    """Synthetic nerf_tcnn model pair: table ~ U(-1,1) (a trained table is O(1)), nn.Linear-style small MLPs."""
+    import numpy as np
+    import torch
+    from mirror_nerf_b200.mirror_nerf_tcnn import MirrorNeRFTcnn
+    models = {}
+    for k, seed in (("coarse", 7), ("fine", 8)):
+        m = MirrorNeRFTcnn(bound=1, predict_normal=True, predict_mirror_mask=True)
+        g = np.random.Generator(np.random.PCG64(seed))
+        with torch.no_grad():
+            for name, p in m.named_parameters():
+                lim = 1.0 if name == "encoder.params" else 1.0 / (p.shape[-1] ** 0.5)
+                p.copy_(torch.from_numpy(g.uniform(-lim, lim, size=tuple(p.shape)).astype(np.float32)))
+            m.sigma_net[1].weight[0] *= sigma_scale
+        models[k] = m.to(dev).eval()
+    return models
+
+
+def hash_train_bench(dev, steps, warmup=2):
+    """BASELINE config 3 under train.py semantics: one optimisation step of the hash-grid model pair on a 4096-ray batch
+    (64+128 samples, perturb=1, noise_std=1, analytic normals with their double backward): forward (csrc/field_hash.cu) +
+    backward (csrc/train_hash.cu: recompute, table scatter, small-MLP gradients) + one Adam kernel over the flat 24.4 M-parameter
+    buffer (two tables of 12.2 M fp32 entries).  Returns a dict."""
+    import torch
+    from mirror_nerf_b200 import _lib
+    from mirror_nerf_b200.mirror_nerf import Embedding
+    from mirror_nerf_b200.parallel import FlatDataParallel
+    from mirror_nerf_b200.rendering import render_rays
+    from mirror_nerf_b200.synthetic import camera_rays
+    models = hash_models(dev, sigma_scale=5.0)
+    for m in models.values():
+        m.train()
+    emb = {"xyz": Embedding(0), "dir": Embedding(0)}
+    ddp = FlatDataParallel(models, lr=1e-3)
+    g = torch.Generator().manual_seed(4321)
+    c2w = torch.tensor([[1.0, 0, 0, 0], [0, 1.0, 0, 0], [0, 0, 1.0, 0.9]])
+    allrays = camera_rays(H, W, c2w=c2w, near=0.05, far=2.0)
+    rays = allrays[torch.randperm(allrays.shape[0], generator=g)[:TRAIN_RAYS]].contiguous().to(dev)
+    target = torch.rand(TRAIN_RAYS, 3, generator=g).to(dev)
+    mask_gt = (torch.rand(TRAIN_RAYS, generator=g) > 0.7).float().to(dev)
+    losses = []
+
+    def one():
+        ddp.zero_grad()
+        r = render_rays(models, emb, rays, N_SAMPLES, False, 1.0, 1.0, N_IMPORTANCE, 32768, False, test_time=False,
+                        compute_normal=True)
+        r["_rays_d"] = rays[:, 3:6]
+        loss = train_loss(r, target, mask_gt)
+        loss.backward()
+        ddp.step()
+        losses.append(loss.detach())
+
+    for _ in range(warmup):
+        one()
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    points = TRAIN_RAYS * (N_SAMPLES + N_SAMPLES + N_IMPORTANCE)
+    return {"metric": "rays/sec (hash-grid train step: forward + backward + Adam; 4096-ray batch, 64+128 samples, analytic "
+                      "normals, fp32)",
+            "value": TRAIN_RAYS / ms * 1e3, "unit": "rays/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
+            "dtype": "f32 (CUDA cores; gather / scatter-atomic bound)", "launches_per_step": (_lib.launch_count() - l0) / steps,
+            "points_per_step": points, "table_atomics_per_step": points * 16 * 8 * 2,
+            "parameters": int(ddp.flat_params.numel()), "loss_first": float(losses[0]), "loss_last": float(losses[-1]),
+            "note": "parity unpinned for the encoder (DESIGN.md 3.5); gradients pinned to the oracle's autograd "
+                    "(tests/test_gpu_hashgrid.py, tests/test_hash_train_emu.py)"}
+
+
 def hash_level_bench(dev, steps):
     """BASELINE config 3 shape: one eval render level (64+128 samples) of an 800x800 view with the hash-grid field
     (nerf_tcnn family; synthetic table and weights).  Returns a dict (rays/s per level)."""
@@ -215,16 +289,7 @@ def hash_level_bench(dev, steps):
     from mirror_nerf_b200.mirror_nerf_tcnn import MirrorNeRFTcnn
     from mirror_nerf_b200.rendering import render_rays
     from mirror_nerf_b200.synthetic import camera_rays
-    models = {}
-    for k, seed in (("coarse", 7), ("fine", 8)):
-        m = MirrorNeRFTcnn(bound=1, predict_normal=True, predict_mirror_mask=True)
-        g = np.random.Generator(np.random.PCG64(seed))
-        with torch.no_grad():
-            for name, p in m.named_parameters():
-                lim = 1.0 if name == "encoder.params" else 1.0 / (p.shape[-1] ** 0.5)
-                p.copy_(torch.from_numpy(g.uniform(-lim, lim, size=tuple(p.shape)).astype(np.float32)))
-            m.sigma_net[1].weight[0] *= 20.0
-        models[k] = m.to(dev).eval()
+    models = hash_models(dev)
     emb = {"xyz": Embedding(0), "dir": Embedding(0)}
     c2w = torch.tensor([[1.0, 0, 0, 0], [0, 1.0, 0, 0], [0, 0, 1.0, 0.9]])
     rays = camera_rays(H, W, c2w=c2w, near=0.05, far=2.0).to(dev)
@@ -510,6 +575,11 @@ def run_ours(args):
             line["train_step"]["cpu_baseline"] = {
                 "value": cpu_train_rate(128, threads), "unit": "rays/s", "cores": threads, "kind": "port",
                 "sample": "one 128-ray train step (forward + backward) of the oracle port on the host cores"}
+    if rank == 0 and world == 1 and not args.no_train:
+        try:  # last GPU work of the run: a failure here cannot touch the numbers above
+            line["hash_grid_train_step"] = hash_train_bench(dev, 3)
+        except Exception as e:
+            line["hash_grid_train_step"] = {"unavailable": repr(e)[:300]}
     if rank == 0:
         emit(line)
     if world > 1:

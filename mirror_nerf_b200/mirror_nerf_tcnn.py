@@ -75,6 +75,7 @@ class PackedHashField:
         self.has_normal = bool(self._lib.mnrf_field_has_normal(self.handle))
         self.has_mirror = bool(self._lib.mnrf_field_has_mirror(self.handle))
         self.kind = "hash"
+        self.bound, self.table_floats = float(bound), int(tensors[0].numel())
 
     def update(self, tensors):
         """Re-pack in place after an optimizer step (same table size and head set)."""
@@ -128,8 +129,9 @@ def packed_hash_field(module) -> PackedHashField:
     if cached is not None and cached[2] == tensors[0].device:
         if cached[1] == key:
             return cached[0]
-        if cached[1] is not None and cached[1][-1] == bound and \
-                tuple(e is None for e in cached[1][:-1]) == tuple(t is None for t in tensors):
+        pf = cached[0]  # a None key = invalidated by a raw optimizer kernel (parallel.FlatDataParallel.step)
+        if pf.bound == bound and pf.has_normal == (tensors[6] is not None) and pf.has_mirror == (tensors[8] is not None) \
+                and pf.table_floats == tensors[0].numel():
             with torch.cuda.device(tensors[0].device):
                 cached[0].update(tensors)  # parameters changed (optimizer step): re-pack in place
             module.__dict__["_mnrf_packed"] = (cached[0], key, tensors[0].device)
