@@ -170,14 +170,14 @@ struct HashGridMeta {
 // float offsets inside the packed weight block (rows padded to multiples of 4 inputs; see field_hash.cu)
 constexpr int HW_S0 = 0, HW_S1 = 2048, HW_C0 = 3072, HW_C1 = 5120, HW_C2 = 9216, HW_N0 = 9472, HW_N1 = 10496, HW_M0 = 10752,
               HW_M0B = 11264, HW_M2 = 11296, HW_M2B = 11328, HW_TOTAL = 11332;
-constexpr int HASH_WREF_FLOATS = 11044;  // the same weights in their reference layouts (hash_train_math.cuh: HT_NW_PAD)
+constexpr int HASH_WREF_FLOATS = 11204;  // the same weights as [out][in] rows padded to 4 inputs (hash_train_math.cuh: HT_NW)
 }  // namespace mnrf
 
 struct mnrf_field {
   int kind;          // 0 = MirrorNeRF MLP field, 1 = hash-grid field
   float* hash_table; // kind 1: device copy of encoder.params
   float* hash_w;     // kind 1: HW_TOTAL packed floats
-  float* hash_wref;  // kind 1: the small MLP weights in their reference layouts (hash_train_math.cuh offsets), for the backward
+  float* hash_wref;  // kind 1: the small MLP weights as [out][in] rows padded to 4 inputs (hash_train_math.cuh offsets), for the backward
   mnrf::HashGridMeta hg;
   int has_normal;
   int has_mirror;

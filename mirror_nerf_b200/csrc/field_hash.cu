@@ -17,7 +17,7 @@
 namespace mnrf {
 namespace {
 
-static_assert(HASH_WREF_FLOATS == ht::HT_NW_PAD, "reference-layout weight block size");
+static_assert(HASH_WREF_FLOATS == ht::HT_NW, "row-padded weight block size");
 constexpr int HB = 128;        // threads per block = 4 warps x 32 points
 constexpr int HX = 64 * 32;    // floats of one per-warp activation buffer: [64 features][32 points]
 constexpr int H_SMEM_FLOATS = HW_TOTAL + 4 * 2 * HX;
@@ -357,6 +357,14 @@ __global__ void k_hash_pack_rows(const float* __restrict__ src, float* __restric
   dst[i] = (src != nullptr && r < rows && c < cols) ? src[(size_t)r * ld + c] : 0.f;
 }
 
+// the row-padded [out][in] image of small tensor t (hash_train_math.cuh): dst[r][small_col(t, c)] = src[r][c]
+__global__ void k_hash_pack_wref(const float* __restrict__ src, float* __restrict__ dst, int t, int rows, int cols, int ld) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const int r = i / cols, c = i - r * cols;
+  dst[r * ld + ht::small_col(t, c)] = src[i];
+}
+
 int pack_rows(const float* src, float* dst, int rows, int cols, int cols_pad, int rows_pad, cudaStream_t st) {
   const int n = rows_pad * cols_pad;
   k_hash_pack_rows<<<(n + 255) / 256, 256, 0, st>>>(src, dst, rows, cols, cols, cols_pad, rows_pad);
@@ -387,12 +395,15 @@ int pack_hash_field(mnrf_field* f, const float* const* t, long long table_floats
   if (pack_rows(t[9], w + HW_M0B, 1, 32, 32, 1, st)) return 1;
   if (pack_rows(t[10], w + HW_M2, 1, 32, 32, 1, st)) return 1;
   if (pack_rows(t[11], w + HW_M2B, 1, 1, 4, 1, st)) return 1;
-  // reference-layout copy for the backward (train_hash.cu); absent heads stay zero
+  // [out][in] image with 16-byte aligned rows for the backward (train_hash.cu); pad columns and absent heads stay zero
   MNRF_CUDA_OK(cudaMemsetAsync(f->hash_wref, 0, sizeof(float) * HASH_WREF_FLOATS, st));
-  for (int i = 1; i < 12; ++i)
-    if (t[i] != nullptr)
-      MNRF_CUDA_OK(cudaMemcpyAsync(f->hash_wref + ht::small_offset(i), t[i], sizeof(float) * ht::small_count(i),
-                                   cudaMemcpyDeviceToDevice, st));
+  for (int i = 1; i < 12; ++i) {
+    if (t[i] == nullptr) continue;
+    const int n = ht::small_rows(i) * ht::small_cols(i);
+    k_hash_pack_wref<<<(n + 255) / 256, 256, 0, st>>>(t[i], f->hash_wref + ht::small_offset(i), i, ht::small_rows(i),
+                                                      ht::small_cols(i), ht::small_ld(i));
+    MNRF_LAUNCH_OK();
+  }
   return 0;
 }
 

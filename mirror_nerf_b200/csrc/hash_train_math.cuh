@@ -34,6 +34,7 @@
 #define HT_ATOMIC_ADD(p, v) (*(p) += (v))
 #define HT_LDG2(p) (*(p))
 struct float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
 #endif
 
 namespace mnrf {
@@ -45,45 +46,55 @@ constexpr float HT_EPS = 1.1920928955078125e-07f;
 constexpr int HT_DR_STRIDE = 12;  // per-point gradient record of k_train_composite_bwd (train.cu)
 constexpr int HT_DXD_STRIDE = 8;  // per-point ray-gradient record: [dx(3), dSH/dd^T g (3), 0, 0]
 
-// rows of the per-warp buffer
+// rows of the per-warp buffer (260 rows = 34 KB: four warps per CTA next to the two 45 KB weight / gradient images)
 constexpr int R_E = 0;     // 32: encoding; later g_e = d sigma / d enc
 constexpr int R_H = 32;    // 64: hidden layer of sigma_net (post ReLU); later the masked tangent
-constexpr int R_J = 96;    // 96: J[k][c] = d enc_k / d u_c   (row 3*k + c)
-constexpr int R_P = 192;   // 64: scratch
-constexpr int R_Q = 256;   // 64: scratch
-constexpr int R_R = 320;   // 32: scratch
-constexpr int R_S = 352;   // 16: [sigma, geo_feat]; later their gradients
-constexpr int R_D = 368;   // 4:  small head gradients
-constexpr int HT_ROWS = 372;
+constexpr int R_P = 96;    // 64: scratch
+constexpr int R_Q = 160;   // 64: scratch
+constexpr int R_R = 224;   // 32: colour-net input [SH4 (16) | sigma | geo_feat (15)]; later d enc
+constexpr int R_S = 240;   // 16: [sigma, geo_feat] = rows 16..31 of R (the colour net's weight column 16 is zero); later their gradients
+constexpr int R_D = 256;   // 4:  small head gradients
+constexpr int HT_ROWS = 260;
 constexpr int HT_WARP_FLOATS = HT_ROWS * HT_LD;
 
-// small weights, reference layouts ([out][in] row-major, R/models/mirror_nerf_tcnn.py:52-149), concatenated
+// The small weights ([out][in] row-major, R/models/mirror_nerf_tcnn.py:52-149) concatenated, every row padded to a multiple of
+// 4 inputs (31 -> 32, 15 -> 16; pad columns are zero) so that rows are 16-byte aligned for vector loads.  The field keeps this
+// image on the device (mnrf_field::hash_wref); the kernel's gradient accumulator has the same layout.
 constexpr int O_S0 = 0;               // sigma_net.0.weight   64 x 32
 constexpr int O_S1 = O_S0 + 64 * 32;  // sigma_net.1.weight   16 x 64
-constexpr int O_C0 = O_S1 + 16 * 64;  // color_net.0.weight   64 x 31
-constexpr int O_C1 = O_C0 + 64 * 31;  // color_net.1.weight   64 x 64
+constexpr int O_C0 = O_S1 + 16 * 64;  // color_net.0.weight   64 x 31 (ld 32; the zero pad column sits at index 16, see R_S)
+constexpr int O_C1 = O_C0 + 64 * 32;  // color_net.1.weight   64 x 64
 constexpr int O_C2 = O_C1 + 64 * 64;  // color_net.2.weight    3 x 64
-constexpr int O_N0 = O_C2 + 3 * 64;   // normal_net.0.weight  64 x 15
-constexpr int O_N1 = O_N0 + 64 * 15;  // normal_net.1.weight   3 x 64
-constexpr int O_M0 = O_N1 + 3 * 64;   // is_mirror_net.0.weight 32 x 15
-constexpr int O_M0B = O_M0 + 32 * 15; // is_mirror_net.0.bias  32
+constexpr int O_N0 = O_C2 + 3 * 64;   // normal_net.0.weight  64 x 15 (ld 16)
+constexpr int O_N1 = O_N0 + 64 * 16;  // normal_net.1.weight   3 x 64
+constexpr int O_M0 = O_N1 + 3 * 64;   // is_mirror_net.0.weight 32 x 15 (ld 16)
+constexpr int O_M0B = O_M0 + 32 * 16; // is_mirror_net.0.bias  32
 constexpr int O_M2 = O_M0B + 32;      // is_mirror_net.2.weight 1 x 32
 constexpr int O_M2B = O_M2 + 32;      // is_mirror_net.2.bias  1
-constexpr int HT_NW = O_M2B + 1;      // 11041
-constexpr int HT_NW_PAD = (HT_NW + 3) / 4 * 4;
-// tensor index (mnrf_hash_field_create order, 1..11) -> offset / element count
+constexpr int HT_NW = O_M2B + 4;      // 11204
+constexpr int LD_C0 = 32, LD_N0 = 16, LD_M0 = 16;
+// tensor index (mnrf_hash_field_create order, 1..11) -> offset / rows / columns / padded row stride
 HT_HD int small_offset(int i) {
   switch (i) {
     case 1: return O_S0; case 2: return O_S1; case 3: return O_C0; case 4: return O_C1; case 5: return O_C2; case 6: return O_N0;
     case 7: return O_N1; case 8: return O_M0; case 9: return O_M0B; case 10: return O_M2; default: return O_M2B;
   }
 }
-HT_HD int small_count(int i) {
+HT_HD int small_rows(int i) {
   switch (i) {
-    case 1: return 64 * 32; case 2: return 16 * 64; case 3: return 64 * 31; case 4: return 64 * 64; case 5: return 3 * 64;
-    case 6: return 64 * 15; case 7: return 3 * 64; case 8: return 32 * 15; case 9: return 32; case 10: return 32; default: return 1;
+    case 1: return 64; case 2: return 16; case 3: return 64; case 4: return 64; case 5: return 3; case 6: return 64;
+    case 7: return 3; case 8: return 32; default: return 1;
   }
 }
+HT_HD int small_cols(int i) {
+  switch (i) {
+    case 1: return 32; case 2: return 64; case 3: return 31; case 4: return 64; case 5: return 64; case 6: return 15;
+    case 7: return 64; case 8: return 15; case 9: return 32; case 10: return 32; default: return 1;
+  }
+}
+HT_HD int small_ld(int i) { return (small_cols(i) + 3) / 4 * 4; }
+// column of the padded image that holds reference column c of tensor i
+HT_HD int small_col(int i, int c) { return (i == 3 && c >= 16) ? c + 1 : c; }
 
 struct Flags {
   int has_normal, has_mirror;
@@ -105,6 +116,7 @@ struct Lane {
   float t[3];      // d L / d g_u  (g_u = d sigma / d u)
   float du[3];     // d L / d u
   float dsh[16];   // d L / d SH(d)
+  float J[96];     // J[3*k + c] = d enc_k / d u_c (only its own lane reads it: local memory, not the shared buffer)
   int mirror_on;   // the mirror-mask loss reaches the density for this ray
   int valid;
 };
@@ -125,41 +137,78 @@ HT_DEV void normalize_bwd(const float (&v)[3], const float (&dy)[3], float (&dv)
 }
 
 // out[j] = sum_{k<K} W[(o0+j)*ldw + k] * X[k][lane]           (thread = point; NB independent accumulators)
+// ldw % 4 == 0 and W 16-byte aligned: the weights (warp-uniform addresses) are read four inputs at a time.
 template <int NB>
 HT_DEV void rows_dot(const float* W, int ldw, int o0, const float* X, int K, int lane, float (&out)[NB]) {
 #pragma unroll
   for (int j = 0; j < NB; ++j) out[j] = 0.f;
-  for (int k = 0; k < K; ++k) {
+  const int K4 = K & ~3;
+  for (int k = 0; k < K4; k += 4) {
+    const float x0 = X[k * HT_LD + lane], x1 = X[(k + 1) * HT_LD + lane], x2 = X[(k + 2) * HT_LD + lane], x3 = X[(k + 3) * HT_LD + lane];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const float4 w = *reinterpret_cast<const float4*>(W + (o0 + j) * ldw + k);
+      out[j] = fmaf(w.x, x0, out[j]); out[j] = fmaf(w.y, x1, out[j]); out[j] = fmaf(w.z, x2, out[j]); out[j] = fmaf(w.w, x3, out[j]);
+    }
+  }
+  for (int k = K4; k < K; ++k) {
     const float x = X[k * HT_LD + lane];
 #pragma unroll
     for (int j = 0; j < NB; ++j) out[j] = fmaf(W[(o0 + j) * ldw + k], x, out[j]);
   }
 }
-// out[j] = sum_{o<O} W[o*ldw + k0 + j] * A[o][lane]           (transposed weights)
-template <int NB>
-HT_DEV void cols_dot(const float* W, int ldw, int k0, const float* A, int O, int lane, float (&out)[NB]) {
+// out[j] = sum_{o<O} W[o*ldw + k0 + j] * A[o][lane], j < 8    (transposed weights; k0 % 4 == 0, ldw % 4 == 0)
+HT_DEV void cols_dot8(const float* W, int ldw, int k0, const float* A, int O, int lane, float (&out)[8]) {
 #pragma unroll
-  for (int j = 0; j < NB; ++j) out[j] = 0.f;
+  for (int j = 0; j < 8; ++j) out[j] = 0.f;
   for (int o = 0; o < O; ++o) {
     const float a = A[o * HT_LD + lane];
-#pragma unroll
-    for (int j = 0; j < NB; ++j) out[j] = fmaf(W[o * ldw + k0 + j], a, out[j]);
+    const float4 w0 = *reinterpret_cast<const float4*>(W + o * ldw + k0);
+    const float4 w1 = *reinterpret_cast<const float4*>(W + o * ldw + k0 + 4);
+    out[0] = fmaf(w0.x, a, out[0]); out[1] = fmaf(w0.y, a, out[1]); out[2] = fmaf(w0.z, a, out[2]); out[3] = fmaf(w0.w, a, out[3]);
+    out[4] = fmaf(w1.x, a, out[4]); out[5] = fmaf(w1.y, a, out[5]); out[6] = fmaf(w1.z, a, out[6]); out[7] = fmaf(w1.w, a, out[7]);
   }
 }
-// warp phase: G[o*ldg + k] += sum_p A[o][p] * B[k][p]   for o < O, k < K; the O*K elements are dealt to the lanes
+// warp phase: G[o*ldg + k] += sum_p A[o][p] * B[k][p]   for o < O, k < K.  Every lane owns register tiles of 4 x 4 elements
+// (o = ob + nb_o*i, k = kb + nb_k*j: strided, so that the lanes of a warp read consecutive rows = distinct banks) and walks the 32
+// points with 8 shared loads per 16 FMAs.
 HT_DEV void wgrad(float* G, int ldg, const float* A, int O, const float* B, int K, int lane) {
-  const int n = O * K;
-  for (int e = lane; e < n; e += 32) {
-    const int o = e / K, k = e - o * K;
-    const float* a = A + o * HT_LD;
-    const float* b = B + k * HT_LD;
-    float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll 8
-    for (int p = 0; p < 32; p += 2) {
-      acc0 = fmaf(a[p], b[p], acc0);
-      acc1 = fmaf(a[p + 1], b[p + 1], acc1);
+  const int nb_o = (O + 3) >> 2, nb_k = (K + 3) >> 2;
+  const int nblk = nb_o * nb_k;
+  for (int blk = lane; blk < nblk; blk += 32) {
+    const int ob = blk / nb_k, kb = blk - ob * nb_k;
+    const float* a[4];
+    const float* b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int o = ob + nb_o * i, k = kb + nb_k * i;
+      a[i] = A + (o < O ? o : O - 1) * HT_LD;  // clamped rows: their products are discarded below
+      b[i] = B + (k < K ? k : K - 1) * HT_LD;
     }
-    HT_ATOMIC_ADD(G + o * ldg + k, acc0 + acc1);
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+    for (int p = 0; p < 32; ++p) {
+      const float a0 = a[0][p], a1 = a[1][p], a2 = a[2][p], a3 = a[3][p];
+      const float b0 = b[0][p], b1 = b[1][p], b2 = b[2][p], b3 = b[3][p];
+      acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]); acc[0][2] = fmaf(a0, b2, acc[0][2]); acc[0][3] = fmaf(a0, b3, acc[0][3]);
+      acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]); acc[1][2] = fmaf(a1, b2, acc[1][2]); acc[1][3] = fmaf(a1, b3, acc[1][3]);
+      acc[2][0] = fmaf(a2, b0, acc[2][0]); acc[2][1] = fmaf(a2, b1, acc[2][1]); acc[2][2] = fmaf(a2, b2, acc[2][2]); acc[2][3] = fmaf(a2, b3, acc[2][3]);
+      acc[3][0] = fmaf(a3, b0, acc[3][0]); acc[3][1] = fmaf(a3, b1, acc[3][1]); acc[3][2] = fmaf(a3, b2, acc[3][2]); acc[3][3] = fmaf(a3, b3, acc[3][3]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int o = ob + nb_o * i;
+      if (o >= O) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = kb + nb_k * j;
+        if (k < K) HT_ATOMIC_ADD(G + o * ldg + k, acc[i][j]);
+      }
+    }
   }
 }
 // warp phase: G[o] += sum_p A[o][p]
@@ -194,7 +243,6 @@ template <class MetaT>
 HT_DEV void phase_a(const float* Wt, float* B, const float* table, const MetaT& M, const Flags& F, Lane& L, int lane) {
   const float2* tab = reinterpret_cast<const float2*>(table);
   float* E = B + R_E * HT_LD;
-  float* J = B + R_J * HT_LD;
   for (int l = 0; l < HT_LEVELS; ++l) {
     const float scale = M.scale[l];
     const unsigned int res = (unsigned int)M.res[l], size = M.size[l];
@@ -226,8 +274,8 @@ HT_DEV void phase_a(const float* Wt, float* B, const float* table, const MetaT& 
     E[(2 * l + 1) * HT_LD + lane] = a1;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      J[(3 * (2 * l) + c) * HT_LD + lane] = scale * j0[c];
-      J[(3 * (2 * l + 1) + c) * HT_LD + lane] = scale * j1[c];
+      L.J[3 * (2 * l) + c] = scale * j0[c];
+      L.J[3 * (2 * l + 1) + c] = scale * j1[c];
     }
   }
   // sigma_net: 32 -> 64 (ReLU) -> 16
@@ -265,13 +313,11 @@ HT_DEV void phase_a(const float* Wt, float* B, const float* table, const MetaT& 
     sh[13] = 0.45704579946446572f * X * (1.0f - 5.0f * z2); sh[14] = 1.4453057213202769f * Z * (x2 - y2);
     sh[15] = 0.59004358992664352f * X * (-x2 + 3.0f * y2);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) Rb[i * HT_LD + lane] = sh[i];
-    for (int i = 0; i < 15; ++i) Rb[(16 + i) * HT_LD + lane] = S[(1 + i) * HT_LD + lane];
-    Rb[31 * HT_LD + lane] = 0.f;
+    for (int i = 0; i < 16; ++i) Rb[i * HT_LD + lane] = sh[i];  // rows 16..31 = [sigma | geo_feat] are already in place (R_S)
   }
   for (int o0 = 0; o0 < 64; o0 += 8) {
     float acc[8];
-    rows_dot<8>(Wt + O_C0, 31, o0, Rb, 31, lane, acc);
+    rows_dot<8>(Wt + O_C0, LD_C0, o0, Rb, 32, lane, acc);  // input row 16 is sigma: its weight column is zero
 #pragma unroll
     for (int j = 0; j < 8; ++j) P[(o0 + j) * HT_LD + lane] = fmaxf(acc[j], 0.f);
   }
@@ -312,39 +358,43 @@ HT_DEV void phase_e(const float* Wt, float* B, int lane) {
   const float* Q = B + R_Q * HT_LD;
   for (int k0 = 0; k0 < 64; k0 += 8) {
     float acc[8];
-    cols_dot<8>(Wt + O_C1, 64, k0, Q, 64, lane, acc);
+    cols_dot8(Wt + O_C1, 64, k0, Q, 64, lane, acc);
 #pragma unroll
     for (int j = 0; j < 8; ++j) P[(k0 + j) * HT_LD + lane] = P[(k0 + j) * HT_LD + lane] > 0.f ? acc[j] : 0.f;
   }
 }
 // warp phase F: d color_net.0
-HT_DEV void phase_f(float* G, const float* B, int lane) { wgrad(G + O_C0, 31, B + R_P * HT_LD, 64, B + R_R * HT_LD, 31, lane); }
+HT_DEV void phase_f(float* G, const float* B, int lane) { wgrad(G + O_C0, LD_C0, B + R_P * HT_LD, 64, B + R_R * HT_LD, 32, lane); }  // column 16 is never read back
 // lane phase G: d [SH | geo] of the colour net; forward of the normal and mirror heads up to their output gradients
 HT_DEV void phase_g(const float* Wt, float* B, const Flags& F, Lane& L, int lane) {
-  const float* P = B + R_P * HT_LD;
+  float* P = B + R_P * HT_LD;
   float* Q = B + R_Q * HT_LD;
-  float* Rb = B + R_R * HT_LD;
+  float* Rb = P;  // the mirror head's hidden layer goes to rows 0..31 of P (d c1 has been consumed by then)
   const float* S = B + R_S * HT_LD;
   float* D = B + R_D * HT_LD;
-  for (int k0 = 16; k0 < 31; k0 += 5) {
-    float acc[5];
-    cols_dot<5>(Wt + O_C0, 31, k0, P, 64, lane, acc);
+  {
+    float acc[8];
+    cols_dot8(Wt + O_C0, LD_C0, 16, P, 64, lane, acc);  // column 16 is padding
 #pragma unroll
-    for (int j = 0; j < 5; ++j) L.dgeo[k0 - 16 + j] += acc[j];
+    for (int j = 1; j < 8; ++j) L.dgeo[j - 1] += acc[j];
+    cols_dot8(Wt + O_C0, LD_C0, 24, P, 64, lane, acc);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) L.dgeo[7 + j] += acc[j];
   }
   if (F.ray_grad) {
-    for (int k0 = 0; k0 < 16; k0 += 8) {
-      float acc[8];
-      cols_dot<8>(Wt + O_C0, 31, k0, P, 64, lane, acc);
+    float acc[8];
+    cols_dot8(Wt + O_C0, LD_C0, 0, P, 64, lane, acc);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) L.dsh[k0 + j] = acc[j];
-    }
+    for (int j = 0; j < 8; ++j) L.dsh[j] = acc[j];
+    cols_dot8(Wt + O_C0, LD_C0, 8, P, 64, lane, acc);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) L.dsh[8 + j] = acc[j];
   }
   const float* GEO = S + HT_LD;  // rows 1..15
   if (F.has_normal) {  // 15 -> 64 (ReLU) -> 3, l2-normalised
     for (int o0 = 0; o0 < 64; o0 += 8) {
       float acc[8];
-      rows_dot<8>(Wt + O_N0, 15, o0, GEO, 15, lane, acc);
+      rows_dot<8>(Wt + O_N0, LD_N0, o0, GEO, 15, lane, acc);
 #pragma unroll
       for (int j = 0; j < 8; ++j) Q[(o0 + j) * HT_LD + lane] = fmaxf(acc[j], 0.f);
     }
@@ -358,7 +408,7 @@ HT_DEV void phase_g(const float* Wt, float* B, const Flags& F, Lane& L, int lane
   if (F.has_mirror) {  // 15 -> 32 (+bias, LeakyReLU 0.01) -> 1 (+bias), sigmoid
     for (int o0 = 0; o0 < 32; o0 += 8) {
       float acc[8];
-      rows_dot<8>(Wt + O_M0, 15, o0, GEO, 15, lane, acc);
+      rows_dot<8>(Wt + O_M0, LD_M0, o0, GEO, 15, lane, acc);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float v = acc[j] + Wt[O_M0B + o0 + j];
@@ -376,7 +426,7 @@ HT_DEV void phase_g(const float* Wt, float* B, const Flags& F, Lane& L, int lane
 HT_DEV void phase_h(float* G, const float* B, const Flags& F, int lane) {
   if (F.has_normal) wgrad(G + O_N1, 64, B + R_D * HT_LD, 3, B + R_Q * HT_LD, 64, lane);
   if (F.has_mirror) {
-    wgrad(G + O_M2, 32, B + (R_D + 3) * HT_LD, 1, B + R_R * HT_LD, 32, lane);
+    wgrad(G + O_M2, 32, B + (R_D + 3) * HT_LD, 1, B + R_P * HT_LD, 32, lane);
     wcolsum(G + O_M2B, B + (R_D + 3) * HT_LD, 1, lane);
   }
 }
@@ -390,7 +440,7 @@ HT_DEV void phase_i(const float* Wt, float* B, const Flags& F, const Lane& L, in
     }
   }
   if (F.has_mirror) {
-    float* Rb = B + R_R * HT_LD;
+    float* Rb = B + R_P * HT_LD;
     for (int o = 0; o < 32; ++o) {
       const float a = Rb[o * HT_LD + lane];  // leaky(pre): same sign as pre
       Rb[o * HT_LD + lane] = Wt[O_M2 + o] * L.dmp * (a > 0.f ? 1.f : 0.01f);
@@ -400,29 +450,31 @@ HT_DEV void phase_i(const float* Wt, float* B, const Flags& F, const Lane& L, in
 // warp phase J: d normal_net.0, d is_mirror_net.0 (+ bias)
 HT_DEV void phase_j(float* G, const float* B, const Flags& F, int lane) {
   const float* GEO = B + (R_S + 1) * HT_LD;
-  if (F.has_normal) wgrad(G + O_N0, 15, B + R_Q * HT_LD, 64, GEO, 15, lane);
+  if (F.has_normal) wgrad(G + O_N0, LD_N0, B + R_Q * HT_LD, 64, GEO, 15, lane);
   if (F.has_mirror) {
-    wgrad(G + O_M0, 15, B + R_R * HT_LD, 32, GEO, 15, lane);
-    wcolsum(G + O_M0B, B + R_R * HT_LD, 32, lane);
+    wgrad(G + O_M0, LD_M0, B + R_P * HT_LD, 32, GEO, 15, lane);
+    wcolsum(G + O_M0B, B + R_P * HT_LD, 32, lane);
   }
 }
 // lane phase K: d geo_feat from the heads, d [sigma, geo] -> S rows, d hidden -> P
 HT_DEV void phase_k(const float* Wt, float* B, const Flags& F, Lane& L, int lane) {
   if (F.has_normal && !F.detach_normal) {
-    for (int k0 = 0; k0 < 15; k0 += 5) {
-      float acc[5];
-      cols_dot<5>(Wt + O_N0, 15, k0, B + R_Q * HT_LD, 64, lane, acc);
+    float acc[8];
+    cols_dot8(Wt + O_N0, LD_N0, 0, B + R_Q * HT_LD, 64, lane, acc);
 #pragma unroll
-      for (int j = 0; j < 5; ++j) L.dgeo[k0 + j] += acc[j];
-    }
+    for (int j = 0; j < 8; ++j) L.dgeo[j] += acc[j];
+    cols_dot8(Wt + O_N0, LD_N0, 8, B + R_Q * HT_LD, 64, lane, acc);  // column 15 is padding
+#pragma unroll
+    for (int j = 0; j < 7; ++j) L.dgeo[8 + j] += acc[j];
   }
   if (F.has_mirror && L.mirror_on) {
-    for (int k0 = 0; k0 < 15; k0 += 5) {
-      float acc[5];
-      cols_dot<5>(Wt + O_M0, 15, k0, B + R_R * HT_LD, 32, lane, acc);
+    float acc[8];
+    cols_dot8(Wt + O_M0, LD_M0, 0, B + R_P * HT_LD, 32, lane, acc);
 #pragma unroll
-      for (int j = 0; j < 5; ++j) L.dgeo[k0 + j] += acc[j];
-    }
+    for (int j = 0; j < 8; ++j) L.dgeo[j] += acc[j];
+    cols_dot8(Wt + O_M0, LD_M0, 8, B + R_P * HT_LD, 32, lane, acc);
+#pragma unroll
+    for (int j = 0; j < 7; ++j) L.dgeo[8 + j] += acc[j];
   }
   float* S = B + R_S * HT_LD;
   S[lane] = L.dr[0];
@@ -431,7 +483,7 @@ HT_DEV void phase_k(const float* Wt, float* B, const Flags& F, Lane& L, int lane
   const float* H = B + R_H * HT_LD;
   for (int k0 = 0; k0 < 64; k0 += 8) {
     float acc[8];
-    cols_dot<8>(Wt + O_S1, 64, k0, S, 16, lane, acc);
+    cols_dot8(Wt + O_S1, 64, k0, S, 16, lane, acc);
 #pragma unroll
     for (int j = 0; j < 8; ++j) P[(k0 + j) * HT_LD + lane] = H[(k0 + j) * HT_LD + lane] > 0.f ? acc[j] : 0.f;
   }
@@ -447,14 +499,13 @@ HT_DEV void phase_m(const float* Wt, float* B, const float* table, float* gtable
                     int lane, bool second_order) {
   float* E = B + R_E * HT_LD;
   float* H = B + R_H * HT_LD;
-  const float* J = B + R_J * HT_LD;
   float* P = B + R_P * HT_LD;
   float* Q = B + R_Q * HT_LD;
   float* Rb = B + R_R * HT_LD;
   // d enc = W0^T d hidden -> R rows
   for (int k0 = 0; k0 < 32; k0 += 8) {
     float acc[8];
-    cols_dot<8>(Wt + O_S0, 32, k0, P, 64, lane, acc);
+    cols_dot8(Wt + O_S0, 32, k0, P, 64, lane, acc);
 #pragma unroll
     for (int j = 0; j < 8; ++j) Rb[(k0 + j) * HT_LD + lane] = acc[j];
   }
@@ -465,7 +516,7 @@ HT_DEV void phase_m(const float* Wt, float* B, const float* table, float* gtable
     for (int o = 0; o < 64; ++o) Q[o * HT_LD + lane] = H[o * HT_LD + lane] > 0.f ? Wt[O_S1 + o] : 0.f;
     for (int k0 = 0; k0 < 32; k0 += 8) {
       float acc[8];
-      cols_dot<8>(Wt + O_S0, 32, k0, Q, 64, lane, acc);
+      cols_dot8(Wt + O_S0, 32, k0, Q, 64, lane, acc);
 #pragma unroll
       for (int j = 0; j < 8; ++j) E[(k0 + j) * HT_LD + lane] = acc[j];
     }
@@ -474,7 +525,7 @@ HT_DEV void phase_m(const float* Wt, float* B, const float* table, float* gtable
     for (int k = 0; k < 32; ++k) {
       const float ge = E[k * HT_LD + lane];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) gu[c] = fmaf(ge, J[(3 * k + c) * HT_LD + lane], gu[c]);
+      for (int c = 0; c < 3; ++c) gu[c] = fmaf(ge, L.J[3 * k + c], gu[c]);
     }
     const float v[3] = {-gu[0] * inv2b, -gu[1] * inv2b, -gu[2] * inv2b};
     const float dy[3] = {L.dr[8], L.dr[9], L.dr[10]};
@@ -484,7 +535,7 @@ HT_DEV void phase_m(const float* Wt, float* B, const float* table, float* gtable
     for (int c = 0; c < 3; ++c) L.t[c] = -dv[c] * inv2b;
     // r = J t -> P rows 0..31 (d L / d g_e);  masked tangent (W0 r) * relu'(h) -> H (in place: d L / d W1[0,:] summand)
     for (int k = 0; k < 32; ++k)
-      P[k * HT_LD + lane] = L.t[0] * J[(3 * k) * HT_LD + lane] + L.t[1] * J[(3 * k + 1) * HT_LD + lane] + L.t[2] * J[(3 * k + 2) * HT_LD + lane];
+      P[k * HT_LD + lane] = L.t[0] * L.J[3 * k] + L.t[1] * L.J[3 * k + 1] + L.t[2] * L.J[3 * k + 2];
     for (int o0 = 0; o0 < 64; o0 += 8) {
       float acc[8];
       rows_dot<8>(Wt + O_S0, 32, o0, P, 32, lane, acc);
@@ -498,7 +549,7 @@ HT_DEV void phase_m(const float* Wt, float* B, const float* table, float* gtable
     for (int k = 0; k < 32; ++k) {
       const float de = Rb[k * HT_LD + lane];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) L.du[c] = fmaf(de, J[(3 * k + c) * HT_LD + lane], L.du[c]);
+      for (int c = 0; c < 3; ++c) L.du[c] = fmaf(de, L.J[3 * k + c], L.du[c]);
     }
   }
   // table scatter: d T[idx] += w * d enc + scale * g_e * (t . d w / d frac)   [+ second-order ray term]

@@ -18,9 +18,10 @@ using namespace ht;
 
 static_assert(sizeof(HashGridMeta) == sizeof(float) * (1 + 4 * HT_LEVELS), "HashGridMeta layout");
 static_assert(HG_LEVELS == HT_LEVELS, "level count");
+static_assert(HT_NW % 4 == 0 && HASH_WREF_FLOATS == HT_NW, "padded weight image");
 
-constexpr int HB_WARPS = 2;  // warps per CTA (each owns HT_WARP_FLOATS of shared memory)
-constexpr int HB_SMEM_FLOATS = 2 * HT_NW_PAD + HB_WARPS * HT_WARP_FLOATS;
+constexpr int HB_WARPS = 4;  // warps per CTA (each owns HT_WARP_FLOATS of shared memory)
+constexpr int HB_SMEM_FLOATS = 2 * HT_NW + HB_WARPS * HT_WARP_FLOATS;
 
 struct SmallPtrs { float* p[12]; };  // index = mnrf_hash_field_create tensor order (entry 0 = table)
 
@@ -30,14 +31,14 @@ k_hash_bwd(const float* __restrict__ table, const float* __restrict__ wref, Hash
            Flags F, int second_order, float* __restrict__ gtable, SmallPtrs gsmall, float* __restrict__ dxd) {
   extern __shared__ __align__(16) float sm[];
   float* Wt = sm;
-  float* G = sm + HT_NW_PAD;
-  for (int i = threadIdx.x; i < HT_NW_PAD; i += blockDim.x) {
-    Wt[i] = i < HT_NW ? wref[i] : 0.f;
+  float* G = sm + HT_NW;
+  for (int i = threadIdx.x; i < HT_NW; i += blockDim.x) {
+    Wt[i] = wref[i];
     G[i] = 0.f;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* B = sm + 2 * HT_NW_PAD + warp * HT_WARP_FLOATS;
+  float* B = sm + 2 * HT_NW + warp * HT_WARP_FLOATS;
   const int n_tiles = (P + 31) / 32;
   for (int tile = blockIdx.x * HB_WARPS + warp; tile < n_tiles; tile += gridDim.x * HB_WARPS) {
     Lane L;
@@ -108,9 +109,10 @@ k_hash_bwd(const float* __restrict__ table, const float* __restrict__ wref, Hash
   for (int t = 1; t < 12; ++t) {
     float* dst = gsmall.p[t];
     if (dst == nullptr) continue;
-    const int off = small_offset(t), cnt = small_count(t);
-    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-      const float v = G[off + i];
+    const int off = small_offset(t), cols = small_cols(t), ld = small_ld(t), cnt = small_rows(t) * cols;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {  // padded rows -> the parameter's own [out][in] layout
+      const int r = i / cols, c = i - r * cols;
+      const float v = G[off + r * ld + small_col(t, c)];
       if (v != 0.f) atomicAdd(dst + i, v);
     }
   }

@@ -24,8 +24,14 @@ extern "C" int hash_bwd_emu(const float* table, const float* wref, const Meta* M
   Flags F;
   F.has_normal = has_normal; F.has_mirror = has_mirror; F.compute_normal = compute_normal;
   F.detach_normal = detach_normal; F.detach_mask = detach_mask; F.ray_grad = ray_grad;
-  std::vector<float> Wt(HT_NW_PAD, 0.f), G(HT_NW_PAD, 0.f), B(HT_WARP_FLOATS, 0.f);
-  memcpy(Wt.data(), wref, sizeof(float) * HT_NW);
+  // wref / gsmall: the 11 small tensors concatenated in their own [out][in] layouts; the kernel works on row-padded images
+  std::vector<float> Wt(HT_NW, 0.f), G(HT_NW, 0.f), B(HT_WARP_FLOATS, 0.f);
+  {
+    int pos = 0;
+    for (int t = 1; t < 12; ++t)
+      for (int r = 0; r < small_rows(t); ++r)
+        for (int c = 0; c < small_cols(t); ++c) Wt[small_offset(t) + r * small_ld(t) + small_col(t, c)] = wref[pos++];
+  }
   const int n_tiles = (P + 31) / 32;
   for (int tile = 0; tile < n_tiles; ++tile) {
     Lane L[32];
@@ -72,8 +78,17 @@ extern "C" int hash_bwd_emu(const float* table, const float* wref, const Meta* M
       }
     }
   }
-  for (int i = 0; i < HT_NW; ++i) gsmall[i] += G[i];
+  {
+    int pos = 0;
+    for (int t = 1; t < 12; ++t)
+      for (int r = 0; r < small_rows(t); ++r)
+        for (int c = 0; c < small_cols(t); ++c) gsmall[pos++] += G[small_offset(t) + r * small_ld(t) + small_col(t, c)];
+  }
   return 0;
 }
 
-extern "C" int hash_bwd_emu_nw(void) { return HT_NW; }
+extern "C" int hash_bwd_emu_nw(void) {
+  int n = 0;
+  for (int t = 1; t < 12; ++t) n += small_rows(t) * small_cols(t);
+  return n;
+}
