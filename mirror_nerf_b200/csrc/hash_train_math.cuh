@@ -104,6 +104,9 @@ struct Flags {
   int ray_grad;        // also d L / d [o, d]
 };
 
+// J[3*k + c] = d enc_k / d u_c is a separate per-lane array of HT_J floats (indexed dynamically, so it lives in local memory; only
+// its own lane reads it, which is why it is not in the shared buffer).
+constexpr int HT_J = 96;
 // per-lane state that lives across phases (registers on the GPU)
 struct Lane {
   float u[3];      // position in the unit cube
@@ -116,7 +119,6 @@ struct Lane {
   float t[3];      // d L / d g_u  (g_u = d sigma / d u)
   float du[3];     // d L / d u
   float dsh[16];   // d L / d SH(d)
-  float J[96];     // J[3*k + c] = d enc_k / d u_c (only its own lane reads it: local memory, not the shared buffer)
   int mirror_on;   // the mirror-mask loss reaches the density for this ray
   int valid;
 };
@@ -235,15 +237,16 @@ HT_DEV unsigned int grid_index(const unsigned int (&c3)[3], unsigned int res, un
   int dim = 0;
   for (; dim < 3 && stride <= size; ++dim) { index += c3[dim] * stride; stride *= res; }
   if (size < stride) index = (c3[0] * 1u) ^ (c3[1] * 2654435761u) ^ (c3[2] * 805459861u);
-  return index % size;
+  return (size & (size - 1u)) == 0u ? (index & (size - 1u)) : (index % size);  // the hashed levels hold 2^19 entries
 }
 
 // ---- lane phase A: encoding + its Jacobian, sigma_net, colour net forward ---------------------------------------------------
 template <class MetaT>
-HT_DEV void phase_a(const float* Wt, float* B, const float* table, const MetaT& M, const Flags& F, Lane& L, int lane) {
+HT_DEV void phase_a(const float* Wt, float* B, const float* table, const MetaT& M, const Flags& F, Lane& L, float* J, int lane) {
   const float2* tab = reinterpret_cast<const float2*>(table);
   float* E = B + R_E * HT_LD;
-  for (int l = 0; l < HT_LEVELS; ++l) {
+#pragma unroll 2
+  for (int l = 0; l < HT_LEVELS; ++l) {  // two levels = 16 independent table reads in flight per lane
     const float scale = M.scale[l];
     const unsigned int res = (unsigned int)M.res[l], size = M.size[l];
     unsigned int g[3];
@@ -274,8 +277,8 @@ HT_DEV void phase_a(const float* Wt, float* B, const float* table, const MetaT& 
     E[(2 * l + 1) * HT_LD + lane] = a1;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      L.J[3 * (2 * l) + c] = scale * j0[c];
-      L.J[3 * (2 * l + 1) + c] = scale * j1[c];
+      J[3 * (2 * l) + c] = scale * j0[c];
+      J[3 * (2 * l + 1) + c] = scale * j1[c];
     }
   }
   // sigma_net: 32 -> 64 (ReLU) -> 16
@@ -478,6 +481,7 @@ HT_DEV void phase_k(const float* Wt, float* B, const Flags& F, Lane& L, int lane
   }
   float* S = B + R_S * HT_LD;
   S[lane] = L.dr[0];
+#pragma unroll
   for (int j = 0; j < 15; ++j) S[(1 + j) * HT_LD + lane] = L.dgeo[j];
   float* P = B + R_P * HT_LD;
   const float* H = B + R_H * HT_LD;
@@ -496,7 +500,7 @@ HT_DEV void phase_l(float* G, const float* B, int lane) {
 // lane phase M: d enc; the double backward through the analytic normal; table scatter; ray-gradient record
 template <class MetaT>
 HT_DEV void phase_m(const float* Wt, float* B, const float* table, float* gtable, const MetaT& M, const Flags& F, Lane& L,
-                    int lane, bool second_order) {
+                    const float* J, int lane, bool second_order) {
   float* E = B + R_E * HT_LD;
   float* H = B + R_H * HT_LD;
   float* P = B + R_P * HT_LD;
@@ -525,7 +529,7 @@ HT_DEV void phase_m(const float* Wt, float* B, const float* table, float* gtable
     for (int k = 0; k < 32; ++k) {
       const float ge = E[k * HT_LD + lane];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) gu[c] = fmaf(ge, L.J[3 * k + c], gu[c]);
+      for (int c = 0; c < 3; ++c) gu[c] = fmaf(ge, J[3 * k + c], gu[c]);
     }
     const float v[3] = {-gu[0] * inv2b, -gu[1] * inv2b, -gu[2] * inv2b};
     const float dy[3] = {L.dr[8], L.dr[9], L.dr[10]};
@@ -535,7 +539,7 @@ HT_DEV void phase_m(const float* Wt, float* B, const float* table, float* gtable
     for (int c = 0; c < 3; ++c) L.t[c] = -dv[c] * inv2b;
     // r = J t -> P rows 0..31 (d L / d g_e);  masked tangent (W0 r) * relu'(h) -> H (in place: d L / d W1[0,:] summand)
     for (int k = 0; k < 32; ++k)
-      P[k * HT_LD + lane] = L.t[0] * L.J[3 * k] + L.t[1] * L.J[3 * k + 1] + L.t[2] * L.J[3 * k + 2];
+      P[k * HT_LD + lane] = L.t[0] * J[3 * k] + L.t[1] * J[3 * k + 1] + L.t[2] * J[3 * k + 2];
     for (int o0 = 0; o0 < 64; o0 += 8) {
       float acc[8];
       rows_dot<8>(Wt + O_S0, 32, o0, P, 32, lane, acc);
@@ -549,7 +553,7 @@ HT_DEV void phase_m(const float* Wt, float* B, const float* table, float* gtable
     for (int k = 0; k < 32; ++k) {
       const float de = Rb[k * HT_LD + lane];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) L.du[c] = fmaf(de, L.J[3 * k + c], L.du[c]);
+      for (int c = 0; c < 3; ++c) L.du[c] = fmaf(de, J[3 * k + c], L.du[c]);
     }
   }
   // table scatter: d T[idx] += w * d enc + scale * g_e * (t . d w / d frac)   [+ second-order ray term]

@@ -42,6 +42,7 @@ k_hash_bwd(const float* __restrict__ table, const float* __restrict__ wref, Hash
   const int n_tiles = (P + 31) / 32;
   for (int tile = blockIdx.x * HB_WARPS + warp; tile < n_tiles; tile += gridDim.x * HB_WARPS) {
     Lane L;
+    float J[HT_J];
     const int p_raw = tile * 32 + lane;
     L.valid = p_raw < P;
     const int p = L.valid ? p_raw : P - 1;  // tail lanes shadow the last point with a zero gradient record
@@ -68,7 +69,7 @@ k_hash_bwd(const float* __restrict__ table, const float* __restrict__ wref, Hash
 #pragma unroll
     for (int i = 0; i < 16; ++i) L.dsh[i] = 0.f;
 
-    phase_a(Wt, B, table, M, F, L, lane);
+    phase_a(Wt, B, table, M, F, L, J, lane);
     __syncwarp();
     phase_b(G, B, lane);
     __syncwarp();
@@ -92,7 +93,7 @@ k_hash_bwd(const float* __restrict__ table, const float* __restrict__ wref, Hash
     __syncwarp();
     phase_l(G, B, lane);
     __syncwarp();
-    phase_m(Wt, B, table, gtable, M, F, L, lane, second_order != 0);
+    phase_m(Wt, B, table, gtable, M, F, L, J, lane, second_order != 0);
     __syncwarp();
     if (second_order) phase_n(G, B, lane);
     if (dxd != nullptr && L.valid) {

@@ -35,6 +35,7 @@ extern "C" int hash_bwd_emu(const float* table, const float* wref, const Meta* M
   const int n_tiles = (P + 31) / 32;
   for (int tile = 0; tile < n_tiles; ++tile) {
     Lane L[32];
+    static float J[32][HT_J];
     for (int lane = 0; lane < 32; ++lane) {
       Lane& l = L[lane];
       const int p_raw = tile * 32 + lane;
@@ -52,7 +53,7 @@ extern "C" int hash_bwd_emu(const float* table, const float* wref, const Meta* M
       for (int i = 0; i < 16; ++i) l.dsh[i] = 0.f;
     }
 #define LANES(call) for (int lane = 0; lane < 32; ++lane) { call; }
-    LANES(phase_a(Wt.data(), B.data(), table, M, F, L[lane], lane))
+    LANES(phase_a(Wt.data(), B.data(), table, M, F, L[lane], J[lane], lane))
     LANES(phase_b(G.data(), B.data(), lane))
     LANES(phase_c(Wt.data(), B.data(), L[lane], lane))
     LANES(phase_d(G.data(), B.data(), lane))
@@ -64,7 +65,7 @@ extern "C" int hash_bwd_emu(const float* table, const float* wref, const Meta* M
     LANES(phase_j(G.data(), B.data(), F, lane))
     LANES(phase_k(Wt.data(), B.data(), F, L[lane], lane))
     LANES(phase_l(G.data(), B.data(), lane))
-    LANES(phase_m(Wt.data(), B.data(), table, gtable, M, F, L[lane], lane, second_order != 0))
+    LANES(phase_m(Wt.data(), B.data(), table, gtable, M, F, L[lane], J[lane], lane, second_order != 0))
     if (second_order) LANES(phase_n(G.data(), B.data(), lane))
     if (dxd != nullptr) {
       const float inv2b = 1.f / (2.f * M.bound);
