@@ -145,3 +145,66 @@ def test_hash_backward_math_matches_autograd(emu, case):
     assert np.abs(dxd[:, 0:3] - gx).max() / sx < 1e-5
     sd_ = np.abs(gd).max()
     assert np.abs(dxd[:, 3:6] - gd).max() / sd_ < 1e-5
+
+
+def _setup(P, seed, heads=True):
+    sd = HG.make_state_dict(seed=5, bound=1.0, sigma_scale=4.0, predict_normal=heads, predict_mirror_mask=heads)
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(-0.98, 0.98, size=(P, 3)).astype(np.float32)
+    d = rng.normal(size=(P, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    DR = rng.normal(size=(P, 12)).astype(np.float32)
+    DR[:, 11] = 0
+    return sd, x, d, DR
+
+
+def test_hash_backward_is_linear_in_the_output_gradients(emu):
+    """Size-independent property: for fixed points the backward is a linear map of the per-point gradient record, second-order
+    path included (the analytic normal's double backward is linear in d L / d n)."""
+    flags = dict(CASES["full"])
+    sd, x, d, DR1 = _setup(64, 21)
+    DR2 = np.random.default_rng(22).normal(size=DR1.shape).astype(np.float32)
+    DR2[:, 11] = 0
+    on = np.ones(64, np.int32)
+    g1, q1 = _run(emu, sd, x, d, DR1, on, flags, 1.0)
+    g2, q2 = _run(emu, sd, x, d, DR2, on, flags, 1.0)
+    g3, q3 = _run(emu, sd, x, d, 2.0 * DR1 - 0.5 * DR2, on, flags, 1.0)
+    for k in g1:
+        want = 2.0 * g1[k] - 0.5 * g2[k]
+        scale = max(np.abs(want).max(), 1e-20)
+        assert np.abs(g3[k] - want).max() / scale < 2e-5, k
+    want = 2.0 * q1 - 0.5 * q2
+    assert np.abs(q3 - want).max() / np.abs(want).max() < 2e-5
+
+
+def test_hash_backward_is_additive_over_point_shards(emu):
+    """Parameter gradients of a batch = sum over any split of its points (tiles, ragged tails and the order of the scatter-adds
+    do not matter beyond fp32 rounding): the property data-parallel training relies on."""
+    flags = dict(CASES["full"])
+    sd, x, d, DR = _setup(101, 23)
+    on = np.ones(101, np.int32)
+    whole, dxd = _run(emu, sd, x, d, DR, on, flags, 1.0)
+    parts = [(0, 37), (37, 38), (38, 101)]
+    acc, rows = None, []
+    for lo, hi in parts:
+        g, q = _run(emu, sd, x[lo:hi], d[lo:hi], DR[lo:hi], on[lo:hi], flags, 1.0)
+        rows.append(q)
+        acc = g if acc is None else {k: acc[k] + g[k] for k in g}
+    for k in whole:
+        scale = max(np.abs(whole[k]).max(), 1e-20)
+        assert np.abs(acc[k] - whole[k]).max() / scale < 2e-5, k
+    assert np.array_equal(np.concatenate(rows, 0), dxd)  # per-point ray-gradient records do not depend on the tiling
+
+
+def test_hash_backward_zero_gradient_and_empty_heads(emu):
+    """Edge cases: an all-zero gradient record gives exactly zero everywhere; a model without heads leaves the head slots at zero."""
+    flags = dict(CASES["full"])
+    sd, x, d, DR = _setup(40, 25)
+    g, q = _run(emu, sd, x, d, np.zeros_like(DR), np.ones(40, np.int32), flags, 1.0)
+    assert all(float(np.abs(v).max()) == 0.0 for v in g.values()) and float(np.abs(q).max()) == 0.0
+    sd2, x, d, DR = _setup(40, 26, heads=False)
+    DR[:, 4:8] = 0
+    g, _ = _run(emu, sd2, x, d, DR, np.ones(40, np.int32), flags, 1.0)
+    for k in ("normal_net.0.weight", "normal_net.1.weight", "is_mirror_net.0.weight", "is_mirror_net.2.bias"):
+        assert float(np.abs(g[k]).max()) == 0.0, k
+    assert float(np.abs(g["encoder.params"]).max()) > 0
