@@ -283,10 +283,8 @@ def hash_train_bench(dev, steps, warmup=2):
 def hash_level_bench(dev, steps):
     """BASELINE config 3 shape: one eval render level (64+128 samples) of an 800x800 view with the hash-grid field
     (nerf_tcnn family; synthetic table and weights).  Returns a dict (rays/s per level)."""
-    import numpy as np
     import torch
     from mirror_nerf_b200.mirror_nerf import Embedding
-    from mirror_nerf_b200.mirror_nerf_tcnn import MirrorNeRFTcnn
     from mirror_nerf_b200.rendering import render_rays
     from mirror_nerf_b200.synthetic import camera_rays
     models = hash_models(dev)
