@@ -55,7 +55,7 @@ def test_sharded_render_world3_ragged(tmp_path):
 
 
 # ---- data-parallel training plumbing (flat gradient all-reduce), world_size 2 over gloo ---------------------------------
-def _ddp_worker(rank, world, port, out_dir):
+def _ddp_worker(rank, world, port, out_dir, family="mlp"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -64,12 +64,20 @@ def _ddp_worker(rank, world, port, out_dir):
     from mirror_nerf_b200.synthetic import make_state_dict
     models = {}
     for name, seed in (("coarse", 1), ("fine", 2)):
-        m = MirrorNeRF(predict_normal=True, predict_mirror_mask=True)
-        m.load_state_dict(make_state_dict(seed))
+        if family == "hash":  # nerf_tcnn family: the hash tables join the same flat all-reduce
+            from mirror_nerf_b200.mirror_nerf_tcnn import MirrorNeRFTcnn
+            torch.manual_seed(seed)
+            m = MirrorNeRFTcnn(bound=1, predict_normal=True, predict_mirror_mask=True)
+        else:
+            m = MirrorNeRF(predict_normal=True, predict_mirror_mask=True)
+            m.load_state_dict(make_state_dict(seed))
         models[name] = m
     before = {k: {n: p.detach().clone() for n, p in m.named_parameters()} for k, m in models.items()}
     ddp = FlatDataParallel(models)
-    assert ddp.flat_params.numel() == 2 * 662152 == ddp.flat_grads.numel()  # 5.30 MB per step
+    if family == "hash":
+        assert ddp.flat_params.numel() == 2 * (12196240 + 11041) == ddp.flat_grads.numel()  # 97.7 MB per step
+    else:
+        assert ddp.flat_params.numel() == 2 * 662152 == ddp.flat_grads.numel()  # 5.30 MB per step
     for k, m in models.items():  # flattening keeps values and makes every parameter / grad a view of the flat buffers
         for n, p in m.named_parameters():
             assert torch.equal(p.detach(), before[k][n])
@@ -101,10 +109,16 @@ def _ddp_worker(rank, world, port, out_dir):
         assert "CUDA" in str(e)
     dist.barrier()
     dist.destroy_process_group()
-    open(os.path.join(out_dir, f"ddp_ok{rank}"), "w").write("ok")
+    open(os.path.join(out_dir, f"ddp_ok{rank}_{family}"), "w").write("ok")
 
 
 def test_flat_gradient_allreduce_world2(tmp_path):
     port = _free_port()
     mp.spawn(_ddp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
-    assert all(os.path.exists(os.path.join(str(tmp_path), f"ddp_ok{r}")) for r in range(2))
+    assert all(os.path.exists(os.path.join(str(tmp_path), f"ddp_ok{r}_mlp")) for r in range(2))
+
+
+def test_flat_gradient_allreduce_world2_hash_grid_family(tmp_path):
+    port = _free_port()
+    mp.spawn(_ddp_worker, args=(2, port, str(tmp_path), "hash"), nprocs=2, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), f"ddp_ok{r}_hash")) for r in range(2))
