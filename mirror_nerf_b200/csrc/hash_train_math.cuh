@@ -140,13 +140,13 @@ HT_DEV void normalize_bwd(const float (&v)[3], const float (&dy)[3], float (&dv)
 
 // out[j] = sum_{k<K} W[(o0+j)*ldw + k] * X[k][lane]           (thread = point; NB independent accumulators)
 // ldw % 4 == 0 and W 16-byte aligned: the weights (warp-uniform addresses) are read four inputs at a time.
-template <int NB>
+template <int NB, int LD = HT_LD>
 HT_DEV void rows_dot(const float* W, int ldw, int o0, const float* X, int K, int lane, float (&out)[NB]) {
 #pragma unroll
   for (int j = 0; j < NB; ++j) out[j] = 0.f;
   const int K4 = K & ~3;
   for (int k = 0; k < K4; k += 4) {
-    const float x0 = X[k * HT_LD + lane], x1 = X[(k + 1) * HT_LD + lane], x2 = X[(k + 2) * HT_LD + lane], x3 = X[(k + 3) * HT_LD + lane];
+    const float x0 = X[k * LD + lane], x1 = X[(k + 1) * LD + lane], x2 = X[(k + 2) * LD + lane], x3 = X[(k + 3) * LD + lane];
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
       const float4 w = *reinterpret_cast<const float4*>(W + (o0 + j) * ldw + k);
@@ -154,17 +154,18 @@ HT_DEV void rows_dot(const float* W, int ldw, int o0, const float* X, int K, int
     }
   }
   for (int k = K4; k < K; ++k) {
-    const float x = X[k * HT_LD + lane];
+    const float x = X[k * LD + lane];
 #pragma unroll
     for (int j = 0; j < NB; ++j) out[j] = fmaf(W[(o0 + j) * ldw + k], x, out[j]);
   }
 }
 // out[j] = sum_{o<O} W[o*ldw + k0 + j] * A[o][lane], j < 8    (transposed weights; k0 % 4 == 0, ldw % 4 == 0)
+template <int LD = HT_LD>
 HT_DEV void cols_dot8(const float* W, int ldw, int k0, const float* A, int O, int lane, float (&out)[8]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) out[j] = 0.f;
   for (int o = 0; o < O; ++o) {
-    const float a = A[o * HT_LD + lane];
+    const float a = A[o * LD + lane];
     const float4 w0 = *reinterpret_cast<const float4*>(W + o * ldw + k0);
     const float4 w1 = *reinterpret_cast<const float4*>(W + o * ldw + k0 + 4);
     out[0] = fmaf(w0.x, a, out[0]); out[1] = fmaf(w0.y, a, out[1]); out[2] = fmaf(w0.z, a, out[2]); out[3] = fmaf(w0.w, a, out[3]);
@@ -174,6 +175,7 @@ HT_DEV void cols_dot8(const float* W, int ldw, int k0, const float* A, int O, in
 // warp phase: G[o*ldg + k] += sum_p A[o][p] * B[k][p]   for o < O, k < K.  Every lane owns register tiles of 4 x 4 elements
 // (o = ob + nb_o*i, k = kb + nb_k*j: strided, so that the lanes of a warp read consecutive rows = distinct banks) and walks the 32
 // points with 8 shared loads per 16 FMAs.
+template <int LD = HT_LD, int NP = 32>
 HT_DEV void wgrad(float* G, int ldg, const float* A, int O, const float* B, int K, int lane) {
   const int nb_o = (O + 3) >> 2, nb_k = (K + 3) >> 2;
   const int nblk = nb_o * nb_k;
@@ -184,8 +186,8 @@ HT_DEV void wgrad(float* G, int ldg, const float* A, int O, const float* B, int 
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int o = ob + nb_o * i, k = kb + nb_k * i;
-      a[i] = A + (o < O ? o : O - 1) * HT_LD;  // clamped rows: their products are discarded below
-      b[i] = B + (k < K ? k : K - 1) * HT_LD;
+      a[i] = A + (o < O ? o : O - 1) * LD;  // clamped rows: their products are discarded below
+      b[i] = B + (k < K ? k : K - 1) * LD;
     }
     float acc[4][4];
 #pragma unroll
@@ -193,7 +195,7 @@ HT_DEV void wgrad(float* G, int ldg, const float* A, int O, const float* B, int 
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 #pragma unroll 4
-    for (int p = 0; p < 32; ++p) {
+    for (int p = 0; p < NP; ++p) {
       const float a0 = a[0][p], a1 = a[1][p], a2 = a[2][p], a3 = a[3][p];
       const float b0 = b[0][p], b1 = b[1][p], b2 = b[2][p], b3 = b[3][p];
       acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]); acc[0][2] = fmaf(a0, b2, acc[0][2]); acc[0][3] = fmaf(a0, b3, acc[0][3]);
@@ -214,10 +216,11 @@ HT_DEV void wgrad(float* G, int ldg, const float* A, int O, const float* B, int 
   }
 }
 // warp phase: G[o] += sum_p A[o][p]
+template <int LD = HT_LD, int NP = 32>
 HT_DEV void wcolsum(float* G, const float* A, int O, int lane) {
   for (int o = lane; o < O; o += 32) {
     float acc = 0.f;
-    for (int p = 0; p < 32; ++p) acc += A[o * HT_LD + p];
+    for (int p = 0; p < NP; ++p) acc += A[o * LD + p];
     HT_ATOMIC_ADD(G + o, acc);
   }
 }

@@ -10,6 +10,9 @@
 // fp32 here), and the double backward through the analytic normal (create_graph=True in the reference) is explicit.
 #include "common.cuh"
 #include "hash_train_math.cuh"
+#include "hash_train_math2.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 namespace mnrf {
 namespace {
@@ -119,6 +122,144 @@ k_hash_bwd(const float* __restrict__ table, const float* __restrict__ wref, Hash
   }
 }
 
+// Second layout (hash_train_math2.cuh): 16 points per warp tile, two lanes per point, EIGHT warps per CTA.
+constexpr int HB2_WARPS = 8;
+constexpr int HB2_SMEM_FLOATS = 2 * HT_NW + HB2_WARPS * ht2::HT2_WARP_FLOATS;
+static_assert(HB2_SMEM_FLOATS * sizeof(float) <= 232448, "k_hash_bwd2: shared memory");
+
+__global__ void __launch_bounds__(HB2_WARPS * 32, 1)
+k_hash_bwd2(const float* __restrict__ table, const float* __restrict__ wref, HashGridMeta M, const float* __restrict__ rays,
+            const float* __restrict__ z, const float* __restrict__ DR, const float* __restrict__ ray_detach_mirror, int P, int S,
+            Flags F, int second_order, float* __restrict__ gtable, SmallPtrs gsmall, float* __restrict__ dxd) {
+  using namespace ht2;
+  extern __shared__ __align__(16) float sm[];
+  float* Wt = sm;
+  float* G = sm + HT_NW;
+  for (int i = threadIdx.x; i < HT_NW; i += blockDim.x) {
+    Wt[i] = wref[i];
+    G[i] = 0.f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col = lane & 15, half = lane >> 4;
+  float* B = sm + 2 * HT_NW + warp * HT2_WARP_FLOATS;
+  const bool so = second_order != 0;
+  const int n_tiles = (P + NP2 - 1) / NP2;
+  for (int tile = blockIdx.x * HB2_WARPS + warp; tile < n_tiles; tile += gridDim.x * HB2_WARPS) {
+    Lane L;
+    float J[HT2_J];
+    const int p_raw = tile * NP2 + col;
+    L.valid = p_raw < P;
+    const int p = L.valid ? p_raw : P - 1;  // tail lanes shadow the last point with a zero gradient record
+    const int ray = p / S;
+    const float* rr = rays + (size_t)ray * 8;
+    const float zz = z[p];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float x = __fadd_rn(rr[c], __fmul_rn(rr[3 + c], zz));
+      L.u[c] = __fdiv_rn(__fadd_rn(x, M.bound), __fmul_rn(2.f, M.bound));
+      L.d[c] = rr[3 + c];
+    }
+    {
+      const float4* dr = reinterpret_cast<const float4*>(DR + (size_t)p * HT_DR_STRIDE);
+      const float4 r0 = dr[0], r1 = dr[1], r2 = dr[2];
+      const float k = L.valid ? 1.f : 0.f;
+      L.dr[0] = k * r0.x; L.dr[1] = k * r0.y; L.dr[2] = k * r0.z; L.dr[3] = k * r0.w;
+      L.dr[4] = k * r1.x; L.dr[5] = k * r1.y; L.dr[6] = k * r1.z; L.dr[7] = k * r1.w;
+      L.dr[8] = k * r2.x; L.dr[9] = k * r2.y; L.dr[10] = k * r2.z; L.dr[11] = 0.f;
+    }
+    L.mirror_on = !F.detach_mask && !(ray_detach_mirror != nullptr && ray_detach_mirror[ray] != 0.f);
+    L.dmp = 0.f;
+    L.dnraw[0] = L.dnraw[1] = L.dnraw[2] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) L.dsh[i] = 0.f;
+
+    step_a1(B, table, M, L, J, lane);
+    __syncwarp();
+    step_a2(Wt, B, lane);
+    __syncwarp();
+    step_a3(Wt, B, L, lane);
+    __syncwarp();
+    step_a4(Wt, B, lane);
+    __syncwarp();
+    step_a5(Wt, B, lane);
+    __syncwarp();
+    step_a6(Wt, B, L, lane);
+    __syncwarp();
+    step_b(G, B, lane);
+    __syncwarp();
+    step_c(Wt, B, L, lane);
+    __syncwarp();
+    step_d(G, B, lane);
+    __syncwarp();
+    step_e(Wt, B, lane);
+    __syncwarp();
+    step_f(G, B, lane);
+    __syncwarp();
+    step_g1(Wt, B, F, L, lane);
+    __syncwarp();
+    step_g2(Wt, B, F, lane);
+    __syncwarp();
+    step_g3(Wt, B, F, L, lane);
+    __syncwarp();
+    step_h(G, B, F, lane);
+    __syncwarp();
+    step_i(Wt, B, F, L, lane);
+    __syncwarp();
+    step_j(G, B, F, lane);
+    __syncwarp();
+    step_k1(Wt, B, F, L, lane);
+    __syncwarp();
+    step_k2(Wt, B, lane);
+    __syncwarp();
+    step_l(G, B, lane);
+    __syncwarp();
+    step_m1(Wt, B, lane, so);
+    __syncwarp();
+    if (so) {
+      step_m2(Wt, B, J, lane);
+      __syncwarp();
+      step_m3(B, M, L, J, lane);
+      __syncwarp();
+    }
+    step_m4(Wt, B, table, gtable, M, F, L, J, lane, so);
+    __syncwarp();
+    if (so) step_n(G, B, lane);
+    step_o(B, L, lane);
+    if (dxd != nullptr && L.valid && half == 0) {
+      const float inv2b = 1.f / (2.f * M.bound);
+      float gd[3];
+      sh4_bwd(L.d, L.dsh, gd);
+      float4* o = reinterpret_cast<float4*>(dxd + (size_t)p_raw * HT_DXD_STRIDE);
+      o[0] = make_float4(L.du[0] * inv2b, L.du[1] * inv2b, L.du[2] * inv2b, gd[0]);
+      o[1] = make_float4(gd[1], gd[2], 0.f, 0.f);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int t = 1; t < 12; ++t) {
+    float* dst = gsmall.p[t];
+    if (dst == nullptr) continue;
+    const int off = small_offset(t), cols = small_cols(t), ld = small_ld(t), cnt = small_rows(t) * cols;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const int r = i / cols, c = i - r * cols;
+      const float v = G[off + r * ld + small_col(t, c)];
+      if (v != 0.f) atomicAdd(dst + i, v);
+    }
+  }
+}
+
+// which layout runs: 2 (default) = 16 points x 2 lanes, 8 warps per CTA; 1 = 32 points x 1 lane, 4 warps per CTA
+// (MNRF_HASH_BWD_LAYOUT=32x1 selects the first one; both are pinned to the same oracle by tests/test_hash_train_emu.py)
+int hash_bwd_layout() {
+  static int layout = -1;
+  if (layout < 0) {
+    const char* e = getenv("MNRF_HASH_BWD_LAYOUT");
+    layout = (e != nullptr && strcmp(e, "32x1") == 0) ? 1 : 2;
+  }
+  return layout;
+}
+
 // d L / d [o, d] of one ray from the per-point records: x = o + d z, SH(d), x_surface = o + d * depth
 __global__ void k_hash_ray_grad(const float* __restrict__ z, const float* __restrict__ dxd, const float* __restrict__ g_xs,
                                 const float* __restrict__ depth, int n, int S, float* __restrict__ grad_rays) {
@@ -205,14 +346,24 @@ int hash_train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, 
   static bool attr = false;
   if (!attr) {
     MNRF_CUDA_OK(cudaFuncSetAttribute(k_hash_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(HB_SMEM_FLOATS * sizeof(float))));
+    MNRF_CUDA_OK(cudaFuncSetAttribute(k_hash_bwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(HB2_SMEM_FLOATS * sizeof(float))));
     attr = true;
   }
-  const int n_tiles = (int)((P + 31) / 32);
-  int blocks = (n_tiles + HB_WARPS - 1) / HB_WARPS;
-  if (blocks > 148) blocks = 148;
-  k_hash_bwd<<<blocks, HB_WARPS * 32, HB_SMEM_FLOATS * sizeof(float), st>>>(f->hash_table, f->hash_wref, f->hg, rays, z, DR,
-                                                                           ray_detach_mirror, (int)P, S, F, second_order, gt[0],
-                                                                           sp, dxd);
+  if (hash_bwd_layout() == 2) {
+    const int n_tiles = (int)((P + ht2::NP2 - 1) / ht2::NP2);
+    int blocks = (n_tiles + HB2_WARPS - 1) / HB2_WARPS;
+    if (blocks > 148) blocks = 148;
+    k_hash_bwd2<<<blocks, HB2_WARPS * 32, HB2_SMEM_FLOATS * sizeof(float), st>>>(f->hash_table, f->hash_wref, f->hg, rays, z, DR,
+                                                                                ray_detach_mirror, (int)P, S, F, second_order,
+                                                                                gt[0], sp, dxd);
+  } else {
+    const int n_tiles = (int)((P + 31) / 32);
+    int blocks = (n_tiles + HB_WARPS - 1) / HB_WARPS;
+    if (blocks > 148) blocks = 148;
+    k_hash_bwd<<<blocks, HB_WARPS * 32, HB_SMEM_FLOATS * sizeof(float), st>>>(f->hash_table, f->hash_wref, f->hg, rays, z, DR,
+                                                                             ray_detach_mirror, (int)P, S, F, second_order, gt[0],
+                                                                             sp, dxd);
+  }
   MNRF_LAUNCH_OK();
   if (grad_rays != nullptr) {
     MNRF_REQUIRE(g.x_surface == nullptr || depth != nullptr, "hash train_pass_bwd: ray gradients need the depth output");

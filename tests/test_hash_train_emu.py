@@ -39,14 +39,18 @@ def emu(tmp_path_factory):
                     os.path.join(ROOT, "tests", "emu", "hash_train_emu.cpp")], check=True)
     lib = C.CDLL(out)
     lib.hash_bwd_emu.restype = C.c_int
+    lib.hash_bwd_emu2.restype = C.c_int
     return lib
+
+
+LAYOUTS = {"32x1": "hash_bwd_emu", "16x2": "hash_bwd_emu2"}  # points per warp tile x lanes per point (hash_train_math{,2}.cuh)
 
 
 def _fp(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def _run(lib, sd, x, d, DR, mirror_on, flags, bound):
+def _run(lib, sd, x, d, DR, mirror_on, flags, bound, layout="32x1"):
     lv, _ = HG.level_table(bound)
     M = Meta()
     M.bound = bound
@@ -69,7 +73,7 @@ def _run(lib, sd, x, d, DR, mirror_on, flags, bound):
     dxd = np.zeros((P, 8), np.float32)
     xs, ds, drs = (np.ascontiguousarray(t, np.float32) for t in (x, d, DR))
     mo = np.ascontiguousarray(mirror_on, np.int32)
-    rc = lib.hash_bwd_emu(_fp(table), _fp(wref), C.byref(M), _fp(xs), _fp(ds), _fp(drs), _fp(mo), P,
+    rc = getattr(lib, LAYOUTS[layout])(_fp(table), _fp(wref), C.byref(M), _fp(xs), _fp(ds), _fp(drs), _fp(mo), P,
                           int("normal_net.0.weight" in sd), int("is_mirror_net.0.weight" in sd), int(flags["compute_normal"]),
                           int(flags["detach_normal"]), int(flags["detach_mask"]), 1, int(flags["compute_normal"]),
                           _fp(gtable), _fp(gsmall), _fp(dxd))
@@ -113,8 +117,9 @@ CASES = {
 }
 
 
+@pytest.mark.parametrize("layout", list(LAYOUTS))
 @pytest.mark.parametrize("case", list(CASES))
-def test_hash_backward_math_matches_autograd(emu, case):
+def test_hash_backward_math_matches_autograd(emu, case, layout):
     flags = dict(CASES[case])
     heads = flags.pop("heads", True)
     bound = 1.0
@@ -133,7 +138,7 @@ def test_hash_backward_math_matches_autograd(emu, case):
     mirror_on = np.ones(P, np.int32)
     if flags["outside"]:
         mirror_on = (rng.uniform(size=P) < 0.5).astype(np.int32)
-    got, dxd = _run(emu, sd, x, d, DR, mirror_on, flags, bound)
+    got, dxd = _run(emu, sd, x, d, DR, mirror_on, flags, bound, layout)
     want, gx, gd = _oracle(sd, x, d, DR, mirror_on, flags, bound)
     for k, w in want.items():
         g = got[k].reshape(w.shape)
@@ -208,3 +213,24 @@ def test_hash_backward_zero_gradient_and_empty_heads(emu):
     for k in ("normal_net.0.weight", "normal_net.1.weight", "is_mirror_net.0.weight", "is_mirror_net.2.bias"):
         assert float(np.abs(g[k]).max()) == 0.0, k
     assert float(np.abs(g["encoder.params"]).max()) > 0
+
+
+@pytest.mark.parametrize("layout", list(LAYOUTS))
+def test_hash_backward_steps_do_not_depend_on_lane_order(emu, layout):
+    """On the GPU the lanes of a step run concurrently; here they run one after the other.  If some step read, in one lane, a
+    buffer element another lane writes in the same step (a missing barrier), the two lane orders would disagree."""
+    flags = dict(CASES["full"])
+    sd, x, d, DR = _setup(53, 31)
+    on = np.ones(53, np.int32)
+    try:
+        emu.hash_bwd_emu_set_reverse(0)
+        g0, q0 = _run(emu, sd, x, d, DR, on, flags, 1.0, layout)
+        emu.hash_bwd_emu_set_reverse(1)
+        g1, q1 = _run(emu, sd, x, d, DR, on, flags, 1.0, layout)
+    finally:
+        emu.hash_bwd_emu_set_reverse(0)
+    assert np.array_equal(q0, q1)
+    for k in g0:
+        # the accumulation order of the sums over points differs between the two runs: compare to rounding, not bit for bit
+        scale = max(np.abs(g0[k]).max(), 1e-20)
+        assert np.abs(g0[k] - g1[k]).max() / scale < 1e-5, k
