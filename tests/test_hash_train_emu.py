@@ -234,3 +234,30 @@ def test_hash_backward_steps_do_not_depend_on_lane_order(emu, layout):
         # the accumulation order of the sums over points differs between the two runs: compare to rounding, not bit for bit
         scale = max(np.abs(g0[k]).max(), 1e-20)
         assert np.abs(g0[k] - g1[k]).max() / scale < 1e-5, k
+
+
+def test_emulation_runs_the_same_step_sequence_as_the_kernels():
+    """The emulation harness repeats the kernels' step sequence by hand; keep the two in lockstep (order and names of the
+    phase_* / step_* calls of k_hash_bwd / k_hash_bwd2 vs hash_bwd_emu / hash_bwd_emu2)."""
+    import re
+    cu = open(os.path.join(ROOT, "mirror_nerf_b200", "csrc", "train_hash.cu")).read()
+    emu_src = open(os.path.join(ROOT, "tests", "emu", "hash_train_emu.cpp")).read()
+
+    def calls(text, prefix):
+        return re.findall(r"\b(" + prefix + r"_[a-z0-9]+)\(", text)
+
+    k1 = cu[cu.index("k_hash_bwd("):cu.index("k_hash_bwd2(")]
+    k2 = cu[cu.index("k_hash_bwd2("):cu.index("int hash_bwd_layout()")]
+    e1 = emu_src[emu_src.index('int hash_bwd_emu('):emu_src.index('int hash_bwd_emu_nw')]
+    e2 = emu_src[emu_src.index('int hash_bwd_emu2('):]
+    assert calls(k1, "phase") == calls(e1, "phase") and len(calls(k1, "phase")) == 14
+    assert calls(k2, "step") == calls(e2, "step") and len(calls(k2, "step")) == 26
+    # every step of the two-lanes-per-point kernel is followed by a warp barrier before the next one (step_n / step_o touch
+    # disjoint rows and share one)
+    body = k2[k2.index("step_a1("):k2.index("if (dxd != nullptr")]
+    stmts = [s.strip() for s in re.split(r";|\{|\}", body) if s.strip()]
+    names = [re.match(r"(?:if \(so\)\s*)?(step_[a-z0-9]+|__syncwarp)\(", s) for s in stmts]
+    seq = [m.group(1) for m in names if m]
+    for a, b in zip(seq, seq[1:]):
+        if a.startswith("step_") and b.startswith("step_"):
+            assert (a, b) == ("step_n", "step_o"), (a, b)
