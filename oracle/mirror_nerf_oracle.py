@@ -373,51 +373,155 @@ def reflect_rays(rays, x_surface, normal, near=0.1):
     return torch.cat([x_surface, r, torch.ones_like(rays[:, 7:8]) * near, rays[:, 7:8]], -1), r
 
 
-def trace_eval(render_fn, rays, max_recursive_level, level=0, typ="fine", normal_noises=None, trace_ray_times=0):
-    """Eval-semantics recursion (R/eval.py:132-160, 295-320, 515-548, 676-697): level 0 re-traces ALL rays, deeper
-    levels only mirror rays; blend rgb = m*reflect + (1-m)*base with the hard mask.
-
-    Roughness cone (R/eval.py:506-511, 623-674): `normal_noises` = list of trace_ray_times+1 noise tensors (n,3) added to
-    the surface normal before reflecting; the extra jittered reflections are traced for the mirror rays only and averaged
-    with the first (the reference's evident intent; as written it adds an (N_mirror,3) to an (N_rays,3) tensor)."""
-    res = render_fn(rays)
-    mask = res[f"mirror_mask_{typ}"]
+def _threshold_(mask):
+    """In-place hard clip of a rendered mirror mask (R/eval.py:305-306, R/train.py:165-166): exactly 0.5 stays."""
     mask[mask > 0.5] = 1
     mask[mask < 0.5] = 0
-    mb = mask.bool()
+    return mask
+
+
+def trace_eval(render_fn, rays, max_recursive_level, level=0, typ="fine", normal_noises=None, trace_ray_times=0,
+               noise_fn=None):
+    """Eval-semantics recursion, R/eval.py:132-160 (level call), :295-320 (mask + trace condition), :336-360 (normal),
+    :506-548 (jitter, reflect, secondary rays, compaction), :609-674 (recursive call + roughness cone), :676-723 (blend).
+    Level 0 re-traces ALL rays of a batch that contains a mirror pixel, deeper levels only the mirror rays.
+
+    Roughness cone (--app_control_mirror_roughness): `noise_fn(n) -> (n,3)` returns the ALREADY SCALED normal noise
+    (`randn_like(normal) * normal_noise_std`) and is called in the reference's order: once before the first reflection of
+    a level (:506-511), then once per extra reflection (:627-631), each draw followed by that reflection's whole sub-tree.
+    `normal_noises` (legacy) = a list of tensors consumed in that same call order.  As written the reference adds the
+    (N_mirror,3) colour of an extra reflection to the (N_rays,3) colour of the first one at level 0 (:655-666) and so only
+    runs when every ray of the batch is a mirror ray; for a partial mask this restatement adds at the mirror rows (the
+    evident intent) -- the pinned fixtures use all-mirror batches at level 0, where both coincide."""
+    if noise_fn is None and normal_noises is not None:
+        it = iter(normal_noises)
+        noise_fn = lambda n: next(it)
+    res = render_fn(rays)
     res[f"rgb_{typ}_reflect"] = torch.zeros_like(res[f"rgb_{typ}"])
     res[f"depth_{typ}_reflect"] = torch.zeros_like(res[f"depth_{typ}"])
+    if f"mirror_mask_{typ}" not in res:
+        return res
+    mb = _threshold_(res[f"mirror_mask_{typ}"]).bool()
     if bool(mb.any()) and level < max_recursive_level:
-        n0 = res[f"surface_normal_{typ}"]
-        jit = (lambda t: n0 + normal_noises[t]) if normal_noises is not None else (lambda t: n0)
-        sec, r = reflect_rays(rays, res[f"x_surface_{typ}"], jit(0))
-        res["reflect_direction"] = r
+        n0 = res[f"surface_normal_{typ}"] if f"surface_normal_{typ}" in res else res[f"surface_normal_grad_{typ}"]
         only_mirror = not (level < 1)
-        sub = trace_eval(render_fn, sec[mb] if only_mirror else sec, max_recursive_level, level + 1, typ)
-        child = sub[f"rgb_{typ}"].clone()
-        if normal_noises is not None and trace_ray_times > 0:
-            for t in range(1, trace_ray_times + 1):
-                sec_t, _ = reflect_rays(rays, res[f"x_surface_{typ}"], jit(t))
-                sub_t = trace_eval(render_fn, sec_t[mb], max_recursive_level, level + 1, typ)
-                if only_mirror:
-                    child = child + sub_t[f"rgb_{typ}"]
-                else:
-                    child[mb] = child[mb] + sub_t[f"rgb_{typ}"]
-            if only_mirror:
-                child = child / (trace_ray_times + 1)
-            else:
-                child[mb] = child[mb] / (trace_ray_times + 1)
-        base = res[f"rgb_{typ}"]
-        res[f"rgb_{typ}_direct"] = base
+        kw = dict(typ=typ, trace_ray_times=trace_ray_times, noise_fn=noise_fn)
+        normal = n0 + noise_fn(n0.shape[0]) if noise_fn is not None else n0
+        sec, r = reflect_rays(rays, res[f"x_surface_{typ}"], normal)
+        res["reflect_direction"] = r
         if only_mirror:
-            refl = base.clone()
-            refl[mb] = child
-            res[f"rgb_{typ}_reflect"][mb] = child
-            res[f"depth_{typ}_reflect"][mb] = sub[f"depth_{typ}"]
+            sec = sec[mb]
+        if sec.shape[0] > 0:
+            sub = trace_eval(render_fn, sec, max_recursive_level, level + 1, **kw)
+            child = sub[f"rgb_{typ}"]
+            if noise_fn is not None:
+                for _ in range(trace_ray_times):
+                    sec_t, _ = reflect_rays(rays, res[f"x_surface_{typ}"], n0 + noise_fn(n0.shape[0]))
+                    sub_t = trace_eval(render_fn, sec_t[mb], max_recursive_level, level + 1, **kw)
+                    if only_mirror or sub_t[f"rgb_{typ}"].shape == child.shape:
+                        child = child + sub_t[f"rgb_{typ}"]
+                    else:
+                        child = child.clone()
+                        child[mb] = child[mb] + sub_t[f"rgb_{typ}"]
+                if only_mirror or bool(mb.all()):
+                    child = child / (trace_ray_times + 1)
+                else:
+                    child = child.clone()
+                    child[mb] = child[mb] / (trace_ray_times + 1)
+            base = res[f"rgb_{typ}"]
+            res[f"rgb_{typ}_direct"] = base
+            if only_mirror:
+                refl = base.clone()
+                refl[mb] = child
+                res[f"rgb_{typ}_reflect"][mb] = child
+                res[f"depth_{typ}_reflect"][mb] = sub[f"depth_{typ}"]
+            else:
+                refl = child
+                res[f"rgb_{typ}_reflect"] = child
+                res[f"depth_{typ}_reflect"] = sub[f"depth_{typ}"]
+            m3 = mb.float().unsqueeze(-1).repeat(1, 3)
+            res[f"rgb_{typ}"] = m3 * refl + (1 - m3) * base
+    return res
+
+
+def trace_train(render_fn, rays, gt_mirror_mask, max_recursive_level, *, level=0, mask_prev=None, select_type="fine",
+                trace_secondary_rays=True, train_geometry_stage=False, only_trace_rays_in_mirrors=True, for_vis=False,
+                detach_normal_in_reflection=False, detach_ref_color=False, is_eval=False):
+    """Train-semantics recursion, R/train.py:129-348 (`NeRFSystem.render_rays_chunk_recursively`).
+
+    `render_fn(rays) -> dict` is the level call (:132-145: render_rays with the run's hparams and **extra_chunk).
+    `gt_mirror_mask` (N,) is extra_chunk["mirror_mask"]: used at level 0 unless it has a negative ("no GT") entry (:155-166);
+    it keeps the PARENT length at deeper levels, exactly as the reference passes **extra_chunk down (:254-259).
+    `detach_ref_color` = hparams.detach_ref_color_for_blend and current_epoch >= train_geometry_stage_end_epoch + 1 (:276-281)."""
+    res = render_fn(rays)
+    if mask_prev is None:
+        mask_prev = torch.ones(rays.shape[0]).bool()                                   # train.py:116-118
+    mirror_mask = gt_mirror_mask.clone()                                               # :155
+    if bool((mirror_mask < 0).any()) or level > 0:                                     # :157-166
+        if "mirror_mask_fine" in res:
+            mirror_mask = res["mirror_mask_fine"].detach()
+        elif "mirror_mask_coarse" in res:
+            mirror_mask = res["mirror_mask_coarse"].detach()
         else:
-            refl = child
-            res[f"rgb_{typ}_reflect"] = child
-            res[f"depth_{typ}_reflect"] = sub[f"depth_{typ}"]
-        m3 = mb.float().unsqueeze(-1).repeat(1, 3)
-        res[f"rgb_{typ}"] = m3 * refl + (1 - m3) * base
+            mirror_mask = torch.zeros(rays.shape[0])
+        _threshold_(mirror_mask)
+    if (not only_trace_rays_in_mirrors) and level > 0:                                 # :167-168
+        mirror_mask = mirror_mask * mask_prev.detach()
+    mb = mirror_mask.bool()
+    trace = trace_secondary_rays and (not train_geometry_stage) and (bool(mb.any()) or for_vis)   # :172-176
+    if level >= max_recursive_level:
+        trace = False
+    t = select_type
+    if trace:
+        if f"pred_normal_{t}" in res:                                                  # :194-214
+            normal = res[f"surface_normal_{t}"] if f"surface_normal_{t}" in res else \
+                (res[f"pred_normal_{t}"] * res[f"weights_{t}"].unsqueeze(-1)).sum(1)
+        else:
+            normal = res[f"surface_normal_grad_{t}"] if f"surface_normal_grad_{t}" in res else \
+                (res[f"normal_{t}"] * res[f"weights_{t}"].unsqueeze(-1)).sum(1)
+        sec, r = reflect_rays(rays, res[f"x_surface_{t}"], normal.detach() if detach_normal_in_reflection else normal)
+        sec_o = res[f"x_surface_{t}"]
+        if only_trace_rays_in_mirrors:
+            sec = sec[mb]                                                              # :248-252
+        if sec.shape[0] > 0:
+            sub = trace_train(render_fn, sec, gt_mirror_mask, max_recursive_level, level=level + 1, mask_prev=mirror_mask,
+                              select_type=t, trace_secondary_rays=trace_secondary_rays,
+                              train_geometry_stage=train_geometry_stage, only_trace_rays_in_mirrors=only_trace_rays_in_mirrors,
+                              for_vis=for_vis, detach_normal_in_reflection=detach_normal_in_reflection,
+                              detach_ref_color=detach_ref_color, is_eval=is_eval)
+            for typ in ("coarse", "fine"):                                             # :263-311
+                if f"rgb_{typ}" in res and f"rgb_{typ}" in sub:
+                    res[f"rgb_{typ}_direct"] = res[f"rgb_{typ}"]
+                    base = res[f"rgb_{typ}"]
+                    if only_trace_rays_in_mirrors:
+                        refl = base.clone().detach()
+                        refl[mb] = sub[f"rgb_{typ}"]
+                    else:
+                        refl = sub[f"rgb_{typ}"]
+                    if detach_ref_color:
+                        refl = refl.detach()
+                    m3 = mirror_mask.float().unsqueeze(-1).repeat(1, 3)
+                    res[f"rgb_{typ}"] = m3 * refl + (1 - m3) * base
+                    if is_eval:
+                        if only_trace_rays_in_mirrors:
+                            res[f"rgb_{typ}_reflect"] = torch.zeros_like(res[f"rgb_{typ}"])
+                            res[f"rgb_{typ}_reflect"][mb] = sub[f"rgb_{typ}"]
+                        else:
+                            res[f"rgb_{typ}_reflect"] = sub[f"rgb_{typ}"]
+            if is_eval:                                                                # :312-326
+                if only_trace_rays_in_mirrors:
+                    res[f"depth_{t}_reflect"] = torch.zeros_like(res[f"depth_{t}"])
+                    res[f"depth_{t}_reflect"][mb] = sub[f"depth_{t}"]
+                else:
+                    res[f"depth_{t}_reflect"] = sub[f"depth_{t}"]
+                res["secondary_rays_o"] = sec_o
+                res["reflect_direction"] = r
+    elif is_eval:                                                                      # :327-346
+        for typ in ("coarse", "fine"):
+            if f"rgb_{typ}" in res:
+                res[f"rgb_{typ}_reflect"] = torch.zeros_like(res[f"rgb_{typ}"])
+                res[f"rgb_{typ}_direct"] = torch.zeros_like(res[f"rgb_{typ}"])
+        res[f"depth_{t}_reflect"] = torch.zeros_like(res[f"depth_{t}"])
+        res["secondary_rays_o"] = torch.zeros_like(res[f"rgb_{t}"])
+        res["reflect_direction"] = torch.zeros_like(res[f"rgb_{t}"])
     return res

@@ -32,10 +32,15 @@ def golden(request):
     if not os.path.isdir(os.path.join(REFERENCE, "models")):
         pytest.skip("reference tree not present on this machine")
     sys.path.insert(0, GOLDEN)
-    import make_golden
-    files = make_golden.generate()
+    files = {}
 
     def load(name):
+        if name not in files:
+            # two generators: the render_rays level (make_golden.py) and its callers / helpers (make_golden_recursion.py)
+            import make_golden
+            import make_golden_recursion
+            gen = make_golden_recursion if name in ("recursion_eval", "recursion_train", "helpers") else make_golden
+            files.update(gen.generate())
         return dict(files[name])
     load.exact = True
     return load
