@@ -401,8 +401,9 @@ def run_ours(args):
     kw = dict(field_impl=args.field_impl)
 
     def step(rays):
+        # the device-side recursion (mnrf_render_recursive): one C call per image, no host sync between level 0 and the blend
         return render_rays_recursive(models, emb, rays, N_SAMPLES, False, 0, 0, N_IMPORTANCE, 32768, False,
-                                     max_recursive_level=1, **kw)
+                                     max_recursive_level=1, compact_outputs=not args.python_recursion, **kw)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
@@ -477,13 +478,15 @@ def run_ours(args):
         traffic, traffic_src = tj["dram_bytes_per_launch_avg"], tj["source"]
     except Exception:
         pass
-    mma_per_mac = 3 if args.field_impl == "tc3" else 1
+    mma_per_mac = {"tc3": 3, "tc2": 2, "tc1": 1}[args.field_impl]
 
     line = {
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None,
-        "dtype": "f16x3-split operands, f32 accumulate (fp32-grade)" if args.field_impl == "tc3" else "f16, f32 accumulate",
+        "dtype": {"tc3": "f16x3-split operands, f32 accumulate (fp32-grade)",
+                  "tc2": "f16 + 2 x e4m3 correction passes (fp8 datapath), f32 accumulate (operand error ~2^-16)",
+                  "tc1": "f16, f32 accumulate"}[args.field_impl],
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": n, "levels_per_ray": LEVELS,
                    "field_impl": args.field_impl, "mirror_ray_fraction": mirror_frac,
@@ -499,7 +502,7 @@ def run_ours(args):
                      "kernel": "k_field_tc", "kernel_launches": int(k_n.value), "kernel_ms": k_ms.value,
                      "kernel_share_of_step": k_ms.value / ms_total if ms_total else None,
                      "flops_basis": "algorithmic 2*MAC of the reference layers (SURVEY.md 8d); the kernel issues "
-                                    f"{mma_per_mac} tensor-core MAC per algorithmic MAC",
+                                    f"{mma_per_mac} fp16-pass equivalents of tensor-core work per algorithmic MAC",
                      "tensor_pipe_flops_frac": (achieved * mma_per_mac / peak if achieved else None)},
     }
 
@@ -612,7 +615,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--field-impl", default="tc3", choices=["tc3", "tc1"])
+    ap.add_argument("--field-impl", default=os.environ.get("MNRF_FIELD_IMPL", "tc3"), choices=["tc3", "tc2", "tc1"])
+    ap.add_argument("--python-recursion", action="store_true",
+                    help="drive the bounce from Python (per-level launches + host syncs) instead of mnrf_render_recursive")
     ap.add_argument("--ref-rays", type=int, default=2048, help="rays per step of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--config4", action="store_true", help="also time BASELINE config 4 (2 bounces + roughness cone)")

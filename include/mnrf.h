@@ -15,8 +15,9 @@
  *   mnrf_searchsorted_right R/models/rendering.py:33        (torch.searchsorted(cdf,u,right=True))
  *   mnrf_render_level       R/models/rendering.py:54-369    (render_rays, one level)
  *   mnrf_render_level_host  same, HOST buffers in/out (what eval.py:1122-1138,735-736 does around it)
- *   mnrf_reflect_rays / mnrf_compact_rays / mnrf_blend_reflection
- *                           R/eval.py:295-320,515-548,676-697 and R/train.py:153-296 (Whitted bounce)
+ *   mnrf_reflect_rays / mnrf_compact_rows / mnrf_blend_reflection
+ *                           R/eval.py:295-320,515-548,676-697 and R/train.py:153-296 (Whitted bounce, one step at a time)
+ *   mnrf_render_recursive   R/eval.py:114-740 batched_inference (the whole recursion incl. the roughness cone, device-side)
  *   mnrf_train_pass_fwd/bwd implicit torch.autograd of R/models/rendering.py:87-266 + mirror_nerf.py:101-212 (training)
  *   mnrf_adam_step / mnrf_peer_allreduce_adam
  *                           R/utils/__init__.py:47-58 (torch.optim.Adam) + PL DDP gradient all-reduce (R/train.py:582)
@@ -74,6 +75,8 @@ int mnrf_hash_field_create(mnrf_field** out, const float* const* tensors, int64_
 
 /* which kernel evaluates the MLP */
 #define MNRF_IMPL_TC3 3   /* tcgen05, fp16 hi/lo split operands, 3 MMAs per product (fp32-grade; parity mode) */
+#define MNRF_IMPL_TC2 2   /* tcgen05, 1 fp16 pass + the two cross terms as e4m3 passes at twice the rate (2 pass-equivalents;
+                             operand error ~2^-16: inside the 1e-3 parity bar on scene-like fields)      */
 #define MNRF_IMPL_TC1 1   /* tcgen05, single fp16 pass (speed mode; does not meet the 1e-3 parity bar)      */
 #define MNRF_IMPL_FP32 0  /* CUDA-core fp32 verification kernel (slow; the only one that exports geo_feat) */
 
@@ -314,6 +317,49 @@ int mnrf_axpy_rows(float* dense, const float* compact, const int* index, int n, 
 int mnrf_blend_reflection(const float* base_rgb, const float* mask, const float* child_rgb,
                           const float* child_depth, const int* index, int n, float* rgb_out, float* rgb_reflect,
                           float* depth_reflect, void* stream);
+
+/* ---- Whitted recursion on the device (additive entry point; the drop-in render_rays stays single-level) ------------------
+ * What the reference's callers do around render_rays at inference time -- R/eval.py::batched_inference:
+ *   :132-160 level call, :295-320 mask threshold + trace condition, :336-360 normal, :506-548 jitter / reflect / secondary rays /
+ *   compaction, :609-674 recursive call + roughness cone (--app_control_mirror_roughness), :676-723 blend
+ * (R/train.py:129-348 has the same structure with `only_trace_rays_in_mirrors` from the hparams) -- as ONE call without any
+ * host synchronisation: a level's mirror rays are counted, compacted and re-enqueued on the device, and the next level's
+ * kernels are launched for a worst-case row count and read the live count from device memory.  The T+1 jittered reflections
+ * of a level's mirror rays are rendered as ONE child batch and averaged per parent ray. */
+typedef struct mnrf_trace_cfg {
+  mnrf_level_cfg level;            /* per-level render_rays arguments; eval semantics: perturb = noise_std = 0, test_time = 1 */
+  int max_recursive_level;         /* 0 = no bounce                                                                           */
+  int only_trace_rays_in_mirrors;  /* -1: eval.py (level 0 re-traces ALL rays of a batch that has a mirror pixel, deeper levels
+                                      only mirror rays, :159); 1: compact at every level (train.py hparam)                     */
+  int trace_ray_times;             /* roughness cone: extra jittered reflections per mirror ray (0 = off)                      */
+  float normal_noise_std;          /* normal += N(0, std^2) before reflecting (0 = off)                                        */
+  uint64_t noise_seed;             /* Philox seed of the on-device normal noise                                                */
+} mnrf_trace_cfg;
+
+typedef struct mnrf_trace_out {    /* level-0 results, DEVICE; rgb, depth, opacity are required, the rest optional (NULL)      */
+  float* rgb;               /* (n,3) blended colour  m*reflect + (1-m)*direct                                                  */
+  float* rgb_direct;        /* (n,3) level-0 colour before the blend                                                           */
+  float* rgb_reflect;       /* (n,3) colour seen along the reflected ray (zeros where nothing was traced)                      */
+  float* depth;             /* (n)                                                                                             */
+  float* depth_reflect;     /* (n)                                                                                             */
+  float* opacity;           /* (n)                                                                                             */
+  float* mirror_mask;       /* (n) hard-clipped mask (>0.5 -> 1, <0.5 -> 0)                                                    */
+  float* surface_normal;    /* (n,3) composited normal used for the reflection (not normalised)                                */
+  float* x_surface;         /* (n,3)                                                                                           */
+  float* reflect_direction; /* (n,3) of the first (t = 0) reflection                                                           */
+  int* level_rays;          /* (max_recursive_level + 1) ints: rays rendered per level, summed over that level's batches       */
+} mnrf_trace_out;
+
+/* Scratch for n primary rays.  `budget_bytes` > 0 caps it: deeper levels are then rendered in slabs of as many rows as fit
+ * (more launches, less memory); 0 = everything in one batch per level.  Returns -1 on bad arguments. */
+int64_t mnrf_recursive_workspace_bytes(const mnrf_field* coarse, const mnrf_field* fine, int n, const mnrf_trace_cfg* cfg,
+                                       int64_t budget_bytes);
+/* level0_normal_noise: optional (trace_ray_times+1, n, 3) standard-normal draws for the LEVEL-0 reflections (tests / replay of a
+ * torch stream); deeper levels and a NULL pointer use the on-device generator.  z_steps / u_det as in mnrf_render_level. */
+int mnrf_render_recursive(const mnrf_field* coarse, const mnrf_field* fine, const float* rays, int n,
+                          const mnrf_trace_cfg* cfg, const float* z_steps, const float* u_det,
+                          const float* level0_normal_noise, void* workspace, int64_t workspace_bytes,
+                          const mnrf_trace_out* out, void* stream);
 
 /* ---- misc ----------------------------------------------------------------------------------------- */
 const char* mnrf_last_error(void);

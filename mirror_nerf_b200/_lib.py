@@ -8,8 +8,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmnrf.so")
 
-IMPL_TC3, IMPL_TC1, IMPL_FP32 = 3, 1, 0
-IMPL_BY_NAME = {"tc3": IMPL_TC3, "tc1": IMPL_TC1, "fp32": IMPL_FP32}
+IMPL_TC3, IMPL_TC2, IMPL_TC1, IMPL_FP32 = 3, 2, 1, 0
+IMPL_BY_NAME = {"tc3": IMPL_TC3, "tc2": IMPL_TC2, "tc1": IMPL_TC1, "fp32": IMPL_FP32}
 NUM_PARAM_TENSORS = 32
 NUM_HASH_PARAM_TENSORS = 12
 RAW_STRIDE = 8
@@ -37,6 +37,17 @@ class LevelRng(C.Structure):
 class LevelOut(C.Structure):
     _fields_ = [("z_coarse", C.c_void_p), ("coarse", CompositeOut), ("normal_coarse", C.c_void_p),
                 ("z_fine", C.c_void_p), ("fine", CompositeOut), ("normal_fine", C.c_void_p)]
+
+
+class TraceCfg(C.Structure):
+    _fields_ = [("level", LevelCfg), ("max_recursive_level", c_int), ("only_trace_rays_in_mirrors", c_int),
+                ("trace_ray_times", c_int), ("normal_noise_std", C.c_float), ("noise_seed", C.c_uint64)]
+
+
+class TraceOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "rgb", "rgb_direct", "rgb_reflect", "depth", "depth_reflect", "opacity", "mirror_mask", "surface_normal",
+        "x_surface", "reflect_direction", "level_rays")]
 
 
 class TrainCfg(C.Structure):
@@ -90,6 +101,9 @@ _SIGS = {
     "mnrf_render_level_host": (c_int, [C.c_void_p, C.c_void_p, c_float_p, c_int, C.POINTER(LevelCfg), c_float_p,
                                        c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
                                        C.c_void_p]),
+    "mnrf_recursive_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_void_p, c_int, C.POINTER(TraceCfg), C.c_int64]),
+    "mnrf_render_recursive": (c_int, [C.c_void_p, C.c_void_p, c_float_p, c_int, C.POINTER(TraceCfg), c_float_p, c_float_p,
+                                      c_float_p, C.c_void_p, C.c_int64, C.POINTER(TraceOut), C.c_void_p]),
     "mnrf_train_fwd_workspace_bytes": (C.c_int64, [c_int, c_int, c_int]),
     "mnrf_train_bwd_workspace_bytes": (C.c_int64, [c_int, c_int, c_int]),
     "mnrf_field_train_fwd_workspace_bytes": (C.c_int64, [C.c_void_p, c_int, c_int, c_int]),

@@ -78,6 +78,11 @@ class _PassFn(torch.autograd.Function):
         ctx.rays, ctx.z, ctx.noise, ctx.ray_detach = rays.detach(), z, noise, ray_detach
         ctx.depth = t["depth"].clone()  # private copy: callers may modify outputs in place
         ctx.param_shapes = [tuple(q.shape) for q in params]
+        # The backward re-reads the packed weights through pf.handle.  save_for_backward makes autograd's version check cover
+        # the parameters (an in-place optimizer step between forward and backward raises, as for any torch op), and the pack
+        # generation covers re-packs by raw kernels that do not bump `_version` (FlatDataParallel.step, load_state_dict).
+        ctx.save_for_backward(*params)
+        ctx.generation = getattr(pf, "generation", 0)
         ctx.out_keys = [k for k in _OUT_ORDER if k in t]
         return tuple(t[k] for k in ctx.out_keys)
 
@@ -87,6 +92,10 @@ class _PassFn(torch.autograd.Function):
         lib = _lib.load()
         meta, cfg = ctx.meta, ctx.cfg
         pf = meta["field"]
+        _ = ctx.saved_tensors  # raises if a parameter was modified in place since the forward
+        if getattr(pf, "generation", 0) != ctx.generation:
+            raise RuntimeError("the field's weights were re-packed between this pass's forward and its backward (optimizer step / "
+                               "load_state_dict in between): the saved activations no longer match the weights")
         n, S = ctx.z.shape
         dev = ctx.rays.device
         g = {}
@@ -95,7 +104,13 @@ class _PassFn(torch.autograd.Function):
                 g[k] = go.contiguous().float()
         grads = _lib.TrainGrads(**{k: _ptr(g.get(k)) for k in _lib.TRAIN_GRAD_FIELDS})
         # gradient tensors in the reference's parameter order / layout; absent heads stay NULL
-        gts = {k: torch.zeros(shp, device=dev, dtype=torch.float32) for k, shp in zip(meta["keys"], ctx.param_shapes)}
+        # one zero-filled flat buffer, one view per parameter (one fill launch instead of one per tensor)
+        sizes = [int(torch.Size(shp).numel()) for shp in ctx.param_shapes]
+        offs = [0]
+        for sz in sizes:
+            offs.append(offs[-1] + ((sz + 3) & ~3))  # 16-byte aligned views (vector atomics / float4 stores of the kernels)
+        flat = torch.zeros(offs[-1], device=dev, dtype=torch.float32)
+        gts = {k: flat[o:o + sz].view(shp) for k, shp, o, sz in zip(meta["keys"], ctx.param_shapes, offs, sizes)}
         all_keys = meta["all_keys"]  # the ABI's tensor order for this field kind (32 MLP tensors / 12 hash-grid tensors)
         arr = (C.c_void_p * len(all_keys))(*[None if k not in gts else gts[k].data_ptr() for k in all_keys])
         grad_rays = torch.empty(n, 8, device=dev, dtype=torch.float32) if ctx.needs_input_grad[1] else None

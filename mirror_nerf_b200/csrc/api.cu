@@ -22,6 +22,23 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+bool first_use_on_device(int tag, int* num_sms) {
+  constexpr int MAX_DEV = 64;
+  static std::atomic<unsigned char> done[MAX_DEV][TAG_COUNT];
+  static std::atomic<int> sms[MAX_DEV];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) dev = 0;
+  if (num_sms != nullptr) {
+    int n = sms[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
+      if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 0;
+      sms[dev].store(n, std::memory_order_relaxed);
+    }
+    *num_sms = n;
+  }
+  return done[dev][tag].exchange(1, std::memory_order_relaxed) == 0;
+}
+
 // ---- per-launch timing of the tcgen05 field kernel (roofline numbers of bench.py) ------------------
 struct ProfRec { cudaEvent_t e0, e1; double flops; };
 static bool g_prof_on = false;
@@ -66,14 +83,15 @@ __global__ void k_unpack_raw(const float* __restrict__ raw, int n, float* __rest
 }
 
 int check_impl(int impl) {
-  MNRF_REQUIRE(impl == MNRF_IMPL_TC3 || impl == MNRF_IMPL_TC1 || impl == MNRF_IMPL_FP32, "unknown impl %d", impl);
+  MNRF_REQUIRE(impl == MNRF_IMPL_TC3 || impl == MNRF_IMPL_TC2 || impl == MNRF_IMPL_TC1 || impl == MNRF_IMPL_FP32,
+               "unknown impl %d", impl);
   return 0;
 }
 
 int run_field(const mnrf_field* f, int impl, const FieldIO& io, cudaStream_t st) {
   if (f->kind == 1) return launch_field_hash(f, io, st);
   if (impl == MNRF_IMPL_FP32) return launch_field_fp32(f, io, st);
-  return launch_field_tc(f, io, impl == MNRF_IMPL_TC3 ? 3 : 1, st);
+  return launch_field_tc(f, io, impl, st);  // MNRF_IMPL_TC1/2/3 == number of fp16-pass equivalents
 }
 
 }  // namespace
@@ -133,13 +151,12 @@ int mnrf_field_create(mnrf_field** out, const float* const* tensors, void* strea
   f->L = make_f32_layout();
   f->f32 = nullptr;
   f->tc = nullptr;
+  f->tc8 = nullptr;
   f->t32 = nullptr;
-  if (cudaMalloc(&f->f32, sizeof(float) * f->L.total) != cudaSuccess ||
-      cudaMalloc(&f->tc, TC_TOTAL_BYTES) != cudaSuccess || cudaMalloc(&f->t32, T32_TOTAL_BYTES) != cudaSuccess) {
+  if (cudaMalloc(&f->f32, sizeof(float) * f->L.total) != cudaSuccess || cudaMalloc(&f->tc, TC_TOTAL_BYTES) != cudaSuccess ||
+      cudaMalloc(&f->tc8, TC_TOTAL_BYTES) != cudaSuccess || cudaMalloc(&f->t32, T32_TOTAL_BYTES) != cudaSuccess) {
     set_error("field_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
-    if (f->f32) cudaFree(f->f32);
-    if (f->tc) cudaFree(f->tc);
-    delete f;
+    mnrf_field_destroy(f);
     return 1;
   }
   if (pack_field(f, tensors, S_(stream))) { mnrf_field_destroy(f); return 1; }
@@ -167,7 +184,7 @@ int mnrf_hash_field_create(mnrf_field** out, const float* const* tensors, int64_
   f->kind = 1;
   f->has_normal = hn;
   f->has_mirror = hm;
-  f->f32 = nullptr; f->tc = nullptr; f->t32 = nullptr;
+  f->f32 = nullptr; f->tc = nullptr; f->tc8 = nullptr; f->t32 = nullptr;
   f->hash_table = nullptr; f->hash_w = nullptr; f->hash_wref = nullptr;
   f->hg.bound = bound;
   for (int l = 0; l < HG_LEVELS; ++l) {
@@ -206,6 +223,7 @@ void mnrf_field_destroy(mnrf_field* f) {
   if (f == nullptr) return;
   if (f->f32) cudaFree(f->f32);
   if (f->tc) cudaFree(f->tc);
+  if (f->tc8) cudaFree(f->tc8);
   if (f->t32) cudaFree(f->t32);
   if (f->hash_table) cudaFree(f->hash_table);
   if (f->hash_w) cudaFree(f->hash_w);
@@ -353,6 +371,16 @@ int64_t mnrf_level_workspace_bytes(int n, const mnrf_level_cfg* cfg) {
 int mnrf_render_level(const mnrf_field* coarse, const mnrf_field* fine, const float* rays, int n,
                       const mnrf_level_cfg* cfg, const mnrf_level_rng* rng, const float* z_steps, const float* u_det,
                       void* workspace, int64_t workspace_bytes, const mnrf_level_out* out, void* stream) {
+  return mnrf::render_level(coarse, fine, rays, n, cfg, rng, z_steps, u_det, workspace, workspace_bytes, out, stream, nullptr);
+}
+
+}  // extern "C"
+
+// One render level; `n_dev` (optional, device) = number of rays that are really alive: every kernel is launched for n rays and
+// processes min(n, *n_dev) of them (mnrf_render_recursive sizes deeper levels on the device, no host read-back).
+int mnrf::render_level(const mnrf_field* coarse, const mnrf_field* fine, const float* rays, int n,
+                       const mnrf_level_cfg* cfg, const mnrf_level_rng* rng, const float* z_steps, const float* u_det,
+                       void* workspace, int64_t workspace_bytes, const mnrf_level_out* out, void* stream, const int* n_dev) {
   MNRF_REQUIRE(coarse && rays && cfg && z_steps && out, "render_level: null argument");
   if (check_impl(cfg->impl)) return 2;
   if (n <= 0) return 0;
@@ -372,14 +400,14 @@ int mnrf_render_level(const mnrf_field* coarse, const mnrf_field* fine, const fl
   const int impl = cfg->impl;
 
   // ---- coarse pass (rendering.py:271-305) ----
-  if (launch_coarse_z(rays, n, z_steps, Sc, cfg->use_disp, cfg->perturb, rng->perturb_u, out->z_coarse, st)) return 1;
+  if (launch_coarse_z(rays, n, z_steps, Sc, cfg->use_disp, cfg->perturb, rng->perturb_u, out->z_coarse, st, n_dev)) return 1;
   const bool sig_only = cfg->test_time && fine != nullptr;  // rendering.py:139
   FieldIO io{};
-  io.rays = rays; io.z = out->z_coarse; io.n_points = n * Sc; io.S = Sc; io.sigma_only = sig_only;
+  io.rays = rays; io.z = out->z_coarse; io.n_points = n * Sc; io.S = Sc; io.sigma_only = sig_only; io.n_rays_dev = n_dev;
   if (sig_only) {
     io.sigma_out = buf_c;
   } else {
-    if (coarse->kind == 0 && launch_dirbias(coarse, rays, n, 8, 0, dirbias, st)) return 1;
+    if (coarse->kind == 0 && launch_dirbias(coarse, rays, n, 8, 0, dirbias, st, n_dev)) return 1;
     io.dirbias = dirbias;
     io.raw = buf_c;
     if (cfg->compute_normal) {
@@ -390,7 +418,7 @@ int mnrf_render_level(const mnrf_field* coarse, const mnrf_field* fine, const fl
   if (run_field(coarse, impl, io, st)) return 1;
   if (launch_composite(rays, out->z_coarse, buf_c, sig_only ? 1 : 8, sig_only ? nullptr : buf_c,
                        sig_only ? nullptr : io.normal_out, rng->noise_coarse, cfg->noise_std, n, Sc, cfg->white_back,
-                       out->coarse, st))
+                       out->coarse, st, n_dev))
     return 1;
 
   // ---- importance resampling + second pass (rendering.py:307-361) ----
@@ -400,11 +428,11 @@ int mnrf_render_level(const mnrf_field* coarse, const mnrf_field* fine, const fl
     const float* u = rng->u_pdf != nullptr ? rng->u_pdf : u_det;
     MNRF_REQUIRE(u != nullptr, "render_level: need u_pdf or u_det");
     if (launch_sample_pdf(out->z_coarse, nullptr, out->coarse.weights, Sc, 1, n, Sc, Ni, u,
-                          rng->u_pdf != nullptr ? Ni : 0, out->z_fine, nullptr, nullptr, nullptr, st))
+                          rng->u_pdf != nullptr ? Ni : 0, out->z_fine, nullptr, nullptr, nullptr, st, n_dev))
       return 1;
-    if (second->kind == 0 && launch_dirbias(second, rays, n, 8, 0, dirbias, st)) return 1;
+    if (second->kind == 0 && launch_dirbias(second, rays, n, 8, 0, dirbias, st, n_dev)) return 1;
     FieldIO io2{};
-    io2.rays = rays; io2.z = out->z_fine; io2.n_points = n * Sf; io2.S = Sf; io2.sigma_only = 0;
+    io2.rays = rays; io2.z = out->z_fine; io2.n_points = n * Sf; io2.S = Sf; io2.sigma_only = 0; io2.n_rays_dev = n_dev;
     io2.dirbias = dirbias; io2.raw = buf_f;
     if (cfg->compute_normal) {
       MNRF_REQUIRE(out->normal_fine != nullptr, "render_level: compute_normal needs normal_fine");
@@ -412,11 +440,13 @@ int mnrf_render_level(const mnrf_field* coarse, const mnrf_field* fine, const fl
     }
     if (run_field(second, impl, io2, st)) return 1;
     if (launch_composite(rays, out->z_fine, buf_f, 8, buf_f, io2.normal_out, rng->noise_fine, cfg->noise_std, n, Sf,
-                         cfg->white_back, out->fine, st))
+                         cfg->white_back, out->fine, st, n_dev))
       return 1;
   }
   return 0;
 }
+
+extern "C" {
 
 int mnrf_render_level_host(const mnrf_field* coarse, const mnrf_field* fine, const float* rays_host, int n,
                            const mnrf_level_cfg* cfg, const float* z_steps_host, const float* u_det_host, float* rgb,

@@ -183,8 +183,10 @@ struct mnrf_field {
   int has_mirror;
   float* f32;        // device, mnrf::F32Layout
   uint8_t* tc;       // device, TC_TOTAL_BYTES of fp16 hi/lo blobs
+  uint8_t* tc8;      // device, TC_TOTAL_BYTES: per K32 chunk [fp16 hi | e4m3(2^-10 hi), e4m3(lo)] blobs of the fp8-corrected mode
   uint8_t* t32;      // device, T32_TOTAL_BYTES of tf32 hi/lo blobs (training GEMMs)
   mnrf::F32Layout L;
+  unsigned long long pack_stamp;  // unique per pack_field call (keys the constant-memory copies of the epilogue table)
 };
 
 namespace mnrf {
@@ -192,6 +194,10 @@ namespace mnrf {
 // error plumbing ---------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+// One-time per-DEVICE launch setup (cudaFuncSetAttribute applies to the device that is current when it is called):
+// returns true the first time it is called for `tag` on the current device.  `num_sms` (optional) = SM count of that device.
+bool first_use_on_device(int tag, int* num_sms = nullptr);
+enum { TAG_FIELD_TC = 0, TAG_FIELD_FP32, TAG_FIELD_HASH, TAG_TRAIN_TC_NN, TAG_TRAIN_TC_TN, TAG_TRAIN_HASH, TAG_COUNT };
 #define MNRF_CUDA_OK(expr)                                                              \
   do {                                                                                  \
     cudaError_t _e = (expr);                                                            \
@@ -227,7 +233,7 @@ int pack_field(mnrf_field* f, const float* const* tensors, cudaStream_t st);
 // per-ray (or per-point) additive term of the dir layer: b_dir + W_dir[:,256:283] . embed(dir)
 // from_embedded == 0: src = rays (n,8), direction embedded in-kernel; else src = x (n,30), cols 3..29
 int launch_dirbias(const mnrf_field* f, const float* src, int n, int src_stride, int from_embedded, float* out,
-                   cudaStream_t st);
+                   cudaStream_t st, const int* n_dev = nullptr);
 
 struct FieldIO {
   // geometry: point p -> ray p / S, sample p % S;  xyz = o + d*z  (flat mode: S = 1, xyz read from x)
@@ -239,6 +245,9 @@ struct FieldIO {
   int n_points;
   int S;
   int sigma_only;
+  // optional device-side ray count (mnrf_render_recursive: a level is launched for its worst-case size and the kernels read
+  // how many rays are really alive): n_points := min(n_points, *n_rays_dev * S)
+  const int* n_rays_dev;
   // outputs (NULL = skip)
   float* raw;        // (n_points, 8)
   float* sigma_out;  // (n_points)
@@ -246,8 +255,9 @@ struct FieldIO {
   float* geo_out;    // (n_points, 256)
 };
 
+// `n_dev` (last argument of the launchers below, optional): device-side count; the kernel processes min(n, *n_dev) rows
 int launch_coarse_z(const float* rays, int n, const float* z_steps, int S, int use_disp, float perturb,
-                    const float* u, float* z_out, cudaStream_t st);
+                    const float* u, float* z_out, cudaStream_t st, const int* n_dev = nullptr);
 int launch_generate_rays(int H, int W, float focal, const float* c2w_host, float near, float far, float* rays,
                          cudaStream_t st);
 int launch_embed(const float* x, int n, int n_freqs, float* out, cudaStream_t st);
@@ -255,18 +265,25 @@ int launch_searchsorted(const float* cdf, int n, int m, const float* u, int n_u,
                         cudaStream_t st);
 int launch_sample_pdf(const float* z_coarse, const float* bins, const float* weights, int w_stride, int w_off, int n,
                       int S, int n_imp, const float* u, int u_stride, float* z_fine, float* samples, int64_t* inds,
-                      float* cdf, cudaStream_t st);
+                      float* cdf, cudaStream_t st, const int* n_dev = nullptr);
 int launch_composite(const float* rays, const float* z, const float* sigma, int sigma_stride, const float* raw,
                      const float* normal, const float* noise, float noise_std, int n, int S, int white_back,
-                     const mnrf_composite_out& out, cudaStream_t st);
+                     const mnrf_composite_out& out, cudaStream_t st, const int* n_dev = nullptr);
+// jitter (optional): normal += jitter_scale * jitter[i]  before normalising (R/eval.py:506-511 roughness cone)
 int launch_reflect(const float* rays, const float* x_surface, const float* normal, float* mask, int n, float near2,
-                   float* sec, float* refl, int* any_mirror, cudaStream_t st);
+                   float* sec, float* refl, int* any_mirror, cudaStream_t st, const int* n_dev = nullptr,
+                   const float* jitter = nullptr, float jitter_scale = 0.f, int threshold_mask = 1);
+// scratch (optional): (n + 1023) / 1024 ints of caller-owned scratch instead of a stream-ordered allocation
 int launch_compact(const float* in, const float* mask, int n, int row_floats, float* out, int* index, int* count,
-                   cudaStream_t st);
+                   cudaStream_t st, const int* n_dev = nullptr, int* scratch = nullptr);
 int launch_axpy_rows(float* dense, const float* compact, const int* index, int n, int c, float alpha, float beta,
-                     cudaStream_t st);
+                     cudaStream_t st, const int* n_dev = nullptr);
+// traced (optional, device): when *traced == 0 the level below was not rendered: rgb_out = base, reflect outputs = 0
 int launch_blend(const float* base, const float* mask, const float* child_rgb, const float* child_depth,
-                 const int* index, int n, float* rgb_out, float* rgb_reflect, float* depth_reflect, cudaStream_t st);
+                 const int* index, int n, float* rgb_out, float* rgb_reflect, float* depth_reflect, cudaStream_t st,
+                 const int* n_dev = nullptr, const int* traced = nullptr);
+// *out = (*flag != 0) ? min(n, n_dev ? *n_dev : n) : 0   -- size of an un-compacted child level (R/eval.py:159,311-320)
+int launch_select_count(const int* flag, int n, const int* n_dev, int* out, cudaStream_t st);
 
 int launch_field_fp32(const mnrf_field* f, const FieldIO& io, cudaStream_t st);
 int launch_field_hash(const mnrf_field* f, const FieldIO& io, cudaStream_t st);
@@ -322,7 +339,10 @@ int train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, const
                    const mnrf_train_cfg& cfg, const void* ws_fwd, void* ws_bwd, const mnrf_train_grads& g,
                    const float* ray_detach_mirror, float* const* grad_tensors, const float* depth, float* grad_rays,
                    cudaStream_t st);
+int render_level(const mnrf_field* coarse, const mnrf_field* fine, const float* rays, int n, const mnrf_level_cfg* cfg,
+                 const mnrf_level_rng* rng, const float* z_steps, const float* u_det, void* workspace, int64_t workspace_bytes,
+                 const mnrf_level_out* out, void* stream, const int* n_dev);
 void set_tc_trace(unsigned long long* buf, unsigned int cap);
-int launch_field_tc(const mnrf_field* f, const FieldIO& io, int precision /*1|3*/, cudaStream_t st);
+int launch_field_tc(const mnrf_field* f, const FieldIO& io, int precision /*1|2|3*/, cudaStream_t st);
 
 }  // namespace mnrf

@@ -18,7 +18,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 __global__ void __launch_bounds__(CW * 32)
 k_composite(const float* __restrict__ rays, const float* __restrict__ z, const float* __restrict__ sigma,
             int sigma_stride, const float* __restrict__ raw, const float* __restrict__ normal,
-            const float* __restrict__ noise, float noise_std, int n, int S, int white_back, mnrf_composite_out out) {
+            const float* __restrict__ noise, float noise_std, int n, int S, int white_back, mnrf_composite_out out,
+            const int* __restrict__ n_dev) {
+  if (n_dev != nullptr) n = min(n, __ldg(n_dev));
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * CW + (threadIdx.x >> 5);
   if (r >= n) return;
@@ -99,7 +101,7 @@ k_composite(const float* __restrict__ rays, const float* __restrict__ z, const f
 
 int launch_composite(const float* rays, const float* z, const float* sigma, int sigma_stride, const float* raw,
                      const float* normal, const float* noise, float noise_std, int n, int S, int white_back,
-                     const mnrf_composite_out& out, cudaStream_t st) {
+                     const mnrf_composite_out& out, cudaStream_t st, const int* n_dev) {
   if (n <= 0) return 0;
   MNRF_REQUIRE(S >= 1 && S <= 32 * MAX_BLK, "composite: 1 <= S <= %d", 32 * MAX_BLK);
   MNRF_REQUIRE(out.weights != nullptr && out.opacity != nullptr, "composite: weights/opacity outputs are required");
@@ -107,7 +109,7 @@ int launch_composite(const float* rays, const float* z, const float* sigma, int 
                                   out.surface_normal == nullptr && out.normal_dif == nullptr),
                "composite: colour/normal outputs need the raw field records");
   k_composite<<<(n + CW - 1) / CW, CW * 32, 0, st>>>(rays, z, sigma, sigma_stride, raw, normal, noise, noise_std, n, S,
-                                                   white_back, out);
+                                                   white_back, out, n_dev);
   MNRF_LAUNCH_OK();
   return 0;
 }

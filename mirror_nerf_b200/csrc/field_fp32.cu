@@ -47,6 +47,10 @@ constexpr int SM_TOTAL = SM_XYZ + TP * 4;
 __global__ void __launch_bounds__(NT, 1)
 k_field_fp32(const float* __restrict__ P, F32Layout L, FieldIO io, int has_normal, int has_mirror) {
   extern __shared__ float sm[];
+  if (io.n_rays_dev != nullptr) {  // device-side ray count (mnrf_render_recursive)
+    io.n_points = min(io.n_points, max(__ldg(io.n_rays_dev), 0) * io.S);
+    if ((int)blockIdx.x * TP >= io.n_points) return;
+  }
   float* pe = sm + SM_PE;
   float* H = sm + SM_H;
   float* t0 = sm + SM_T0;
@@ -278,9 +282,11 @@ k_field_fp32(const float* __restrict__ P, F32Layout L, FieldIO io, int has_norma
 // ---- dir-layer additive term ---------------------------------------------------------------------
 // out[r][n] = b_dir[n] + sum_j W_dir[n][256+j] * embed(dir_r)[j]   (mirror_nerf.py:201-203, rendering.py:275-277)
 __global__ void k_dirbias(const float* __restrict__ P, F32Layout L, const float* __restrict__ src, int n,
-                          int src_stride, int from_embedded, float* __restrict__ out) {
+                          int src_stride, int from_embedded, float* __restrict__ out, const int* __restrict__ n_dev) {
   __shared__ float e[8][IN_DIR + 1];
+  if (n_dev != nullptr) n = min(n, __ldg(n_dev));
   int r0 = blockIdx.x * 8;
+  if (r0 >= n) return;
   int tid = threadIdx.x;  // 128
   for (int i = tid; i < 8 * IN_DIR; i += 128) {
     int rr = i / IN_DIR, j = i % IN_DIR;
@@ -314,21 +320,18 @@ __global__ void k_dirbias(const float* __restrict__ P, F32Layout L, const float*
 }  // namespace
 
 int launch_dirbias(const mnrf_field* f, const float* src, int n, int src_stride, int from_embedded, float* out,
-                   cudaStream_t st) {
+                   cudaStream_t st, const int* n_dev) {
   if (n <= 0) return 0;
-  k_dirbias<<<(n + 7) / 8, 128, 0, st>>>(f->f32, f->L, src, n, src_stride, from_embedded, out);
+  k_dirbias<<<(n + 7) / 8, 128, 0, st>>>(f->f32, f->L, src, n, src_stride, from_embedded, out, n_dev);
   MNRF_LAUNCH_OK();
   return 0;
 }
 
 int launch_field_fp32(const mnrf_field* f, const FieldIO& io, cudaStream_t st) {
   if (io.n_points <= 0) return 0;
-  static bool attr_set = false;
   size_t smem = SM_TOTAL * sizeof(float);
-  if (!attr_set) {
+  if (first_use_on_device(TAG_FIELD_FP32))
     MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
   int blocks = (io.n_points + TP - 1) / TP;
   k_field_fp32<<<blocks, NT, smem, st>>>(f->f32, f->L, io, f->has_normal, f->has_mirror);
   MNRF_LAUNCH_OK();

@@ -94,6 +94,10 @@ template <bool NORMALS>
 __global__ void __launch_bounds__(HB) k_field_hash(const float* __restrict__ table, const float* __restrict__ wpack, HashGridMeta M,
                                                    FieldIO io, int has_normal, int has_mirror) {
   extern __shared__ __align__(16) float sw[];
+  if (io.n_rays_dev != nullptr) {  // device-side ray count (mnrf_render_recursive)
+    io.n_points = min(io.n_points, max(__ldg(io.n_rays_dev), 0) * io.S);
+    if ((long long)blockIdx.x * HB >= io.n_points) return;
+  }
   for (int i = threadIdx.x; i < HW_TOTAL / 4; i += HB)
     reinterpret_cast<float4*>(sw)[i] = reinterpret_cast<const float4*>(wpack)[i];
   __syncthreads();
@@ -411,11 +415,9 @@ int launch_field_hash(const mnrf_field* f, const FieldIO& io, cudaStream_t st) {
   if (io.n_points <= 0) return 0;
   MNRF_REQUIRE(io.normal_out == nullptr || !io.sigma_only, "hash-grid field: analytic normals need the full (non sigma-only) pass");
   MNRF_REQUIRE(io.geo_out == nullptr, "hash-grid field: geo_feat export is not built");
-  static bool attr = false;
-  if (!attr) {
+  if (first_use_on_device(TAG_FIELD_HASH)) {
     MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_hash<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(H_SMEM_FLOATS * sizeof(float))));
     MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_hash<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(H_SMEM_FLOATS * sizeof(float))));
-    attr = true;
   }
   const long long blocks = ((long long)io.n_points + HB - 1) / HB;
   if (io.normal_out != nullptr)

@@ -19,9 +19,15 @@
 //
 // Precision: operands are split x = hi + lo in fp16 (weights pre-scaled by 2^s per layer) and
 // each product is formed as hi*hi + lo*hi + hi*lo with fp32 accumulation ("3x" mode, fp32-grade);
-// PREC3 == false drops the lo terms (speed mode).
+// PREC == 1 drops the lo terms (speed mode).
+// PREC == 2 ("tc2"): the two cross terms need only a few bits of their own, so they run on the fp8 datapath at twice the fp16
+// rate: D = A_hi W_hi (fp16, K16) + e4m3(2^10 A_lo) e4m3(2^-10 W_hi) + e4m3(A_hi) e4m3(W_lo) (kind::f8f6f4, K32), all three
+// accumulated into the same fp32 TMEM accumulator (measured: the accumulator keeps full fp32 precision across kinds,
+// profiles/r02_v1_fp8_mma_microbench.txt) -- 2.0 fp16-pass equivalents per algorithmic MAC instead of 3, operand error ~2^-16.
 //
 // Shared memory (1 CTA/SM): A hi/lo 2x64 KB | PE hi/lo 2x16 KB | 4 x 16 KB weight stages | 2 KB partial sums.
+#include <mutex>
+
 #include "common.cuh"
 
 namespace mnrf {
@@ -63,14 +69,18 @@ struct TcParams {
   int has_normal, has_mirror;
   FieldIO io;
   int n_tiles;
+  int slot;                   // which copy of the epilogue table (c_epi) belongs to this launch's field
   unsigned long long* trace;  // optional device-side event trace of CTA 0 (bring-up builds)
   unsigned int trace_cap;
   int debug;
 };
 
-// Epilogue table (biases, head weights, scales: common.cuh ET_*): copied device-to-device into constant memory in front of
-// every launch (stream ordered), so the warp-uniform epilogue reads are constant-cache accesses instead of global loads.
-__constant__ float c_epi[ET_TOTAL];
+// Epilogue table (biases, head weights, scales: common.cuh ET_*) in constant memory, so that the warp-uniform epilogue reads are
+// constant-cache accesses instead of global loads.  EPI_SLOTS copies: a launch names the slot that holds ITS field's table, so
+// the coarse and the fine field (and a third one) stay resident and two fields rendered on different streams do not share a
+// table; the host side (epi_slot_acquire) orders a slot's rewrite after the last kernel that read it.
+constexpr int EPI_SLOTS = 3;
+__constant__ float c_epi_slots[EPI_SLOTS][ET_TOTAL];
 
 // device-side tracing (mnrf_debug_set_trace): lane 0 of a warp of CTA 0 logs (clock64, tag) with plain stores into its own
 // region of the buffer (no atomics, so the perturbation is one clock read + one store): region r = who, 8192 events each
@@ -182,6 +192,19 @@ __device__ __forceinline__ void epi_bar_sync(int id) { asm volatile("bar.sync %0
 // (address >> 4) | (LBO >> 4) << 16, so stepping through an operand is an integer add in 16-byte units.
 constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
 __device__ __forceinline__ uint32_t desc_lo(uint32_t addr, uint32_t lbo) { return ((addr >> 4) & 0x3FFFu) | ((lbo >> 4) << 16); }
+// fp8 (e4m3 x e4m3 -> f32, K = 32 per instruction): same descriptor and instruction-descriptor bits as the fp16 form (format 0 is
+// F16 for kind::f16 and E4M3 for kind::f8f6f4); K-major core matrices hold 16 K values per 16-byte row
+template <int N>
+__device__ __forceinline__ void tc_mma_f8(uint32_t d_tmem, uint32_t a_lo32, uint32_t b_lo32, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %4};\n\t"
+      "mov.b64 db, {%2, %4};\n\t"
+      "setp.ne.b32 p, %3, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo32), "r"(b_lo32), "r"(accumulate), "r"(DESC_HI), "r"(N == 256 ? IDESC_N256 : (N == 128 ? IDESC_N128 : IDESC_N64))
+      : "memory");
+}
 template <int N>
 __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint32_t a_lo32, uint32_t b_lo32, uint32_t accumulate) {
   asm volatile(
@@ -197,9 +220,9 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint32_t a_lo32, uint32_
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
 // ---- x = hi + lo in fp16, two values per 32-bit word (element 0 in the low half) -----------------------------------
-template <bool RELU, bool PREC3>
+template <bool RELU, int PREC>
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  if (PREC3) {
+  if (PREC == 3) {
     // hi rounded toward zero so that the residual of a non-negative value is non-negative: both ReLUs ride on the cvt
     if (RELU) asm("cvt.rz.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
     else      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
@@ -214,13 +237,42 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
 }
 
 // store 8 consecutive K values (one 16-byte core-matrix row) of an A-type operand, hi and lo parts
-template <bool RELU, bool PREC3>
+template <bool RELU, int PREC>
 __device__ __forceinline__ void store_a8(uint32_t hi_addr, uint32_t lo_addr, const float (&v)[8]) {
   uint32_t h[4], l[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) split2<RELU, PREC3>(v[2 * i], v[2 * i + 1], h[i], l[i]);
+  for (int i = 0; i < 4; ++i) split2<RELU, PREC>(v[2 * i], v[2 * i + 1], h[i], l[i]);
   st_shared_v4(hi_addr, h[0], h[1], h[2], h[3]);
-  if (PREC3) st_shared_v4(lo_addr, l[0], l[1], l[2], l[3]);
+  if (PREC == 3) st_shared_v4(lo_addr, l[0], l[1], l[2], l[3]);
+}
+
+// ---- tc2: 16 consecutive K values of an A operand -> fp16 hi (two core-matrix rows) + e4m3(x) + e4m3(2^10 (x - hi)) -----------
+// hi16_addr: the core-matrix row of the first 8 values (the next 8 are one K-group = 2048 B further); a8_addr: the 16-byte row
+// of the e4m3 copy of x; the residual copy lives A8_LO_OFF bytes behind it.
+__device__ __forceinline__ uint32_t cvt_e4m3x2(float a, float b) {  // {low byte = e4m3(a), high byte = e4m3(b)}
+  uint16_t r;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(b), "f"(a));
+  return (uint32_t)r;
+}
+template <bool RELU>
+__device__ __forceinline__ void store_a16_tc2(uint32_t hi16_addr, uint32_t a8_addr, uint32_t lo8_off, const float (&v)[16]) {
+  uint32_t h[8], x8[4], l8[4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float a = RELU ? fmaxf(v[2 * i], 0.f) : v[2 * i], b = RELU ? fmaxf(v[2 * i + 1], 0.f) : v[2 * i + 1];
+    // hi: round toward zero after the ReLU (residual >= 0), round to nearest for signed values
+    if (RELU) asm("cvt.rz.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(b), "f"(a));
+    else      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(b), "f"(a));
+    const float2 hf = __half22float2(*reinterpret_cast<__half2*>(&h[i]));
+    const uint32_t xa = cvt_e4m3x2(a, b);
+    const uint32_t la = cvt_e4m3x2((a - hf.x) * 1024.f, (b - hf.y) * 1024.f);
+    if (i & 1) { x8[i >> 1] |= xa << 16; l8[i >> 1] |= la << 16; }
+    else       { x8[i >> 1] = xa;        l8[i >> 1] = la; }
+  }
+  st_shared_v4(hi16_addr, h[0], h[1], h[2], h[3]);
+  st_shared_v4(hi16_addr + 2048u, h[4], h[5], h[6], h[7]);
+  st_shared_v4(a8_addr, x8[0], x8[1], x8[2], x8[3]);
+  st_shared_v4(a8_addr + lo8_off, l8[0], l8[1], l8[2], l8[3]);
 }
 
 // accurate sin/cos (arguments reach 2^9 * |x|): shared, not inlined 30 times
@@ -231,7 +283,7 @@ __device__ __noinline__ float2 sincos_pe(float a) {
 }
 
 // ---- positional encoding of one row, K range [32*HALF, 32*HALF+32) (mirror_nerf.py:33-38) ----------------
-template <int HALF, bool PREC3>
+template <int HALF, int PREC>
 __device__ __forceinline__ void pe_fill(const float (&x)[3], uint32_t pe_hi, uint32_t pe_lo, uint32_t rowoff) {
   constexpr int K0 = 32 * HALF;
   float vals[32];
@@ -253,23 +305,60 @@ __device__ __forceinline__ void pe_fill(const float (&x)[3], uint32_t pe_hi, uin
       }
     }
   }
+  if (PREC == 2) {
+    // pe_lo = base of the e4m3 copies: [x (8 KB) | 2^10 residual (8 KB)], 16 K values per core-matrix row
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = vals[16 * j + i];
+      store_a16_tc2<false>(pe_hi + (uint32_t)(4 * HALF + 2 * j) * 2048u + rowoff, pe_lo + (uint32_t)(2 * HALF + j) * 2048u + rowoff, 8192u, v);
+    }
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = vals[8 * j + i];
     const uint32_t off = (uint32_t)(4 * HALF + j) * 2048u + rowoff;
-    store_a8<false, PREC3>(pe_hi + off, pe_lo + off, v);
+    store_a8<false, PREC>(pe_hi + off, pe_lo + off, v);
   }
 }
 
 // ---- epilogue of NC accumulator columns of one row ------------------------------------------------------------------
 // MASK: 0 = none; 1 = record (bit i of `mbits` from `bit0` up := value > 0, the ReLU derivative needed by the analytic-normal
 // chain); 2 = apply (value := bit ? value : 0, no bias: a step of the chain g_{l-1} = (g_l W_l) * relu'(h_{l-1})).
-template <int NC, bool RELU, bool DOTS, bool WRITE_A, bool PREC3, int MASK>
+template <int NC, bool RELU, bool DOTS, bool WRITE_A, int PREC, int MASK>
 __device__ __forceinline__ void epi_cols(const uint32_t (&r)[NC], const float4 (&b)[NC / 4], float inv, uint32_t s_hi,
                                          uint32_t s_lo, const float4* __restrict__ hw, float (&d)[4], uint32_t& mbits,
                                          int bit0) {
+  if (PREC == 2) {
+    // s_lo = address of this thread's e4m3 row for the first 16 columns (see layer_epilogue); residual copy 32 KB behind
+#pragma unroll
+    for (int j = 0; j < NC / 16; ++j) {
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 bb = b[4 * j + i];
+        v[4 * i + 0] = fmaf(__uint_as_float(r[16 * j + 4 * i + 0]), inv, bb.x);
+        v[4 * i + 1] = fmaf(__uint_as_float(r[16 * j + 4 * i + 1]), inv, bb.y);
+        v[4 * i + 2] = fmaf(__uint_as_float(r[16 * j + 4 * i + 2]), inv, bb.z);
+        v[4 * i + 3] = fmaf(__uint_as_float(r[16 * j + 4 * i + 3]), inv, bb.w);
+      }
+      if (DOTS) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          v[i] = fmaxf(v[i], 0.f);
+          const float4 w = hw[16 * j + i];
+          d[0] = fmaf(v[i], w.x, d[0]); d[1] = fmaf(v[i], w.y, d[1]);
+          d[2] = fmaf(v[i], w.z, d[2]); d[3] = fmaf(v[i], w.w, d[3]);
+        }
+      }
+      if (WRITE_A) store_a16_tc2<RELU>(s_hi + (uint32_t)j * 4096u, s_lo + (uint32_t)j * 2048u, 32768u, v);
+    }
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < NC / 8; ++j) {
     float v[8];
@@ -300,7 +389,7 @@ __device__ __forceinline__ void epi_cols(const uint32_t (&r)[NC], const float4 (
         d[2] = fmaf(v[i], w.z, d[2]); d[3] = fmaf(v[i], w.w, d[3]);
       }
     }
-    if (WRITE_A) store_a8<RELU, PREC3>(s_hi + (uint32_t)j * 2048u, s_lo + (uint32_t)j * 2048u, v);
+    if (WRITE_A) store_a8<RELU, PREC>(s_hi + (uint32_t)j * 2048u, s_lo + (uint32_t)j * 2048u, v);
   }
 }
 
@@ -337,7 +426,7 @@ __device__ __forceinline__ int acc_bar(int s) {  // steps 9 and 10 share slot 2;
 __device__ __forceinline__ int step_at(int i) { return i < 8 ? i : (i == 8 ? 9 : (i == 9 ? 8 : i)); }
 
 // ================================================================================================
-template <bool PREC3, bool NORMALS>
+template <int PREC, bool NORMALS>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -347,7 +436,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
   auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SM_BAR + 8 * BAR_TMEM_SLOT);
   const int n_issue = P.io.sigma_only ? 8 : (NORMALS ? 20 : 11);
-  constexpr uint32_t NST = PREC3 ? 4u : 8u;  // weight stages (the 1x mode also uses the idle A_lo region)
+  // device-side ray count (mnrf_render_recursive): every role derives the same tile count from it
+  int n_points = P.io.n_points;
+  if (P.io.n_rays_dev != nullptr) {
+    const long long alive = (long long)__ldg(P.io.n_rays_dev) * P.io.S;
+    if (alive < n_points) n_points = (int)(alive < 0 ? 0 : alive);
+  }
+  const int n_tiles = (n_points + TILE_M - 1) / TILE_M;
+  const float* const c_epi = c_epi_slots[P.slot];
+  constexpr bool PREC3 = PREC == 3;                 // three fp16 passes
+  constexpr bool TWO_BLOBS = PREC != 1;              // weight chunk = two 16 KB halves (3x: hi|lo; tc2: hi16 | hi8,lo8)
+  constexpr uint32_t NST = TWO_BLOBS ? 4u : 8u;  // weight stages (the 1x mode also uses the idle A_lo region)  // weight stages (the 1x mode also uses the idle A_lo region)
   auto stage_addr = [&](uint32_t st) { return sbase + (st < 4u ? SM_WST + st * WSTAGE_BYTES : SM_A_LO + (st - 4u) * WSTAGE_BYTES); };
 
   if (threadIdx.x == 0) {
@@ -376,7 +475,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
     // chunk (2 x 8 KB, contiguous).  1x mode: N=256 -> hi blob of a K32 chunk; N=128 -> hi blobs of two K32 chunks.
     if (elect_one()) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int i = 0; i < n_issue; ++i) {
           const int s = step_at(i);
           if (s == 9 && !P.has_mirror) continue;
@@ -385,18 +484,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
           const bool wide = sn == 256;
           const int nch = tc_step_chunks(s);
           // N = 64 steps (4 KB blobs): 3x -> [hi|lo] of two K32 chunks per stage (contiguous); 1x -> hi of four chunks
-          const int nst = sn == 64 ? (PREC3 ? nch / 2 : nch / 4) : (PREC3 ? (wide ? 2 * nch : nch) : (wide ? nch : nch / 2));
+          const int nst = sn == 64 ? (TWO_BLOBS ? nch / 2 : nch / 4) : (TWO_BLOBS ? (wide ? 2 * nch : nch) : (wide ? nch : nch / 2));
           for (int si = 0; si < nst; ++si) {
             mbar_wait(bar(BAR_W_EMPTY + stage), phase ^ 1u);
             const uint32_t dst = stage_addr(stage);
             const uint32_t fb = bar(BAR_W_FULL + stage);
             mbar_expect_tx(fb, WSTAGE_BYTES);
-            if (sn == 64 && !PREC3) {
+            if (sn == 64 && !TWO_BLOBS) {
 #pragma unroll
               for (int piece = 0; piece < 4; ++piece) bulk_g2s(dst + piece * 4096u, src + (size_t)(4 * si + piece) * 8192, 4096u, fb);
-            } else if (PREC3 || wide) {
+            } else if (TWO_BLOBS || wide) {
               // 16 contiguous KB: blob si (3x wide), blobs 2si,2si+1 (3x narrow), blob 2si = hi of chunk si (1x wide)
-              const uint8_t* g = src + (size_t)(PREC3 ? si : 2 * si) * WSTAGE_BYTES;
+              const uint8_t* g = src + (size_t)(TWO_BLOBS ? si : 2 * si) * WSTAGE_BYTES;
 #pragma unroll
               for (int piece = 0; piece < 4; ++piece) bulk_g2s(dst + piece * 4096u, g + piece * 4096, 4096u, fb);
             } else {
@@ -417,8 +516,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
       TraceCtx trc{0};
       const uint32_t dl_a_hi = desc_lo(sbase + SM_A_HI, 2048), dl_a_lo = desc_lo(sbase + SM_A_LO, 2048);
       const uint32_t dl_pe_hi = desc_lo(sbase + SM_PE_HI, 2048), dl_pe_lo = desc_lo(sbase + SM_PE_LO, 2048);
+      // tc2: e4m3 copies of the A operand (x at +0, 2^10 residual behind it); a K32 chunk = two 2048-byte K-groups = 256 units
+      const uint32_t dl_a8 = dl_a_lo, dl_a8r = desc_lo(sbase + SM_A_LO + 32768u, 2048);
+      const uint32_t dl_pe8 = dl_pe_lo, dl_pe8r = desc_lo(sbase + SM_PE_LO + 8192u, 2048);
       auto next_stage = [&]() { if (++stage == NST) { stage = 0; phase ^= 1u; } };
-      for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int i = 0; i < n_issue; ++i) {
           const int s = step_at(i);
           if (s == 9 && !P.has_mirror) continue;
@@ -431,9 +533,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
           trace_ev(P, trc, 0, 1, 1, s, 0);
           for (int kc = 0; kc < nch; ++kc) {
             uint32_t ah, al;  // descriptor low words of this K32 chunk of the A operand (hi / lo parts)
+            uint32_t a8 = 0, a8r = 0;  // tc2: e4m3 copy of the chunk and of its residual
             if (kc < n_pe) {
               if (s == 0 && kc == 0) { mbar_wait(bar(BAR_PE), pe_phase); pe_phase ^= 1u; }
               ah = dl_pe_hi + (uint32_t)kc * 512u; al = dl_pe_lo + (uint32_t)kc * 512u;
+              a8 = dl_pe8 + (uint32_t)kc * 256u; a8r = dl_pe8r + (uint32_t)kc * 256u;
             } else {
               const int ka = kc - n_pe;
               // first touch of freshly written activation columns: chunk 0 is signalled in two 32-column halves
@@ -444,6 +548,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
                 trace_ev(P, trc, 0, 1, 2, s, c);
               }
               ah = dl_a_hi + (uint32_t)ka * 512u; al = dl_a_lo + (uint32_t)ka * 512u;
+              a8 = dl_a8 + (uint32_t)ka * 256u; a8r = dl_a8r + (uint32_t)ka * 256u;
             }
             if (wide) {
               // ---- N = 256: K16 step of the B operand = 8192 B = 512 units ----
@@ -462,6 +567,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
                 wb = desc_lo(stage_addr(stage), 4096);
                 tc_mma<256>(d_tmem, ah, wb, 1u);                              // A_hi * W_lo
                 tc_mma<256>(d_tmem, ah + 256u, wb + 512u, 1u);
+                tc_commit(bar(BAR_W_EMPTY + stage));
+                next_stage();
+              }
+              if (PREC == 2) {
+                // second stage of the chunk = [e4m3(2^-10 W_hi) 8 KB | e4m3(W_lo) 8 KB], 32 K values per instruction
+                mbar_wait(bar(BAR_W_FULL + stage), phase);
+                tc_fence_after();
+                wb = desc_lo(stage_addr(stage), 4096);
+                tc_mma_f8<256>(d_tmem, a8r, wb, 1u);                          // (2^10 A_lo) * (2^-10 W_hi)
+                tc_mma_f8<256>(d_tmem, a8, wb + 512u, 1u);                    // A_hi * W_lo
                 tc_commit(bar(BAR_W_EMPTY + stage));
                 next_stage();
               }
@@ -484,6 +599,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
                 tc_mma<64>(d_tmem, ah + 256u, wb + 128u, 1u);
                 if ((kc & 3) == 3) { tc_commit(bar(BAR_W_EMPTY + stage)); next_stage(); }
               }
+            } else if (PREC == 2) {
+              // ---- N = 128, tc2: stage = [W_hi fp16 8 KB | e4m3(2^-10 W_hi) 4 KB | e4m3(W_lo) 4 KB] of this K32 chunk ----
+              mbar_wait(bar(BAR_W_FULL + stage), phase);
+              tc_fence_after();
+              const uint32_t wb = desc_lo(stage_addr(stage), 2048);
+              tc_mma<128>(d_tmem, ah, wb, accumulate);
+              tc_mma<128>(d_tmem, ah + 256u, wb + 256u, 1u);
+              tc_mma_f8<128>(d_tmem, a8r, wb + 512u, 1u);
+              tc_mma_f8<128>(d_tmem, a8, wb + 768u, 1u);
+              tc_commit(bar(BAR_W_EMPTY + stage));
+              next_stage();
             } else if (PREC3) {
               // ---- N = 128, 3x: stage = [W_hi | W_lo] of this K32 chunk; K16 step = 4096 B = 256 units ----
               mbar_wait(bar(BAR_W_FULL + stage), phase);
@@ -520,7 +646,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
     const int row = q * 32 + lane;
     const uint32_t rowoff = (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u;
     const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
-    const float* F = P.f32;
     const float4* headw = reinterpret_cast<const float4*>(c_epi + ET_HEADW);
     float4* part = reinterpret_cast<float4*>(smem + SM_PART);
     uint32_t acc_phase = 0;  // one parity bit per accumulator barrier
@@ -543,7 +668,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
     auto pe_tile = [&](int tile) {
       if (q == 0) trace_ev(P, trc, lane, 4 + g, 12, 0, 0);
       const long long pr = (long long)tile * TILE_M + row;
-      const long long p = pr < P.io.n_points ? pr : (long long)P.io.n_points - 1;
+      const long long p = pr < n_points ? pr : (long long)n_points - 1;
       float x[3];
       if (P.io.rays != nullptr) {
         const float* rr = P.io.rays + (p / P.io.S) * 8;
@@ -554,8 +679,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) x[c] = __ldg(P.io.x + p * P.io.x_stride + c);
       }
-      if (g == 0) pe_fill<0, PREC3>(x, sbase + SM_PE_HI, sbase + SM_PE_LO, rowoff);
-      else        pe_fill<1, PREC3>(x, sbase + SM_PE_HI, sbase + SM_PE_LO, rowoff);
+      if (g == 0) pe_fill<0, PREC>(x, sbase + SM_PE_HI, sbase + SM_PE_LO, rowoff);
+      else        pe_fill<1, PREC>(x, sbase + SM_PE_HI, sbase + SM_PE_LO, rowoff);
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(BAR_PE));
@@ -564,13 +689,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
     // One 256-wide layer: this warp owns columns [64c + 32g, 64c + 32g + 32) of every chunk c, chunks in K order, the next
     // chunk's TMEM load in flight while the current one is converted.
     // mk: this thread's four 32-bit relu' words of the layer (chunk c -> mk[c]; chunk 0's two 16-column pieces share mk[0])
+    // address of this thread's row in the second operand buffer for the columns that start at byte offset `off` of the fp16
+    // buffer: 3x -> the fp16 lo part (same layout); tc2 -> the e4m3 copy (16 K values per 16-byte row: half the K-group count)
+    auto lo_addr = [&](uint32_t off) {
+      return PREC == 2 ? sbase + SM_A_LO + ((off - rowoff) >> 1) + rowoff : sbase + SM_A_LO + off;
+    };
     auto layer_epilogue = [&](auto tag, int s, const float* bias256, float (&d)[4], uint32_t (&mk)[4]) {
       constexpr bool RELU = decltype(tag)::relu, DOTS = decltype(tag)::dots, WRITE_A = decltype(tag)::write_a;
       constexpr int MASK = decltype(tag)::mask;
       if (MASK == 1) { mk[0] = 0u; mk[1] = 0u; mk[2] = 0u; mk[3] = 0u; }
       const float4* b4 = reinterpret_cast<const float4*>(bias256);
       // everything that does not depend on the accumulator is fetched before waiting for it
-      const float inv = c_epi[ET_INV_SCALE + s];
+      const float inv = c_epi[ET_INV_SCALE + s] * (PREC == 2 ? 0.03125f : 1.f);  // tc2 blobs carry 2^5 more scale (pack.cu)
       float4 b0a[4], b0b[4], b[8];
 #pragma unroll
       for (int i = 0; i < 4; ++i) { b0a[i] = b4[4 * g + i]; b0b[i] = b4[8 + 4 * g + i]; }
@@ -587,12 +717,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
       pin<16>(r0b);
       {
         const uint32_t off = (uint32_t)(g * 2) * 2048u + rowoff;
-        epi_cols<16, RELU, DOTS, WRITE_A, PREC3, MASK>(r0a, b0a, inv, sbase + SM_A_HI + off, sbase + SM_A_LO + off, headw + g * 16, d, mk[0], 0);
+        epi_cols<16, RELU, DOTS, WRITE_A, PREC, MASK>(r0a, b0a, inv, sbase + SM_A_HI + off, lo_addr(off), headw + g * 16, d, mk[0], 0);
         if (WRITE_A) a_ready(0);
       }
       {
         const uint32_t off = (uint32_t)(4 + g * 2) * 2048u + rowoff;
-        epi_cols<16, RELU, DOTS, WRITE_A, PREC3, MASK>(r0b, b0b, inv, sbase + SM_A_HI + off, sbase + SM_A_LO + off, headw + 32 + g * 16, d, mk[0], 16);
+        epi_cols<16, RELU, DOTS, WRITE_A, PREC, MASK>(r0b, b0b, inv, sbase + SM_A_HI + off, lo_addr(off), headw + 32 + g * 16, d, mk[0], 16);
         if (WRITE_A) a_ready(4);
       }
 #pragma unroll
@@ -605,17 +735,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
           else       tmem_ld32(tcol + (uint32_t)(c + 1) * 64u + (uint32_t)g * 32u, rb);
         }
         const uint32_t off = (uint32_t)(c * 8 + g * 4) * 2048u + rowoff;
-        if (c & 1) { pin32(rb); epi_cols<32, RELU, DOTS, WRITE_A, PREC3, MASK>(rb, b, inv, sbase + SM_A_HI + off, sbase + SM_A_LO + off, headw + c * 64 + g * 32, d, mk[c], 0); }
-        else       { pin32(ra); epi_cols<32, RELU, DOTS, WRITE_A, PREC3, MASK>(ra, b, inv, sbase + SM_A_HI + off, sbase + SM_A_LO + off, headw + c * 64 + g * 32, d, mk[c], 0); }
+        if (c & 1) { pin32(rb); epi_cols<32, RELU, DOTS, WRITE_A, PREC, MASK>(rb, b, inv, sbase + SM_A_HI + off, lo_addr(off), headw + c * 64 + g * 32, d, mk[c], 0); }
+        else       { pin32(ra); epi_cols<32, RELU, DOTS, WRITE_A, PREC, MASK>(ra, b, inv, sbase + SM_A_HI + off, lo_addr(off), headw + c * 64 + g * 32, d, mk[c], 0); }
         if (WRITE_A) a_ready(c);
       }
     };
 
-    if ((int)blockIdx.x < P.n_tiles) pe_tile(blockIdx.x);
-    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+    if ((int)blockIdx.x < n_tiles) pe_tile(blockIdx.x);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long p_raw = (long long)tile * TILE_M + row;
-      const bool valid = p_raw < P.io.n_points;
-      const long long p = valid ? p_raw : (long long)P.io.n_points - 1;
+      const bool valid = p_raw < n_points;
+      const long long p = valid ? p_raw : (long long)n_points - 1;
       const long long ray = (P.io.rays != nullptr) ? p / P.io.S : p;
       float o_sigma = 0.f, o_n[3] = {0.f, 0.f, 0.f}, o_mirror = 0.f, o_rgb[3] = {0.f, 0.f, 0.f};
       float d[4] = {0.f, 0.f, 0.f, 0.f};
@@ -636,7 +766,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
           else layer_epilogue(TagSigma{}, s, bias, d, masks[0]);
         }
         // the PE buffer is free once layer 5's MMAs are done: encode the next tile while the tensor pipe is busy
-        if (s == 5 && tile + (int)gridDim.x < P.n_tiles) pe_tile(tile + gridDim.x);
+        if (s == 5 && tile + (int)gridDim.x < n_tiles) pe_tile(tile + gridDim.x);
       }
       // combine the two column groups' partial dot products (sigma + folded normal head)
       {
@@ -659,7 +789,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
         // ---- mirror head (step 9): LeakyReLU(0.01) -> Linear(128,1) -> sigmoid (mirror_nerf.py:94-99) ----
         if (P.has_mirror) {
           wait_acc(9);
-          const float inv = c_epi[ET_INV_SCALE + 9];
+          const float inv = c_epi[ET_INV_SCALE + 9] * (PREC == 2 ? 0.03125f : 1.f);
           float dm = 0.f;
           uint32_t ra[32], rb[32];
           tmem_ld32(tlane + acc_col(9) + (uint32_t)g * 64u, ra);
@@ -697,7 +827,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
         // ---- dir layer (step 10): relu(W_f f + [b + W_d embed(dir)]) -> rgb (mirror_nerf.py:199-204) ----
         wait_acc(10);
         {
-          const float inv = c_epi[ET_INV_SCALE + 10];
+          const float inv = c_epi[ET_INV_SCALE + 10] * (PREC == 2 ? 0.03125f : 1.f);
           const float4* db = reinterpret_cast<const float4*>(P.io.dirbias + ray * WH + g * 64);
           const float4* wr = reinterpret_cast<const float4*>(c_epi + ET_W_RGB + g * 64);
           float d0 = 0.f, d1 = 0.f, d2 = 0.f;
@@ -758,7 +888,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] = ((masks[7][c] >> (bit0 + 8 * j + i)) & 1u) ? hw[col0 + 8 * j + i].x : 0.f;
               const uint32_t off = (uint32_t)(col0 / 8 + j) * 2048u + rowoff;
-              store_a8<false, PREC3>(sbase + SM_A_HI + off, sbase + SM_A_LO + off, v);
+              store_a8<false, PREC>(sbase + SM_A_HI + off, sbase + SM_A_LO + off, v);
             }
             a_ready(piece == 0 ? 0 : (piece == 1 ? 4 : c));
           }
@@ -865,21 +995,71 @@ static unsigned long long* g_trace_buf = nullptr;
 static unsigned int g_trace_cap = 0;
 void set_tc_trace(unsigned long long* buf, unsigned int cap) { g_trace_buf = buf; g_trace_cap = cap; }
 
+// ---- constant-memory slots of the epilogue table (per device) -------------------------------------------------------------
+// A slot is keyed by the field's pack stamp (unique per pack_field call, so a re-packed or re-created field never hits a stale
+// copy).  `filled` orders the table copy before readers on other streams, `used` orders a rewrite after the last reader.
+namespace {
+struct EpiSlot { unsigned long long stamp = 0; unsigned long long tick = 0; cudaEvent_t filled = nullptr, used = nullptr; };
+struct EpiDevice { EpiSlot s[EPI_SLOTS]; unsigned long long clock = 0; };
+std::mutex g_epi_mu;
+EpiDevice g_epi[64];
+
+int epi_slot_acquire(const mnrf_field* f, cudaStream_t st, int* slot_out) {
+  int dev = 0;
+  MNRF_CUDA_OK(cudaGetDevice(&dev));
+  MNRF_REQUIRE(dev >= 0 && dev < 64, "field_tc: device index %d out of range", dev);
+  std::lock_guard<std::mutex> lock(g_epi_mu);
+  EpiDevice& D = g_epi[dev];
+  int hit = -1, lru = 0;
+  for (int i = 0; i < EPI_SLOTS; ++i) {
+    if (D.s[i].stamp == f->pack_stamp && f->pack_stamp != 0) hit = i;
+    if (D.s[i].tick < D.s[lru].tick) lru = i;
+  }
+  const int k = hit >= 0 ? hit : lru;
+  EpiSlot& S = D.s[k];
+  if (S.filled == nullptr) {
+    MNRF_CUDA_OK(cudaEventCreateWithFlags(&S.filled, cudaEventDisableTiming));
+    MNRF_CUDA_OK(cudaEventCreateWithFlags(&S.used, cudaEventDisableTiming));
+    MNRF_CUDA_OK(cudaEventRecord(S.used, st));
+    MNRF_CUDA_OK(cudaEventRecord(S.filled, st));
+  }
+  if (hit < 0) {
+    MNRF_CUDA_OK(cudaStreamWaitEvent(st, S.used, 0));   // the last kernel that read this slot (any stream) is done first
+    MNRF_CUDA_OK(cudaMemcpyToSymbolAsync(c_epi_slots, f->f32 + f->L.epi_tab, sizeof(float) * ET_TOTAL,
+                                         sizeof(float) * ET_TOTAL * (size_t)k, cudaMemcpyDeviceToDevice, st));
+    MNRF_CUDA_OK(cudaEventRecord(S.filled, st));
+    S.stamp = f->pack_stamp;
+  } else {
+    MNRF_CUDA_OK(cudaStreamWaitEvent(st, S.filled, 0)); // the copy may have been issued on another stream
+  }
+  S.tick = ++D.clock;
+  *slot_out = k;
+  return 0;
+}
+
+int epi_slot_release(int slot, cudaStream_t st) {
+  int dev = 0;
+  MNRF_CUDA_OK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_epi_mu);
+  MNRF_CUDA_OK(cudaEventRecord(g_epi[dev].s[slot].used, st));
+  return 0;
+}
+}  // namespace
+
 int launch_field_tc(const mnrf_field* f, const FieldIO& io, int precision, cudaStream_t st) {
   if (io.n_points <= 0) return 0;
-  MNRF_REQUIRE(precision == 1 || precision == 3, "field_tc: precision must be 1 or 3");
+  MNRF_REQUIRE(precision >= 1 && precision <= 3, "field_tc: precision must be 1, 2 or 3");
+  if (precision == 2 && io.normal_out != nullptr) precision = 3;  // the analytic-normal chain has no fp8 variant
   MNRF_REQUIRE(io.normal_out == nullptr || !io.sigma_only, "field_tc: analytic normals need the full (non sigma-only) pass");
   MNRF_REQUIRE(io.geo_out == nullptr, "field_tc: geo_feat output needs MNRF_IMPL_FP32");
   MNRF_REQUIRE(io.sigma_only || io.dirbias != nullptr, "field_tc: dirbias missing");
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    MNRF_CUDA_OK(cudaGetDevice(&dev));
-    MNRF_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
-    MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
-    MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_tc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
-    MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
+  int num_sms = 0;
+  if (first_use_on_device(TAG_FIELD_TC, &num_sms)) {
+    MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_tc<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
+    MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_tc<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
+    MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_tc<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
+    MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_tc<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
+    MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_tc<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
   }
   TcParams P;
   const F32Layout& L = f->L;
@@ -897,19 +1077,25 @@ int launch_field_tc(const mnrf_field* f, const FieldIO& io, int precision, cudaS
   const int grid = P.n_tiles < num_sms ? P.n_tiles : num_sms;
   // algorithmic MACs of this launch (unpadded reference layer sizes)
   const double macs = (double)io.n_points * (io.sigma_only ? (double)mnrf_macs_sigma_only() : (double)mnrf_macs_full());
-  MNRF_CUDA_OK(cudaMemcpyToSymbolAsync(c_epi, f->f32 + L.epi_tab, sizeof(float) * ET_TOTAL, 0, cudaMemcpyDeviceToDevice, st));
+  MNRF_REQUIRE(num_sms > 0, "field_tc: no CUDA device");
+  int slot = 0;
+  if (epi_slot_acquire(f, st, &slot)) return 1;
+  P.slot = slot;
   prof_begin(st);
   const bool normals = io.normal_out != nullptr;
-  if (precision == 3) {
-    if (normals) k_field_tc<true, true><<<grid, NUM_THREADS, SM_TOTAL, st>>>(P);
-    else         k_field_tc<true, false><<<grid, NUM_THREADS, SM_TOTAL, st>>>(P);
+  if (precision == 2) {
+    P.tc = f->tc8;
+    k_field_tc<2, false><<<grid, NUM_THREADS, SM_TOTAL, st>>>(P);
+  } else if (precision == 3) {
+    if (normals) k_field_tc<3, true><<<grid, NUM_THREADS, SM_TOTAL, st>>>(P);
+    else         k_field_tc<3, false><<<grid, NUM_THREADS, SM_TOTAL, st>>>(P);
   } else {
-    if (normals) k_field_tc<false, true><<<grid, NUM_THREADS, SM_TOTAL, st>>>(P);
-    else         k_field_tc<false, false><<<grid, NUM_THREADS, SM_TOTAL, st>>>(P);
+    if (normals) k_field_tc<1, true><<<grid, NUM_THREADS, SM_TOTAL, st>>>(P);
+    else         k_field_tc<1, false><<<grid, NUM_THREADS, SM_TOTAL, st>>>(P);
   }
   prof_end(st, 2.0 * macs);
   MNRF_LAUNCH_OK();
-  return 0;
+  return epi_slot_release(slot, st);
 }
 
 }  // namespace mnrf

@@ -5,6 +5,10 @@
 //          cp.async.bulk drops a ready-to-use B operand stage into shared memory.
 // Everything runs on the device, asynchronously on the caller's stream (no host sync: the optimizer
 // can step and the next render can repack without draining the GPU).
+#include <atomic>
+
+#include <cuda_fp8.h>
+
 #include "common.cuh"
 
 namespace mnrf {
@@ -151,6 +155,30 @@ __global__ void k_pack_tc(TcSrc src, const float* __restrict__ inv_scale, uint8_
   }
 }
 
+// tc2 blobs (field_tc.cu PREC == 2): same chunk geometry as k_pack_tc, 2^5 more scale (max |W| * scale in [2^14, 2^15): the
+// fp16 lo part of typical weights lands in e4m3's normal range), second half of a chunk = [e4m3(2^-10 W_hi) | e4m3(W_lo)] with
+// 16 K values per 16-byte core-matrix row.
+__global__ void k_pack_tc8(TcSrc src, const float* __restrict__ inv_scale, uint8_t* __restrict__ tc8) {
+  int s = blockIdx.y;
+  if (s >= TC_FWD_STEPS) return;  // the analytic-normal chain has no fp8 variant
+  int N = tc_step_n(s), K = tc_step_k(s);
+  uint8_t* base = tc8 + tc_step_offset(s);
+  const int blob = tc_blob_bytes(s);
+  float scale = 32.f / inv_scale[s];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N * K; i += gridDim.x * blockDim.x) {
+    int n = i / K, k = i % K;
+    const float v = tc_src_value(src, s, n, k) * scale;
+    const __half hi = __float2half_rn(v);
+    const float lo = v - __half2float(hi);
+    int kc = k >> 5, kk = k & 31;
+    uint8_t* chunk = base + (size_t)kc * 2 * blob;
+    *reinterpret_cast<__half*>(chunk + (kk >> 3) * (N * 16) + (n >> 3) * 128 + (n & 7) * 16 + (kk & 7) * 2) = hi;
+    const int off8 = (kk >> 4) * (N * 16) + (n >> 3) * 128 + (n & 7) * 16 + (kk & 15);
+    chunk[blob + off8] = (uint8_t)__nv_cvt_float_to_fp8(__half2float(hi) * 0.0009765625f, __NV_SATFINITE, __NV_E4M3);
+    chunk[blob + blob / 2 + off8] = (uint8_t)__nv_cvt_float_to_fp8(lo, __NV_SATFINITE, __NV_E4M3);
+  }
+}
+
 // ---- tf32 blobs of the training GEMMs (common.cuh T32_*) ------------------------------------------------------------
 struct T32Src {
   TcSrc base;
@@ -218,6 +246,8 @@ static int transpose_to(const float* src, float* dst, int N, int K, cudaStream_t
 }
 
 int pack_field(mnrf_field* f, const float* const* t, cudaStream_t st) {
+  static std::atomic<unsigned long long> g_pack_stamp{0};
+  f->pack_stamp = ++g_pack_stamp;  // invalidates the constant-memory copies of the epilogue table (field_tc.cu)
   const F32Layout& L = f->L;
   float* d = f->f32;
   for (int l = 0; l < 8; ++l) {
@@ -268,6 +298,8 @@ int pack_field(mnrf_field* f, const float* const* t, cudaStream_t st) {
   k_scales<<<1, 32, 0, st>>>(absmax, d + L.inv_scale);
   MNRF_LAUNCH_OK();
   k_pack_tc<<<dim3(64, TC_NUM_STEPS), 256, 0, st>>>(src, d + L.inv_scale, f->tc);
+  MNRF_LAUNCH_OK();
+  k_pack_tc8<<<dim3(64, TC_FWD_STEPS), 256, 0, st>>>(src, d + L.inv_scale, f->tc8);
   MNRF_LAUNCH_OK();
   T32Src s32;
   s32.base = src;

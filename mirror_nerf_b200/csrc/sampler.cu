@@ -18,7 +18,9 @@ __device__ __forceinline__ float coarse_z_at(float near, float far, float t, int
 }
 
 __global__ void k_coarse_z(const float* __restrict__ rays, int n, const float* __restrict__ z_steps, int S,
-                           int use_disp, float perturb, const float* __restrict__ u, float* __restrict__ z_out) {
+                           int use_disp, float perturb, const float* __restrict__ u, float* __restrict__ z_out,
+                           const int* __restrict__ n_dev) {
+  if (n_dev != nullptr) n = min(n, __ldg(n_dev));
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)n * S) return;
   int r = (int)(i / S), s = (int)(i % S);
@@ -118,7 +120,8 @@ __global__ void __launch_bounds__(SP_WARPS * 32)
 k_sample_pdf(const float* __restrict__ z_coarse, const float* __restrict__ bins_in, const float* __restrict__ weights,
              int w_stride, int w_off, int n, int S, int n_imp,
              const float* __restrict__ u, int u_stride, float* __restrict__ z_fine, float* __restrict__ samples_out,
-             int64_t* __restrict__ inds_out, float* __restrict__ cdf_out) {
+             int64_t* __restrict__ inds_out, float* __restrict__ cdf_out, const int* __restrict__ n_dev) {
+  if (n_dev != nullptr) n = min(n, __ldg(n_dev));
   __shared__ float s_bins[SP_WARPS][SP_MAXS];
   __shared__ float s_cdf[SP_WARPS][SP_MAXS];
   __shared__ float s_w[SP_WARPS][SP_MAXS];
@@ -204,12 +207,12 @@ k_sample_pdf(const float* __restrict__ z_coarse, const float* __restrict__ bins_
 }  // namespace
 
 int launch_coarse_z(const float* rays, int n, const float* z_steps, int S, int use_disp, float perturb,
-                    const float* u, float* z_out, cudaStream_t st) {
+                    const float* u, float* z_out, cudaStream_t st, const int* n_dev) {
   if (n <= 0) return 0;
   MNRF_REQUIRE(S >= 1, "coarse_z: S must be >= 1");
   MNRF_REQUIRE(!(perturb > 0.f) || u != nullptr, "coarse_z: perturb > 0 needs perturb_u");
   long long total = (long long)n * S;
-  k_coarse_z<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(rays, n, z_steps, S, use_disp, perturb, u, z_out);
+  k_coarse_z<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(rays, n, z_steps, S, use_disp, perturb, u, z_out, n_dev);
   MNRF_LAUNCH_OK();
   return 0;
 }
@@ -243,12 +246,12 @@ int launch_searchsorted(const float* cdf, int n, int m, const float* u, int n_u,
 
 int launch_sample_pdf(const float* z_coarse, const float* bins, const float* weights, int w_stride, int w_off, int n,
                       int S, int n_imp, const float* u, int u_stride, float* z_fine, float* samples, int64_t* inds,
-                      float* cdf, cudaStream_t st) {
+                      float* cdf, cudaStream_t st, const int* n_dev) {
   if (n <= 0) return 0;
   MNRF_REQUIRE(S >= 3 && S <= SP_MAXS, "sample_pdf: need 3 <= N_samples <= %d (got %d)", SP_MAXS, S);
   MNRF_REQUIRE(n_imp >= 1 && S + n_imp <= SP_MAXT, "sample_pdf: need N_samples + N_importance <= %d", SP_MAXT);
   k_sample_pdf<<<(n + SP_WARPS - 1) / SP_WARPS, SP_WARPS * 32, 0, st>>>(z_coarse, bins, weights, w_stride, w_off, n, S, n_imp, u,
-                                                                      u_stride, z_fine, samples, inds, cdf);
+                                                                      u_stride, z_fine, samples, inds, cdf, n_dev);
   MNRF_LAUNCH_OK();
   return 0;
 }

@@ -343,11 +343,9 @@ int hash_train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, 
   const int second_order = cfg.compute_normal && (g.normal != nullptr || g.surface_normal_grad != nullptr || g.normal_dif != nullptr);
   SmallPtrs sp;
   for (int i = 0; i < 12; ++i) sp.p[i] = gt[i];
-  static bool attr = false;
-  if (!attr) {
+  if (first_use_on_device(TAG_TRAIN_HASH)) {
     MNRF_CUDA_OK(cudaFuncSetAttribute(k_hash_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(HB_SMEM_FLOATS * sizeof(float))));
     MNRF_CUDA_OK(cudaFuncSetAttribute(k_hash_bwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(HB2_SMEM_FLOATS * sizeof(float))));
-    attr = true;
   }
   if (hash_bwd_layout() == 2) {
     const int n_tiles = (int)((P + ht2::NP2 - 1) / ht2::NP2);

@@ -586,14 +586,7 @@ int make_a_map(CUtensorMap* m, const float* A, int rows, int cols, int ld) {
   return 0;
 }
 
-int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 0;
-  }
-  return n;
-}
+
 
 }  // namespace
 
@@ -604,15 +597,13 @@ int gemm_nn_tc(const mnrf_field* f, int step, const float* A0, int lda0, int K0,
   const int N = t32_step_n(step), K = t32_step_k(step);
   MNRF_REQUIRE(K0 % 16 == 0 && K0 <= K && (K0 == K || A1 != nullptr), "gemm_nn_tc: bad K split %d of %d", K0, K);
   MNRF_REQUIRE(lda0 % 4 == 0 && (A1 == nullptr || lda1 % 4 == 0) && ldc % 4 == 0, "gemm_nn_tc: leading dimensions must be multiples of 4");
-  static bool attr = false;
-  if (!attr) {
+  int sms = 0;
+  if (first_use_on_device(TAG_TRAIN_TC_NN, &sms)) {
     MNRF_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nn<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SM_TOTAL));
     MNRF_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nn<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SM_TOTAL));
     MNRF_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nn<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SM_TOTAL));
     MNRF_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_nn<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SM_TOTAL));
-    attr = true;
   }
-  const int sms = num_sms();
   MNRF_REQUIRE(sms > 0, "gemm_nn_tc: no CUDA device");
   NNParams P;
   P.A0 = A0; P.lda0 = lda0; P.K0 = K0; P.A1 = A1; P.lda1 = lda1;
@@ -642,12 +633,9 @@ int gemm_tn_tc(const float* A, int lda, int NA, const float* B, int ldb, int NB,
   if (Wg == nullptr || Pn <= 0) return 0;
   MNRF_REQUIRE((NA == 128 || NA == 256) && (NB == 64 || NB == 128 || NB == 256), "gemm_tn_tc: bad shape %d x %d", NA, NB);
   MNRF_REQUIRE(lda == NA && ldb == NB, "gemm_tn_tc: operands must be contiguous (lda == NA, ldb == NB): their chunks are bulk-copied");
-  static bool attr = false;
-  if (!attr) {
+  int sms = 0;
+  if (first_use_on_device(TAG_TRAIN_TC_TN, &sms))
     MNRF_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc_tn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TN_SM_TOTAL));
-    attr = true;
-  }
-  const int sms = num_sms();
   MNRF_REQUIRE(sms > 0, "gemm_tn_tc: no CUDA device");
   TNParams P;
   P.A = A; P.lda = lda; P.NA = NA; P.B = B; P.ldb = ldb; P.NB = NB;

@@ -50,10 +50,13 @@ class PackedField:
         _lib.check(self._lib.mnrf_field_create(C.byref(self.handle), arr, _stream_ptr()), "mnrf_field_create")
         self.has_normal = bool(self._lib.mnrf_field_has_normal(self.handle))
         self.has_mirror = bool(self._lib.mnrf_field_has_mirror(self.handle))
+        self.generation = 0  # bumped by every re-pack: autograd nodes refuse to run their backward against newer weights
 
     def update(self, tensors):
         arr = (C.c_void_p * _lib.NUM_PARAM_TENSORS)(*[None if t is None else t.data_ptr() for t in tensors])
-        _lib.check(self._lib.mnrf_field_update(self.handle, arr, _stream_ptr()), "mnrf_field_update")
+        with torch.cuda.device(next(t for t in tensors if t is not None).device):
+            _lib.check(self._lib.mnrf_field_update(self.handle, arr, _stream_ptr()), "mnrf_field_update")
+        self.generation += 1
 
     def __del__(self):
         try:
@@ -64,16 +67,20 @@ class PackedField:
             pass
 
 
-def _collect(source):
-    """The 32 parameter tensors (or None for an absent head) of an nn.Module or a {key: tensor} mapping."""
+def _collect(source, with_key=False):
+    """The 32 parameter tensors (or None for an absent head) of an nn.Module or a {key: tensor} mapping.  with_key: also the
+    cache key, built from the ORIGINAL tensors' (data_ptr, _version) -- a `.contiguous()` temporary of a non-contiguous
+    parameter can reuse an address with version 0 and would fake a cache hit."""
     named = dict(source.named_parameters()) if isinstance(source, nn.Module) else dict(source)
     out = []
+    key = []
     for k in PARAM_KEYS:
         t = named.get(k)
         if t is None:
             if not (k.startswith("normal_net") or k.startswith("is_mirror_net")):
                 raise KeyError(f"MirrorNeRF parameter '{k}' missing (only D=8, W=256, skips=[4] is supported)")
             out.append(None)
+            key.append(None)
             continue
         if not t.is_cuda:
             raise RuntimeError(f"parameter '{k}' is on {t.device}: the renderer has no CPU path, move the model to CUDA")
@@ -84,13 +91,13 @@ def _collect(source):
             raise RuntimeError(f"parameter '{k}' has shape {tuple(t.shape)}, expected {exp} "
                                "(only the reference architecture D=8, W=256, skips=[4], 10/4 frequencies is supported)")
         out.append(t.detach() if t.is_contiguous() else t.detach().contiguous())
-    return out
+        key.append((t.data_ptr(), t._version, t.is_contiguous()))
+    return (out, tuple(key)) if with_key else out
 
 
 def packed_field(source) -> PackedField:
     """Packed device weights for ``source`` (module or state-dict-like mapping), cached on modules."""
-    tensors = _collect(source)
-    key = tuple((None if t is None else (t.data_ptr(), t._version)) for t in tensors)
+    tensors, key = _collect(source, with_key=True)
     if isinstance(source, nn.Module):
         cached = source.__dict__.get("_mnrf_packed")
         if cached is not None:

@@ -76,11 +76,13 @@ class PackedHashField:
         self.has_mirror = bool(self._lib.mnrf_field_has_mirror(self.handle))
         self.kind = "hash"
         self.bound, self.table_floats = float(bound), int(tensors[0].numel())
+        self.generation = 0  # bumped by every re-pack (autograd.py refuses a backward against newer weights)
 
     def update(self, tensors):
         """Re-pack in place after an optimizer step (same table size and head set)."""
         arr = (C.c_void_p * 12)(*[None if t is None else t.data_ptr() for t in tensors])
         _lib.check(self._lib.mnrf_field_update(self.handle, arr, _stream_ptr()), "mnrf_field_update")
+        self.generation += 1
 
     def __del__(self):
         try:

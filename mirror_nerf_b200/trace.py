@@ -13,7 +13,7 @@ from . import _lib
 from .mirror_nerf import _ptr, _stream_ptr
 from .rendering import render_rays
 
-__all__ = ["render_rays_recursive", "reflect_rays", "compact_rows", "blend_reflection", "axpy_rows"]
+__all__ = ["render_rays_recursive", "render_rays_recursive_device", "reflect_rays", "compact_rows", "blend_reflection", "axpy_rows"]
 
 RAY_FORWARD_OFFSET = 0.1  # near of a secondary ray (eval.py:529, train.py:232)
 
@@ -78,7 +78,7 @@ def axpy_rows(dense, compact, index, alpha, beta):
 def render_rays_recursive(models, embeddings, rays, N_samples=64, use_disp=False, perturb=0, noise_std=0,
                           N_importance=0, chunk=1024 * 32, white_back=False, max_recursive_level=1,
                           only_trace_rays_in_mirrors=None, test_time=True, _level=0, render_fn=None,
-                          normal_noise_std=0.0, trace_ray_times=0, normal_noises=None, **kwargs):
+                          normal_noise_std=0.0, trace_ray_times=0, normal_noises=None, compact_outputs=False, **kwargs):
     """Eval-semantics recursion (R/eval.py:132-725): level 0 re-traces ALL rays of a batch that contains a mirror
     pixel, deeper levels only the mirror rays; `only_trace_rays_in_mirrors=True` compacts at every level (train.py
     semantics).  Returns the level-0 render_rays dict with rgb_{typ} blended plus rgb_{typ}_direct/_reflect,
@@ -91,6 +91,12 @@ def render_rays_recursive(models, embeddings, rays, N_samples=64, use_disp=False
     (N_mirror,3) tensor to an (N_rays,3) one at level 0 -- a latent shape bug; the evident intent, mirror rays only, is
     what is implemented).  `normal_noises`: optional list of trace_ray_times+1 explicit (n,3) noise tensors (tests)."""
     kwargs.setdefault("compute_normal", False)
+    if compact_outputs:
+        if render_fn is not None or _level != 0:
+            raise ValueError("compact_outputs=True is the device-side recursion of libmnrf.so: it renders the real field")
+        return render_rays_recursive_device(models, embeddings, rays, N_samples, use_disp, perturb, noise_std, N_importance,
+                                            white_back, max_recursive_level, only_trace_rays_in_mirrors, test_time,
+                                            normal_noise_std, trace_ray_times, normal_noises, **kwargs)
     if render_fn is None and torch.is_grad_enabled() and any(
             p.requires_grad for m in models.values() if hasattr(m, "parameters") for p in m.parameters()):
         # the reflect / compact / blend kernels of this driver are not differentiable: refuse instead of silently cutting the graph
@@ -108,6 +114,9 @@ def render_rays_recursive(models, embeddings, rays, N_samples=64, use_disp=False
         return res
     rays = rays.detach().contiguous()
     normal = res.get(f"surface_normal_{typ}", res.get(f"surface_normal_grad_{typ}"))
+    if normal is None:
+        raise RuntimeError("render_rays_recursive: the field has no normal_net, so the reflection needs the analytic normal: "
+                           "pass compute_normal=True (R/eval.py:146-148,351-360)")
     mask = res[f"mirror_mask_{typ}"]
     rough = normal_noise_std > 0
 
@@ -162,4 +171,94 @@ def render_rays_recursive(models, embeddings, rays, N_samples=64, use_disp=False
     res[f"rgb_{typ}"] = rgb
     res[f"rgb_{typ}_reflect"] = rgb_reflect
     res[f"depth_{typ}_reflect"] = depth_reflect
+    return res
+
+
+def render_rays_recursive_device(models, embeddings, rays, N_samples=64, use_disp=False, perturb=0, noise_std=0, N_importance=0,
+                                 white_back=False, max_recursive_level=1, only_trace_rays_in_mirrors=None, test_time=True,
+                                 normal_noise_std=0.0, trace_ray_times=0, normal_noises=None, noise_seed=0,
+                                 workspace_budget_bytes=None, with_level_rays=False, **kwargs):
+    """The whole eval-semantics recursion (R/eval.py::batched_inference :114-740, incl. --app_control_mirror_roughness) as ONE
+    call of ``mnrf_render_recursive``: no host synchronisation between level 0 and the blend, mirror rays counted / compacted /
+    re-enqueued on the device, the T+1 jittered reflections of a level rendered as one child batch.
+
+    Returns the compact per-ray dict of the select type ``t`` (fine, or coarse without a second pass):
+    ``rgb_t`` (blended), ``rgb_t_direct``, ``rgb_t_reflect``, ``depth_t``, ``depth_t_reflect``, ``opacity_t``, ``mirror_mask_t``
+    (hard-clipped, as eval.py:305-306 leaves it), ``surface_normal_t`` / ``surface_normal_grad_t``, ``x_surface_t``,
+    ``reflect_direction`` -- the per-sample tensors (weights, z_vals, pred_normal) are not materialised on this path.
+    ``normal_noises``: optional list of trace_ray_times+1 (n,3) standard-normal*std tensors for the LEVEL-0 reflections."""
+    import ctypes as C
+
+    from .rendering import DEFAULT_IMPL, _check_rays, _linspace
+    from .mirror_nerf import packed_field
+    from .mirror_nerf_tcnn import is_hash_field, packed_hash_field
+    if perturb != 0 or noise_std != 0:
+        raise NotImplementedError("render_rays_recursive_device renders with eval semantics (perturb = noise_std = 0, eval.py:141-142)")
+    if only_trace_rays_in_mirrors is False:
+        raise NotImplementedError("only_trace_rays_in_mirrors=False at every level (train.py's mask *= mask_prev) is not built; "
+                                  "None = eval.py semantics, True = compact at every level")
+    lib = _lib.load()
+    rays = _check_rays(rays)
+    dev = rays.device
+    n = rays.shape[0]
+    hashed = is_hash_field(models["coarse"])
+    pack = packed_hash_field if hashed else packed_field
+    only_one_field = bool(kwargs.get("only_one_field", False))
+    has_fine = "fine" in models
+    rerun = (N_importance > 0 and only_one_field
+             and kwargs.get("current_epoch", 0) > kwargs.get("only_one_field_fine_epoch", 2))
+    second = N_importance > 0 and (rerun or (has_fine and not only_one_field))
+    coarse = pack(models["coarse"])
+    fine = pack(models["fine"]) if (has_fine and not only_one_field) else None
+    sig_only = bool(test_time) and has_fine
+    fine_for_lib = fine if fine is not None else (coarse if sig_only else None)
+    last = (coarse if rerun else fine) if second else coarse
+    typ = "coarse" if (rerun or not second) else "fine"
+    Sc, Ni = int(N_samples), int(N_importance) if second else 0
+    impl = _lib.IMPL_BY_NAME[kwargs.get("field_impl", DEFAULT_IMPL)]
+    compute_normal = bool(kwargs.get("compute_normal", False)) and not last.has_normal
+    lc = _lib.LevelCfg(n_samples=Sc, n_importance=Ni, use_disp=int(bool(use_disp)), perturb=0.0, noise_std=0.0,
+                       white_back=int(bool(white_back)), test_time=int(sig_only), compute_normal=int(compute_normal),
+                       rerun_coarse_on_fine=int(rerun), impl=impl)
+    T = int(trace_ray_times) if normal_noise_std > 0 else 0
+    cfg = _lib.TraceCfg(level=lc, max_recursive_level=int(max_recursive_level),
+                        only_trace_rays_in_mirrors=1 if only_trace_rays_in_mirrors else -1, trace_ray_times=T,
+                        normal_noise_std=float(normal_noise_std), noise_seed=int(noise_seed))
+    new = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+    t = dict(rgb=new(n, 3), rgb_direct=new(n, 3), rgb_reflect=new(n, 3), depth=new(n), depth_reflect=new(n), opacity=new(n),
+             surface_normal=new(n, 3), x_surface=new(n, 3), reflect_direction=new(n, 3))
+    if last.has_mirror:
+        t["mirror_mask"] = new(n)
+    level_rays = torch.zeros(int(max_recursive_level) + 1, device=dev, dtype=torch.int32) if with_level_rays else None
+    noise0 = None
+    if normal_noises is not None and T >= 0 and normal_noise_std > 0:
+        if len(normal_noises) != T + 1:
+            raise ValueError(f"normal_noises must hold trace_ray_times+1 = {T + 1} tensors")
+        # the C side multiplies standard-normal draws by the std; explicit tensors are already scaled -> divide it out exactly
+        # when std is a power of two, otherwise accept the 1-ulp difference
+        noise0 = (torch.stack([z.to(device=dev, dtype=torch.float32) for z in normal_noises], 0) / float(normal_noise_std)).contiguous()
+        if tuple(noise0.shape) != (T + 1, n, 3):
+            raise ValueError(f"normal_noises tensors must be (n,3); got {tuple(noise0.shape)}")
+    with torch.cuda.device(dev):
+        budget = int(workspace_budget_bytes) if workspace_budget_bytes else 0
+        if budget == 0 and T > 0:
+            free, _total = torch.cuda.mem_get_info(dev)
+            budget = int(free * 0.6)
+        need = int(lib.mnrf_recursive_workspace_bytes(coarse.handle, None if fine_for_lib is None else fine_for_lib.handle, n,
+                                                      C.byref(cfg), budget))
+        if need < 0:
+            _lib.check(1, "mnrf_recursive_workspace_bytes")
+        ws = torch.empty(max(need, 256), device=dev, dtype=torch.uint8)
+        out = _lib.TraceOut(**{k: _ptr(v) for k, v in t.items()}, level_rays=_ptr(level_rays))
+        _lib.check(lib.mnrf_render_recursive(coarse.handle, None if fine_for_lib is None else fine_for_lib.handle, _ptr(rays), n,
+                                             C.byref(cfg), _ptr(_linspace(Sc, dev)), _ptr(_linspace(Ni, dev)) if Ni > 0 else None,
+                                             _ptr(noise0), _ptr(ws), need, C.byref(out), _stream_ptr()), "mnrf_render_recursive")
+    res = {f"rgb_{typ}": t["rgb"], f"rgb_{typ}_direct": t["rgb_direct"], f"rgb_{typ}_reflect": t["rgb_reflect"],
+           f"depth_{typ}": t["depth"], f"depth_{typ}_reflect": t["depth_reflect"], f"opacity_{typ}": t["opacity"],
+           f"x_surface_{typ}": t["x_surface"], "reflect_direction": t["reflect_direction"]}
+    res[f"surface_normal_{typ}" if last.has_normal else f"surface_normal_grad_{typ}"] = t["surface_normal"]
+    if last.has_mirror:
+        res[f"mirror_mask_{typ}"] = t["mirror_mask"]
+    if level_rays is not None:
+        res["level_rays"] = level_rays
     return res

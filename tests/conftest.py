@@ -13,6 +13,22 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run on the GPU box with -m gpu)")
 
 
+def pytest_sessionfinish(session, exitstatus):
+    """Measured error distributions of this run -> gpurun_out/parity_stats.json (GPU runs only)."""
+    try:
+        import json
+        import torch
+        import util
+        if not util.RECORDED or not torch.cuda.is_available():
+            return
+        out = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_stats.json"), "w") as f:
+            json.dump(util.RECORDED, f, indent=0)
+    except Exception:
+        pass
+
+
 REFERENCE = os.environ.get("MNRF_REFERENCE", "/root/reference")
 
 

@@ -37,7 +37,7 @@ def params():
 
 
 def assert_close_dist(got, want, name, median=1e-4, frac=0.03, p99=None):
-    s = err_stats(got, want)
+    s = err_stats(got, want, name=name)
     msg = fmt_stats(name, s)
     assert s["median"] <= median, msg
     assert s["frac"] <= frac, msg
@@ -575,7 +575,7 @@ def test_room_scene_parity_and_psnr(oracle):
         want = oracle.trace_eval(fn, rays, 1)
         got = render_rays_recursive(models, emb, rays.cuda(), 64, False, 0, 0, 128, 32768, False, max_recursive_level=1)
     for k in ("rgb_fine", "depth_fine", "opacity_fine"):
-        s = err_stats(got[k].cpu(), want[k])
+        s = err_stats(got[k].cpu(), want[k], name=f"room tc3 {k}")
         assert s["median"] <= 1e-5 and s["frac"] <= 0.01, fmt_stats(k, s)
     assert float((got["mirror_mask_fine"].cpu() != want["mirror_mask_fine"]).float().mean()) <= 0.002  # thresholded masks
     psnr = lambda x: -10 * math.log10(float(((x - gt) ** 2).mean()))

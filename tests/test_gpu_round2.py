@@ -1,0 +1,275 @@
+"""GPU tests of the round-2 work (run on the B200 box with `-m gpu`), all through Python -> ctypes -> C ABI:
+
+* the fp8-corrected tensor-core mode `tc2` (csrc/field_tc.cu PREC == 2) against the reference-generated goldens and, on the
+  fitted room scene, against the oracle at the same bounds as the 3-pass mode;
+* `mnrf_render_recursive` (csrc/recursive.cu): the device-side Whitted recursion against the oracle's restatement of
+  R/eval.py::batched_inference, against the reference-generated fixture tests/golden/recursion_eval.npz, bit-identical to the
+  per-level Python driver, with zero host synchronisations, and the batched roughness cone."""
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from util import T, err_stats, fmt_stats, make_models, room_state_dicts
+
+pytestmark = pytest.mark.gpu
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+
+
+@pytest.fixture(scope="module")
+def mm():
+    return make_models()
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle import mirror_nerf_oracle as O
+    return O
+
+
+@pytest.fixture(scope="module")
+def room():
+    """(models on cuda, embeddings, state dicts) of the fitted room field."""
+    from mirror_nerf_b200.mirror_nerf import Embedding, MirrorNeRF
+    sds = room_state_dicts()
+    models = {}
+    for k, sd in sds.items():
+        m = MirrorNeRF(predict_normal=True, predict_mirror_mask=True)
+        m.load_state_dict(sd)
+        models[k] = m.cuda().eval()
+    return models, {"xyz": Embedding(10), "dir": Embedding(4)}, sds
+
+
+def room_rays(n, pose=1, res=200):
+    from mirror_nerf_b200.room_scene import room_pose
+    from mirror_nerf_b200.synthetic import camera_rays
+    allrays = camera_rays(res, res, c2w=room_pose(pose), near=0.05, far=12.0)
+    return allrays[torch.linspace(0, allrays.shape[0] - 1, n).long()].contiguous()
+
+
+def close(got, want, name, median, frac, p99=None):
+    s = err_stats(got, want, name=name)
+    msg = fmt_stats(name, s)
+    assert s["median"] <= median and s["frac"] <= frac, msg
+    if p99 is not None:
+        assert s["p99"] <= p99, msg
+    return s
+
+
+ARGS = (64, False, 0, 0, 128, 32768, False)
+
+
+# ------------------------------------------------------------------------------------------------ tc2 (fp8-corrected mode)
+def test_field_tc2_kernel_golden(golden, mm):
+    """Per-point outputs of the fp8-corrected mode on the ADVERSARIAL golden field (sigma head x40): operand error ~2^-16, i.e.
+    ~40x the 3-pass mode's and ~16x below the single-pass mode's (tools/emulate_precision.py predicts sigma median 3e-5)."""
+    g = golden("field")
+    models, _ = mm
+    m = models["fine"]
+    m.return_geo_feat = False
+    m.field_impl = "tc2"
+    x = torch.cat([T(g["xyz"]), T(g["pe_dir"])], 1).cuda()
+    try:
+        with torch.no_grad():
+            o = m(x, compute_normal=False, sigma_only=False)
+    finally:
+        m.field_impl = "tc3"
+        m.return_geo_feat = True
+    for k, gk in (("sigma", "full_sigma"), ("pred_normal", "full_pred_normal"), ("rgb", "full_rgb"), ("is_mirror", "full_is_mirror")):
+        close(o[k].cpu(), T(g[gk]), f"tc2 {k}", median=1e-4, frac=0.0, p99=1e-3)
+
+
+def test_render_eval_golden_tc2(golden, mm):
+    from mirror_nerf_b200.rendering import render_rays
+    g = golden("render_eval")
+    models, emb = mm
+    with torch.no_grad():
+        r = render_rays(models, emb, T(g["rays"], "cuda"), *ARGS, test_time=True, compute_normal=False, field_impl="tc2")
+    assert set(r) == set(g) - {"rays"}
+    assert torch.equal(r["z_vals_coarse"].cpu(), T(g["z_vals_coarse"]))
+    for k in sorted(r):
+        close(r[k].cpu(), T(g[k]), f"tc2 render {k}", median=1e-4, frac=0.03)
+
+
+def test_room_scene_parity_and_psnr_tc2(oracle, room):
+    """The north-star bar on the scene-like field for the fp8-corrected mode, at the SAME bounds as the 3-pass mode
+    (test_gpu_parity.py::test_room_scene_parity_and_psnr): median <= 1e-5, < 1 % of rays beyond 1e-3, |dPSNR| <= 0.05 dB."""
+    from mirror_nerf_b200.room_scene import trace_room
+    from mirror_nerf_b200.trace import render_rays_recursive
+    models, emb, sds = room
+    rays = room_rays(1536)
+    gt, _, _ = trace_room(rays)
+    fn = lambda r: oracle.render_rays(sds, r, *ARGS, test_time=True, compute_normal=False)
+    with torch.no_grad():
+        want = oracle.trace_eval(fn, rays, 1)
+        got = render_rays_recursive(models, emb, rays.cuda(), *ARGS, max_recursive_level=1, field_impl="tc2")
+    for k in ("rgb_fine", "depth_fine", "opacity_fine"):
+        close(got[k].cpu(), want[k], f"room tc2 {k}", median=1e-5, frac=0.01)
+    assert float((got["mirror_mask_fine"].cpu() != want["mirror_mask_fine"]).float().mean()) <= 0.002
+    psnr = lambda x: -10 * math.log10(float(((x - gt) ** 2).mean()))
+    p_ours, p_ref = psnr(got["rgb_fine"].cpu()), psnr(want["rgb_fine"])
+    print(f"room scene tc2: PSNR ours {p_ours:.4f} dB, reference {p_ref:.4f} dB")
+    assert abs(p_ours - p_ref) <= 0.05
+
+
+def test_tc2_full_size_agrees_with_tc3(mm):
+    """Full-size property: on 20,000 rays (several tiles per SM, ragged tail) the two modes agree ray by ray."""
+    from mirror_nerf_b200.rendering import render_rays
+    from mirror_nerf_b200.synthetic import random_rays
+    models, emb = mm
+    rays = random_rays(20000, seed=31).cuda()
+    with torch.no_grad():
+        a = render_rays(models, emb, rays, *ARGS, test_time=True, compute_normal=False, field_impl="tc3")
+        b = render_rays(models, emb, rays, *ARGS, test_time=True, compute_normal=False, field_impl="tc2")
+    assert torch.equal(a["z_vals_coarse"], b["z_vals_coarse"])
+    for k in ("rgb_fine", "depth_fine", "opacity_fine", "mirror_mask_fine"):
+        close(b[k].cpu(), a[k].cpu(), f"tc2 vs tc3 {k} (adversarial field)", median=1e-4, frac=0.03)
+
+
+# ------------------------------------------------------------------------------------------------ device-side recursion
+@pytest.mark.parametrize("levels", [1, 2])
+def test_device_recursion_equals_python_driver_bitwise(room, levels):
+    """mnrf_render_recursive runs the same kernels on the same rows as the per-level Python driver (trace.py), so every output
+    must be bit-identical -- including the compaction order at level >= 1."""
+    from mirror_nerf_b200.trace import render_rays_recursive
+    models, emb, _ = room
+    rays = room_rays(3000, pose=2).cuda()
+    with torch.no_grad():
+        a = render_rays_recursive(models, emb, rays, *ARGS, max_recursive_level=levels)
+        b = render_rays_recursive(models, emb, rays, *ARGS, max_recursive_level=levels, compact_outputs=True)
+    for k in b:
+        if k in a:
+            assert torch.equal(a[k], b[k]), (k, float((a[k] - b[k]).abs().max()))
+    assert {"rgb_fine", "rgb_fine_direct", "rgb_fine_reflect", "depth_fine", "depth_fine_reflect", "mirror_mask_fine",
+            "surface_normal_fine", "x_surface_fine", "opacity_fine", "reflect_direction"} <= set(b)
+
+
+@pytest.mark.parametrize("levels", [1, 2])
+def test_device_recursion_vs_oracle(oracle, room, levels):
+    from mirror_nerf_b200.trace import render_rays_recursive
+    models, emb, sds = room
+    rays = room_rays(1024, pose=0)
+    fn = lambda r: oracle.render_rays(sds, r, *ARGS, test_time=True, compute_normal=False)
+    with torch.no_grad():
+        want = oracle.trace_eval(fn, rays, levels)
+        got = render_rays_recursive(models, emb, rays.cuda(), *ARGS, max_recursive_level=levels, compact_outputs=True,
+                                    with_level_rays=True)
+    assert float((got["mirror_mask_fine"].cpu() != want["mirror_mask_fine"]).float().mean()) <= 0.002
+    for k in ("rgb_fine", "rgb_fine_direct", "rgb_fine_reflect", "depth_fine", "depth_fine_reflect", "opacity_fine",
+              "surface_normal_fine", "x_surface_fine", "reflect_direction"):
+        close(got[k].cpu(), want[k], f"device recursion L{levels} {k}", median=1e-5, frac=0.01)
+    lr = got["level_rays"].cpu().tolist()
+    assert lr[0] == rays.shape[0] and lr[1] == rays.shape[0]   # level 0 re-traces ALL rays when the batch has a mirror pixel
+    if levels == 2:
+        assert 0 <= lr[2] <= rays.shape[0]
+
+
+@pytest.mark.parametrize("name", ["l1", "l2"])
+def test_device_recursion_vs_reference_fixture(golden, room, name):
+    """Against R/eval.py::batched_inference itself (tests/golden/recursion_eval.npz, written by the unmodified reference)."""
+    import make_golden_recursion as M
+    from mirror_nerf_b200.trace import render_rays_recursive
+    models, emb, _ = room
+    g = golden("recursion_eval")
+    c = {k[len(name) + 1:]: v for k, v in g.items() if k.startswith(name + "/")}
+    levels = M.EVAL_CASES[name][2]
+    with torch.no_grad():
+        got = render_rays_recursive(models, emb, T(c["rays"], "cuda"), *ARGS, max_recursive_level=levels, compact_outputs=True)
+    assert torch.equal(got["mirror_mask_fine"].cpu(), T(c["out/mirror_mask_fine"]))
+    for k in ("rgb_fine", "rgb_fine_reflect", "depth_fine", "depth_fine_reflect", "opacity_fine", "surface_normal_fine",
+              "x_surface_fine", "reflect_direction"):
+        close(got[k].cpu(), T(c["out/" + k]), f"device recursion vs reference {name} {k}", median=1e-5, frac=0.03)
+
+
+def test_device_recursion_has_no_host_sync(room):
+    """Zero host synchronisations between level 0 and the blend: torch's sync-debug mode turns any into an error."""
+    from mirror_nerf_b200.trace import render_rays_recursive
+    models, emb, _ = room
+    rays = room_rays(2048, pose=3).cuda()
+    with torch.no_grad():
+        render_rays_recursive(models, emb, rays, *ARGS, max_recursive_level=2, compact_outputs=True)   # warm-up: packs, tables
+        torch.cuda.synchronize()
+        torch.cuda.set_sync_debug_mode("error")
+        try:
+            out = render_rays_recursive(models, emb, rays, *ARGS, max_recursive_level=2, compact_outputs=True)
+        finally:
+            torch.cuda.set_sync_debug_mode("default")
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(out["rgb_fine"]).all())
+
+
+def test_device_recursion_no_mirror_and_empty(mm, room):
+    from mirror_nerf_b200.trace import render_rays_recursive
+    models, emb, _ = room
+    # rays looking away from the mirror wall: nothing is traced, colour == direct colour, reflect outputs zero
+    rays = room_rays(512, pose=1)
+    rays[:, 3] = -rays[:, 3].abs()
+    with torch.no_grad():
+        got = render_rays_recursive(models, emb, rays.cuda(), *ARGS, max_recursive_level=2, compact_outputs=True, with_level_rays=True)
+        e = render_rays_recursive(models, emb, torch.zeros(0, 8, device="cuda"), *ARGS, max_recursive_level=1, compact_outputs=True)
+    if float(got["mirror_mask_fine"].sum()) == 0:
+        assert torch.equal(got["rgb_fine"], got["rgb_fine_direct"])
+        assert float(got["rgb_fine_reflect"].abs().sum()) == 0 and float(got["depth_fine_reflect"].abs().sum()) == 0
+        assert got["level_rays"].cpu().tolist() == [512, 0, 0]
+    assert e["rgb_fine"].shape == (0, 3)
+
+
+def test_device_roughness_cone_level0_noise_vs_oracle(oracle, room):
+    """--app_control_mirror_roughness (R/eval.py:506-511,623-674): explicit level-0 noise, 3 extra jittered reflections rendered as
+    one child batch and averaged; std = 2^-5 so that the scaling is exact."""
+    from mirror_nerf_b200.trace import render_rays_recursive
+    models, emb, sds = room
+    rays = room_rays(768, pose=1)
+    std, T_extra = 2.0 ** -5, 3
+    gen = torch.Generator().manual_seed(5)
+    noises = [torch.randn(rays.shape[0], 3, generator=gen) * std for _ in range(T_extra + 1)]
+    fn = lambda r: oracle.render_rays(sds, r, *ARGS, test_time=True, compute_normal=False)
+    with torch.no_grad():
+        want = oracle.trace_eval(fn, rays, 1, normal_noises=[z.clone() for z in noises], trace_ray_times=T_extra)
+        got = render_rays_recursive(models, emb, rays.cuda(), *ARGS, max_recursive_level=1, compact_outputs=True,
+                                    normal_noise_std=std, trace_ray_times=T_extra, normal_noises=noises)
+    assert float((got["mirror_mask_fine"].cpu() != want["mirror_mask_fine"]).float().mean()) <= 0.002
+    for k in ("rgb_fine", "rgb_fine_reflect", "depth_fine_reflect", "reflect_direction"):
+        close(got[k].cpu(), want[k], f"device roughness {k}", median=1e-5, frac=0.01)
+
+
+@pytest.mark.parametrize("budget", [None, 600 << 20])
+def test_device_roughness_cone_zero_noise_is_identity(room, budget):
+    """With a vanishing std every jittered reflection equals the first one, and (a+a+a+a)/4 == a exactly: the batched cone (two
+    levels, slabs when the workspace budget is small) must reproduce the plain 2-bounce render bit for bit."""
+    from mirror_nerf_b200.trace import render_rays_recursive
+    models, emb, _ = room
+    rays = room_rays(4000, pose=2).cuda()
+    with torch.no_grad():
+        a = render_rays_recursive(models, emb, rays, *ARGS, max_recursive_level=2, compact_outputs=True)
+        b = render_rays_recursive(models, emb, rays, *ARGS, max_recursive_level=2, compact_outputs=True, normal_noise_std=1e-30,
+                                  trace_ray_times=3, workspace_budget_bytes=budget, with_level_rays=True)
+    for k in ("rgb_fine", "rgb_fine_reflect", "depth_fine_reflect", "mirror_mask_fine"):
+        assert torch.equal(a[k], b[k]), (k, float((a[k] - b[k]).abs().max()))
+    lr = b["level_rays"].cpu().tolist()
+    c0 = int(a["mirror_mask_fine"].sum())
+    assert lr[1] == rays.shape[0] + 3 * c0     # block 0 = all rays (eval level 0), 3 compacted blocks of the mirror rays
+
+
+def test_device_recursion_hash_field():
+    """The device counts reach the hash-grid kernels too: device recursion == per-level driver on the nerf_tcnn model family."""
+    from mirror_nerf_b200.mirror_nerf import Embedding
+    from mirror_nerf_b200.mirror_nerf_tcnn import MirrorNeRFTcnn
+    from mirror_nerf_b200.synthetic import random_rays
+    from mirror_nerf_b200.trace import render_rays_recursive
+    from oracle import hashgrid_oracle as HG
+    models = {}
+    for k, seed in (("coarse", 31), ("fine", 32)):
+        m = MirrorNeRFTcnn(bound=1, predict_normal=True, predict_mirror_mask=True)
+        m.load_state_dict(HG.make_state_dict(seed, sigma_scale=6.0))
+        models[k] = m.cuda().eval()
+    emb = {"xyz": Embedding(0), "dir": Embedding(0)}
+    rays = random_rays(1500, seed=4, near=0.05, far=2.0).cuda()
+    with torch.no_grad():
+        a = render_rays_recursive(models, emb, rays, *ARGS, max_recursive_level=2)
+        b = render_rays_recursive(models, emb, rays, *ARGS, max_recursive_level=2, compact_outputs=True)
+    for k in ("rgb_fine", "depth_fine", "mirror_mask_fine", "rgb_fine_reflect"):
+        assert torch.equal(a[k], b[k]), k

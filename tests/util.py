@@ -21,7 +21,21 @@ def make_models(device="cuda", predict_normal=True, predict_mirror_mask=True):
     return models, emb
 
 
-def err_stats(got, want, floor=None):
+# every err_stats() call of a GPU test run is logged here and written to gpurun_out/parity_stats.json by conftest.py, so that the
+# thresholds in the tests can be kept at "measured x 2" and bench.py / DESIGN.md can quote the measured distributions
+RECORDED = []
+
+
+def _caller_tag():
+    import inspect
+    import os
+    for fr in inspect.stack()[2:8]:
+        if fr.function.startswith("test_"):
+            return f"{os.path.basename(fr.filename)}::{fr.function}:{fr.lineno}"
+    return ""
+
+
+def err_stats(got, want, floor=None, name=None):
     """Relative error |got-want| / max(|want|, floor) as (median, p99, max, frac>1e-3).  `floor` defaults to the
     RMS of `want` so that near-zero entries are judged on the tensor's own scale."""
     got = got.detach().double().cpu().flatten()
@@ -31,9 +45,12 @@ def err_stats(got, want, floor=None):
     e = (got - want).abs() / want.abs().clamp_min(floor)
     if e.numel() == 0:
         return dict(median=0.0, p99=0.0, max=0.0, frac=0.0)
+    e = torch.nan_to_num(e, nan=float("inf"))
     q = torch.quantile(e, torch.tensor([0.5, 0.99], dtype=torch.double)) if e.numel() < 1_000_000 else \
         torch.tensor([e.median(), e.kthvalue(int(0.99 * e.numel()))[0]])
-    return dict(median=float(q[0]), p99=float(q[1]), max=float(e.max()), frac=float((e > 1e-3).double().mean()))
+    out = dict(median=float(q[0]), p99=float(q[1]), max=float(e.max()), frac=float((e > 1e-3).double().mean()))
+    RECORDED.append(dict(where=_caller_tag(), name=name, n=int(e.numel()), **out))
+    return out
 
 
 def fmt_stats(name, s):
