@@ -403,7 +403,8 @@ def run_ours(args):
     def step(rays):
         # the device-side recursion (mnrf_render_recursive): one C call per image, no host sync between level 0 and the blend
         return render_rays_recursive(models, emb, rays, N_SAMPLES, False, 0, 0, N_IMPORTANCE, 32768, False,
-                                     max_recursive_level=1, compact_outputs=not args.python_recursion, **kw)
+                                     max_recursive_level=1, compact_outputs=not args.python_recursion, **kw,
+                                     **({} if args.python_recursion else {"early_termination_eps": args.early_termination_eps}))
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
@@ -616,6 +617,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--field-impl", default=os.environ.get("MNRF_FIELD_IMPL", "tc3"), choices=["tc3", "tc2", "tc1"])
+    ap.add_argument("--early-termination-eps", type=float, default=1e-5,
+                    help="transmittance below which the fused fine pass stops a ray (0 = composite every sample)")
     ap.add_argument("--python-recursion", action="store_true",
                     help="drive the bounce from Python (per-level launches + host syncs) instead of mnrf_render_recursive")
     ap.add_argument("--ref-rays", type=int, default=2048, help="rays per step of the CPU reference sample")

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MNRF_ABI_VERSION 1
+#define MNRF_ABI_VERSION 2
 
 /* ---- field (MirrorNeRF MLP) ------------------------------------------------------------------ */
 
@@ -165,6 +165,15 @@ typedef struct mnrf_level_cfg {
   int compute_normal;/* analytic normals normalize(-d sigma/d xyz) for every pass that is not sigma-only         */
   int rerun_coarse_on_fine; /* only_one_field after only_one_field_fine_epoch (rendering.py:328-348)    */
   int impl;          /* MNRF_IMPL_*                                                                     */
+  /* ---- ABI 2 (zero = the behaviour of ABI 1) ---- */
+  float early_termination_eps; /* > 0: a ray stops once its transmittance prod(1 - alpha + 1e-10) falls below this; honoured by
+                                  the fused compositor and only when no per-sample output (weights, pred_normal) is requested:
+                                  every skipped sample has weight < eps (rendering.py:194-205)                                */
+  int no_fused_composite;      /* 1: field kernel -> raw point records -> separate compositor (the ABI-1 launch sequence)      */
+  const float* dir_source;     /* optional (n,8) rows whose columns 3..5 replace rays_d in the direction embedding only
+                                  (rendering.py:276 `view_dir`); MLP field                                                     */
+  unsigned long long* stats;   /* optional device counters of the fused fine pass: [0] += tiles executed, [1] += 32-sample
+                                  chunks skipped by early termination                                                          */
 } mnrf_level_cfg;
 
 typedef struct mnrf_level_rng { /* explicit draws (device); NULL -> deterministic (perturb=0 / noise 0) */
@@ -178,7 +187,8 @@ typedef struct mnrf_level_out {
   float* z_coarse;             /* (n,Sc) required */
   mnrf_composite_out coarse;   /* weights+opacity required */
   float* normal_coarse;        /* (n,Sc,3) analytic normals or NULL */
-  float* z_fine;               /* (n,Sc+Ni) required when a second pass runs */
+  float* z_fine;               /* (n,Sc+Ni) required when a second pass runs; fine.weights may be NULL when that pass composites
+                                  inside the field kernel (MLP field, tensor-core impl, no analytic normals, no sigma noise)  */
   mnrf_composite_out fine;
   float* normal_fine;          /* (n,Sc+Ni,3) or NULL */
 } mnrf_level_out;

@@ -27,7 +27,8 @@ class CompositeOut(C.Structure):
 class LevelCfg(C.Structure):
     _fields_ = [("n_samples", c_int), ("n_importance", c_int), ("use_disp", c_int), ("perturb", C.c_float),
                 ("noise_std", C.c_float), ("white_back", c_int), ("test_time", c_int), ("compute_normal", c_int),
-                ("rerun_coarse_on_fine", c_int), ("impl", c_int)]
+                ("rerun_coarse_on_fine", c_int), ("impl", c_int), ("early_termination_eps", C.c_float),
+                ("no_fused_composite", c_int), ("dir_source", C.c_void_p), ("stats", C.c_void_p)]
 
 
 class LevelRng(C.Structure):
@@ -152,7 +153,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the ABI is incomplete
         fn.restype = res
         fn.argtypes = args
-    if lib.mnrf_abi_version() != 1:
+    if lib.mnrf_abi_version() != 2:
         raise MnrfError("libmnrf.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -65,6 +65,11 @@ void prof_end(cudaStream_t st, double flops) {
   g_prof_pending = nullptr;
 }
 
+bool can_fuse_composite(const mnrf_field* f, const mnrf_level_cfg* cfg, const float* noise, int S) {
+  return f->kind == 0 && cfg->impl != MNRF_IMPL_FP32 && !cfg->compute_normal && !cfg->no_fused_composite &&
+         (noise == nullptr || cfg->noise_std == 0.f) && S <= 512;
+}
+
 namespace {
 
 inline cudaStream_t S_(void* s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -92,6 +97,34 @@ int run_field(const mnrf_field* f, int impl, const FieldIO& io, cudaStream_t st)
   if (f->kind == 1) return launch_field_hash(f, io, st);
   if (impl == MNRF_IMPL_FP32) return launch_field_fp32(f, io, st);
   return launch_field_tc(f, io, impl, st);  // MNRF_IMPL_TC1/2/3 == number of fp16-pass equivalents
+}
+
+// A full (non sigma-only) pass of the MLP field can composite inside the tensor-core kernel (field_tc.cu FUSE): no raw point
+// records, no k_composite launch.  Not for analytic normals (their chain has its own kernel variant), sigma noise, or more
+// than 512 samples per ray.
+bool can_fuse(const mnrf_field* f, const mnrf_level_cfg* cfg, const float* noise, int S) {
+  return can_fuse_composite(f, cfg, noise, S);
+}
+
+// field + compositor of one full pass: fused when possible, else field kernel -> raw records -> k_composite
+int run_full_pass(const mnrf_field* f, const mnrf_level_cfg* cfg, FieldIO io, const float* noise, float* raw_buf, int n, int S,
+                  const mnrf_composite_out& out, int* counter, unsigned long long* stats, cudaStream_t st, const int* n_dev) {
+  if (can_fuse(f, cfg, noise, S)) {
+    FusedComposite fc;
+    fc.comp = out;
+    fc.white_back = cfg->white_back;
+    // early termination only when no per-sample output is wanted (the skipped samples would have weights < eps)
+    fc.term_eps = (out.weights == nullptr && out.pred_normal == nullptr) ? cfg->early_termination_eps : 0.f;
+    fc.work_counter = counter;
+    fc.stats = stats;
+    io.raw = nullptr;
+    return launch_field_tc(f, io, cfg->impl, st, &fc);
+  }
+  MNRF_REQUIRE(out.weights != nullptr, "render_level: the unfused compositor needs the per-sample weights buffer");
+  io.raw = raw_buf;
+  if (run_field(f, cfg->impl, io, st)) return 1;
+  return launch_composite(io.rays, io.z, raw_buf, 8, raw_buf, io.normal_out, noise, cfg->noise_std, n, S, cfg->white_back, out,
+                          st, n_dev);
 }
 
 }  // namespace
@@ -365,7 +398,7 @@ int64_t mnrf_level_workspace_bytes(int n, const mnrf_level_cfg* cfg) {
   if (cfg == nullptr || n < 0) return -1;
   const size_t Sc = cfg->n_samples, Sf = cfg->n_samples + cfg->n_importance;
   return (int64_t)(align256(sizeof(float) * (size_t)n * WH) + align256(sizeof(float) * (size_t)n * Sc * 8) +
-                   (cfg->n_importance > 0 ? align256(sizeof(float) * (size_t)n * Sf * 8) : 0));
+                   (cfg->n_importance > 0 ? align256(sizeof(float) * (size_t)n * Sf * 8) : 0) + 256 /* work counter */);
 }
 
 int mnrf_render_level(const mnrf_field* coarse, const mnrf_field* fine, const float* rays, int n,
@@ -390,6 +423,8 @@ int mnrf::render_level(const mnrf_field* coarse, const mnrf_field* fine, const f
   MNRF_REQUIRE(workspace != nullptr && workspace_bytes >= mnrf_level_workspace_bytes(n, cfg),
                "render_level: workspace too small");
   MNRF_REQUIRE(out->z_coarse && out->coarse.weights && out->coarse.opacity, "render_level: coarse outputs missing");
+  MNRF_REQUIRE(cfg->dir_source == nullptr || coarse->kind == 0, "render_level: view_dir needs the MLP field");
+  const float* dir_src = cfg->dir_source != nullptr ? cfg->dir_source : rays;   // rendering.py:276 view_dir
   static const mnrf_level_rng no_rng = {nullptr, nullptr, nullptr, nullptr};
   if (rng == nullptr) rng = &no_rng;
   cudaStream_t st = S_(stream);
@@ -397,6 +432,7 @@ int mnrf::render_level(const mnrf_field* coarse, const mnrf_field* fine, const f
   float* dirbias = reinterpret_cast<float*>(ws); ws += align256(sizeof(float) * (size_t)n * WH);
   float* buf_c = reinterpret_cast<float*>(ws);   ws += align256(sizeof(float) * (size_t)n * Sc * 8);
   float* buf_f = reinterpret_cast<float*>(ws);
+  int* counter = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(workspace) + mnrf_level_workspace_bytes(n, cfg) - 256);
   const int impl = cfg->impl;
 
   // ---- coarse pass (rendering.py:271-305) ----
@@ -406,42 +442,38 @@ int mnrf::render_level(const mnrf_field* coarse, const mnrf_field* fine, const f
   io.rays = rays; io.z = out->z_coarse; io.n_points = n * Sc; io.S = Sc; io.sigma_only = sig_only; io.n_rays_dev = n_dev;
   if (sig_only) {
     io.sigma_out = buf_c;
+    if (run_field(coarse, impl, io, st)) return 1;
+    if (launch_composite(rays, out->z_coarse, buf_c, 1, nullptr, nullptr, rng->noise_coarse, cfg->noise_std, n, Sc,
+                         cfg->white_back, out->coarse, st, n_dev))
+      return 1;
   } else {
-    if (coarse->kind == 0 && launch_dirbias(coarse, rays, n, 8, 0, dirbias, st, n_dev)) return 1;
+    if (coarse->kind == 0 && launch_dirbias(coarse, dir_src, n, 8, 0, dirbias, st, n_dev)) return 1;
     io.dirbias = dirbias;
-    io.raw = buf_c;
     if (cfg->compute_normal) {
       MNRF_REQUIRE(out->normal_coarse != nullptr, "render_level: compute_normal needs normal_coarse");
       io.normal_out = out->normal_coarse;
     }
+    if (run_full_pass(coarse, cfg, io, rng->noise_coarse, buf_c, n, Sc, out->coarse, counter, nullptr, st, n_dev)) return 1;
   }
-  if (run_field(coarse, impl, io, st)) return 1;
-  if (launch_composite(rays, out->z_coarse, buf_c, sig_only ? 1 : 8, sig_only ? nullptr : buf_c,
-                       sig_only ? nullptr : io.normal_out, rng->noise_coarse, cfg->noise_std, n, Sc, cfg->white_back,
-                       out->coarse, st, n_dev))
-    return 1;
 
   // ---- importance resampling + second pass (rendering.py:307-361) ----
   const mnrf_field* second = cfg->rerun_coarse_on_fine ? coarse : fine;
   if (Ni > 0 && second != nullptr) {
-    MNRF_REQUIRE(out->z_fine && out->fine.weights && out->fine.opacity, "render_level: fine outputs missing");
+    MNRF_REQUIRE(out->z_fine && out->fine.opacity, "render_level: fine outputs missing");
     const float* u = rng->u_pdf != nullptr ? rng->u_pdf : u_det;
     MNRF_REQUIRE(u != nullptr, "render_level: need u_pdf or u_det");
     if (launch_sample_pdf(out->z_coarse, nullptr, out->coarse.weights, Sc, 1, n, Sc, Ni, u,
                           rng->u_pdf != nullptr ? Ni : 0, out->z_fine, nullptr, nullptr, nullptr, st, n_dev))
       return 1;
-    if (second->kind == 0 && launch_dirbias(second, rays, n, 8, 0, dirbias, st, n_dev)) return 1;
+    if (second->kind == 0 && launch_dirbias(second, dir_src, n, 8, 0, dirbias, st, n_dev)) return 1;
     FieldIO io2{};
     io2.rays = rays; io2.z = out->z_fine; io2.n_points = n * Sf; io2.S = Sf; io2.sigma_only = 0; io2.n_rays_dev = n_dev;
-    io2.dirbias = dirbias; io2.raw = buf_f;
+    io2.dirbias = dirbias;
     if (cfg->compute_normal) {
       MNRF_REQUIRE(out->normal_fine != nullptr, "render_level: compute_normal needs normal_fine");
       io2.normal_out = out->normal_fine;
     }
-    if (run_field(second, impl, io2, st)) return 1;
-    if (launch_composite(rays, out->z_fine, buf_f, 8, buf_f, io2.normal_out, rng->noise_fine, cfg->noise_std, n, Sf,
-                         cfg->white_back, out->fine, st, n_dev))
-      return 1;
+    if (run_full_pass(second, cfg, io2, rng->noise_fine, buf_f, n, Sf, out->fine, counter, cfg->stats, st, n_dev)) return 1;
   }
   return 0;
 }

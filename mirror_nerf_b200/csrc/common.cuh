@@ -339,10 +339,20 @@ int train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, const
                    const mnrf_train_cfg& cfg, const void* ws_fwd, void* ws_bwd, const mnrf_train_grads& g,
                    const float* ray_detach_mirror, float* const* grad_tensors, const float* depth, float* grad_rays,
                    cudaStream_t st);
+bool can_fuse_composite(const mnrf_field* f, const mnrf_level_cfg* cfg, const float* noise, int S);
 int render_level(const mnrf_field* coarse, const mnrf_field* fine, const float* rays, int n, const mnrf_level_cfg* cfg,
                  const mnrf_level_rng* rng, const float* z_steps, const float* u_det, void* workspace, int64_t workspace_bytes,
                  const mnrf_level_out* out, void* stream, const int* n_dev);
 void set_tc_trace(unsigned long long* buf, unsigned int cap);
-int launch_field_tc(const mnrf_field* f, const FieldIO& io, int precision /*1|2|3*/, cudaStream_t st);
+// compositing fused into the tensor-core field kernel (field_tc.cu FUSE): per-ray outputs straight from the epilogue registers
+struct FusedComposite {
+  mnrf_composite_out comp;     // opacity required; weights / pred_normal (per sample) optional
+  int white_back;
+  float term_eps;              // > 0: early ray termination (only when no per-sample output is requested)
+  int* work_counter;           // device int (zeroed by the launcher)
+  unsigned long long* stats;   // optional device counters: [0] tiles executed, [1] 32-sample chunks skipped
+};
+int launch_field_tc(const mnrf_field* f, const FieldIO& io, int precision /*1|2|3*/, cudaStream_t st,
+                    const FusedComposite* fuse = nullptr);
 
 }  // namespace mnrf

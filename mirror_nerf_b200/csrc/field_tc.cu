@@ -26,6 +26,7 @@
 // profiles/r02_v1_fp8_mma_microbench.txt) -- 2.0 fp16-pass equivalents per algorithmic MAC instead of 3, operand error ~2^-16.
 //
 // Shared memory (1 CTA/SM): A hi/lo 2x64 KB | PE hi/lo 2x16 KB | 4 x 16 KB weight stages | 2 KB partial sums.
+#include <cstring>
 #include <mutex>
 
 #include "common.cuh"
@@ -47,7 +48,8 @@ constexpr uint32_t SM_PE_LO = 147456;
 constexpr uint32_t SM_WST = 163840;
 constexpr uint32_t SM_PART = SM_WST + 4 * WSTAGE_BYTES;  // 229376: float4[128]
 constexpr uint32_t SM_BAR = SM_PART + 2048;              // 231424
-constexpr uint32_t SM_TOTAL = SM_BAR + 256;              // 231680 <= 232448
+constexpr uint32_t SM_FUSE = SM_BAR + 256;               // 231680: work descriptors of the fused (ray-tile) mode, 256 B
+constexpr uint32_t SM_TOTAL = SM_FUSE + 256;             // 231936 <= 232448
 
 // barrier slots (8 bytes each)
 constexpr int BAR_W_FULL = 0;    // [8]
@@ -55,6 +57,7 @@ constexpr int BAR_W_EMPTY = 8;   // [8]
 constexpr int BAR_PE = 16;       // PE chunk written (8 warp arrivals)
 constexpr int BAR_A = 17;        // [5] A columns written (8 warp arrivals): [0] cols 0-31, [1..3] 64-col chunks 1..3, [4] cols 32-63
 constexpr int BAR_ACC = 22;      // [4] accumulator of a GEMM step complete (tcgen05.commit)
+constexpr int BAR_GO = 26;       // fused mode: "next tile is decided" for the weight producer (8 warp arrivals, like BAR_PE)
 constexpr int BAR_TMEM_SLOT = 30;
 
 constexpr uint32_t IDESC_N256 = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);  // f16 x f16 -> f32, K-major
@@ -70,6 +73,13 @@ struct TcParams {
   FieldIO io;
   int n_tiles;
   int slot;                   // which copy of the epilogue table (c_epi) belongs to this launch's field
+  // fused (ray-tile) mode: tile = 4 rays x 32 consecutive samples, compositing in the epilogue registers
+  mnrf_composite_out comp;    // per-ray outputs (+ optional per-sample weights / pred_normal)
+  int n_rays;                 // rays of the launch (the device count io.n_rays_dev clamps it)
+  int white_back;
+  float term_eps;             // > 0: stop a ray once its transmittance falls below this (eval, compact outputs only)
+  int* work_counter;          // device int, zero at launch: next ray to hand out
+  unsigned long long* stats;  // optional device counters: [0] tiles executed, [1] chunks skipped by early termination
   unsigned long long* trace;  // optional device-side event trace of CTA 0 (bring-up builds)
   unsigned int trace_cap;
   int debug;
@@ -426,7 +436,12 @@ __device__ __forceinline__ int acc_bar(int s) {  // steps 9 and 10 share slot 2;
 __device__ __forceinline__ int step_at(int i) { return i < 8 ? i : (i == 8 ? 9 : (i == 9 ? 8 : i)); }
 
 // ================================================================================================
-template <int PREC, bool NORMALS>
+// FUSE (ray-tile mode, full non-NORMALS pass only): a tile is 4 rays x 32 consecutive samples -- TMEM lane quarter q = one ray's
+// chunk -- handed out dynamically (two rays in flight per quarter, alternating tiles, so that the (ray, chunk) of a tile is
+// known one tile ahead for the positional encoding); the epilogue composites the chunk in registers with the arithmetic of
+// composite.cu (same warp scan, same running carry: bit-identical), optionally stops a ray whose transmittance fell below
+// term_eps, and writes per-ray outputs -- no per-point record goes through HBM.  R/models/rendering.py:175-264,363-367.
+template <int PREC, bool NORMALS, bool FUSE = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -444,6 +459,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
   }
   const int n_tiles = (n_points + TILE_M - 1) / TILE_M;
   const float* const c_epi = c_epi_slots[P.slot];
+  // fused mode: work descriptors of the two alternating tile slots, [slot][quarter]; stop flag for the producer / MMA roles
+  volatile int* f_ray = reinterpret_cast<volatile int*>(smem + SM_FUSE);        // ray index or -1
+  volatile int* f_chunk = f_ray + 8;                                              // 32-sample chunk of that ray
+  volatile int* f_stop = f_ray + 16;
   constexpr bool PREC3 = PREC == 3;                 // three fp16 passes
   constexpr bool TWO_BLOBS = PREC != 1;              // weight chunk = two 16 KB halves (3x: hi|lo; tc2: hi16 | hi8,lo8)
   constexpr uint32_t NST = TWO_BLOBS ? 4u : 8u;  // weight stages (the 1x mode also uses the idle A_lo region)  // weight stages (the 1x mode also uses the idle A_lo region)
@@ -453,6 +472,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
     if (sbase & 127u) { printf("mnrf field_tc: unaligned dynamic smem base %u\n", sbase); __trap(); }
     for (int i = 0; i < 8; ++i) { mbar_init(bar(BAR_W_FULL + i), 1); mbar_init(bar(BAR_W_EMPTY + i), 1); }
     mbar_init(bar(BAR_PE), 8);
+    mbar_init(bar(BAR_GO), 8);
     for (int i = 0; i < 5; ++i) mbar_init(bar(BAR_A + i), 8);
     for (int i = 0; i < 4; ++i) mbar_init(bar(BAR_ACC + i), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -474,8 +494,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
     // Stage contents.  3x mode: N=256 steps -> one blob (hi or lo of a K32 chunk, 16 KB); N=128 steps -> [hi|lo] of a K32
     // chunk (2 x 8 KB, contiguous).  1x mode: N=256 -> hi blob of a K32 chunk; N=128 -> hi blobs of two K32 chunks.
     if (elect_one()) {
-      uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      uint32_t stage = 0, phase = 0, go_phase = 0;
+      for (int tile = blockIdx.x; FUSE || tile < n_tiles; tile += gridDim.x) {
+        if (FUSE) {  // the epilogue warps decide tile by tile whether there is another one
+          mbar_wait(bar(BAR_GO), go_phase);
+          go_phase ^= 1u;
+          if (*f_stop) break;
+        }
         for (int i = 0; i < n_issue; ++i) {
           const int s = step_at(i);
           if (s == 9 && !P.has_mirror) continue;
@@ -520,7 +545,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
       const uint32_t dl_a8 = dl_a_lo, dl_a8r = desc_lo(sbase + SM_A_LO + 32768u, 2048);
       const uint32_t dl_pe8 = dl_pe_lo, dl_pe8r = desc_lo(sbase + SM_PE_LO + 8192u, 2048);
       auto next_stage = [&]() { if (++stage == NST) { stage = 0; phase ^= 1u; } };
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; FUSE || tile < n_tiles; tile += gridDim.x) {
+        if (FUSE) {  // PE barrier = "the next tile's encoding is in place" or "stop"
+          mbar_wait(bar(BAR_PE), pe_phase);
+          pe_phase ^= 1u;
+          if (*f_stop) break;
+        }
         for (int i = 0; i < n_issue; ++i) {
           const int s = step_at(i);
           if (s == 9 && !P.has_mirror) continue;
@@ -535,7 +565,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
             uint32_t ah, al;  // descriptor low words of this K32 chunk of the A operand (hi / lo parts)
             uint32_t a8 = 0, a8r = 0;  // tc2: e4m3 copy of the chunk and of its residual
             if (kc < n_pe) {
-              if (s == 0 && kc == 0) { mbar_wait(bar(BAR_PE), pe_phase); pe_phase ^= 1u; }
+              if (!FUSE && s == 0 && kc == 0) { mbar_wait(bar(BAR_PE), pe_phase); pe_phase ^= 1u; }
               ah = dl_pe_hi + (uint32_t)kc * 512u; al = dl_pe_lo + (uint32_t)kc * 512u;
               a8 = dl_pe8 + (uint32_t)kc * 256u; a8r = dl_pe8r + (uint32_t)kc * 256u;
             } else {
@@ -741,12 +771,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
       }
     };
 
-    if ((int)blockIdx.x < n_tiles) pe_tile(blockIdx.x);
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const long long p_raw = (long long)tile * TILE_M + row;
-      const bool valid = p_raw < n_points;
-      const long long p = valid ? p_raw : (long long)n_points - 1;
-      const long long ray = (P.io.rays != nullptr) ? p / P.io.S : p;
+    // One tile: p = this thread's point (clamped), ray = its ray; pe_next() is called while layer 6 runs (the PE buffer is free
+    // then) to encode the following tile; emit(...) receives this thread's per-point results (g == 0 threads hold them).
+    auto tile_body = [&](const long long p_raw, const bool valid, const long long p, const long long ray, auto&& pe_next,
+                         auto&& emit) {
       float o_sigma = 0.f, o_n[3] = {0.f, 0.f, 0.f}, o_mirror = 0.f, o_rgb[3] = {0.f, 0.f, 0.f};
       float d[4] = {0.f, 0.f, 0.f, 0.f};
       uint32_t masks[NORMALS ? 8 : 1][4];  // relu' bits of this thread's (row, columns) for every trunk layer
@@ -766,7 +794,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
           else layer_epilogue(TagSigma{}, s, bias, d, masks[0]);
         }
         // the PE buffer is free once layer 5's MMAs are done: encode the next tile while the tensor pipe is busy
-        if (s == 5 && tile + (int)gridDim.x < n_tiles) pe_tile(tile + gridDim.x);
+        if (s == 5) pe_next();
       }
       // combine the two column groups' partial dot products (sigma + folded normal head)
       {
@@ -961,20 +989,168 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
         }
       }
 
-      // ---- write the point record ----
       if (q == 0) trace_ev(P, trc, lane, 4 + g, 14, 0, 0);
       tc_fence_before();
-      if (g == 0 && valid) {
-        if (P.io.sigma_out != nullptr) P.io.sigma_out[p_raw] = o_sigma;
-        if (P.io.raw != nullptr) {
-          float4* o = reinterpret_cast<float4*>(P.io.raw + p_raw * 8);
-          o[0] = make_float4(o_sigma, o_rgb[0], o_rgb[1], o_rgb[2]);
-          o[1] = make_float4(o_mirror, o_n[0], o_n[1], o_n[2]);
+      emit(o_sigma, o_rgb, o_mirror, o_n, o_an);
+      (void)p_raw; (void)valid;
+    };
+
+    if (!FUSE) {
+      // ---- static tiles: 128 consecutive points, one record per point ----
+      if ((int)blockIdx.x < n_tiles) pe_tile(blockIdx.x);
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long p_raw = (long long)tile * TILE_M + row;
+        const bool valid = p_raw < n_points;
+        const long long p = valid ? p_raw : (long long)n_points - 1;
+        const long long ray = (P.io.rays != nullptr) ? p / P.io.S : p;
+        tile_body(p_raw, valid, p, ray, [&]() { if (tile + (int)gridDim.x < n_tiles) pe_tile(tile + gridDim.x); },
+                  [&](float o_sigma, const float (&o_rgb)[3], float o_mirror, const float (&o_n)[3], const float (&o_an)[3]) {
+          if (g == 0 && valid) {
+            if (P.io.sigma_out != nullptr) P.io.sigma_out[p_raw] = o_sigma;
+            if (P.io.raw != nullptr) {
+              float4* o = reinterpret_cast<float4*>(P.io.raw + p_raw * 8);
+              o[0] = make_float4(o_sigma, o_rgb[0], o_rgb[1], o_rgb[2]);
+              o[1] = make_float4(o_mirror, o_n[0], o_n[1], o_n[2]);
+            }
+            if (NORMALS && P.io.normal_out != nullptr) {
+              float* no = P.io.normal_out + p_raw * 3;
+              no[0] = o_an[0]; no[1] = o_an[1]; no[2] = o_an[2];
+            }
+          }
+        });
+      }
+    } else {
+      // ---- fused ray tiles ----
+      const int S = P.io.S;
+      const int nch = (S + 31) >> 5;                  // 32-sample chunks per ray
+      int n_rays = P.n_rays;
+      if (P.io.n_rays_dev != nullptr) n_rays = min(n_rays, max(__ldg(P.io.n_rays_dev), 0));
+      // per-slot compositing state of this quarter's ray (meaningful in the g == 0 warp: lane = sample within the chunk)
+      struct RayAcc { float carry, op, r, gg, b, d, m, n0, n1, n2; };
+      RayAcc st[2];
+      auto reset = [](RayAcc& a) { a.carry = 1.f; a.op = a.r = a.gg = a.b = a.d = a.m = a.n0 = a.n1 = a.n2 = 0.f; };
+      reset(st[0]); reset(st[1]);
+      auto grab = [&]() {   // warp-uniform: next ray index or -1
+        int r = 0;
+        if (lane == 0) { r = atomicAdd(P.work_counter, 1); if (r >= n_rays) r = -1; }
+        return __shfl_sync(0xffffffffu, r, 0);
+      };
+      if (g == 0) {
+        const int r0 = grab(), r1 = grab();
+        if (lane == 0) { f_ray[q] = r0; f_chunk[q] = 0; f_ray[4 + q] = r1; f_chunk[4 + q] = 0; }
+        if (warp == 4 && lane == 0) *f_stop = 0;
+      }
+      epi_bar_sync(1);
+      auto slot_alive = [&](int sl) { return (f_ray[4 * sl] >= 0) || (f_ray[4 * sl + 1] >= 0) || (f_ray[4 * sl + 2] >= 0) || (f_ray[4 * sl + 3] >= 0); };
+      // encode the tile of slot `sl` (or announce the stop) and release the MMA issuer / weight producer for it
+      auto pe_slot = [&](int sl, bool stop) {
+        if (!stop) {
+          const int rr_ = f_ray[4 * sl + q], ch = f_chunk[4 * sl + q];
+          const long long ray = rr_ >= 0 ? rr_ : 0;
+          const int smp = min(ch * 32 + lane, S - 1);
+          const float* rr = P.io.rays + ray * 8;
+          const float z = __ldg(P.io.z + ray * S + smp);
+          float x[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(__ldg(rr + c), __fmul_rn(__ldg(rr + 3 + c), z));
+          if (g == 0) pe_fill<0, PREC>(x, sbase + SM_PE_HI, sbase + SM_PE_LO, rowoff);
+          else        pe_fill<1, PREC>(x, sbase + SM_PE_HI, sbase + SM_PE_LO, rowoff);
+        } else if (warp == 4 && lane == 0) {
+          *f_stop = 1;
         }
-        if (NORMALS && P.io.normal_out != nullptr) {
-          float* no = P.io.normal_out + p_raw * 3;
-          no[0] = o_an[0]; no[1] = o_an[1]; no[2] = o_an[2];
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(bar(BAR_PE)); mbar_arrive(bar(BAR_GO)); }
+      };
+      int cur = 0;
+      bool alive_cur = slot_alive(0), alive_other = slot_alive(1);
+      pe_slot(0, !alive_cur);
+      while (alive_cur) {
+        const int rr_ = f_ray[4 * cur + q], ch = f_chunk[4 * cur + q];
+        const bool has_ray = rr_ >= 0;
+        const long long ray = has_ray ? rr_ : 0;
+        const int smp_raw = ch * 32 + lane;
+        const bool valid = has_ray && smp_raw < S;
+        const long long p = ray * S + min(smp_raw, S - 1);
+        bool pe_done = false;
+        tile_body(p, valid, p, ray, [&]() { if (alive_other) { pe_slot(cur ^ 1, false); pe_done = true; } },
+                  [&](float o_sigma, const float (&o_rgb)[3], float o_mirror, const float (&o_n)[3], const float (&o_an)[3]) {
+          (void)o_an;
+          if (g == 0) {
+            // ---- composite this chunk (composite.cu::k_composite, one 32-sample block) ----
+            RayAcc& A = st[cur];
+            float zz = 0.f, alpha = 0.f;
+            if (valid) {
+              zz = __ldg(P.io.z + p);
+              const float delta = (smp_raw + 1 < S) ? __fsub_rn(__ldg(P.io.z + p + 1), zz) : 1e10f;  // rendering.py:182-186
+              alpha = __fsub_rn(1.f, expf(-__fmul_rn(delta, fmaxf(o_sigma, 0.f))));
+            }
+            const float f = valid ? __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f) : 1.f;
+            float incl = f;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const float t = __shfl_up_sync(0xffffffffu, incl, o);
+              if (lane >= o) incl *= t;
+            }
+            float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) excl = 1.f;
+            const float Tr = A.carry * excl;
+            const float w = alpha * Tr;
+            A.carry *= __shfl_sync(0xffffffffu, incl, 31);
+            if (valid) {
+              if (P.comp.weights != nullptr) P.comp.weights[p] = w;
+              A.op += w;
+              A.d = fmaf(w, zz, A.d);
+              A.r = fmaf(w, o_rgb[0], A.r); A.gg = fmaf(w, o_rgb[1], A.gg); A.b = fmaf(w, o_rgb[2], A.b);
+              A.m = fmaf(w, o_mirror, A.m);
+              A.n0 = fmaf(w, o_n[0], A.n0); A.n1 = fmaf(w, o_n[1], A.n1); A.n2 = fmaf(w, o_n[2], A.n2);
+              if (P.comp.pred_normal != nullptr) {
+                float* pn = P.comp.pred_normal + p * 3;
+                pn[0] = o_n[0]; pn[1] = o_n[1]; pn[2] = o_n[2];
+              }
+            }
+            // ---- next work item of this (quarter, slot) ----
+            if (has_ray) {
+              const bool terminated = P.term_eps > 0.f && A.carry < P.term_eps;   // warp-uniform
+              if (ch + 1 >= nch || terminated) {
+                auto wsum = [](float v) { for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); return v; };
+                float a_op = wsum(A.op), a_d = wsum(A.d), a_r = wsum(A.r), a_g = wsum(A.gg), a_b = wsum(A.b), a_m = wsum(A.m);
+                const float a_n0 = wsum(A.n0), a_n1 = wsum(A.n1), a_n2 = wsum(A.n2);
+                if (lane == 0) {
+                  const mnrf_composite_out& O = P.comp;
+                  O.opacity[ray] = a_op;
+                  if (P.white_back) { const float bg = 1.f - a_op; a_r += bg; a_g += bg; a_b += bg; }  // rendering.py:216-217
+                  if (O.rgb) { O.rgb[ray * 3 + 0] = a_r; O.rgb[ray * 3 + 1] = a_g; O.rgb[ray * 3 + 2] = a_b; }
+                  if (O.depth) O.depth[ray] = a_d;
+                  if (O.mirror_mask) O.mirror_mask[ray] = a_m;
+                  if (O.surface_normal) { O.surface_normal[ray * 3 + 0] = a_n0; O.surface_normal[ray * 3 + 1] = a_n1; O.surface_normal[ray * 3 + 2] = a_n2; }
+                  if (O.x_surface) {
+                    const float* ry = P.io.rays + ray * 8;
+                    for (int c = 0; c < 3; ++c) O.x_surface[ray * 3 + c] = __fadd_rn(ry[c], __fmul_rn(ry[3 + c], a_d));
+                  }
+                  if (P.stats != nullptr && ch + 1 < nch) atomicAdd(P.stats + 1, (unsigned long long)(nch - 1 - ch));
+                }
+                reset(A);
+                const int nr = grab();
+                if (lane == 0) { f_ray[4 * cur + q] = nr; f_chunk[4 * cur + q] = 0; }
+              } else if (lane == 0) {
+                f_chunk[4 * cur + q] = ch + 1;
+              }
+            }
+          }
+        });
+        if (warp == 4 && lane == 0 && P.stats != nullptr) atomicAdd(P.stats, 1ull);
+        epi_bar_sync(1);   // every quarter's next work item of slot `cur` is published
+        const bool alive_this = slot_alive(cur);
+        if (pe_done) {           // the other slot's tile is already encoded and released: it runs next
+          alive_other = alive_this;
+          cur ^= 1;
+          alive_cur = true;
+        } else {                 // the other slot had run dry: stay on this one (its encoding could not be prepared ahead)
+          alive_cur = alive_this;
+          pe_slot(cur, !alive_this);
         }
+        epi_bar_sync(2);   // nobody re-reads the descriptors of the finished tile after this point
       }
     }
   }
@@ -1046,8 +1222,13 @@ int epi_slot_release(int slot, cudaStream_t st) {
 }
 }  // namespace
 
-int launch_field_tc(const mnrf_field* f, const FieldIO& io, int precision, cudaStream_t st) {
+int launch_field_tc(const mnrf_field* f, const FieldIO& io, int precision, cudaStream_t st, const FusedComposite* fuse) {
   if (io.n_points <= 0) return 0;
+  if (fuse != nullptr) {
+    MNRF_REQUIRE(!io.sigma_only && io.normal_out == nullptr && io.rays != nullptr && io.z != nullptr,
+                 "field_tc: the fused compositor needs a full ray pass without analytic normals");
+    MNRF_REQUIRE(fuse->comp.opacity != nullptr && fuse->work_counter != nullptr, "field_tc: fused compositor outputs missing");
+  }
   MNRF_REQUIRE(precision >= 1 && precision <= 3, "field_tc: precision must be 1, 2 or 3");
   if (precision == 2 && io.normal_out != nullptr) precision = 3;  // the analytic-normal chain has no fp8 variant
   MNRF_REQUIRE(io.normal_out == nullptr || !io.sigma_only, "field_tc: analytic normals need the full (non sigma-only) pass");
@@ -1060,6 +1241,9 @@ int launch_field_tc(const mnrf_field* f, const FieldIO& io, int precision, cudaS
     MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_tc<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
     MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_tc<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
     MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_tc<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
+    MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_tc<3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
+    MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_tc<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
+    MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_tc<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
   }
   TcParams P;
   const F32Layout& L = f->L;
@@ -1072,6 +1256,13 @@ int launch_field_tc(const mnrf_field* f, const FieldIO& io, int precision, cudaS
   P.io = io;
   P.trace = g_trace_buf;
   P.trace_cap = g_trace_cap;
+  memset(&P.comp, 0, sizeof(P.comp));
+  P.n_rays = 0; P.white_back = 0; P.term_eps = 0.f; P.work_counter = nullptr; P.stats = nullptr;
+  if (fuse != nullptr) {
+    P.comp = fuse->comp; P.n_rays = io.n_points / io.S; P.white_back = fuse->white_back; P.term_eps = fuse->term_eps;
+    P.work_counter = fuse->work_counter; P.stats = fuse->stats;
+    MNRF_CUDA_OK(cudaMemsetAsync(fuse->work_counter, 0, sizeof(int), st));
+  }
   P.debug = 0;
   P.n_tiles = (io.n_points + TILE_M - 1) / TILE_M;
   const int grid = P.n_tiles < num_sms ? P.n_tiles : num_sms;
@@ -1083,7 +1274,14 @@ int launch_field_tc(const mnrf_field* f, const FieldIO& io, int precision, cudaS
   P.slot = slot;
   prof_begin(st);
   const bool normals = io.normal_out != nullptr;
-  if (precision == 2) {
+  if (fuse != nullptr) {
+    // ray tiles: 4 rays x 32 samples, work handed out dynamically; at most one CTA per SM, no more CTAs than ray quartets
+    const int quartets = (P.n_rays + 3) / 4;
+    const int fgrid = quartets < num_sms ? quartets : num_sms;
+    if (precision == 2) { P.tc = f->tc8; k_field_tc<2, false, true><<<fgrid, NUM_THREADS, SM_TOTAL, st>>>(P); }
+    else if (precision == 3) k_field_tc<3, false, true><<<fgrid, NUM_THREADS, SM_TOTAL, st>>>(P);
+    else k_field_tc<1, false, true><<<fgrid, NUM_THREADS, SM_TOTAL, st>>>(P);
+  } else if (precision == 2) {
     P.tc = f->tc8;
     k_field_tc<2, false><<<grid, NUM_THREADS, SM_TOTAL, st>>>(P);
   } else if (precision == 3) {

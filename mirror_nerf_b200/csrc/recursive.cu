@@ -179,7 +179,7 @@ int rec(Ctx& C, int level, const float* rays, const int* cnt_dev, long long cap,
     memset(&lo, 0, sizeof(lo));
     lo.z_coarse = C.z_c; lo.coarse.weights = C.w_c; lo.coarse.opacity = C.op_c;
     mnrf_composite_out& last = C.second ? lo.fine : lo.coarse;
-    if (C.second) { lo.z_fine = C.z_f; lo.fine.weights = C.w_f; }
+    if (C.second) { lo.z_fine = C.z_f; lo.fine.weights = C.w_f; }   // w_f == NULL: the pass composites inside the field kernel
     last.opacity = opacity; last.rgb = base_rgb; last.depth = depth; last.mirror_mask = mask; last.x_surface = xs;
     if (C.has_pred_normal) last.surface_normal = normal; else last.surface_normal_grad = normal;   // eval.py:337-360
     if (C.lc.compute_normal) { lo.normal_coarse = C.nrm_c; lo.normal_fine = C.nrm_f; }
@@ -257,7 +257,11 @@ int64_t plan(Ctx& C, long long slab) {
   C.bump.off = 0; C.bump.peak = 0;
   C.z_c = C.bump.take<float>(R * Sc); C.w_c = C.bump.take<float>(R * Sc); C.op_c = C.bump.take<float>(R);
   C.z_f = C.second ? C.bump.take<float>(R * Sf) : nullptr;
-  C.w_f = C.second ? C.bump.take<float>(R * Sf) : nullptr;
+  {
+    const mnrf_field* last = C.lc.rerun_coarse_on_fine ? C.coarse : C.fine;
+    const bool fused = C.second && last != nullptr && can_fuse_composite(last, &C.lc, nullptr, (int)Sf);
+    C.w_f = C.second && !fused ? C.bump.take<float>(R * Sf) : nullptr;   // per-sample weights only for the unfused compositor
+  }
   C.nrm_c = C.lc.compute_normal && !(C.lc.test_time && C.fine != nullptr) ? C.bump.take<float>(R * Sc * 3) : nullptr;
   C.nrm_f = C.lc.compute_normal && C.second ? C.bump.take<float>(R * Sf * 3) : nullptr;
   C.level_ws_bytes = mnrf_level_workspace_bytes((int)C.rows_max, &C.lc);

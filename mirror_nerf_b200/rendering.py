@@ -11,7 +11,8 @@ Differences from the reference that a caller can observe:
     (``autograd.py`` / ``csrc/train.cu``: fp32 layer-by-layer kernels with a hand-written backward); gradients reach the
     parameters of both models and, when the rays require grad, the rays' origins and directions;
   * a batch of exactly one ray works (the reference's ``.squeeze()`` at rendering.py:365 breaks it);
-  * ``view_dir`` (never passed by any reference caller) is not supported.
+  * ``view_dir`` (rendering.py:276; never passed by any reference caller) is honoured by the inference path and refused
+    under autograd.
 """
 from __future__ import annotations
 
@@ -177,8 +178,16 @@ def render_rays(models, embeddings, rays, N_samples=64, use_disp=False, perturb=
             raise NotImplementedError(f"embedding_{name}.N_freqs={nf}: the {'hash-grid' if hashed else 'MLP'} field takes "
                                       f"N_freqs={want} (R/train.py:45-47,69-70)")
     pack = packed_hash_field if hashed else packed_field
-    if "view_dir" in kwargs:
-        raise NotImplementedError("view_dir is not supported (no reference caller passes it)")
+    view_dir = kwargs.get("view_dir")
+    dir_source = None
+    if view_dir is not None:  # rendering.py:276: embedding_dir(kwargs.get("view_dir", rays_d)); the ray geometry keeps rays_d
+        if hashed:
+            raise NotImplementedError("view_dir with the hash-grid field is not built")
+        view_dir = view_dir.detach().to(device=dev, dtype=torch.float32)
+        if tuple(view_dir.shape) != (n, 3):
+            raise RuntimeError(f"view_dir must be (N,3), got {tuple(view_dir.shape)}")
+        dir_source = rays.clone()
+        dir_source[:, 3:6] = view_dir
     if "coarse" not in models:
         raise KeyError("models must contain 'coarse'")
     compute_normal = bool(kwargs.get("compute_normal", True))
@@ -214,14 +223,21 @@ def render_rays(models, embeddings, rays, N_samples=64, use_disp=False, perturb=
                 raise RuntimeError(f"rng['{name}'] has shape {tuple(t.shape)}, expected {tuple(shape)}")
         return t
 
-    # RNG tensors come from torch, drawn in the reference's call order.  The reference also
-    # draws (and discards) sigma noise when noise_std == 0; we skip that draw.
+    # RNG tensors come from torch, drawn in the reference's call order: rand_like(z_vals) if perturb > 0
+    # (rendering.py:298), randn_like(sigmas) in EVERY inference() call even when noise_std == 0 (:189), rand(N, N_importance) in
+    # sample_pdf if perturb != 0 (:29-31).  The noise_std == 0 draws are made and discarded so that a seeded run consumes the
+    # same generator stream as the reference on the same device (consume_rng=False skips them).
+    consume = bool(kwargs.get("consume_rng", True))
     perturb_u = draw("perturb_u", (n, Sc), torch.rand) if perturb > 0 else None
-    noise_c = draw("noise_coarse", (n, Sc), torch.randn) if noise_std != 0 else None
+    noise_c = draw("noise_coarse", (n, Sc), torch.randn) if (noise_std != 0 or consume) else None
     u_pdf = draw("u_pdf", (n, Ni), torch.rand) if (second_pass and perturb != 0) else None
-    noise_f = draw("noise_fine", (n, Sf), torch.randn) if (second_pass and noise_std != 0) else None
+    noise_f = draw("noise_fine", (n, Sf), torch.randn) if (second_pass and (noise_std != 0 or consume)) else None
+    if noise_std == 0:
+        noise_c = noise_f = None
 
     if needs_grad:
+        if dir_source is not None:
+            raise NotImplementedError("view_dir is not supported under autograd (no reference caller passes it)")
         return _render_level_train(lib, models, rays_in.contiguous(), Sc, Ni, second_pass, rerun, sig_only, use_disp, perturb, noise_std,
                                    white_back, compute_normal, kwargs, perturb_u, noise_c, u_pdf, noise_f)
 
@@ -249,7 +265,9 @@ def render_rays(models, embeddings, rays, N_samples=64, use_disp=False, perturb=
 
     cfg = _lib.LevelCfg(n_samples=Sc, n_importance=Ni, use_disp=int(bool(use_disp)), perturb=float(perturb),
                         noise_std=float(noise_std), white_back=int(bool(white_back)), test_time=int(sig_only),
-                        compute_normal=int(compute_normal), rerun_coarse_on_fine=int(rerun), impl=impl)
+                        compute_normal=int(compute_normal), rerun_coarse_on_fine=int(rerun), impl=impl,
+                        early_termination_eps=0.0, no_fused_composite=int(not kwargs.get("fused_composite", True)),
+                        dir_source=None, stats=None)
     z_steps = _linspace(Sc, dev)
     u_det = _linspace(Ni, dev) if Ni > 0 else None
 
@@ -279,6 +297,7 @@ def render_rays(models, embeddings, rays, N_samples=64, use_disp=False, perturb=
                 normal_coarse=off(tc.get("normal"), lo, 3 * Sc),
                 z_fine=off(tf["z_vals"], lo, Sf) if tf else None, fine=comp_struct(tf, lo, lo + m, Sf),
                 normal_fine=off(tf.get("normal"), lo, 3 * Sf) if tf else None)
+            cfg.dir_source = None if dir_source is None else dir_source.data_ptr() + lo * 8 * 4
             rs = _lib.LevelRng(perturb_u=off(perturb_u, lo, Sc), noise_coarse=off(noise_c, lo, Sc),
                                u_pdf=off(u_pdf, lo, Ni), noise_fine=off(noise_f, lo, Sf))
             _lib.check(lib.mnrf_render_level(

@@ -177,7 +177,8 @@ def render_rays_recursive(models, embeddings, rays, N_samples=64, use_disp=False
 def render_rays_recursive_device(models, embeddings, rays, N_samples=64, use_disp=False, perturb=0, noise_std=0, N_importance=0,
                                  white_back=False, max_recursive_level=1, only_trace_rays_in_mirrors=None, test_time=True,
                                  normal_noise_std=0.0, trace_ray_times=0, normal_noises=None, noise_seed=0,
-                                 workspace_budget_bytes=None, with_level_rays=False, **kwargs):
+                                 workspace_budget_bytes=None, with_level_rays=False, early_termination_eps=1e-5,
+                                 with_stats=False, **kwargs):
     """The whole eval-semantics recursion (R/eval.py::batched_inference :114-740, incl. --app_control_mirror_roughness) as ONE
     call of ``mnrf_render_recursive``: no host synchronisation between level 0 and the blend, mirror rays counted / compacted /
     re-enqueued on the device, the T+1 jittered reflections of a level rendered as one child batch.
@@ -186,7 +187,10 @@ def render_rays_recursive_device(models, embeddings, rays, N_samples=64, use_dis
     ``rgb_t`` (blended), ``rgb_t_direct``, ``rgb_t_reflect``, ``depth_t``, ``depth_t_reflect``, ``opacity_t``, ``mirror_mask_t``
     (hard-clipped, as eval.py:305-306 leaves it), ``surface_normal_t`` / ``surface_normal_grad_t``, ``x_surface_t``,
     ``reflect_direction`` -- the per-sample tensors (weights, z_vals, pred_normal) are not materialised on this path.
-    ``normal_noises``: optional list of trace_ray_times+1 (n,3) standard-normal*std tensors for the LEVEL-0 reflections."""
+    ``normal_noises``: optional list of trace_ray_times+1 (n,3) standard-normal*std tensors for the LEVEL-0 reflections.
+    ``early_termination_eps``: the fused fine pass stops a ray once its transmittance is below this (every skipped sample has
+    weight < eps, so |d rgb| < eps; 0 = composite all samples as the reference does).  ``with_stats``: adds ``fused_stats`` =
+    int64 [tiles executed, 32-sample chunks skipped] of all fine passes of the call."""
     import ctypes as C
 
     from .rendering import DEFAULT_IMPL, _check_rays, _linspace
@@ -219,7 +223,11 @@ def render_rays_recursive_device(models, embeddings, rays, N_samples=64, use_dis
     compute_normal = bool(kwargs.get("compute_normal", False)) and not last.has_normal
     lc = _lib.LevelCfg(n_samples=Sc, n_importance=Ni, use_disp=int(bool(use_disp)), perturb=0.0, noise_std=0.0,
                        white_back=int(bool(white_back)), test_time=int(sig_only), compute_normal=int(compute_normal),
-                       rerun_coarse_on_fine=int(rerun), impl=impl)
+                       rerun_coarse_on_fine=int(rerun), impl=impl, early_termination_eps=float(early_termination_eps or 0.0),
+                       no_fused_composite=int(not kwargs.get("fused_composite", True)), dir_source=None, stats=None)
+    stats = torch.zeros(2, device=dev, dtype=torch.int64) if with_stats else None
+    if stats is not None:
+        lc.stats = stats.data_ptr()
     T = int(trace_ray_times) if normal_noise_std > 0 else 0
     cfg = _lib.TraceCfg(level=lc, max_recursive_level=int(max_recursive_level),
                         only_trace_rays_in_mirrors=1 if only_trace_rays_in_mirrors else -1, trace_ray_times=T,
@@ -261,4 +269,6 @@ def render_rays_recursive_device(models, embeddings, rays, N_samples=64, use_dis
         res[f"mirror_mask_{typ}"] = t["mirror_mask"]
     if level_rays is not None:
         res["level_rays"] = level_rays
+    if stats is not None:
+        res["fused_stats"] = stats
     return res

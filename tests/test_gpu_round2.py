@@ -273,3 +273,121 @@ def test_device_recursion_hash_field():
         b = render_rays_recursive(models, emb, rays, *ARGS, max_recursive_level=2, compact_outputs=True)
     for k in ("rgb_fine", "depth_fine", "mirror_mask_fine", "rgb_fine_reflect"):
         assert torch.equal(a[k], b[k]), k
+
+
+# ------------------------------------------------------------------------------------------------ fused compositor (row g1)
+FUSE_CASES = {
+    "eval_64_128": dict(args=(64, False, 0, 0, 128, 32768, False), kw=dict(test_time=True), fine=True),
+    "white_back": dict(args=(64, False, 0, 0, 128, 32768, True), kw=dict(test_time=True), fine=True),
+    "ragged_s32_i16": dict(args=(32, False, 0, 0, 16, 1000, False), kw=dict(test_time=True), fine=True),       # 48 = 32 + 16 samples
+    "ragged_s40_i33": dict(args=(40, True, 0, 0, 33, 1000, False), kw=dict(test_time=True), fine=True),        # 73 samples, disparity
+    "coarse_only_full": dict(args=(64, False, 0, 0, 0, 32768, False), kw=dict(test_time=True), fine=False),    # full coarse pass
+    "train_mode_forward": dict(args=(64, False, 0, 0, 128, 32768, False), kw=dict(test_time=False), fine=True),  # both passes full
+    "one_field": dict(args=(64, False, 0, 0, 128, 32768, False), kw=dict(test_time=True, only_one_field=True, current_epoch=3), fine=False),
+}
+
+
+@pytest.mark.parametrize("impl", ["tc3", "tc2"])
+@pytest.mark.parametrize("tag", sorted(FUSE_CASES))
+def test_fused_composite_is_bit_identical_to_unfused(mm, tag, impl):
+    """Compositing inside the field kernel (ray tiles of 4 x 32 samples, dynamic work queue, state in the epilogue registers) runs
+    the arithmetic of composite.cu on the same per-point values: every output of render_rays -- per-ray AND per-sample -- must be
+    bit-identical to the field kernel -> raw records -> k_composite sequence."""
+    from mirror_nerf_b200.rendering import render_rays
+    from mirror_nerf_b200.synthetic import random_rays
+    models, emb = mm
+    v = FUSE_CASES[tag]
+    ms = models if v["fine"] else {"coarse": models["coarse"]}
+    for n in (1, 5, 3001):
+        rays = random_rays(n, seed=40 + n).cuda()
+        with torch.no_grad():
+            a = render_rays(ms, emb, rays, *v["args"], compute_normal=False, field_impl=impl, fused_composite=False, **v["kw"])
+            b = render_rays(ms, emb, rays, *v["args"], compute_normal=False, field_impl=impl, fused_composite=True, **v["kw"])
+        assert set(a) == set(b)
+        for k in a:
+            assert torch.equal(a[k], b[k]), (tag, impl, n, k, float((a[k] - b[k]).abs().max()))
+
+
+def test_fused_composite_room_field_bitwise(room):
+    from mirror_nerf_b200.rendering import render_rays
+    models, emb, _ = room
+    rays = room_rays(20000, pose=4).cuda()
+    with torch.no_grad():
+        a = render_rays(models, emb, rays, *ARGS, test_time=True, compute_normal=False, fused_composite=False)
+        b = render_rays(models, emb, rays, *ARGS, test_time=True, compute_normal=False, fused_composite=True)
+    for k in a:
+        assert torch.equal(a[k], b[k]), (k, float((a[k] - b[k]).abs().max()))
+
+
+@pytest.mark.parametrize("impl", ["tc3", "tc2"])
+def test_early_termination_bound_and_savings(oracle, room, impl):
+    """Early ray termination (eps = 1e-5, compact outputs only): every skipped sample has weight < eps, so rgb / opacity move by
+    less than eps per channel and depth by less than eps * far; on the room scene (every ray ends on a wall) at least 10 % of
+    the fine pass's 32-sample chunks are skipped, and the north-star bounds against the oracle still hold."""
+    from mirror_nerf_b200.trace import render_rays_recursive
+    models, emb, sds = room
+    rays = room_rays(4096, pose=1)
+    with torch.no_grad():
+        full = render_rays_recursive(models, emb, rays.cuda(), *ARGS, max_recursive_level=1, compact_outputs=True,
+                                     early_termination_eps=0.0, with_stats=True, field_impl=impl)
+        et = render_rays_recursive(models, emb, rays.cuda(), *ARGS, max_recursive_level=1, compact_outputs=True,
+                                   early_termination_eps=1e-5, with_stats=True, field_impl=impl)
+    assert int(full["fused_stats"][1]) == 0
+    tiles_full, tiles_et, skipped = int(full["fused_stats"][0]), int(et["fused_stats"][0]), int(et["fused_stats"][1])
+    total_chunks = 2 * rays.shape[0] * 6
+    print(f"early termination [{impl}]: tiles {tiles_full} -> {tiles_et}, chunks skipped {skipped} of {total_chunks} "
+          f"({100.0 * skipped / total_chunks:.1f} %)")
+    assert skipped >= 0.10 * total_chunks
+    assert tiles_et <= 0.93 * tiles_full
+    assert float((et["rgb_fine_direct"] - full["rgb_fine_direct"]).abs().max()) <= 1.5e-5
+    assert float((et["opacity_fine"] - full["opacity_fine"]).abs().max()) <= 1.5e-5
+    assert float((et["depth_fine"] - full["depth_fine"]).abs().max()) <= 1.5e-5 * 12.0
+    if impl == "tc3":
+        fn = lambda r: oracle.render_rays(sds, r[:1024], *ARGS, test_time=True, compute_normal=False)
+        with torch.no_grad():
+            want = oracle.trace_eval(lambda r: oracle.render_rays(sds, r, *ARGS, test_time=True, compute_normal=False), rays[:1024], 1)
+            got = render_rays_recursive(models, emb, rays[:1024].cuda(), *ARGS, max_recursive_level=1, compact_outputs=True,
+                                        early_termination_eps=1e-5)
+        for k in ("rgb_fine", "depth_fine", "opacity_fine"):
+            close(got[k].cpu(), want[k], f"early termination vs oracle {k}", median=1e-5, frac=0.01)
+
+
+def test_view_dir_kwarg(oracle, mm):
+    """render_rays(view_dir=...) (R/models/rendering.py:276): the direction embedding uses view_dir, the ray geometry rays_d."""
+    from mirror_nerf_b200.rendering import render_rays
+    from mirror_nerf_b200.synthetic import random_rays, scene_state_dicts
+    models, emb = mm
+    rays = random_rays(64, seed=77)
+    vd = torch.nn.functional.normalize(torch.randn(64, 3, generator=torch.Generator().manual_seed(1)), dim=-1)
+    with torch.no_grad():
+        got = render_rays(models, emb, rays.cuda(), *ARGS, test_time=True, compute_normal=False, view_dir=vd.cuda())
+        base = render_rays(models, emb, rays.cuda(), *ARGS, test_time=True, compute_normal=False)
+        want = oracle.render_rays(scene_state_dicts(), rays, *ARGS, test_time=True, compute_normal=False, view_dir=vd)
+    assert torch.equal(got["depth_fine"], base["depth_fine"]) and torch.equal(got["weights_fine"], base["weights_fine"])
+    assert not torch.equal(got["rgb_fine"], base["rgb_fine"])
+    close(got["rgb_fine"].cpu(), want["rgb_fine"], "view_dir rgb", median=1e-4, frac=0.03)
+
+
+def test_rng_stream_matches_reference_call_order(mm):
+    """A seeded run consumes the generator exactly as the reference does on the same device (R/models/rendering.py:189 draws
+    randn_like(sigmas) in every inference() call, even for noise_std == 0; :298 rand_like(z) if perturb > 0; :29-31 rand(N, Ni)
+    in sample_pdf if perturb != 0): after render_rays the next draw must equal the one after replaying those shapes."""
+    from mirror_nerf_b200.rendering import render_rays
+    from mirror_nerf_b200.synthetic import random_rays
+    models, emb = mm
+    n = 33
+    rays = random_rays(n, seed=3).cuda()
+    for perturb, noise_std in ((0.0, 0.0), (1.0, 0.0), (1.0, 1.0)):
+        torch.manual_seed(123)
+        with torch.no_grad():
+            render_rays(models, emb, rays, 64, False, perturb, noise_std, 128, 32768, False, test_time=True, compute_normal=False)
+        got = torch.rand(4, device="cuda")
+        torch.manual_seed(123)
+        if perturb > 0:
+            torch.rand(n, 64, device="cuda")
+        torch.randn(n, 64, device="cuda")
+        if perturb != 0:
+            torch.rand(n, 128, device="cuda")
+        torch.randn(n, 192, device="cuda")
+        want = torch.rand(4, device="cuda")
+        assert torch.equal(got, want), (perturb, noise_std)

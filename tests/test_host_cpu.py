@@ -25,20 +25,22 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/mnrf.h but not exported by libmnrf.so"
     assert set(names) == set(_lib.EXPORTED_SYMBOLS), set(names) ^ set(_lib.EXPORTED_SYMBOLS)
-    assert lib.mnrf_abi_version() == 1
+    assert lib.mnrf_abi_version() == 2
     assert lib.mnrf_macs_full() == 659456 and lib.mnrf_macs_sigma_only() == 524416
 
 
 def test_struct_sizes_match_header():
     from mirror_nerf_b200 import _lib
     assert C.sizeof(_lib.CompositeOut) == 10 * 8
-    assert C.sizeof(_lib.LevelCfg) == 10 * 4
+    assert C.sizeof(_lib.LevelCfg) == 10 * 4 + 4 + 4 + 8 + 8      # ABI 2: + early_termination_eps, no_fused_composite, 2 pointers
+    assert C.sizeof(_lib.TraceCfg) == 64 + 3 * 4 + 4 + 8
+    assert C.sizeof(_lib.TraceOut) == 11 * 8
     assert C.sizeof(_lib.LevelRng) == 4 * 8
     assert C.sizeof(_lib.LevelOut) == 8 + 80 + 8 + 8 + 80 + 8
     lib = _lib.load()
     cfg = _lib.LevelCfg(n_samples=64, n_importance=128)
-    # dirbias n*128*4 + coarse n*64*32 + fine n*192*32 bytes
-    assert lib.mnrf_level_workspace_bytes(1000, C.byref(cfg)) == 1000 * (512 + 2048 + 6144)
+    # dirbias n*128*4 + coarse n*64*32 + fine n*192*32 bytes + the fused compositor's work counter
+    assert lib.mnrf_level_workspace_bytes(1000, C.byref(cfg)) == 1000 * (512 + 2048 + 6144) + 256
 
 
 def test_compute_without_gpu_fails_loudly():

@@ -4,10 +4,11 @@ mkdir -p gpurun_out
 timeout 600 python -m pytest tests -q -m gpu -p no:cacheprovider > gpurun_out/pytest_r2a.log 2>&1; echo "pytest rc=$?"; tail -25 gpurun_out/pytest_r2a.log
 timeout 200 python bench.py --field-impl tc3 --no-train --no-cpu-baseline --steps 5 > gpurun_out/bench_r2a_tc3.json 2> gpurun_out/bench_r2a_tc3.err; echo "bench tc3 rc=$?"
 timeout 200 python bench.py --field-impl tc2 --no-train --no-cpu-baseline --steps 5 > gpurun_out/bench_r2a_tc2.json 2> gpurun_out/bench_r2a_tc2.err; echo "bench tc2 rc=$?"
+timeout 200 python bench.py --field-impl tc3 --no-train --no-cpu-baseline --steps 5 --early-termination-eps 0 > gpurun_out/bench_r2a_tc3_noet.json 2> gpurun_out/bench_r2a_tc3_noet.err; echo "bench tc3 no-ET rc=$?"
 timeout 200 python bench.py --field-impl tc3 --no-train --no-cpu-baseline --steps 5 --python-recursion > gpurun_out/bench_r2a_tc3_py.json 2> gpurun_out/bench_r2a_tc3_py.err; echo "bench tc3 py rc=$?"
 python - <<'PY'
 import json
-for f in ("tc3","tc2","tc3_py"):
+for f in ("tc3","tc2","tc3_noet","tc3_py"):
     try:
         d=json.loads(open(f"gpurun_out/bench_r2a_{f}.json").read().strip().splitlines()[-1])
         print(f, "value", round(d["value"]), "e2e", round(d["e2e"]["value"]), "frac", d["roofline"]["frac"], "launches", d["gpu_launches"], d["clocks"])
