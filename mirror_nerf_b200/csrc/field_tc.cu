@@ -86,10 +86,12 @@ struct TcParams {
 };
 
 // Epilogue table (biases, head weights, scales: common.cuh ET_*) in constant memory, so that the warp-uniform epilogue reads are
-// constant-cache accesses instead of global loads.  EPI_SLOTS copies: a launch names the slot that holds ITS field's table, so
-// the coarse and the fine field (and a third one) stay resident and two fields rendered on different streams do not share a
-// table; the host side (epi_slot_acquire) orders a slot's rewrite after the last kernel that read it.
-constexpr int EPI_SLOTS = 3;
+// constant-cache accesses instead of global loads.  The host side (epi_slot_acquire) keys the copy by the field's pack stamp
+// and orders a rewrite after the last kernel (on any stream) that read it, so two fields rendered on different streams never
+// race on the table.  ONE slot: with a compile-time slot index the biases are immediate constant operands of the epilogue's
+// FFMAs; indexing several slots at run time turned every bias read into a register-indexed LDC (measured: 976 LDC in the
+// tc2 kernel, 0.5 per element), which costs more than re-copying 16 KB when the coarse and the fine field alternate.
+constexpr int EPI_SLOTS = 1;
 __constant__ float c_epi_slots[EPI_SLOTS][ET_TOTAL];
 
 // device-side tracing (mnrf_debug_set_trace): lane 0 of a warp of CTA 0 logs (clock64, tag) with plain stores into its own
@@ -259,9 +261,11 @@ __device__ __forceinline__ void store_a8(uint32_t hi_addr, uint32_t lo_addr, con
 // ---- tc2: 16 consecutive K values of an A operand -> fp16 hi (two core-matrix rows) + e4m3(x) + e4m3(2^10 (x - hi)) -----------
 // hi16_addr: the core-matrix row of the first 8 values (the next 8 are one K-group = 2048 B further); a8_addr: the 16-byte row
 // of the e4m3 copy of x; the residual copy lives A8_LO_OFF bytes behind it.
+template <bool RELU>
 __device__ __forceinline__ uint32_t cvt_e4m3x2(float a, float b) {  // {low byte = e4m3(a), high byte = e4m3(b)}
   uint16_t r;
-  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(b), "f"(a));
+  if (RELU) asm("cvt.rn.satfinite.relu.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(b), "f"(a));
+  else      asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(b), "f"(a));
   return (uint32_t)r;
 }
 template <bool RELU>
@@ -269,13 +273,14 @@ __device__ __forceinline__ void store_a16_tc2(uint32_t hi16_addr, uint32_t a8_ad
   uint32_t h[8], x8[4], l8[4];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const float a = RELU ? fmaxf(v[2 * i], 0.f) : v[2 * i], b = RELU ? fmaxf(v[2 * i + 1], 0.f) : v[2 * i + 1];
-    // hi: round toward zero after the ReLU (residual >= 0), round to nearest for signed values
-    if (RELU) asm("cvt.rz.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(b), "f"(a));
+    const float a = v[2 * i], b = v[2 * i + 1];
+    // The ReLU rides on the conversions (no separate max): hi = rz(relu(x)) so that the residual of a positive value is >= 0;
+    // for x < 0: hi = 0 and the residual x - 0 < 0 is clamped by the relu of its own conversion.  Signed values: rn, no relu.
+    if (RELU) asm("cvt.rz.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(b), "f"(a));
     else      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(b), "f"(a));
     const float2 hf = __half22float2(*reinterpret_cast<__half2*>(&h[i]));
-    const uint32_t xa = cvt_e4m3x2(a, b);
-    const uint32_t la = cvt_e4m3x2((a - hf.x) * 1024.f, (b - hf.y) * 1024.f);
+    const uint32_t xa = cvt_e4m3x2<RELU>(a, b);
+    const uint32_t la = cvt_e4m3x2<RELU>((a - hf.x) * 1024.f, (b - hf.y) * 1024.f);
     if (i & 1) { x8[i >> 1] |= xa << 16; l8[i >> 1] |= la << 16; }
     else       { x8[i >> 1] = xa;        l8[i >> 1] = la; }
   }
@@ -458,7 +463,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
     if (alive < n_points) n_points = (int)(alive < 0 ? 0 : alive);
   }
   const int n_tiles = (n_points + TILE_M - 1) / TILE_M;
-  const float* const c_epi = c_epi_slots[P.slot];
+  const float* const c_epi = c_epi_slots[0];
   // fused mode: work descriptors of the two alternating tile slots, [slot][quarter]; stop flag for the producer / MMA roles
   volatile int* f_ray = reinterpret_cast<volatile int*>(smem + SM_FUSE);        // ray index or -1
   volatile int* f_chunk = f_ray + 8;                                              // 32-sample chunk of that ray

@@ -323,6 +323,7 @@ int mnrf_render_recursive(const mnrf_field* coarse, const mnrf_field* fine, cons
                           const mnrf_trace_cfg* cfg, const float* z_steps, const float* u_det,
                           const float* level0_normal_noise, void* workspace, int64_t workspace_bytes,
                           const mnrf_trace_out* out, void* stream) {
+  if (n == 0) return 0;
   MNRF_REQUIRE(rays && z_steps && out && workspace, "render_recursive: null argument");
   MNRF_REQUIRE(out->rgb && out->depth && out->opacity, "render_recursive: rgb, depth and opacity outputs are required");
   Ctx C{};

@@ -1,11 +1,17 @@
-"""Attribute warp-stall samples of a kernel to mbarrier wait loops (by barrier smem offset) and to the rest."""
+"""Attribute warp-stall samples of the first kernel of an .ncu-rep (source page) to mbarrier wait loops and to the rest.
+usage: python tools/ncu_waits.py <rep> [top N instructions]"""
 import csv, subprocess, sys, re
-rep, kid = sys.argv[1], sys.argv[2]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-id", f":::{kid}"], capture_output=True, text=True).stdout
+rep = sys.argv[1]
+topn = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
-hi = [i for i, r in enumerate(rows) if "# Samples" in r][0]
+his = [i for i, r in enumerate(rows) if "# Samples" in r]
+hi = his[0]
+end = [i for i, r in enumerate(rows) if i > hi and r and r[0] == "Kernel Name"]
+end = end[0] if end else len(rows)
 hdr = rows[hi]; ix = {h: i for i, h in enumerate(hdr)}
-data = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+data = [r for r in rows[hi + 1:end] if len(r) == len(hdr)]
+print(rows[hi - 1][:2])
 def f(r, k):
     try: return float(r[ix[k]])
     except Exception: return 0.0
@@ -24,7 +30,15 @@ for i, r in enumerate(data):
 for k, v in sorted(waits.items(), key=lambda kv: -kv[1]):
     print(f"  wait {k:32s} {int(v):9d} {100*v/tot:5.1f} %")
 rest = [(f(r, "# Samples"), r[ix["Source"]].strip()) for i, r in enumerate(data) if i not in seen]
-rest.sort(reverse=True)
 print("  non-wait samples", int(sum(x for x, _ in rest)), f"{100*sum(x for x,_ in rest)/tot:.1f} %")
-for v, s in rest[:int(sys.argv[3]) if len(sys.argv) > 3 else 25]:
-    print(f"    {int(v):8d} {100*v/tot:5.2f} %  {s[:90]}")
+# by opcode
+ops = {}
+for v, s in rest:
+    op = s.split()[0] if not s.startswith("@") else s.split()[1]
+    op = op.split(".")[0]
+    ops[op] = ops.get(op, 0) + v
+for k, v in sorted(ops.items(), key=lambda kv: -kv[1])[:18]:
+    print(f"    op {k:12s} {int(v):9d} {100*v/tot:5.1f} %")
+rest.sort(reverse=True)
+for v, s in rest[:topn]:
+    print(f"    {int(v):8d} {100*v/tot:5.2f} %  {s[:100]}")
