@@ -35,8 +35,8 @@ namespace mnrf {
 namespace {
 
 constexpr int TILE_M = 128;
-constexpr int NUM_THREADS = 384;
-// warp 0: weight producer; warp 1: MMA issuer; warps 4..11: epilogue/PE (TMEM lane quarter = warp % 4).
+constexpr int NUM_THREADS = 640;
+// warp 0: weight producer; warp 1: MMA issuer; warps 4..19: epilogue/PE (TMEM lane quarter = warp % 4, column group = (warp-4)/4).
 constexpr int WARP_PRODUCER = 0;
 constexpr int WARP_MMA = 1;
 constexpr uint32_t WSTAGE_BYTES = 16384;
@@ -54,8 +54,8 @@ constexpr uint32_t SM_TOTAL = SM_FUSE + 256;             // 231936 <= 232448
 // barrier slots (8 bytes each)
 constexpr int BAR_W_FULL = 0;    // [8]
 constexpr int BAR_W_EMPTY = 8;   // [8]
-constexpr int BAR_PE = 16;       // PE chunk written (8 warp arrivals)
-constexpr int BAR_A = 17;        // [5] A columns written (8 warp arrivals): [0] cols 0-31, [1..3] 64-col chunks 1..3, [4] cols 32-63
+constexpr int BAR_PE = 16;       // PE chunk written (16 warp arrivals)
+constexpr int BAR_A = 17;        // [5] A columns written: [0] cols 0-31 and [4] cols 32-63 (8 warp arrivals each), [1..3] 64-col chunks 1..3 (16)
 constexpr int BAR_ACC = 22;      // [4] accumulator of a GEMM step complete (tcgen05.commit)
 constexpr int BAR_GO = 26;       // fused mode: "next tile is decided" for the weight producer (8 warp arrivals, like BAR_PE)
 constexpr int BAR_TMEM_SLOT = 30;
@@ -196,7 +196,13 @@ __device__ __forceinline__ bool elect_one() {
       : "+r"(pred));
   return pred != 0;
 }
-__device__ __forceinline__ void epi_bar_sync(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void epi_bar_sync(int id) { asm volatile("bar.sync %0, 512;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, float a, float b, float c, float d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(a)),
+               "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // K-major, no-swizzle operand descriptors.  Core matrix = 8 rows x 16 bytes stored as 128 contiguous bytes; SBO (distance
 // between 8-row groups) = 128 B for every operand, so all descriptors share the high word; LBO (distance between K-adjacent
@@ -297,14 +303,14 @@ __device__ __noinline__ float2 sincos_pe(float a) {
   return make_float2(s, c);
 }
 
-// ---- positional encoding of one row, K range [32*HALF, 32*HALF+32) (mirror_nerf.py:33-38) ----------------
-template <int HALF, int PREC>
+// ---- positional encoding of one row, K range [16*QUARTER, 16*QUARTER+16) (mirror_nerf.py:33-38) --------
+template <int QUARTER, int PREC>
 __device__ __forceinline__ void pe_fill(const float (&x)[3], uint32_t pe_hi, uint32_t pe_lo, uint32_t rowoff) {
-  constexpr int K0 = 32 * HALF;
-  float vals[32];
+  constexpr int K0 = 16 * QUARTER;
+  float vals[16];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) vals[i] = 0.f;  // k = 63 stays 0 (padding)
-  if (HALF == 0) {
+  for (int i = 0; i < 16; ++i) vals[i] = 0.f;  // k = 63 stays 0 (padding)
+  if (QUARTER == 0) {
     vals[0] = x[0]; vals[1] = x[1]; vals[2] = x[2];
   }
 #pragma unroll
@@ -312,7 +318,7 @@ __device__ __forceinline__ void pe_fill(const float (&x)[3], uint32_t pe_hi, uin
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const int ks = 3 + 6 * f + c, kc = ks + 3;
-      const bool need_s = (ks >= K0 && ks < K0 + 32), need_c = (kc >= K0 && kc < K0 + 32);
+      const bool need_s = (ks >= K0 && ks < K0 + 16), need_c = (kc >= K0 && kc < K0 + 16);
       if (need_s || need_c) {
         const float2 sc = sincos_pe(ldexpf(x[c], f));  // 2^f * x is exact
         if (need_s) vals[ks - K0] = sc.x;
@@ -322,21 +328,15 @@ __device__ __forceinline__ void pe_fill(const float (&x)[3], uint32_t pe_hi, uin
   }
   if (PREC == 2) {
     // pe_lo = base of the e4m3 copies: [x (8 KB) | 2^10 residual (8 KB)], 16 K values per core-matrix row
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      float v[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = vals[16 * j + i];
-      store_a16_tc2<false>(pe_hi + (uint32_t)(4 * HALF + 2 * j) * 2048u + rowoff, pe_lo + (uint32_t)(2 * HALF + j) * 2048u + rowoff, 8192u, v);
-    }
+    store_a16_tc2<false>(pe_hi + (uint32_t)(2 * QUARTER) * 2048u + rowoff, pe_lo + (uint32_t)QUARTER * 2048u + rowoff, 8192u, vals);
     return;
   }
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < 2; ++j) {
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = vals[8 * j + i];
-    const uint32_t off = (uint32_t)(4 * HALF + j) * 2048u + rowoff;
+    const uint32_t off = (uint32_t)(2 * QUARTER + j) * 2048u + rowoff;
     store_a8<false, PREC>(pe_hi + off, pe_lo + off, v);
   }
 }
@@ -476,9 +476,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
   if (threadIdx.x == 0) {
     if (sbase & 127u) { printf("mnrf field_tc: unaligned dynamic smem base %u\n", sbase); __trap(); }
     for (int i = 0; i < 8; ++i) { mbar_init(bar(BAR_W_FULL + i), 1); mbar_init(bar(BAR_W_EMPTY + i), 1); }
-    mbar_init(bar(BAR_PE), 8);
-    mbar_init(bar(BAR_GO), 8);
-    for (int i = 0; i < 5; ++i) mbar_init(bar(BAR_A + i), 8);
+    mbar_init(bar(BAR_PE), 16);   // one arrival per epilogue warp
+    mbar_init(bar(BAR_GO), 16);
+    for (int i = 0; i < 5; ++i) mbar_init(bar(BAR_A + i), (i == 0 || i == 4) ? 8 : 16);  // halves of chunk 0: two column groups each
     for (int i = 0; i < 4; ++i) mbar_init(bar(BAR_ACC + i), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -675,14 +675,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
     }
   } else if (warp >= 4) {
     // =========================== epilogue / PE warps ===========================
-    const int ew = warp - 4;
+    const int ew = warp - 4;       // 0..15
     const int q = ew & 3;          // TMEM lane quarter == warp_id % 4
-    const int g = ew >> 2;         // 32-column half of every 64-column chunk (64-column half of the 128-wide heads)
+    const int g = ew >> 2;         // 16-column quarter of every 64-column chunk (32-column quarter of the 128-wide heads)
     const int row = q * 32 + lane;
     const uint32_t rowoff = (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u;
     const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
     const float4* headw = reinterpret_cast<const float4*>(c_epi + ET_HEADW);
-    float4* part = reinterpret_cast<float4*>(smem + SM_PART);
     uint32_t acc_phase = 0;  // one parity bit per accumulator barrier
     TraceCtx trc{0};
     auto wait_acc = [&](int s) {
@@ -699,6 +698,41 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
       if (lane == 0) mbar_arrive(bar(BAR_A + c));
       if (q == 0) trace_ev(P, trc, lane, 4 + g, 11, c, 0);
     };
+    // Sum of up to 4 floats per row over the four column groups, in the fixed order g = 0, 1, 2, 3.  The four warps of a lane
+    // quarter own the same TMEM lanes, so the exchange goes through 16 accumulator columns that are idle at that moment
+    // (`xcol`): groups 1..3 store, group 0 loads and adds.  Returns the sum in v for g == 0.  Only the four warps of the quarter
+    // synchronise (named barrier 3 + q, 128 threads).
+    auto quarter_sync = [&]() {   // the four warps (column groups) that own this TMEM lane quarter
+      tc_fence_before();
+      asm volatile("bar.sync %0, 128;" ::"r"(3 + q) : "memory");
+      tc_fence_after();
+    };
+    auto xreduce = [&](float (&v)[4], uint32_t xcol) {
+      quarter_sync();   // every group is done reading whatever accumulator these columns belonged to
+      if (g != 0) {
+        tmem_st4(tlane + xcol + 4u * (uint32_t)g, v[0], v[1], v[2], v[3]);
+        tmem_wait_st();
+      }
+      quarter_sync();
+      if (g == 0) {
+        uint32_t r[16];
+        tmem_ld16(tlane + xcol, r);
+        tmem_wait_ld();
+        pin<16>(r);
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[i] += __uint_as_float(r[4 * k + i]);
+        }
+      }
+      quarter_sync();   // the columns may be stored to again (next reduction) or overwritten by a later MMA
+    };
+    auto pe_point = [&](const float (&x)[3]) {
+      if (g == 0) pe_fill<0, PREC>(x, sbase + SM_PE_HI, sbase + SM_PE_LO, rowoff);
+      else if (g == 1) pe_fill<1, PREC>(x, sbase + SM_PE_HI, sbase + SM_PE_LO, rowoff);
+      else if (g == 2) pe_fill<2, PREC>(x, sbase + SM_PE_HI, sbase + SM_PE_LO, rowoff);
+      else pe_fill<3, PREC>(x, sbase + SM_PE_HI, sbase + SM_PE_LO, rowoff);
+    };
     // xyz + positional encoding of this thread's row of `tile` -> PE operand buffer
     auto pe_tile = [&](int tile) {
       if (q == 0) trace_ev(P, trc, lane, 4 + g, 12, 0, 0);
@@ -714,64 +748,55 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) x[c] = __ldg(P.io.x + p * P.io.x_stride + c);
       }
-      if (g == 0) pe_fill<0, PREC>(x, sbase + SM_PE_HI, sbase + SM_PE_LO, rowoff);
-      else        pe_fill<1, PREC>(x, sbase + SM_PE_HI, sbase + SM_PE_LO, rowoff);
+      pe_point(x);
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(BAR_PE));
       if (q == 0) trace_ev(P, trc, lane, 4 + g, 13, 0, 0);
     };
-    // One 256-wide layer: this warp owns columns [64c + 32g, 64c + 32g + 32) of every chunk c, chunks in K order, the next
-    // chunk's TMEM load in flight while the current one is converted.
-    // mk: this thread's four 32-bit relu' words of the layer (chunk c -> mk[c]; chunk 0's two 16-column pieces share mk[0])
     // address of this thread's row in the second operand buffer for the columns that start at byte offset `off` of the fp16
     // buffer: 3x -> the fp16 lo part (same layout); tc2 -> the e4m3 copy (16 K values per 16-byte row: half the K-group count)
     auto lo_addr = [&](uint32_t off) {
       return PREC == 2 ? sbase + SM_A_LO + ((off - rowoff) >> 1) + rowoff : sbase + SM_A_LO + off;
     };
-    auto layer_epilogue = [&](auto tag, int s, const float* bias256, float (&d)[4], uint32_t (&mk)[4]) {
+    // One 256-wide layer: this warp owns columns [64c + 16g, 64c + 16g + 16) of every 64-column chunk c, chunks in K order, the
+    // next chunk's TMEM load in flight while the current one is converted.  Chunk 0 is signalled in two 32-column halves
+    // (groups 0,1 -> BAR_A[0], groups 2,3 -> BAR_A[4]) so that the next layer's MMAs start after a 16-column piece per warp.
+    // mk: this thread's two 32-bit relu' words of the layer (chunk c -> bits [16 (c & 1), +16) of mk[c >> 1])
+    auto layer_epilogue = [&](auto tag, int s, const float* bias256, float (&d)[4], uint32_t (&mk)[2]) {
       constexpr bool RELU = decltype(tag)::relu, DOTS = decltype(tag)::dots, WRITE_A = decltype(tag)::write_a;
       constexpr int MASK = decltype(tag)::mask;
-      if (MASK == 1) { mk[0] = 0u; mk[1] = 0u; mk[2] = 0u; mk[3] = 0u; }
-      const float4* b4 = reinterpret_cast<const float4*>(bias256);
+      if (MASK == 1) { mk[0] = 0u; mk[1] = 0u; }
+      const float4* b4 = reinterpret_cast<const float4*>(bias256) + 4 * g;
       // everything that does not depend on the accumulator is fetched before waiting for it
       const float inv = c_epi[ET_INV_SCALE + s] * (PREC == 2 ? 0.03125f : 1.f);  // tc2 blobs carry 2^5 more scale (pack.cu)
-      float4 b0a[4], b0b[4], b[8];
+      float4 b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { b0a[i] = b4[4 * g + i]; b0b[i] = b4[8 + 4 * g + i]; }
+      for (int i = 0; i < 4; ++i) b[i] = b4[i];
       wait_acc(s);
-      const uint32_t tcol = tlane + acc_col(s);
-      // chunk 0 goes out as two 32-column K chunks (16 columns per warp each) so that the next layer's MMAs can start
-      // after a quarter of a chunk; chunks 1..3: 32 columns per warp, next chunk's TMEM load in flight during conversion
-      uint32_t r0a[16], r0b[16], ra[32], rb[32];
-      tmem_ld16(tcol + (uint32_t)g * 16u, r0a);
-      tmem_ld16(tcol + 32u + (uint32_t)g * 16u, r0b);
+      const uint32_t tcol = tlane + acc_col(s) + 16u * (uint32_t)g;
+      uint32_t ra[16], rb[16];
+      tmem_ld16(tcol, ra);
       tmem_wait_ld();
-      tmem_ld32(tcol + 64u + (uint32_t)g * 32u, rb);  // chunk 1
-      pin<16>(r0a);
-      pin<16>(r0b);
+      tmem_ld16(tcol + 64u, rb);  // chunk 1
+      pin<16>(ra);
       {
-        const uint32_t off = (uint32_t)(g * 2) * 2048u + rowoff;
-        epi_cols<16, RELU, DOTS, WRITE_A, PREC, MASK>(r0a, b0a, inv, sbase + SM_A_HI + off, lo_addr(off), headw + g * 16, d, mk[0], 0);
-        if (WRITE_A) a_ready(0);
-      }
-      {
-        const uint32_t off = (uint32_t)(4 + g * 2) * 2048u + rowoff;
-        epi_cols<16, RELU, DOTS, WRITE_A, PREC, MASK>(r0b, b0b, inv, sbase + SM_A_HI + off, lo_addr(off), headw + 32 + g * 16, d, mk[0], 16);
-        if (WRITE_A) a_ready(4);
+        const uint32_t off = (uint32_t)(2 * g) * 2048u + rowoff;
+        epi_cols<16, RELU, DOTS, WRITE_A, PREC, MASK>(ra, b, inv, sbase + SM_A_HI + off, lo_addr(off), headw + 16 * g, d, mk[0], 0);
+        if (WRITE_A) a_ready(g < 2 ? 0 : 4);
       }
 #pragma unroll
       for (int c = 1; c < 4; ++c) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) b[i] = b4[c * 16 + g * 8 + i];
+        for (int i = 0; i < 4; ++i) b[i] = b4[16 * c + i];
         tmem_wait_ld();  // the load of chunk c (issued one iteration ago) has landed
         if (c < 3) {     // next chunk's load flies while this chunk is converted
-          if (c & 1) tmem_ld32(tcol + (uint32_t)(c + 1) * 64u + (uint32_t)g * 32u, ra);
-          else       tmem_ld32(tcol + (uint32_t)(c + 1) * 64u + (uint32_t)g * 32u, rb);
+          if (c & 1) tmem_ld16(tcol + (uint32_t)(c + 1) * 64u, ra);
+          else       tmem_ld16(tcol + (uint32_t)(c + 1) * 64u, rb);
         }
-        const uint32_t off = (uint32_t)(c * 8 + g * 4) * 2048u + rowoff;
-        if (c & 1) { pin32(rb); epi_cols<32, RELU, DOTS, WRITE_A, PREC, MASK>(rb, b, inv, sbase + SM_A_HI + off, lo_addr(off), headw + c * 64 + g * 32, d, mk[c], 0); }
-        else       { pin32(ra); epi_cols<32, RELU, DOTS, WRITE_A, PREC, MASK>(ra, b, inv, sbase + SM_A_HI + off, lo_addr(off), headw + c * 64 + g * 32, d, mk[c], 0); }
+        const uint32_t off = (uint32_t)(8 * c + 2 * g) * 2048u + rowoff;
+        if (c & 1) { pin<16>(rb); epi_cols<16, RELU, DOTS, WRITE_A, PREC, MASK>(rb, b, inv, sbase + SM_A_HI + off, lo_addr(off), headw + 64 * c + 16 * g, d, mk[c >> 1], 16 * (c & 1)); }
+        else       { pin<16>(ra); epi_cols<16, RELU, DOTS, WRITE_A, PREC, MASK>(ra, b, inv, sbase + SM_A_HI + off, lo_addr(off), headw + 64 * c + 16 * g, d, mk[c >> 1], 16 * (c & 1)); }
         if (WRITE_A) a_ready(c);
       }
     };
@@ -782,7 +807,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
                          auto&& emit) {
       float o_sigma = 0.f, o_n[3] = {0.f, 0.f, 0.f}, o_mirror = 0.f, o_rgb[3] = {0.f, 0.f, 0.f};
       float d[4] = {0.f, 0.f, 0.f, 0.f};
-      uint32_t masks[NORMALS ? 8 : 1][4];  // relu' bits of this thread's (row, columns) for every trunk layer
+      uint32_t masks[NORMALS ? 8 : 1][2];  // relu' bits of this thread's (row, columns) for every trunk layer
       float o_an[3] = {0.f, 0.f, 0.f};     // analytic normal
 
       // ---- trunk layers 1..8 (steps 0..7) ----
@@ -801,21 +826,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
         // the PE buffer is free once layer 5's MMAs are done: encode the next tile while the tensor pipe is busy
         if (s == 5) pe_next();
       }
-      // combine the two column groups' partial dot products (sigma + folded normal head)
+      // combine the four column groups' partial dot products (sigma + folded normal head); columns [384,400) are idle here
+      // (step 7's accumulator is consumed, the dir layer's MMAs come after the final layer's epilogue)
       {
-        if (g == 1) part[row] = make_float4(d[0], d[1], d[2], d[3]);
-        epi_bar_sync(1);
+        xreduce(d, 384u);
         if (g == 0) {
-          const float4 o = part[row];
           const float4 hb = *reinterpret_cast<const float4*>(c_epi + ET_HEADB);
-          o_sigma = d[0] + o.x + hb.x;
+          o_sigma = d[0] + hb.x;
           if (P.has_normal) {
-            const float a = d[1] + o.y + hb.y, b = d[2] + o.z + hb.z, cc = d[3] + o.w + hb.w;
+            const float a = d[1] + hb.y, b = d[2] + hb.z, cc = d[3] + hb.w;
             const float nn = sqrtf(fmaxf(a * a + b * b + cc * cc, FP32_EPS));  // utils/func.py:5-7
             o_n[0] = a / nn; o_n[1] = b / nn; o_n[2] = cc / nn;
           }
         }
-        epi_bar_sync(2);
       }
 
       if (!P.io.sigma_only) {
@@ -823,15 +846,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
         if (P.has_mirror) {
           wait_acc(9);
           const float inv = c_epi[ET_INV_SCALE + 9] * (PREC == 2 ? 0.03125f : 1.f);
-          float dm = 0.f;
-          uint32_t ra[32], rb[32];
-          tmem_ld32(tlane + acc_col(9) + (uint32_t)g * 64u, ra);
-          tmem_ld32(tlane + acc_col(9) + (uint32_t)g * 64u + 32u, rb);
-          const float4* bm = reinterpret_cast<const float4*>(c_epi + ET_B_M0 + g * 64);
-          const float4* wm = reinterpret_cast<const float4*>(c_epi + ET_W_M2 + g * 64);
+          float dm[4] = {0.f, 0.f, 0.f, 0.f};
+          uint32_t ra[32];
+          tmem_ld32(tlane + acc_col(9) + (uint32_t)g * 32u, ra);
+          const float4* bm = reinterpret_cast<const float4*>(c_epi + ET_B_M0 + g * 32);
+          const float4* wm = reinterpret_cast<const float4*>(c_epi + ET_W_M2 + g * 32);
           tmem_wait_ld();
           pin32(ra);
-          pin32(rb);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 bb = bm[i], ww = wm[i];
@@ -839,21 +860,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
             float v2 = fmaf(__uint_as_float(ra[4 * i + 2]), inv, bb.z), v3 = fmaf(__uint_as_float(ra[4 * i + 3]), inv, bb.w);
             v0 = v0 > 0.f ? v0 : 0.01f * v0; v1 = v1 > 0.f ? v1 : 0.01f * v1;
             v2 = v2 > 0.f ? v2 : 0.01f * v2; v3 = v3 > 0.f ? v3 : 0.01f * v3;
-            dm = fmaf(v0, ww.x, dm); dm = fmaf(v1, ww.y, dm); dm = fmaf(v2, ww.z, dm); dm = fmaf(v3, ww.w, dm);
+            dm[0] = fmaf(v0, ww.x, dm[0]); dm[0] = fmaf(v1, ww.y, dm[0]); dm[0] = fmaf(v2, ww.z, dm[0]); dm[0] = fmaf(v3, ww.w, dm[0]);
           }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 bb = bm[8 + i], ww = wm[8 + i];
-            float v0 = fmaf(__uint_as_float(rb[4 * i + 0]), inv, bb.x), v1 = fmaf(__uint_as_float(rb[4 * i + 1]), inv, bb.y);
-            float v2 = fmaf(__uint_as_float(rb[4 * i + 2]), inv, bb.z), v3 = fmaf(__uint_as_float(rb[4 * i + 3]), inv, bb.w);
-            v0 = v0 > 0.f ? v0 : 0.01f * v0; v1 = v1 > 0.f ? v1 : 0.01f * v1;
-            v2 = v2 > 0.f ? v2 : 0.01f * v2; v3 = v3 > 0.f ? v3 : 0.01f * v3;
-            dm = fmaf(v0, ww.x, dm); dm = fmaf(v1, ww.y, dm); dm = fmaf(v2, ww.z, dm); dm = fmaf(v3, ww.w, dm);
-          }
-          if (g == 1) part[row].x = dm;
-          epi_bar_sync(1);
-          if (g == 0) o_mirror = sigmoidf_(dm + part[row].x + c_epi[ET_B_M2]);
-          epi_bar_sync(2);
+          xreduce(dm, 384u);
+          if (g == 0) o_mirror = sigmoidf_(dm[0] + c_epi[ET_B_M2]);
         }
         // ---- final linear (step 8): f = W h8 + b, written over h8 (its readers, steps 9 and 8, are complete) ----
         layer_epilogue(TagFinal{}, 8, c_epi + ET_BIAS + 256 * 8, d, masks[0]);
@@ -861,15 +871,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
         wait_acc(10);
         {
           const float inv = c_epi[ET_INV_SCALE + 10] * (PREC == 2 ? 0.03125f : 1.f);
-          const float4* db = reinterpret_cast<const float4*>(P.io.dirbias + ray * WH + g * 64);
-          const float4* wr = reinterpret_cast<const float4*>(c_epi + ET_W_RGB + g * 64);
-          float d0 = 0.f, d1 = 0.f, d2 = 0.f;
-          uint32_t ra[32], rb[32];
-          tmem_ld32(tlane + acc_col(10) + (uint32_t)g * 64u, ra);
-          tmem_ld32(tlane + acc_col(10) + (uint32_t)g * 64u + 32u, rb);
+          const float4* db = reinterpret_cast<const float4*>(P.io.dirbias + ray * WH + g * 32);
+          const float4* wr = reinterpret_cast<const float4*>(c_epi + ET_W_RGB + g * 32);
+          float dc[4] = {0.f, 0.f, 0.f, 0.f};
+          uint32_t ra[32];
+          tmem_ld32(tlane + acc_col(10) + (uint32_t)g * 32u, ra);
           tmem_wait_ld();
           pin32(ra);
-          pin32(rb);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 bb = __ldg(db + i), w0 = wr[i], w1 = wr[WH / 4 + i], w2 = wr[2 * (WH / 4) + i];
@@ -877,30 +885,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
             const float v1 = fmaxf(fmaf(__uint_as_float(ra[4 * i + 1]), inv, bb.y), 0.f);
             const float v2 = fmaxf(fmaf(__uint_as_float(ra[4 * i + 2]), inv, bb.z), 0.f);
             const float v3 = fmaxf(fmaf(__uint_as_float(ra[4 * i + 3]), inv, bb.w), 0.f);
-            d0 = fmaf(v0, w0.x, d0); d0 = fmaf(v1, w0.y, d0); d0 = fmaf(v2, w0.z, d0); d0 = fmaf(v3, w0.w, d0);
-            d1 = fmaf(v0, w1.x, d1); d1 = fmaf(v1, w1.y, d1); d1 = fmaf(v2, w1.z, d1); d1 = fmaf(v3, w1.w, d1);
-            d2 = fmaf(v0, w2.x, d2); d2 = fmaf(v1, w2.y, d2); d2 = fmaf(v2, w2.z, d2); d2 = fmaf(v3, w2.w, d2);
+            dc[0] = fmaf(v0, w0.x, dc[0]); dc[0] = fmaf(v1, w0.y, dc[0]); dc[0] = fmaf(v2, w0.z, dc[0]); dc[0] = fmaf(v3, w0.w, dc[0]);
+            dc[1] = fmaf(v0, w1.x, dc[1]); dc[1] = fmaf(v1, w1.y, dc[1]); dc[1] = fmaf(v2, w1.z, dc[1]); dc[1] = fmaf(v3, w1.w, dc[1]);
+            dc[2] = fmaf(v0, w2.x, dc[2]); dc[2] = fmaf(v1, w2.y, dc[2]); dc[2] = fmaf(v2, w2.z, dc[2]); dc[2] = fmaf(v3, w2.w, dc[2]);
           }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 bb = __ldg(db + 8 + i), w0 = wr[8 + i], w1 = wr[WH / 4 + 8 + i], w2 = wr[2 * (WH / 4) + 8 + i];
-            const float v0 = fmaxf(fmaf(__uint_as_float(rb[4 * i + 0]), inv, bb.x), 0.f);
-            const float v1 = fmaxf(fmaf(__uint_as_float(rb[4 * i + 1]), inv, bb.y), 0.f);
-            const float v2 = fmaxf(fmaf(__uint_as_float(rb[4 * i + 2]), inv, bb.z), 0.f);
-            const float v3 = fmaxf(fmaf(__uint_as_float(rb[4 * i + 3]), inv, bb.w), 0.f);
-            d0 = fmaf(v0, w0.x, d0); d0 = fmaf(v1, w0.y, d0); d0 = fmaf(v2, w0.z, d0); d0 = fmaf(v3, w0.w, d0);
-            d1 = fmaf(v0, w1.x, d1); d1 = fmaf(v1, w1.y, d1); d1 = fmaf(v2, w1.z, d1); d1 = fmaf(v3, w1.w, d1);
-            d2 = fmaf(v0, w2.x, d2); d2 = fmaf(v1, w2.y, d2); d2 = fmaf(v2, w2.z, d2); d2 = fmaf(v3, w2.w, d2);
-          }
-          if (g == 1) part[row] = make_float4(d0, d1, d2, 0.f);
-          epi_bar_sync(1);
+          // columns [256,272): inside the final layer's accumulator (consumed), not touched by the next tile's first layer
+          xreduce(dc, 256u);
           if (g == 0) {
-            const float4 o = part[row];
-            o_rgb[0] = sigmoidf_(d0 + o.x + c_epi[ET_B_RGB + 0]);
-            o_rgb[1] = sigmoidf_(d1 + o.y + c_epi[ET_B_RGB + 1]);
-            o_rgb[2] = sigmoidf_(d2 + o.z + c_epi[ET_B_RGB + 2]);
+            o_rgb[0] = sigmoidf_(dc[0] + c_epi[ET_B_RGB + 0]);
+            o_rgb[1] = sigmoidf_(dc[1] + c_epi[ET_B_RGB + 1]);
+            o_rgb[2] = sigmoidf_(dc[2] + c_epi[ET_B_RGB + 2]);
           }
-          epi_bar_sync(2);
         }
       }
 
@@ -910,23 +905,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
         {
           const float4* hw = headw;
 #pragma unroll
-          for (int piece = 0; piece < 5; ++piece) {  // same column ownership as layer_epilogue: chunk 0 as two 16-col pieces
-            const int c = piece < 2 ? 0 : piece - 1;
-            const int ncol = piece < 2 ? 16 : 32;
-            const int col0 = piece == 0 ? g * 16 : (piece == 1 ? 32 + g * 16 : c * 64 + g * 32);
-            const int bit0 = piece == 1 ? 16 : 0;
+          for (int c = 0; c < 4; ++c) {  // same column ownership as layer_epilogue
+            const int col0 = 64 * c + 16 * g;
+            const uint32_t bits = masks[7][c >> 1] >> (16 * (c & 1));
 #pragma unroll
-            for (int j = 0; j < ncol / 8; ++j) {
+            for (int j = 0; j < 2; ++j) {
               float v[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = ((masks[7][c] >> (bit0 + 8 * j + i)) & 1u) ? hw[col0 + 8 * j + i].x : 0.f;
+              for (int i = 0; i < 8; ++i) v[i] = ((bits >> (8 * j + i)) & 1u) ? hw[col0 + 8 * j + i].x : 0.f;
               const uint32_t off = (uint32_t)(col0 / 8 + j) * 2048u + rowoff;
               store_a8<false, PREC>(sbase + SM_A_HI + off, sbase + SM_A_LO + off, v);
             }
-            a_ready(piece == 0 ? 0 : (piece == 1 ? 4 : c));
+            a_ready(c == 0 ? (g < 2 ? 0 : 4) : c);
           }
         }
-        float gpe[32];  // this thread's 32 of the 64 PE-gradient entries: columns [32g, 32g+32)
+        float gpe[16];  // this thread's 16 of the 64 PE-gradient entries: columns [16g, 16g+16)
         // wide chain steps: 11 (W8^T) .. 18 (W2^T), masks of the layer whose output the gradient now refers to
 #pragma unroll 1
         for (int s = 11; s <= 18; ++s) {
@@ -934,13 +927,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
           if (s == 14) {
             // the PE part of layer 5 (step 15) lands in 64 columns that the NEXT wide step overwrites: read it first
             wait_acc(15);
-            uint32_t r[32];
-            tmem_ld32(tlane + acc_col(15) + (uint32_t)g * 32u, r);
+            uint32_t r[16];
+            tmem_ld16(tlane + acc_col(15) + (uint32_t)g * 16u, r);
             tmem_wait_ld();
-            pin32(r);
+            pin<16>(r);
             const float inv15 = c_epi[ET_INV_SCALE + 15];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) gpe[i] = __uint_as_float(r[i]) * inv15;
+            for (int i = 0; i < 16; ++i) gpe[i] = __uint_as_float(r[i]) * inv15;
           }
           const int layer = tc_step_layer(s);  // 0-based trunk layer of this transposed weight; gradient is w.r.t. its input
           layer_epilogue(TagChain{}, s, c_epi, d, masks[layer - 1]);
@@ -948,13 +941,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
         // last step 19 (W1^T): PE gradient of layer 1; total PE gradient -> xyz gradient through the PE Jacobian
         wait_acc(19);
         {
-          uint32_t r[32];
-          tmem_ld32(tlane + acc_col(19) + (uint32_t)g * 32u, r);
+          uint32_t r[16];
+          tmem_ld16(tlane + acc_col(19) + (uint32_t)g * 16u, r);
           tmem_wait_ld();
-          pin32(r);
+          pin<16>(r);
           const float inv19 = c_epi[ET_INV_SCALE + 19];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) gpe[i] = fmaf(__uint_as_float(r[i]), inv19, gpe[i]);
+          for (int i = 0; i < 16; ++i) gpe[i] = fmaf(__uint_as_float(r[i]), inv19, gpe[i]);
           float x[3];
           if (P.io.rays != nullptr) {
             const float* rr = P.io.rays + ray * 8;
@@ -965,32 +958,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) x[c] = __ldg(P.io.x + p * P.io.x_stride + c);
           }
-          float dx[3] = {0.f, 0.f, 0.f};
-          const int K0 = 32 * g;
+          float dx[4] = {0.f, 0.f, 0.f, 0.f};
+          const int K0 = 16 * g;
           if (g == 0) { dx[0] = gpe[0]; dx[1] = gpe[1]; dx[2] = gpe[2]; }
 #pragma unroll
           for (int f = 0; f < NFREQ_XYZ; ++f) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
               const int ks = 3 + 6 * f + c, kc = ks + 3;  // PE columns of sin(2^f x_c) and cos(2^f x_c)
-              const bool need_s = (ks >= K0 && ks < K0 + 32), need_c = (kc >= K0 && kc < K0 + 32);
+              const bool need_s = (ks >= K0 && ks < K0 + 16), need_c = (kc >= K0 && kc < K0 + 16);
               if (need_s || need_c) {
                 const float fr = (float)(1 << f);
                 const float2 sc = sincos_pe(fr * x[c]);
-                if (need_s) dx[c] = fmaf(fr * gpe[(ks - K0) & 31], sc.y, dx[c]);    // d sin = +f cos
-                if (need_c) dx[c] = fmaf(-fr * gpe[(kc - K0) & 31], sc.x, dx[c]);   // d cos = -f sin
+                if (need_s) dx[c] = fmaf(fr * gpe[(ks - K0) & 15], sc.y, dx[c]);    // d sin = +f cos
+                if (need_c) dx[c] = fmaf(-fr * gpe[(kc - K0) & 15], sc.x, dx[c]);   // d cos = -f sin
               }
             }
           }
-          if (g == 1) part[row] = make_float4(dx[0], dx[1], dx[2], 0.f);
-          epi_bar_sync(1);
+          xreduce(dx, 384u);   // [384,512) is idle after the chain (step 19 sits in [256,320))
           if (g == 0) {
-            const float4 o = part[row];
-            const float a = -(dx[0] + o.x), b = -(dx[1] + o.y), cc = -(dx[2] + o.z);
+            const float a = -dx[0], b = -dx[1], cc = -dx[2];
             const float nn = sqrtf(fmaxf(a * a + b * b + cc * cc, FP32_EPS));  // utils/func.py:5-7
             o_an[0] = a / nn; o_an[1] = b / nn; o_an[2] = cc / nn;
           }
-          epi_bar_sync(2);
         }
       }
 
@@ -1058,8 +1048,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
           float x[3];
 #pragma unroll
           for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(__ldg(rr + c), __fmul_rn(__ldg(rr + 3 + c), z));
-          if (g == 0) pe_fill<0, PREC>(x, sbase + SM_PE_HI, sbase + SM_PE_LO, rowoff);
-          else        pe_fill<1, PREC>(x, sbase + SM_PE_HI, sbase + SM_PE_LO, rowoff);
+          pe_point(x);
         } else if (warp == 4 && lane == 0) {
           *f_stop = 1;
         }
