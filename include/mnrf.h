@@ -193,8 +193,12 @@ typedef struct mnrf_level_out {
   float* normal_fine;          /* (n,Sc+Ni,3) or NULL */
 } mnrf_level_out;
 
-/* bytes of scratch mnrf_render_level needs for n rays */
+/* bytes of scratch mnrf_render_level needs for n rays: upper bound for any field pair ... */
 int64_t mnrf_level_workspace_bytes(int n, const mnrf_level_cfg* cfg);
+/* ... and the exact amount for these fields (a pass that composites inside the field kernel needs no per-point records;
+ * with_sigma_noise != 0: the call will pass noise tensors, which selects the unfused compositor when noise_std != 0) */
+int64_t mnrf_level_workspace_bytes_for(const mnrf_field* coarse, const mnrf_field* fine, int n, const mnrf_level_cfg* cfg,
+                                       int with_sigma_noise);
 
 /* fine may be NULL (coarse only, or only_one_field).  z_steps (n_samples), u_det (n_importance) are the
  * torch.linspace tables (device).  All launches go to `stream`; nothing synchronises. */

@@ -97,6 +97,7 @@ _SIGS = {
     "mnrf_composite": (c_int, [c_float_p, c_float_p, c_float_p, c_int, c_float_p, c_float_p, c_float_p, C.c_float,
                                c_int, c_int, c_int, C.POINTER(CompositeOut), C.c_void_p]),
     "mnrf_level_workspace_bytes": (C.c_int64, [c_int, C.POINTER(LevelCfg)]),
+    "mnrf_level_workspace_bytes_for": (C.c_int64, [C.c_void_p, C.c_void_p, c_int, C.POINTER(LevelCfg), c_int]),
     "mnrf_render_level": (c_int, [C.c_void_p, C.c_void_p, c_float_p, c_int, C.POINTER(LevelCfg), C.POINTER(LevelRng),
                                   c_float_p, c_float_p, C.c_void_p, C.c_int64, C.POINTER(LevelOut), C.c_void_p]),
     "mnrf_render_level_host": (c_int, [C.c_void_p, C.c_void_p, c_float_p, c_int, C.POINTER(LevelCfg), c_float_p,

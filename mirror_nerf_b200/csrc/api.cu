@@ -394,11 +394,35 @@ int mnrf_composite(const float* rays, const float* z, const float* sigma, int si
                           S_(stream));
 }
 
+// scratch layout of one level: [dirbias n x 128][coarse records][second-pass records][work counter 256 B].  A sigma-only coarse
+// pass keeps one float per point, a full pass 8 floats per point unless it composites inside the field kernel (no records).
+struct LevelScratch { size_t dirbias, buf_c, buf_f, total; };
+static LevelScratch level_scratch(const mnrf_field* coarse, const mnrf_field* fine, int n, const mnrf_level_cfg* cfg, bool has_noise) {
+  const size_t Sc = cfg->n_samples, Sf = cfg->n_samples + cfg->n_importance;
+  const bool sig_only = cfg->test_time && fine != nullptr;
+  const mnrf_field* second = cfg->rerun_coarse_on_fine ? coarse : fine;
+  const bool two = cfg->n_importance > 0 && second != nullptr;
+  const float* noise = has_noise ? reinterpret_cast<const float*>(1) : nullptr;
+  // without the field handles (mnrf_level_workspace_bytes) assume the unfused sequence: an upper bound
+  const bool fuse_c = coarse != nullptr && !sig_only && can_fuse_composite(coarse, cfg, noise, (int)Sc);
+  const bool fuse_f = coarse != nullptr && two && can_fuse_composite(second, cfg, noise, (int)Sf);
+  LevelScratch L;
+  L.dirbias = align256(sizeof(float) * (size_t)n * WH);
+  L.buf_c = (coarse != nullptr && sig_only) ? align256(sizeof(float) * (size_t)n * Sc) : (fuse_c ? 0 : align256(sizeof(float) * (size_t)n * Sc * 8));
+  L.buf_f = (cfg->n_importance > 0 && (coarse == nullptr || two)) ? (fuse_f ? 0 : align256(sizeof(float) * (size_t)n * Sf * 8)) : 0;
+  L.total = L.dirbias + L.buf_c + L.buf_f + 256;
+  return L;
+}
+
 int64_t mnrf_level_workspace_bytes(int n, const mnrf_level_cfg* cfg) {
   if (cfg == nullptr || n < 0) return -1;
-  const size_t Sc = cfg->n_samples, Sf = cfg->n_samples + cfg->n_importance;
-  return (int64_t)(align256(sizeof(float) * (size_t)n * WH) + align256(sizeof(float) * (size_t)n * Sc * 8) +
-                   (cfg->n_importance > 0 ? align256(sizeof(float) * (size_t)n * Sf * 8) : 0) + 256 /* work counter */);
+  return (int64_t)level_scratch(nullptr, nullptr, n, cfg, true).total;
+}
+
+int64_t mnrf_level_workspace_bytes_for(const mnrf_field* coarse, const mnrf_field* fine, int n, const mnrf_level_cfg* cfg,
+                                       int with_sigma_noise) {
+  if (cfg == nullptr || coarse == nullptr || n < 0) return -1;
+  return (int64_t)level_scratch(coarse, fine, n, cfg, with_sigma_noise != 0 && cfg->noise_std != 0.f).total;
 }
 
 int mnrf_render_level(const mnrf_field* coarse, const mnrf_field* fine, const float* rays, int n,
@@ -420,8 +444,11 @@ int mnrf::render_level(const mnrf_field* coarse, const mnrf_field* fine, const f
   const int Sc = cfg->n_samples, Ni = cfg->n_importance, Sf = Sc + Ni;
   MNRF_REQUIRE(Sc >= 1 && Ni >= 0, "render_level: bad sample counts");
   MNRF_REQUIRE((long long)n * Sf < (1ll << 31), "render_level: too many points; split the ray batch");
-  MNRF_REQUIRE(workspace != nullptr && workspace_bytes >= mnrf_level_workspace_bytes(n, cfg),
-               "render_level: workspace too small");
+  static const mnrf_level_rng no_rng0 = {nullptr, nullptr, nullptr, nullptr};
+  const bool has_noise = (rng != nullptr ? rng : &no_rng0)->noise_coarse != nullptr || (rng != nullptr ? rng : &no_rng0)->noise_fine != nullptr;
+  const LevelScratch LS = level_scratch(coarse, fine, n, cfg, has_noise && cfg->noise_std != 0.f);
+  MNRF_REQUIRE(workspace != nullptr && workspace_bytes >= (int64_t)LS.total,
+               "render_level: workspace too small (%lld bytes needed: mnrf_level_workspace_bytes_for)", (long long)LS.total);
   MNRF_REQUIRE(out->z_coarse && out->coarse.weights && out->coarse.opacity, "render_level: coarse outputs missing");
   MNRF_REQUIRE(cfg->dir_source == nullptr || coarse->kind == 0, "render_level: view_dir needs the MLP field");
   const float* dir_src = cfg->dir_source != nullptr ? cfg->dir_source : rays;   // rendering.py:276 view_dir
@@ -429,10 +456,10 @@ int mnrf::render_level(const mnrf_field* coarse, const mnrf_field* fine, const f
   if (rng == nullptr) rng = &no_rng;
   cudaStream_t st = S_(stream);
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
-  float* dirbias = reinterpret_cast<float*>(ws); ws += align256(sizeof(float) * (size_t)n * WH);
-  float* buf_c = reinterpret_cast<float*>(ws);   ws += align256(sizeof(float) * (size_t)n * Sc * 8);
-  float* buf_f = reinterpret_cast<float*>(ws);
-  int* counter = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(workspace) + mnrf_level_workspace_bytes(n, cfg) - 256);
+  float* dirbias = reinterpret_cast<float*>(ws); ws += LS.dirbias;
+  float* buf_c = reinterpret_cast<float*>(ws);   ws += LS.buf_c;
+  float* buf_f = reinterpret_cast<float*>(ws);   ws += LS.buf_f;
+  int* counter = reinterpret_cast<int*>(ws);
   const int impl = cfg->impl;
 
   // ---- coarse pass (rendering.py:271-305) ----

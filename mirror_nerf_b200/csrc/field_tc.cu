@@ -55,7 +55,7 @@ constexpr uint32_t SM_TOTAL = SM_FUSE + 256;             // 231936 <= 232448
 constexpr int BAR_W_FULL = 0;    // [8]
 constexpr int BAR_W_EMPTY = 8;   // [8]
 constexpr int BAR_PE = 16;       // PE chunk written (16 warp arrivals)
-constexpr int BAR_A = 17;        // [5] A columns written: [0] cols 0-31 and [4] cols 32-63 (8 warp arrivals each), [1..3] 64-col chunks 1..3 (16)
+constexpr int BAR_A = 17;        // [5] A columns written (4 warp arrivals: one column group): [0] cols 0-31, [4] cols 32-63, [1..3] 64-col chunks 1..3
 constexpr int BAR_ACC = 22;      // [4] accumulator of a GEMM step complete (tcgen05.commit)
 constexpr int BAR_GO = 26;       // fused mode: "next tile is decided" for the weight producer (8 warp arrivals, like BAR_PE)
 constexpr int BAR_TMEM_SLOT = 30;
@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
     for (int i = 0; i < 8; ++i) { mbar_init(bar(BAR_W_FULL + i), 1); mbar_init(bar(BAR_W_EMPTY + i), 1); }
     mbar_init(bar(BAR_PE), 16);   // one arrival per epilogue warp
     mbar_init(bar(BAR_GO), 16);
-    for (int i = 0; i < 5; ++i) mbar_init(bar(BAR_A + i), (i == 0 || i == 4) ? 8 : 16);  // halves of chunk 0: two column groups each
+    for (int i = 0; i < 5; ++i) mbar_init(bar(BAR_A + i), 4);  // a chunk (or half of chunk 0) is written by one column group: 4 warps
     for (int i = 0; i < 4; ++i) mbar_init(bar(BAR_ACC + i), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -759,45 +759,48 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
     auto lo_addr = [&](uint32_t off) {
       return PREC == 2 ? sbase + SM_A_LO + ((off - rowoff) >> 1) + rowoff : sbase + SM_A_LO + off;
     };
-    // One 256-wide layer: this warp owns columns [64c + 16g, 64c + 16g + 16) of every 64-column chunk c, chunks in K order, the
-    // next chunk's TMEM load in flight while the current one is converted.  Chunk 0 is signalled in two 32-column halves
-    // (groups 0,1 -> BAR_A[0], groups 2,3 -> BAR_A[4]) so that the next layer's MMAs start after a 16-column piece per warp.
-    // mk: this thread's two 32-bit relu' words of the layer (chunk c -> bits [16 (c & 1), +16) of mk[c >> 1])
+    // One 256-wide layer: column group g owns the whole 64-column K chunk g of the next layer's A operand (its 32 rows of it),
+    // converted as four 16-column pieces with the next piece's TMEM load in flight.  The four chunks are therefore produced
+    // CONCURRENTLY by the four groups instead of one after the other by everybody: the next layer's MMAs find chunk 0 after two
+    // pieces of one warp and all other chunks shortly after (measured before: the serial chain of five load -> convert ->
+    // proxy fence -> barrier rounds per layer, not instruction issue, set the layer period).  Group 0 signals its chunk in two
+    // 32-column halves (BAR_A[0], BAR_A[4]); groups 1..3 signal BAR_A[g] once.
+    // mk: this thread's two 32-bit relu' words of the layer (piece j -> bits [16 (j & 1), +16) of mk[j >> 1])
     auto layer_epilogue = [&](auto tag, int s, const float* bias256, float (&d)[4], uint32_t (&mk)[2]) {
       constexpr bool RELU = decltype(tag)::relu, DOTS = decltype(tag)::dots, WRITE_A = decltype(tag)::write_a;
       constexpr int MASK = decltype(tag)::mask;
       if (MASK == 1) { mk[0] = 0u; mk[1] = 0u; }
-      const float4* b4 = reinterpret_cast<const float4*>(bias256) + 4 * g;
+      const float4* b4 = reinterpret_cast<const float4*>(bias256) + 16 * g;
       // everything that does not depend on the accumulator is fetched before waiting for it
       const float inv = c_epi[ET_INV_SCALE + s] * (PREC == 2 ? 0.03125f : 1.f);  // tc2 blobs carry 2^5 more scale (pack.cu)
       float4 b[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) b[i] = b4[i];
       wait_acc(s);
-      const uint32_t tcol = tlane + acc_col(s) + 16u * (uint32_t)g;
+      const uint32_t tcol = tlane + acc_col(s) + 64u * (uint32_t)g;
       uint32_t ra[16], rb[16];
       tmem_ld16(tcol, ra);
       tmem_wait_ld();
-      tmem_ld16(tcol + 64u, rb);  // chunk 1
+      tmem_ld16(tcol + 16u, rb);  // piece 1
       pin<16>(ra);
       {
-        const uint32_t off = (uint32_t)(2 * g) * 2048u + rowoff;
-        epi_cols<16, RELU, DOTS, WRITE_A, PREC, MASK>(ra, b, inv, sbase + SM_A_HI + off, lo_addr(off), headw + 16 * g, d, mk[0], 0);
-        if (WRITE_A) a_ready(g < 2 ? 0 : 4);
+        const uint32_t off = (uint32_t)(8 * g) * 2048u + rowoff;
+        epi_cols<16, RELU, DOTS, WRITE_A, PREC, MASK>(ra, b, inv, sbase + SM_A_HI + off, lo_addr(off), headw + 64 * g, d, mk[0], 0);
       }
 #pragma unroll
-      for (int c = 1; c < 4; ++c) {
+      for (int j = 1; j < 4; ++j) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) b[i] = b4[16 * c + i];
-        tmem_wait_ld();  // the load of chunk c (issued one iteration ago) has landed
-        if (c < 3) {     // next chunk's load flies while this chunk is converted
-          if (c & 1) tmem_ld16(tcol + (uint32_t)(c + 1) * 64u, ra);
-          else       tmem_ld16(tcol + (uint32_t)(c + 1) * 64u, rb);
+        for (int i = 0; i < 4; ++i) b[i] = b4[4 * j + i];
+        tmem_wait_ld();  // the load of piece j (issued one iteration ago) has landed
+        if (j < 3) {     // next piece's load flies while this piece is converted
+          if (j & 1) tmem_ld16(tcol + (uint32_t)(j + 1) * 16u, ra);
+          else       tmem_ld16(tcol + (uint32_t)(j + 1) * 16u, rb);
         }
-        const uint32_t off = (uint32_t)(8 * c + 2 * g) * 2048u + rowoff;
-        if (c & 1) { pin<16>(rb); epi_cols<16, RELU, DOTS, WRITE_A, PREC, MASK>(rb, b, inv, sbase + SM_A_HI + off, lo_addr(off), headw + 64 * c + 16 * g, d, mk[c >> 1], 16 * (c & 1)); }
-        else       { pin<16>(ra); epi_cols<16, RELU, DOTS, WRITE_A, PREC, MASK>(ra, b, inv, sbase + SM_A_HI + off, lo_addr(off), headw + 64 * c + 16 * g, d, mk[c >> 1], 16 * (c & 1)); }
-        if (WRITE_A) a_ready(c);
+        const uint32_t off = (uint32_t)(8 * g + 2 * j) * 2048u + rowoff;
+        if (j & 1) { pin<16>(rb); epi_cols<16, RELU, DOTS, WRITE_A, PREC, MASK>(rb, b, inv, sbase + SM_A_HI + off, lo_addr(off), headw + 64 * g + 16 * j, d, mk[j >> 1], 16 * (j & 1)); }
+        else       { pin<16>(ra); epi_cols<16, RELU, DOTS, WRITE_A, PREC, MASK>(ra, b, inv, sbase + SM_A_HI + off, lo_addr(off), headw + 64 * g + 16 * j, d, mk[j >> 1], 16 * (j & 1)); }
+        if (WRITE_A && g == 0 && j == 1) a_ready(0);   // columns 0..31: the next layer's first K32 chunk
+        if (WRITE_A && j == 3) a_ready(g == 0 ? 4 : g);
       }
     };
 
@@ -905,8 +908,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
         {
           const float4* hw = headw;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {  // same column ownership as layer_epilogue
-            const int col0 = 64 * c + 16 * g;
+          for (int c = 0; c < 4; ++c) {  // same column ownership as layer_epilogue: piece c of chunk g
+            const int col0 = 64 * g + 16 * c;
             const uint32_t bits = masks[7][c >> 1] >> (16 * (c & 1));
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -916,7 +919,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
               const uint32_t off = (uint32_t)(col0 / 8 + j) * 2048u + rowoff;
               store_a8<false, PREC>(sbase + SM_A_HI + off, sbase + SM_A_LO + off, v);
             }
-            a_ready(c == 0 ? (g < 2 ? 0 : 4) : c);
+            if (g == 0 && c == 1) a_ready(0);
+            if (c == 3) a_ready(g == 0 ? 4 : g);
           }
         }
         float gpe[16];  // this thread's 16 of the 64 PE-gradient entries: columns [16g, 16g+16)

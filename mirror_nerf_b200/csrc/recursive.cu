@@ -264,7 +264,7 @@ int64_t plan(Ctx& C, long long slab) {
   }
   C.nrm_c = C.lc.compute_normal && !(C.lc.test_time && C.fine != nullptr) ? C.bump.take<float>(R * Sc * 3) : nullptr;
   C.nrm_f = C.lc.compute_normal && C.second ? C.bump.take<float>(R * Sf * 3) : nullptr;
-  C.level_ws_bytes = mnrf_level_workspace_bytes((int)C.rows_max, &C.lc);
+  C.level_ws_bytes = mnrf_level_workspace_bytes_for(C.coarse, C.fine, (int)C.rows_max, &C.lc, 0);
   C.level_ws = C.bump.take<uint8_t>((size_t)C.level_ws_bytes);
   C.node = 0;
   const bool was_dry = C.dry;

@@ -289,7 +289,8 @@ def render_rays(models, embeddings, rays, N_samples=64, use_disp=False, perturb=
         ws = None
         for lo in range(0, n, step):
             m = min(step, n - lo)
-            need = int(lib.mnrf_level_workspace_bytes(m, C.byref(cfg)))
+            need = int(lib.mnrf_level_workspace_bytes_for(coarse.handle, None if fine_for_lib is None else fine_for_lib.handle,
+                                                          m, C.byref(cfg), int(noise_c is not None or noise_f is not None)))
             if ws is None or ws.numel() < need:
                 ws = torch.empty(need, device=dev, dtype=torch.uint8)
             out = _lib.LevelOut(
