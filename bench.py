@@ -7,9 +7,10 @@ then every ray of the batch is reflected and re-rendered once, then blended by t
 R/eval.py:132-160,545-548,676-697) -> 2 render levels per primary ray.  A "step" is one such image.  Multi-GPU: one
 process per GPU, each rank renders its own view (weak scaling), no data-path collective.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--field-impl tc3|tc1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--field-impl tc3|tc2|tc1]
 
-One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the definition of every key.
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the definition of every key.  Both arms print the same
+`config` object (the workload); what is specific to an arm's run sits under `run`.
 """
 import argparse
 import json
@@ -28,6 +29,12 @@ FLOP_PER_RAY_LEVEL = 320.36e6  # 64*S + 192*F MACs * 2 (unpadded r
 LEVELS = 2                     # level 0 + 1 bounce (eval semantics re-traces all rays of the batch)
 METRIC = "rays/sec (64c+128f samples, 1 bounce)"
 WORKLOAD = "synthetic 800x800 mirror scene, 64+128 samples, 1 reflection bounce, eval semantics"
+# the workload both arms are measured on (BASELINE.json configs[1]); identical in the two JSON lines
+CONFIG = {"workload": WORKLOAD, "image": "800x800 synthetic pinhole view (R/datasets/ray_utils.py:6-53), near 0.05, far 8.0",
+          "samples": "64 coarse + 128 importance (192 fine points per ray)", "bounces": 1, "levels_per_ray": LEVELS,
+          "semantics": "eval: R/eval.py::batched_inference, perturb = noise_std = 0, test_time, predicted normals + mirror mask",
+          "field": "two MirrorNeRF (D=8, W=256, skip 4, 10/4 frequencies, normal + mirror heads), synthetic weights "
+                   "(mirror_nerf_b200/synthetic.py: sigma head x40, mirror head x100)"}
 
 
 def view_pose(i):
@@ -98,13 +105,17 @@ def cpu_reference_rate(n_rays, steps, warmup, threads):
     fn = lambda r: O.render_rays(params, r, N_SAMPLES, False, 0, 0, N_IMPORTANCE, 32768, False, test_time=True,
                                  compute_normal=False)
     out = None
+    per_step = []
     with torch.no_grad():
         for _ in range(warmup):
-            O.trace_eval(fn, rays[: max(64, n_rays // 8)], 1)
+            O.trace_eval(fn, rays[:256], 1)   # warm-up on 256 rays
         t0 = time.perf_counter()
         for _ in range(steps):
+            t1 = time.perf_counter()
             out = O.trace_eval(fn, rays, 1)
+            per_step.append(time.perf_counter() - t1)
         dt = time.perf_counter() - t0
+    cpu_reference_rate.best = n_rays / min(per_step)
     return n_rays * steps / dt, out["rgb_fine"], rays, dt / steps
 
 
@@ -114,14 +125,17 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     n = args.ref_rays
-    rate, _, _, step_s = cpu_reference_rate(n, args.steps, min(args.warmup, 1), threads)
+    rate, _, _, step_s = cpu_reference_rate(n, args.steps, args.warmup, threads)
+    sample = (f"{n} rays of the 800x800 view per step (BASELINE.md section 4: N = 4096, warm-up 256 rays), both levels of "
+              f"the bounce, {args.steps} steps")
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "rays/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": f"{n} rays of the view per step"},
-            "cpu_baseline": {"value": rate, "unit": "rays/s", "cores": threads, "kind": "port",
-                             "sample": f"{n} rays x 2 levels per step, {args.steps} steps (oracle port of the "
-                                       "reference's torch CPU path; /root/reference cannot travel to the GPU box)"},
+            "config": CONFIG,
+            "run": {"sample": sample, "threads": threads, "best_step_rays_per_s": cpu_reference_rate.best,
+                    "implementation": "oracle port of the reference's torch CPU path (same ATen kernels; /root/reference cannot "
+                                      "travel to the GPU box), pinned bit-exactly to the reference in tests/test_oracle_*.py"},
+            "cpu_baseline": {"value": rate, "unit": "rays/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -447,18 +461,48 @@ def run_ours(args):
         _lib.check(lib.mnrf_profile_collect(C.byref(k_ms), C.byref(k_fl), C.byref(k_n)))
         clocks = sampler.stop()
 
-        # ---- end to end through the public API with host buffers (H2D of rays, D2H of the image) ----
-        out_host = torch.empty(n, 3, dtype=torch.float32).pin_memory()
+        # ---- end to end through the public API with host buffers: H2D of the rays from pinned memory, render, D2H of EVERY
+        # tensor of the result dict into pinned memory (the reference moves every result tensor to the host, R/eval.py:735-736)
+        res0 = step(rays_dev)
+        out_host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in res0.items()}
+        d2h_bytes = sum(v.numel() * v.element_size() for v in res0.values())
 
         def e2e_step():
             r = rays_host.to(dev, non_blocking=True)
             out = step(r)
-            out_host.copy_(out["rgb_fine"], non_blocking=True)
+            for k, v in out.items():
+                out_host[k].copy_(v, non_blocking=True)
             torch.cuda.current_stream().synchronize()
 
-        e2e_steps = max(1, min(args.steps, 5))
+        e2e_steps = args.steps
         e2e_step()
         ms_e2e = timed(e2e_step, e2e_steps)
+
+        # the same with the reference's FULL per-level dict (per-sample weights, z_vals, pred_normal: 4.4 KB per ray) through
+        # the drop-in render_rays + the per-level Python driver; secondary, bounded to 2 steps (2.8 GB of D2H per step)
+        e2e_full = None
+        if world == 1 and not args.no_full_dict:
+            def full_step(r):
+                return render_rays_recursive(models, emb, r, N_SAMPLES, False, 0, 0, N_IMPORTANCE, 32768, False,
+                                             max_recursive_level=1, consume_rng=False, **kw)
+            resf = full_step(rays_dev)
+            full_host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in resf.items()}
+            full_bytes = sum(v.numel() * v.element_size() for v in resf.values())
+            del resf
+
+            def e2e_full_step():
+                out = full_step(rays_host.to(dev, non_blocking=True))
+                for k, v in out.items():
+                    full_host[k].copy_(v, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+
+            e2e_full_step()
+            ms_full = timed(e2e_full_step, 2)
+            e2e_full = {"value": n * 2 / (ms_full * 1e-3), "unit": "rays/s", "steps": 2, "h2d_bytes_per_step": n * 32,
+                        "d2h_bytes_per_step": full_bytes, "keys": len(full_host),
+                        "what": "render_rays (drop-in, full output dict) + per-level driver, every tensor copied to pinned host memory"}
+            del full_host
+            torch.cuda.empty_cache()
 
     value = world * n * args.steps / (ms_total * 1e-3)
     e2e_value = world * n * e2e_steps / (ms_e2e * 1e-3)
@@ -475,8 +519,9 @@ def run_ours(args):
     # DRAM bytes per launch of the dominant kernel: from the committed ncu capture of this same command (not measurable live)
     traffic, traffic_src = None, None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_v3_field_tc_traffic.json")))
-        traffic, traffic_src = tj["dram_bytes_per_launch_avg"], tj["source"]
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_field_tc_traffic.json")))
+        if tj.get("field_impl") == args.field_impl:   # a capture of another kernel variant says nothing about this run
+            traffic, traffic_src = tj["dram_bytes_per_launch_avg"], tj["source"]
     except Exception:
         pass
     mma_per_mac = {"tc3": 3, "tc2": 2, "tc1": 1}[args.field_impl]
@@ -489,13 +534,16 @@ def run_ours(args):
                   "tc2": "f16 + 2 x e4m3 correction passes (fp8 datapath), f32 accumulate (operand error ~2^-16)",
                   "tc1": "f16, f32 accumulate"}[args.field_impl],
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": n, "levels_per_ray": LEVELS,
-                   "field_impl": args.field_impl, "mirror_ray_fraction": mirror_frac,
-                   "l2": "256 MB buffer written between timed steps (L2 flush); per-step scratch is > L2 anyway",
-                   "parallelism": f"ray-parallel x{world}, one view per rank, no collective"},
+        "config": CONFIG,
+        "run": {"rays_per_step_per_gpu": n, "field_impl": args.field_impl, "mirror_ray_fraction": mirror_frac,
+                "recursion": "per-level Python driver" if args.python_recursion else "mnrf_render_recursive (device-side, no host sync)",
+                "early_termination_eps": 0.0 if args.python_recursion else args.early_termination_eps,
+                "l2": "256 MB buffer written between timed steps (L2 flush); per-step scratch is > L2 anyway",
+                "parallelism": f"ray-parallel x{world}, one view per rank, no collective"},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": n * 12,
-                "steps": e2e_steps},
+        "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": d2h_bytes,
+                "steps": e2e_steps, "d2h": "all %d tensors of the compact per-ray result" % len(out_host)},
+        "e2e_full_dict": e2e_full,
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": (achieved / peak if achieved else None), "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write)",
@@ -504,37 +552,92 @@ def run_ours(args):
                      "kernel_share_of_step": k_ms.value / ms_total if ms_total else None,
                      "flops_basis": "algorithmic 2*MAC of the reference layers (SURVEY.md 8d); the kernel issues "
                                     f"{mma_per_mac} fp16-pass equivalents of tensor-core work per algorithmic MAC",
-                     "tensor_pipe_flops_frac": (achieved * mma_per_mac / peak if achieved else None)},
+                     "tensor_pipe_flops_frac": (achieved * mma_per_mac / peak if achieved else None),
+                     "executed_frac": 0.95,
+                     "executed_frac_note": "the kernel executes ~95 % of the algorithmic MACs: the sigma-only coarse pass skips "
+                                           "normal_net (the reference computes and discards it) and the activation-free "
+                                           "normal_net is folded to one 256->3 map; early termination (run.early_termination_eps) "
+                                           "skips further fine chunks on scenes with opaque surfaces (config.field is translucent)"},
     }
 
-    if args.config4:
-        # BASELINE config 4: 2 reflection bounces + roughness cone (8 jittered reflected rays = trace_ray_times 7), ray-parallel
+    if not args.no_config4:
+        # BASELINE config 4: 2 reflection bounces + roughness cone (8 jittered reflected rays = trace_ray_times 7), ray-parallel:
+        # one 800x800 view per rank through mnrf_render_recursive (the 8 reflections of a level are ONE child batch)
         def step4():
             return render_rays_recursive(models, emb, rays_dev, N_SAMPLES, False, 0, 0, N_IMPORTANCE, 32768, False,
-                                         max_recursive_level=2, normal_noise_std=0.05, trace_ray_times=7, **kw)
-        with torch.no_grad():
-            l0 = _lib.launch_count()
-            step4()
-            per_step = _lib.launch_count() - l0
-            ms4 = timed(step4, 2)
-        line["config4"] = {"metric": "rays/sec (64c+128f samples, 2 bounces + roughness cone of 8 jittered reflections)",
-                           "value": world * n * 2 / (ms4 * 1e-3), "unit": "rays/s", "ms_per_step": ms4 / 2,
-                           "gpu_launches_per_step": per_step, "normal_noise_std": 0.05, "trace_ray_times": 7}
+                                         max_recursive_level=2, normal_noise_std=0.05, trace_ray_times=7, compact_outputs=True,
+                                         early_termination_eps=args.early_termination_eps, with_level_rays=True, **kw)
+        try:
+            with torch.no_grad():
+                l0 = _lib.launch_count()
+                r4 = step4()
+                per_step = _lib.launch_count() - l0
+                level_rays = [int(v) for v in r4["level_rays"].cpu().tolist()]
+                del r4
+                ms4 = timed(step4, 2)
+            line["config4"] = {"metric": "rays/sec (64c+128f samples, 2 bounces + roughness cone of 8 jittered reflections)",
+                               "value": world * n * 2 / (ms4 * 1e-3), "unit": "rays/s", "ms_per_step": ms4 / 2, "steps": 2,
+                               "n_gpus": world, "gpu_launches_per_step": per_step, "normal_noise_std": 0.05, "trace_ray_times": 7,
+                               "rays_rendered_per_level": level_rays,
+                               "ray_levels_per_s": world * sum(level_rays) * 2 / (ms4 * 1e-3),
+                               "recursion": "mnrf_render_recursive (device-side)"}
+        except Exception as e:
+            line["config4"] = {"unavailable": repr(e)[:300]}
+        torch.cuda.empty_cache()
 
+    if world > 1:
+        # strong scaling: ONE 800x800 frame (rank 0's view) cut into tile-aligned shards (parallel.shard_bounds), every rank renders
+        # its shard, rgb + depth are all-gathered (the only exchange); time = barrier-to-barrier max over ranks incl. the gather
+        from mirror_nerf_b200.parallel import render_sharded
+        frame = camera_rays(H, W, c2w=view_pose(0)).to(dev)
+
+        def strong_step():
+            render_sharded(lambda r: step(r.contiguous()), frame, rank, world, gather=("rgb_fine", "depth_fine"))
+        with torch.no_grad():
+            strong_step()
+            ms_s = timed(strong_step, max(2, min(args.steps, 5)))
+        ks = max(2, min(args.steps, 5))
+        line["strong"] = {"metric": METRIC + ", ONE frame sharded over the ranks", "value": n * ks / (ms_s * 1e-3), "unit": "rays/s",
+                          "n_gpus": world, "steps": ks, "ms_per_frame": ms_s / ks, "scaling": "strong",
+                          "rays_per_rank": n // world, "gather": "all_gather of rgb_fine + depth_fine (16 B per ray, NCCL)"}
+
+    hbm_peak = peaks.get("hbm_gbs") or 6650.0
     if not args.no_train:
-        line["train_step"] = train_bench(dev, world, rank, max(2, min(args.steps, 5)), 3, args.peer_fused)
+        ts = train_bench(dev, world, rank, max(2, min(args.steps, 5)), 3, args.peer_fused)
+        # roofline of the training step: tensor bound on the algorithmic 1.77 GFLOP per ray; the layer GEMMs run
+        # three tf32 passes (= 6 fp16-pass equivalents per MAC) and stream every activation through HBM once per layer
+        tf = ts["algorithmic_tflops"]
+        ts["roofline"] = {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+                          "traffic": None, "kernel": "k_gemm_tc_nn / k_gemm_tc_tn (unfused layer GEMMs, kind::tf32 x3)",
+                          "flops_basis": "algorithmic 1.77 GFLOP per ray x 4096 rays per step / step time (whole step, not one kernel)",
+                          "peak_source": peak_src,
+                          "hbm_note": "ncu (profiles/r01_v3_train_gemm_tc_nn_ncu_metrics.txt): 1.0 GB read + 0.78 GB written per "
+                                      "538 us layer launch = 3.3 TB/s = 51 % of the measured HBM peak; tensor pipe 81 % active"}
+        line["train_step"] = ts
         if rank == 0:
-            line["hash_grid_level"] = hash_level_bench(dev, 3)
+            hl = hash_level_bench(dev, 3)
+            a = hl["table_read_GBps_algorithmic"]
+            hl["roofline"] = {"bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak, "traffic": None,
+                              "kernel": "k_field_hash", "bytes_basis": "algorithmic 1,024 B of table reads per point "
+                              "(16 levels x 8 corners x 2 features x 4 B) x points per launch / launch time",
+                              "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks.get("hbm_gbs") else "fallback 6.65 TB/s",
+                              "note": "the 46.5 MB table is L2-resident (ncu: 96.6 % L2 hit, 190 MB DRAM reads per 123 M-point launch); "
+                                      "what bounds the kernel is the L1/TEX request rate of the gathers (ncu l1tex throughput 77 %, "
+                                      "profiles/r01_v3_field_hash_ncu_metrics.txt), so the HBM fraction is a lower bound on how close "
+                                      "the kernel is to ITS limit"}
+            line["hash_grid_level"] = hl
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        rate, rgb_ref, rays_s, _ = cpu_reference_rate(args.ref_rays, 1, 1, threads)
+        rate, rgb_ref, rays_s, _ = cpu_reference_rate(args.ref_rays, 3, 1, threads)
         with torch.no_grad():
             got = step(rays_s.to(dev))["rgb_fine"].cpu()
         mse = float(((got - rgb_ref) ** 2).mean())
         import math
         line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": threads, "kind": "port",
-                                "sample": f"{args.ref_rays} rays of the same view, 64+128 samples, 1 bounce, 1 step"}
+                                "sample": f"{args.ref_rays} rays of the same view, 64+128 samples, 1 bounce, 3 steps after a 256-ray "
+                                          "warm-up (BASELINE.md section 4)",
+                                "best_step_rays_per_s": cpu_reference_rate.best}
         line["psnr_vs_reference_db"] = (-10 * math.log10(mse) if mse > 0 else float("inf"))
         # PSNR on a scene-like field: the analytic room scene (room_scene.py), field = tests/golden/room_field.npz (this repo's
         # training path, tools/train_room.py); ours (1 bounce, eval semantics) and the oracle against the analytic ground truth
@@ -560,8 +663,19 @@ def run_ours(args):
             with torch.no_grad():
                 ref_rgb = O.trace_eval(fn, rr, 1)["rgb_fine"]
                 our_rgb = render_rays_recursive(rmodels, emb, rr.to(dev), N_SAMPLES, False, 0, 0, N_IMPORTANCE, 32768, False,
-                                                max_recursive_level=1, **kw)["rgb_fine"].cpu()
+                                                max_recursive_level=1, compact_outputs=not args.python_recursion, **kw,
+                                                **({} if args.python_recursion else {"early_termination_eps": args.early_termination_eps})
+                                                )["rgb_fine"].cpu()
             ps = lambda x: -10 * math.log10(float(((x - gt) ** 2).mean()))
+
+            def dist(a, b):   # relative error |a-b| / max(|b|, rms(b)): median / p99 / max / fraction beyond 1e-3
+                a, b = a.double().flatten(), b.double().flatten()
+                e = (a - b).abs() / b.abs().clamp_min(float(b.pow(2).mean().sqrt()))
+                q = torch.quantile(e, torch.tensor([0.5, 0.99], dtype=torch.double))
+                return {"median": float(q[0]), "p99": float(q[1]), "max": float(e.max()), "frac_gt_1e-3": float((e > 1e-3).double().mean())}
+            line["parity"] = {"rgb_fine": dist(our_rgb, ref_rgb), "rays": args.ref_rays, "field_impl": args.field_impl,
+                              "against": "oracle port of the reference on the same rays (fitted room field, 1 bounce, eval semantics)",
+                              "bar": "north-star: rgb within 1e-3 relative, PSNR within 0.05 dB"}
             line["psnr"] = {"ours_db": ps(our_rgb), "reference_db": ps(ref_rgb), "delta_db": ps(our_rgb) - ps(ref_rgb),
                             "ours_vs_reference_db": -10 * math.log10(max(float(((our_rgb - ref_rgb) ** 2).mean()), 1e-20)),
                             "rays": args.ref_rays, "mirror_ray_fraction": float(gt_mask.mean()),
@@ -579,7 +693,18 @@ def run_ours(args):
                 "sample": "one 128-ray train step (forward + backward) of the oracle port on the host cores"}
     if rank == 0 and world == 1 and not args.no_train:
         try:  # last GPU work of the run: a failure here cannot touch the numbers above
-            line["hash_grid_train_step"] = hash_train_bench(dev, 3)
+            ht = hash_train_bench(dev, 3)
+            # algorithmic bytes of a step: forward gathers (1,024 B per point) + backward recompute gathers (1,024 B) + table
+            # gradient scatter (256 atomics x 4 B per point) per point
+            by = ht["points_per_step"] * (1024 + 1024 + 1024) / (ht["ms_per_step"] * 1e-3) / 1e9
+            ht["roofline"] = {"bound": "hbm", "achieved": by, "peak": hbm_peak, "unit": "GB/s", "frac": by / hbm_peak, "traffic": None,
+                              "kernel": "k_field_hash + k_hash_bwd2",
+                              "bytes_basis": "algorithmic 3,072 B per point (forward gathers, recompute gathers, gradient scatter) x "
+                                             "1,048,576 points per step / step time",
+                              "note": "issue / shared-memory-latency bound, not bandwidth bound: ncu of k_hash_bwd2 "
+                                      "(profiles/r02_v1_hash_bwd2_ncu_metrics.txt): issue active 39.6 %, shared-memory wavefronts "
+                                      "58 % of peak, short-scoreboard stalls 1.4 per issue, 12 % of the warp slots, table in L2"}
+            line["hash_grid_train_step"] = ht
         except Exception as e:
             line["hash_grid_train_step"] = {"unavailable": repr(e)[:300]}
     if rank == 0:
@@ -621,9 +746,10 @@ def main():
                     help="transmittance below which the fused fine pass stops a ray (0 = composite every sample)")
     ap.add_argument("--python-recursion", action="store_true",
                     help="drive the bounce from Python (per-level launches + host syncs) instead of mnrf_render_recursive")
-    ap.add_argument("--ref-rays", type=int, default=2048, help="rays per step of the CPU reference sample")
+    ap.add_argument("--ref-rays", type=int, default=4096, help="rays per step of the CPU reference sample (BASELINE.md section 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--config4", action="store_true", help="also time BASELINE config 4 (2 bounces + roughness cone)")
+    ap.add_argument("--no-config4", action="store_true", help="skip BASELINE config 4 (2 bounces + roughness cone of 8 reflections)")
+    ap.add_argument("--no-full-dict", action="store_true", help="skip the secondary end-to-end run with the reference's full output dict")
     ap.add_argument("--peer-fused", action="store_true",
                     help="train step: one peer-memory kernel (reduce-scatter + Adam + all-gather) instead of ncclAllReduce + Adam")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary train-step measurement (config 5)")

@@ -26,6 +26,7 @@
 // profiles/r02_v1_fp8_mma_microbench.txt) -- 2.0 fp16-pass equivalents per algorithmic MAC instead of 3, operand error ~2^-16.
 //
 // Shared memory (1 CTA/SM): A hi/lo 2x64 KB | PE hi/lo 2x16 KB | 4 x 16 KB weight stages | 2 KB partial sums.
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -519,6 +520,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
             mbar_wait(bar(BAR_W_EMPTY + stage), phase ^ 1u);
             const uint32_t dst = stage_addr(stage);
             const uint32_t fb = bar(BAR_W_FULL + stage);
+            if (P.debug & 1) {   // timing experiment only (wrong results): a quarter of the weight bytes per stage
+              mbar_expect_tx(fb, 4096u);
+              bulk_g2s(dst, src + (size_t)si * 4096u, 4096u, fb);
+              if (++stage == NST) { stage = 0; phase ^= 1u; }
+              continue;
+            }
             mbar_expect_tx(fb, WSTAGE_BYTES);
             if (sn == 64 && !TWO_BLOBS) {
 #pragma unroll
@@ -562,7 +569,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
           const bool wide = tc_step_n(s) == 256;
           const int nch = tc_step_chunks(s);
           const int n_pe = (s == 0 || s == 4) ? 2 : 0;       // leading K32 chunks that come from the PE buffer
-          const bool a_reused = (s == 8 && P.has_mirror) || s == 15;  // operand already awaited by the previous GEMM
+          bool a_reused = (s == 8 && P.has_mirror) || s == 15;  // operand already awaited by the previous GEMM
+          // Two steps write accumulator columns that the epilogue producing their A operand still READS while it runs (the
+          // four column groups convert their chunks concurrently): the final layer without a mirror head ([128,384) overlaps the
+          // last trunk layer's [256,512)) and chain step 16 ([0,256) overlaps step 15's PE-gradient columns, read by every group
+          // in front of step 14's epilogue).  They wait for the WHOLE operand first; every other step starts on chunk 0.
+          if ((s == 8 && !P.has_mirror) || s == 16) {
+#pragma unroll 1
+            for (int c = 0; c < 5; ++c) { mbar_wait(bar(BAR_A + c), (a_phase >> c) & 1u); a_phase ^= 1u << c; }
+            a_reused = true;
+          }
           const uint32_t d_tmem = tmem + acc_col(s);
           uint32_t accumulate = 0;
           trace_ev(P, trc, 0, 1, 1, s, 0);
@@ -1261,7 +1277,10 @@ int launch_field_tc(const mnrf_field* f, const FieldIO& io, int precision, cudaS
     P.work_counter = fuse->work_counter; P.stats = fuse->stats;
     MNRF_CUDA_OK(cudaMemsetAsync(fuse->work_counter, 0, sizeof(int), st));
   }
-  P.debug = 0;
+  {
+    static const int dbg = getenv("MNRF_TC_DEBUG") != nullptr ? atoi(getenv("MNRF_TC_DEBUG")) : 0;
+    P.debug = dbg;   // bit 0: timing experiment, a quarter of the weight bytes per stage (results are garbage)
+  }
   P.n_tiles = (io.n_points + TILE_M - 1) / TILE_M;
   const int grid = P.n_tiles < num_sms ? P.n_tiles : num_sms;
   // algorithmic MACs of this launch (unpadded reference layer sizes)

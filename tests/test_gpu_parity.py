@@ -9,7 +9,11 @@ Tolerances (north-star: ray/sample indices bit-exact; rgb/depth within 1e-3 rela
     (fp32 kernel: p99 <= 1e-4);
   * per-ray composited outputs on the adversarial golden field (sigma head x40, SURVEY.md 7.3: the reference itself is
     discontinuous in sign(sigma_last) and re-ordering fp32 sums already moves 0.05-0.15 % of rays by > 1e-3):
-    median <= 1e-4 and at most 3 % of entries off by more than 1e-3 (relative to max(|ref|, rms)).
+    median <= 2e-5 and at most 1 % of entries off by more than 1e-3 (relative to max(|ref|, rms)).
+
+Every bound below is "measured x 2" (round 2: the measured distributions of a B200 run are in profiles/r02_*_parity_stats.json;
+tests/util.py::err_stats logs them on every run into gpurun_out/parity_stats.json).  Where a fixture has only 8 or 12 rays the
+fraction bound is "one ray": the FP32 CUDA-core kernel shows the same single ray (error 1.1e-3 .. 2e-3) on those fixtures.
 """
 import pytest
 import torch
@@ -36,7 +40,7 @@ def params():
     return scene_state_dicts()
 
 
-def assert_close_dist(got, want, name, median=1e-4, frac=0.03, p99=None):
+def assert_close_dist(got, want, name, median=2e-5, frac=0.01, p99=None):
     s = err_stats(got, want, name=name)
     msg = fmt_stats(name, s)
     assert s["median"] <= median, msg
@@ -298,8 +302,9 @@ def test_render_variants_golden(golden, mm, tag, impl):
     assert set(r) == set(want), sorted(set(r) ^ set(want))
     for k in sorted(r):
         assert tuple(r[k].shape) == want[k].shape, k
-        # 12 rays only: allow one ray (x channels) to sit on the sigma_last discontinuity
-        assert_close_dist(r[k].cpu(), T(want[k]), f"{tag}/{impl} {k}", frac=0.09)
+        # 12 rays only: one ray (x channels) sits on the sigma_last discontinuity -- also for the fp32 kernel (measured: that ray is
+        # off by 1.1e-3 (fp32) / 1.5e-3 (tc3) in opacity, every other entry < 1e-3; medians <= 1.4e-5)
+        assert_close_dist(r[k].cpu(), T(want[k]), f"{tag}/{impl} {k}", median=3e-5, frac=0.09)
 
 
 @pytest.mark.parametrize("impl", ["fp32", "tc3"])
@@ -318,6 +323,8 @@ def test_render_train_mode_forward_golden(golden, mm, impl):
     assert torch.equal(r["z_vals_coarse"].cpu(), T(want["z_vals_coarse"]))
     for k in sorted(r):
         assert tuple(r[k].shape) == want[k].shape, k
+        # 8 rays, analytic normals of the sharp field: one ray (12.5 %) beyond 1e-3 for both kernels; medians measured <= 9.6e-5.
+        # The tight train-mode check is test_room_train_mode_forward below (scene-like field, 256 rays).
         assert_close_dist(r[k].cpu(), T(want[k]), f"train {k}", median=2e-4, frac=0.13)
 
 
@@ -523,6 +530,40 @@ def test_generate_rays_matches_reference_camera():
         assert got.shape == want.shape
         assert torch.equal(got[:, [0, 1, 2, 6, 7]], want[:, [0, 1, 2, 6, 7]])
         assert float((got[:, 3:6] - want[:, 3:6]).abs().max()) <= 2e-7  # matmul summation order / FMA contraction
+
+
+def test_room_train_mode_forward(oracle):
+    """Train-mode forward (test_time=False, compute_normal=True, perturb = noise_std = 1 with the draws replayed) on the SCENE-LIKE
+    field: both passes full, analytic normals from the tcgen05 reverse chain, vs the oracle on the same rays and draws."""
+    from mirror_nerf_b200.mirror_nerf import Embedding, MirrorNeRF
+    from mirror_nerf_b200.rendering import render_rays
+    from mirror_nerf_b200.room_scene import room_pose
+    from mirror_nerf_b200.synthetic import camera_rays
+    from util import room_state_dicts
+    sds = room_state_dicts()
+    models = {}
+    for k, sd in sds.items():
+        m = MirrorNeRF(predict_normal=True, predict_mirror_mask=True)
+        m.load_state_dict(sd)
+        models[k] = m.cuda().eval()
+    emb = {"xyz": Embedding(10), "dir": Embedding(4)}
+    allrays = camera_rays(200, 200, c2w=room_pose(3), near=0.05, far=12.0)
+    n = 256
+    rays = allrays[torch.linspace(0, allrays.shape[0] - 1, n).long()].contiguous()
+    g = torch.Generator().manual_seed(17)
+    rng = {"perturb_u": torch.rand(n, 64, generator=g), "noise_coarse": torch.randn(n, 64, generator=g),
+           "u_pdf": torch.rand(n, 128, generator=g), "noise_fine": torch.randn(n, 192, generator=g)}
+    args = (64, False, 1.0, 1.0, 128, 32768, False)
+    want = oracle.render_rays(sds, rays, *args, test_time=False, compute_normal=True, rng=rng)
+    with torch.no_grad():
+        got = render_rays(models, emb, rays.cuda(), *args, test_time=False, compute_normal=True, rng=rng)
+    assert set(got) == set(want), sorted(set(got) ^ set(want))
+    assert torch.equal(got["z_vals_coarse"].cpu(), want["z_vals_coarse"])
+    for k in sorted(got):
+        per_sample = got[k].dim() >= 2 and got[k].shape[1] in (64, 192)
+        # per-ray outputs: tight; per-sample tensors (weights, normals of points in empty space) carry the field's own
+        # conditioning: a looser tail
+        assert_close_dist(got[k].cpu(), want[k].detach(), f"room train-mode {k}", median=5e-5, frac=0.05 if per_sample else 0.02)
 
 
 def test_sharded_render_equals_unsharded_bitwise(mm):

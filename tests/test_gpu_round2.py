@@ -79,7 +79,7 @@ def test_field_tc2_kernel_golden(golden, mm):
         m.field_impl = "tc3"
         m.return_geo_feat = True
     for k, gk in (("sigma", "full_sigma"), ("pred_normal", "full_pred_normal"), ("rgb", "full_rgb"), ("is_mirror", "full_is_mirror")):
-        close(o[k].cpu(), T(g[gk]), f"tc2 {k}", median=1e-4, frac=0.0, p99=1e-3)
+        close(o[k].cpu(), T(g[gk]), f"tc2 {k}", median=6e-5, frac=0.0, p99=3e-4)   # measured: sigma median 2.9e-5, p99 1.0e-4
 
 
 def test_render_eval_golden_tc2(golden, mm):
@@ -91,7 +91,7 @@ def test_render_eval_golden_tc2(golden, mm):
     assert set(r) == set(g) - {"rays"}
     assert torch.equal(r["z_vals_coarse"].cpu(), T(g["z_vals_coarse"]))
     for k in sorted(r):
-        close(r[k].cpu(), T(g[k]), f"tc2 render {k}", median=1e-4, frac=0.03)
+        close(r[k].cpu(), T(g[k]), f"tc2 render {k}", median=6e-5, frac=0.035)   # measured: median 2.6e-5, one ray of 64 (1.6 %)
 
 
 def test_room_scene_parity_and_psnr_tc2(oracle, room):
@@ -126,7 +126,7 @@ def test_tc2_full_size_agrees_with_tc3(mm):
         b = render_rays(models, emb, rays, *ARGS, test_time=True, compute_normal=False, field_impl="tc2")
     assert torch.equal(a["z_vals_coarse"], b["z_vals_coarse"])
     for k in ("rgb_fine", "depth_fine", "opacity_fine", "mirror_mask_fine"):
-        close(b[k].cpu(), a[k].cpu(), f"tc2 vs tc3 {k} (adversarial field)", median=1e-4, frac=0.03)
+        close(b[k].cpu(), a[k].cpu(), f"tc2 vs tc3 {k} (adversarial field)", median=6e-5, frac=0.005)   # measured 2.9e-5 / 0.22 %
 
 
 # ------------------------------------------------------------------------------------------------ device-side recursion
