@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmnrf.so")
+# MNRF_LIB: another build flavour of the same library (tools/tc_trace.py uses the -DMNRF_TC_TRACE build); never a fallback
+LIB_PATH = os.environ.get("MNRF_LIB") or os.path.join(_HERE, "lib", "libmnrf.so")
 
 IMPL_TC3, IMPL_TC2, IMPL_TC1, IMPL_FP32 = 3, 2, 1, 0
 IMPL_BY_NAME = {"tc3": IMPL_TC3, "tc2": IMPL_TC2, "tc1": IMPL_TC1, "fp32": IMPL_FP32}

@@ -109,6 +109,24 @@ __device__ __forceinline__ void trace_ev(const TcParams& P, TraceCtx& tc, int la
 #endif
 }
 
+// trace builds only: cycles the MMA issuer spends blocked on one barrier class, accumulated over a tile (payload of events 5..7)
+#ifdef MNRF_TC_TRACE
+#define TR_T0() const long long _tr_t0 = clock64()
+#define TR_ADD(x) (x) += (unsigned int)(clock64() - _tr_t0)
+__device__ __forceinline__ void trace_val(const TcParams& P, TraceCtx& tc, int who, int ev, unsigned int val) {
+  if (P.trace != nullptr && blockIdx.x == 0 && tc.n < 8192u) {
+    unsigned long long* r = P.trace + 1 + (size_t)who * 2 * 8192 + 2 * tc.n;
+    r[0] = (unsigned long long)clock64();
+    r[1] = ((unsigned long long)val << 32) | ((unsigned long long)who << 24) | ((unsigned long long)ev << 16);
+    ++tc.n;
+  }
+}
+#else
+#define TR_T0() do {} while (0)
+#define TR_ADD(x) do {} while (0)
+__device__ __forceinline__ void trace_val(const TcParams&, TraceCtx&, int, int, unsigned int) {}
+#endif
+
 // ---- PTX wrappers --------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -558,6 +576,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
       const uint32_t dl_pe8 = dl_pe_lo, dl_pe8r = desc_lo(sbase + SM_PE_LO + 8192u, 2048);
       auto next_stage = [&]() { if (++stage == NST) { stage = 0; phase ^= 1u; } };
       for (int tile = blockIdx.x; FUSE || tile < n_tiles; tile += gridDim.x) {
+        unsigned int w_pe = 0, w_a = 0, w_w = 0;   // trace builds: cycles blocked on the PE / activation / weight barriers
+        (void)w_pe; (void)w_a; (void)w_w;
         if (FUSE) {  // PE barrier = "the next tile's encoding is in place" or "stop"
           mbar_wait(bar(BAR_PE), pe_phase);
           pe_phase ^= 1u;
@@ -586,7 +606,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
             uint32_t ah, al;  // descriptor low words of this K32 chunk of the A operand (hi / lo parts)
             uint32_t a8 = 0, a8r = 0;  // tc2: e4m3 copy of the chunk and of its residual
             if (kc < n_pe) {
-              if (!FUSE && s == 0 && kc == 0) { mbar_wait(bar(BAR_PE), pe_phase); pe_phase ^= 1u; }
+              if (!FUSE && s == 0 && kc == 0) { TR_T0(); mbar_wait(bar(BAR_PE), pe_phase); pe_phase ^= 1u; TR_ADD(w_pe); }
               ah = dl_pe_hi + (uint32_t)kc * 512u; al = dl_pe_lo + (uint32_t)kc * 512u;
               a8 = dl_pe8 + (uint32_t)kc * 256u; a8r = dl_pe8r + (uint32_t)kc * 256u;
             } else {
@@ -594,7 +614,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
               // first touch of freshly written activation columns: chunk 0 is signalled in two 32-column halves
               if (((ka & 1) == 0 || ka == 1) && !a_reused) {
                 const int c = ka == 1 ? 4 : (ka >> 1);
+                TR_T0();
                 mbar_wait(bar(BAR_A + c), (a_phase >> c) & 1u);
+                TR_ADD(w_a);
                 a_phase ^= 1u << c;
                 trace_ev(P, trc, 0, 1, 2, s, c);
               }
@@ -603,7 +625,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
             }
             if (wide) {
               // ---- N = 256: K16 step of the B operand = 8192 B = 512 units ----
-              mbar_wait(bar(BAR_W_FULL + stage), phase);
+              { TR_T0(); mbar_wait(bar(BAR_W_FULL + stage), phase); TR_ADD(w_w); }
               tc_fence_after();
               uint32_t wb = desc_lo(stage_addr(stage), 4096);
               tc_mma<256>(d_tmem, ah, wb, accumulate);                        // A_hi * W_hi  (k 0..15)
@@ -623,7 +645,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
               }
               if (PREC == 2) {
                 // second stage of the chunk = [e4m3(2^-10 W_hi) 8 KB | e4m3(W_lo) 8 KB], 32 K values per instruction
-                mbar_wait(bar(BAR_W_FULL + stage), phase);
+                { TR_T0(); mbar_wait(bar(BAR_W_FULL + stage), phase); TR_ADD(w_w); }
                 tc_fence_after();
                 wb = desc_lo(stage_addr(stage), 4096);
                 tc_mma_f8<256>(d_tmem, a8r, wb, 1u);                          // (2^10 A_lo) * (2^-10 W_hi)
@@ -687,6 +709,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
           tc_commit(bar(BAR_ACC + acc_bar(s)));
           trace_ev(P, trc, 0, 1, 3, s, 0);
         }
+        trace_val(P, trc, 1, 5, w_pe); trace_val(P, trc, 1, 6, w_a); trace_val(P, trc, 1, 7, w_w);
       }
     }
   } else if (warp >= 4) {

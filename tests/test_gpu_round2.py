@@ -392,3 +392,24 @@ def test_rng_stream_matches_reference_call_order(mm):
         torch.randn(n, 192, device="cuda")
         want = torch.rand(4, device="cuda")
         assert torch.equal(got, want), (perturb, noise_std)
+
+
+def test_analytic_normal_kernel_is_deterministic(mm):
+    """The tensor-core kernel with the analytic-normal chain (20 GEMM steps, accumulators re-used across steps while four column
+    groups convert their chunks concurrently) must give bit-identical results run after run: a column group reading an
+    accumulator that a later step already overwrites would show up here as run-to-run differences."""
+    from mirror_nerf_b200.rendering import render_rays
+    from mirror_nerf_b200.synthetic import random_rays
+    models, emb = mm
+    rays = random_rays(6000, seed=91).cuda()
+    g = torch.Generator().manual_seed(2)
+    rng = {"perturb_u": torch.rand(6000, 64, generator=g), "noise_coarse": torch.randn(6000, 64, generator=g),
+           "u_pdf": torch.rand(6000, 128, generator=g), "noise_fine": torch.randn(6000, 192, generator=g)}
+    outs = []
+    with torch.no_grad():
+        for _ in range(3):
+            outs.append(render_rays(models, emb, rays, 64, False, 1.0, 1.0, 128, 32768, False, test_time=False, compute_normal=True,
+                                    rng=rng))
+    for k in outs[0]:
+        for o in outs[1:]:
+            assert torch.equal(outs[0][k], o[k]), (k, float((outs[0][k] - o[k]).abs().max()))

@@ -1,4 +1,7 @@
-"""Device-side timeline of the tcgen05 field kernel (CTA 0): prints per-tile event offsets in cycles."""
+"""Device-side timeline of the tcgen05 field kernel (CTA 0): prints per-tile event offsets in cycles.
+Needs the trace flavour of the library:
+    make -C mirror_nerf_b200/csrc OBJDIR=../lib/obj_trace OUT=../lib/libmnrf_trace.so EXTRA=-DMNRF_TC_TRACE
+    MNRF_LIB=mirror_nerf_b200/lib/libmnrf_trace.so python tools/tc_trace.py tc2"""
 import os
 import sys
 
@@ -17,7 +20,7 @@ lib = _lib.load()
 models, emb = make_models()
 rays = camera_rays(800, 800)[::19][:32768].contiguous().cuda()
 cap = 200000
-kw = dict(test_time=True, compute_normal=False, field_impl=impl)
+kw = dict(test_time=True, compute_normal=False, field_impl=impl, fused_composite=False)
 with torch.no_grad():
     # a single full-model launch: coarse-only render with train-style (non sigma-only) coarse pass, 192 samples
     one = {"coarse": models["fine"]}
@@ -41,15 +44,27 @@ ev.sort()
 print("events", len(ev))
 # the trace holds the coarse launch then the fine launch: split at the largest time gap, keep the fine one
 fine = ev
-names = {1: "mma_begin", 2: "mma_A_ready", 3: "mma_last_chunk", 10: "epi_acc_ready", 11: "epi_chunk_written",
-         12: "pe_begin", 13: "pe_end", 14: "tile_epilogue_done"}
+names = {1: "mma_begin", 2: "mma_A_ready", 3: "mma_last_chunk", 5: "TILE wait PE cycles", 6: "TILE wait A cycles",
+         7: "TILE wait W cycles", 10: "epi_acc_ready", 11: "epi_chunk_written", 12: "pe_begin", 13: "pe_end", 14: "tile_epilogue_done"}
+# per-tile totals of the MMA issuer's blocked cycles (payload in the upper 32 bits of the tag)
+tot = {5: [], 6: [], 7: []}
+for t, tag in ev:
+    e = (tag >> 16) & 255
+    if (tag >> 24) & 255 == 1 and e in tot:
+        tot[e].append(tag >> 32)
+for e, v in tot.items():
+    if v:
+        v = v[2:-1] or v
+        print(f"MMA issuer, {names[e]}: mean {sum(v) / len(v):.0f} over {len(v)} tiles")
 starts = [i for i, (t, tag) in enumerate(fine)
-          if (tag >> 24) == 1 and ((tag >> 16) & 255) == 1 and ((tag >> 8) & 255) == 0 and (tag & 255) == 0]
+          if ((tag >> 24) & 255) == 1 and ((tag >> 16) & 255) == 1 and ((tag >> 8) & 255) == 0 and (tag & 255) == 0]
 print("tiles traced", len(starts))
 print("tile period (cycles):", [fine[starts[j + 1]][0] - fine[starts[j]][0] for j in range(2, min(14, len(starts) - 1))])
 k = min(20, len(starts) - 2)
 lo, hi = starts[k], starts[k + 1]
 t0 = fine[lo][0]
 for t, tag in fine[lo:hi + 8]:
-    who, e, a, bb = tag >> 24, (tag >> 16) & 255, (tag >> 8) & 255, tag & 255
+    who, e, a, bb = (tag >> 24) & 255, (tag >> 16) & 255, (tag >> 8) & 255, tag & 255
+    if e in (5, 6, 7):
+        a, bb = tag >> 32, 0
     print(f"{t - t0:8d}  {'MMA ' if who == 1 else 'EPI' + str(who - 4)}  {names.get(e, e):20s} {a} {bb}")
