@@ -816,16 +816,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) b[i] = b4[i];
       wait_acc(s);
+      // Stagger the groups (named barriers 7..9, arrive = non-blocking): the next layer's MMAs wait for chunk 0, so group 0
+      // converts it with the schedulers to itself (measured: with all 16 warps converting at once a 16-column piece took 800
+      // cycles and chunk 0 appeared 2,300 cycles after the accumulator); group 1 starts when group 0 is half done, group 2 when
+      // group 0 is done, group 3 when group 1 is done -- each chunk is still ready before the MMAs reach it.
+      if (g == 1) asm volatile("bar.sync 7, 256;" ::: "memory");
+      else if (g == 2) asm volatile("bar.sync 8, 256;" ::: "memory");
+      else if (g == 3) asm volatile("bar.sync 9, 256;" ::: "memory");
       const uint32_t tcol = tlane + acc_col(s) + 64u * (uint32_t)g;
       uint32_t ra[16], rb[16];
       tmem_ld16(tcol, ra);
       tmem_wait_ld();
+      if (q == 0) trace_ev(P, trc, lane, 4 + g, 20, s, 0);   // first TMEM load landed
       tmem_ld16(tcol + 16u, rb);  // piece 1
       pin<16>(ra);
       {
         const uint32_t off = (uint32_t)(8 * g) * 2048u + rowoff;
         epi_cols<16, RELU, DOTS, WRITE_A, PREC, MASK>(ra, b, inv, sbase + SM_A_HI + off, lo_addr(off), headw + 64 * g, d, mk[0], 0);
       }
+      if (q == 0) trace_ev(P, trc, lane, 4 + g, 21, s, 0);   // piece 0 converted and stored
 #pragma unroll
       for (int j = 1; j < 4; ++j) {
 #pragma unroll
@@ -838,8 +847,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
         const uint32_t off = (uint32_t)(8 * g + 2 * j) * 2048u + rowoff;
         if (j & 1) { pin<16>(rb); epi_cols<16, RELU, DOTS, WRITE_A, PREC, MASK>(rb, b, inv, sbase + SM_A_HI + off, lo_addr(off), headw + 64 * g + 16 * j, d, mk[j >> 1], 16 * (j & 1)); }
         else       { pin<16>(ra); epi_cols<16, RELU, DOTS, WRITE_A, PREC, MASK>(ra, b, inv, sbase + SM_A_HI + off, lo_addr(off), headw + 64 * g + 16 * j, d, mk[j >> 1], 16 * (j & 1)); }
+        if (q == 0) trace_ev(P, trc, lane, 4 + g, 22, s, j);  // piece j converted and stored
         if (WRITE_A && g == 0 && j == 1) a_ready(0);   // columns 0..31: the next layer's first K32 chunk
         if (WRITE_A && j == 3) a_ready(g == 0 ? 4 : g);
+        if (g == 0 && j == 1) asm volatile("bar.arrive 7, 256;" ::: "memory");   // releases group 1
+        if (g == 0 && j == 3) asm volatile("bar.arrive 8, 256;" ::: "memory");   // releases group 2
+        if (g == 1 && j == 3) asm volatile("bar.arrive 9, 256;" ::: "memory");   // releases group 3
       }
     };
 
