@@ -162,6 +162,31 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// Spinning wait for the two single-thread roles (weight producer, MMA issuer): mbarrier.test_wait never suspends the thread, so
+// the role reacts within a few cycles of the phase flip.  try_wait may park the thread for an implementation-defined time;
+// measured with the device timeline: ~400 cycles between an arrive and the waiter's next instruction, twice per weight-stage
+// round trip (commit -> producer, copy complete -> issuer), which is what starved the 4-stage ring.
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
+  if (mbar_test(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_test(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("mnrf field_tc: mbarrier timeout (block %d thread %d bar@%u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
@@ -521,7 +546,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
       uint32_t stage = 0, phase = 0, go_phase = 0;
       for (int tile = blockIdx.x; FUSE || tile < n_tiles; tile += gridDim.x) {
         if (FUSE) {  // the epilogue warps decide tile by tile whether there is another one
-          mbar_wait(bar(BAR_GO), go_phase);
+          mbar_spin(bar(BAR_GO), go_phase);
           go_phase ^= 1u;
           if (*f_stop) break;
         }
@@ -535,7 +560,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
           // N = 64 steps (4 KB blobs): 3x -> [hi|lo] of two K32 chunks per stage (contiguous); 1x -> hi of four chunks
           const int nst = sn == 64 ? (TWO_BLOBS ? nch / 2 : nch / 4) : (TWO_BLOBS ? (wide ? 2 * nch : nch) : (wide ? nch : nch / 2));
           for (int si = 0; si < nst; ++si) {
-            mbar_wait(bar(BAR_W_EMPTY + stage), phase ^ 1u);
+            mbar_spin(bar(BAR_W_EMPTY + stage), phase ^ 1u);
             const uint32_t dst = stage_addr(stage);
             const uint32_t fb = bar(BAR_W_FULL + stage);
             if (P.debug & 1) {   // timing experiment only (wrong results): a quarter of the weight bytes per stage
@@ -579,7 +604,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
         unsigned int w_pe = 0, w_a = 0, w_w = 0;   // trace builds: cycles blocked on the PE / activation / weight barriers
         (void)w_pe; (void)w_a; (void)w_w;
         if (FUSE) {  // PE barrier = "the next tile's encoding is in place" or "stop"
-          mbar_wait(bar(BAR_PE), pe_phase);
+          mbar_spin(bar(BAR_PE), pe_phase);
           pe_phase ^= 1u;
           if (*f_stop) break;
         }
@@ -596,7 +621,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
           // in front of step 14's epilogue).  They wait for the WHOLE operand first; every other step starts on chunk 0.
           if ((s == 8 && !P.has_mirror) || s == 16) {
 #pragma unroll 1
-            for (int c = 0; c < 5; ++c) { mbar_wait(bar(BAR_A + c), (a_phase >> c) & 1u); a_phase ^= 1u << c; }
+            for (int c = 0; c < 5; ++c) { mbar_spin(bar(BAR_A + c), (a_phase >> c) & 1u); a_phase ^= 1u << c; }
             a_reused = true;
           }
           const uint32_t d_tmem = tmem + acc_col(s);
@@ -606,7 +631,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
             uint32_t ah, al;  // descriptor low words of this K32 chunk of the A operand (hi / lo parts)
             uint32_t a8 = 0, a8r = 0;  // tc2: e4m3 copy of the chunk and of its residual
             if (kc < n_pe) {
-              if (!FUSE && s == 0 && kc == 0) { TR_T0(); mbar_wait(bar(BAR_PE), pe_phase); pe_phase ^= 1u; TR_ADD(w_pe); }
+              if (!FUSE && s == 0 && kc == 0) { TR_T0(); mbar_spin(bar(BAR_PE), pe_phase); pe_phase ^= 1u; TR_ADD(w_pe); }
               ah = dl_pe_hi + (uint32_t)kc * 512u; al = dl_pe_lo + (uint32_t)kc * 512u;
               a8 = dl_pe8 + (uint32_t)kc * 256u; a8r = dl_pe8r + (uint32_t)kc * 256u;
             } else {
@@ -615,7 +640,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
               if (((ka & 1) == 0 || ka == 1) && !a_reused) {
                 const int c = ka == 1 ? 4 : (ka >> 1);
                 TR_T0();
-                mbar_wait(bar(BAR_A + c), (a_phase >> c) & 1u);
+                mbar_spin(bar(BAR_A + c), (a_phase >> c) & 1u);
                 TR_ADD(w_a);
                 a_phase ^= 1u << c;
                 trace_ev(P, trc, 0, 1, 2, s, c);
@@ -625,7 +650,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
             }
             if (wide) {
               // ---- N = 256: K16 step of the B operand = 8192 B = 512 units ----
-              { TR_T0(); mbar_wait(bar(BAR_W_FULL + stage), phase); TR_ADD(w_w); }
+              { TR_T0(); mbar_spin(bar(BAR_W_FULL + stage), phase); TR_ADD(w_w); }
               tc_fence_after();
               uint32_t wb = desc_lo(stage_addr(stage), 4096);
               tc_mma<256>(d_tmem, ah, wb, accumulate);                        // A_hi * W_hi  (k 0..15)
@@ -635,7 +660,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
               tc_commit(bar(BAR_W_EMPTY + stage));
               next_stage();
               if (PREC3) {
-                mbar_wait(bar(BAR_W_FULL + stage), phase);
+                mbar_spin(bar(BAR_W_FULL + stage), phase);
                 tc_fence_after();
                 wb = desc_lo(stage_addr(stage), 4096);
                 tc_mma<256>(d_tmem, ah, wb, 1u);                              // A_hi * W_lo
@@ -645,7 +670,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
               }
               if (PREC == 2) {
                 // second stage of the chunk = [e4m3(2^-10 W_hi) 8 KB | e4m3(W_lo) 8 KB], 32 K values per instruction
-                { TR_T0(); mbar_wait(bar(BAR_W_FULL + stage), phase); TR_ADD(w_w); }
+                { TR_T0(); mbar_spin(bar(BAR_W_FULL + stage), phase); TR_ADD(w_w); }
                 tc_fence_after();
                 wb = desc_lo(stage_addr(stage), 4096);
                 tc_mma_f8<256>(d_tmem, a8r, wb, 1u);                          // (2^10 A_lo) * (2^-10 W_hi)
@@ -656,7 +681,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
             } else if (tc_step_n(s) == 64) {
               // ---- N = 64 (PE-gradient steps of the normal chain): K16 step of B = 2048 B = 128 units, LBO = 1024 ----
               if (PREC3) {  // stage = [hi|lo] of chunks 2j, 2j+1 (4 x 4 KB)
-                if ((kc & 1) == 0) { mbar_wait(bar(BAR_W_FULL + stage), phase); tc_fence_after(); }
+                if ((kc & 1) == 0) { mbar_spin(bar(BAR_W_FULL + stage), phase); tc_fence_after(); }
                 const uint32_t wb = desc_lo(stage_addr(stage), 1024) + (uint32_t)(kc & 1) * 512u;
                 tc_mma<64>(d_tmem, ah, wb, accumulate);
                 tc_mma<64>(d_tmem, al, wb, 1u);
@@ -666,7 +691,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
                 tc_mma<64>(d_tmem, ah + 256u, wb + 384u, 1u);
                 if (kc & 1) { tc_commit(bar(BAR_W_EMPTY + stage)); next_stage(); }
               } else {      // stage = hi of chunks 4j..4j+3
-                if ((kc & 3) == 0) { mbar_wait(bar(BAR_W_FULL + stage), phase); tc_fence_after(); }
+                if ((kc & 3) == 0) { mbar_spin(bar(BAR_W_FULL + stage), phase); tc_fence_after(); }
                 const uint32_t wb = desc_lo(stage_addr(stage), 1024) + (uint32_t)(kc & 3) * 256u;
                 tc_mma<64>(d_tmem, ah, wb, accumulate);
                 tc_mma<64>(d_tmem, ah + 256u, wb + 128u, 1u);
@@ -674,7 +699,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
               }
             } else if (PREC == 2) {
               // ---- N = 128, tc2: stage = [W_hi fp16 8 KB | e4m3(2^-10 W_hi) 4 KB | e4m3(W_lo) 4 KB] of this K32 chunk ----
-              mbar_wait(bar(BAR_W_FULL + stage), phase);
+              mbar_spin(bar(BAR_W_FULL + stage), phase);
               tc_fence_after();
               const uint32_t wb = desc_lo(stage_addr(stage), 2048);
               tc_mma<128>(d_tmem, ah, wb, accumulate);
@@ -685,7 +710,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
               next_stage();
             } else if (PREC3) {
               // ---- N = 128, 3x: stage = [W_hi | W_lo] of this K32 chunk; K16 step = 4096 B = 256 units ----
-              mbar_wait(bar(BAR_W_FULL + stage), phase);
+              mbar_spin(bar(BAR_W_FULL + stage), phase);
               tc_fence_after();
               const uint32_t wb = desc_lo(stage_addr(stage), 2048);
               tc_mma<128>(d_tmem, ah, wb, accumulate);
@@ -698,7 +723,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
               next_stage();
             } else {
               // ---- N = 128, 1x: stage = W_hi of two K32 chunks ----
-              if ((kc & 1) == 0) { mbar_wait(bar(BAR_W_FULL + stage), phase); tc_fence_after(); }
+              if ((kc & 1) == 0) { mbar_spin(bar(BAR_W_FULL + stage), phase); tc_fence_after(); }
               const uint32_t wb = desc_lo(stage_addr(stage), 2048) + (uint32_t)(kc & 1) * 512u;
               tc_mma<128>(d_tmem, ah, wb, accumulate);
               tc_mma<128>(d_tmem, ah + 256u, wb + 256u, 1u);
