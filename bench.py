@@ -741,7 +741,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--field-impl", default=os.environ.get("MNRF_FIELD_IMPL", "tc3"), choices=["tc3", "tc2", "tc1"])
+    ap.add_argument("--field-impl", default=os.environ.get("MNRF_BENCH_FIELD_IMPL", "tc2"), choices=["tc3", "tc2", "tc1"])
     ap.add_argument("--early-termination-eps", type=float, default=1e-5,
                     help="transmittance below which the fused fine pass stops a ray (0 = composite every sample)")
     ap.add_argument("--python-recursion", action="store_true",

@@ -31,9 +31,11 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace mnrf {
 namespace {
+using namespace tcx;
 
 constexpr int TILE_M = 128;
 constexpr int NUM_THREADS = 640;
@@ -127,133 +129,8 @@ __device__ __forceinline__ void trace_val(const TcParams& P, TraceCtx& tc, int w
 __device__ __forceinline__ void trace_val(const TcParams&, TraceCtx&, int, int, unsigned int) {}
 #endif
 
-// ---- PTX wrappers --------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// PTX wrappers (mbarrier, bulk copy, tcgen05 fences / commit / ld / st, descriptors): tc_ptx.cuh, shared with train_tc.cu
 
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU box
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("mnrf field_tc: mbarrier timeout (block %d thread %d bar@%u parity %u)\n", blockIdx.x, threadIdx.x, bar,
-             parity);
-      __trap();
-    }
-  }
-}
-// Spinning wait for the two single-thread roles (weight producer, MMA issuer): mbarrier.test_wait never suspends the thread, so
-// the role reacts within a few cycles of the phase flip.  try_wait may park the thread for an implementation-defined time;
-// measured with the device timeline: ~400 cycles between an arrive and the waiter's next instruction, twice per weight-stage
-// round trip (commit -> producer, copy complete -> issuer), which is what starved the 4-stage ring.
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
-  if (mbar_test(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_test(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("mnrf field_tc: mbarrier timeout (block %d thread %d bar@%u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-// wait for this thread's outstanding tcgen05.ld, then pin the destination registers behind the wait
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-template <int NR>
-__device__ __forceinline__ void pin(uint32_t (&r)[NR]) {
-#pragma unroll
-  for (int i = 0; i < NR; ++i) asm volatile("" : "+r"(r[i]));
-}
-__device__ __forceinline__ void pin32(uint32_t (&r)[32]) { pin<32>(r); }
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
-}
-// one lane of a converged warp (the pattern ptxas turns into ELECT + predicated uniform-datapath instructions)
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred = 0;
-  asm volatile(
-      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
-      "elect.sync rx|px, 0xffffffff;\n\t"
-      "@px mov.s32 %0, 1;\n\t}"
-      : "+r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void epi_bar_sync(int id) { asm volatile("bar.sync %0, 512;" ::"r"(id) : "memory"); }
-__device__ __forceinline__ void tmem_st4(uint32_t taddr, float a, float b, float c, float d) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(a)),
-               "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d))
-               : "memory");
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-// K-major, no-swizzle operand descriptors.  Core matrix = 8 rows x 16 bytes stored as 128 contiguous bytes; SBO (distance
-// between 8-row groups) = 128 B for every operand, so all descriptors share the high word; LBO (distance between K-adjacent
-// core matrices) = rows*16: 2048 for the 128-row A operands and N=128 weights, 4096 for N=256 weights.  The low word is
-// (address >> 4) | (LBO >> 4) << 16, so stepping through an operand is an integer add in 16-byte units.
-constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
-__device__ __forceinline__ uint32_t desc_lo(uint32_t addr, uint32_t lbo) { return ((addr >> 4) & 0x3FFFu) | ((lbo >> 4) << 16); }
 // fp8 (e4m3 x e4m3 -> f32, K = 32 per instruction): same descriptor and instruction-descriptor bits as the fp16 form (format 0 is
 // F16 for kind::f16 and E4M3 for kind::f8f6f4); K-major core matrices hold 16 K values per 16-byte row
 template <int N>
@@ -1116,7 +993,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
         if (lane == 0) { f_ray[q] = r0; f_chunk[q] = 0; f_ray[4 + q] = r1; f_chunk[4 + q] = 0; }
         if (warp == 4 && lane == 0) *f_stop = 0;
       }
-      epi_bar_sync(1);
+      epi_bar_sync<512>(1);
       auto slot_alive = [&](int sl) { return (f_ray[4 * sl] >= 0) || (f_ray[4 * sl + 1] >= 0) || (f_ray[4 * sl + 2] >= 0) || (f_ray[4 * sl + 3] >= 0); };
       // encode the tile of slot `sl` (or announce the stop) and release the MMA issuer / weight producer for it
       auto pe_slot = [&](int sl, bool stop) {
@@ -1215,7 +1092,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
           }
         });
         if (warp == 4 && lane == 0 && P.stats != nullptr) atomicAdd(P.stats, 1ull);
-        epi_bar_sync(1);   // every quarter's next work item of slot `cur` is published
+        epi_bar_sync<512>(1);   // every quarter's next work item of slot `cur` is published
         const bool alive_this = slot_alive(cur);
         if (pe_done) {           // the other slot's tile is already encoded and released: it runs next
           alive_other = alive_this;
@@ -1225,7 +1102,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
           alive_cur = alive_this;
           pe_slot(cur, !alive_this);
         }
-        epi_bar_sync(2);   // nobody re-reads the descriptors of the finished tile after this point
+        epi_bar_sync<512>(2);   // nobody re-reads the descriptors of the finished tile after this point
       }
     }
   }

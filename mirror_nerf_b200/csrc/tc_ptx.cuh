@@ -1,5 +1,5 @@
-// tcgen05 / TMEM / mbarrier / bulk-copy PTX wrappers shared by the training GEMM kernels (train_tc.cu).
-// Same wrappers as field_tc.cu keeps privately; sm_100a only.
+// tcgen05 / TMEM / mbarrier / bulk-copy PTX wrappers shared by the inference field kernel (field_tc.cu) and the training GEMM
+// kernels (train_tc.cu); sm_100a only.
 #pragma once
 #include <stdint.h>
 #include <stdio.h>
@@ -38,6 +38,31 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (clock64() - t0 > 4000000000LL) {
       printf("mnrf train_tc: mbarrier timeout (block %d thread %d bar@%u parity %u)\n", blockIdx.x, threadIdx.x, bar,
              parity);
+      __trap();
+    }
+  }
+}
+// Spinning wait for the two single-thread roles (weight producer, MMA issuer): mbarrier.test_wait never suspends the thread, so
+// the role reacts within a few cycles of the phase flip.  try_wait may park the thread for an implementation-defined time;
+// measured with the device timeline: ~400 cycles between an arrive and the waiter's next instruction, twice per weight-stage
+// round trip (commit -> producer, copy complete -> issuer), which is what starved the 4-stage ring.
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
+  if (mbar_test(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_test(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("mnrf: mbarrier timeout (block %d thread %d bar@%u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
       __trap();
     }
   }
@@ -106,7 +131,14 @@ __device__ __forceinline__ bool elect_one() {
       : "+r"(pred));
   return pred != 0;
 }
-__device__ __forceinline__ void epi_bar_sync(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
+template <int THREADS = 256>
+__device__ __forceinline__ void epi_bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(THREADS) : "memory"); }
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, float a, float b, float c, float d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(a)),
+               "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // K-major, no-swizzle operand descriptors (see field_tc.cu): core matrix = 8 rows x 16 bytes stored as 128 contiguous bytes,
 // SBO (8-row group stride) = 128 B, LBO (K-adjacent core matrices) = rows * 16 B.  Low word = (addr >> 4) | (LBO >> 4) << 16.
