@@ -504,6 +504,18 @@ def run_ours(args):
             del full_host
             torch.cuda.empty_cache()
 
+    other = None
+    if args.field_impl != "tc3" and world == 1:
+        # the library's default parity mode (three fp16 passes) on the same workload, for context
+        def step3():
+            return render_rays_recursive(models, emb, rays_dev, N_SAMPLES, False, 0, 0, N_IMPORTANCE, 32768, False,
+                                         max_recursive_level=1, compact_outputs=not args.python_recursion, field_impl="tc3",
+                                         **({} if args.python_recursion else {"early_termination_eps": args.early_termination_eps}))
+        with torch.no_grad():
+            step3()
+            ms3 = timed(step3, max(2, min(args.steps, 5)))
+        other = {"field_impl": "tc3", "value": n * max(2, min(args.steps, 5)) / (ms3 * 1e-3), "unit": "rays/s",
+                 "what": "same workload with the library default (3 fp16 passes, operand error 2^-21)"}
     value = world * n * args.steps / (ms_total * 1e-3)
     e2e_value = world * n * e2e_steps / (ms_e2e * 1e-3)
     peaks = {}
@@ -544,6 +556,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": d2h_bytes,
                 "steps": e2e_steps, "d2h": "all %d tensors of the compact per-ray result" % len(out_host)},
         "e2e_full_dict": e2e_full,
+        "parity_mode": other,
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": (achieved / peak if achieved else None), "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write)",
@@ -673,7 +686,17 @@ def run_ours(args):
                 e = (a - b).abs() / b.abs().clamp_min(float(b.pow(2).mean().sqrt()))
                 q = torch.quantile(e, torch.tensor([0.5, 0.99], dtype=torch.double))
                 return {"median": float(q[0]), "p99": float(q[1]), "max": float(e.max()), "frac_gt_1e-3": float((e > 1e-3).double().mean())}
+            et = None
+            if not args.python_recursion:   # what early termination skips on a scene with opaque surfaces (the room)
+                with torch.no_grad():
+                    st = render_rays_recursive(rmodels, emb, rr.to(dev), N_SAMPLES, False, 0, 0, N_IMPORTANCE, 32768, False,
+                                               max_recursive_level=1, compact_outputs=True, with_stats=True,
+                                               early_termination_eps=args.early_termination_eps, **kw)["fused_stats"].cpu().tolist()
+                chunks = 2 * args.ref_rays * ((N_SAMPLES + N_IMPORTANCE + 31) // 32)
+                et = {"eps": args.early_termination_eps, "chunks_skipped": int(st[1]), "chunks_total": chunks,
+                      "skipped_frac": st[1] / chunks, "tiles_executed": int(st[0])}
             line["parity"] = {"rgb_fine": dist(our_rgb, ref_rgb), "rays": args.ref_rays, "field_impl": args.field_impl,
+                              "early_termination_on_room_scene": et,
                               "against": "oracle port of the reference on the same rays (fitted room field, 1 bounce, eval semantics)",
                               "bar": "north-star: rgb within 1e-3 relative, PSNR within 0.05 dB"}
             line["psnr"] = {"ours_db": ps(our_rgb), "reference_db": ps(ref_rgb), "delta_db": ps(our_rgb) - ps(ref_rgb),

@@ -192,6 +192,8 @@ int mnrf_field_create(mnrf_field** out, const float* const* tensors, void* strea
     mnrf_field_destroy(f);
     return 1;
   }
+  // padding floats of the fp32 section (e.g. behind b_rgb / b_m2 in the epilogue table) are copied around but never used
+  if (cudaMemsetAsync(f->f32, 0, sizeof(float) * f->L.total, S_(stream)) != cudaSuccess) { mnrf_field_destroy(f); return 1; }
   if (pack_field(f, tensors, S_(stream))) { mnrf_field_destroy(f); return 1; }
   *out = f;
   return 0;

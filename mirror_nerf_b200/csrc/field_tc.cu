@@ -1115,6 +1115,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
   }
+  if (FUSE && threadIdx.x == 0) {
+    // the last CTA to finish rewinds the work queue, so the launch can be replayed as is (ncu kernel replay, CUDA graphs)
+    if (atomicAdd(P.work_counter + 1, 1) == (int)gridDim.x - 1) {
+      P.work_counter[0] = 0;
+      P.work_counter[1] = 0;
+    }
+  }
 }
 
 }  // namespace
@@ -1213,7 +1220,7 @@ int launch_field_tc(const mnrf_field* f, const FieldIO& io, int precision, cudaS
   if (fuse != nullptr) {
     P.comp = fuse->comp; P.n_rays = io.n_points / io.S; P.white_back = fuse->white_back; P.term_eps = fuse->term_eps;
     P.work_counter = fuse->work_counter; P.stats = fuse->stats;
-    MNRF_CUDA_OK(cudaMemsetAsync(fuse->work_counter, 0, sizeof(int), st));
+    MNRF_CUDA_OK(cudaMemsetAsync(fuse->work_counter, 0, 2 * sizeof(int), st));   // [0] next ray, [1] CTAs finished
   }
   {
     static const int dbg = getenv("MNRF_TC_DEBUG") != nullptr ? atoi(getenv("MNRF_TC_DEBUG")) : 0;
