@@ -31,14 +31,33 @@ _SHAPES = {"sigma_net.0.weight": (64, 32), "sigma_net.1.weight": (16, 64), "colo
            "is_mirror_net.2.weight": (1, 32), "is_mirror_net.2.bias": (1,)}
 
 
+
+def _libm_f32(name):
+    """glibc's float32 `name` (what tinycudann's host code calls); numpy's float32 ufunc if libm cannot be loaded."""
+    try:
+        import ctypes
+        f = getattr(ctypes.CDLL("libm.so.6"), name)
+        f.restype, f.argtypes = ctypes.c_float, [ctypes.c_float]
+        return lambda x: np.float32(f(float(np.float32(x))))
+    except Exception:
+        return {"log2f": lambda x: np.log2(np.float32(x)), "exp2f": lambda x: np.exp2(np.float32(x))}[name]
+
+
+_log2f, _exp2f = _libm_f32("log2f"), _libm_f32("exp2f")
+
+
 def level_table(bound=1.0):
     """Per level (grid scale, resolution, first table entry, entries) and the total number of entries, as tinycudann builds
     them (grid.h): scale_l = 2^(l*log2(per_level_scale))*16 - 1 in fp32, resolution = ceil(scale)+1, entries = min(round_up(
     res^3, 8), 2^19); per_level_scale = 2^(log2(2048*bound/16)/15) (R/models/mirror_nerf_tcnn.py:38)."""
-    log2_pls = math.log2(float(np.exp2(np.log2(2048 * bound / N_LEVELS) / (N_LEVELS - 1))))
+    # tinycudann does this arithmetic in float32 on the host (grid.h: per_level_scale is read into a float,
+    # grid_scale = exp2f(level * log2f(per_level_scale)) * base_resolution - 1.0f); a double-precision log2 differs in the last
+    # ulp of the scale and, for some bounds (e.g. 0.5), in the resolution of a level, i.e. in the indexing
+    pls = np.float32(np.exp2(np.log2(2048 * bound / N_LEVELS) / (N_LEVELS - 1)))
+    log2_pls = _log2f(pls)
     out, offset = [], 0
     for lvl in range(N_LEVELS):
-        scale = float(np.float32(np.exp2(np.float32(lvl * log2_pls)) * BASE_RES - 1.0))
+        scale = float(_exp2f(np.float32(lvl) * log2_pls) * np.float32(BASE_RES) - np.float32(1.0))
         res = int(math.ceil(scale)) + 1
         n = min((res ** 3 + 7) // 8 * 8, 1 << LOG2_HASHMAP)
         out.append((scale, res, offset, n))

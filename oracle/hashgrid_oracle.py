@@ -33,12 +33,29 @@ def per_level_scale(bound=1.0):
     return float(np.exp2(np.log2(2048 * bound / N_LEVELS) / (N_LEVELS - 1)))
 
 
+
+def _libm_f32(name):
+    """glibc's float32 `name` (what tinycudann's host code calls); numpy's float32 ufunc if libm cannot be loaded."""
+    try:
+        import ctypes
+        f = getattr(ctypes.CDLL("libm.so.6"), name)
+        f.restype, f.argtypes = ctypes.c_float, [ctypes.c_float]
+        return lambda x: np.float32(f(float(np.float32(x))))
+    except Exception:
+        return {"log2f": lambda x: np.log2(np.float32(x)), "exp2f": lambda x: np.exp2(np.float32(x))}[name]
+
+
+_log2f, _exp2f = _libm_f32("log2f"), _libm_f32("exp2f")
+
+
 def level_table(bound=1.0):
     """[(scale, resolution, offset, size)] per level (grid.h: offset table construction) and the total entry count."""
-    log2_pls = math.log2(per_level_scale(bound))
+    # float32 host arithmetic as in tinycudann's grid.h (per_level_scale read into a float, log2f, exp2f)
+    pls = np.float32(per_level_scale(bound))
+    log2_pls = _log2f(pls)
     out, offset = [], 0
     for lvl in range(N_LEVELS):
-        scale = float(np.float32(np.exp2(np.float32(lvl * log2_pls)) * BASE_RES - 1.0))
+        scale = float(_exp2f(np.float32(lvl) * log2_pls) * np.float32(BASE_RES) - np.float32(1.0))
         res = int(math.ceil(scale)) + 1
         n = res ** 3
         n = (n + 7) // 8 * 8
