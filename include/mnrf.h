@@ -388,6 +388,11 @@ int mnrf_profile_collect(double* total_ms, double* total_flops, int64_t* launche
 /* Bring-up aid: CTA 0 of the tcgen05 field kernel logs (clock64, tag) pairs into buf = uint64[1 + 2*capacity]
  * (buf[0] = event count; zero it first).  NULL disables. */
 int mnrf_debug_set_trace(void* buf, int64_t capacity_events);
+/* Schedule of the 256-wide layers in the MNRF_IMPL_TC2 kernels: 1 = N-split (two 128-column halves per layer, the first half's
+ * epilogue overlaps the second half's MMAs), 0 = one N = 256 accumulation per layer, -1 = library default (environment
+ * variable MNRF_TC_SPLIT, else the built-in default).  Same arithmetic per accumulator element either way; returns the
+ * schedule now in force.  A measurement / regression knob, not part of the reference's interface. */
+int mnrf_debug_set_tc_schedule(int split);
 /* algorithmic MACs per point (unpadded layer dims): full forward / sigma-only+pred-normal */
 int64_t mnrf_macs_full(void);
 int64_t mnrf_macs_sigma_only(void);

@@ -72,6 +72,7 @@ _SIGS = {
     "mnrf_profile_enable": (c_int, [c_int]),
     "mnrf_profile_collect": (c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "mnrf_debug_set_trace": (c_int, [C.c_void_p, C.c_int64]),
+    "mnrf_debug_set_tc_schedule": (c_int, [c_int]),
     "mnrf_macs_full": (C.c_int64, []),
     "mnrf_macs_sigma_only": (C.c_int64, []),
     "mnrf_field_create": (c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]),

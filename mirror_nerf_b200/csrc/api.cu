@@ -162,6 +162,7 @@ int mnrf_debug_set_trace(void* buf, int64_t capacity_events) {
   set_tc_trace(reinterpret_cast<unsigned long long*>(buf), (unsigned int)capacity_events);
   return 0;
 }
+int mnrf_debug_set_tc_schedule(int split) { return set_tc_split(split); }
 int64_t mnrf_macs_full(void) {
   // trunk 491,264 + colour 102,144 + normal 33,152 + mirror 32,896
   return 659456;
@@ -187,7 +188,7 @@ int mnrf_field_create(mnrf_field** out, const float* const* tensors, void* strea
   f->tc8 = nullptr;
   f->t32 = nullptr;
   if (cudaMalloc(&f->f32, sizeof(float) * f->L.total) != cudaSuccess || cudaMalloc(&f->tc, TC_TOTAL_BYTES) != cudaSuccess ||
-      cudaMalloc(&f->tc8, TC_TOTAL_BYTES) != cudaSuccess || cudaMalloc(&f->t32, T32_TOTAL_BYTES) != cudaSuccess) {
+      cudaMalloc(&f->tc8, 2 * (size_t)TC_TOTAL_BYTES) != cudaSuccess || cudaMalloc(&f->t32, T32_TOTAL_BYTES) != cudaSuccess) {
     set_error("field_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
     mnrf_field_destroy(f);
     return 1;

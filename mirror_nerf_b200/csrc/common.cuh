@@ -53,6 +53,7 @@ __host__ __device__ constexpr int tc_step_offset(int s) {
   return o;
 }
 constexpr int TC_TOTAL_BYTES = tc_step_offset(TC_NUM_STEPS);
+constexpr int TC_SPLIT_LAST = 8;   // steps 0..8 (the 256-wide forward layers) also exist in the N-split layout of the tc2 blobs (pack.cu)
 
 // tf32 hi/lo blobs of the training GEMMs (train_tc.cu): steps 0..19 as above plus
 //   20: normal_net.0 (N128,K256)   21: dir layer^T, feature part (N256,K128)   22: final^T (N256,K256)
@@ -183,7 +184,8 @@ struct mnrf_field {
   int has_mirror;
   float* f32;        // device, mnrf::F32Layout
   uint8_t* tc;       // device, TC_TOTAL_BYTES of fp16 hi/lo blobs
-  uint8_t* tc8;      // device, TC_TOTAL_BYTES: per K32 chunk [fp16 hi | e4m3(2^-10 hi), e4m3(lo)] blobs of the fp8-corrected mode
+  uint8_t* tc8;      // device, 2 x TC_TOTAL_BYTES: per K32 chunk [fp16 hi | e4m3(2^-10 hi), e4m3(lo)] blobs of the fp8-corrected mode,
+                     // then the same step offsets again with steps 0..TC_SPLIT_LAST in the N-split layout (pack.cu k_pack_tc8)
   uint8_t* t32;      // device, T32_TOTAL_BYTES of tf32 hi/lo blobs (training GEMMs)
   mnrf::F32Layout L;
   unsigned long long pack_stamp;  // unique per pack_field call (keys the constant-memory copies of the epilogue table)
@@ -344,6 +346,7 @@ int render_level(const mnrf_field* coarse, const mnrf_field* fine, const float* 
                  const mnrf_level_rng* rng, const float* z_steps, const float* u_det, void* workspace, int64_t workspace_bytes,
                  const mnrf_level_out* out, void* stream, const int* n_dev);
 void set_tc_trace(unsigned long long* buf, unsigned int cap);
+int set_tc_split(int split);   // -1 = default (MNRF_TC_SPLIT or built-in); returns the schedule in force
 // compositing fused into the tensor-core field kernel (field_tc.cu FUSE): per-ray outputs straight from the epilogue registers
 struct FusedComposite {
   mnrf_composite_out comp;     // opacity required; weights / pred_normal (per sample) optional

@@ -40,8 +40,16 @@ using namespace tcx;
 constexpr int TILE_M = 128;
 constexpr int NUM_THREADS = 640;
 // warp 0: weight producer; warp 1: MMA issuer; warps 4..19: epilogue/PE (TMEM lane quarter = warp % 4, column group = (warp-4)/4).
+#ifdef MNRF_TC_ROLES_HIGH
+// experiment: the two single-thread roles on the highest warp ids (the warp arbiter favours them, tools/mma_bench4.cu)
+constexpr int EPI_WARP0 = 0;
+constexpr int WARP_PRODUCER = 16;
+constexpr int WARP_MMA = 17;
+#else
+constexpr int EPI_WARP0 = 4;
 constexpr int WARP_PRODUCER = 0;
 constexpr int WARP_MMA = 1;
+#endif
 constexpr uint32_t WSTAGE_BYTES = 16384;
 
 constexpr uint32_t SM_A_HI = 0;
@@ -61,6 +69,8 @@ constexpr int BAR_PE = 16;       // PE chunk written (16 warp arrivals)
 constexpr int BAR_A = 17;        // [5] A columns written (4 warp arrivals: one column group): [0] cols 0-31, [4] cols 32-63, [1..3] 64-col chunks 1..3
 constexpr int BAR_ACC = 22;      // [4] accumulator of a GEMM step complete (tcgen05.commit)
 constexpr int BAR_GO = 26;       // fused mode: "next tile is decided" for the weight producer (8 warp arrivals, like BAR_PE)
+constexpr int BAR_ACCH = 27;     // N-split schedule: the first 128 accumulator columns of a layer are complete (tcgen05.commit)
+constexpr int BAR_AFREE = 28;    // [2] N-split schedule: the layer's MMAs have read A chunk 0 / 1 for the last time (tcgen05.commit)
 constexpr int BAR_TMEM_SLOT = 30;
 
 constexpr uint32_t IDESC_N256 = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);  // f16 x f16 -> f32, K-major
@@ -70,6 +80,8 @@ constexpr uint32_t IDESC_N64 = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 
 struct TcParams {
   const float* f32;        // fp32 section
   const uint8_t* tc;       // packed blobs
+  const uint8_t* tc_split; // tc2 only: the same step offsets with steps 0..TC_SPLIT_LAST in the N-split layout (pack.cu)
+  int split;               // tc2, no analytic normals: run the 256-wide layers as two 128-column halves (see issue_split_step)
   int b_trunk[8];
   int b_final, b_m0, w_m2, b_m2, w_rgb, b_rgb, headw, headb, inv_scale;
   int has_normal, has_mirror;
@@ -156,6 +168,71 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint32_t a_lo32, uint32_
       : "memory");
 }
 
+// ---- N-split schedule of a 256-wide layer (tc2) ------------------------------------------------------------------------------
+// The layer is issued as two N = 128 GEMMs over the full K: columns [0,128) first, then [128,256), each into its own half of the
+// layer's accumulator and with its own completion barrier.  The epilogue of the first half (the next layer's A chunks 0 and 1)
+// then runs WHILE the tensor pipe works on the second half, so the next layer's MMAs find half of their operand in place the
+// moment this layer's last MMA is issued; the hand-over bubble of the unsplit schedule (accumulator drain -> TMEM load ->
+// convert -> proxy fence -> barrier, ~2,000 cycles per layer with the pipe idle) shrinks to the tail of the second half.
+// The in-place A operand needs one more ordering: the first half's epilogue overwrites A chunks 0/1 while the second half's
+// MMAs still read the OLD operand, so the issuer commits BAR_AFREE[c] right after the second half's last MMAs on chunk c.
+// One 16 KB weight stage per (half, K32 chunk) in the N = 128 blob format (pack.cu); every step consumes a multiple of 4 stages,
+// so a step starts at ring position 0 and the ring position of every stage is a compile-time constant of the unrolled loop
+// (measured, tools/mma_bench4.cu: 282 vs 363 cycles per N = 128 stage against the run-time stage index).  The PE operand of
+// step 0 is awaited once in front of the step (WAIT_PE: static tiles; fused tiles wait at the tile start).
+struct SplitCtx {
+  uint32_t bars;                        // shared address of barrier slot 0
+  uint32_t wdesc0;                      // descriptor low word of weight stage 0 (LBO 2048); stage st is + st * 1024
+  uint32_t dl_a_hi, dl_a8, dl_a8r;      // A operand: fp16 hi, e4m3 copy, e4m3 residual
+  uint32_t dl_pe_hi, dl_pe8, dl_pe8r;   // PE operand
+};
+template <int NCH, int NPE, bool WAIT_PE, class Tracer>
+__device__ __forceinline__ void issue_split_step(const SplitCtx& c, uint32_t d_base, int acc_slot, bool a_reused, uint32_t& phase,
+                                                 uint32_t& a_phase, uint32_t& pe_phase, Tracer&& tr) {
+  static_assert((2 * NCH) % 4 == 0, "a split step must consume whole trips of the 4-stage ring");
+  constexpr int K0 = (NPE + 1 < NCH - 1) ? NPE + 1 : NCH - 1;   // last K32 chunk that reads A chunk 0 / chunk 1 (PE-only
+  constexpr int K1 = (NPE + 3 < NCH - 1) ? NPE + 3 : NCH - 1;   // layer: nothing reads the A buffer, signal at the end)
+  auto bar = [&](int i) { return c.bars + 8u * (uint32_t)i; };
+  if (WAIT_PE) { mbar_spin(bar(BAR_PE), pe_phase); pe_phase ^= 1u; }
+  // Fully unrolled: half, K chunk and ring position of every stage are compile-time constants, so each descriptor is a uniform
+  // base register plus an immediate -- the issuing thread shares its scheduler with four epilogue warps and its dependent
+  // address arithmetic (14 R2UR per stage with run-time indices), not the tensor pipe, set the stage time.
+#pragma unroll
+  for (int t = 0; t < (2 * NCH) / 4; ++t) {   // one trip around the ring
+#pragma unroll
+    for (int st = 0; st < 4; ++st) {
+      const int i = 4 * t + st;
+      const int h = i >= NCH ? 1 : 0, kc = i - h * NCH;
+      uint32_t ah, a8, a8r;
+      if (kc < NPE) {
+        ah = c.dl_pe_hi + (uint32_t)kc * 512u; a8 = c.dl_pe8 + (uint32_t)kc * 256u; a8r = c.dl_pe8r + (uint32_t)kc * 256u;
+      } else {
+        const int ka = kc - NPE;
+        if (h == 0 && ((ka & 1) == 0 || ka == 1) && !a_reused) {   // first touch of freshly written activation columns
+          const int cb = ka == 1 ? 4 : (ka >> 1);
+          mbar_spin(bar(BAR_A + cb), (a_phase >> cb) & 1u);
+          a_phase ^= 1u << cb;
+        }
+        ah = c.dl_a_hi + (uint32_t)ka * 512u; a8 = c.dl_a8 + (uint32_t)ka * 256u; a8r = c.dl_a8r + (uint32_t)ka * 256u;
+      }
+      mbar_spin(bar(BAR_W_FULL + st), phase);
+      tc_fence_after();
+      tr(i);   // trace builds: this stage's operands are in place, its MMAs are issued now
+      const uint32_t wb = c.wdesc0 + (uint32_t)st * 1024u;
+      const uint32_t d = d_base + 128u * (uint32_t)h;
+      tc_mma<128>(d, ah, wb, kc > 0 ? 1u : 0u);
+      tc_mma<128>(d, ah + 256u, wb + 256u, 1u);
+      tc_mma_f8<128>(d, a8r, wb + 512u, 1u);     // (2^10 A_lo) * (2^-10 W_hi)
+      tc_mma_f8<128>(d, a8, wb + 768u, 1u);      // A_hi * W_lo
+      tc_commit(bar(BAR_W_EMPTY + st));
+      if (h == 1 && kc == K0) tc_commit(bar(BAR_AFREE + 0));
+      if (h == 1 && kc == K1) tc_commit(bar(BAR_AFREE + 1));
+      if (kc == NCH - 1) tc_commit(h == 0 ? bar(BAR_ACCH) : bar(BAR_ACC + acc_slot));
+    }
+    phase ^= 1u;
+  }
+}
+
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
 // ---- x = hi + lo in fp16, two values per 32-bit word (element 0 in the low half) -----------------------------------
@@ -166,8 +243,10 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
     if (RELU) asm("cvt.rz.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
     else      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
     const float2 hf = __half22float2(*reinterpret_cast<__half2*>(&hi));
-    if (RELU) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - hf.y), "f"(a - hf.x));
-    else      asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - hf.y), "f"(a - hf.x));
+    float ra, rb;   // both residuals with one packed subtraction (FADD2)
+    f2_unpack(f2_sub(f2_pack(a, b), f2_pack(hf.x, hf.y)), ra, rb);
+    if (RELU) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
+    else      asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
   } else {
     if (RELU) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
     else      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
@@ -196,18 +275,24 @@ __device__ __forceinline__ uint32_t cvt_e4m3x2(float a, float b) {  // {low byte
   return (uint32_t)r;
 }
 template <bool RELU>
-__device__ __forceinline__ void store_a16_tc2(uint32_t hi16_addr, uint32_t a8_addr, uint32_t lo8_off, const float (&v)[16]) {
+__device__ __forceinline__ void store_a16_tc2(uint32_t hi16_addr, uint32_t a8_addr, uint32_t lo8_off, const f32x2 (&v)[8]) {
   uint32_t h[8], x8[4], l8[4];
+  const f32x2 k_pos = f2_pack(1024.f, 1024.f), k_neg = f2_pack(-1024.f, -1024.f);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const float a = v[2 * i], b = v[2 * i + 1];
+    float a, b;
+    f2_unpack(v[i], a, b);
     // The ReLU rides on the conversions (no separate max): hi = rz(relu(x)) so that the residual of a positive value is >= 0;
     // for x < 0: hi = 0 and the residual x - 0 < 0 is clamped by the relu of its own conversion.  Signed values: rn, no relu.
     if (RELU) asm("cvt.rz.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(b), "f"(a));
     else      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(b), "f"(a));
     const float2 hf = __half22float2(*reinterpret_cast<__half2*>(&h[i]));
     const uint32_t xa = cvt_e4m3x2<RELU>(a, b);
-    const uint32_t la = cvt_e4m3x2<RELU>((a - hf.x) * 1024.f, (b - hf.y) * 1024.f);
+    // 2^10 (x - hi), both lanes at once: x - hi is exact (hi is x with low mantissa bits removed) and so is the scaling, hence
+    // fma(x, 1024, -1024 hi) returns the same bits as the scalar (x - hi) * 1024
+    float la_, lb_;
+    f2_unpack(f2_fma(v[i], k_pos, f2_mul(f2_pack(hf.x, hf.y), k_neg)), la_, lb_);
+    const uint32_t la = cvt_e4m3x2<RELU>(la_, lb_);
     if (i & 1) { x8[i >> 1] |= xa << 16; l8[i >> 1] |= la << 16; }
     else       { x8[i >> 1] = xa;        l8[i >> 1] = la; }
   }
@@ -249,7 +334,10 @@ __device__ __forceinline__ void pe_fill(const float (&x)[3], uint32_t pe_hi, uin
   }
   if (PREC == 2) {
     // pe_lo = base of the e4m3 copies: [x (8 KB) | 2^10 residual (8 KB)], 16 K values per core-matrix row
-    store_a16_tc2<false>(pe_hi + (uint32_t)(2 * QUARTER) * 2048u + rowoff, pe_lo + (uint32_t)QUARTER * 2048u + rowoff, 8192u, vals);
+    f32x2 v2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v2[i] = f2_pack(vals[2 * i], vals[2 * i + 1]);
+    store_a16_tc2<false>(pe_hi + (uint32_t)(2 * QUARTER) * 2048u + rowoff, pe_lo + (uint32_t)QUARTER * 2048u + rowoff, 8192u, v2);
     return;
   }
 #pragma unroll
@@ -271,25 +359,30 @@ __device__ __forceinline__ void epi_cols(const uint32_t (&r)[NC], const float4 (
                                          int bit0) {
   if (PREC == 2) {
     // s_lo = address of this thread's e4m3 row for the first 16 columns (see layer_epilogue); residual copy 32 KB behind
+    const f32x2 inv2 = f2_pack(inv, inv);
 #pragma unroll
     for (int j = 0; j < NC / 16; ++j) {
-      float v[16];
+      f32x2 v[8];   // 16 values as packed fp32 pairs (FFMA2: half the issue slots of the scalar bias / scale FMAs)
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float4 bb = b[4 * j + i];
-        v[4 * i + 0] = fmaf(__uint_as_float(r[16 * j + 4 * i + 0]), inv, bb.x);
-        v[4 * i + 1] = fmaf(__uint_as_float(r[16 * j + 4 * i + 1]), inv, bb.y);
-        v[4 * i + 2] = fmaf(__uint_as_float(r[16 * j + 4 * i + 2]), inv, bb.z);
-        v[4 * i + 3] = fmaf(__uint_as_float(r[16 * j + 4 * i + 3]), inv, bb.w);
+        v[2 * i + 0] = f2_fma(f2_pack(__uint_as_float(r[16 * j + 4 * i + 0]), __uint_as_float(r[16 * j + 4 * i + 1])), inv2, f2_pack(bb.x, bb.y));
+        v[2 * i + 1] = f2_fma(f2_pack(__uint_as_float(r[16 * j + 4 * i + 2]), __uint_as_float(r[16 * j + 4 * i + 3])), inv2, f2_pack(bb.z, bb.w));
       }
       if (DOTS) {
+        f32x2 d01 = f2_pack(d[0], d[1]), d23 = f2_pack(d[2], d[3]);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          v[i] = fmaxf(v[i], 0.f);
-          const float4 w = hw[16 * j + i];
-          d[0] = fmaf(v[i], w.x, d[0]); d[1] = fmaf(v[i], w.y, d[1]);
-          d[2] = fmaf(v[i], w.z, d[2]); d[3] = fmaf(v[i], w.w, d[3]);
+        for (int i = 0; i < 8; ++i) {
+          float a0, a1;
+          f2_unpack(v[i], a0, a1);
+          a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f);
+          v[i] = f2_pack(a0, a1);
+          const float4 w0 = hw[16 * j + 2 * i], w1 = hw[16 * j + 2 * i + 1];
+          d01 = f2_fma(f2_pack(a0, a0), f2_pack(w0.x, w0.y), d01); d23 = f2_fma(f2_pack(a0, a0), f2_pack(w0.z, w0.w), d23);
+          d01 = f2_fma(f2_pack(a1, a1), f2_pack(w1.x, w1.y), d01); d23 = f2_fma(f2_pack(a1, a1), f2_pack(w1.z, w1.w), d23);
         }
+        f2_unpack(d01, d[0], d[1]);
+        f2_unpack(d23, d[2], d[3]);
       }
       if (WRITE_A) store_a16_tc2<RELU>(s_hi + (uint32_t)j * 4096u, s_lo + (uint32_t)j * 2048u, 32768u, v);
     }
@@ -303,27 +396,28 @@ __device__ __forceinline__ void epi_cols(const uint32_t (&r)[NC], const float4 (
       for (int i = 0; i < 8; ++i) v[i] = ((mbits >> (bit0 + 8 * j + i)) & 1u) ? __uint_as_float(r[8 * j + i]) * inv : 0.f;
     } else {
       const float4 b0 = b[2 * j], b1 = b[2 * j + 1];
-      v[0] = fmaf(__uint_as_float(r[8 * j + 0]), inv, b0.x);
-      v[1] = fmaf(__uint_as_float(r[8 * j + 1]), inv, b0.y);
-      v[2] = fmaf(__uint_as_float(r[8 * j + 2]), inv, b0.z);
-      v[3] = fmaf(__uint_as_float(r[8 * j + 3]), inv, b0.w);
-      v[4] = fmaf(__uint_as_float(r[8 * j + 4]), inv, b1.x);
-      v[5] = fmaf(__uint_as_float(r[8 * j + 5]), inv, b1.y);
-      v[6] = fmaf(__uint_as_float(r[8 * j + 6]), inv, b1.z);
-      v[7] = fmaf(__uint_as_float(r[8 * j + 7]), inv, b1.w);
+      const f32x2 inv2 = f2_pack(inv, inv);   // scale + bias as packed pairs (FFMA2)
+      f2_unpack(f2_fma(f2_pack(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1])), inv2, f2_pack(b0.x, b0.y)), v[0], v[1]);
+      f2_unpack(f2_fma(f2_pack(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])), inv2, f2_pack(b0.z, b0.w)), v[2], v[3]);
+      f2_unpack(f2_fma(f2_pack(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])), inv2, f2_pack(b1.x, b1.y)), v[4], v[5]);
+      f2_unpack(f2_fma(f2_pack(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])), inv2, f2_pack(b1.z, b1.w)), v[6], v[7]);
     }
     if (MASK == 1) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) mbits |= (v[i] > 0.f ? 1u : 0u) << (bit0 + 8 * j + i);
     }
     if (DOTS) {
+      f32x2 d01 = f2_pack(d[0], d[1]), d23 = f2_pack(d[2], d[3]);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         v[i] = fmaxf(v[i], 0.f);
         const float4 w = hw[8 * j + i];
-        d[0] = fmaf(v[i], w.x, d[0]); d[1] = fmaf(v[i], w.y, d[1]);
-        d[2] = fmaf(v[i], w.z, d[2]); d[3] = fmaf(v[i], w.w, d[3]);
+        const f32x2 vv = f2_pack(v[i], v[i]);
+        d01 = f2_fma(vv, f2_pack(w.x, w.y), d01);
+        d23 = f2_fma(vv, f2_pack(w.z, w.w), d23);
       }
+      f2_unpack(d01, d[0], d[1]);
+      f2_unpack(d23, d[2], d[3]);
     }
     if (WRITE_A) store_a8<RELU, PREC>(s_hi + (uint32_t)j * 2048u, s_lo + (uint32_t)j * 2048u, v);
   }
@@ -367,8 +461,9 @@ __device__ __forceinline__ int step_at(int i) { return i < 8 ? i : (i == 8 ? 9 :
 // known one tile ahead for the positional encoding); the epilogue composites the chunk in registers with the arithmetic of
 // composite.cu (same warp scan, same running carry: bit-identical), optionally stops a ray whose transmittance fell below
 // term_eps, and writes per-ray outputs -- no per-point record goes through HBM.  R/models/rendering.py:175-264,363-367.
-template <int PREC, bool NORMALS, bool FUSE = false>
+template <int PREC, bool NORMALS, bool FUSE = false, bool SPLIT = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
+  static_assert(!SPLIT || (PREC == 2 && !NORMALS), "the N-split schedule exists for the tc2 kernels without analytic normals");
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5;
@@ -399,7 +494,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
     for (int i = 0; i < 8; ++i) { mbar_init(bar(BAR_W_FULL + i), 1); mbar_init(bar(BAR_W_EMPTY + i), 1); }
     mbar_init(bar(BAR_PE), 16);   // one arrival per epilogue warp
     mbar_init(bar(BAR_GO), 16);
-    for (int i = 0; i < 5; ++i) mbar_init(bar(BAR_A + i), 4);  // a chunk (or half of chunk 0) is written by one column group: 4 warps
+    // a chunk (or half of chunk 0) is written by one column group: 4 warps; N-split schedule: every warp writes 16 columns of
+    // every chunk (the halves of chunk 0 come from groups 0,1 / 2,3)
+    for (int i = 0; i < 5; ++i) mbar_init(bar(BAR_A + i), SPLIT ? ((i == 0 || i == 4) ? 8 : 16) : 4);
+    mbar_init(bar(BAR_ACCH), 1);
+    mbar_init(bar(BAR_AFREE), 1);
+    mbar_init(bar(BAR_AFREE + 1), 1);
     for (int i = 0; i < 4; ++i) mbar_init(bar(BAR_ACC + i), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -430,7 +530,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
         for (int i = 0; i < n_issue; ++i) {
           const int s = step_at(i);
           if (s == 9 && !P.has_mirror) continue;
-          const uint8_t* src = P.tc + tc_step_offset(s);
+          // N-split steps: 2 * nch stages of 16 KB, contiguous in (half, K32 chunk) order -- the same walk as the unsplit layout
+          const uint8_t* src = ((SPLIT && s <= TC_SPLIT_LAST) ? P.tc_split : P.tc) + tc_step_offset(s);
           const int sn = tc_step_n(s);
           const bool wide = sn == 256;
           const int nch = tc_step_chunks(s);
@@ -477,6 +578,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
       const uint32_t dl_a8 = dl_a_lo, dl_a8r = desc_lo(sbase + SM_A_LO + 32768u, 2048);
       const uint32_t dl_pe8 = dl_pe_lo, dl_pe8r = desc_lo(sbase + SM_PE_LO + 8192u, 2048);
       auto next_stage = [&]() { if (++stage == NST) { stage = 0; phase ^= 1u; } };
+      SplitCtx sc;
+      sc.bars = bars; sc.wdesc0 = desc_lo(sbase + SM_WST, 2048);
+      sc.dl_a_hi = dl_a_hi; sc.dl_a8 = dl_a8; sc.dl_a8r = dl_a8r; sc.dl_pe_hi = dl_pe_hi; sc.dl_pe8 = dl_pe8; sc.dl_pe8r = dl_pe8r;
       for (int tile = blockIdx.x; FUSE || tile < n_tiles; tile += gridDim.x) {
         unsigned int w_pe = 0, w_a = 0, w_w = 0;   // trace builds: cycles blocked on the PE / activation / weight barriers
         (void)w_pe; (void)w_a; (void)w_w;
@@ -504,6 +608,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
           const uint32_t d_tmem = tmem + acc_col(s);
           uint32_t accumulate = 0;
           trace_ev(P, trc, 0, 1, 1, s, 0);
+          if constexpr (SPLIT) if (s <= TC_SPLIT_LAST) {
+            // the ring is at position 0 here: every step of this mode consumes a multiple of 4 stages
+            auto tr = [&](int i) { trace_ev(P, trc, 0, 1, 4, s, i); };
+            if (s == 0) issue_split_step<2, 2, !FUSE>(sc, d_tmem, acc_bar(s), a_reused, phase, a_phase, pe_phase, tr);
+            else if (s == 4) issue_split_step<10, 2, false>(sc, d_tmem, acc_bar(s), a_reused, phase, a_phase, pe_phase, tr);
+            else issue_split_step<8, 0, false>(sc, d_tmem, acc_bar(s), a_reused, phase, a_phase, pe_phase, tr);
+            trace_ev(P, trc, 0, 1, 3, s, 0);
+            continue;
+          }
           for (int kc = 0; kc < nch; ++kc) {
             uint32_t ah, al;  // descriptor low words of this K32 chunk of the A operand (hi / lo parts)
             uint32_t a8 = 0, a8r = 0;  // tc2: e4m3 copy of the chunk and of its residual
@@ -614,9 +727,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
         trace_val(P, trc, 1, 5, w_pe); trace_val(P, trc, 1, 6, w_a); trace_val(P, trc, 1, 7, w_w);
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + 16) {
     // =========================== epilogue / PE warps ===========================
-    const int ew = warp - 4;       // 0..15
+    const int ew = warp - EPI_WARP0;       // 0..15
     const int q = ew & 3;          // TMEM lane quarter == warp_id % 4
     const int g = ew >> 2;         // 16-column quarter of every 64-column chunk (32-column quarter of the 128-wide heads)
     const int row = q * 32 + lane;
@@ -758,6 +871,79 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
       }
     };
 
+    // N-split schedule (issue_split_step): this warp owns columns [64c + 16g, +16) of every 64-column chunk c, chunks in K
+    // order.  Chunks 0 and 1 come from the first accumulator half (ready while the second half's MMAs still run; their stores
+    // wait until those MMAs have read the old A chunk for the last time), chunks 2 and 3 from the second half.  Chunk 0 is
+    // signalled in two 32-column halves (groups 0,1 -> BAR_A[0], groups 2,3 -> BAR_A[4]).
+    uint32_t acch_phase = 0, afree_phase = 0;
+    auto layer_epilogue_split = [&](auto tag, int s, const float* bias256, float (&d)[4]) {
+      constexpr bool RELU = decltype(tag)::relu, DOTS = decltype(tag)::dots, WRITE_A = decltype(tag)::write_a;
+      const float4* b4 = reinterpret_cast<const float4*>(bias256) + 4 * g;
+      const float inv = c_epi[ET_INV_SCALE + s] * 0.03125f;   // tc2 blobs carry 2^5 more scale (pack.cu)
+      uint32_t mk = 0u;
+      float4 b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) b[i] = b4[i];
+      const uint32_t tcol = tlane + acc_col(s) + 16u * (uint32_t)g;
+      uint32_t ra[16], rb[16];
+      // ---- first half: chunks 0, 1 ----
+      mbar_wait(bar(BAR_ACCH), acch_phase);
+      acch_phase ^= 1u;
+      tc_fence_after();
+      if (q == 0) trace_ev(P, trc, lane, 4 + g, 10, s, 0);
+      tmem_ld16(tcol, ra);
+      tmem_wait_ld();
+      tmem_ld16(tcol + 64u, rb);
+      pin<16>(ra);
+      mbar_wait(bar(BAR_AFREE + 0), afree_phase & 1u);   // the second half's MMAs are past A chunk 0
+      tc_fence_after();
+      {
+        const uint32_t off = (uint32_t)(2 * g) * 2048u + rowoff;
+        epi_cols<16, RELU, DOTS, WRITE_A, PREC, 0>(ra, b, inv, sbase + SM_A_HI + off, lo_addr(off), headw + 16 * g, d, mk, 0);
+        if (WRITE_A) a_ready(g < 2 ? 0 : 4);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) b[i] = b4[16 + i];
+      tmem_wait_ld();
+      pin<16>(rb);
+      mbar_wait(bar(BAR_AFREE + 1), (afree_phase >> 1) & 1u);
+      afree_phase ^= 3u;
+      tc_fence_after();
+      {
+        const uint32_t off = (uint32_t)(8 + 2 * g) * 2048u + rowoff;
+        epi_cols<16, RELU, DOTS, WRITE_A, PREC, 0>(rb, b, inv, sbase + SM_A_HI + off, lo_addr(off), headw + 64 + 16 * g, d, mk, 0);
+        if (WRITE_A) a_ready(1);
+      }
+      // ---- second half: chunks 2, 3 ----
+#pragma unroll
+      for (int i = 0; i < 4; ++i) b[i] = b4[32 + i];
+      {
+        const int ab = acc_bar(s);
+        mbar_wait(bar(BAR_ACC + ab), (acc_phase >> ab) & 1u);
+        acc_phase ^= 1u << ab;
+        tc_fence_after();
+        if (q == 0) trace_ev(P, trc, lane, 4 + g, 20, s, 0);
+      }
+      tmem_ld16(tcol + 128u, ra);
+      tmem_wait_ld();
+      tmem_ld16(tcol + 192u, rb);
+      pin<16>(ra);
+      {
+        const uint32_t off = (uint32_t)(16 + 2 * g) * 2048u + rowoff;
+        epi_cols<16, RELU, DOTS, WRITE_A, PREC, 0>(ra, b, inv, sbase + SM_A_HI + off, lo_addr(off), headw + 128 + 16 * g, d, mk, 0);
+        if (WRITE_A) a_ready(2);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) b[i] = b4[48 + i];
+      tmem_wait_ld();
+      pin<16>(rb);
+      {
+        const uint32_t off = (uint32_t)(24 + 2 * g) * 2048u + rowoff;
+        epi_cols<16, RELU, DOTS, WRITE_A, PREC, 0>(rb, b, inv, sbase + SM_A_HI + off, lo_addr(off), headw + 192 + 16 * g, d, mk, 0);
+        if (WRITE_A) a_ready(3);
+      }
+    };
+
     // One tile: p = this thread's point (clamped), ray = its ray; pe_next() is called while layer 6 runs (the PE buffer is free
     // then) to encode the following tile; emit(...) receives this thread's per-point results (g == 0 threads hold them).
     auto tile_body = [&](const long long p_raw, const bool valid, const long long p, const long long ray, auto&& pe_next,
@@ -771,10 +957,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
 #pragma unroll 1
       for (int s = 0; s < 8; ++s) {
         const float* bias = c_epi + ET_BIAS + 256 * s;
-        if (NORMALS) {
+        if constexpr (NORMALS) {
           if (s < 7) layer_epilogue(TagTrunkM{}, s, bias, d, masks[s]);
           else if (!P.io.sigma_only) layer_epilogue(TagLastM{}, s, bias, d, masks[s]);
           else layer_epilogue(TagSigmaM{}, s, bias, d, masks[s]);
+        } else if constexpr (SPLIT) {
+          if (s < 7) layer_epilogue_split(TagTrunk{}, s, bias, d);
+          else if (!P.io.sigma_only) layer_epilogue_split(TagLast{}, s, bias, d);
+          else layer_epilogue_split(TagSigma{}, s, bias, d);
         } else {
           if (s < 7) layer_epilogue(TagTrunk{}, s, bias, d, masks[0]);
           else if (!P.io.sigma_only) layer_epilogue(TagLast{}, s, bias, d, masks[0]);
@@ -823,7 +1013,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
           if (g == 0) o_mirror = sigmoidf_(dm[0] + c_epi[ET_B_M2]);
         }
         // ---- final linear (step 8): f = W h8 + b, written over h8 (its readers, steps 9 and 8, are complete) ----
-        layer_epilogue(TagFinal{}, 8, c_epi + ET_BIAS + 256 * 8, d, masks[0]);
+        if constexpr (SPLIT) layer_epilogue_split(TagFinal{}, 8, c_epi + ET_BIAS + 256 * 8, d);
+        else layer_epilogue(TagFinal{}, 8, c_epi + ET_BIAS + 256 * 8, d, masks[0]);
         // ---- dir layer (step 10): relu(W_f f + [b + W_d embed(dir)]) -> rgb (mirror_nerf.py:199-204) ----
         wait_acc(10);
         {
@@ -991,7 +1182,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
       if (g == 0) {
         const int r0 = grab(), r1 = grab();
         if (lane == 0) { f_ray[q] = r0; f_chunk[q] = 0; f_ray[4 + q] = r1; f_chunk[4 + q] = 0; }
-        if (warp == 4 && lane == 0) *f_stop = 0;
+        if (warp == EPI_WARP0 && lane == 0) *f_stop = 0;
       }
       epi_bar_sync<512>(1);
       auto slot_alive = [&](int sl) { return (f_ray[4 * sl] >= 0) || (f_ray[4 * sl + 1] >= 0) || (f_ray[4 * sl + 2] >= 0) || (f_ray[4 * sl + 3] >= 0); };
@@ -1007,7 +1198,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
 #pragma unroll
           for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(__ldg(rr + c), __fmul_rn(__ldg(rr + 3 + c), z));
           pe_point(x);
-        } else if (warp == 4 && lane == 0) {
+        } else if (warp == EPI_WARP0 && lane == 0) {
           *f_stop = 1;
         }
         fence_async_smem();
@@ -1091,7 +1282,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
             }
           }
         });
-        if (warp == 4 && lane == 0 && P.stats != nullptr) atomicAdd(P.stats, 1ull);
+        if (warp == EPI_WARP0 && lane == 0 && P.stats != nullptr) atomicAdd(P.stats, 1ull);
         epi_bar_sync<512>(1);   // every quarter's next work item of slot `cur` is published
         const bool alive_this = slot_alive(cur);
         if (pe_done) {           // the other slot's tile is already encoded and released: it runs next
@@ -1126,9 +1317,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
 
 }  // namespace
 
+static int g_tc_split = -1;                 // -1: not decided yet (environment / built-in default at the first launch)
+constexpr int TC_SPLIT_DEFAULT = 0;
 static unsigned long long* g_trace_buf = nullptr;
 static unsigned int g_trace_cap = 0;
 void set_tc_trace(unsigned long long* buf, unsigned int cap) { g_trace_buf = buf; g_trace_cap = cap; }
+int set_tc_split(int split) {
+  if (split < 0) {
+    const char* e = getenv("MNRF_TC_SPLIT");
+    split = e != nullptr ? (atoi(e) != 0) : TC_SPLIT_DEFAULT;
+  }
+  g_tc_split = split != 0 ? 1 : 0;
+  return g_tc_split;
+}
 
 // ---- constant-memory slots of the epilogue table (per device) -------------------------------------------------------------
 // A slot is keyed by the field's pack stamp (unique per pack_field call, so a re-packed or re-created field never hits a stale
@@ -1203,6 +1404,8 @@ int launch_field_tc(const mnrf_field* f, const FieldIO& io, int precision, cudaS
     MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_tc<3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
     MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_tc<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
     MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_tc<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
+    MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_tc<2, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
+    MNRF_CUDA_OK(cudaFuncSetAttribute(k_field_tc<2, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
   }
   TcParams P;
   const F32Layout& L = f->L;
@@ -1225,6 +1428,8 @@ int launch_field_tc(const mnrf_field* f, const FieldIO& io, int precision, cudaS
   {
     static const int dbg = getenv("MNRF_TC_DEBUG") != nullptr ? atoi(getenv("MNRF_TC_DEBUG")) : 0;
     P.debug = dbg;   // bit 0: timing experiment, a quarter of the weight bytes per stage (results are garbage)
+    P.split = set_tc_split(g_tc_split);   // N-split schedule of the tc2 kernels (issue_split_step)
+    P.tc_split = f->tc8 + TC_TOTAL_BYTES;
   }
   P.n_tiles = (io.n_points + TILE_M - 1) / TILE_M;
   const int grid = P.n_tiles < num_sms ? P.n_tiles : num_sms;
@@ -1240,12 +1445,17 @@ int launch_field_tc(const mnrf_field* f, const FieldIO& io, int precision, cudaS
     // ray tiles: 4 rays x 32 samples, work handed out dynamically; at most one CTA per SM, no more CTAs than ray quartets
     const int quartets = (P.n_rays + 3) / 4;
     const int fgrid = quartets < num_sms ? quartets : num_sms;
-    if (precision == 2) { P.tc = f->tc8; k_field_tc<2, false, true><<<fgrid, NUM_THREADS, SM_TOTAL, st>>>(P); }
+    if (precision == 2) {
+      P.tc = f->tc8;
+      if (P.split) k_field_tc<2, false, true, true><<<fgrid, NUM_THREADS, SM_TOTAL, st>>>(P);
+      else k_field_tc<2, false, true><<<fgrid, NUM_THREADS, SM_TOTAL, st>>>(P);
+    }
     else if (precision == 3) k_field_tc<3, false, true><<<fgrid, NUM_THREADS, SM_TOTAL, st>>>(P);
     else k_field_tc<1, false, true><<<fgrid, NUM_THREADS, SM_TOTAL, st>>>(P);
   } else if (precision == 2) {
     P.tc = f->tc8;
-    k_field_tc<2, false><<<grid, NUM_THREADS, SM_TOTAL, st>>>(P);
+    if (P.split) k_field_tc<2, false, false, true><<<grid, NUM_THREADS, SM_TOTAL, st>>>(P);
+    else k_field_tc<2, false><<<grid, NUM_THREADS, SM_TOTAL, st>>>(P);
   } else if (precision == 3) {
     if (normals) k_field_tc<3, true><<<grid, NUM_THREADS, SM_TOTAL, st>>>(P);
     else         k_field_tc<3, false><<<grid, NUM_THREADS, SM_TOTAL, st>>>(P);

@@ -174,8 +174,20 @@ __global__ void k_pack_tc8(TcSrc src, const float* __restrict__ inv_scale, uint8
     uint8_t* chunk = base + (size_t)kc * 2 * blob;
     *reinterpret_cast<__half*>(chunk + (kk >> 3) * (N * 16) + (n >> 3) * 128 + (n & 7) * 16 + (kk & 7) * 2) = hi;
     const int off8 = (kk >> 4) * (N * 16) + (n >> 3) * 128 + (n & 7) * 16 + (kk & 15);
-    chunk[blob + off8] = (uint8_t)__nv_cvt_float_to_fp8(__half2float(hi) * 0.0009765625f, __NV_SATFINITE, __NV_E4M3);
-    chunk[blob + blob / 2 + off8] = (uint8_t)__nv_cvt_float_to_fp8(lo, __NV_SATFINITE, __NV_E4M3);
+    const uint8_t hi8 = (uint8_t)__nv_cvt_float_to_fp8(__half2float(hi) * 0.0009765625f, __NV_SATFINITE, __NV_E4M3);
+    const uint8_t lo8 = (uint8_t)__nv_cvt_float_to_fp8(lo, __NV_SATFINITE, __NV_E4M3);
+    chunk[blob + off8] = hi8;
+    chunk[blob + blob / 2 + off8] = lo8;
+    if (s <= TC_SPLIT_LAST) {
+      // second copy for the N-split schedule of field_tc.cu: the 256 output rows as two 128-row halves, half-major, each
+      // (half, K32 chunk) one 16 KB stage in the N = 128 blob format [fp16 hi 8 KB | e4m3(2^-10 hi) 4 KB | e4m3(lo) 4 KB]
+      const int h = n >> 7, n2 = n & 127, nch = K >> 5;
+      uint8_t* c2 = tc8 + TC_TOTAL_BYTES + tc_step_offset(s) + (size_t)(h * nch + kc) * 16384;
+      *reinterpret_cast<__half*>(c2 + (kk >> 3) * 2048 + (n2 >> 3) * 128 + (n2 & 7) * 16 + (kk & 7) * 2) = hi;
+      const int o8 = (kk >> 4) * 2048 + (n2 >> 3) * 128 + (n2 & 7) * 16 + (kk & 15);
+      c2[8192 + o8] = hi8;
+      c2[8192 + 4096 + o8] = lo8;
+    }
   }
 }
 

@@ -30,16 +30,17 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU box
+// bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU box.  The report is one shared out-of-line
+// function, so that every inlined wait stays a handful of instructions.
+static __device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
+  printf("mnrf: mbarrier timeout (block %d thread %d bar@%u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("mnrf train_tc: mbarrier timeout (block %d thread %d bar@%u parity %u)\n", blockIdx.x, threadIdx.x, bar,
-             parity);
-      __trap();
-    }
+    if (clock64() - t0 > 4000000000LL) mbar_timeout(bar, parity);
   }
 }
 // Spinning wait for the two single-thread roles (weight producer, MMA issuer): mbarrier.test_wait never suspends the thread, so
@@ -61,10 +62,7 @@ __device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
   if (mbar_test(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_test(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("mnrf: mbarrier timeout (block %d thread %d bar@%u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-      __trap();
-    }
+    if (clock64() - t0 > 4000000000LL) mbar_timeout(bar, parity);
   }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -162,6 +160,32 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint32_t a_lo32, uint3
       ::"r"(d_tmem), "r"(a_lo32), "r"(b_lo32), "r"(accumulate), "r"(a_hi32), "r"(idesc), "r"(b_hi32)
       : "memory");
 }
+// ---- packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2): two IEEE fp32 operations per issued instruction, bit-identical to the
+// scalar forms.  The conversion epilogues are bound by instruction issue (four warps per scheduler plus the single-thread
+// roles), not by the FMA pipe, so halving the fp32 instruction count is worth the 64-bit register pairs.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_sub(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
 // x = hi + lo with hi, lo representable in tf32 (10-bit mantissa, fp32 exponent range): no scaling needed
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));

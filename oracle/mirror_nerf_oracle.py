@@ -290,7 +290,7 @@ def render_rays(params, rays, N_samples=64, use_disp=False, perturb=0, noise_std
     """One render level (R/models/rendering.py:54-369).
 
     params: {"coarse": {key: tensor}, "fine": {...}?}.   rng: optional dict with explicit draws
-    {"perturb_u","noise_coarse","u_pdf","noise_fine"}; otherwise torch's global RNG is used in the
+    {"perturb_u","noise_coarse","u_pdf","noise_fine"} (+ the test hook "z_fine", see fine_z); otherwise torch's global RNG is used in the
     reference's call order so that a shared torch.manual_seed gives identical draws.
     """
     rng = rng or {}
@@ -342,6 +342,11 @@ def render_rays(params, rays, N_samples=64, use_disp=False, perturb=0, noise_std
     run_pass(results, params["coarse"], "coarse", o3 + d3 * z.unsqueeze(-1), z, rng.get("noise_coarse"))
 
     def fine_z(z_c):
+        if rng.get("z_fine") is not None:
+            # test hook: the merged, sorted fine depths of the implementation under test.  The reference detaches sample_pdf's
+            # output (R/models/rendering.py:346-349), so no gradient depends on how these depths were obtained; gradient tests of
+            # encodings whose Jacobian jumps at cell faces (hash grid) inject them so that both sides evaluate identical positions.
+            return rng["z_fine"].to(z_c)
         mid = 0.5 * (z_c[:, :-1] + z_c[:, 1:])
         z_new = sample_pdf(mid, results["weights_coarse"][:, 1:-1].detach(), N_importance,
                            det=(perturb == 0), u=rng.get("u_pdf"))

@@ -140,9 +140,12 @@ HASH_TRAIN_VARIANTS = {
 @pytest.mark.parametrize("variant", list(HASH_TRAIN_VARIANTS))
 def test_hash_train_gradients_vs_oracle(variant):
     """R/train.py:129-145 with --model_type nerf_tcnn: test_time=False, perturb=1, noise_std=1.  Forward outputs and the
-    gradients of every parameter tensor (hash table included) against torch autograd over the oracle restatement.  Tolerances:
-    per-tensor cosine >= 0.9998 and norm within 5e-3 (fp32 on both sides; the fine depths differ in the last bits, which moves
-    single samples across cell faces of the finest grid levels, where the trilinear Jacobian jumps)."""
+    gradients of every parameter tensor (hash table included) against torch autograd over the oracle restatement.
+    Forward: an independent oracle run.  Gradients: a second oracle run at the implementation's fine depths (oracle hook
+    rng["z_fine"]; the reference detaches them, R/models/rendering.py:346-349) -- independently sampled depths differ in the last
+    bits, which moves a few of the 2,368 samples across cell faces of the fine grid levels where the trilinear Jacobian jumps
+    (~2e-4 crossings per sample, axis and level: per-tensor cosine 0.9995..0.99994 depending on the level table's last bits),
+    a property of the encoding, not of either implementation."""
     from mirror_nerf_b200.rendering import render_rays
     from mirror_nerf_b200.synthetic import random_rays
     from oracle import mirror_nerf_oracle as O
@@ -158,14 +161,19 @@ def test_hash_train_gradients_vs_oracle(variant):
     if v.get("gt_mask"):
         kw["mirror_mask"] = (torch.arange(n) % 2).float()
     params = {t: {k: x.clone().requires_grad_(True) for k, x in sd.items()} for t, sd in sds.items()}
-    want = O.render_rays(params, rays, *args, rng=rng, n_freqs_xyz=0, n_freqs_dir=0, **kw)
-    _loss(want, rays[:, 3:6], 1).backward()
+    with torch.no_grad():
+        want = O.render_rays(sds, rays, *args, rng=rng, n_freqs_xyz=0, n_freqs_dir=0, **kw)
     models, emb = _train_models(sds)
     kw_gpu = dict(kw)
     if "mirror_mask" in kw_gpu:
         kw_gpu["mirror_mask"] = kw_gpu["mirror_mask"].cuda()
     got = render_rays(models, emb, rays.cuda(), *args, rng=rng, **kw_gpu)
     _loss(got, rays[:, 3:6].cuda(), 1).backward()
+    rng_g = dict(rng)
+    if "z_vals_fine" in got:
+        rng_g["z_fine"] = got["z_vals_fine"].detach().cpu()
+    want_g = O.render_rays(params, rays, *args, rng=rng_g, n_freqs_xyz=0, n_freqs_dir=0, **kw)
+    _loss(want_g, rays[:, 3:6], 1).backward()
     assert set(got) == set(want), sorted(set(got) ^ set(want))
     for k in sorted(got):
         assert tuple(got[k].shape) == tuple(want[k].shape), k
@@ -173,7 +181,8 @@ def test_hash_train_gradients_vs_oracle(variant):
         assert s["median"] <= 1e-4 and s["frac"] <= (0.13 if "normal" in k else 0.05), fmt_stats(k, s)
     if args[4] == 0:
         params = {"coarse": params["coarse"]}
-    _grad_compare(models, params, 0.9998, 5e-3, whole_cos_min=0.9999)  # measured: worst tensor 0.99994, whole 0.99998, norm 1.0012
+    # measured at identical depths: every tensor and the whole vector 1.000000 (6 digits), norm ratio 1.000000
+    _grad_compare(models, params, 0.99999, 1e-4, whole_cos_min=0.99999)
 
 
 @pytest.mark.parametrize("compute_normal", [True, False])
@@ -190,19 +199,20 @@ def test_hash_train_ray_gradients(compute_normal):
     rays = random_rays(n, seed=10, near=0.05, far=2.0)
     rng = _rng(n, args[0], args[4])
     kw = dict(test_time=False, compute_normal=compute_normal)
-    rc = rays.clone().requires_grad_(True)
-    want = O.render_rays(sds, rc, *args, rng=rng, n_freqs_xyz=0, n_freqs_dir=0, **kw)
-    _loss(want, rays[:, 3:6], 2).backward()
     models, emb = _train_models(sds)
     for m in models.values():
         m.requires_grad_(False)
     rg = rays.cuda().requires_grad_(True)
     got = render_rays(models, emb, rg, *args, rng=rng, **kw)
     _loss(got, rays[:, 3:6].cuda(), 2).backward()
+    # the oracle at the implementation's (detached) fine depths: see test_hash_train_gradients_vs_oracle
+    rc = rays.clone().requires_grad_(True)
+    want = O.render_rays(sds, rc, *args, rng=dict(rng, z_fine=got["z_vals_fine"].detach().cpu()), n_freqs_xyz=0, n_freqs_dir=0, **kw)
+    _loss(want, rays[:, 3:6], 2).backward()
     a, b = rg.grad[:, :6].double().cpu().flatten(), rc.grad[:, :6].double().flatten()
     cos = float((a * b).sum() / (a.norm() * b.norm()))
     print(f"hash-grid ray gradient: cos {cos:.6f}, norm ratio {float(a.norm() / b.norm()):.6f}")
-    assert cos >= 0.9999 and abs(float(a.norm() / b.norm()) - 1) <= 2e-3, (cos, float(a.norm()), float(b.norm()))  # measured 0.999999 / 1.8e-4
+    assert cos >= 0.99999 and abs(float(a.norm() / b.norm()) - 1) <= 1e-4, (cos, float(a.norm()), float(b.norm()))  # measured 1.000000 / 1.000000
     assert float(rg.grad[:, 6:].abs().max()) == 0.0
 
 

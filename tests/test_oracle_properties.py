@@ -68,3 +68,24 @@ def test_composite_weights_form_a_sub_partition_of_unity(seed, white_back, S):
     dense_last = sig[:, -1] > 0
     assert torch.allclose(res["opacity_fine"][dense_last], torch.ones(int(dense_last.sum())), atol=1e-4)
     assert bool((res["rgb_fine"] >= -1e-6).all()) and bool((res["rgb_fine"] <= 1 + 1e-4).all())
+
+
+def test_z_fine_hook_reproduces_the_sampled_run():
+    """rng["z_fine"] (the gradient tests' hook: evaluate the oracle at the fine depths of the implementation under test) changes
+    nothing when it is fed the oracle's own depths, and the depths carry no gradient (R/models/rendering.py:346-349 detaches)."""
+    import torch
+    from oracle import mirror_nerf_oracle as O
+    from mirror_nerf_b200.synthetic import random_rays, scene_state_dicts
+    sds = scene_state_dicts()
+    rays = random_rays(5, seed=3)
+    g = torch.Generator().manual_seed(1)
+    rng = {"perturb_u": torch.rand(5, 16, generator=g), "noise_coarse": torch.randn(5, 16, generator=g),
+           "u_pdf": torch.rand(5, 24, generator=g), "noise_fine": torch.randn(5, 40, generator=g)}
+    args = (16, False, 1.0, 1.0, 24, 32768, False)
+    with torch.no_grad():
+        a = O.render_rays(sds, rays, *args, rng=rng, test_time=False)
+        b = O.render_rays(sds, rays, *args, rng=dict(rng, z_fine=a["z_vals_fine"]), test_time=False)
+    assert set(a) == set(b)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    assert not a["z_vals_fine"].requires_grad

@@ -42,10 +42,12 @@ class Policy:
     def __init__(self, params, table):
         """table: {layer name: policy}"""
         self.by_id = {}
+        self.tag_of = {}
         for tag, sd in params.items():
             for k, v in sd.items():
                 if k.endswith(".weight"):
                     self.by_id[id(v)] = k[: -len(".weight")]
+                    self.tag_of[id(v)] = tag
         self.table = table
         self.cache = {}
 
@@ -62,7 +64,7 @@ class Policy:
 
     def linear(self, x, w, b=None):
         name = self.by_id.get(id(w))
-        pol = self.table.get(name, 0)
+        pol = self.table.get((self.tag_of.get(id(w)), name), self.table.get(name, 0))   # per-model entry wins
         if pol == 0:
             return torch.nn.functional.linear(x, w, b)
         k_tc = 256 if name == "dir_encoding.0" else w.shape[1]   # the 27 direction inputs are a per-ray fp32 term
@@ -105,9 +107,12 @@ TRUNK = [f"xyz_encoding_{i}.0" for i in range(1, 9)]
 HEADS = ["xyz_encoding_final", "dir_encoding.0", "is_mirror_net.0"]
 
 
-def table(trunk, heads):
+def table(trunk, heads, coarse=None):
+    """coarse: policy of every layer of the coarse model (its sigma only feeds sample_pdf at test time), None = like the fine one"""
     t = {k: trunk for k in TRUNK}
     t.update({k: heads for k in HEADS})
+    if coarse is not None:
+        t.update({("coarse", k): coarse for k in TRUNK + HEADS})
     return t
 
 
@@ -137,7 +142,8 @@ def main():
     with torch.no_grad():
         want = O.trace_eval(fn, rays, 1)
     cases = {"tc3": table(3, 3), "tc1": table(1, 1), "fp8c": table(8, 8), "fp8c+heads1": table(8, 1), "tc3+heads1": table(3, 1),
-             "2a": table("2a", "2a"), "2w": table("2w", "2w")}
+             "2a": table("2a", "2a"), "2w": table("2w", "2w"),
+             "coarse1+fine8": table(8, 8, coarse=1), "coarse1+fine3": table(3, 3, coarse=1)}
     for name, tab in cases.items():
         O.F = FShim(Policy(sds, tab))
         try:

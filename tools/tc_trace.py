@@ -44,7 +44,7 @@ ev.sort()
 print("events", len(ev))
 # the trace holds the coarse launch then the fine launch: split at the largest time gap, keep the fine one
 fine = ev
-names = {1: "mma_begin", 2: "mma_A_ready", 3: "mma_last_chunk", 5: "TILE wait PE cycles", 6: "TILE wait A cycles",
+names = {1: "mma_begin", 2: "mma_A_ready", 3: "mma_last_chunk", 4: "mma_stage_issue", 5: "TILE wait PE cycles", 6: "TILE wait A cycles",
          7: "TILE wait W cycles", 20: "epi_first_ld_landed", 21: "epi_piece0_stored", 22: "epi_piece_stored", 10: "epi_acc_ready", 11: "epi_chunk_written", 12: "pe_begin", 13: "pe_end", 14: "tile_epilogue_done"}
 # per-tile totals of the MMA issuer's blocked cycles (payload in the upper 32 bits of the tag)
 tot = {5: [], 6: [], 7: []}
