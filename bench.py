@@ -52,12 +52,17 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz, self._stop_evt = index, [], set(), None, threading.Event()
+        self.power, self.power_limit = [], None
         try:
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            try:
+                self.power_limit = pynvml.nvmlDeviceGetEnforcedPowerLimit(self.h) / 1000.0
+            except Exception:
+                self.power_limit = None
         except Exception:
             self.nv = None
 
@@ -73,6 +78,10 @@ class ClockSampler(threading.Thread):
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 try:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                except Exception:
+                    pass
+                try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
                     r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -86,9 +95,11 @@ class ClockSampler(threading.Thread):
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=2)
-        s = sorted(self.samples)
+        s, pw = sorted(self.samples), sorted(self.power)
+        # board power under load against the enforced limit: with sw_power_cap active the SM clock is whatever the power budget
+        # allows, i.e. throughput follows energy per ray, not cycles per ray
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+                "samples": len(s), "power_w": (pw[len(pw) // 2] if pw else None), "power_limit_w": self.power_limit}
 
 
 def cpu_reference_rate(n_rays, steps, warmup, threads):

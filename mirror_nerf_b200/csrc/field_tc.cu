@@ -2,20 +2,22 @@
 //   o + d*z  ->  positional encoding  ->  8x256 trunk (skip at layer 5)  ->  sigma / folded normal head
 //   ->  mirror head  ->  final 256x256  ->  dir layer (+ per-ray dir term)  ->  rgb      -> 8 floats/point.
 //
-// One persistent CTA per SM, 12 warps:
-//   warp 0        weight producer: cp.async.bulk (TMA 1-D) of pre-packed B-operand blobs, 16 KB mbarrier-ring stages
-//   warp 1        MMA issuer: ONE elected thread runs the whole role and issues tcgen05.mma
-//                 (M=128, N=256 | 128, K=16, fp16 operands in shared memory, fp32 accumulators in TMEM)
-//   warps 4..11   epilogue/PE: TMEM -> registers (tcgen05.ld) -> bias/ReLU -> fp16 hi/lo split -> next layer's
-//                 A operand written in place into shared memory in the UMMA K-major core-matrix layout.
+// One persistent CTA per SM, 20 warps:
+//   warps 0..15   epilogue/PE (TMEM lane quarter = warp % 4, column group = warp / 4): TMEM -> registers (tcgen05.ld) ->
+//                 bias/ReLU -> operand split -> next layer's A operand written in place into shared memory in the UMMA K-major
+//                 core-matrix layout; heads, positional encoding of the next tile, and (fused mode) compositing
+//   warp 16       weight producer: cp.async.bulk (TMA 1-D) of pre-packed B-operand blobs, 16 KB mbarrier-ring stages
+//   warp 17       MMA issuer: ONE elected thread runs the whole role and issues tcgen05.mma
+//                 (M=128, N=256 | 128, K=16 | 32, fp16 / e4m3 operands in shared memory, fp32 accumulators in TMEM)
 //
 // Pipelining.  Measured on B200 (tools/mma_bench*.cu, profiles/): the tensor pipe needs 128 cycles per M128xN256xK16 and 64
-// per N128; a single issuing thread with an mbarrier wait + commit per weight stage sustains one MMA per ~90-110 cycles.
-// So the 256-wide layers are issued as N=256 instructions (issue cost hidden behind 128 cycles of work), one accumulator
-// barrier per layer, two 256-column TMEM accumulators alternating by layer.  The epilogue of layer l starts when its
-// accumulator is complete (every reader of the in-place activations is done by then), walks the four 64-column K chunks in
-// order with all 8 warps on each chunk (32 columns per warp) and signals a per-chunk mbarrier, so layer l+1's MMAs start
-// after a quarter of the epilogue and then run back to back:  period = T_mma + T_epi/4 + handshake.
+// per N128; the 256-wide layers are issued as N=256 instructions, one accumulator barrier per layer, two 256-column TMEM
+// accumulators alternating by layer.  The epilogue of layer l starts when its accumulator is complete (every reader of the
+// in-place activations is done by then) and signals per-chunk mbarriers, so layer l+1's MMAs start after the first chunk.
+// An optional N-split schedule (issue_split_step) issues every 256-wide layer as two 128-column halves so that the first
+// half's epilogue overlaps the second half's MMAs.  Measured neutral (profiles/r02_v5_*): while the sixteen epilogue warps
+// convert they saturate all four schedulers, and the two single-thread roles that share those schedulers then get an issue
+// slot every ~45 cycles (device timeline) -- tensor pipe and epilogue time add up whichever way they are ordered.
 //
 // Precision: operands are split x = hi + lo in fp16 (weights pre-scaled by 2^s per layer) and
 // each product is formed as hi*hi + lo*hi + hi*lo with fp32 accumulation ("3x" mode, fp32-grade);
@@ -39,16 +41,19 @@ using namespace tcx;
 
 constexpr int TILE_M = 128;
 constexpr int NUM_THREADS = 640;
-// warp 0: weight producer; warp 1: MMA issuer; warps 4..19: epilogue/PE (TMEM lane quarter = warp % 4, column group = (warp-4)/4).
-#ifdef MNRF_TC_ROLES_HIGH
-// experiment: the two single-thread roles on the highest warp ids (the warp arbiter favours them, tools/mma_bench4.cu)
-constexpr int EPI_WARP0 = 0;
-constexpr int WARP_PRODUCER = 16;
-constexpr int WARP_MMA = 17;
-#else
+// warps 0..15: epilogue/PE (TMEM lane quarter = warp % 4, column group = warp / 4); warp 16: weight producer; warp 17: MMA issuer.
+// The two single-thread roles sit on the HIGHEST warp ids of their schedulers: they share the issue slots with four epilogue
+// warps each, and under that contention the arbiter serves higher warp ids first (tools/mma_bench4.cu: an ALU-saturated
+// scheduler slows the issuer 2.1x with the roles on warps 0/1 and 1.5x on warps 16/17; on the bench +0.6..1.1 %).
+// MNRF_TC_ROLES_LOW restores the old placement for A/B measurements.
+#ifdef MNRF_TC_ROLES_LOW
 constexpr int EPI_WARP0 = 4;
 constexpr int WARP_PRODUCER = 0;
 constexpr int WARP_MMA = 1;
+#else
+constexpr int EPI_WARP0 = 0;
+constexpr int WARP_PRODUCER = 16;
+constexpr int WARP_MMA = 17;
 #endif
 constexpr uint32_t WSTAGE_BYTES = 16384;
 

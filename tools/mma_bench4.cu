@@ -36,6 +36,16 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) { while (!mbar_test(bar, parity)) {} }
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0,1,0,p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// wm = 0: poll with test_wait (never suspends); 1: try_wait (the hardware may park the warp until the phase flips)
+__device__ __forceinline__ void mbar_w(uint32_t bar, uint32_t parity, int wm) {
+  if (wm) { while (!mbar_try(bar, parity)) {} } else { while (!mbar_test(bar, parity)) {} }
+}
 __device__ __forceinline__ void commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -88,7 +98,7 @@ __device__ __forceinline__ void issue_stage(uint32_t d, uint32_t ah, uint32_t a8
 // busy: warps 4..19 (four per scheduler, like the kernel's epilogue warps) run an ALU loop with 4 independent chains
 template <int N, int SB, int NST, int STYLE, int PROD>
 __global__ void __launch_bounds__(640, 1) k(int chunks, const uint8_t* __restrict__ wsrc, uint32_t wbytes, long long* out, int busy,
-                                            float* sink, int wp, int wi) {
+                                            float* sink, int wp, int wi, int wm, int ym) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint32_t tmem_slot;
   __shared__ int stop;
@@ -119,7 +129,7 @@ __global__ void __launch_bounds__(640, 1) k(int chunks, const uint8_t* __restric
     if (PROD && elect_one()) {
       uint32_t stage = 0, phase = 0, off = (blockIdx.x * 65536u) % wbytes;
       for (int s = 0; s < total_stages; ++s) {
-        mbar_spin(empty0 + 8u * stage, phase ^ 1u);
+        mbar_w(empty0 + 8u * stage, phase ^ 1u, wm);
         const uint32_t fb = full0 + 8u * stage, dst = sbase + SM_WST + stage * SB;
         expect_tx(fb, SB);
 #pragma unroll
@@ -142,7 +152,7 @@ __global__ void __launch_bounds__(640, 1) k(int chunks, const uint8_t* __restric
           const uint32_t ah = dl_a_hi + ka * 512u, a8 = dl_a8 + ka * 256u, a8r = dl_a8r + ka * 256u;
           const uint32_t d = tmem + (N == 128 ? (uint32_t)((c >> 3) & 1) * 128u : 0u);
           for (int r = 0; r < SPC; ++r) {
-            if (PROD) mbar_spin(full0 + 8u * stage, phase);
+            if (PROD) mbar_w(full0 + 8u * stage, phase, wm);
             fence_after();
             issue_stage<N, SB>(d, ah, a8, a8r, sbase + SM_WST + stage * SB, r, (c & 7) != 0 || r != 0);
             commit(empty0 + 8u * stage);
@@ -172,7 +182,7 @@ __global__ void __launch_bounds__(640, 1) k(int chunks, const uint8_t* __restric
             for (int r = 0; r < SPC; ++r) {
               constexpr int dummy = 0; (void)dummy;
               const int stage = cc * SPC + r;   // compile-time after unrolling
-              if (PROD) mbar_spin(full0 + 8u * stage, phase);
+              if (PROD) mbar_w(full0 + 8u * stage, phase, wm);
               fence_after();
               if (STYLE == 3) {
                 if (lead3) {
@@ -209,6 +219,8 @@ __global__ void __launch_bounds__(640, 1) k(int chunks, const uint8_t* __restric
     while (!*vs) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) { a0 = fmaf(a0, 1.0001f, 0.5f); a1 = fmaf(a1, 0.9999f, 0.25f); a2 = fmaf(a2, 1.0002f, 0.125f); a3 = fmaf(a3, 0.9998f, 1.f); }
+      if (ym == 1) __nanosleep(0);
+      else if (ym == 2) asm volatile("bar.warp.sync 0xffffffff;" ::: "memory");
     }
     if (a0 + a1 + a2 + a3 == 12345.f) sink[threadIdx.x] = a0;
   }
@@ -222,7 +234,7 @@ static float* g_sink = nullptr;
 constexpr uint32_t WBYTES = 4u << 20;
 
 template <int N, int SB, int NST, int STYLE, int PROD>
-void run(int busy = 0, int wp = 0, int wi = 1) {
+void run(int busy = 0, int wp = 0, int wi = 1, int wm = 0, int ym = 0) {
   int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   long long* d;
@@ -231,8 +243,8 @@ void run(int busy = 0, int wp = 0, int wi = 1) {
   auto kern = k<N, SB, NST, STYLE, PROD>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
   const int chunks = 8 * 400;   // multiple of every ring trip
-  kern<<<sms, 640, SM_TOTAL>>>(64, g_w, WBYTES, d, busy, g_sink, wp, wi);
-  kern<<<sms, 640, SM_TOTAL>>>(chunks, g_w, WBYTES, d, busy, g_sink, wp, wi);
+  kern<<<sms, 640, SM_TOTAL>>>(64, g_w, WBYTES, d, busy, g_sink, wp, wi, wm, ym);
+  kern<<<sms, 640, SM_TOTAL>>>(chunks, g_w, WBYTES, d, busy, g_sink, wp, wi, wm, ym);
   cudaError_t e = cudaDeviceSynchronize();
   long long h[256];
   cudaMemcpy(h, d, sizeof(long long) * sms, cudaMemcpyDeviceToHost);
@@ -240,8 +252,8 @@ void run(int busy = 0, int wp = 0, int wi = 1) {
   for (int i = 0; i < sms; ++i) { avg += h[i]; if (h[i] > mx) mx = h[i]; }
   avg /= sms;
   const double ideal = N == 256 ? 512.0 : 256.0;
-  printf("N=%3d stage=%5d B x %d  style=%d producer=%d busy=%d roles=warp %d,%d : %7.1f cycles per K32 chunk (max SM %7.1f), ideal %3.0f -> %.2fx   [%s]\n", N, SB, NST,
-         STYLE, PROD, busy, wp, wi, avg / chunks, mx / chunks, ideal, avg / chunks / ideal, cudaGetErrorString(e));
+  printf("N=%3d stage=%5d B x %d  style=%d producer=%d busy=%d roles=warp %d,%d wait=%s yield=%d : %7.1f cycles per K32 chunk (max SM %7.1f), ideal %3.0f -> %.2fx   [%s]\n", N, SB, NST,
+         STYLE, PROD, busy, wp, wi, wm ? "try" : "test", ym, avg / chunks, mx / chunks, ideal, avg / chunks / ideal, cudaGetErrorString(e));
   cudaFree(d);
 }
 
@@ -249,17 +261,15 @@ int main() {
   cudaMalloc(&g_w, WBYTES);
   cudaMemset(g_w, 0, WBYTES);
   cudaMalloc(&g_sink, 4096);
-  // roles on the lowest warp ids (0, 1: the kernel today) against the highest (16/17: same schedulers, 18/19: the other two)
-  const int roles[3][2] = {{0, 1}, {16, 17}, {18, 19}};
-  for (int r = 0; r < 3; ++r) {
-    for (int busy = 0; busy < 2; ++busy) {
-      run<256, 16384, 4, 0, 1>(busy, roles[r][0], roles[r][1]);
-      run<256, 16384, 4, 1, 1>(busy, roles[r][0], roles[r][1]);
-      run<128, 16384, 4, 0, 1>(busy, roles[r][0], roles[r][1]);
-      run<128, 16384, 4, 1, 1>(busy, roles[r][0], roles[r][1]);
+  // contention study: ALU-saturating warps (four per scheduler) against the producer / issuer pair
+  for (int wm = 0; wm < 2; ++wm)
+    for (int ym = 0; ym < 3; ++ym) {
+      run<256, 16384, 4, 0, 1>(1, 0, 1, wm, ym);
+      run<128, 16384, 4, 1, 1>(1, 0, 1, wm, ym);
+      run<256, 16384, 4, 0, 1>(1, 16, 17, wm, ym);
+      run<128, 16384, 4, 1, 1>(1, 16, 17, wm, ym);
     }
-    run<256, 16384, 4, 0, 0>(1, roles[r][0], roles[r][1]);
-    run<128, 16384, 4, 1, 0>(1, roles[r][0], roles[r][1]);
-  }
+  run<256, 16384, 4, 0, 1>(0, 0, 1, 1, 0);
+  run<128, 16384, 4, 1, 1>(0, 0, 1, 1, 0);
   return 0;
 }
