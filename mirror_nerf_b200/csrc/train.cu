@@ -1321,6 +1321,11 @@ int mnrf_train_pass_bwd(const mnrf_field* f, const float* rays, const float* z, 
 int mnrf_debug_gemm_bench(const mnrf_field* f, int kind, int step, int P, int engine, int dbg, int iters, float* ms_out) {
   MNRF_REQUIRE(f && ms_out && P > 0 && iters > 0 && f->kind == 0, "gemm_bench: bad argument");
   float *A = nullptr, *C = nullptr, *Wg = nullptr;
+  // zero bias of the widest layer: with a bias the NN launch takes the bias + ReLU epilogue flavour of the forward trunk
+  // (k_gemm_tc_nn<1>), which is what a training step runs; without one it would fall back to the generic run-time flavour
+  float* bias_z = nullptr;
+  MNRF_CUDA_OK(cudaMalloc(&bias_z, sizeof(float) * W));
+  MNRF_CUDA_OK(cudaMemset(bias_z, 0, sizeof(float) * W));
   MNRF_CUDA_OK(cudaMalloc(&A, sizeof(float) * (size_t)P * W));
   MNRF_CUDA_OK(cudaMalloc(&C, sizeof(float) * (size_t)P * W));
   MNRF_CUDA_OK(cudaMalloc(&Wg, sizeof(float) * W * W));
@@ -1339,6 +1344,7 @@ int mnrf_debug_gemm_bench(const mnrf_field* f, int kind, int step, int P, int en
     if (kind == 0) {
       GemmEpi e;
       e.act = 1;
+      e.bias = bias_z;
       const int K = t32_step_k(step);
       rc = gemm_w(f, step, A, W, K > W ? 64 : K, K > W ? A : nullptr, W, C, W, P, e, 0);
     } else {
@@ -1354,7 +1360,7 @@ int mnrf_debug_gemm_bench(const mnrf_field* f, int kind, int step, int P, int en
   set_train_tc_debug(0);
   g_engine = saved;
   set_train_tc_one_pass(saved == 2);
-  cudaFree(A); cudaFree(C); cudaFree(Wg);
+  cudaFree(A); cudaFree(C); cudaFree(Wg); cudaFree(bias_z);
   if (err != cudaSuccess) { set_error("gemm_bench: %s", cudaGetErrorString(err)); return 1; }
   return rc;
 }
