@@ -9,7 +9,6 @@ import math
 import os
 import sys
 
-import numpy as np
 import pytest
 import torch
 

@@ -1,5 +1,5 @@
 """Top stall-sample instructions of the (single) kernel in an .ncu-rep, with mbarrier wait loops grouped."""
-import csv, subprocess, sys, re
+import csv, subprocess, sys
 rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
