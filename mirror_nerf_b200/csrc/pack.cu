@@ -13,32 +13,47 @@
 
 namespace mnrf {
 
-// ---- small generic kernels ---------------------------------------------------------------------
-__global__ void k_copy(const float* __restrict__ src, float* __restrict__ dst, int n) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = src[i];
-}
-
-// dst[k][n] = src[n][k]  (src is [N][K] row-major), rows k >= K (padding) are zero
-__global__ void k_transpose_pad(const float* __restrict__ src, float* __restrict__ dst, int N, int K, int Kpad) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= Kpad * N) return;
-  int k = i / N, n = i % N;
-  dst[i] = (k < K) ? src[n * K + k] : 0.f;
-}
-
-// dst[r][c] = c < cols ? src[r*ld + c0 + c] : 0   (dst is [rows][cols_pad]): aligned-row copies for the training GEMMs
-__global__ void k_copy_block_pad(const float* __restrict__ src, float* __restrict__ dst, int rows, int ld, int c0, int cols,
-                                 int cols_pad) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows * cols_pad) return;
-  int r = i / cols_pad, c = i % cols_pad;
-  dst[i] = (c < cols) ? src[(size_t)r * ld + c0 + c] : 0.f;
-}
-
-__global__ void k_fill(float* dst, float v, int n) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = v;
+// ---- one launch for all the plain copies of a pack ---------------------------------------------------------------
+// pack_field used to issue ~80 tiny launches per field (k_copy / k_transpose_pad / k_copy_block_pad / k_fill), i.e. ~160 per
+// training step (both fields are re-packed after every optimizer step).  They are described by a table in the kernel
+// parameters and executed by ONE grid-stride kernel: element i of the concatenated destination ranges -> (op, local index).
+enum { PK_COPY = 0, PK_TRANSPOSE = 1, PK_BLOCK = 2 };
+struct PackOp {
+  const float* src;   // nullptr: the destination range is zero-filled
+  int dst;            // offset into the fp32 section
+  int kind;
+  int p0, p1, p2, p3; // COPY: -; TRANSPOSE: N, K (dst is [Kpad][N]); BLOCK: ld, c0, cols, cols_pad
+  int end;            // exclusive prefix sum of destination elements up to and including this op
+};
+constexpr int PK_MAX_OPS = 72;
+struct PackOps {
+  PackOp op[PK_MAX_OPS];
+  int n;
+};
+__global__ void k_pack_ops(const __grid_constant__ PackOps T, float* __restrict__ f32) {
+  const int total = T.op[T.n - 1].end;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int lo = 0, hi = T.n - 1;   // first op whose range ends behind i
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (T.op[mid].end > i) hi = mid; else lo = mid + 1;
+    }
+    const PackOp& o = T.op[lo];
+    const int j = i - (lo > 0 ? T.op[lo - 1].end : 0);
+    float v = 0.f;
+    if (o.src != nullptr) {
+      if (o.kind == PK_COPY) {
+        v = o.src[j];
+      } else if (o.kind == PK_TRANSPOSE) {      // dst[k][n] = src[n][k], rows k >= K are padding
+        const int k = j / o.p0, n = j - k * o.p0;
+        v = k < o.p1 ? o.src[n * o.p1 + k] : 0.f;
+      } else {                                  // dst[r][c] = c < cols ? src[r*ld + c0 + c] : 0
+        const int r = j / o.p3, c = j - r * o.p3;
+        v = c < o.p2 ? o.src[(size_t)r * o.p0 + o.p1 + c] : 0.f;
+      }
+    }
+    f32[o.dst + j] = v;
+  }
 }
 
 // normal_net has no activation between its two Linears (mirror_nerf.py:85-88), so
@@ -225,73 +240,57 @@ __global__ void k_pack_t32(T32Src src, uint8_t* __restrict__ t32) {
   }
 }
 
-static int copy_to(const float* src, float* dst, int n, cudaStream_t st) {
-  if (src == nullptr) {
-    k_fill<<<(n + 255) / 256, 256, 0, st>>>(dst, 0.f, n);
-  } else {
-    k_copy<<<(n + 255) / 256, 256, 0, st>>>(src, dst, n);
-  }
-  MNRF_LAUNCH_OK();
-  return 0;
-}
-
-static int block_to(const float* src, float* dst, int rows, int ld, int c0, int cols, int cols_pad, cudaStream_t st) {
-  const int n = rows * cols_pad;
-  if (src == nullptr) {
-    k_fill<<<(n + 255) / 256, 256, 0, st>>>(dst, 0.f, n);
-  } else {
-    k_copy_block_pad<<<(n + 255) / 256, 256, 0, st>>>(src, dst, rows, ld, c0, cols, cols_pad);
-  }
-  MNRF_LAUNCH_OK();
-  return 0;
-}
-
-static int transpose_to(const float* src, float* dst, int N, int K, cudaStream_t st) {
-  int Kp = pad4(K);
-  if (src == nullptr) {
-    k_fill<<<(Kp * N + 255) / 256, 256, 0, st>>>(dst, 0.f, Kp * N);
-  } else {
-    k_transpose_pad<<<(Kp * N + 255) / 256, 256, 0, st>>>(src, dst, N, K, Kp);
-  }
-  MNRF_LAUNCH_OK();
-  return 0;
-}
-
 int pack_field(mnrf_field* f, const float* const* t, cudaStream_t st) {
   static std::atomic<unsigned long long> g_pack_stamp{0};
   f->pack_stamp = ++g_pack_stamp;  // invalidates the constant-memory copies of the epilogue table (field_tc.cu)
   const F32Layout& L = f->L;
   float* d = f->f32;
+  PackOps ops;
+  ops.n = 0;
+  int total = 0;
+  auto add = [&](const float* src, int dst, int kind, int n, int p0, int p1, int p2, int p3) {
+    PackOp& o = ops.op[ops.n++];
+    o.src = src; o.dst = dst; o.kind = kind; o.p0 = p0; o.p1 = p1; o.p2 = p2; o.p3 = p3;
+    total += n;
+    o.end = total;
+  };
+  auto copy_to = [&](const float* src, int dst, int n) { add(src, dst, PK_COPY, n, 0, 0, 0, 0); };
+  auto transpose_to = [&](const float* src, int dst, int N, int K) { add(src, dst, PK_TRANSPOSE, pad4(K) * N, N, K, 0, 0); };
+  auto block_to = [&](const float* src, int dst, int rows, int ld, int c0, int cols, int cols_pad) {
+    add(src, dst, PK_BLOCK, rows * cols_pad, ld, c0, cols, cols_pad);
+  };
   for (int l = 0; l < 8; ++l) {
-    if (transpose_to(t[2 * l], d + L.wt_trunk[l], W, trunk_k(l), st)) return 1;
-    if (copy_to(t[2 * l], d + L.w_trunk[l], W * trunk_k(l), st)) return 1;
-    if (copy_to(t[2 * l + 1], d + L.b_trunk[l], W, st)) return 1;
+    transpose_to(t[2 * l], L.wt_trunk[l], W, trunk_k(l));
+    copy_to(t[2 * l], L.w_trunk[l], W * trunk_k(l));
+    copy_to(t[2 * l + 1], L.b_trunk[l], W);
   }
-  if (transpose_to(t[T_FINAL_W], d + L.wt_final, W, W, st)) return 1;
-  if (copy_to(t[T_FINAL_B], d + L.b_final, W, st)) return 1;
-  if (transpose_to(t[T_DIR_W], d + L.wt_dir, WH, W + IN_DIR, st)) return 1;
-  if (copy_to(t[T_DIR_B], d + L.b_dir, WH, st)) return 1;
-  if (copy_to(t[T_SIGMA_W], d + L.w_sigma, W, st)) return 1;
-  if (copy_to(t[T_SIGMA_B], d + L.b_sigma, 1, st)) return 1;
-  if (copy_to(t[T_RGB_W], d + L.w_rgb, 3 * WH, st)) return 1;
-  if (copy_to(t[T_RGB_B], d + L.b_rgb, 3, st)) return 1;
-  if (transpose_to(t[T_N0_W], d + L.wt_n0, WH, W, st)) return 1;
-  if (copy_to(t[T_N0_B], d + L.b_n0, WH, st)) return 1;
-  if (copy_to(t[T_N1_W], d + L.w_n1, 3 * WH, st)) return 1;
-  if (copy_to(t[T_N1_B], d + L.b_n1, 3, st)) return 1;
-  if (transpose_to(t[T_M0_W], d + L.wt_m0, WH, W, st)) return 1;
-  if (copy_to(t[T_M0_B], d + L.b_m0, WH, st)) return 1;
-  if (copy_to(t[T_M2_W], d + L.w_m2, WH, st)) return 1;
-  if (copy_to(t[T_M2_B], d + L.b_m2, 1, st)) return 1;
-
+  transpose_to(t[T_FINAL_W], L.wt_final, W, W);
+  copy_to(t[T_FINAL_B], L.b_final, W);
+  transpose_to(t[T_DIR_W], L.wt_dir, WH, W + IN_DIR);
+  copy_to(t[T_DIR_B], L.b_dir, WH);
+  copy_to(t[T_SIGMA_W], L.w_sigma, W);
+  copy_to(t[T_SIGMA_B], L.b_sigma, 1);
+  copy_to(t[T_RGB_W], L.w_rgb, 3 * WH);
+  copy_to(t[T_RGB_B], L.b_rgb, 3);
+  transpose_to(t[T_N0_W], L.wt_n0, WH, W);
+  copy_to(t[T_N0_B], L.b_n0, WH);
+  copy_to(t[T_N1_W], L.w_n1, 3 * WH);
+  copy_to(t[T_N1_B], L.b_n1, 3);
+  transpose_to(t[T_M0_W], L.wt_m0, WH, W);
+  copy_to(t[T_M0_B], L.b_m0, WH);
+  copy_to(t[T_M2_W], L.w_m2, WH);
+  copy_to(t[T_M2_B], L.b_m2, 1);
   // aligned [out][in] copies for the training path (train.cu)
-  if (block_to(t[0], d + L.tw_l1, W, IN_XYZ, 0, IN_XYZ, PE_PAD, st)) return 1;
-  if (block_to(t[8], d + L.tw_l5a, W, IN_XYZ + W, 0, IN_XYZ, PE_PAD, st)) return 1;
-  if (block_to(t[8], d + L.tw_l5b, W, IN_XYZ + W, IN_XYZ, W, W, st)) return 1;
-  if (block_to(t[T_FINAL_W], d + L.tw_final, W, W, 0, W, W, st)) return 1;
-  if (block_to(t[T_DIR_W], d + L.tw_dira, WH, W + IN_DIR, 0, W, W, st)) return 1;
-  if (block_to(t[T_N0_W], d + L.tw_n0, WH, W, 0, W, W, st)) return 1;
-  if (block_to(t[T_M0_W], d + L.tw_m0, WH, W, 0, W, W, st)) return 1;
+  block_to(t[0], L.tw_l1, W, IN_XYZ, 0, IN_XYZ, PE_PAD);
+  block_to(t[8], L.tw_l5a, W, IN_XYZ + W, 0, IN_XYZ, PE_PAD);
+  block_to(t[8], L.tw_l5b, W, IN_XYZ + W, IN_XYZ, W, W);
+  block_to(t[T_FINAL_W], L.tw_final, W, W, 0, W, W);
+  block_to(t[T_DIR_W], L.tw_dira, WH, W + IN_DIR, 0, W, W);
+  block_to(t[T_N0_W], L.tw_n0, WH, W, 0, W, W);
+  block_to(t[T_M0_W], L.tw_m0, WH, W, 0, W, W);
+  MNRF_REQUIRE(ops.n <= PK_MAX_OPS, "pack_field: op table overflow (%d)", ops.n);
+  k_pack_ops<<<(total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184, 256, 0, st>>>(ops, d);
+  MNRF_LAUNCH_OK();
 
   k_fold_heads<<<1, 256, 0, st>>>(t[T_SIGMA_W], t[T_SIGMA_B], t[T_N0_W], t[T_N0_B], t[T_N1_W], t[T_N1_B],
                                   reinterpret_cast<float4*>(d + L.headw), d + L.headb);
