@@ -222,7 +222,7 @@ __device__ __forceinline__ void issue_split_step(const SplitCtx& c, uint32_t d_b
       }
       mbar_spin(bar(BAR_W_FULL + st), phase);
       tc_fence_after();
-      tr(i);   // trace builds: this stage's operands are in place, its MMAs are issued now
+      tr(4, i);   // trace builds: this stage's operands are in place, its MMAs are issued now
       const uint32_t wb = c.wdesc0 + (uint32_t)st * 1024u;
       const uint32_t d = d_base + 128u * (uint32_t)h;
       tc_mma<128>(d, ah, wb, kc > 0 ? 1u : 0u);
@@ -236,6 +236,54 @@ __device__ __forceinline__ void issue_split_step(const SplitCtx& c, uint32_t d_b
     }
     phase ^= 1u;
   }
+}
+
+// ---- one 256-wide layer of the unsplit tc2 schedule, fully unrolled -------------------------------------------------------
+// Same MMAs in the same order as the generic issue loop of the kernel (per K32 chunk: stage [W_hi fp16] -> two f16 K16 MMAs,
+// stage [e4m3(2^-10 W_hi) | e4m3(W_lo)] -> two f8 K32 MMAs), but chunk index and ring position of every stage are compile-time
+// constants, so every descriptor is a base register plus an immediate: about half the instructions per stage.  That matters
+// where the issuer overlaps the epilogue of the previous layer: there it gets an issue slot only every few tens of cycles
+// (device timeline: 350-410 cycles per 256-cycle stage under the epilogue, 260 once the epilogue is done).
+template <int NCH, int NPE, bool WAIT_PE, class Tracer>
+__device__ __forceinline__ void issue_wide_step(const SplitCtx& c, uint32_t d, int acc_slot, bool a_reused, uint32_t& phase,
+                                                uint32_t& a_phase, uint32_t& pe_phase, Tracer&& tr) {
+  static_assert((2 * NCH) % 4 == 0, "a 256-wide tc2 step must consume whole trips of the 4-stage ring");
+  auto bar = [&](int i) { return c.bars + 8u * (uint32_t)i; };
+  if (WAIT_PE) { mbar_spin(bar(BAR_PE), pe_phase); pe_phase ^= 1u; }
+#pragma unroll
+  for (int t = 0; t < (2 * NCH) / 4; ++t) {   // one trip around the ring = two K32 chunks
+#pragma unroll
+    for (int st = 0; st < 4; ++st) {
+      const int i = 4 * t + st, kc = i >> 1, half = i & 1;
+      uint32_t ah, a8, a8r;
+      if (kc < NPE) {
+        ah = c.dl_pe_hi + (uint32_t)kc * 512u; a8 = c.dl_pe8 + (uint32_t)kc * 256u; a8r = c.dl_pe8r + (uint32_t)kc * 256u;
+      } else {
+        const int ka = kc - NPE;
+        if (half == 0 && ((ka & 1) == 0 || ka == 1) && !a_reused) {   // first touch of freshly written activation columns
+          const int cb = ka == 1 ? 4 : (ka >> 1);
+          mbar_spin(bar(BAR_A + cb), (a_phase >> cb) & 1u);
+          a_phase ^= 1u << cb;
+          tr(2, cb);
+        }
+        ah = c.dl_a_hi + (uint32_t)ka * 512u; a8 = c.dl_a8 + (uint32_t)ka * 256u; a8r = c.dl_a8r + (uint32_t)ka * 256u;
+      }
+      mbar_spin(bar(BAR_W_FULL + st), phase);
+      tc_fence_after();
+      // descriptor low word of stage st with the N = 256 leading-byte offset (4096): wdesc0 carries LBO 2048 in bits 16+
+      const uint32_t wb = c.wdesc0 + (uint32_t)st * 1024u + (128u << 16);
+      if (half == 0) {
+        tc_mma<256>(d, ah, wb, kc > 0 ? 1u : 0u);        // A_hi * W_hi  (k 0..15)
+        tc_mma<256>(d, ah + 256u, wb + 512u, 1u);        // (k 16..31)
+      } else {
+        tc_mma_f8<256>(d, a8r, wb, 1u);                  // (2^10 A_lo) * (2^-10 W_hi)
+        tc_mma_f8<256>(d, a8, wb + 512u, 1u);            // A_hi * W_lo
+      }
+      tc_commit(bar(BAR_W_EMPTY + st));
+    }
+    phase ^= 1u;
+  }
+  tc_commit(bar(BAR_ACC + acc_slot));
 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
@@ -615,10 +663,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
           trace_ev(P, trc, 0, 1, 1, s, 0);
           if constexpr (SPLIT) if (s <= TC_SPLIT_LAST) {
             // the ring is at position 0 here: every step of this mode consumes a multiple of 4 stages
-            auto tr = [&](int i) { trace_ev(P, trc, 0, 1, 4, s, i); };
+            auto tr = [&](int ev, int v) { trace_ev(P, trc, 0, 1, ev, s, v); };
             if (s == 0) issue_split_step<2, 2, !FUSE>(sc, d_tmem, acc_bar(s), a_reused, phase, a_phase, pe_phase, tr);
             else if (s == 4) issue_split_step<10, 2, false>(sc, d_tmem, acc_bar(s), a_reused, phase, a_phase, pe_phase, tr);
             else issue_split_step<8, 0, false>(sc, d_tmem, acc_bar(s), a_reused, phase, a_phase, pe_phase, tr);
+            trace_ev(P, trc, 0, 1, 3, s, 0);
+            continue;
+          }
+          if constexpr (PREC == 2 && !NORMALS && !SPLIT) if (s <= 8 && !(P.debug & 3)) {
+            // unsplit tc2 schedule of the 256-wide steps: the unrolled issue loop (the ring is at position 0 here)
+            auto tr = [&](int ev, int v) { trace_ev(P, trc, 0, 1, ev, s, v); };
+            if (s == 0) issue_wide_step<2, 2, !FUSE>(sc, d_tmem, acc_bar(s), a_reused, phase, a_phase, pe_phase, tr);
+            else if (s == 4) issue_wide_step<10, 2, false>(sc, d_tmem, acc_bar(s), a_reused, phase, a_phase, pe_phase, tr);
+            else issue_wide_step<8, 0, false>(sc, d_tmem, acc_bar(s), a_reused, phase, a_phase, pe_phase, tr);
             trace_ev(P, trc, 0, 1, 3, s, 0);
             continue;
           }
@@ -1432,7 +1489,8 @@ int launch_field_tc(const mnrf_field* f, const FieldIO& io, int precision, cudaS
   }
   {
     static const int dbg = getenv("MNRF_TC_DEBUG") != nullptr ? atoi(getenv("MNRF_TC_DEBUG")) : 0;
-    P.debug = dbg;   // bit 0: timing experiment, a quarter of the weight bytes per stage (results are garbage)
+    P.debug = dbg;   // bit 0: timing experiment, a quarter of the weight bytes per stage (results are garbage);
+                     // bit 1: the generic (run-time stage index) issue loop instead of the unrolled one of the tc2 kernels
     P.split = set_tc_split(g_tc_split);   // N-split schedule of the tc2 kernels (issue_split_step)
     P.tc_split = f->tc8 + TC_TOTAL_BYTES;
   }
