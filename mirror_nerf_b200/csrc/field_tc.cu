@@ -286,6 +286,39 @@ __device__ __forceinline__ void issue_wide_step(const SplitCtx& c, uint32_t d, i
   tc_commit(bar(BAR_ACC + acc_slot));
 }
 
+// ---- a 128-wide step (mirror head, dir layer) of the tc2 kernels, fully unrolled: K = 256 = 8 stages of
+// [W_hi fp16 8 KB | e4m3(2^-10 W_hi) 4 KB | e4m3(W_lo) 4 KB], four N = 128 MMAs each (64 pipe cycles apiece, so the issue
+// work per stage counts twice as much as in the 256-wide steps: the generic loop ran them at ~440 cycles per 256-cycle stage)
+template <class Tracer>
+__device__ __forceinline__ void issue_narrow_step(const SplitCtx& c, uint32_t d, int acc_slot, bool a_reused, uint32_t& phase,
+                                                  uint32_t& a_phase, Tracer&& tr) {
+  auto bar = [&](int i) { return c.bars + 8u * (uint32_t)i; };
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+#pragma unroll
+    for (int st = 0; st < 4; ++st) {
+      const int ka = 4 * t + st;
+      if (((ka & 1) == 0 || ka == 1) && !a_reused) {   // first touch of freshly written activation columns
+        const int cb = ka == 1 ? 4 : (ka >> 1);
+        mbar_spin(bar(BAR_A + cb), (a_phase >> cb) & 1u);
+        a_phase ^= 1u << cb;
+        tr(2, cb);
+      }
+      const uint32_t ah = c.dl_a_hi + (uint32_t)ka * 512u, a8 = c.dl_a8 + (uint32_t)ka * 256u, a8r = c.dl_a8r + (uint32_t)ka * 256u;
+      mbar_spin(bar(BAR_W_FULL + st), phase);
+      tc_fence_after();
+      const uint32_t wb = c.wdesc0 + (uint32_t)st * 1024u;
+      tc_mma<128>(d, ah, wb, ka > 0 ? 1u : 0u);
+      tc_mma<128>(d, ah + 256u, wb + 256u, 1u);
+      tc_mma_f8<128>(d, a8r, wb + 512u, 1u);
+      tc_mma_f8<128>(d, a8, wb + 768u, 1u);
+      tc_commit(bar(BAR_W_EMPTY + st));
+    }
+    phase ^= 1u;
+  }
+  tc_commit(bar(BAR_ACC + acc_slot));
+}
+
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
 // ---- x = hi + lo in fp16, two values per 32-bit word (element 0 in the low half) -----------------------------------
@@ -666,6 +699,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
             if (s == 0) issue_split_step<2, 2, !FUSE>(sc, d_tmem, acc_bar(s), a_reused, phase, a_phase, pe_phase, tr);
             else if (s == 4) issue_split_step<10, 2, false>(sc, d_tmem, acc_bar(s), a_reused, phase, a_phase, pe_phase, tr);
             else issue_split_step<8, 0, false>(sc, d_tmem, acc_bar(s), a_reused, phase, a_phase, pe_phase, tr);
+            trace_ev(P, trc, 0, 1, 3, s, 0);
+            continue;
+          }
+          if constexpr (PREC == 2 && !NORMALS) if ((s == 9 || s == 10) && !(P.debug & 3)) {
+            auto tr = [&](int ev, int v) { trace_ev(P, trc, 0, 1, ev, s, v); };
+            issue_narrow_step(sc, d_tmem, acc_bar(s), a_reused, phase, a_phase, tr);
             trace_ev(P, trc, 0, 1, 3, s, 0);
             continue;
           }
