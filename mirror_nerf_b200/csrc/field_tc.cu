@@ -623,6 +623,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
           const int nch = tc_step_chunks(s);
           // N = 64 steps (4 KB blobs): 3x -> [hi|lo] of two K32 chunks per stage (contiguous); 1x -> hi of four chunks
           const int nst = sn == 64 ? (TWO_BLOBS ? nch / 2 : nch / 4) : (TWO_BLOBS ? (wide ? 2 * nch : nch) : (wide ? nch : nch / 2));
+          if constexpr (PREC == 2 && !NORMALS) {
+            // tc2 forward steps: every stage is 16 contiguous KB and every step takes a multiple of 4 stages, so the ring
+            // position is unrolled (constant stage / barrier addresses): like the issuer, this thread shares its scheduler with
+            // four epilogue warps and its reaction time is part of every stage's round trip
+            for (int t = 0; t < nst / 4; ++t) {
+#pragma unroll
+              for (int st = 0; st < 4; ++st) {
+                mbar_spin(bar(BAR_W_EMPTY + st), phase ^ 1u);
+                const uint32_t fb = bar(BAR_W_FULL + st);
+                mbar_expect_tx(fb, WSTAGE_BYTES);
+                bulk_g2s(sbase + SM_WST + (uint32_t)st * WSTAGE_BYTES, src, WSTAGE_BYTES, fb);
+                src += WSTAGE_BYTES;
+              }
+              phase ^= 1u;
+            }
+            continue;
+          }
           for (int si = 0; si < nst; ++si) {
             mbar_spin(bar(BAR_W_EMPTY + stage), phase ^ 1u);
             const uint32_t dst = stage_addr(stage);
