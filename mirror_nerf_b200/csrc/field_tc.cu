@@ -623,10 +623,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_field_tc(const TcParams P) {
           const int nch = tc_step_chunks(s);
           // N = 64 steps (4 KB blobs): 3x -> [hi|lo] of two K32 chunks per stage (contiguous); 1x -> hi of four chunks
           const int nst = sn == 64 ? (TWO_BLOBS ? nch / 2 : nch / 4) : (TWO_BLOBS ? (wide ? 2 * nch : nch) : (wide ? nch : nch / 2));
-          if constexpr (PREC == 2 && !NORMALS) {
-            // tc2 forward steps: every stage is 16 contiguous KB and every step takes a multiple of 4 stages, so the ring
-            // position is unrolled (constant stage / barrier addresses): like the issuer, this thread shares its scheduler with
-            // four epilogue warps and its reaction time is part of every stage's round trip
+          if constexpr (TWO_BLOBS) {
+            // tc3 / tc2: every stage is 16 contiguous KB and every step takes a multiple of 4 stages (4, 8, 16 or 20), so the
+            // ring position is unrolled (constant stage / barrier addresses): like the issuer, this thread shares its scheduler
+            // with four epilogue warps and its reaction time is part of every stage's round trip.  The generic issue loops
+            // walk the same ring in the same order.
+            if (nst & 3) { printf("mnrf field_tc: step %d takes %d weight stages\n", s, nst); __trap(); }
             for (int t = 0; t < nst / 4; ++t) {
 #pragma unroll
               for (int st = 0; st < 4; ++st) {
