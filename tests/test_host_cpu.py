@@ -212,3 +212,25 @@ def test_bench_reference_arm_prints_one_contract_line():
         r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "0"], capture_output=True,
                            text=True, timeout=300)
         assert r.returncode != 0 and not r.stdout.strip(), "ours must fail loudly without a GPU, not fall back to the CPU"
+
+
+def test_traffic_record_is_reproducible_from_the_committed_launch_list(tmp_path):
+    """bench.py reports `roofline.traffic` from profiles/r02_field_tc_traffic.json; that record must be what
+    tools/ncu_launch_summary.py derives from the committed ncu launch list of the bench command (no hand-edited constant)."""
+    import gzip
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csv_path = tmp_path / "launches.csv"
+    with gzip.open(os.path.join(root, "profiles", "r02_v5_bench_launches.csv.gz"), "rb") as f:
+        csv_path.write_bytes(f.read())
+    out_txt, out_json = tmp_path / "summary.txt", tmp_path / "traffic.json"
+    subprocess.run([sys.executable, os.path.join(root, "tools", "ncu_launch_summary.py"), str(csv_path), str(out_txt), str(out_json)],
+                   check=True, capture_output=True)
+    got = json.loads(out_json.read_text())
+    want = json.load(open(os.path.join(root, "profiles", "r02_field_tc_traffic.json")))
+    for k in ("launches", "rays_per_launch", "dram_bytes_per_launch_avg", "dram_bytes_per_ray"):
+        assert got[k] == want[k], (k, got[k], want[k])
+    # the fused fine pass moves ~1.4 KB per ray through DRAM (the unfused sequence of round 1: 17.6 KB)
+    assert 1000 < want["dram_bytes_per_ray"] < 2000
